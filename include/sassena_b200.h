@@ -1,0 +1,154 @@
+/*
+ * sassena_b200.h — C-ABI of the B200-native Sassena scattering hot path (libsassena_b200.so).
+ *
+ * This is the drop-in boundary: everything a Sassena scatter device does between "coordinates are
+ * staged" and "atfinal_/afinal_/a2final_ are ready for write()" (reference:
+ * src/scatter_devices/abstract_scatter_device.cpp:105-175,239-244).  Plain pointers and sizes only;
+ * no exceptions cross the boundary — every call returns 0 on success and a non-zero SGPU_E* code on
+ * failure, with the message available from sgpu_last_error().  There is NO CPU fallback: without a
+ * CUDA device (sm_100a) sgpu_init fails.
+ *
+ * Conventions
+ *   coor_t = float (reference include/common.hpp:37-40), all signal math in FP64.
+ *   complex values are interleaved (re, im) doubles, as fftw_complex.
+ *   One sgpu_ctx drives one GPU; one process (rank) per GPU.
+ */
+#ifndef SASSENA_B200_H
+#define SASSENA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgpu_ctx sgpu_ctx;
+
+/* error codes */
+#define SGPU_OK 0
+#define SGPU_EINVAL 1   /* bad argument (the reference's Err::write + throw paths) */
+#define SGPU_ECUDA 2    /* CUDA runtime failure */
+#define SGPU_ESTATE 3   /* call order violated (e.g. compute before stage) */
+#define SGPU_ENOMEM 4   /* device or pinned allocation failed (reference: ram_check / terminate_request) */
+
+/* scattering.dsp.type / scattering.dsp.method (reference: src/control/parameters.cpp:502-511,
+ * dispatch in all_vectors_scatter_device.cpp:209-229) */
+#define SGPU_DSP_AUTOCORRELATE 0
+#define SGPU_DSP_SQUARE 1
+#define SGPU_DSP_PLAIN 2
+#define SGPU_METHOD_FFTW 0   /* smath::auto_correlate_fftw, src/math/smath.cpp:141-156 */
+#define SGPU_METHOD_DIRECT 1 /* smath::auto_correlate_direct, smath.cpp:51-76 (= conj of the fftw form) */
+
+/* coordinate representation of staged frames (reference: CoordinateSets::set_representation,
+ * multipole_scatter_device.cpp:53; conversion coordinate_set.cpp:303-315) */
+#define SGPU_REPR_CARTESIAN 0
+#define SGPU_REPR_SPHERICAL 1 /* (r, phi, theta) per atom */
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Create a context on CUDA device `device`.  Fails (SGPU_ECUDA) if no sm_100 device is present. */
+int sgpu_init(int device, sgpu_ctx **out);
+void sgpu_destroy(sgpu_ctx *ctx);
+/* Message of the last failing call on ctx (ctx may be NULL: message of the last failed sgpu_init). */
+const char *sgpu_last_error(const sgpu_ctx *ctx);
+/* Library version string, and the count of kernels this context has launched so far. */
+const char *sgpu_version(void);
+uint64_t sgpu_launch_count(const sgpu_ctx *ctx);
+/* Block until all work queued by ctx is done. */
+int sgpu_synchronize(sgpu_ctx *ctx);
+
+/* Pinned host memory for the stager (cudaHostAlloc / cudaFreeHost). */
+int sgpu_host_alloc(void **ptr, size_t bytes);
+int sgpu_host_free(void *ptr);
+
+/* ---- staging: replaces DataStagerByFrame / DataStagerByAtom ------------------------------------ */
+
+/* DataStagerByFrame::stage (src/stager/data_stager.cpp:72-129): xyz is host float [NF][NA][3]
+ * (frame-major, the layout all_vectors_scatter_device.cpp:420 / multipole...:473 index).
+ * The copy is asynchronous and chunked by frames; compute calls wait per chunk, so staging overlaps
+ * the first compute.  xyz must stay valid until sgpu_synchronize() or the first compute returns.
+ * Pinned memory (sgpu_host_alloc) gives true overlap; pageable memory works but copies serially. */
+int sgpu_stage_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, int repr);
+/* Same, but adopts coordinates already resident in device memory (no copy; caller keeps ownership). */
+int sgpu_stage_frames_device(sgpu_ctx *ctx, const float *d_xyz, size_t NF, size_t NA, int repr);
+/* Device-side cartesian -> spherical conversion of the staged frames (coor3d.cpp:168-215 +
+ * float narrowing data_stager.cpp:111-113); used when an MPSphere device is fed cartesian input. */
+int sgpu_frames_to_spherical(sgpu_ctx *ctx);
+
+/* DataStagerByAtom::stage (data_stager.cpp:214-349): xyz is host float [NA_local][NF][3]
+ * (atom-major, self_vectors_scatter_device.cpp:303). */
+int sgpu_stage_atoms(sgpu_ctx *ctx, const float *xyz, size_t NA_local, size_t NF);
+int sgpu_stage_atoms_device(sgpu_ctx *ctx, const float *d_xyz, size_t NA_local, size_t NF);
+/* Frame-major host input [NF][NA][3] -> atom-major device layout for the atoms this rank owns under
+ * ModAssignment(nranks, rank, NA) (assignment.cpp:82-118); the transpose runs on the GPU. */
+int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t nranks,
+                                 size_t rank);
+
+/* ScatterFactors::get_all() for the current |q| (src/scatter_devices/scatter_factors.cpp:56-78,100):
+ * b has one entry per staged atom (NA for frames, NA_local for atoms, in staged order). */
+int sgpu_set_factors(sgpu_ctx *ctx, const double *b, size_t n);
+
+/* ---- compute(): one |q| ------------------------------------------------------------------------ */
+/* All three fill atfinal[NF][2], afinal[2], a2final[2] exactly as the reference leaves atfinal_,
+ * afinal_, a2final_ on partition rank 0 at the end of compute(): summed over the NM subvectors /
+ * moments (and atoms for self) and scaled by 1/NM (vectors) or 1/(4 pi) (multipole sphere). */
+
+/* AllVectorsScatterDevice::compute (all_vectors_scatter_device.cpp:238-361).  qvecs[NM][3] are the
+ * subvectors produced by init_subvectors() (abstract_vectors_scatter_device.cpp:112-175). */
+int sgpu_compute_all_vectors(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, int dsp_method,
+                             double *atfinal, double afinal[2], double a2final[2]);
+
+/* SelfVectorsScatterDevice::compute (self_vectors_scatter_device.cpp:145-239). */
+int sgpu_compute_self_vectors(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, int dsp_method,
+                              double *atfinal, double afinal[2], double a2final[2]);
+
+/* MPSphereScatterDevice::compute (multipole_scatter_device.cpp:278-401), moments lm[NM][2]=(l,m)
+ * (parameters.cpp:1037-1075); requires frames staged with SGPU_REPR_SPHERICAL.
+ * Returns SGPU_EINVAL if |m|>l for any moment (multipole_scatter_device.cpp:459-465). */
+int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type, int dsp_method,
+                          double *atfinal, double afinal[2], double a2final[2]);
+
+/* ---- multi-GPU: partial sums + finalize --------------------------------------------------------- */
+/* The reference reduces atfinal_/afinal_/a2final_ over the partition with three boost::mpi::reduce
+ * calls (all_vectors_scatter_device.cpp:335-343, self...:213-221, multipole...:375-383).  Here every
+ * rank computes an UNSCALED packed partial into device memory, the caller sums the packed buffers
+ * over ranks (one NCCL all-reduce, f64 sum), and sgpu_finalize turns the sum into the outputs.
+ * sgpu_partial_len gives the packed length in doubles for the staged NF and the dsp type. */
+int sgpu_partial_len(sgpu_ctx *ctx, int dsp_type, size_t *n_doubles);
+int sgpu_compute_all_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t NM_local, int dsp_type,
+                                     double *d_partial);
+int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type,
+                                      double *d_partial);
+int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM_local, int dsp_type,
+                                  double *d_partial);
+/* scale = 1/NM_total (vectors) or 1/(4 pi) (multipole sphere). */
+int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_method, double scale,
+                  double *atfinal, double afinal[2], double a2final[2]);
+/* The CUDA stream (cudaStream_t) the partial/finalize work is queued on, for callers that order their
+ * own collective against it. */
+void *sgpu_stream(sgpu_ctx *ctx);
+
+/* ---- introspection used by tests and bench ------------------------------------------------------ */
+/* Raw amplitudes A[NM][NF][2] of the last all_vectors / mpsphere compute (pre-DSP), copied to host. */
+int sgpu_get_amplitudes(sgpu_ctx *ctx, double *A, size_t NM, size_t NF);
+/* Time of the amplitude kernel(s) of the last compute call, in ms (CUDA events on the compute stream). */
+int sgpu_last_amplitude_ms(sgpu_ctx *ctx, float *ms);
+/* Time of the DSP (correlation/reduction) kernels of the last compute call, in ms. */
+int sgpu_last_dsp_ms(sgpu_ctx *ctx, float *ms);
+/* Dependency-free DFMA microbenchmark over all SMs: measured FP64 peak in TFLOP/s (FMA = 2 flop). */
+int sgpu_measure_fp64_peak(sgpu_ctx *ctx, double *tflops);
+/* Fill device coordinates with the synthetic random-walk trajectory of tests/bench (counter-based
+ * RNG, see sassena_b200/synth.py for the CPU twin).  layout: 0 = [NF][NA][3], 1 = [NA][NF][3]. */
+int sgpu_synth_trajectory(sgpu_ctx *ctx, float *d_xyz, size_t NF, size_t NA, size_t atom0, size_t atom_stride,
+                          size_t NA_out, float box, float offset, float step_scale, uint64_t seed, int layout);
+/* Plain device allocation helpers for callers without their own allocator (the C++ host layer). */
+int sgpu_device_alloc(void **d_ptr, size_t bytes);
+int sgpu_device_free(void *d_ptr);
+int sgpu_memcpy_d2h(sgpu_ctx *ctx, void *dst, const void *d_src, size_t bytes);
+int sgpu_memcpy_h2d(sgpu_ctx *ctx, void *d_dst, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SASSENA_B200_H */

@@ -1,0 +1,316 @@
+"""ctypes binding of the CPU oracle (oracle/sassena_oracle.c) plus an independent numpy restatement.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs.  The product package (sassena_b200/) never imports this module.
+
+PARITY UNPINNED (see the header of sassena_oracle.c): the reference has no golden vectors and cannot be
+built here, so the C port is pinned by analytic known answers and by the numpy/scipy functions below.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+DSP_AUTOCORRELATE, DSP_SQUARE, DSP_PLAIN = 0, 1, 2
+METHOD_FFTW, METHOD_DIRECT = 0, 1
+
+_DSP = {"autocorrelate": 0, "square": 1, "plain": 2}
+_METHOD = {"fftw": 0, "direct": 1}
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc -O3 -DNDEBUG -fopenmp)."""
+    src = os.path.join(_HERE, "sassena_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_decomposition_penalty.restype = C.c_size_t
+        _lib.orc_scan_unfold.restype = C.c_size_t
+        _lib.orc_cylinder_raster_linear.restype = C.c_size_t
+        _lib.orc_moments_sphere.restype = C.c_size_t
+        _lib.orc_init_subvectors.restype = C.c_size_t
+        _lib.orc_sph_bessel.restype = C.c_double
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# decomposition
+# ---------------------------------------------------------------------------------------------
+def div_assignment(NN, rank, NAF):
+    o, s, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    lib().orc_div_assignment(C.c_size_t(NN), C.c_size_t(rank), C.c_size_t(NAF), C.byref(o), C.byref(s), C.byref(m))
+    return o.value, s.value, m.value
+
+
+def mod_assignment(NN, rank, NAF):
+    o, s, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    lib().orc_mod_assignment(C.c_size_t(NN), C.c_size_t(rank), C.c_size_t(NAF), C.byref(o), C.byref(s), C.byref(m))
+    return o.value, s.value, m.value
+
+
+def decomposition_plan(nn, nq, naf, elbytes, maxbytes, min_utilization=0.95):
+    p, ps, pen = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    rc = lib().orc_decomposition_plan(C.c_size_t(nn), C.c_size_t(nq), C.c_size_t(naf), C.c_size_t(elbytes),
+                                      C.c_size_t(maxbytes), C.c_double(min_utilization), C.byref(p), C.byref(ps),
+                                      C.byref(pen))
+    return rc, p.value, ps.value, pen.value
+
+
+# ---------------------------------------------------------------------------------------------
+# generators
+# ---------------------------------------------------------------------------------------------
+def scan_unfold(base, frm, to, points, exponent=1.0):
+    out = np.zeros((max(points, 1), 3))
+    n = lib().orc_scan_unfold(_p(_f64(base), C.c_double), C.c_double(frm), C.c_double(to), C.c_size_t(points),
+                              C.c_double(exponent), _p(out, C.c_double))
+    return out[:n]
+
+
+def qvectors_from_scans(scans):
+    """ScatteringVectorsParameters::create_from_scans (parameters.cpp:1125-1189): outer-product sum of <=3 scans.
+    scans: list of dicts(base, from, to, points, exponent)."""
+    if len(scans) > 3:
+        raise ValueError("More than 3 scan definitions are not supported.")
+    lists = [scan_unfold(s.get("base", (1, 0, 0)), s.get("from", 0.0), s.get("to", 1.0), s.get("points", 100),
+                         s.get("exponent", 1.0)) for s in scans]
+    if len(lists) == 1:
+        return lists[0].copy()
+    if len(lists) == 2:
+        return np.array([a + b for a in lists[0] for b in lists[1]])
+    return np.array([a + b + c for a in lists[0] for b in lists[1] for c in lists[2]])
+
+
+def mt19937_stream(seed, n):
+    out = np.zeros(n, dtype=np.uint32)
+    lib().orc_mt19937_stream(C.c_uint32(seed), C.c_size_t(n), _p(out, C.c_uint32))
+    return out
+
+
+def uniform_on_sphere(seed, dim, count):
+    out = np.zeros((count, 3))
+    lib().orc_uniform_on_sphere(C.c_uint32(seed), C.c_int(dim), C.c_size_t(count), _p(out, C.c_double))
+    return out
+
+
+def normalize_rows(v):
+    v = _f64(v).copy()
+    lib().orc_normalize_rows(_p(v, C.c_double), C.c_size_t(len(v)))
+    return v
+
+
+def cylinder_raster_linear(resolution):
+    n = lib().orc_cylinder_raster_linear(C.c_size_t(resolution), None)
+    out = np.zeros((n, 3))
+    lib().orc_cylinder_raster_linear(C.c_size_t(resolution), _p(out, C.c_double))
+    return out
+
+
+def moments_sphere(resolution):
+    n = lib().orc_moments_sphere(C.c_long(resolution), None)
+    out = np.zeros((n, 2), dtype=np.int64)
+    lib().orc_moments_sphere(C.c_long(resolution), _p(out, C.c_long))
+    return out
+
+
+def vector_base(axis):
+    out = np.zeros((3, 3))
+    lib().orc_vector_base(_p(_f64(axis), C.c_double), _p(out, C.c_double))
+    return out
+
+
+def init_subvectors(kind, q, orient=None, axis=(0, 0, 1)):
+    """kind: 'none' | 'sphere' | 'file' | 'cylinder'."""
+    t = {"none": 0, "sphere": 1, "file": 1, "cylinder": 2}[kind]
+    orient = np.zeros((0, 3)) if orient is None else _f64(orient)
+    out = np.zeros((max(len(orient), 1), 3))
+    n = lib().orc_init_subvectors(C.c_int(t), _p(_f64(q), C.c_double), _p(orient, C.c_double),
+                                  C.c_size_t(len(orient)), _p(_f64(axis), C.c_double), _p(out, C.c_double))
+    return out[:n]
+
+
+def cart_to_spherical(xyz):
+    xyz = _f32(xyz)
+    out = np.zeros_like(xyz)
+    lib().orc_cart_to_spherical(_p(xyz, C.c_float), C.c_size_t(xyz.size // 3), _p(out, C.c_float))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# math
+# ---------------------------------------------------------------------------------------------
+def fft(x, sign=-1):
+    a = np.ascontiguousarray(x, dtype=np.complex128).copy()
+    lib().orc_fft(_p(a.view(np.float64), C.c_double), C.c_size_t(a.size), C.c_int(sign))
+    return a
+
+
+def auto_correlate_fftw(x):
+    NF = len(x)
+    a = np.zeros(2 * NF, dtype=np.complex128)
+    a[:NF] = x
+    lib().orc_auto_correlate_fftw(_p(a.view(np.float64), C.c_double), C.c_size_t(NF))
+    return a[:NF].copy()
+
+
+def auto_correlate_direct(x):
+    a = np.ascontiguousarray(x, dtype=np.complex128).copy()
+    lib().orc_auto_correlate_direct(_p(a.view(np.float64), C.c_double), C.c_size_t(len(a)))
+    return a
+
+
+def sph_bessel(l, x):
+    return lib().orc_sph_bessel(C.c_long(l), C.c_double(x))
+
+
+def spherical_harmonic(n, m, theta, phi):
+    re, im = C.c_double(), C.c_double()
+    lib().orc_spherical_harmonic(C.c_long(n), C.c_long(m), C.c_double(theta), C.c_double(phi), C.byref(re),
+                                 C.byref(im))
+    return complex(re.value, im.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# compute() drivers
+# ---------------------------------------------------------------------------------------------
+def _res(atfinal, af, a2f):
+    return atfinal.view(np.complex128).reshape(-1), complex(af[0], af[1]), complex(a2f[0], a2f[1])
+
+
+def compute_all_vectors(coords, sfs, qvecs, dsp="autocorrelate", method="fftw", nthreads=1, return_amplitudes=False,
+                        framesplit=False):
+    """coords float32 [NF][NA][3]; sfs f64 [NA]; qvecs f64 [NM][3] (already expanded subvectors).
+    Returns (fqt[NF] complex, fq complex, fq2 complex[, A[NM][NF]])."""
+    coords = _f32(coords)
+    NF, NA, _ = coords.shape
+    sfs, qvecs = _f64(sfs), _f64(qvecs).reshape(-1, 3)
+    NM = len(qvecs)
+    atfinal = np.zeros(2 * NF)
+    af, a2f = np.zeros(2), np.zeros(2)
+    if framesplit:
+        rc = lib().orc_compute_all_vectors_framesplit(
+            _p(coords, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(sfs, C.c_double), _p(qvecs, C.c_double),
+            C.c_size_t(NM), C.c_int(_DSP[dsp]), C.c_int(_METHOD[method]), C.c_int(nthreads), _p(atfinal, C.c_double),
+            _p(af, C.c_double), _p(a2f, C.c_double))
+        if rc:
+            raise RuntimeError("oracle: DSP type/method not understood")
+        return _res(atfinal, af, a2f)
+    at_out = np.zeros((NM, NF), dtype=np.complex128) if return_amplitudes else None
+    rc = lib().orc_compute_all_vectors(
+        _p(coords, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(sfs, C.c_double), _p(qvecs, C.c_double),
+        C.c_size_t(NM), C.c_int(_DSP[dsp]), C.c_int(_METHOD[method]), C.c_int(nthreads), _p(atfinal, C.c_double),
+        _p(af, C.c_double), _p(a2f, C.c_double),
+        _p(at_out.view(np.float64), C.c_double) if return_amplitudes else None)
+    if rc:
+        raise RuntimeError("oracle: DSP type/method not understood")
+    r = _res(atfinal, af, a2f)
+    return r + (at_out,) if return_amplitudes else r
+
+
+def compute_self_vectors(coords_by_atom, sfs_local, qvecs, dsp="autocorrelate", method="fftw", nthreads=1):
+    """coords float32 [NA_local][NF][3]; sfs_local f64 [NA_local]."""
+    coords = _f32(coords_by_atom)
+    NA, NF, _ = coords.shape
+    sfs, qvecs = _f64(sfs_local), _f64(qvecs).reshape(-1, 3)
+    atfinal = np.zeros(2 * NF)
+    af, a2f = np.zeros(2), np.zeros(2)
+    rc = lib().orc_compute_self_vectors(
+        _p(coords, C.c_float), C.c_size_t(NA), C.c_size_t(NF), _p(sfs, C.c_double), _p(qvecs, C.c_double),
+        C.c_size_t(len(qvecs)), C.c_int(_DSP[dsp]), C.c_int(_METHOD[method]), C.c_int(nthreads),
+        _p(atfinal, C.c_double), _p(af, C.c_double), _p(a2f, C.c_double))
+    if rc:
+        raise RuntimeError("oracle: DSP type/method not understood")
+    return _res(atfinal, af, a2f)
+
+
+def compute_mpsphere(coords_sph, sfs, ql, moments, dsp="autocorrelate", method="fftw", nthreads=1,
+                     return_amplitudes=False):
+    """coords_sph float32 [NF][NA][3] holding (r, phi, theta); moments int [NM][2] (l, m)."""
+    coords = _f32(coords_sph)
+    NF, NA, _ = coords.shape
+    sfs = _f64(sfs)
+    mom = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+    NM = len(mom)
+    atfinal = np.zeros(2 * NF)
+    af, a2f = np.zeros(2), np.zeros(2)
+    at_out = np.zeros((NM, NF), dtype=np.complex128) if return_amplitudes else None
+    rc = lib().orc_compute_mpsphere(
+        _p(coords, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(sfs, C.c_double), C.c_double(ql),
+        _p(mom, C.c_long), C.c_size_t(NM), C.c_int(_DSP[dsp]), C.c_int(_METHOD[method]), C.c_int(nthreads),
+        _p(atfinal, C.c_double), _p(af, C.c_double), _p(a2f, C.c_double),
+        _p(at_out.view(np.float64), C.c_double) if return_amplitudes else None)
+    if rc == 2:
+        raise RuntimeError("oracle: Combination of Major and minor moment not allowed")
+    if rc:
+        raise RuntimeError("oracle: DSP type/method not understood")
+    r = _res(atfinal, af, a2f)
+    return r + (at_out,) if return_amplitudes else r
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# Independent numpy restatement (used to pin the C port; numpy.fft replaces FFTW3)
+# ---------------------------------------------------------------------------------------------
+def np_amplitudes_all(coords, sfs, qvecs):
+    """A[m][f] = sum_j b_j exp(i q_m . r_j(f))  (all_vectors_scatter_device.cpp:418-438), float64 math."""
+    c = np.asarray(coords, dtype=np.float32).astype(np.float64)
+    ph = np.einsum("fac,mc->mfa", c, _f64(qvecs))
+    return (np.cos(ph) * sfs).sum(-1) + 1j * (np.sin(ph) * sfs).sum(-1)
+
+
+def np_autocorrelate(a, method="fftw"):
+    """smath.cpp:141-156 with numpy.fft, or :51-76 as an explicit O(N^2) sum."""
+    NF = len(a)
+    if method == "fftw":
+        X = np.fft.fft(a, 2 * NF)
+        c = np.fft.ifft(np.abs(X) ** 2) * (2 * NF)
+        return c[:NF] / (2 * NF * (NF - np.arange(NF)))
+    out = np.zeros(NF, dtype=np.complex128)
+    for tau in range(NF):
+        out[tau] = np.sum(a[: NF - tau] * np.conj(a[tau:])) / (NF - tau)
+    return out
+
+
+def np_dsp_store(A, dsp="autocorrelate", method="fftw", norm=None):
+    """dsp()+store()+final scale for a stack of timelines A[M][NF] (all_vectors_scatter_device.cpp:209-236,355-360)."""
+    M, NF = A.shape
+    if dsp == "autocorrelate":
+        T = np.array([np_autocorrelate(a, method) for a in A])
+    elif dsp == "square":
+        T = (np.abs(A) ** 2).astype(np.complex128)
+    else:
+        T = A.astype(np.complex128)
+    a = T.mean(axis=1)
+    norm = (1.0 / M) if norm is None else norm
+    return T.sum(0) * norm, a.sum() * norm, (a * np.conj(a)).sum() * norm

@@ -1,0 +1,256 @@
+"""Thin Python mirror of the C-ABI (include/sassena_b200.h).  No compute happens here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import load_library
+
+DSP_AUTOCORRELATE, DSP_SQUARE, DSP_PLAIN = 0, 1, 2
+METHOD_FFTW, METHOD_DIRECT = 0, 1
+REPR_CARTESIAN, REPR_SPHERICAL = 0, 1
+
+_DSP = {"autocorrelate": 0, "square": 1, "plain": 2}
+_METHOD = {"fftw": 0, "direct": 1}
+
+
+class SgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sgpu error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def _dsp(v):
+    return _DSP[v] if isinstance(v, str) else int(v)
+
+
+def _method(v):
+    return _METHOD[v] if isinstance(v, str) else int(v)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (the stager's pinned buffers)."""
+
+    def __init__(self, lib, shape, dtype):
+        self._lib = lib
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        rc = lib.sgpu_host_alloc(C.byref(p), nbytes)
+        if rc:
+            raise SgpuError(rc, "sgpu_host_alloc failed")
+        self.ptr = p.value
+        buf = (C.c_char * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.sgpu_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ScatterContext:
+    """One GPU worth of the hot path: stage -> set_factors -> compute_* (one call per |q|)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.sgpu_init(int(device), C.byref(h))
+        if rc:
+            raise SgpuError(rc, self.lib.sgpu_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.NF = self.NA = 0
+        self._keep = None  # host array kept alive during async staging
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise SgpuError(rc, self.lib.sgpu_last_error(self.h).decode())
+
+    def synchronize(self):
+        self._ck(self.lib.sgpu_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.sgpu_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.sgpu_stream(self.h) or 0)
+
+    def pinned(self, shape, dtype=np.float32) -> PinnedArray:
+        return PinnedArray(self.lib, shape, dtype)
+
+    # -- staging
+    def stage_frames(self, xyz, repr=REPR_CARTESIAN):
+        """xyz: float32 [NF][NA][3] host array (numpy or PinnedArray.array)."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise SgpuError(1, "stage_frames expects [NF][NA][3]")
+        self._keep = a
+        self._ck(self.lib.sgpu_stage_frames(self.h, a.ctypes.data, a.shape[0], a.shape[1], int(repr)))
+        self.NF, self.NA = a.shape[0], a.shape[1]
+
+    def stage_frames_device(self, d_ptr: int, NF: int, NA: int, repr=REPR_CARTESIAN):
+        self._ck(self.lib.sgpu_stage_frames_device(self.h, C.c_void_p(d_ptr), NF, NA, int(repr)))
+        self.NF, self.NA = NF, NA
+
+    def frames_to_spherical(self):
+        self._ck(self.lib.sgpu_frames_to_spherical(self.h))
+
+    def stage_atoms(self, xyz_by_atom):
+        """xyz_by_atom: float32 [NA_local][NF][3]."""
+        a = np.ascontiguousarray(xyz_by_atom, dtype=np.float32)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise SgpuError(1, "stage_atoms expects [NA][NF][3]")
+        self._keep = a
+        self._ck(self.lib.sgpu_stage_atoms(self.h, a.ctypes.data, a.shape[0], a.shape[1]))
+        self.synchronize()
+        self.NA, self.NF = a.shape[0], a.shape[1]
+
+    def stage_atoms_device(self, d_ptr: int, NA_local: int, NF: int):
+        self._ck(self.lib.sgpu_stage_atoms_device(self.h, C.c_void_p(d_ptr), NA_local, NF))
+        self.NA, self.NF = NA_local, NF
+
+    def stage_atoms_from_frames(self, xyz, nranks=1, rank=0):
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        self._ck(self.lib.sgpu_stage_atoms_from_frames(self.h, a.ctypes.data, a.shape[0], a.shape[1], nranks, rank))
+        NA = a.shape[1]
+        self.NF = a.shape[0]
+        self.NA = NA // nranks + (1 if rank < NA % nranks else 0)
+
+    def set_factors(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        self._ck(self.lib.sgpu_set_factors(self.h, _dp(b), b.size))
+
+    # -- compute
+    def _outputs(self):
+        return np.zeros(2 * self.NF), np.zeros(2), np.zeros(2)
+
+    @staticmethod
+    def _pack(at, af, a2f):
+        return at.view(np.complex128).copy(), complex(af[0], af[1]), complex(a2f[0], a2f[1])
+
+    def compute_all_vectors(self, qvecs, dsp="autocorrelate", method="fftw"):
+        q = np.ascontiguousarray(qvecs, dtype=np.float64).reshape(-1, 3)
+        at, af, a2f = self._outputs()
+        self._ck(self.lib.sgpu_compute_all_vectors(self.h, _dp(q), len(q), _dsp(dsp), _method(method), _dp(at), _dp(af),
+                                                   _dp(a2f)))
+        return self._pack(at, af, a2f)
+
+    def compute_self_vectors(self, qvecs, dsp="autocorrelate", method="fftw"):
+        q = np.ascontiguousarray(qvecs, dtype=np.float64).reshape(-1, 3)
+        at, af, a2f = self._outputs()
+        self._ck(self.lib.sgpu_compute_self_vectors(self.h, _dp(q), len(q), _dsp(dsp), _method(method), _dp(at),
+                                                    _dp(af), _dp(a2f)))
+        return self._pack(at, af, a2f)
+
+    def compute_mpsphere(self, qlen, moments, dsp="autocorrelate", method="fftw"):
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        at, af, a2f = self._outputs()
+        self._ck(self.lib.sgpu_compute_mpsphere(self.h, float(qlen), lm.ctypes.data_as(C.POINTER(C.c_long)), len(lm),
+                                                _dsp(dsp), _method(method), _dp(at), _dp(af), _dp(a2f)))
+        return self._pack(at, af, a2f)
+
+    # -- multi-GPU split
+    def partial_len(self, dsp="autocorrelate") -> int:
+        n = C.c_size_t()
+        self._ck(self.lib.sgpu_partial_len(self.h, _dsp(dsp), C.byref(n)))
+        return int(n.value)
+
+    def compute_all_vectors_partial(self, qvecs, d_partial: int, dsp="autocorrelate"):
+        q = np.ascontiguousarray(qvecs, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.sgpu_compute_all_vectors_partial(self.h, _dp(q), len(q), _dsp(dsp), C.c_void_p(d_partial)))
+
+    def compute_self_vectors_partial(self, qvecs, d_partial: int, dsp="autocorrelate"):
+        q = np.ascontiguousarray(qvecs, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.sgpu_compute_self_vectors_partial(self.h, _dp(q), len(q), _dsp(dsp), C.c_void_p(d_partial)))
+
+    def compute_mpsphere_partial(self, qlen, moments, d_partial: int, dsp="autocorrelate"):
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        self._ck(self.lib.sgpu_compute_mpsphere_partial(self.h, float(qlen), lm.ctypes.data_as(C.POINTER(C.c_long)),
+                                                        len(lm), _dsp(dsp), C.c_void_p(d_partial)))
+
+    def finalize(self, d_partial: int, scale: float, dsp="autocorrelate", method="fftw"):
+        at, af, a2f = self._outputs()
+        self._ck(self.lib.sgpu_finalize(self.h, C.c_void_p(d_partial), _dsp(dsp), _method(method), float(scale), _dp(at),
+                                        _dp(af), _dp(a2f)))
+        return self._pack(at, af, a2f)
+
+    # -- introspection
+    def get_amplitudes(self, NM):
+        A = np.zeros((NM, self.NF), dtype=np.complex128)
+        self._ck(self.lib.sgpu_get_amplitudes(self.h, _dp(A.view(np.float64)), NM, self.NF))
+        return A
+
+    def last_amplitude_ms(self) -> float:
+        v = C.c_float()
+        self._ck(self.lib.sgpu_last_amplitude_ms(self.h, C.byref(v)))
+        return float(v.value)
+
+    def last_dsp_ms(self) -> float:
+        v = C.c_float()
+        self._ck(self.lib.sgpu_last_dsp_ms(self.h, C.byref(v)))
+        return float(v.value)
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._ck(self.lib.sgpu_measure_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        rc = self.lib.sgpu_device_alloc(C.byref(p), nbytes)
+        if rc:
+            raise SgpuError(rc, "sgpu_device_alloc failed")
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        self.lib.sgpu_device_free(C.c_void_p(ptr))
+
+    def memcpy_d2h(self, host_array: np.ndarray, d_ptr: int):
+        self._ck(self.lib.sgpu_memcpy_d2h(self.h, host_array.ctypes.data, C.c_void_p(d_ptr), host_array.nbytes))
+
+    def memcpy_h2d(self, d_ptr: int, host_array: np.ndarray):
+        a = np.ascontiguousarray(host_array)
+        self._ck(self.lib.sgpu_memcpy_h2d(self.h, C.c_void_p(d_ptr), a.ctypes.data, a.nbytes))
+
+    def synth_trajectory(self, d_ptr: int, NF, NA, box, sigma, seed, layout=0, atom0=0, atom_stride=1, NA_out=None,
+                         offset=0.0):
+        from .synth import step_scale
+        NA_out = NA if NA_out is None else NA_out
+        self._ck(self.lib.sgpu_synth_trajectory(self.h, C.c_void_p(d_ptr), NF, NA, atom0, atom_stride, NA_out,
+                                                C.c_float(box), C.c_float(offset), C.c_float(step_scale(sigma)),
+                                                C.c_uint64(seed), layout))

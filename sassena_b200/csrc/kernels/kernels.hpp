@@ -1,0 +1,66 @@
+// kernels.hpp — launchers of the sm_100a kernels behind the C-ABI (include/sassena_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace sass {
+
+// ---- amplitude.cu -------------------------------------------------------------------------------
+// K1: A[m][f] = sum_j b_j exp(i q_m . r_j(f)) for frames [f0, f0+nf), all NM vectors.
+// d_qs: [NMpad][3] q-vectors pre-scaled by 2/pi, zero padded to a multiple of amplitude_all_qpad().
+// Returns the number of kernel launches queued.
+int amplitude_all_qpad();
+int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
+                         size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st);
+// K2: per-atom timelines a[(n*NM+m)][t] = b_n exp(i q_m . r_n(t)) for local atoms [n0, n0+nn).
+int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,
+                          size_t ldA, size_t NF, size_t NM, size_t n0, size_t nn, cudaStream_t st);
+// cart -> (r, phi, theta), in place, n points
+int launch_cart_to_spherical(float *d_xyz, size_t n, cudaStream_t st);
+// chunk of frames [nf][NA][3] starting at frame f0 -> [NA_out][NF][3] taking atoms atom0 + i*stride
+int launch_frames_to_atoms(const float *d_frames, float *d_atoms, size_t NF, size_t nf, size_t f0, size_t NA,
+                           size_t atom0, size_t stride, size_t NA_out, cudaStream_t st);
+int launch_synth_trajectory(float *d_xyz, size_t NF, size_t NA, size_t atom0, size_t atom_stride, size_t NA_out,
+                            float box, float offset, float step_scale, uint64_t seed, int layout, cudaStream_t st);
+// DFMA peak probe; returns flops executed
+double launch_fp64_peak(double *d_sink, int iters, int blocks, cudaStream_t st);
+
+// ---- multipole.cu -------------------------------------------------------------------------------
+// K5: A[mom][f] = sum_j 4pi i^l b_j j_l(q r_j) conj(Y_lm(theta_j, phi_j)), frames [f0,f0+nf).
+// d_lm: [NM][2] (l,m) as int; lmax = max l.  d_work: scratch of multipole_work_doubles() doubles.
+size_t multipole_work_doubles(size_t nf, int lmax, int *nsplit_out, size_t NA);
+int launch_multipole_sphere(const float *d_sph, const double *d_b, double ql, const int *d_lm, size_t NM, int lmax,
+                            double2 *d_A, size_t ldA, size_t NA, size_t f0, size_t nf, double *d_work,
+                            cudaStream_t st);
+
+// ---- correlate.cu -------------------------------------------------------------------------------
+struct CorrPlan {
+    size_t NF = 0;   // frames per timeline
+    size_t L = 0;    // padded FFT length (power of two >= 2*NF)
+    int log2N1 = 0;  // L = N1*N2, column FFT length N1 (strided), row FFT length N2 (contiguous)
+    int log2N2 = 0;
+    double2 *d_tw = nullptr;  // W_Nmax^k, k < Nmax/2  (Nmax = max(N1,N2)), forward sign
+    double2 *d_w = nullptr;   // weights What'[k1*N2+k2] for a_m = sum_k P[k] What[k] / (NF*L)
+    size_t Nmax = 0;
+};
+int corr_plan_create(CorrPlan *p, size_t NF, cudaStream_t st, uint64_t *launches);
+void corr_plan_destroy(CorrPlan *p);
+// bytes of scratch needed for nt timelines
+size_t corr_work_bytes(const CorrPlan *p, size_t nt);
+// DSP=autocorrelate over nt timelines A[nt][ldA] (first NF entries valid).  Accumulates (+=) into
+//   d_P[L] (power spectrum, internal [k1][k2] order), d_acc[4] = {sum a_re, sum a_im, sum |a|^2, 0}.
+int corr_power_accumulate(const CorrPlan *p, const double2 *d_A, size_t ldA, size_t nt, void *d_work, double *d_P,
+                          double *d_acc, cudaStream_t st);
+// inverse transform of the summed power spectrum: d_out[tau] = scale * c[tau]/(L*(NF-tau)), tau<NF;
+// conj_out negates the imaginary part (dsp.method=direct).  d_work >= corr_work_bytes(p,1).
+int corr_finalize(const CorrPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
+                  cudaStream_t st);
+// DSP=square / plain: d_at[NF] += sum_m f(A[m][t]); d_acc += {sum_m mean_t, sum_m |mean_t|^2}
+int dsp_elementwise_accumulate(const double2 *d_A, size_t ldA, size_t nt, size_t NF, int square, double2 *d_at,
+                               double *d_acc, void *d_work, cudaStream_t st);
+size_t dsp_elementwise_work_bytes(size_t nt);
+// out[i] = in[i]*scale (complex, n entries); acc_out[0..3] = acc[0..3]*scale
+int launch_scale_complex(const double2 *d_in, double2 *d_out, size_t n, double scale, cudaStream_t st);
+
+}  // namespace sass

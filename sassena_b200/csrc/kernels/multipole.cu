@@ -1,0 +1,277 @@
+// multipole.cu — multipole-sphere amplitude kernel (K5).
+//
+// Restates MPSphereScatterDevice::scatter (reference src/scatter_devices/multipole_scatter_device.cpp:428-498):
+//     A_lm[f] = sum_j 4 pi i^l b_j j_l(q r_j) conj(Y_lm(theta_j, phi_j)),   coordinates (r, phi, theta) as float.
+// The reference evaluates boost::math::sph_bessel and spherical_harmonic once per (moment, atom, frame);
+// here one pass over the atoms of a frame produces ALL moments:
+//   * j_l(x), l = 0..lmax, by one recurrence per atom (series for x<1, Miller downward recurrence for
+//     x < lmax, upward recurrence otherwise) kept in shared memory;
+//   * the normalised associated Legendre functions by the standard (m, l) recurrence with host-made
+//     coefficient tables, and cos(m phi), sin(m phi) by rotation — each term costs a few FP64 ops;
+//   * only m >= 0 is evaluated: with U = sum b j_l P_lm cos(m phi), V = sum b j_l P_lm sin(m phi),
+//       A_{l,+m} = 4 pi i^l (U - iV),   A_{l,-m} = 4 pi i^l (-1)^m (U + iV)       (Y_{l,-m} = (-1)^m conj Y_{lm}).
+// Reduction over atoms: warp shuffle tree per (l,m), accumulated in per-warp shared memory, combined in
+// a fixed order (no atomics).
+#include "kernels.hpp"
+
+#include <cmath>
+#include <vector>
+
+namespace sass {
+
+namespace {
+
+constexpr int MP_THREADS = 128;
+constexpr int MP_WARPS = MP_THREADS / 32;
+constexpr int MP_SERIES_TERMS = 10;
+constexpr int MP_LMAX = 50;
+
+struct MpTables {
+    int lmax = -1;
+    double *d = nullptr;  // [cMM (lmax+1)] [cM1 (lmax+1)] [A npairs] [B npairs] [series (lmax+1)*TERMS]
+};
+MpTables g_tab[16];  // per device
+
+__host__ __device__ inline int mp_npairs(int lmax) { return (lmax + 1) * (lmax + 2) / 2; }
+__host__ __device__ inline int mp_pair(int lmax, int l, int m) { return m * (lmax + 1) - (m * (m - 1)) / 2 + (l - m); }
+
+__global__ void __launch_bounds__(MP_THREADS) multipole_sphere_kernel(
+    const float *__restrict__ sph, const double *__restrict__ b, double ql, int lmax, int lstart, size_t NA,
+    size_t f0, int nsplit, size_t atoms_per_split, const double *__restrict__ tab, double2 *__restrict__ part,
+    size_t nf) {
+    extern __shared__ double smem[];
+    const int npairs = mp_npairs(lmax);
+    double *sJ = smem;                                 // [(lmax+1)][MP_THREADS]
+    double *sAcc = smem + (lmax + 1) * MP_THREADS;     // [MP_WARPS][npairs*2]
+    const double *cMM = tab;
+    const double *cM1 = tab + (lmax + 1);
+    const double *cA = tab + 2 * (lmax + 1);
+    const double *cB = cA + npairs;
+    const double *cS = cB + npairs;  // series coefficients [(lmax+1)][TERMS]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t fr = blockIdx.x;
+    const int split = blockIdx.y;
+    for (int i = tid; i < MP_WARPS * npairs * 2; i += MP_THREADS) sAcc[i] = 0.0;
+    __syncthreads();
+
+    const size_t a_begin = (size_t)split * atoms_per_split;
+    const size_t a_end = min(NA, a_begin + atoms_per_split);
+    const float *p = sph + (f0 + fr) * NA * 3;
+    double *myAcc = sAcc + warp * npairs * 2;
+
+    for (size_t base = a_begin; base < a_end; base += MP_THREADS) {
+        const size_t atom = base + tid;
+        double r = 0.0, phi = 0.0, theta = 0.0, bj = 0.0;
+        if (atom < a_end) {
+            r = (double)__ldg(&p[3 * atom]);
+            phi = (double)__ldg(&p[3 * atom + 1]);
+            theta = (double)__ldg(&p[3 * atom + 2]);
+            bj = __ldg(&b[atom]);
+        }
+        const double x = ql * r;
+        // ---- spherical Bessel ladder into sJ[l][tid] ----
+        if (x < 1.0) {
+            const double x2 = x * x;
+            double pref = 1.0;
+            for (int l = 0; l <= lmax; l++) {
+                if (l > 0) pref *= x / (double)(2 * l + 1);
+                double term = 1.0, sum = 1.0;
+#pragma unroll
+                for (int k = 0; k < MP_SERIES_TERMS; k++) {
+                    term *= x2 * __ldg(&cS[l * MP_SERIES_TERMS + k]);
+                    sum += term;
+                }
+                sJ[l * MP_THREADS + tid] = pref * sum;
+            }
+        } else {
+            double sn, cs;
+            sincos(x, &sn, &cs);
+            const double invx = 1.0 / x;
+            const double j0 = sn * invx;
+            const double j1 = (sn * invx - cs) * invx;
+            if (x >= (double)lmax) {
+                double jm = j0, jc = j1;
+                sJ[tid] = j0;
+                if (lmax >= 1) sJ[MP_THREADS + tid] = j1;
+                for (int l = 1; l < lmax; l++) {
+                    const double jn = fma((double)(2 * l + 1) * invx, jc, -jm);
+                    jm = jc;
+                    jc = jn;
+                    sJ[(l + 1) * MP_THREADS + tid] = jn;
+                }
+            } else {
+                double jp = 0.0, jc = 1e-300;
+                for (int k = lstart; k >= 1; k--) {
+                    const double jm = fma((double)(2 * k + 1) * invx, jc, -jp);  // j_{k-1}
+                    jp = jc;
+                    jc = jm;
+                    if (k - 1 <= lmax) sJ[(k - 1) * MP_THREADS + tid] = jc;
+                }
+                // jc ~ j_0, jp ~ j_1 (unnormalised)
+                const double scale = (fabs(j0) >= fabs(j1)) ? j0 / jc : j1 / jp;
+                for (int l = 0; l <= lmax; l++) sJ[l * MP_THREADS + tid] *= scale;
+            }
+        }
+        // ---- Legendre / azimuth recurrences, one (l,m>=0) term at a time ----
+        double st, ct, s1, c1;
+        sincos(theta, &st, &ct);
+        sincos(phi, &s1, &c1);
+        double pmm = 0.28209479177387814347;  // sqrt(1/(4 pi))
+        double cm = 1.0, sm = 0.0;
+        for (int m = 0; m <= lmax; m++) {
+            if (m > 0) {
+                pmm *= __ldg(&cMM[m]) * st;
+                const double cn = cm * c1 - sm * s1;
+                sm = fma(sm, c1, cm * s1);
+                cm = cn;
+            }
+            double p2 = 0.0, p1 = pmm;
+            const int pbase = mp_pair(lmax, m, m);
+            for (int l = m; l <= lmax; l++) {
+                double pl;
+                if (l == m) pl = pmm;
+                else if (l == m + 1) pl = __ldg(&cM1[m]) * ct * pmm;
+                else pl = __ldg(&cA[pbase + l - m]) * fma(ct, p1, -__ldg(&cB[pbase + l - m]) * p2);
+                p2 = p1;
+                p1 = pl;
+                const double t = bj * sJ[l * MP_THREADS + tid] * pl;
+                double u = t * cm, v = t * sm;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    u += __shfl_xor_sync(0xffffffffu, u, o);
+                    v += __shfl_xor_sync(0xffffffffu, v, o);
+                }
+                if (lane == 0) {
+                    myAcc[2 * (pbase + l - m)] += u;
+                    myAcc[2 * (pbase + l - m) + 1] += v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < npairs; i += MP_THREADS) {
+        double u = 0.0, v = 0.0;
+#pragma unroll
+        for (int w = 0; w < MP_WARPS; w++) {
+            u += sAcc[w * npairs * 2 + 2 * i];
+            v += sAcc[w * npairs * 2 + 2 * i + 1];
+        }
+        part[((size_t)split * nf + fr) * npairs + i] = make_double2(u, v);
+    }
+}
+
+// A[mom][f0+fr] = 4 pi i^l * { U - iV  (m>=0) ; (-1)^m (U + iV) (m<0) }, summed over the atom splits
+__global__ void multipole_assemble_kernel(const double2 *__restrict__ part, int nsplit, size_t nf, int lmax,
+                                          const int *__restrict__ lm, size_t NM, double2 *__restrict__ A, size_t ldA,
+                                          size_t f0) {
+    const size_t fr = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t mom = blockIdx.y;
+    if (fr >= nf || mom >= NM) return;
+    const int l = lm[2 * mom], m = lm[2 * mom + 1];
+    const int am = m < 0 ? -m : m;
+    const int npairs = mp_npairs(lmax);
+    const int pi = mp_pair(lmax, l, am);
+    double u = 0.0, v = 0.0;
+    for (int s = 0; s < nsplit; s++) {
+        const double2 w = part[((size_t)s * nf + fr) * npairs + pi];
+        u += w.x;
+        v += w.y;
+    }
+    double wr, wi;
+    if (m >= 0) {
+        wr = u;
+        wi = -v;
+    } else {
+        const double sg = (am & 1) ? -1.0 : 1.0;
+        wr = sg * u;
+        wi = sg * v;
+    }
+    const double FOURPI = 12.566370614359172954;
+    double ar, ai;
+    switch (l & 3) {
+        case 0: ar = wr; ai = wi; break;
+        case 1: ar = -wi; ai = wr; break;
+        case 2: ar = -wr; ai = -wi; break;
+        default: ar = wi; ai = -wr; break;
+    }
+    A[mom * ldA + f0 + fr] = make_double2(FOURPI * ar, FOURPI * ai);
+}
+
+int mp_lstart(int lmax) { return lmax + 20 + (int)std::sqrt(60.0 * (lmax + 10)); }
+
+const double *mp_tables(int lmax, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    MpTables &T = g_tab[dev & 15];
+    if (T.lmax == lmax && T.d) return T.d;
+    if (T.d) {
+        cudaStreamSynchronize(st);
+        cudaFree(T.d);
+        T.d = nullptr;
+    }
+    const int np = mp_npairs(lmax);
+    std::vector<double> h(2 * (lmax + 1) + 2 * np + (lmax + 1) * MP_SERIES_TERMS, 0.0);
+    double *cMM = h.data(), *cM1 = cMM + (lmax + 1), *cA = cM1 + (lmax + 1), *cB = cA + np, *cS = cB + np;
+    for (int m = 0; m <= lmax; m++) {
+        if (m > 0) cMM[m] = -std::sqrt((2.0 * m + 1.0) / (2.0 * m));
+        cM1[m] = std::sqrt(2.0 * m + 3.0);
+        for (int l = m + 2; l <= lmax; l++) {
+            const double dl = l, dm = m;
+            cA[mp_pair(lmax, l, m)] = std::sqrt((4.0 * dl * dl - 1.0) / (dl * dl - dm * dm));
+            cB[mp_pair(lmax, l, m)] = std::sqrt(((dl - 1.0) * (dl - 1.0) - dm * dm) / (4.0 * (dl - 1.0) * (dl - 1.0) - 1.0));
+        }
+    }
+    for (int l = 0; l <= lmax; l++)
+        for (int k = 1; k <= MP_SERIES_TERMS; k++) cS[l * MP_SERIES_TERMS + (k - 1)] = -0.5 / (k * (2.0 * l + 2.0 * k + 1.0));
+    if (cudaMalloc(reinterpret_cast<void **>(&T.d), h.size() * sizeof(double)) != cudaSuccess) return nullptr;
+    cudaMemcpyAsync(T.d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    T.lmax = lmax;
+    return T.d;
+}
+
+int mp_nsplit(size_t nf, size_t NA) {
+    size_t want = (600 + nf - 1) / nf;
+    size_t cap = (NA + 4 * MP_THREADS - 1) / (4 * MP_THREADS);
+    size_t n = want < cap ? want : cap;
+    if (n < 1) n = 1;
+    if (n > 4096) n = 4096;
+    return (int)n;
+}
+
+}  // namespace
+
+size_t multipole_work_doubles(size_t nf, int lmax, int *nsplit_out, size_t NA) {
+    const int ns = mp_nsplit(nf, NA);
+    if (nsplit_out) *nsplit_out = ns;
+    return (size_t)ns * nf * mp_npairs(lmax) * 2;
+}
+
+int launch_multipole_sphere(const float *d_sph, const double *d_b, double ql, const int *d_lm, size_t NM, int lmax,
+                            double2 *d_A, size_t ldA, size_t NA, size_t f0, size_t nf, double *d_work,
+                            cudaStream_t st) {
+    if (nf == 0 || NM == 0) return 0;
+    if (lmax > MP_LMAX) return -1;
+    const double *tab = mp_tables(lmax, st);
+    if (!tab) return -1;
+    const int nsplit = mp_nsplit(nf, NA);
+    const size_t per = (NA + nsplit - 1) / nsplit;
+    const size_t smem = ((size_t)(lmax + 1) * MP_THREADS + (size_t)MP_WARPS * mp_npairs(lmax) * 2) * sizeof(double);
+    cudaFuncSetAttribute(multipole_sphere_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int launches = 0;
+    double2 *part = reinterpret_cast<double2 *>(d_work);
+    // grid.x = frames (<= 2^31-1), grid.y = splits
+    multipole_sphere_kernel<<<dim3((unsigned)nf, (unsigned)nsplit), MP_THREADS, smem, st>>>(
+        d_sph, d_b, ql, lmax, mp_lstart(lmax), NA, f0, nsplit, per, tab, part, nf);
+    launches++;
+    for (size_t m0 = 0; m0 < NM; m0 += 65535) {
+        const size_t cnt = NM - m0 < 65535 ? NM - m0 : 65535;
+        multipole_assemble_kernel<<<dim3((unsigned)((nf + 127) / 128), (unsigned)cnt), 128, 0, st>>>(
+            part, nsplit, nf, lmax, d_lm + 2 * m0, cnt, d_A + m0 * ldA, ldA, f0);
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace sass

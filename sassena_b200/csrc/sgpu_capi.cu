@@ -1,0 +1,796 @@
+// sgpu_capi.cu — implementation of the C-ABI in include/sassena_b200.h.
+//
+// One sgpu_ctx owns one GPU: the staged coordinates, the per-|q| scratch (amplitudes, FFT work,
+// packed partial) and two streams (compute + copy).  All compute is CUDA; there is no CPU path.
+#include "../../include/sassena_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels/kernels.hpp"
+
+using namespace sass;
+
+namespace {
+std::string g_init_error;
+const double kTwoOverPi = 0.63661977236758134308;
+}  // namespace
+
+struct sgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // staged coordinates
+    int mode = 0;  // 0 none, 1 frames [NF][NA][3], 2 atoms [NA][NF][3]
+    float *d_xyz = nullptr;
+    bool own_xyz = false;
+    size_t xyz_cap = 0;  // bytes owned
+    size_t NF = 0, NA = 0;
+    int repr = SGPU_REPR_CARTESIAN;
+    struct Chunk {
+        size_t f0, nf;
+        cudaEvent_t ready;
+    };
+    std::vector<Chunk> chunks;  // pending async staging chunks (frames mode)
+    float *d_stage_tmp = nullptr;
+    size_t stage_tmp_cap = 0;
+
+    double *d_b = nullptr;
+    size_t nb = 0, b_cap = 0;
+    double *d_qs = nullptr;
+    size_t q_cap = 0;
+    int *d_lm = nullptr;
+    size_t lm_cap = 0;
+    std::vector<double> h_qs;
+
+    double2 *d_A = nullptr;
+    size_t A_cap = 0;  // entries
+    size_t A_NM = 0;   // timelines held by the last all/mpsphere compute
+    void *d_work = nullptr;
+    size_t work_cap = 0;
+    double *d_partial = nullptr;
+    size_t partial_cap = 0;
+    double2 *d_out = nullptr;
+    size_t out_cap = 0;
+    double *h_acc = nullptr;  // pinned, 4 doubles
+
+    CorrPlan plan;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool have_times = false;
+
+    ~sgpu_ctx() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        for (auto &c : chunks) cudaEventDestroy(c.ready);
+        if (own_xyz && d_xyz) cudaFree(d_xyz);
+        if (d_stage_tmp) cudaFree(d_stage_tmp);
+        if (d_b) cudaFree(d_b);
+        if (d_qs) cudaFree(d_qs);
+        if (d_lm) cudaFree(d_lm);
+        if (d_A) cudaFree(d_A);
+        if (d_work) cudaFree(d_work);
+        if (d_partial) cudaFree(d_partial);
+        if (d_out) cudaFree(d_out);
+        if (h_acc) cudaFreeHost(h_acc);
+        corr_plan_destroy(&plan);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+namespace {
+
+int fail(sgpu_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else g_init_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            cudaGetLastError();                                                                           \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SGPU_ENOMEM : SGPU_ECUDA,                 \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                             \
+        }                                                                                                 \
+    } while (0)
+
+template <typename T>
+int ensure(sgpu_ctx *ctx, T **p, size_t *cap, size_t need_elems) {
+    if (*cap >= need_elems && *p) return SGPU_OK;
+    if (*p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t n = std::max<size_t>(need_elems, 1);
+    CK(cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T)));
+    *cap = n;
+    return SGPU_OK;
+}
+
+int ensure_work(sgpu_ctx *ctx, size_t bytes) {
+    char *p = reinterpret_cast<char *>(ctx->d_work);
+    int rc = ensure<char>(ctx, &p, &ctx->work_cap, bytes);
+    ctx->d_work = p;
+    return rc;
+}
+
+void drop_chunks(sgpu_ctx *ctx) {
+    for (auto &c : ctx->chunks) cudaEventDestroy(c.ready);
+    ctx->chunks.clear();
+}
+
+int release_xyz(sgpu_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    drop_chunks(ctx);
+    if (!ctx->own_xyz) {
+        ctx->d_xyz = nullptr;
+        ctx->xyz_cap = 0;
+    }
+    ctx->mode = 0;
+    return SGPU_OK;
+}
+
+int own_xyz_buffer(sgpu_ctx *ctx, size_t bytes) {
+    if (!ctx->own_xyz || ctx->xyz_cap < bytes || !ctx->d_xyz) {
+        if (ctx->own_xyz && ctx->d_xyz) CK(cudaFree(ctx->d_xyz));
+        ctx->d_xyz = nullptr;
+        ctx->own_xyz = true;
+        ctx->xyz_cap = 0;
+        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xyz), std::max<size_t>(bytes, 4)));
+        ctx->xyz_cap = bytes;
+    }
+    return SGPU_OK;
+}
+
+int ensure_plan(sgpu_ctx *ctx) {
+    if (ctx->plan.NF == ctx->NF && ctx->plan.d_tw) return SGPU_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    corr_plan_destroy(&ctx->plan);
+    int rc = corr_plan_create(&ctx->plan, ctx->NF, ctx->stream, &ctx->launches);
+    if (rc == 1) return fail(ctx, SGPU_EINVAL, "number of frames not supported by the correlation plan (1 <= NF <= 2^21)");
+    if (rc) return fail(ctx, SGPU_ECUDA, std::string("corr_plan_create: ") + cudaGetErrorString(cudaGetLastError()));
+    return SGPU_OK;
+}
+
+size_t partial_len(const sgpu_ctx *ctx, int dsp_type) {
+    return (dsp_type == SGPU_DSP_AUTOCORRELATE ? ctx->plan.L : 2 * ctx->NF) + 4;
+}
+
+int check_dsp(sgpu_ctx *ctx, int dsp_type, int dsp_method) {
+    // reference: all_vectors_scatter_device.cpp:209-229 (Err::write + throw on unknown type/method)
+    if (dsp_type != SGPU_DSP_AUTOCORRELATE && dsp_type != SGPU_DSP_SQUARE && dsp_type != SGPU_DSP_PLAIN)
+        return fail(ctx, SGPU_EINVAL, "DSP type not understood: scattering.dsp.type == autocorrelate, square, plain");
+    if (dsp_type == SGPU_DSP_AUTOCORRELATE && dsp_method != SGPU_METHOD_FFTW && dsp_method != SGPU_METHOD_DIRECT)
+        return fail(ctx, SGPU_EINVAL, "Correlation method not understood: scattering.dsp.method == direct, fftw");
+    return SGPU_OK;
+}
+
+// upload q-vectors pre-scaled to quarter turns, zero padded to `pad` multiples
+int upload_q(sgpu_ctx *ctx, const double *qvecs, size_t NM, size_t pad) {
+    const size_t NMpad = ((NM + pad - 1) / pad) * pad;
+    ctx->h_qs.assign(NMpad * 3, 0.0);
+    for (size_t i = 0; i < NM * 3; i++) ctx->h_qs[i] = qvecs[i] * kTwoOverPi;
+    int rc = ensure<double>(ctx, &ctx->d_qs, &ctx->q_cap, NMpad * 3);
+    if (rc) return rc;
+    // the host vector is reused by the next call: make the copy synchronous with respect to the host
+    CK(cudaMemcpyAsync(ctx->d_qs, ctx->h_qs.data(), NMpad * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+// DSP of nt timelines in d_A (ld = NF) accumulated into the packed partial
+int dsp_accumulate(sgpu_ctx *ctx, size_t nt, int dsp_type, double *d_partial) {
+    if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
+        ctx->launches += corr_power_accumulate(&ctx->plan, ctx->d_A, ctx->NF, nt, ctx->d_work, d_partial,
+                                               d_partial + ctx->plan.L, ctx->stream);
+    } else {
+        ctx->launches += dsp_elementwise_accumulate(ctx->d_A, ctx->NF, nt, ctx->NF, dsp_type == SGPU_DSP_SQUARE,
+                                                    reinterpret_cast<double2 *>(d_partial), d_partial + 2 * ctx->NF,
+                                                    ctx->d_work, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    return SGPU_OK;
+}
+
+size_t dsp_work_bytes(const sgpu_ctx *ctx, size_t nt, int dsp_type) {
+    size_t b = (dsp_type == SGPU_DSP_AUTOCORRELATE) ? corr_work_bytes(&ctx->plan, nt) : dsp_elementwise_work_bytes(nt);
+    return std::max(b, corr_work_bytes(&ctx->plan, 1));
+}
+
+int ensure_internal_partial(sgpu_ctx *ctx, int dsp_type) {
+    return ensure<double>(ctx, &ctx->d_partial, &ctx->partial_cap, partial_len(ctx, dsp_type));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sgpu_version(void) { return "sassena_b200 0.1 (sm_100a)"; }
+
+int sgpu_init(int device, sgpu_ctx **out) {
+    sgpu_ctx *ctx = nullptr;  // for CK/fail: errors go to g_init_error
+    if (!out) return fail(nullptr, SGPU_EINVAL, "sgpu_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SGPU_ECUDA,
+                    std::string("sgpu_init: no CUDA device available (") + cudaGetErrorString(e) +
+                        "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, SGPU_EINVAL, "sgpu_init: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, SGPU_ECUDA,
+                    std::string("sgpu_init: device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        ", this library is built for sm_100a (B200) only");
+    sgpu_ctx *c = new sgpu_ctx();
+    c->device = device;
+    ctx = nullptr;
+    cudaError_t e2;
+    if ((e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e2 = cudaEventCreate(&c->ev0)) != cudaSuccess || (e2 = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e2 = cudaEventCreate(&c->ev2)) != cudaSuccess ||
+        (e2 = cudaHostAlloc(reinterpret_cast<void **>(&c->h_acc), 4 * sizeof(double), cudaHostAllocDefault)) !=
+            cudaSuccess) {
+        delete c;
+        return fail(nullptr, SGPU_ECUDA, std::string("sgpu_init: ") + cudaGetErrorString(e2));
+    }
+    *out = c;
+    return SGPU_OK;
+}
+
+void sgpu_destroy(sgpu_ctx *ctx) { delete ctx; }
+
+const char *sgpu_last_error(const sgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+uint64_t sgpu_launch_count(const sgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int sgpu_synchronize(sgpu_ctx *ctx) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+void *sgpu_stream(sgpu_ctx *ctx) { return ctx ? reinterpret_cast<void *>(ctx->stream) : nullptr; }
+
+int sgpu_host_alloc(void **ptr, size_t bytes) {
+    sgpu_ctx *ctx = nullptr;
+    if (!ptr) return SGPU_EINVAL;
+    CK(cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+    return SGPU_OK;
+}
+int sgpu_host_free(void *ptr) {
+    sgpu_ctx *ctx = nullptr;
+    CK(cudaFreeHost(ptr));
+    return SGPU_OK;
+}
+int sgpu_device_alloc(void **d_ptr, size_t bytes) {
+    sgpu_ctx *ctx = nullptr;
+    if (!d_ptr) return SGPU_EINVAL;
+    CK(cudaMalloc(d_ptr, std::max<size_t>(bytes, 1)));
+    return SGPU_OK;
+}
+int sgpu_device_free(void *d_ptr) {
+    sgpu_ctx *ctx = nullptr;
+    CK(cudaFree(d_ptr));
+    return SGPU_OK;
+}
+int sgpu_memcpy_d2h(sgpu_ctx *ctx, void *dst, const void *d_src, size_t bytes) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+int sgpu_memcpy_h2d(sgpu_ctx *ctx, void *d_dst, const void *src, size_t bytes) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+/* ---- staging ---------------------------------------------------------------------------------- */
+
+int sgpu_stage_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, int repr) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!xyz || NF < 1 || NA < 1)
+        return fail(ctx, SGPU_EINVAL, "sgpu_stage_frames: No frames / atoms available");  // factory.cpp:39-47
+    if (repr != SGPU_REPR_CARTESIAN && repr != SGPU_REPR_SPHERICAL)
+        return fail(ctx, SGPU_EINVAL, "sgpu_stage_frames: unknown representation");
+    CK(cudaSetDevice(ctx->device));
+    int rc = release_xyz(ctx);
+    if (rc) return rc;
+    const size_t frame_bytes = NA * 3 * sizeof(float);
+    rc = own_xyz_buffer(ctx, NF * frame_bytes);
+    if (rc) return rc;
+    // chunk by frames: big enough that one chunk is many waves of amplitude CTAs, small enough to overlap
+    size_t nfc = std::max<size_t>(1, ((size_t)256 << 20) / frame_bytes);
+    for (size_t f0 = 0; f0 < NF; f0 += nfc) {
+        const size_t nf = std::min(nfc, NF - f0);
+        sgpu_ctx::Chunk c{f0, nf, nullptr};
+        CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+        cudaError_t e = cudaMemcpyAsync(ctx->d_xyz + f0 * NA * 3, xyz + f0 * NA * 3, nf * frame_bytes,
+                                        cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c.ready, ctx->copy_stream);
+        ctx->chunks.push_back(c);
+        if (e != cudaSuccess) {
+            drop_chunks(ctx);
+            return fail(ctx, SGPU_ECUDA, std::string("sgpu_stage_frames: ") + cudaGetErrorString(e));
+        }
+    }
+    ctx->mode = 1;
+    ctx->NF = NF;
+    ctx->NA = NA;
+    ctx->repr = repr;
+    return SGPU_OK;
+}
+
+int sgpu_stage_frames_device(sgpu_ctx *ctx, const float *d_xyz, size_t NF, size_t NA, int repr) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!d_xyz || NF < 1 || NA < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_frames_device: No frames / atoms available");
+    CK(cudaSetDevice(ctx->device));
+    int rc = release_xyz(ctx);
+    if (rc) return rc;
+    if (ctx->own_xyz && ctx->d_xyz) CK(cudaFree(ctx->d_xyz));
+    ctx->own_xyz = false;
+    ctx->xyz_cap = 0;
+    ctx->d_xyz = const_cast<float *>(d_xyz);
+    ctx->mode = 1;
+    ctx->NF = NF;
+    ctx->NA = NA;
+    ctx->repr = repr;
+    return SGPU_OK;
+}
+
+int sgpu_frames_to_spherical(sgpu_ctx *ctx) {
+    if (!ctx) return SGPU_EINVAL;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: no frames staged");
+    if (ctx->repr == SGPU_REPR_SPHERICAL) return SGPU_OK;
+    if (!ctx->own_xyz) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: adopted device buffers are read-only");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    drop_chunks(ctx);
+    ctx->launches += launch_cart_to_spherical(ctx->d_xyz, ctx->NF * ctx->NA, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->repr = SGPU_REPR_SPHERICAL;
+    return SGPU_OK;
+}
+
+int sgpu_stage_atoms(sgpu_ctx *ctx, const float *xyz, size_t NA_local, size_t NF) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!xyz || NF < 1 || NA_local < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms: No frames / atoms available");
+    CK(cudaSetDevice(ctx->device));
+    int rc = release_xyz(ctx);
+    if (rc) return rc;
+    const size_t bytes = NA_local * NF * 3 * sizeof(float);
+    rc = own_xyz_buffer(ctx, bytes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_xyz, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mode = 2;
+    ctx->NF = NF;
+    ctx->NA = NA_local;
+    ctx->repr = SGPU_REPR_CARTESIAN;
+    return SGPU_OK;
+}
+
+int sgpu_stage_atoms_device(sgpu_ctx *ctx, const float *d_xyz, size_t NA_local, size_t NF) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!d_xyz || NF < 1 || NA_local < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_device: No frames / atoms available");
+    CK(cudaSetDevice(ctx->device));
+    int rc = release_xyz(ctx);
+    if (rc) return rc;
+    if (ctx->own_xyz && ctx->d_xyz) CK(cudaFree(ctx->d_xyz));
+    ctx->own_xyz = false;
+    ctx->xyz_cap = 0;
+    ctx->d_xyz = const_cast<float *>(d_xyz);
+    ctx->mode = 2;
+    ctx->NF = NF;
+    ctx->NA = NA_local;
+    ctx->repr = SGPU_REPR_CARTESIAN;
+    return SGPU_OK;
+}
+
+int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t nranks, size_t rank) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!xyz || NF < 1 || NA < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: No frames / atoms available");
+    if (nranks < 1 || rank >= nranks) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: bad rank / nranks");
+    CK(cudaSetDevice(ctx->device));
+    int rc = release_xyz(ctx);
+    if (rc) return rc;
+    // ModAssignment::size (assignment.cpp:82-90)
+    size_t NA_local = NA / nranks;
+    if ((NA % nranks) != 0 && rank < (NA - nranks * (NA / nranks))) NA_local += 1;
+    if (NA_local == 0) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: this rank owns no atoms");
+    rc = own_xyz_buffer(ctx, NA_local * NF * 3 * sizeof(float));
+    if (rc) return rc;
+    const size_t frame_bytes = NA * 3 * sizeof(float);
+    size_t nfc = std::max<size_t>(32, ((size_t)256 << 20) / frame_bytes);
+    nfc = std::min(nfc, NF);
+    // two bounce buffers so the H2D copy of chunk i+1 overlaps the transpose of chunk i
+    rc = ensure<float>(ctx, &ctx->d_stage_tmp, &ctx->stage_tmp_cap, 2 * nfc * NA * 3);
+    if (rc) return rc;
+    cudaEvent_t copied[2], consumed[2];
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
+    }
+    int slot = 0;
+    size_t iter = 0;
+    for (size_t f0 = 0; f0 < NF; f0 += nfc, slot ^= 1, iter++) {
+        const size_t nf = std::min(nfc, NF - f0);
+        float *tmp = ctx->d_stage_tmp + (size_t)slot * nfc * NA * 3;
+        if (iter >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, consumed[slot], 0));
+        CK(cudaMemcpyAsync(tmp, xyz + f0 * NA * 3, nf * frame_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(copied[slot], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, copied[slot], 0));
+        ctx->launches += launch_frames_to_atoms(tmp, ctx->d_xyz, NF, nf, f0, NA, rank, nranks, NA_local, ctx->stream);
+        CK(cudaEventRecord(consumed[slot], ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(copied[i]);
+        cudaEventDestroy(consumed[i]);
+    }
+    CK(cudaGetLastError());
+    ctx->mode = 2;
+    ctx->NF = NF;
+    ctx->NA = NA_local;
+    ctx->repr = SGPU_REPR_CARTESIAN;
+    return SGPU_OK;
+}
+
+int sgpu_set_factors(sgpu_ctx *ctx, const double *b, size_t n) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!b || n == 0) return fail(ctx, SGPU_EINVAL, "sgpu_set_factors: empty factors");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure<double>(ctx, &ctx->d_b, &ctx->b_cap, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_b, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nb = n;
+    return SGPU_OK;
+}
+
+/* ---- compute ---------------------------------------------------------------------------------- */
+
+int sgpu_partial_len(sgpu_ctx *ctx, int dsp_type, size_t *n_doubles) {
+    if (!ctx || !n_doubles) return SGPU_EINVAL;
+    if (ctx->mode == 0) return fail(ctx, SGPU_ESTATE, "sgpu_partial_len: nothing staged");
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    *n_doubles = partial_len(ctx, dsp_type);
+    return SGPU_OK;
+}
+
+static int frames_amplitude_prologue(sgpu_ctx *ctx, const char *who, size_t NM, int dsp_type, double *d_partial) {
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, std::string(who) + ": frames are not staged (stage_frames first)");
+    if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, std::string(who) + ": scattering factors not set for the staged atoms");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
+    if (!d_partial) return fail(ctx, SGPU_EINVAL, std::string(who) + ": d_partial is NULL");
+    int rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure<double2>(ctx, &ctx->d_A, &ctx->A_cap, NM * ctx->NF);
+    if (rc) return rc;
+    rc = ensure_work(ctx, dsp_work_bytes(ctx, NM, dsp_type));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_partial, 0, partial_len(ctx, dsp_type) * sizeof(double), ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_compute_all_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (!qvecs) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors: qvecs is NULL");
+    if (ctx->mode == 1 && ctx->repr != SGPU_REPR_CARTESIAN)
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors: staged frames are not cartesian");
+    rc = frames_amplitude_prologue(ctx, "sgpu_compute_all_vectors", NM, dsp_type, d_partial);
+    if (rc) return rc;
+    rc = upload_q(ctx, qvecs, NM, (size_t)amplitude_all_qpad());
+    if (rc) return rc;
+
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // if every staging chunk has landed, run one launch over all frames; else one launch per chunk
+    bool all_ready = true;
+    for (auto &c : ctx->chunks)
+        if (cudaEventQuery(c.ready) != cudaSuccess) all_ready = false;
+    cudaGetLastError();
+    if (all_ready) {
+        drop_chunks(ctx);
+        ctx->launches += launch_amplitude_all(ctx->d_xyz, ctx->d_b, ctx->d_qs, ctx->d_A, ctx->NF, ctx->NA, NM, 0,
+                                              ctx->NF, ctx->stream);
+    } else {
+        for (auto &c : ctx->chunks) {
+            CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+            ctx->launches += launch_amplitude_all(ctx->d_xyz, ctx->d_b, ctx->d_qs, ctx->d_A, ctx->NF, ctx->NA, NM, c.f0,
+                                                  c.nf, ctx->stream);
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->A_NM = NM;
+    rc = dsp_accumulate(ctx, NM, dsp_type, d_partial);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    return SGPU_OK;
+}
+
+int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (!qvecs) return fail(ctx, SGPU_EINVAL, "sgpu_compute_self_vectors: qvecs is NULL");
+    if (ctx->mode != 2) return fail(ctx, SGPU_ESTATE, "sgpu_compute_self_vectors: atoms are not staged (stage_atoms first)");
+    if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, "sgpu_compute_self_vectors: scattering factors not set for the staged atoms");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_self_vectors: No qvectors left to compute");
+    if (!d_partial) return fail(ctx, SGPU_EINVAL, "sgpu_compute_self_vectors: d_partial is NULL");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = upload_q(ctx, qvecs, NM, 1);
+    if (rc) return rc;
+
+    // batch atoms so that amplitudes + FFT scratch fit a memory budget
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>((free_b + ctx->work_cap + ctx->A_cap * sizeof(double2)) / 3, (size_t)24 << 30);
+    const size_t per_tl = corr_work_bytes(&ctx->plan, 1024) / 1024 + ctx->NF * sizeof(double2) + 64;
+    size_t nt_max = std::max<size_t>(budget / per_tl, NM);
+    size_t atoms_per_batch = std::max<size_t>(1, nt_max / NM);
+    atoms_per_batch = std::min(atoms_per_batch, ctx->NA);
+    const size_t nt_batch = atoms_per_batch * NM;
+    rc = ensure<double2>(ctx, &ctx->d_A, &ctx->A_cap, nt_batch * ctx->NF);
+    if (rc) return rc;
+    rc = ensure_work(ctx, dsp_work_bytes(ctx, nt_batch, dsp_type));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_partial, 0, partial_len(ctx, dsp_type) * sizeof(double), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (size_t n0 = 0; n0 < ctx->NA; n0 += atoms_per_batch) {
+        const size_t nn = std::min(atoms_per_batch, ctx->NA - n0);
+        ctx->launches += launch_amplitude_self(ctx->d_xyz, ctx->d_b, ctx->d_qs, ctx->d_A, ctx->NF, ctx->NF, NM, n0, nn,
+                                               ctx->stream);
+        CK(cudaGetLastError());
+        rc = dsp_accumulate(ctx, nn * NM, dsp_type, d_partial);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->A_NM = 0;
+    return SGPU_OK;
+}
+
+int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type,
+                                  double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (!lm) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: lm is NULL");
+    if (ctx->mode == 1 && ctx->repr != SGPU_REPR_SPHERICAL)
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: staged frames are not in spherical representation");
+    int lmax = 0;
+    std::vector<int> h_lm(NM * 2);
+    for (size_t i = 0; i < NM; i++) {
+        const long l = lm[2 * i], m = lm[2 * i + 1];
+        if (l < 0 || std::labs(m) > l)  // multipole_scatter_device.cpp:459-465, parameters.cpp:1101-1113
+            return fail(ctx, SGPU_EINVAL,
+                        "Combination of Major and minor moment not allowed: l=" + std::to_string(l) + ", m" +
+                            std::to_string(m));
+        if (l > 50) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: major moment > 50 not supported");
+        lmax = std::max<int>(lmax, (int)l);
+        h_lm[2 * i] = (int)l;
+        h_lm[2 * i + 1] = (int)m;
+    }
+    rc = frames_amplitude_prologue(ctx, "sgpu_compute_mpsphere", NM, dsp_type, d_partial);
+    if (rc) return rc;
+    rc = ensure<int>(ctx, &ctx->d_lm, &ctx->lm_cap, NM * 2);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_lm, h_lm.data(), NM * 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    drop_chunks(ctx);
+    int nsplit = 1;
+    const size_t mp_work = multipole_work_doubles(ctx->NF, lmax, &nsplit, ctx->NA) * sizeof(double);
+    rc = ensure_work(ctx, std::max(mp_work, dsp_work_bytes(ctx, NM, dsp_type)));
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ctx->launches += launch_multipole_sphere(ctx->d_xyz, ctx->d_b, qlen, ctx->d_lm, NM, lmax, ctx->d_A, ctx->NF, ctx->NA, 0,
+                                             ctx->NF, reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->A_NM = NM;
+    rc = dsp_accumulate(ctx, NM, dsp_type, d_partial);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    return SGPU_OK;
+}
+
+int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_method, double scale, double *atfinal,
+                  double afinal[2], double a2final[2]) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode == 0) return fail(ctx, SGPU_ESTATE, "sgpu_finalize: nothing staged");
+    if (!d_partial || !atfinal || !afinal || !a2final) return fail(ctx, SGPU_EINVAL, "sgpu_finalize: NULL argument");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure<double2>(ctx, &ctx->d_out, &ctx->out_cap, ctx->NF);
+    if (rc) return rc;
+    rc = ensure_work(ctx, corr_work_bytes(&ctx->plan, 1));
+    if (rc) return rc;
+    const bool conj = (dsp_type == SGPU_DSP_AUTOCORRELATE && dsp_method == SGPU_METHOD_DIRECT);
+    const double *acc;
+    if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
+        ctx->launches += corr_finalize(&ctx->plan, d_partial, ctx->d_work, ctx->d_out, scale, conj ? 1 : 0, ctx->stream);
+        acc = d_partial + ctx->plan.L;
+    } else {
+        ctx->launches += launch_scale_complex(reinterpret_cast<const double2 *>(d_partial), ctx->d_out, ctx->NF, scale,
+                                              ctx->stream);
+        acc = d_partial + 2 * ctx->NF;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_acc, acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(atfinal, ctx->d_out, ctx->NF * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    afinal[0] = ctx->h_acc[0] * scale;
+    afinal[1] = (conj ? -ctx->h_acc[1] : ctx->h_acc[1]) * scale;
+    a2final[0] = ctx->h_acc[2] * scale;
+    a2final[1] = 0.0;
+    return SGPU_OK;
+}
+
+int sgpu_compute_all_vectors(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, int dsp_method,
+                             double *atfinal, double afinal[2], double a2final[2]) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors: frames are not staged (stage_frames first)");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors: No qvectors left to compute");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure_internal_partial(ctx, dsp_type);
+    if (rc) return rc;
+    rc = sgpu_compute_all_vectors_partial(ctx, qvecs, NM, dsp_type, ctx->d_partial);
+    if (rc) return rc;
+    return sgpu_finalize(ctx, ctx->d_partial, dsp_type, dsp_method, 1.0 / (double)NM, atfinal, afinal, a2final);
+}
+
+int sgpu_compute_self_vectors(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, int dsp_method,
+                              double *atfinal, double afinal[2], double a2final[2]) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode != 2) return fail(ctx, SGPU_ESTATE, "sgpu_compute_self_vectors: atoms are not staged (stage_atoms first)");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_self_vectors: No qvectors left to compute");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure_internal_partial(ctx, dsp_type);
+    if (rc) return rc;
+    rc = sgpu_compute_self_vectors_partial(ctx, qvecs, NM, dsp_type, ctx->d_partial);
+    if (rc) return rc;
+    return sgpu_finalize(ctx, ctx->d_partial, dsp_type, dsp_method, 1.0 / (double)NM, atfinal, afinal, a2final);
+}
+
+int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type, int dsp_method,
+                          double *atfinal, double afinal[2], double a2final[2]) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: frames are not staged (stage_frames first)");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: No moments to compute");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure_internal_partial(ctx, dsp_type);
+    if (rc) return rc;
+    rc = sgpu_compute_mpsphere_partial(ctx, qlen, lm, NM, dsp_type, ctx->d_partial);
+    if (rc) return rc;
+    const double scale = 1.0 / (4.0 * 3.14159265358979323846);  // multipole_scatter_device.cpp:395
+    return sgpu_finalize(ctx, ctx->d_partial, dsp_type, dsp_method, scale, atfinal, afinal, a2final);
+}
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+
+int sgpu_get_amplitudes(sgpu_ctx *ctx, double *A, size_t NM, size_t NF) {
+    if (!ctx || !A) return SGPU_EINVAL;
+    if (ctx->A_NM == 0 || NM != ctx->A_NM || NF != ctx->NF)
+        return fail(ctx, SGPU_ESTATE, "sgpu_get_amplitudes: no matching amplitudes from the last compute");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(A, ctx->d_A, NM * NF * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_last_amplitude_ms(sgpu_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return SGPU_EINVAL;
+    if (!ctx->have_times) return fail(ctx, SGPU_ESTATE, "no compute has run yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev2));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return SGPU_OK;
+}
+
+int sgpu_last_dsp_ms(sgpu_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return SGPU_EINVAL;
+    if (!ctx->have_times) return fail(ctx, SGPU_ESTATE, "no compute has run yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev2));
+    CK(cudaEventElapsedTime(ms, ctx->ev1, ctx->ev2));
+    return SGPU_OK;
+}
+
+int sgpu_measure_fp64_peak(sgpu_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    double *sink = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void **>(&sink), 64));
+    const int blocks = prop.multiProcessorCount * 8;
+    double best = 0.0;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(a, ctx->stream));
+        const double flops = launch_fp64_peak(sink, 20000, blocks, ctx->stream);
+        ctx->launches++;
+        CK(cudaEventRecord(b, ctx->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops = best;
+    return SGPU_OK;
+}
+
+int sgpu_synth_trajectory(sgpu_ctx *ctx, float *d_xyz, size_t NF, size_t NA, size_t atom0, size_t atom_stride,
+                          size_t NA_out, float box, float offset, float step_scale, uint64_t seed, int layout) {
+    if (!ctx || !d_xyz) return SGPU_EINVAL;
+    if (layout != 0 && layout != 1) return fail(ctx, SGPU_EINVAL, "sgpu_synth_trajectory: layout must be 0 or 1");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches += launch_synth_trajectory(d_xyz, NF, NA, atom0, atom_stride, NA_out, box, offset, step_scale, seed,
+                                             layout, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
+}  // extern "C"

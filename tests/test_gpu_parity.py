@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+
+Tolerance: BASELINE.json north_star — 1e-9 relative on fq / fqt (checked norm-wise, see util.rel_err).
+"""
+import numpy as np
+import pytest
+
+from sassena_b200 import synth
+from util import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def small_case(NA=1000, NF=100, NM=100, seed=1, box=30.0, sigma=0.1):
+    xyz = synth.trajectory(NF, NA, box, sigma, seed)
+    b = synth.factors(NA)
+    u = synth.unit_vectors(NM, seed + 1)
+    return xyz, b, u
+
+
+def test_synth_trajectory_twin(gpu_ctx):
+    """device generator == numpy twin, bit for bit, in both layouts and for strided atom subsets"""
+    NF, NA = 37, 301
+    ref = synth.trajectory(NF, NA, 30.0, 0.1, 11)
+    d = gpu_ctx.device_alloc(ref.nbytes)
+    try:
+        gpu_ctx.synth_trajectory(d, NF, NA, 30.0, 0.1, 11, layout=0)
+        got = np.empty_like(ref)
+        gpu_ctx.memcpy_d2h(got, d)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        gpu_ctx.synth_trajectory(d, NF, NA, 30.0, 0.1, 11, layout=1)
+        got1 = np.empty((NA, NF, 3), dtype=np.float32)
+        gpu_ctx.memcpy_d2h(got1, d)
+        assert np.array_equal(got1, ref.transpose(1, 0, 2))
+        # atoms 2, 7, 12, ... (ModAssignment style subset), offset box
+        atoms = np.arange(2, NA, 5)
+        ref2 = synth.trajectory(NF, NA, 30.0, 0.1, 11, atoms=atoms, offset=-15.0, layout=1)
+        gpu_ctx.synth_trajectory(d, NF, NA, 30.0, 0.1, 11, layout=1, atom0=2, atom_stride=5, NA_out=len(atoms),
+                                 offset=-15.0)
+        got2 = np.empty_like(ref2)
+        gpu_ctx.memcpy_d2h(got2, d)
+        assert np.array_equal(got2, ref2)
+    finally:
+        gpu_ctx.device_free(d)
+
+
+def test_amplitudes_config1(gpu_ctx, oracle):
+    """K1 amplitudes A[m][f] vs all_vectors_scatter_device.cpp:418-438 on BASELINE config 1 (one |q|)."""
+    xyz, b, u = small_case()
+    q = 1.3 * u
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    gpu_ctx.compute_all_vectors(q)
+    A = gpu_ctx.get_amplitudes(len(q))
+    *_, Aref = oracle.compute_all_vectors(xyz, b, q, return_amplitudes=True, nthreads=4)
+    assert rel_err(A, Aref) < 1e-12
+
+
+@pytest.mark.parametrize("dsp,method", [("autocorrelate", "fftw"), ("autocorrelate", "direct"), ("square", "fftw"),
+                                        ("plain", "fftw")])
+def test_all_vectors_config1(gpu_ctx, oracle, dsp, method):
+    """BASELINE config 1: 1k atoms, 100 frames, 10 |q| x 100 vectors, coherent fq/fq0/fq2/fqt."""
+    xyz, b, u = small_case()
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    qls = synth.qlengths(0.2, 2.0, 10)
+    nq = 10 if (dsp, method) == ("autocorrelate", "fftw") else 2
+    for ql in qls[:nq]:
+        q = oracle.init_subvectors("sphere", [ql, 0, 0], u)
+        fqt, fq, fq2 = gpu_ctx.compute_all_vectors(q, dsp=dsp, method=method)
+        rfqt, rfq, rfq2 = oracle.compute_all_vectors(xyz, b, q, dsp=dsp, method=method, nthreads=4)
+        assert rel_err(fqt, rfqt) < TOL
+        assert abs(fq - rfq) < TOL * abs(rfqt[0])
+        assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+        assert fqt[0] == pytest.approx(rfqt[0], rel=TOL)  # fq0
+        # observed accuracy is far better than the contract
+        assert rel_err(fqt, rfqt) < 1e-11
+
+
+@pytest.mark.parametrize("NF", [1, 2, 3, 5, 64, 100, 129, 257, 1000])
+def test_all_vectors_frame_counts(gpu_ctx, oracle, NF):
+    """ragged / odd / power-of-two frame counts (zero padding 2NF -> L)"""
+    NA, NM = 60, 7
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3)
+    b = synth.factors(NA)
+    q = 0.9 * synth.unit_vectors(NM, 5)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors(q)
+    rfqt, rfq, rfq2 = oracle.compute_all_vectors(xyz, b, q)
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+    assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
+@pytest.mark.parametrize("NA,NM", [(1, 1), (31, 8), (33, 9), (64, 64), (65, 65), (2000, 130)])
+def test_all_vectors_ragged_atoms_vectors(gpu_ctx, oracle, NA, NM):
+    """atom counts around the warp size, vector counts around the q-block (8) and CTA (64) sizes"""
+    NF = 20
+    xyz = synth.trajectory(NF, NA, 25.0, 0.3, 7)
+    b = synth.factors(NA)
+    q = 2.1 * synth.unit_vectors(NM, 8)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors(q)
+    A = gpu_ctx.get_amplitudes(NM)
+    rfqt, rfq, rfq2, Aref = oracle.compute_all_vectors(xyz, b, q, return_amplitudes=True)
+    assert rel_err(A, Aref) < 1e-12
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+
+
+def test_large_phase_arguments(gpu_ctx, oracle):
+    """|q.r| of several thousand radians: the range reduction must hold its accuracy"""
+    NF, NA, NM = 8, 500, 16
+    xyz = synth.trajectory(NF, NA, 2000.0, 1.0, 21, offset=-1000.0)
+    b = synth.factors(NA)
+    q = 5.0 * synth.unit_vectors(NM, 22)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    gpu_ctx.compute_all_vectors(q, dsp="plain")
+    A = gpu_ctx.get_amplitudes(NM)
+    *_, Aref = oracle.compute_all_vectors(xyz, b, q, dsp="plain", return_amplitudes=True)
+    # the reference's own rounding of p=x*qx+y*qy+z*qz (no FMA) is ~1e-12 rad here; stay well under 1e-9
+    assert np.max(np.abs(A - Aref)) / (np.abs(b).sum()) < 1e-11
+
+
+@pytest.mark.parametrize("dsp,method", [("autocorrelate", "fftw"), ("autocorrelate", "direct"), ("square", "fftw"),
+                                        ("plain", "fftw")])
+def test_self_vectors_small(gpu_ctx, oracle, dsp, method):
+    """incoherent self scattering, per-atom timelines (self_vectors_scatter_device.cpp:145-239)"""
+    NA, NF, NM = 40, 100, 12
+    xyz = synth.trajectory(NF, NA, 30.0, 0.1, 3, layout=1)
+    b = synth.factors(NA)
+    q = 1.1 * synth.unit_vectors(NM, 4)
+    gpu_ctx.stage_atoms(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_self_vectors(q, dsp=dsp, method=method)
+    rfqt, rfq, rfq2 = oracle.compute_self_vectors(xyz, b, q, dsp=dsp, method=method, nthreads=4)
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+    assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
+def test_self_from_frames_modassignment(gpu_ctx, oracle):
+    """frame-major input transposed on the GPU for the atoms of rank r under ModAssignment(NN, r, NA);
+    the sum of the per-rank partials equals the single-rank result (self...:199-230 reduce)."""
+    NA, NF, NM, NN = 23, 50, 5, 3
+    frames = synth.trajectory(NF, NA, 30.0, 0.1, 9)
+    b = synth.factors(NA)
+    q = 0.7 * synth.unit_vectors(NM, 10)
+    plen = None
+    total = None
+    for r in range(NN):
+        gpu_ctx.stage_atoms_from_frames(frames, NN, r)
+        off, size, _ = oracle.mod_assignment(NN, r, NA)
+        assert gpu_ctx.NA == size
+        ids = off + NN * np.arange(size)
+        gpu_ctx.set_factors(b[ids])
+        plen = gpu_ctx.partial_len("autocorrelate")
+        d = gpu_ctx.device_alloc(plen * 8)
+        gpu_ctx.compute_self_vectors_partial(q, d)
+        gpu_ctx.synchronize()
+        part = np.empty(plen)
+        gpu_ctx.memcpy_d2h(part, d)
+        gpu_ctx.device_free(d)
+        total = part if total is None else total + part
+    d = gpu_ctx.device_alloc(plen * 8)
+    gpu_ctx.memcpy_h2d(d, total)
+    fqt, fq, fq2 = gpu_ctx.finalize(d, 1.0 / NM)
+    gpu_ctx.device_free(d)
+    rfqt, rfq, rfq2 = oracle.compute_self_vectors(frames.transpose(1, 0, 2), b, q)
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+    assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
+def test_all_vectors_sharded_equals_single(gpu_ctx, oracle):
+    """KA6: q-vector sharding over k logical GPUs (DivAssignment of the NM subvectors) + summed partials
+    == single-GPU result to 1e-12, == oracle to 1e-9."""
+    xyz, b, u = small_case(NA=300, NF=64, NM=50)
+    q = 1.7 * u
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    single = gpu_ctx.compute_all_vectors(q)
+    for dsp in ("autocorrelate", "square"):
+        single = gpu_ctx.compute_all_vectors(q, dsp=dsp)
+        plen = gpu_ctx.partial_len(dsp)
+        d = gpu_ctx.device_alloc(plen * 8)
+        total = np.zeros(plen)
+        for r in range(4):
+            off, size, _ = oracle.div_assignment(4, r, len(q))
+            gpu_ctx.compute_all_vectors_partial(q[off:off + size], d, dsp=dsp)
+            gpu_ctx.synchronize()
+            part = np.empty(plen)
+            gpu_ctx.memcpy_d2h(part, d)
+            total += part
+        gpu_ctx.memcpy_h2d(d, total)
+        fqt, fq, fq2 = gpu_ctx.finalize(d, 1.0 / len(q), dsp=dsp)
+        gpu_ctx.device_free(d)
+        assert rel_err(fqt, single[0]) < 1e-12
+        assert abs(fq - single[1]) < 1e-12 * abs(single[0][0])
+        rfqt, rfq, rfq2 = oracle.compute_all_vectors(xyz, b, q, dsp=dsp)
+        assert rel_err(fqt, rfqt) < TOL
+
+
+@pytest.mark.parametrize("dsp", ["autocorrelate", "square"])
+def test_mpsphere_small(gpu_ctx, oracle, dsp):
+    """multipole sphere moments (multipole_scatter_device.cpp:428-498), L=6, cartesian input converted on the GPU"""
+    NA, NF, L = 300, 16, 6
+    xyz = synth.trajectory(NF, NA, 40.0, 0.3, 13, offset=-20.0)
+    b = synth.factors(NA)
+    mom = oracle.moments_sphere(L)
+    sph = oracle.cart_to_spherical(xyz)
+    for ql in (0.05, 0.4, 1.5):
+        gpu_ctx.stage_frames(xyz)
+        gpu_ctx.frames_to_spherical()
+        gpu_ctx.set_factors(b)
+        fqt, fq, fq2 = gpu_ctx.compute_mpsphere(ql, mom, dsp=dsp)
+        A = gpu_ctx.get_amplitudes(len(mom))
+        rfqt, rfq, rfq2, Aref = oracle.compute_mpsphere(sph, b, ql, mom, dsp=dsp, nthreads=4, return_amplitudes=True)
+        assert rel_err(A, Aref) < 1e-9
+        assert rel_err(fqt, rfqt) < TOL
+        assert abs(fq - rfq) < TOL * abs(rfqt[0])
+        assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
+def test_mpsphere_resolution20_staged_spherical(gpu_ctx, oracle):
+    """default multipole.moments.resolution=20 (441 moments), input staged already in (r,phi,theta)"""
+    NA, NF = 150, 6
+    xyz = synth.trajectory(NF, NA, 60.0, 0.3, 15, offset=-30.0)
+    b = synth.factors(NA)
+    mom = oracle.moments_sphere(20)
+    sph = oracle.cart_to_spherical(xyz)
+    from sassena_b200 import REPR_SPHERICAL
+    gpu_ctx.stage_frames(sph, repr=REPR_SPHERICAL)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_mpsphere(0.3, mom, dsp="square")
+    rfqt, rfq, rfq2 = oracle.compute_mpsphere(sph, b, 0.3, mom, dsp="square", nthreads=8)
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+
+
+def test_known_answers(gpu_ctx):
+    """KA1/KA2 of SURVEY 8c: single static atom -> fqt = b^2, fq = b^2, fq2 = b^4; single atom in linear
+    motion, no orientational average -> fftw: b^2 e^{+i q.v tau}, direct: conjugate."""
+    NF = 50
+    b = np.array([6.65])
+    xyz = np.tile(np.array([[1.5, -2.0, 0.25]], dtype=np.float32), (NF, 1, 1))
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors(np.array([[0.3, 0.1, -0.7]]))
+    assert np.allclose(fqt, b[0] ** 2, rtol=1e-12, atol=0)
+    assert fq == pytest.approx(b[0] ** 2, rel=1e-12)
+    assert fq2 == pytest.approx(b[0] ** 4, rel=1e-12)
+    # linear motion along x with exactly representable steps
+    v = 0.125
+    xyz = np.zeros((NF, 1, 3), dtype=np.float32)
+    xyz[:, 0, 0] = v * np.arange(NF)
+    q = np.array([[0.8, 0.0, 0.0]])
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    tau = np.arange(NF)
+    fqt, _, _ = gpu_ctx.compute_all_vectors(q, method="fftw")
+    assert np.allclose(fqt, b[0] ** 2 * np.exp(1j * 0.8 * v * tau), rtol=0, atol=1e-11 * b[0] ** 2)
+    fqt, _, _ = gpu_ctx.compute_all_vectors(q, method="direct")
+    assert np.allclose(fqt, b[0] ** 2 * np.exp(-1j * 0.8 * v * tau), rtol=0, atol=1e-11 * b[0] ** 2)
+
+
+def test_two_atom_debye(gpu_ctx, oracle):
+    """KA3: two static atoms at distance d; sphere average -> b1^2+b2^2+2 b1 b2 sin(qd)/(qd).
+    The multipole expansion (L=14) reproduces it to the accuracy the reference's float32 (r,phi,theta) staging
+    allows (~1e-7, data_stager.cpp:111-113); 4000 random vectors agree within Monte-Carlo error."""
+    d, ql = 3.0, 1.1
+    b = np.array([2.0, 3.5])
+    xyz = np.zeros((4, 2, 3), dtype=np.float32)
+    xyz[:, 0] = (0.5, 0.25, -0.125)
+    xyz[:, 1] = (0.5, 0.25 + d, -0.125)
+    exact = b[0] ** 2 + b[1] ** 2 + 2 * b[0] * b[1] * np.sin(ql * d) / (ql * d)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.frames_to_spherical()
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_mpsphere(ql, oracle.moments_sphere(14), dsp="square")
+    assert fqt[0].real == pytest.approx(exact, rel=1e-6)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, _, _ = gpu_ctx.compute_all_vectors(ql * synth.unit_vectors(4000, 3), dsp="square")
+    assert fqt[0].real == pytest.approx(exact, rel=0.05)
+
+
+def test_error_paths(gpu_ctx):
+    """C-ABI error behaviour mirrors the reference's Err::write+throw sites, as return codes."""
+    import sassena_b200
+    ctx = sassena_b200.ScatterContext(0)
+    with pytest.raises(sassena_b200.SgpuError) as e:
+        ctx.compute_all_vectors(np.ones((1, 3)))  # nothing staged
+    assert e.value.code == 3
+    xyz, b, u = small_case(NA=10, NF=4, NM=2)
+    ctx.stage_frames(xyz)
+    with pytest.raises(sassena_b200.SgpuError):
+        ctx.compute_all_vectors(u)  # factors missing
+    ctx.set_factors(b)
+    with pytest.raises(sassena_b200.SgpuError) as e:
+        ctx.compute_all_vectors(u, dsp=7)  # "DSP type not understood"
+    assert e.value.code == 1 and "DSP type not understood" in e.value.msg
+    with pytest.raises(sassena_b200.SgpuError) as e:
+        ctx.compute_all_vectors(u, method=5)
+    assert "Correlation method not understood" in e.value.msg
+    with pytest.raises(sassena_b200.SgpuError) as e:
+        ctx.compute_mpsphere(1.0, [[1, 2]])  # frames not spherical
+    ctx.frames_to_spherical()
+    with pytest.raises(sassena_b200.SgpuError) as e:
+        ctx.compute_mpsphere(1.0, [[1, 2]])  # |m| > l
+    assert "Combination of Major and minor moment not allowed" in e.value.msg
+    with pytest.raises(sassena_b200.SgpuError):
+        ctx.compute_self_vectors(u)  # atoms not staged
+    ctx.close()
+
+
+def test_launch_counter_and_timers(gpu_ctx):
+    xyz, b, u = small_case(NA=100, NF=16, NM=8)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    n0 = gpu_ctx.launch_count
+    gpu_ctx.compute_all_vectors(u)
+    assert gpu_ctx.launch_count > n0
+    assert gpu_ctx.last_amplitude_ms() > 0
+    assert gpu_ctx.last_dsp_ms() > 0
