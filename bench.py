@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Sassena scattering hot path on B200.
+
+Metric (BASELINE.json): amplitude evaluations/s, one evaluation = one (atom, frame, q-vector) triple, plus the
+F(q,t) wall time it implies.  Workload (default): BASELINE configs[2] "coherent F(q,t): 100k atoms x 10k frames,
+50 |q| x 500 sphere vectors" — the configuration north_star's Target sentence is quoted on; it fits one GPU
+(12 GB of coordinates).  A STEP is one compute() of the reference's runner loop
+(abstract_scatter_device.cpp:162-173): one |q| with its 500 orientation vectors over the full trajectory,
+i.e. amplitudes -> FFT autocorrelation -> orientational average -> fqt/fq/fq2 for that |q| (5e11 evaluations).
+
+N GPUs: one process per GPU (torchrun), coordinates replicated, the 500 subvectors of the step sharded with
+DivAssignment, per-rank packed partials summed with ONE NCCL all-reduce per step, finalize on every rank
+("strong" scaling: total work per step is fixed).
+
+`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's loops; the reference
+itself cannot be built in this image) on all host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FLOP_PER_EVAL = 45.0        # algorithmic FP64 flop per amplitude evaluation
+FP64_INSTR_PER_EVAL = 21.0  # what the kernel executes (sincos_qt.cuh)
+
+WORKLOADS = {
+    # name: (config key in sassena_b200.synth.CONFIGS, description)
+    "C3": "coherent F(q,t): 100k atoms x 10k frames, 50 |q| x 500 sphere vectors (one |q| per step)",
+    "C1": "synthetic 1k-atom box, 100 frames, 10 |q| x 100 sphere vectors, coherent (one |q| per step)",
+}
+
+
+def div_assignment(NN, rank, N):
+    """DivAssignment (reference src/decomposition/assignment.cpp:27-35)."""
+    first = (rank * N) // NN
+    nxt = ((rank + 1) * N) // NN
+    return first, nxt - first
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.p = None
+        self.path = f"/tmp/bench_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        try:
+            self.p.terminate()
+            self.p.wait(timeout=5)
+            self.f.close()
+            sm, smax, power = [], [], []
+            reasons = set()
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    smax.append(float(c[2]))
+                    power.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                       "samples": len(sm), "power_w_max": max(power)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def cpu_sample_shape(cfg, cores, target_core_seconds, evals_per_core_s=2.4e7):
+    """bounded CPU sample of the workload: all atoms, first NF_s frames, NM_s subvectors of one |q|"""
+    NA = cfg["NA"]
+    NM_s = min(cfg["NM"], 4 * cores)
+    NM_s = max(cores, (NM_s // cores) * cores)
+    evals = evals_per_core_s * cores * target_core_seconds
+    NF_s = int(max(16, min(cfg["NF"], evals / (NA * NM_s))))
+    return NF_s, NM_s
+
+
+def run_cpu_oracle(cfg, NF_s, NM_s, ql, threads, coords=None):
+    from oracle import oracle as o
+    from sassena_b200 import synth
+    o.build()
+    if coords is None:
+        coords = synth.trajectory(NF_s, cfg["NA"], cfg["box"], cfg["sigma"], cfg["seed"])
+    b = synth.factors(cfg["NA"])
+    u = synth.unit_vectors(cfg["NM"], cfg["vseed"])[:NM_s]
+    q = ql * u
+    t0 = time.perf_counter()
+    res = o.compute_all_vectors(coords, b, q, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return dt, res, coords
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores (oracle port; rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import oracle as o
+    from sassena_b200 import synth
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames:
+        cfg["NF"] = args.frames
+    if args.atoms:
+        cfg["NA"] = args.atoms
+    cores = o.max_threads()
+    NF_s, NM_s = cpu_sample_shape(cfg, cores, args.cpu_seconds)
+    qls = synth.qlengths(*cfg["q"])
+    coords = synth.trajectory(NF_s, cfg["NA"], cfg["box"], cfg["sigma"], cfg["seed"])
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _, _ = run_cpu_oracle(cfg, NF_s, NM_s, qls[i % len(qls)], cores, coords)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    evals = float(cfg["NA"]) * NF_s * NM_s * len(times)
+    value = evals / total
+    sample = (f"{cfg['NA']} atoms x first {NF_s} frames x {NM_s} of {cfg['NM']} subvectors of one |q| per step "
+              f"(amplitudes + FFT autocorrelation + store), {cores} OpenMP threads over subvectors")
+    line = {
+        "impl": "reference", "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "NA": cfg["NA"], "NF": cfg["NF"], "NM": cfg["NM"],
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sassena_b200
+    from sassena_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames:
+        cfg["NF"] = args.frames
+    if args.atoms:
+        cfg["NA"] = args.atoms
+    NA, NF, NM = cfg["NA"], cfg["NF"], cfg["NM"]
+    qls = synth.qlengths(*cfg["q"])
+    b = synth.factors(NA)
+    u = synth.unit_vectors(NM, cfg["vseed"])
+    m_off, m_cnt = div_assignment(world, rank, NM)
+
+    ctx = sassena_b200.ScatterContext(local_rank)
+    fp64_peak = ctx.measure_fp64_peak()
+
+    # synthetic trajectory generated on the device (CPU twin: sassena_b200/synth.py), resident in HBM
+    xyz = torch.empty(NF * NA * 3, dtype=torch.float32, device=dev)
+    ctx.synth_trajectory(xyz.data_ptr(), NF, NA, cfg["box"], cfg["sigma"], cfg["seed"])
+    ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
+    ctx.set_factors(b)
+    plen = ctx.partial_len("autocorrelate")
+    partial = torch.zeros(plen, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def step(i):
+        q = qls[i % len(qls)] * u[m_off:m_off + m_cnt]
+        ctx.compute_all_vectors_partial(q, partial.data_ptr())
+        if world > 1:
+            ctx.synchronize()
+            dist.all_reduce(partial)
+            torch.cuda.synchronize()
+        return ctx.finalize(partial.data_ptr(), 1.0 / NM)
+
+    # ---- device-resident measurement ----
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = ctx.launch_count
+    amp_ms = 0.0
+    dsp_ms = 0.0
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = step(args.warmup + i)
+        amp_ms += ctx.last_amplitude_ms()
+        dsp_ms += ctx.last_dsp_ms()
+    ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, amp_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, amp_ms_max = float(t[0]), float(t[1])
+    evals_step = float(NA) * NF * NM
+    value = evals_step * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end: host buffers in, host results out, every step ----
+    e2e = None
+    if not args.no_e2e:
+        f_off, f_cnt = div_assignment(world, rank, NF)
+        host = ctx.pinned((f_cnt, NA, 3), np.float32)  # this rank's slice of the trajectory, pinned
+        ctx.memcpy_d2h(host.array, xyz.data_ptr() + f_off * NA * 12)
+        slice_dev = torch.empty(f_cnt * NA * 3, dtype=torch.float32, device=dev) if world > 1 else None
+        equal = all(div_assignment(world, r, NF)[1] == f_cnt for r in range(world))
+
+        def e2e_step(i):
+            q = qls[i % len(qls)] * u[m_off:m_off + m_cnt]
+            if world == 1:
+                # stager: chunked async H2D on the copy stream; the amplitude launches wait per chunk
+                ctx.stage_frames(host.array)
+                ctx.set_factors(b)
+                ctx.compute_all_vectors_partial(q, partial.data_ptr())
+            else:
+                # DataStagerByFrame: every rank loads its DivAssignment slice from the host, the slices are
+                # replicated over NVLink (the reference's stage_fillpartitions broadcast, data_stager.cpp:102-118)
+                ctx.memcpy_h2d(slice_dev.data_ptr(), host.array)
+                if equal:
+                    dist.all_gather_into_tensor(xyz, slice_dev)
+                else:
+                    parts = [xyz[div_assignment(world, r, NF)[0] * NA * 3:(sum(div_assignment(world, r, NF))) * NA * 3]
+                             for r in range(world)]
+                    dist.all_gather(parts, slice_dev)
+                torch.cuda.synchronize()
+                ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
+                ctx.set_factors(b)
+                ctx.compute_all_vectors_partial(q, partial.data_ptr())
+                ctx.synchronize()
+                dist.all_reduce(partial)
+                torch.cuda.synchronize()
+            return ctx.finalize(partial.data_ptr(), 1.0 / NM)
+
+        for i in range(min(args.warmup, 2)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            res_e2e = e2e_step(args.warmup + i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0])
+        e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
+               "h2d_bytes_per_step": int(f_cnt * NA * 12 + NA * 8 + m_cnt * 24),
+               "d2h_bytes_per_step": int(NF * 16 + 32),
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "note": ("coordinates re-staged from pinned host memory every step (chunked async H2D overlapped "
+                        "with the amplitude kernel)" if world == 1 else
+                        "every rank H2D's its frame slice each step, slices all-gathered over NVLink, then compute")}
+        # restore the resident staging for anything that follows
+        ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
+        ctx.set_factors(b)
+        host.free()
+
+    # ---- CPU baseline + parity on a bounded sample (rank 0, N=1) ----
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as o
+        cores = o.max_threads()
+        NF_s, NM_s = cpu_sample_shape(cfg, cores, args.cpu_seconds)
+        coords = np.empty((NF_s, NA, 3), dtype=np.float32)
+        ctx.memcpy_d2h(coords, xyz.data_ptr())
+        ql = qls[len(qls) // 2]
+        dt, (rfqt, rfq, rfq2), _ = run_cpu_oracle(cfg, NF_s, NM_s, ql, cores, coords)
+        sample = (f"{NA} atoms x first {NF_s} frames x {NM_s} of {NM} subvectors of one |q| "
+                  f"(amplitudes + FFT autocorrelation + store), {cores} OpenMP threads over subvectors")
+        cpu_baseline = {"value": float(NA) * NF_s * NM_s / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                        "sample": sample, "seconds": dt}
+        ctx.stage_frames_device(xyz.data_ptr(), NF_s, NA)
+        ctx.set_factors(b)
+        fqt, fq, fq2 = ctx.compute_all_vectors(ql * u[:NM_s])
+        parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
+                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9, "vs": "oracle on the CPU sample"}
+        ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
+        ctx.set_factors(b)
+
+    if rank == 0:
+        amp_s = amp_ms_max * 1e-3
+        evals_rank = float(NA) * NF * div_assignment(world, 0, NM)[1] * args.steps
+        achieved = evals_rank * FLOP_PER_EVAL / amp_s / 1e12
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NF": NF, "NM_per_q": NM, "NQ": len(qls),
+                       "step": "one |q| (compute() of the runner loop): amplitudes + FFT autocorrelation + average",
+                       "parallelism": f"q-vector shard x{world}" if world > 1 else "single GPU",
+                       "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
+            "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": traffic,
+                         "kernel": "amplitude_all_kernel", "kernel_share_of_step": amp_ms_max / ms_max,
+                         "algorithmic_flop_per_eval": FLOP_PER_EVAL,
+                         "fp64_pipe_util_executed": evals_rank * FP64_INSTR_PER_EVAL * 2 / amp_s / 1e12 / fp64_peak,
+                         "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry"},
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity": parity,
+            "host_wall_ms_per_step": wall_ms / args.steps,
+            "dsp_ms_per_step": dsp_ms / args.steps,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="override NF (debug; changes the workload)")
+    ap.add_argument("--atoms", type=int, default=0, help="override NA (debug; changes the workload)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle sample, seconds per core")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 3) if not args.frames else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -136,6 +136,10 @@ int sgpu_get_amplitudes(sgpu_ctx *ctx, double *A, size_t NM, size_t NF);
 int sgpu_last_amplitude_ms(sgpu_ctx *ctx, float *ms);
 /* Time of the DSP (correlation/reduction) kernels of the last compute call, in ms. */
 int sgpu_last_dsp_ms(sgpu_ctx *ctx, float *ms);
+/* CUDA-event stopwatch on the compute stream: start records an event, stop records another, waits for it and
+ * returns the elapsed device time in ms (used by bench.py to time whole steps on the device). */
+int sgpu_timer_start(sgpu_ctx *ctx);
+int sgpu_timer_stop(sgpu_ctx *ctx, float *ms);
 /* Dependency-free DFMA microbenchmark over all SMs: measured FP64 peak in TFLOP/s (FMA = 2 flop). */
 int sgpu_measure_fp64_peak(sgpu_ctx *ctx, double *tflops);
 /* Fill device coordinates with the synthetic random-walk trajectory of tests/bench (counter-based

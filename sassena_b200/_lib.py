@@ -48,6 +48,8 @@ SIGNATURES = {
     "sgpu_get_amplitudes": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_size_t]),
     "sgpu_last_amplitude_ms": (C.c_int, [C.c_void_p, c_float_p]),
     "sgpu_last_dsp_ms": (C.c_int, [C.c_void_p, c_float_p]),
+    "sgpu_timer_start": (C.c_int, [C.c_void_p]),
+    "sgpu_timer_stop": (C.c_int, [C.c_void_p, c_float_p]),
     "sgpu_measure_fp64_peak": (C.c_int, [C.c_void_p, c_double_p]),
     "sgpu_synth_trajectory": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_int]),
     "sgpu_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

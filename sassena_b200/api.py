@@ -225,6 +225,14 @@ class ScatterContext:
         self._ck(self.lib.sgpu_last_dsp_ms(self.h, C.byref(v)))
         return float(v.value)
 
+    def timer_start(self):
+        self._ck(self.lib.sgpu_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        v = C.c_float()
+        self._ck(self.lib.sgpu_timer_stop(self.h, C.byref(v)))
+        return float(v.value)
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         self._ck(self.lib.sgpu_measure_fp64_peak(self.h, C.byref(v)))

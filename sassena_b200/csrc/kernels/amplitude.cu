@@ -11,6 +11,8 @@
 #include "kernels.hpp"
 #include "sincos_qt.cuh"
 
+#include <cstdlib>
+
 namespace sass {
 
 namespace {
@@ -79,6 +81,271 @@ __global__ void __launch_bounds__(WARPS * 32) amplitude_all_kernel(
 #pragma unroll
         for (int k = 0; k < QPT; k++)
             if (m0 + k < NM) A[(size_t)(m0 + k) * ldA + frame] = make_double2(re[k], im[k]);
+    }
+}
+
+// ---- K1, tiled variant: TMA bulk-staged atom tiles + mbarrier ring --------------------------------------
+// Same mapping as above (CTA = one frame x WARPS*QPT q-vectors) but the atoms of the frame stream through a
+// STAGES-deep shared-memory ring of TILE-atom tiles ([TILE][3] floats + [TILE] doubles of b).  One elected
+// thread issues two cp.async.bulk (TMA, 1-D) copies per tile that complete on the tile's "full" mbarrier; a
+// warp's lane 0 arrives on the tile's "empty" mbarrier when the warp is done with it.  All WARPS warps consume
+// the same tile, so every coordinate is fetched from L2/HBM once per CTA and the consumer side sees ~30-cycle
+// LDS latency instead of global-load latency.  Frames whose byte offset is not 16-byte aligned (NA % 4 != 0)
+// use 4-byte cp.async (LDGSTS) by all threads on the same barriers (cp.async.mbarrier.arrive.noinc).
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace ptx
+
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
+    const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs,
+    double2 *__restrict__ A, size_t ldA, int NA, int NM, unsigned ngroups, size_t f0, int use_bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_xyz = reinterpret_cast<float *>(smem_raw);                                     // [STAGES][TILE*3]
+    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);     // [STAGES][TILE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8));
+    uint64_t *empty = full + STAGES;
+
+    const unsigned group = blockIdx.x % ngroups;
+    const size_t frame = f0 + blockIdx.x / ngroups;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = (group * WARPS + warp) * QPT;
+    const float *p = xyz + frame * (size_t)NA * 3;
+    const int ntiles = (NA + TILE - 1) / TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full[s], use_bulk ? 1u : (unsigned)(WARPS * 32));
+            ptx::mbar_init(&empty[s], (unsigned)WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {  // queue the load of tile t into its ring slot
+        const int s = t % STAGES;
+        const int a0 = t * TILE;
+        const int cnt = min(TILE, NA - a0);
+        if (use_bulk) {
+            if (tid == 0) {
+                if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+                ptx::mbar_expect_tx(&full[s], (unsigned)cnt * 20u);
+                ptx::bulk_g2s(s_xyz + (size_t)s * TILE * 3, p + (size_t)a0 * 3, (unsigned)cnt * 12u, &full[s]);
+                ptx::bulk_g2s(s_b + (size_t)s * TILE, b + a0, (unsigned)cnt * 8u, &full[s]);
+            }
+        } else {
+            if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+            float *dx = s_xyz + (size_t)s * TILE * 3;
+            const float *sx = p + (size_t)a0 * 3;
+            for (int i = tid; i < cnt * 3; i += WARPS * 32) ptx::cp_async4(dx + i, sx + i);
+            float *db = reinterpret_cast<float *>(s_b + (size_t)s * TILE);
+            const float *sb = reinterpret_cast<const float *>(b + a0);
+            for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
+            ptx::cp_async_mbar_arrive_noinc(&full[s]);
+        }
+    };
+
+    for (int t = 0; t < STAGES - 1 && t < ntiles; t++) issue(t);
+
+    const bool active = m0 < NM;
+    double qx[QPT], qy[QPT], qz[QPT], re[QPT], im[QPT];
+#pragma unroll
+    for (int k = 0; k < QPT; k++) {
+        qx[k] = __ldg(&qs[3 * (m0 + k)]);  // qs is zero padded to a multiple of WARPS*QPT
+        qy[k] = __ldg(&qs[3 * (m0 + k) + 1]);
+        qz[k] = __ldg(&qs[3 * (m0 + k) + 2]);
+        re[k] = 0.0;
+        im[k] = 0.0;
+    }
+
+    for (int t = 0; t < ntiles; t++) {
+        if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);
+        const int s = t % STAGES;
+        const int cnt = min(TILE, NA - t * TILE);
+        ptx::mbar_wait(&full[s], (unsigned)((t / STAGES) & 1));
+        if (active) {
+            const float *sx = s_xyz + (size_t)s * TILE * 3;
+            const double *sb = s_b + (size_t)s * TILE;
+#pragma unroll 1
+            for (int j = lane; j < cnt; j += 32) {
+                const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
+                const double bj = sb[j];
+#pragma unroll
+                for (int k = 0; k < QPT; k++) {
+                    const double u = fma(z, qz[k], fma(y, qy[k], x * qx[k]));
+                    sincos_qt_accumulate2<ABL>(u, bj, re[k], im[k]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    }
+    if (!active) return;
+#pragma unroll
+    for (int k = 0; k < QPT; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            re[k] += __shfl_xor_sync(0xffffffffu, re[k], o);
+            im[k] += __shfl_xor_sync(0xffffffffu, im[k], o);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < QPT; k++)
+            if (m0 + k < NM) A[(size_t)(m0 + k) * ldA + frame] = make_double2(re[k], im[k]);
+    }
+}
+
+// ---- K1, uniform-q variant -------------------------------------------------------------------------------
+// On B200 the FP64 pipe accepts one warp instruction every 2 cycles, but a DFMA whose three operands are all
+// distinct vector registers needs 3 register-file cycles (measured, tools/micro/fp64_micro.cu).  Here the whole
+// CTA works on the SAME QPT q-vectors, read from constant memory with a block-uniform index, so ptxas keeps them
+// in uniform registers / constant operands: the phase FMAs have two vector operands, 48 vector registers are
+// freed, and the WARPS warps split the atoms of every tile instead of the q-vectors.  A fixed-order shared-memory
+// reduction over the warps finishes the sum.
+constexpr int UQ_MAXQ = 2048;  // q-vectors per launch held in constant memory (48 KB)
+__constant__ double c_q[UQ_MAXQ * 3];
+
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_uq_kernel(
+    const float *__restrict__ xyz, const double *__restrict__ b, double2 *__restrict__ A, size_t ldA, int NA, int NM,
+    int m_base, unsigned ngroups, size_t f0, int use_bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_xyz = reinterpret_cast<float *>(smem_raw);
+    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8));
+    uint64_t *empty = full + STAGES;
+    double *s_red = reinterpret_cast<double *>(empty + STAGES);  // [WARPS][2*QPT]
+
+    const unsigned group = blockIdx.x % ngroups;
+    const size_t frame = f0 + blockIdx.x / ngroups;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mq = group * QPT;  // block-uniform index into c_q
+    const float *p = xyz + frame * (size_t)NA * 3;
+    const int ntiles = (NA + TILE - 1) / TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full[s], use_bulk ? 1u : (unsigned)(WARPS * 32));
+            ptx::mbar_init(&empty[s], (unsigned)WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int s = t % STAGES;
+        const int a0 = t * TILE;
+        const int cnt = min(TILE, NA - a0);
+        if (use_bulk) {
+            if (tid == 0) {
+                if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+                ptx::mbar_expect_tx(&full[s], (unsigned)cnt * 20u);
+                ptx::bulk_g2s(s_xyz + (size_t)s * TILE * 3, p + (size_t)a0 * 3, (unsigned)cnt * 12u, &full[s]);
+                ptx::bulk_g2s(s_b + (size_t)s * TILE, b + a0, (unsigned)cnt * 8u, &full[s]);
+            }
+        } else {
+            if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+            float *dx = s_xyz + (size_t)s * TILE * 3;
+            const float *sx = p + (size_t)a0 * 3;
+            for (int i = tid; i < cnt * 3; i += WARPS * 32) ptx::cp_async4(dx + i, sx + i);
+            float *db = reinterpret_cast<float *>(s_b + (size_t)s * TILE);
+            const float *sb = reinterpret_cast<const float *>(b + a0);
+            for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
+            ptx::cp_async_mbar_arrive_noinc(&full[s]);
+        }
+    };
+    for (int t = 0; t < STAGES - 1 && t < ntiles; t++) issue(t);
+
+    double re[QPT], im[QPT];
+#pragma unroll
+    for (int k = 0; k < QPT; k++) {
+        re[k] = 0.0;
+        im[k] = 0.0;
+    }
+    for (int t = 0; t < ntiles; t++) {
+        if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);
+        const int s = t % STAGES;
+        const int cnt = min(TILE, NA - t * TILE);
+        ptx::mbar_wait(&full[s], (unsigned)((t / STAGES) & 1));
+        const float *sx = s_xyz + (size_t)s * TILE * 3;
+        const double *sb = s_b + (size_t)s * TILE;
+#pragma unroll 1
+        for (int j = tid; j < cnt; j += WARPS * 32) {
+            const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
+            const double bj = sb[j];
+#pragma unroll
+            for (int k = 0; k < QPT; k++) {
+                const double u = fma(z, c_q[3 * (mq + k) + 2], fma(y, c_q[3 * (mq + k) + 1], x * c_q[3 * (mq + k)]));
+                sincos_qt_accumulate2(u, bj, re[k], im[k]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int k = 0; k < QPT; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            re[k] += __shfl_xor_sync(0xffffffffu, re[k], o);
+            im[k] += __shfl_xor_sync(0xffffffffu, im[k], o);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < QPT; k++) {
+            s_red[warp * 2 * QPT + 2 * k] = re[k];
+            s_red[warp * 2 * QPT + 2 * k + 1] = im[k];
+        }
+    }
+    __syncthreads();
+    if (tid < QPT) {
+        double r = 0.0, i = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            r += s_red[w * 2 * QPT + 2 * tid];
+            i += s_red[w * 2 * QPT + 2 * tid + 1];
+        }
+        const int m = m_base + mq + tid;
+        if (m < NM) A[(size_t)m * ldA + frame] = make_double2(r, i);
     }
 }
 
@@ -232,11 +499,100 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters)
 
 }  // namespace
 
-int amplitude_all_qpad() { return K1_QPT * K1_WARPS; }
+int amplitude_all_qpad() { return 64; }  // every variant covers 64 q-vectors per CTA or a divisor of it
+
+namespace {
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0>
+int launch_tiled(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+                 size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    const unsigned per_cta = QPT * WARPS;
+    const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
+    const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
+    auto kern = amplitude_all_tiled_kernel<QPT, WARPS, TILE, STAGES, MINB, ABL>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    // TMA bulk copies need 16-byte aligned global addresses: frame stride NA*12 bytes and the base pointers
+    const int use_bulk = (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
+    int launches = 0;
+    const size_t max_frames = (size_t)0x7fffffff / ngroups;
+    for (size_t done = 0; done < nf;) {
+        size_t cnt = nf - done < max_frames ? nf - done : max_frames;
+        kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups,
+                                                                   f0 + done, use_bulk);
+        launches++;
+        done += cnt;
+    }
+    return launches;
+}
+
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
+int launch_uq(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+              size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t) + (size_t)WARPS * 2 * QPT * 8;
+    auto kern = amplitude_all_uq_kernel<QPT, WARPS, TILE, STAGES, MINB>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    const int use_bulk = (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
+    int launches = 0;
+    const size_t chunk = (UQ_MAXQ / QPT) * QPT;
+    for (size_t m0 = 0; m0 < NM; m0 += chunk) {
+        const size_t cnt_m = NM - m0 < chunk ? NM - m0 : chunk;
+        const size_t padded = ((cnt_m + QPT - 1) / QPT) * QPT;  // d_qs is zero padded to a multiple of 64 >= QPT multiple
+        cudaMemcpyToSymbolAsync(c_q, d_qs + 3 * m0, padded * 3 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st);
+        const unsigned ngroups = (unsigned)(padded / QPT);
+        const size_t max_frames = (size_t)0x7fffffff / ngroups;
+        for (size_t done = 0; done < nf;) {
+            size_t cnt = nf - done < max_frames ? nf - done : max_frames;
+            kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_A, ldA, (int)NA, (int)NM, (int)m0,
+                                                                       ngroups, f0 + done, use_bulk);
+            launches++;
+            done += cnt;
+        }
+    }
+    return launches;
+}
+
+int k1_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SASSENA_K1_VARIANT");
+        v = e ? atoi(e) : 7;
+    }
+    return v;
+}
+}  // namespace
 
 int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
                          size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
     if (nf == 0 || NM == 0) return 0;
+    switch (k1_variant()) {
+        case 1: return launch_tiled<8, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 2: return launch_tiled<4, 8, 512, 4, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 3: return launch_tiled<4, 8, 512, 4, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 4: return launch_tiled<8, 4, 512, 4, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 5: return launch_tiled<8, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 6: return launch_tiled<4, 16, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 7: return launch_tiled<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 20: return launch_tiled<6, 8, 512, 4, 2, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 21: return launch_tiled<6, 8, 512, 4, 2, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 8: return launch_tiled<6, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 9: return launch_tiled<5, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 10: return launch_uq<8, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 11: return launch_uq<8, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 12: return launch_uq<6, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 13: return launch_uq<4, 8, 1024, 3, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 14: return launch_uq<8, 4, 1024, 3, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 15: return launch_uq<10, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        default: break;
+    }
     const unsigned per_cta = K1_QPT * K1_WARPS;
     const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
     int launches = 0;

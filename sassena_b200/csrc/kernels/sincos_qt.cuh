@@ -89,4 +89,46 @@ __device__ __forceinline__ void sincos_qt_accumulate(double u, int bhi, int blo,
     im = fma(bs, sm, im);
 }
 
+
+// Variant used by the tiled kernel: the quadrant signs are applied to f (odd polynomial) and to the even
+// polynomial value instead of to b, which removes the register-pair moves of sincos_qt_accumulate (ptxas turns
+// predicated FMAs back into FMA+select pairs, so the odd-quadrant swap stays four 32-bit selects):
+//   sign(cos-type term) = bit1(k), sign(sin-type term) = bit1(k+1)   (see DESIGN.md "quadrant algebra").
+// coefficient tables in constant memory: DFMA takes them as c[bank][offset] operands (no register or
+// uniform-register materialisation inside the atom loop)
+__constant__ double kSinC[6] = {SASS_S0, SASS_S1, SASS_S2, SASS_S3, SASS_S4, SASS_S5};
+__constant__ double kCosC[6] = {SASS_C0, SASS_C1, SASS_C2, SASS_C3, SASS_C4, SASS_C5};
+
+template <int ABL = 0>
+__device__ __forceinline__ void sincos_qt_accumulate2(double u, double b, double &re, double &im) {
+    const double MAGIC = 6755399441055744.0;
+    double t = u + MAGIC;
+    const int k = __double2loint(t);
+    double kd = t - MAGIC;
+    double f = u - kd;
+    double z = f * f;
+    double S = fma(z, kSinC[5], kSinC[4]);
+    double Cp = fma(z, kCosC[5], kCosC[4]);
+    S = fma(z, S, kSinC[3]);
+    Cp = fma(z, Cp, kCosC[3]);
+    S = fma(z, S, kSinC[2]);
+    Cp = fma(z, Cp, kCosC[2]);
+    S = fma(z, S, kSinC[1]);
+    Cp = fma(z, Cp, kCosC[1]);
+    S = fma(z, S, kSinC[0]);
+    Cp = fma(z, Cp, kCosC[0]);
+    const int ks = k << 30;
+    // signed odd part: (+-f) * S      (ABL != 0: timing ablations only, results are wrong)
+    const double fs = (ABL >= 2) ? f : __hiloint2double(__double2hiint(f) ^ ((ks + 0x40000000) & 0x80000000), __double2loint(f));
+    const double sv = fs * S;
+    double cv = fma(z, Cp, 1.0);
+    if (ABL < 2) cv = __hiloint2double(__double2hiint(cv) ^ (ks & 0x80000000), __double2loint(cv));
+    // odd quadrant: (re, im) += b*(sv, cv); even: += b*(cv, sv)
+    const bool odd = (ABL >= 1) ? false : ((k & 1) != 0);
+    const double cm = odd ? sv : cv;
+    const double sm = odd ? cv : sv;
+    re = fma(b, cm, re);
+    im = fma(b, sm, im);
+}
+
 }  // namespace sass

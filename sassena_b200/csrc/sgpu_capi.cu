@@ -64,6 +64,7 @@ struct sgpu_ctx {
 
     CorrPlan plan;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     bool have_times = false;
 
     ~sgpu_ctx() {
@@ -85,6 +86,8 @@ struct sgpu_ctx {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
+        if (tm0) cudaEventDestroy(tm0);
+        if (tm1) cudaEventDestroy(tm1);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
@@ -749,6 +752,25 @@ int sgpu_last_dsp_ms(sgpu_ctx *ctx, float *ms) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev2));
     CK(cudaEventElapsedTime(ms, ctx->ev1, ctx->ev2));
+    return SGPU_OK;
+}
+
+int sgpu_timer_start(sgpu_ctx *ctx) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->tm0) CK(cudaEventCreate(&ctx->tm0));
+    if (!ctx->tm1) CK(cudaEventCreate(&ctx->tm1));
+    CK(cudaEventRecord(ctx->tm0, ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_timer_stop(sgpu_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return SGPU_EINVAL;
+    if (!ctx->tm0 || !ctx->tm1) return fail(ctx, SGPU_ESTATE, "sgpu_timer_stop: timer not started");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->tm1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->tm1));
+    CK(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
     return SGPU_OK;
 }
 
