@@ -47,7 +47,8 @@ typedef struct sgpu_ctx sgpu_ctx;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 
-/* Create a context on CUDA device `device`.  Fails (SGPU_ECUDA) if no sm_100 device is present. */
+/* Create a context on CUDA device `device` (-1: the device the calling thread is bound to).
+ * Fails (SGPU_ECUDA) if no sm_100 device is present. */
 int sgpu_init(int device, sgpu_ctx **out);
 void sgpu_destroy(sgpu_ctx *ctx);
 /* Message of the last failing call on ctx (ctx may be NULL: message of the last failed sgpu_init). */
@@ -114,7 +115,8 @@ int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM,
  * calls (all_vectors_scatter_device.cpp:335-343, self...:213-221, multipole...:375-383).  Here every
  * rank computes an UNSCALED packed partial into device memory, the caller sums the packed buffers
  * over ranks (one NCCL all-reduce, f64 sum), and sgpu_finalize turns the sum into the outputs.
- * sgpu_partial_len gives the packed length in doubles for the staged NF and the dsp type. */
+ * sgpu_partial_len gives the packed length in doubles for the staged NF and the dsp type.
+ * A *_partial call with zero subvectors / moments just zeroes the buffer (a rank the decomposition left idle). */
 int sgpu_partial_len(sgpu_ctx *ctx, int dsp_type, size_t *n_doubles);
 int sgpu_compute_all_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t NM_local, int dsp_type,
                                      double *d_partial);

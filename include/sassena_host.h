@@ -1,0 +1,102 @@
+/*
+ * sassena_host.h — C entry points of the host layer (sassena_b200/csrc/host): the reference's scatter-device
+ * interface (ScatterDeviceFactory::create + IScatterDevice::run, src/scatter_devices/scatter_device_factory.cpp:23-210,
+ * src/scatter_devices/abstract_scatter_device.cpp:105-175) driven from C / ctypes, plus the pure host logic
+ * (assignments, decomposition plan, q-vector / orientation / moment generators) as unit-testable functions.
+ * All functions return 0 on success; on failure the message is in sass_last_error().
+ */
+#ifndef SASSENA_HOST_H
+#define SASSENA_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "sassena_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* communicator callbacks: stands in for boost::mpi::communicator (one rank = one GPU). allreduce_sum sums n doubles
+ * in DEVICE memory over the ranks (NCCL all-reduce); the callee must leave the result visible to the caller's
+ * subsequent CUDA work (synchronise its stream before returning). */
+typedef struct sass_comm_vtbl {
+    void *user;
+    size_t (*rank)(void *user);
+    size_t (*size)(void *user);
+    int (*allreduce_sum)(void *user, double *d_buf, size_t n);
+    int (*barrier)(void *user);
+    void *(*split)(void *user, int color); /* boost::mpi::communicator::split; returns the new `user` handle */
+    void (*release)(void *user);
+} sass_comm_vtbl;
+
+/* The C-ABI (sassena_b200.h) as a table.  NULL selects the library's own sgpu_* functions; tests bind the table
+ * to the CPU oracle to exercise the multi-rank host logic without a GPU. */
+typedef struct sass_backend_vtbl {
+    int (*init)(int, sgpu_ctx **);
+    void (*destroy)(sgpu_ctx *);
+    const char *(*last_error)(const sgpu_ctx *);
+    int (*synchronize)(sgpu_ctx *);
+    int (*stage_frames)(sgpu_ctx *, const float *, size_t, size_t, int);
+    int (*frames_to_spherical)(sgpu_ctx *);
+    int (*stage_atoms)(sgpu_ctx *, const float *, size_t, size_t);
+    int (*stage_atoms_from_frames)(sgpu_ctx *, const float *, size_t, size_t, size_t, size_t);
+    int (*set_factors)(sgpu_ctx *, const double *, size_t);
+    int (*partial_len)(sgpu_ctx *, int, size_t *);
+    int (*compute_all_vectors_partial)(sgpu_ctx *, const double *, size_t, int, double *);
+    int (*compute_self_vectors_partial)(sgpu_ctx *, const double *, size_t, int, double *);
+    int (*compute_mpsphere_partial)(sgpu_ctx *, double, const long *, size_t, int, double *);
+    int (*finalize)(sgpu_ctx *, const double *, int, int, double, double *, double *, double *);
+    int (*device_alloc)(void **, size_t);
+    int (*device_free)(void *);
+} sass_backend_vtbl;
+
+const char *sass_last_error(void);
+
+/* ---- Params: keys are the scatter.xml paths (src/control/parameters.cpp:372-397,612-636) -------------------- */
+typedef struct sass_params sass_params;
+sass_params *sass_params_new(void);
+void sass_params_free(sass_params *p);
+/* keys: scattering.type, scattering.dsp.type, scattering.dsp.method, scattering.average.orientation.type,
+ * scattering.average.orientation.axis.{x,y,z}, scattering.average.orientation.vectors.{type,algorithm,resolution,seed},
+ * scattering.average.orientation.multipole.type, scattering.average.orientation.multipole.moments.{type,resolution},
+ * limits.stage.memory.data, limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size} */
+int sass_params_set(sass_params *p, const char *key, const char *value);
+/* vectors.type=file rows / multipole.moments.type=file rows */
+int sass_params_set_vectors(sass_params *p, const double *xyz, size_t n);
+int sass_params_set_moments(sass_params *p, const long *lm, size_t n);
+/* run the generators (Params::init: vectors.create(), moments.create(); parameters.cpp:930-1122) */
+int sass_params_create(sass_params *p);
+size_t sass_params_num_vectors(const sass_params *p);
+int sass_params_get_vectors(const sass_params *p, double *out);
+size_t sass_params_num_moments(const sass_params *p);
+int sass_params_get_moments(const sass_params *p, long *out);
+
+/* ---- run: factory + device.run() ------------------------------------------------------------------------------ */
+/* ScatterFactors::update(q)+get_all(): fill b[NA] for |q| = ql (scatter_factors.cpp:56-78) */
+typedef void (*sass_factors_fn)(void *user, double ql, double *b, size_t NA);
+/* HDF5WriterClient::write(qvector, fqt, NF, fq, fq2) (file_writer_service.cpp:504-515); fq0 = fqt[0] */
+typedef void (*sass_write_fn)(void *user, const double q[3], const double *fqt, size_t NF, const double fq[2],
+                              const double fq2[2]);
+/* frames: host float [NF][NA][3] cartesian.  Either b_const (NA doubles, |q|-independent factors) or ffn is used.
+ * has_device (optional out): 0 on ranks the decomposition left spare.  timers (optional out): "key=sum_s:count;..." */
+int sass_scatter_run(const sass_params *p, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend, sgpu_ctx *ctx,
+                     size_t NA, size_t NF, const float *frames, const double *b_const, sass_factors_fn ffn,
+                     void *fuser, const double *qvectors, size_t NQ, sass_write_fn wfn, void *wuser, int *has_device,
+                     char *timers, size_t timers_cap);
+
+/* ---- host logic, unit-testable ---------------------------------------------------------------------------------- */
+int sass_div_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max);
+int sass_mod_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max);
+int sass_decomposition_plan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize, double utilization,
+                            int automatic, size_t manual_size, size_t *partitions, size_t *partitionsize,
+                            size_t *penalty);
+/* scans: [nscans][7] = base x,y,z, from, to, points, exponent.  Returns the count (out may be NULL to size). */
+size_t sass_create_from_scans(const double *scans, size_t nscans, double *out, size_t cap);
+/* AbstractVectorsScatterDevice::init_subvectors for q (abstract_vectors_scatter_device.cpp:112-175) */
+size_t sass_init_subvectors(const sass_params *p, const double q[3], double *out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,80 @@
+"""ctypes signatures of the host-layer C API (include/sassena_host.h)."""
+import ctypes as C
+
+c_size_p = C.POINTER(C.c_size_t)
+c_double_p = C.POINTER(C.c_double)
+c_long_p = C.POINTER(C.c_long)
+
+RANK_FN = C.CFUNCTYPE(C.c_size_t, C.c_void_p)
+SIZE_FN = C.CFUNCTYPE(C.c_size_t, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+SPLIT_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int)
+RELEASE_FN = C.CFUNCTYPE(None, C.c_void_p)
+
+
+class CommVtbl(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("rank", RANK_FN), ("size", SIZE_FN), ("allreduce_sum", ALLREDUCE_FN),
+                ("barrier", BARRIER_FN), ("split", SPLIT_FN), ("release", RELEASE_FN)]
+
+
+# backend table: same order as sass_backend_vtbl
+BE_INIT = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_void_p))
+BE_DESTROY = C.CFUNCTYPE(None, C.c_void_p)
+BE_LAST_ERROR = C.CFUNCTYPE(C.c_char_p, C.c_void_p)
+BE_SYNC = C.CFUNCTYPE(C.c_int, C.c_void_p)
+BE_STAGE_FRAMES = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int)
+BE_TO_SPH = C.CFUNCTYPE(C.c_int, C.c_void_p)
+BE_STAGE_ATOMS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t)
+BE_STAGE_ATOMS_FF = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t)
+BE_SET_FACTORS = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t)
+BE_PARTIAL_LEN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_size_p)
+BE_COMPUTE_VEC = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p)
+BE_COMPUTE_MP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, c_long_p, C.c_size_t, C.c_int, C.c_void_p)
+BE_FINALIZE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p,
+                          c_double_p)
+BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
+BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class BackendVtbl(C.Structure):
+    _fields_ = [("init", BE_INIT), ("destroy", BE_DESTROY), ("last_error", BE_LAST_ERROR), ("synchronize", BE_SYNC),
+                ("stage_frames", BE_STAGE_FRAMES), ("frames_to_spherical", BE_TO_SPH), ("stage_atoms", BE_STAGE_ATOMS),
+                ("stage_atoms_from_frames", BE_STAGE_ATOMS_FF), ("set_factors", BE_SET_FACTORS),
+                ("partial_len", BE_PARTIAL_LEN), ("compute_all_vectors_partial", BE_COMPUTE_VEC),
+                ("compute_self_vectors_partial", BE_COMPUTE_VEC), ("compute_mpsphere_partial", BE_COMPUTE_MP),
+                ("finalize", BE_FINALIZE), ("device_alloc", BE_ALLOC), ("device_free", BE_FREE)]
+
+
+FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)
+WRITE_FN = C.CFUNCTYPE(None, C.c_void_p, c_double_p, c_double_p, C.c_size_t, c_double_p, c_double_p)
+
+SIGNATURES = {
+    "sass_last_error": (C.c_char_p, []),
+    "sass_params_new": (C.c_void_p, []),
+    "sass_params_free": (None, [C.c_void_p]),
+    "sass_params_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "sass_params_set_vectors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
+    "sass_params_set_moments": (C.c_int, [C.c_void_p, c_long_p, C.c_size_t]),
+    "sass_params_create": (C.c_int, [C.c_void_p]),
+    "sass_params_num_vectors": (C.c_size_t, [C.c_void_p]),
+    "sass_params_get_vectors": (C.c_int, [C.c_void_p, c_double_p]),
+    "sass_params_num_moments": (C.c_size_t, [C.c_void_p]),
+    "sass_params_get_moments": (C.c_int, [C.c_void_p, c_long_p]),
+    "sass_scatter_run": (C.c_int, [C.c_void_p, C.POINTER(CommVtbl), C.POINTER(BackendVtbl), C.c_void_p, C.c_size_t,
+                                   C.c_size_t, C.c_void_p, c_double_p, FACTORS_FN, C.c_void_p, c_double_p, C.c_size_t,
+                                   WRITE_FN, C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
+    "sass_div_assignment": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_size_p, c_size_p, c_size_p]),
+    "sass_mod_assignment": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_size_p, c_size_p, c_size_p]),
+    "sass_decomposition_plan": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double,
+                                          C.c_int, C.c_size_t, c_size_p, c_size_p, c_size_p]),
+    "sass_create_from_scans": (C.c_size_t, [c_double_p, C.c_size_t, c_double_p, C.c_size_t]),
+    "sass_init_subvectors": (C.c_size_t, [C.c_void_p, c_double_p, c_double_p, C.c_size_t]),
+}
+
+
+def bind(lib):
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args

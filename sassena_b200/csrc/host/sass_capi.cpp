@@ -1,0 +1,278 @@
+// sass_capi.cpp — C wrapper of the host layer (include/sassena_host.h).  Exceptions stop here.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "sassena_host.hpp"
+
+using namespace sassena;
+
+struct sass_params {
+    Params params;
+};
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F>
+int guard(F f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    } catch (...) {
+        g_err = "unknown error";
+        return 1;
+    }
+}
+
+bool parse_bool(const std::string &v) {
+    // xml_interface.cpp:56-61: true/false in any case, or 1/0
+    std::string s;
+    for (char c : v) s += (char)tolower(c);
+    if (s == "true" || s == "1") return true;
+    if (s == "false" || s == "0") return false;
+    throw Error("boolean value not understood: " + v);
+}
+
+class FnSink : public IResultSink {
+    sass_write_fn fn_;
+    void *user_;
+
+   public:
+    FnSink(sass_write_fn fn, void *user) : fn_(fn), user_(user) {}
+    void write(CartesianCoor3D q, const double *fqt, size_t NF, std::complex<double> fq, std::complex<double> fq2) override {
+        if (!fn_) return;
+        double qq[3] = {q.x, q.y, q.z};
+        double a[2] = {fq.real(), fq.imag()};
+        double b[2] = {fq2.real(), fq2.imag()};
+        fn_(user_, qq, fqt, NF, a, b);
+    }
+};
+}  // namespace
+
+extern "C" {
+
+const char *sass_last_error(void) { return g_err.c_str(); }
+
+sass_params *sass_params_new(void) { return new sass_params(); }
+void sass_params_free(sass_params *p) { delete p; }
+
+int sass_params_set(sass_params *p, const char *key, const char *value) {
+    return guard([&] {
+        if (!p || !key || !value) throw Error("sass_params_set: NULL argument");
+        const std::string k(key), v(value);
+        ScatteringParameters &s = p->params.scattering;
+        const std::string o = "scattering.average.orientation.";
+        if (k == "scattering.type") s.type = v;
+        else if (k == "scattering.dsp.type") s.dsp_type = v;
+        else if (k == "scattering.dsp.method") s.dsp_method = v;
+        else if (k == o + "type") s.orientation_type = v;
+        else if (k == o + "axis.x") s.axis.x = atof(value);
+        else if (k == o + "axis.y") s.axis.y = atof(value);
+        else if (k == o + "axis.z") s.axis.z = atof(value);
+        else if (k == o + "vectors.type") s.vectors.type = v;
+        else if (k == o + "vectors.algorithm") s.vectors.algorithm = v;
+        else if (k == o + "vectors.resolution") s.vectors.resolution = strtoull(value, nullptr, 10);
+        else if (k == o + "vectors.seed") s.vectors.seed = (uint32_t)strtoul(value, nullptr, 10);
+        else if (k == o + "multipole.type") s.multipole.type = v;
+        else if (k == o + "multipole.moments.type") s.multipole.moments_type = v;
+        else if (k == o + "multipole.moments.resolution") s.multipole.resolution = atol(value);
+        else if (k == "limits.stage.memory.data") p->params.limits.stage_memory_data = strtoull(value, nullptr, 10);
+        else if (k == "limits.decomposition.utilization") p->params.limits.decomposition.utilization = atof(value);
+        else if (k == "limits.decomposition.partitions.automatic")
+            p->params.limits.decomposition.partitions_automatic = parse_bool(v);
+        else if (k == "limits.decomposition.partitions.size")
+            p->params.limits.decomposition.partitions_size = strtoull(value, nullptr, 10);
+        else if (k == "scattering.target")
+            throw Error("scattering.target is obsolete. Use stager.target instead.");  // parameters.cpp:404-407
+        else throw Error("unknown parameter key: " + k);
+    });
+}
+
+int sass_params_set_vectors(sass_params *p, const double *xyz, size_t n) {
+    return guard([&] {
+        if (!p || (!xyz && n)) throw Error("sass_params_set_vectors: NULL argument");
+        auto &v = p->params.scattering.vectors.vectors;
+        v.clear();
+        for (size_t i = 0; i < n; i++) v.push_back(CartesianCoor3D(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    });
+}
+
+int sass_params_set_moments(sass_params *p, const long *lm, size_t n) {
+    return guard([&] {
+        if (!p || (!lm && n)) throw Error("sass_params_set_moments: NULL argument");
+        auto &m = p->params.scattering.multipole.moments;
+        m.clear();
+        for (size_t i = 0; i < n; i++) m.push_back(std::make_pair(lm[2 * i], lm[2 * i + 1]));
+    });
+}
+
+int sass_params_create(sass_params *p) {
+    return guard([&] {
+        if (!p) throw Error("sass_params_create: NULL argument");
+        ScatteringParameters &s = p->params.scattering;
+        if (s.orientation_type == "vectors") s.vectors.create();
+        else if (s.orientation_type == "multipole") s.multipole.create();
+        else if (s.orientation_type != "none")
+            throw Error("scattering.average.orientation.type not understood: " + s.orientation_type);
+    });
+}
+
+size_t sass_params_num_vectors(const sass_params *p) { return p ? p->params.scattering.vectors.vectors.size() : 0; }
+int sass_params_get_vectors(const sass_params *p, double *out) {
+    return guard([&] {
+        if (!p || !out) throw Error("NULL argument");
+        size_t i = 0;
+        for (auto &v : p->params.scattering.vectors.vectors) {
+            out[3 * i] = v.x;
+            out[3 * i + 1] = v.y;
+            out[3 * i + 2] = v.z;
+            i++;
+        }
+    });
+}
+size_t sass_params_num_moments(const sass_params *p) { return p ? p->params.scattering.multipole.moments.size() : 0; }
+int sass_params_get_moments(const sass_params *p, long *out) {
+    return guard([&] {
+        if (!p || !out) throw Error("NULL argument");
+        size_t i = 0;
+        for (auto &m : p->params.scattering.multipole.moments) {
+            out[2 * i] = m.first;
+            out[2 * i + 1] = m.second;
+            i++;
+        }
+    });
+}
+
+int sass_scatter_run(const sass_params *p, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend, sgpu_ctx *ctx,
+                     size_t NA, size_t NF, const float *frames, const double *b_const, sass_factors_fn ffn,
+                     void *fuser, const double *qvectors, size_t NQ, sass_write_fn wfn, void *wuser, int *has_device,
+                     char *timers, size_t timers_cap) {
+    return guard([&] {
+        if (!p || !frames || !qvectors) throw Error("sass_scatter_run: NULL argument");
+        if (!b_const && !ffn) throw Error("sass_scatter_run: no scattering factors given");
+        std::shared_ptr<ICommunicator> c;
+        if (comm) c = std::make_shared<CallbackCommunicator>(*comm, false);
+        else c = std::make_shared<SingleCommunicator>();
+        Sample sample;
+        sample.NA = NA;
+        sample.NF = NF;
+        sample.frames = frames;
+        if (ffn) sample.factors = [=](double ql, double *b) { ffn(fuser, ql, b, NA); };
+        else sample.factors = [=](double, double *b) { memcpy(b, b_const, NA * sizeof(double)); };
+        std::vector<CartesianCoor3D> qv;
+        for (size_t i = 0; i < NQ; i++) qv.push_back(CartesianCoor3D(qvectors[3 * i], qvectors[3 * i + 1], qvectors[3 * i + 2]));
+        FnSink sink(wfn, wuser);
+        const SgpuBackend &be = backend ? *backend : default_backend();
+        std::unique_ptr<IScatterDevice> dev(ScatterDeviceFactory::create(c, sample, &sink, qv, p->params, be, ctx));
+        if (has_device) *has_device = dev ? 1 : 0;
+        if (timers && timers_cap) timers[0] = 0;
+        if (!dev) return;
+        dev->run();
+        if (timers && timers_cap) {
+            std::string t;
+            Timer &tm = dev->getTimer();
+            for (auto &k : tm.keys()) {
+                char buf[160];
+                snprintf(buf, sizeof(buf), "%s=%.6f:%zu;", k.c_str(), tm.sum(k), tm.count(k));
+                t += buf;
+            }
+            strncpy(timers, t.c_str(), timers_cap - 1);
+            timers[timers_cap - 1] = 0;
+        }
+    });
+}
+
+int sass_div_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max) {
+    return guard([&] {
+        DivAssignment a(NN, rank, NAF);
+        *offset = a.offset();
+        *size = a.size();
+        *max = a.max();
+    });
+}
+int sass_mod_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max) {
+    return guard([&] {
+        ModAssignment a(NN, rank, NAF);
+        *offset = a.offset();
+        *size = a.size();
+        *max = a.max();
+    });
+}
+int sass_decomposition_plan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize, double utilization,
+                            int automatic, size_t manual_size, size_t *partitions, size_t *partitionsize,
+                            size_t *penalty) {
+    return guard([&] {
+        DecompositionLimits lim;
+        lim.utilization = utilization;
+        lim.partitions_automatic = automatic != 0;
+        lim.partitions_size = manual_size;
+        DecompositionPlan plan(nn, nq, naf, elbytesize, nmaxbytesize, lim);
+        *partitions = plan.partitions();
+        *partitionsize = plan.partitionsize();
+        if (penalty) *penalty = plan.penalty();
+    });
+}
+size_t sass_create_from_scans(const double *scans, size_t nscans, double *out, size_t cap) {
+    size_t n = 0;
+    guard([&] {
+        std::vector<ScatteringVectorsScan> sc;
+        for (size_t i = 0; i < nscans; i++) {
+            ScatteringVectorsScan s;
+            s.basevector = CartesianCoor3D(scans[7 * i], scans[7 * i + 1], scans[7 * i + 2]);
+            s.from = scans[7 * i + 3];
+            s.to = scans[7 * i + 4];
+            s.points = (size_t)scans[7 * i + 5];
+            s.exponent = scans[7 * i + 6];
+            sc.push_back(s);
+        }
+        auto q = create_from_scans(sc);
+        n = q.size();
+        if (out)
+            for (size_t i = 0; i < n && i < cap; i++) {
+                out[3 * i] = q[i].x;
+                out[3 * i + 1] = q[i].y;
+                out[3 * i + 2] = q[i].z;
+            }
+    });
+    return n;
+}
+
+namespace {
+// exposes the protected init_subvectors for sass_init_subvectors
+struct SubvectorProbe : AllVectorsScatterDevice {
+    using AllVectorsScatterDevice::AllVectorsScatterDevice;
+    using AbstractVectorsScatterDevice::init_subvectors;
+};
+}  // namespace
+
+size_t sass_init_subvectors(const sass_params *p, const double q[3], double *out, size_t cap) {
+    size_t n = 0;
+    guard([&] {
+        if (!p || !q) throw Error("NULL argument");
+        // init_subvectors only reads params; build a device shell around a dummy backend-less context
+        static sass_backend_vtbl none = {};
+        Sample sample;
+        sample.NA = 1;
+        sample.NF = 1;
+        auto c = std::make_shared<SingleCommunicator>();
+        SubvectorProbe probe(c, c, sample, {}, 1, nullptr, p->params, none, reinterpret_cast<sgpu_ctx *>(&none));
+        CartesianCoor3D qq(q[0], q[1], q[2]);
+        probe.init_subvectors(qq);
+        const auto &sv = probe.subvectors();
+        n = sv.size();
+        if (out)
+            for (size_t i = 0; i < n && i < cap; i++) {
+                out[3 * i] = sv[i].x;
+                out[3 * i + 1] = sv[i].y;
+                out[3 * i + 2] = sv[i].z;
+            }
+    });
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,771 @@
+// sassena_host.cpp — see sassena_host.hpp.  Reference citations are relative to benlabs/sassena v1.4.2.
+#include "sassena_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <random>
+
+namespace sassena {
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------
+// coor3d
+// ---------------------------------------------------------------------------------------------------------------
+double CartesianCoor3D::length() const { return std::sqrt(std::pow(x, 2) + std::pow(y, 2) + std::pow(z, 2)); }
+
+CartesianVectorBase::CartesianVectorBase(CartesianCoor3D axis) {
+    CartesianCoor3D ek(0, 0, 1), ej(0, 1, 0);
+    CartesianCoor3D ez = axis / axis.length();
+    CartesianCoor3D ekez = ek.cross_product(ez);
+    if (ekez.length() == 0) ekez = ej.cross_product(ez);
+    CartesianCoor3D er = ekez / ekez.length();
+    CartesianCoor3D ezer = ez.cross_product(er);
+    CartesianCoor3D ephi = ezer / ezer.length();
+    base_.push_back(er);
+    base_.push_back(ephi);
+    base_.push_back(ez);
+}
+
+CartesianCoor3D CartesianVectorBase::project(CartesianCoor3D vec) {
+    return CartesianCoor3D(vec * base_[0], vec * base_[1], vec * base_[2]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decomposition (assignment.cpp:27-132)
+// ---------------------------------------------------------------------------------------------------------------
+DivAssignment::DivAssignment(size_t NN, size_t rank, size_t NAF) : NN_(NN), rank_(rank), NAF_(NAF) {
+    if (NN == 0) throw Error("DivAssignment: NN == 0");
+    size_t first = (rank_ * NAF_) / NN_;
+    size_t next = ((rank_ + 1) * NAF_) / NN_;
+    offset_ = first;
+    size_ = next - first;
+}
+size_t DivAssignment::operator[](size_t index) const {
+    if (index < size_) return offset_ + index;
+    throw Error("Assignment out of bounds, operator[]");
+}
+size_t DivAssignment::max() const {
+    size_t m = NAF_ / NN_;
+    if ((NAF_ % NN_) != 0) m += 1;
+    return m;
+}
+bool DivAssignment::contains(size_t i) const { return i >= offset_ && i < offset_ + size_; }
+size_t DivAssignment::index(size_t i) const {
+    if (!contains(i)) throw Error("Assignment: index not contained");
+    return i - offset_;
+}
+
+ModAssignment::ModAssignment(size_t NN, size_t rank, size_t NAF) : NN_(NN), rank_(rank), NAF_(NAF) {
+    if (NN == 0) throw Error("ModAssignment: NN == 0");
+    size_ = NAF_ / NN_;
+    if ((NAF_ % NN_) != 0) {
+        if (rank < (NAF_ - NN_ * (NAF_ / NN_))) size_ += 1;
+    }
+    offset_ = rank;
+}
+size_t ModAssignment::operator[](size_t index) const {
+    if (index < size_) return offset_ + index * NN_;
+    throw Error("Assignment out of bounds, operator[]");
+}
+size_t ModAssignment::max() const {
+    size_t m = NAF_ / NN_;
+    if ((NAF_ % NN_) != 0) m += 1;
+    return m;
+}
+bool ModAssignment::contains(size_t i) const {
+    if (i < offset_) return false;
+    return ((i - offset_) % NN_) == 0;
+}
+size_t ModAssignment::index(size_t i) const {
+    if (!contains(i)) throw Error("Assignment: index not contained");
+    return (i - offset_) / NN_;
+}
+
+// decomposition_plan.cpp:29-66
+DecompositionParameters::DecompositionParameters(size_t NN, size_t NQ, size_t NAF, size_t NNpP, size_t elbytesize) {
+    size_t NP = NN / NNpP;
+    size_t NPused = NP;
+    if (NQ < NP) NPused = NQ;
+    size_t NNnotused = NN - NPused * NNpP;
+    size_t NQcycles = ((NQ % NP) == 0) ? NQ / NP : NQ / NP + 1;
+    size_t NAFcycles = ((NAF % NNpP) == 0) ? NAF / NNpP : NAF / NNpP + 1;
+    size_t penalty = NNnotused * NQcycles * NAFcycles;
+    penalty += (NPused * NQcycles - NQ) * (NNpP * NAFcycles);
+    penalty += (NNpP * NAFcycles - NAF) * NQ;
+    m_penalty = penalty;
+    m_NAFcycles = NAFcycles;
+    m_NQcycles = NQcycles;
+    m_NNpP = NNpP;
+    m_NN = NN;
+    m_NQ = NQ;
+    m_NAF = NAF;
+    m_NP = NP;
+    m_elbytesize = elbytesize;
+    m_nbytesize = NAFcycles * m_elbytesize;
+}
+
+// decomposition_plan.cpp:69-156
+DecompositionPlan::DecompositionPlan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize,
+                                     const DecompositionLimits &lim) {
+    if (naf < 1) throw Error("No data to decompose.");
+    if (nn < 1) throw Error("No nodes to decompose onto.");
+    if (lim.partitions_automatic) {
+        size_t npmax = naf;
+        if (naf > nn) npmax = nn;
+        for (size_t nnpp = npmax; nnpp >= 1; nnpp--) {
+            std::unique_ptr<DecompositionParameters> p_dp(new DecompositionParameters(nn, nq, naf, nnpp, elbytesize));
+            if (p_dp->nbytesize() > nmaxbytesize) continue;
+            if (!p_dp_best || p_dp->penalty() < p_dp_best->penalty()) p_dp_best = std::move(p_dp);
+        }
+        if (!p_dp_best)
+            throw Error(
+                "Automatic decomposition failed to match the necessary requirements. Either change the partition size "
+                "manually or change the number of nodes. (limits.stage.memory.data)");
+    } else {
+        size_t nnpp = lim.partitions_size;
+        if (nnpp > nn) nnpp = nn;
+        if (lim.partitions_size > naf) nnpp = naf;
+        if (nnpp < 1) nnpp = 1;
+        p_dp_best.reset(new DecompositionParameters(nn, nq, naf, nnpp, elbytesize));
+    }
+    if (utilization() < lim.utilization) {
+        p_dp_best.reset();
+        throw Error("Utilization too low. Aborting. Change the number of nodes or the threshold value");
+    }
+}
+
+double DecompositionPlan::utilization() const {
+    size_t used = p_dp_best->get_NQ() * p_dp_best->get_NAF();
+    size_t wasted = p_dp_best->penalty();
+    return used * 1.0 / (used + wasted);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generators (parameters.cpp:930-1189)
+// ---------------------------------------------------------------------------------------------------------------
+std::vector<CartesianCoor3D> create_from_scans(const std::vector<ScatteringVectorsScan> &scans) {
+    if (scans.size() > 3) throw Error("More than 3 scan definitions are not supported.");
+    std::vector<std::vector<CartesianCoor3D>> qvectors(scans.size());
+    for (size_t i = 0; i < scans.size(); ++i) {
+        const ScatteringVectorsScan &s = scans[i];
+        if (s.points == 0) continue;
+        if (s.points == 1) {
+            double scal = (s.from + s.to) / 2;
+            qvectors[i].push_back(scal * s.basevector);
+            continue;
+        }
+        if (s.points == 2) {
+            qvectors[i].push_back(s.from * s.basevector);
+            qvectors[i].push_back(s.to * s.basevector);
+            continue;
+        }
+        qvectors[i].push_back(s.from * s.basevector);
+        for (size_t j = 1; j < (s.points - 1); j++) {
+            // float-rounded fraction, as the reference's powf call (parameters.cpp:1151)
+            double scal = s.from + powf((float)(j * 1.0 / (s.points - 1)), (float)s.exponent) * (s.to - s.from);
+            qvectors[i].push_back(scal * s.basevector);
+        }
+        qvectors[i].push_back(s.to * s.basevector);
+    }
+    std::vector<CartesianCoor3D> out;
+    if (scans.size() == 1) out = qvectors[0];
+    if (scans.size() == 2)
+        for (auto &a : qvectors[0])
+            for (auto &b : qvectors[1]) out.push_back(a + b);
+    if (scans.size() == 3)
+        for (auto &a : qvectors[0])
+            for (auto &b : qvectors[1])
+                for (auto &c : qvectors[2]) out.push_back(a + b + c);
+    return out;
+}
+
+namespace {
+// boost::uniform_on_sphere<double>(dim) over boost::mt19937 with Boost 1.4x's Box-Muller normal_distribution
+// (one cached value, uniform_01 = x / 2^32).  std::mt19937 is the same engine and seeding as boost::mt19937.
+// BEST EFFORT: the stream of later Boost versions differs; parity runs pass explicit vectors.
+struct UniformOnSphere {
+    std::mt19937 rng;
+    int dim;
+    bool valid = false;
+    double r1 = 0, cached_rho = 0;
+    UniformOnSphere(uint32_t seed, int d) : rng(seed), dim(d) {}
+    double normal() {
+        if (!valid) {
+            r1 = rng() / 4294967296.0;
+            double r2 = rng() / 4294967296.0;
+            cached_rho = std::sqrt(-2.0 * std::log(1.0 - r2));
+            valid = true;
+            return cached_rho * std::cos(2 * M_PI * r1);
+        }
+        valid = false;
+        return cached_rho * std::sin(2 * M_PI * r1);
+    }
+    std::vector<double> operator()() {
+        std::vector<double> v(dim);
+        double sq = 0;
+        for (int d = 0; d < dim; d++) {
+            v[d] = normal();
+            sq += v[d] * v[d];
+        }
+        double inv = 1.0 / std::sqrt(sq);
+        for (auto &c : v) c *= inv;
+        return v;
+    }
+};
+}  // namespace
+
+void OrientationVectorsParameters::create() {
+    if (type == "file") {
+        for (auto &q : vectors) {
+            double ql = q.length();
+            if (ql != 0) q = (1.0 / ql) * q;
+        }
+    } else if (type == "sphere") {
+        if (algorithm != "boost_uniform_on_sphere") throw Error("Vectors algorithm not understood: " + algorithm);
+        vectors.clear();
+        UniformOnSphere s(seed, 3);
+        for (size_t i = 0; i < resolution; ++i) {
+            std::vector<double> r = s();
+            vectors.push_back(CartesianCoor3D(r[0], r[1], r[2]));
+        }
+    } else if (type == "cylinder") {
+        vectors.clear();
+        if (algorithm == "boost_uniform_on_sphere") {
+            UniformOnSphere s(seed, 2);
+            for (size_t i = 0; i < resolution; ++i) {
+                std::vector<double> r = s();
+                vectors.push_back(CartesianCoor3D(r[0], r[1], 0));
+            }
+        } else if (algorithm == "raster_linear") {
+            const double M_2PI = 2 * M_PI;
+            const double radincr = (M_2PI) / (360 * resolution);
+            for (double phi = 0; phi < M_2PI; phi += radincr) vectors.push_back(CartesianCoor3D(cos(phi), sin(phi), 0));
+        } else {
+            throw Error("Vectors algorithm not understood: " + algorithm);
+        }
+    } else {
+        throw Error("Vectors orientation averaging type not understood: " + type);
+    }
+}
+
+void OrientationMultipoleParameters::create() {
+    if (moments_type == "file") {
+        // moments already given
+    } else if (moments_type == "resolution") {
+        moments.clear();
+        if (type == "sphere") {
+            moments.push_back(std::make_pair(0L, 0L));
+            for (long l = 1; l <= resolution; ++l)
+                for (long m = -l; m <= l; ++m) moments.push_back(std::make_pair(l, m));
+        } else if (type == "cylinder") {
+            moments.push_back(std::make_pair(0L, 0L));
+            for (long l = 1; l <= resolution; ++l)
+                for (long m = 0; m <= 3; ++m) moments.push_back(std::make_pair(l, m));
+        } else {
+            throw Error("Type not understood: scattering.average.orientation.multipole.moments.type=" + moments_type);
+        }
+    } else {
+        throw Error("Type not understood: scattering.average.orientation.multipole.type=" + type);
+    }
+    // validity checks, parameters.cpp:1081-1118
+    for (auto &mm : moments) {
+        if (mm.first < 0) throw Error("Major multipole moment must be >= 0!");
+        if (type == "cylinder") {
+            if (mm.second < 0 || mm.second > 3) throw Error("Minor multipole moment must be between 0 and 3!");
+            if (mm.first == 0 && mm.second != 0) throw Error("Minor multipole moment must be 0 for Major 0!");
+        } else if (type == "sphere") {
+            if (labs(mm.second) > mm.first) throw Error("Minor multipole moment must be between -Major and +Major!");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// communicator / backend / timer
+// ---------------------------------------------------------------------------------------------------------------
+CallbackCommunicator::~CallbackCommunicator() {
+    if (owned_ && v_.release) v_.release(v_.user);
+}
+void CallbackCommunicator::allreduce_sum(double *d, size_t n) {
+    if (v_.allreduce_sum(v_.user, d, n) != 0) throw Error("communicator: allreduce failed");
+}
+void CallbackCommunicator::barrier() {
+    if (v_.barrier(v_.user) != 0) throw Error("communicator: barrier failed");
+}
+std::shared_ptr<ICommunicator> CallbackCommunicator::split(int color) {
+    void *u = v_.split(v_.user, color);
+    if (!u) throw Error("communicator: split failed");
+    sass_comm_vtbl nv = v_;
+    nv.user = u;
+    return std::make_shared<CallbackCommunicator>(nv, true);
+}
+
+const SgpuBackend &default_backend() {
+    static const SgpuBackend be = {sgpu_init,
+                                   sgpu_destroy,
+                                   sgpu_last_error,
+                                   sgpu_synchronize,
+                                   sgpu_stage_frames,
+                                   sgpu_frames_to_spherical,
+                                   sgpu_stage_atoms,
+                                   sgpu_stage_atoms_from_frames,
+                                   sgpu_set_factors,
+                                   sgpu_partial_len,
+                                   sgpu_compute_all_vectors_partial,
+                                   sgpu_compute_self_vectors_partial,
+                                   sgpu_compute_mpsphere_partial,
+                                   sgpu_finalize,
+                                   sgpu_device_alloc,
+                                   sgpu_device_free};
+    return be;
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void Timer::start(const std::string &key) { start_[key] = now_s(); }
+void Timer::stop(const std::string &key) {
+    auto it = start_.find(key);
+    if (it == start_.end()) return;
+    auto &a = acc_[key];
+    a.first += now_s() - it->second;
+    a.second += 1;
+}
+double Timer::sum(const std::string &key) const {
+    auto it = acc_.find(key);
+    return it == acc_.end() ? 0.0 : it->second.first;
+}
+size_t Timer::count(const std::string &key) const {
+    auto it = acc_.find(key);
+    return it == acc_.end() ? 0 : it->second.second;
+}
+std::vector<std::string> Timer::keys() const {
+    std::vector<std::string> k;
+    for (auto &kv : acc_) k.push_back(kv.first);
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stager
+// ---------------------------------------------------------------------------------------------------------------
+DataStagerByFrame::DataStagerByFrame(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
+                                     const SgpuBackend &be, sgpu_ctx *ctx, const Params &params)
+    : m_sample(sample), allcomm_(allcomm), partitioncomm_(partitioncomm), timer_(timer), be_(be), ctx_(ctx), params_(params) {
+    // data_stager.cpp:57-63: every GPU holds all frames here (no frame decomposition inside a partition)
+    size_t data_bytesize = m_sample.NF * m_sample.NA * 3 * sizeof(float);
+    if (params_.limits.stage_memory_data < data_bytesize)
+        throw Error("Insufficient Buffer size for coordinates (limits.memory.data) Requested (bytes): " +
+                    std::to_string(data_bytesize));
+}
+
+void DataStagerByFrame::stage(int repr) {
+    timer_.start("st:first");
+    int rc = be_.stage_frames(ctx_, m_sample.frames, m_sample.NF, m_sample.NA, SGPU_REPR_CARTESIAN);
+    if (rc) throw Error(std::string("stage_frames: ") + be_.last_error(ctx_));
+    if (repr == SGPU_REPR_SPHERICAL) {
+        rc = be_.frames_to_spherical(ctx_);
+        if (rc) throw Error(std::string("frames_to_spherical: ") + be_.last_error(ctx_));
+    }
+    timer_.stop("st:first");
+    timer_.start("st:wait");
+    allcomm_.barrier();
+    timer_.stop("st:wait");
+}
+
+DataStagerByAtom::DataStagerByAtom(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
+                                   const SgpuBackend &be, sgpu_ctx *ctx, const Params &params)
+    : m_sample(sample), allcomm_(allcomm), partitioncomm_(partitioncomm), timer_(timer), be_(be), ctx_(ctx), params_(params) {
+    ModAssignment assignment(partitioncomm_.size(), partitioncomm_.rank(), m_sample.NA);
+    size_t data_bytesize = assignment.max() * m_sample.NF * 3 * sizeof(float);  // data_stager.cpp:194-204
+    if (params_.limits.stage_memory_data < data_bytesize)
+        throw Error("Insufficient Buffer size for coordinates (limits.memory.data) Requested (bytes): " +
+                    std::to_string(data_bytesize));
+}
+
+void DataStagerByAtom::stage() {
+    timer_.start("st:first");
+    int rc = be_.stage_atoms_from_frames(ctx_, m_sample.frames, m_sample.NF, m_sample.NA, partitioncomm_.size(),
+                                         partitioncomm_.rank());
+    if (rc) throw Error(std::string("stage_atoms_from_frames: ") + be_.last_error(ctx_));
+    timer_.stop("st:first");
+    timer_.start("st:wait");
+    allcomm_.barrier();
+    timer_.stop("st:wait");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AbstractScatterDevice (abstract_scatter_device.cpp)
+// ---------------------------------------------------------------------------------------------------------------
+AbstractScatterDevice::AbstractScatterDevice(std::shared_ptr<ICommunicator> allcomm,
+                                             std::shared_ptr<ICommunicator> partitioncomm, Sample &sample,
+                                             std::vector<CartesianCoor3D> vectors, size_t NAF, IResultSink *sink,
+                                             const Params &params, const SgpuBackend &be, sgpu_ctx *ctx)
+    : allcomm_(allcomm), partitioncomm_(partitioncomm), sample_(sample), vectors_(vectors), p_hdf5writer_(sink),
+      params_(params), be_(be), ctx_(ctx), afinal_(0), a2final_(0) {
+    (void)NAF;
+    NN = allcomm_->size();
+    NA = sample_.NA;
+    NF = sample_.NF;
+    if (!ctx_) {
+        int rc = be_.init(-1, &ctx_);  // -1: "the device this process is bound to" (current CUDA device)
+        if (rc) throw Error(std::string("sgpu_init: ") + be_.last_error(nullptr));
+        own_ctx_ = true;
+    }
+}
+
+AbstractScatterDevice::~AbstractScatterDevice() {
+    if (d_partial_) be_.device_free(d_partial_);
+    if (own_ctx_ && ctx_) be_.destroy(ctx_);
+}
+
+void AbstractScatterDevice::ck(int rc, const char *what) {
+    if (rc) throw Error(std::string(what) + ": " + be_.last_error(ctx_));
+}
+
+int AbstractScatterDevice::dsp_type_code() const {
+    const std::string &t = params_.scattering.dsp_type;
+    if (t == "autocorrelate") return SGPU_DSP_AUTOCORRELATE;
+    if (t == "square") return SGPU_DSP_SQUARE;
+    if (t == "plain") return SGPU_DSP_PLAIN;
+    // all_vectors_scatter_device.cpp:224-228
+    throw Error("DSP type not understood: " + t + " (scattering.dsp.type == autocorrelate, square, plain)");
+}
+
+int AbstractScatterDevice::dsp_method_code() const {
+    const std::string &m = params_.scattering.dsp_method;
+    if (m == "fftw") return SGPU_METHOD_FFTW;
+    if (m == "direct") return SGPU_METHOD_DIRECT;
+    if (params_.scattering.dsp_type != "autocorrelate") return SGPU_METHOD_FFTW;
+    throw Error("Correlation method not understood (scattering.dsp.method == direct, fftw)");  // :218-221
+}
+
+double *AbstractScatterDevice::partial_buffer(int dsp_type) {
+    size_t len = 0;
+    ck(be_.partial_len(ctx_, dsp_type, &len), "sgpu_partial_len");
+    if (len > partial_cap_) {
+        if (d_partial_) be_.device_free(d_partial_);
+        d_partial_ = nullptr;
+        void *p = nullptr;
+        if (be_.device_alloc(&p, len * sizeof(double))) throw Error("device allocation of the partial buffer failed");
+        d_partial_ = static_cast<double *>(p);
+        partial_cap_ = len;
+    }
+    return d_partial_;
+}
+
+// the three boost::mpi::reduce calls of compute() (all_vectors_scatter_device.cpp:324-352) as one all-reduce of the
+// packed partial, followed by the inverse transform / scaling on every rank (rank 0 of the partition writes)
+void AbstractScatterDevice::reduce_and_finalize(int dsp_type, double scale) {
+    size_t len = 0;
+    ck(be_.partial_len(ctx_, dsp_type, &len), "sgpu_partial_len");
+    timer_.start("sd:c:wait");
+    ck(be_.synchronize(ctx_), "sgpu_synchronize");
+    timer_.stop("sd:c:wait");
+    timer_.start("sd:c:reduce");
+    if (partitioncomm_->size() > 1) partitioncomm_->allreduce_sum(d_partial_, len);
+    timer_.stop("sd:c:reduce");
+    double af[2], a2f[2];
+    ck(be_.finalize(ctx_, d_partial_, dsp_type, dsp_method_code(), scale, atfinal_.data(), af, a2f), "sgpu_finalize");
+    afinal_ = std::complex<double>(af[0], af[1]);
+    a2final_ = std::complex<double>(a2f[0], a2f[1]);
+}
+
+bool AbstractScatterDevice::ram_check() {
+    // the reference checks limits.computation.memory.* against host buffers; here the device allocator reports
+    // exhaustion (SGPU_ENOMEM) at stage/compute time, and the stagers check limits.stage.memory.data
+    return true;
+}
+
+void AbstractScatterDevice::run() {
+    if (!ram_check()) throw terminate_request();
+    print_pre_stage_info();
+    allcomm_->barrier();
+    timer_.start("sd:stage");
+    stage_data();
+    timer_.stop("sd:stage");
+    allcomm_->barrier();
+    print_post_stage_info();
+
+    atfinal_.assign(2 * NF, 0.0);
+
+    print_pre_runner_info();
+    allcomm_->barrier();
+    timer_.start("sd:runner");
+    runner();
+    timer_.stop("sd:runner");
+    allcomm_->barrier();
+    print_post_runner_info();
+}
+
+void AbstractScatterDevice::runner() {
+    while (status() == 0) {
+        timer_.start("sd:compute");
+        compute();
+        timer_.stop("sd:compute");
+        timer_.start("sd:write");
+        write();
+        timer_.stop("sd:write");
+        next();
+    }
+}
+
+void AbstractScatterDevice::next() {
+    if (current_vector_ >= vectors_.size()) return;
+    current_vector_++;
+}
+
+double AbstractScatterDevice::progress() {
+    double scale = 1.0 / vectors_.size();
+    return current_vector_ * scale;
+}
+
+size_t AbstractScatterDevice::status() { return current_vector_ == vectors_.size() ? 1 : 0; }
+
+void AbstractScatterDevice::write() {
+    if (partitioncomm_->rank() == 0 && p_hdf5writer_) {
+        CartesianCoor3D vector = vectors_[current_vector_];
+        p_hdf5writer_->write(vector, atfinal_.data(), NF, afinal_, a2final_);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AbstractVectorsScatterDevice (abstract_vectors_scatter_device.cpp:96-175)
+// ---------------------------------------------------------------------------------------------------------------
+double AbstractVectorsScatterDevice::progress() {
+    double scale1 = 1.0 / vectors_.size();
+    double scale2 = 1.0 / NM;
+    return current_vector_ * scale1 + current_subvector_ * scale1 * scale2;
+}
+
+void AbstractVectorsScatterDevice::init_subvectors(CartesianCoor3D &q) {
+    subvector_index_.clear();
+    const OrientationVectorsParameters &ov = params_.scattering.vectors;
+    // the reference keys on vectors.size()>0, which is only the case for orientation.type=="vectors"
+    if (params_.scattering.orientation_type == "vectors" && ov.vectors.size() > 0) {
+        if (ov.type == "file" || ov.type == "sphere") {
+            double ql = q.length();
+            for (size_t i = 0; i < ov.vectors.size(); ++i) subvector_index_.push_back(ql * ov.vectors[i]);
+        } else if (ov.type == "cylinder") {
+            CartesianCoor3D o = params_.scattering.axis;
+            CartesianVectorBase base(o);
+            CartesianCoor3D qprojected = base.project(q);
+            // CylinderCoor3D(CartesianCoor3D): r = sqrt(x^2+y^2), z = z (coor3d.cpp:116-140)
+            double qr = std::sqrt(std::pow(qprojected.x, 2) + std::pow(qprojected.y, 2));
+            double qz = qprojected.z;
+            if (qr == 0) {
+                subvector_index_.push_back(qprojected);  // quirk kept: the projected vector (:134-135)
+            } else {
+                for (size_t i = 0; i < ov.vectors.size(); ++i) {
+                    const CartesianCoor3D &vec = ov.vectors[i];
+                    CartesianCoor3D qnew = qz * base[2] + qr * (vec.x * base[0] + vec.y * base[1]);
+                    subvector_index_.push_back(qnew);
+                }
+            }
+        }
+    } else {
+        subvector_index_.push_back(q);
+    }
+    NM = subvector_index_.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// AllVectorsScatterDevice (all_vectors_scatter_device.cpp)
+// ---------------------------------------------------------------------------------------------------------------
+void AllVectorsScatterDevice::stage_data() {
+    DataStagerByFrame data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
+    data_stager.stage(SGPU_REPR_CARTESIAN);
+    factors_.assign(NA, 0.0);
+}
+
+void AllVectorsScatterDevice::compute() {
+    CartesianCoor3D q = vectors_[current_vector_];
+    timer_.start("sd:c:init");
+    init_subvectors(q);
+    sample_.factors(q.length(), factors_.data());  // scatterfactors.update(q) (:245)
+    ck(be_.set_factors(ctx_, factors_.data(), NA), "sgpu_set_factors");
+    timer_.stop("sd:c:init");
+
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    current_subvector_ = 0;
+    // q-vector decomposition inside the partition: rank r takes DivAssignment(NNPP, r, NM) of the subvectors
+    // (replaces the reference's frame decomposition + all_to_all, :291-315; every GPU holds all frames)
+    DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NM);
+    std::vector<double> qv(3 * std::max<size_t>(mine.size(), 1));
+    for (size_t i = 0; i < mine.size(); i++) {
+        const CartesianCoor3D &s = subvector_index_[mine[i]];
+        qv[3 * i] = s.x;
+        qv[3 * i + 1] = s.y;
+        qv[3 * i + 2] = s.z;
+    }
+    double *partial = partial_buffer(dsp);
+    timer_.start("sd:c:block");
+    ck(be_.compute_all_vectors_partial(ctx_, qv.data(), mine.size(), dsp, partial), "sgpu_compute_all_vectors_partial");
+    current_subvector_ = NM;
+    timer_.stop("sd:c:block");
+    reduce_and_finalize(dsp, 1.0 / subvector_index_.size());  // factor = 1/NM (:355-360)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SelfVectorsScatterDevice (self_vectors_scatter_device.cpp)
+// ---------------------------------------------------------------------------------------------------------------
+SelfVectorsScatterDevice::SelfVectorsScatterDevice(std::shared_ptr<ICommunicator> allcomm,
+                                                   std::shared_ptr<ICommunicator> partitioncomm, Sample &sample,
+                                                   std::vector<CartesianCoor3D> vectors, size_t NAF, IResultSink *sink,
+                                                   const Params &params, const SgpuBackend &be, sgpu_ctx *ctx)
+    : AbstractVectorsScatterDevice(allcomm, partitioncomm, sample, vectors, NAF, sink, params, be, ctx),
+      assignment_(partitioncomm->size(), partitioncomm->rank(), NAF) {}
+
+void SelfVectorsScatterDevice::stage_data() {
+    DataStagerByAtom data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
+    data_stager.stage();
+    factors_.assign(NA, 0.0);
+}
+
+void SelfVectorsScatterDevice::compute() {
+    CartesianCoor3D q = vectors_[current_vector_];
+    timer_.start("sd:c:init");
+    init_subvectors(q);
+    sample_.factors(q.length(), factors_.data());
+    // scatterfactors.get(assignment_[ai]) (:291): factors of this rank's atoms in staged order
+    std::vector<double> mine(std::max<size_t>(assignment_.size(), 1));
+    for (size_t i = 0; i < assignment_.size(); i++) mine[i] = factors_[assignment_[i]];
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    double *partial = partial_buffer(dsp);
+    std::vector<double> qv(3 * NM);
+    for (size_t i = 0; i < NM; i++) {
+        qv[3 * i] = subvector_index_[i].x;
+        qv[3 * i + 1] = subvector_index_[i].y;
+        qv[3 * i + 2] = subvector_index_[i].z;
+    }
+    timer_.stop("sd:c:init");
+    timer_.start("sd:c:block");
+    if (assignment_.size() > 0) {
+        ck(be_.set_factors(ctx_, mine.data(), assignment_.size()), "sgpu_set_factors");
+        ck(be_.compute_self_vectors_partial(ctx_, qv.data(), NM, dsp, partial), "sgpu_compute_self_vectors_partial");
+    } else {
+        // a rank without atoms contributes zeros: an empty q-list zeroes the partial
+        ck(be_.compute_self_vectors_partial(ctx_, qv.data(), 0, dsp, partial), "sgpu_compute_self_vectors_partial");
+    }
+    current_subvector_ = NM;
+    timer_.stop("sd:c:block");
+    reduce_and_finalize(dsp, 1.0 / subvector_index_.size());  // :233-238
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MPSphereScatterDevice (multipole_scatter_device.cpp:32-498)
+// ---------------------------------------------------------------------------------------------------------------
+void MPSphereScatterDevice::init_moments(CartesianCoor3D &q) {
+    multipole_index_.clear();
+    for (size_t i = 0; i < params_.scattering.multipole.moments.size(); ++i)
+        multipole_index_.push_back(params_.scattering.multipole.moments[i]);
+    qvector_ = q;
+    NM = multipole_index_.size();
+}
+
+void MPSphereScatterDevice::stage_data() {
+    DataStagerByFrame data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
+    data_stager.stage(SGPU_REPR_SPHERICAL);  // set_representation(SPHERICAL) (:53)
+    factors_.assign(NA, 0.0);
+}
+
+void MPSphereScatterDevice::compute() {
+    CartesianCoor3D q = vectors_[current_vector_];
+    timer_.start("sd:c:init");
+    init_moments(q);
+    sample_.factors(q.length(), factors_.data());
+    ck(be_.set_factors(ctx_, factors_.data(), NA), "sgpu_set_factors");
+    timer_.stop("sd:c:init");
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    for (auto &mm : multipole_index_)
+        if (labs(mm.second) > mm.first)  // :459-465
+            throw Error("Combination of Major and minor moment not allowed: l=" + std::to_string(mm.first) + ", m" +
+                        std::to_string(mm.second));
+    DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NM);
+    std::vector<long> lm(2 * std::max<size_t>(mine.size(), 1));
+    for (size_t i = 0; i < mine.size(); i++) {
+        lm[2 * i] = multipole_index_[mine[i]].first;
+        lm[2 * i + 1] = multipole_index_[mine[i]].second;
+    }
+    double *partial = partial_buffer(dsp);
+    timer_.start("sd:c:block");
+    ck(be_.compute_mpsphere_partial(ctx_, qvector_.length(), lm.data(), mine.size(), dsp, partial),
+       "sgpu_compute_mpsphere_partial");
+    timer_.stop("sd:c:block");
+    reduce_and_finalize(dsp, 1.0 / (4 * M_PI));  // :395-400
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ScatterDeviceFactory (scatter_device_factory.cpp:23-210)
+// ---------------------------------------------------------------------------------------------------------------
+IScatterDevice *ScatterDeviceFactory::create(std::shared_ptr<ICommunicator> scatter_comm, Sample &sample,
+                                             IResultSink *sink, std::vector<CartesianCoor3D> &qvectors,
+                                             const Params &params, const SgpuBackend &be, sgpu_ctx *ctx) {
+    size_t NN = scatter_comm->size();
+    size_t NF = sample.NF;
+    size_t NA = sample.NA;
+    size_t NQ = qvectors.size();
+    if (NF < 1) throw Error("No frames available. Aborting");
+    if (NA < 1) throw Error("No atoms available. Aborting");
+    if (NQ < 1) throw Error("No qvectors left to compute. Aborting");
+
+    const std::string &stype = params.scattering.type;
+    size_t NAF = NA;
+    size_t ELBYTESIZE;
+    if (stype == "self") {
+        NAF = NA;
+        ELBYTESIZE = NF * 3 * sizeof(float);
+    } else if (stype == "all") {
+        NAF = NF;
+        ELBYTESIZE = NA * 3 * sizeof(float);
+    } else {
+        throw Error("Scattering Interference type not understood. Must be 'self' or 'all'.");
+    }
+    // every rank evaluates the (deterministic) plan; the reference computes it on rank 0 and broadcasts (:95-102)
+    DecompositionPlan dplan(NN, NQ, NAF, ELBYTESIZE, params.limits.stage_memory_data, params.limits.decomposition);
+    size_t partitions = dplan.partitions();
+    size_t partitionsize = dplan.partitionsize();
+
+    size_t allcommsize = partitions * partitionsize;
+    int allcommflag = scatter_comm->rank() < allcommsize ? 1 : 0;
+    std::shared_ptr<ICommunicator> all_comm = scatter_comm->split(allcommflag);
+    if (allcommflag == 0) return nullptr;
+
+    size_t partitionID = (all_comm->rank() * partitions) / allcommsize;
+    std::shared_ptr<ICommunicator> partition_comm = all_comm->split((int)partitionID);
+
+    DivAssignment qindex_assignment(partitions, partitionID, qvectors.size());
+    std::vector<CartesianCoor3D> thispartition_QIV;
+    for (size_t i = 0; i < qindex_assignment.size(); i++) thispartition_QIV.push_back(qvectors[qindex_assignment[i]]);
+
+    IScatterDevice *p_ScatterDevice = nullptr;
+    if (stype == "self") {
+        p_ScatterDevice = new SelfVectorsScatterDevice(all_comm, partition_comm, sample, thispartition_QIV, NAF, sink,
+                                                       params, be, ctx);
+    } else {
+        const std::string &otype = params.scattering.orientation_type;
+        if (otype == "vectors" || otype == "none") {
+            p_ScatterDevice = new AllVectorsScatterDevice(all_comm, partition_comm, sample, thispartition_QIV, NAF, sink,
+                                                          params, be, ctx);
+        } else if (otype == "multipole") {
+            if (params.scattering.multipole.type == "sphere") {
+                p_ScatterDevice = new MPSphereScatterDevice(all_comm, partition_comm, sample, thispartition_QIV, NAF,
+                                                            sink, params, be, ctx);
+            } else if (params.scattering.multipole.type == "cylinder") {
+                throw Error("MPCylinderScatterDevice is not part of the B200 hot path yet (SURVEY 8f-4)");
+            } else {
+                throw Error("scattering.average.orientation.multipole.type not understood: " +
+                            params.scattering.multipole.type);
+            }
+        }
+    }
+    if (p_ScatterDevice == nullptr) throw Error("Error initializing ScatterDevice");
+    return p_ScatterDevice;
+}
+
+}  // namespace sassena

@@ -1,0 +1,406 @@
+// sassena_host.hpp — host-side mirror of the reference's operator interface for the scattering hot path.
+//
+// Same names, argument meaning and control flow as the reference (benlabs/sassena v1.4.2):
+//   DivAssignment / ModAssignment      src/decomposition/assignment.cpp:27-132
+//   DecompositionPlan                  src/decomposition/decomposition_plan.cpp:29-156
+//   orientation / scan / moment generators   src/control/parameters.cpp:930-1189
+//   CartesianVectorBase                src/math/coor3d.cpp:278-304
+//   DataStagerByFrame / ByAtom         src/stager/data_stager.cpp:39-349
+//   IScatterDevice, AbstractScatterDevice, AbstractVectorsScatterDevice, AllVectorsScatterDevice,
+//   SelfVectorsScatterDevice, MPSphereScatterDevice, ScatterDeviceFactory    src/scatter_devices/*
+// What changed is what sits underneath: compute() drives the CUDA kernels through the C-ABI
+// (include/sassena_b200.h), a "rank" is one GPU, MPI collectives become one NCCL all-reduce of the packed
+// partial per |q|, and the boost::asio result service becomes an IResultSink callback.
+// Errors: the reference does Err::write(msg) + throw; here every such site throws sassena::Error(msg),
+// which the C wrapper (sass_capi.cpp) turns into a return code.
+#pragma once
+
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/sassena_host.h"
+
+namespace sassena {
+
+struct Error : std::runtime_error {
+    explicit Error(const std::string &m) : std::runtime_error(m) {}
+};
+// reference: sassena::terminate_request (include/exceptions/exceptions.hpp:26-29), thrown when ram_check fails
+struct terminate_request : Error {
+    terminate_request() : Error("terminate_request: memory limits exceeded") {}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// math/coor3d
+// ---------------------------------------------------------------------------------------------------------------
+struct CartesianCoor3D {
+    double x = 0, y = 0, z = 0;
+    CartesianCoor3D() = default;
+    CartesianCoor3D(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {}
+    double length() const;  // coor3d.cpp:58-60
+    CartesianCoor3D operator+(const CartesianCoor3D &o) const { return {x + o.x, y + o.y, z + o.z}; }
+    CartesianCoor3D operator-(const CartesianCoor3D &o) const { return {x - o.x, y - o.y, z - o.z}; }
+    double operator*(const CartesianCoor3D &o) const { return x * o.x + y * o.y + z * o.z; }
+    CartesianCoor3D cross_product(const CartesianCoor3D &o) const {
+        return {y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x};
+    }
+};
+inline CartesianCoor3D operator*(double l, const CartesianCoor3D &c) { return {l * c.x, l * c.y, l * c.z}; }
+inline CartesianCoor3D operator/(const CartesianCoor3D &c, double l) { return {c.x / l, c.y / l, c.z / l}; }
+
+// orthonormal base (e_r, e_phi, e_z) built "out of thin air" from an axis, coor3d.cpp:278-304
+class CartesianVectorBase {
+    std::vector<CartesianCoor3D> base_;
+
+   public:
+    explicit CartesianVectorBase(CartesianCoor3D axis);
+    CartesianCoor3D &operator[](size_t i) { return base_.at(i); }
+    CartesianCoor3D project(CartesianCoor3D vec);
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// decomposition
+// ---------------------------------------------------------------------------------------------------------------
+class DivAssignment {
+    size_t NN_, rank_, NAF_, offset_, size_;
+
+   public:
+    DivAssignment(size_t NN, size_t rank, size_t NAF);
+    size_t operator[](size_t index) const;
+    size_t size() const { return size_; }
+    size_t offset() const { return offset_; }
+    size_t max() const;
+    bool contains(size_t i) const;
+    size_t index(size_t i) const;
+};
+
+class ModAssignment {
+    size_t NN_, rank_, NAF_, offset_, size_;
+
+   public:
+    ModAssignment(size_t NN, size_t rank, size_t NAF);
+    size_t operator[](size_t index) const;
+    size_t size() const { return size_; }
+    size_t offset() const { return offset_; }
+    size_t max() const;
+    bool contains(size_t i) const;
+    size_t index(size_t i) const;
+};
+
+class DecompositionParameters {
+    size_t m_penalty, m_NAFcycles, m_NQcycles, m_NNpP, m_NN, m_NQ, m_NAF, m_NP, m_elbytesize, m_nbytesize;
+
+   public:
+    DecompositionParameters(size_t NN, size_t NQ, size_t NAF, size_t NNpP, size_t elbytesize);
+    size_t penalty() const { return m_penalty; }
+    size_t nbytesize() const { return m_nbytesize; }
+    size_t get_NN() const { return m_NN; }
+    size_t get_NQ() const { return m_NQ; }
+    size_t get_NAF() const { return m_NAF; }
+    size_t get_NP() const { return m_NP; }
+    size_t get_NNpP() const { return m_NNpP; }
+    size_t get_NAFcycles() const { return m_NAFcycles; }
+    size_t get_NQcycles() const { return m_NQcycles; }
+};
+
+struct DecompositionLimits {  // limits.decomposition.* (parameters.cpp:634-636)
+    double utilization = 0.95;
+    bool partitions_automatic = true;
+    size_t partitions_size = 1;
+};
+
+class DecompositionPlan {
+    std::unique_ptr<DecompositionParameters> p_dp_best;
+
+   public:
+    DecompositionPlan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize,
+                      const DecompositionLimits &lim = DecompositionLimits());
+    size_t partitions() const { return p_dp_best->get_NP(); }
+    size_t partitionsize() const { return p_dp_best->get_NNpP(); }
+    size_t penalty() const { return p_dp_best->penalty(); }
+    double utilization() const;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// control: the part of Params the hot path reads (src/control/parameters.cpp:372-397, 612-636)
+// ---------------------------------------------------------------------------------------------------------------
+struct ScatteringVectorsScan {  // scattering.vectors.scans.scan (parameters.cpp:453-484)
+    CartesianCoor3D basevector{1, 0, 0};
+    double from = 0, to = 1, exponent = 1.0;
+    size_t points = 100;
+};
+// ScatteringVectorsParameters::create_from_scans, parameters.cpp:1125-1189 (powf-rounded fractions)
+std::vector<CartesianCoor3D> create_from_scans(const std::vector<ScatteringVectorsScan> &scans);
+
+struct OrientationVectorsParameters {  // scattering.average.orientation.vectors.*
+    std::string type = "sphere";       // sphere | cylinder | file
+    std::string algorithm = "boost_uniform_on_sphere";
+    size_t resolution = 100;
+    uint32_t seed = 0;
+    std::vector<CartesianCoor3D> vectors;  // filled by create() or given explicitly (type=file rows)
+    // ScatteringAverageOrientationVectorsParameters::create, parameters.cpp:930-1034.
+    // For type=="file" the rows already in `vectors` are normalised (:932-943).
+    void create();
+};
+
+struct OrientationMultipoleParameters {  // scattering.average.orientation.multipole.*
+    std::string type = "sphere";         // sphere | cylinder
+    std::string moments_type;            // resolution | file  (no default in the reference, :1037-1079)
+    long resolution = 20;
+    std::vector<std::pair<long, long>> moments;
+    void create();  // parameters.cpp:1037-1122
+};
+
+struct ScatteringParameters {
+    std::string type = "all";  // all | self
+    std::string dsp_type = "autocorrelate";
+    std::string dsp_method = "fftw";
+    std::string orientation_type = "none";  // none | vectors | multipole
+    CartesianCoor3D axis{0, 0, 1};
+    OrientationVectorsParameters vectors;
+    OrientationMultipoleParameters multipole;
+};
+
+struct LimitsParameters {
+    // limits.stage.memory.data re-targeted: bytes of coordinates one GPU may hold (default 150 GB of the 180 GB HBM3e)
+    size_t stage_memory_data = (size_t)150 << 30;
+    DecompositionLimits decomposition;
+};
+
+struct Params {
+    ScatteringParameters scattering;
+    LimitsParameters limits;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// plumbing that replaces boost::mpi::communicator, HDF5WriterClient and the sgpu library binding
+// ---------------------------------------------------------------------------------------------------------------
+class ICommunicator {
+   public:
+    virtual ~ICommunicator() {}
+    virtual size_t rank() const = 0;
+    virtual size_t size() const = 0;
+    // sum `n` doubles in device memory over the ranks, result on every rank (NCCL all-reduce, f64)
+    virtual void allreduce_sum(double *d_buf, size_t n) = 0;
+    virtual void barrier() = 0;
+    // boost::mpi::communicator::split(color): ranks with equal color form a new communicator, ordered by old rank
+    virtual std::shared_ptr<ICommunicator> split(int color) = 0;
+};
+
+class SingleCommunicator : public ICommunicator {
+   public:
+    size_t rank() const override { return 0; }
+    size_t size() const override { return 1; }
+    void allreduce_sum(double *, size_t) override {}
+    void barrier() override {}
+    std::shared_ptr<ICommunicator> split(int) override { return std::make_shared<SingleCommunicator>(); }
+};
+
+// C callbacks (torch.distributed / NCCL live on the caller's side): sass_comm_vtbl, include/sassena_host.h
+class CallbackCommunicator : public ICommunicator {
+    sass_comm_vtbl v_;
+    bool owned_;
+
+   public:
+    CallbackCommunicator(const sass_comm_vtbl &v, bool owned) : v_(v), owned_(owned) {}
+    ~CallbackCommunicator() override;
+    size_t rank() const override { return v_.rank(v_.user); }
+    size_t size() const override { return v_.size(v_.user); }
+    void allreduce_sum(double *d, size_t n) override;
+    void barrier() override;
+    std::shared_ptr<ICommunicator> split(int color) override;
+};
+
+// the C-ABI as a table (sass_backend_vtbl, include/sassena_host.h), so that the host logic can be exercised
+// without a GPU in tests (tests/ bind it to the CPU oracle)
+using SgpuBackend = sass_backend_vtbl;
+const SgpuBackend &default_backend();  // the real library (sgpu_* of this .so)
+
+// Sample: what the hot path needs from sample_ (atoms in stager.target, frames, scattering factors)
+struct Sample {
+    size_t NA = 0, NF = 0;
+    const float *frames = nullptr;  // host [NF][NA][3], cartesian (CoordinateSets::load order, data_stager.cpp:102-118)
+    // ScatterFactors::update(q) + get_all() (scatter_factors.cpp:56-78,100): fill b[NA] for |q|
+    std::function<void(double ql, double *b)> factors;
+};
+
+// HDF5WriterClient::write(qvector, data, NF, data2, data3) stand-in (file_writer_service.cpp:504-531)
+class IResultSink {
+   public:
+    virtual ~IResultSink() {}
+    virtual void write(CartesianCoor3D qvector, const double *fqt, size_t NF, std::complex<double> fq,
+                       std::complex<double> fq2) = 0;
+};
+
+// named wall-clock timers with the reference's keys (sd:stage, sd:compute, sd:c:init, ... report/timer.cpp:35-59)
+class Timer {
+    std::map<std::string, std::pair<double, size_t>> acc_;  // sum seconds, count
+    std::map<std::string, double> start_;
+
+   public:
+    void start(const std::string &key);
+    void stop(const std::string &key);
+    double sum(const std::string &key) const;
+    size_t count(const std::string &key) const;
+    std::vector<std::string> keys() const;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// stager
+// ---------------------------------------------------------------------------------------------------------------
+class DataStagerByFrame {  // data_stager.cpp:39-129
+    Sample &m_sample;
+    ICommunicator &allcomm_, &partitioncomm_;
+    Timer &timer_;
+    const SgpuBackend &be_;
+    sgpu_ctx *ctx_;
+    const Params &params_;
+
+   public:
+    DataStagerByFrame(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
+                      const SgpuBackend &be, sgpu_ctx *ctx, const Params &params);
+    void stage(int repr);  // coordinates end up resident on this rank's GPU, frame-major
+};
+
+class DataStagerByAtom {  // data_stager.cpp:176-349
+    Sample &m_sample;
+    ICommunicator &allcomm_, &partitioncomm_;
+    Timer &timer_;
+    const SgpuBackend &be_;
+    sgpu_ctx *ctx_;
+    const Params &params_;
+
+   public:
+    DataStagerByAtom(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
+                     const SgpuBackend &be, sgpu_ctx *ctx, const Params &params);
+    void stage();  // ModAssignment(partition size, partition rank, NA) atoms, atom-major on the GPU
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// scatter devices
+// ---------------------------------------------------------------------------------------------------------------
+class IScatterDevice {
+   protected:
+    virtual void runner() = 0;
+    virtual size_t status() = 0;
+    virtual double progress() = 0;
+
+   public:
+    virtual ~IScatterDevice() {}
+    virtual Timer &getTimer() = 0;
+    virtual void run() = 0;
+};
+
+class AbstractScatterDevice : public IScatterDevice {
+   protected:
+    std::shared_ptr<ICommunicator> allcomm_, partitioncomm_;
+    Sample &sample_;
+    std::vector<CartesianCoor3D> vectors_;
+    size_t current_vector_ = 0;
+    IResultSink *p_hdf5writer_;
+    const Params &params_;
+    const SgpuBackend &be_;
+    sgpu_ctx *ctx_ = nullptr;
+    bool own_ctx_ = false;
+
+    size_t NN, NF, NA;
+    std::vector<double> atfinal_;  // [NF][2]
+    std::complex<double> afinal_, a2final_;
+    std::vector<double> factors_;  // ScatterFactors::get_all() of this rank's staged atoms
+    double *d_partial_ = nullptr;
+    size_t partial_cap_ = 0;
+    Timer timer_;
+
+    virtual void stage_data() = 0;
+    virtual void compute() = 0;
+    void next();
+    void write();
+    void runner() override;
+    virtual void print_pre_stage_info() {}
+    virtual void print_post_stage_info() {}
+    virtual void print_pre_runner_info() {}
+    virtual void print_post_runner_info() {}
+    virtual bool ram_check();
+    size_t status() override;
+    double progress() override;
+
+    // helpers shared by the concrete devices
+    void ck(int rc, const char *what);
+    int dsp_type_code() const;
+    int dsp_method_code() const;
+    double *partial_buffer(int dsp_type);
+    void reduce_and_finalize(int dsp_type, double scale);
+
+   public:
+    AbstractScatterDevice(std::shared_ptr<ICommunicator> allcomm, std::shared_ptr<ICommunicator> partitioncomm,
+                          Sample &sample, std::vector<CartesianCoor3D> vectors, size_t NAF, IResultSink *sink,
+                          const Params &params, const SgpuBackend &be, sgpu_ctx *ctx);
+    ~AbstractScatterDevice() override;
+    Timer &getTimer() override { return timer_; }
+    void run() override;
+};
+
+class AbstractVectorsScatterDevice : public AbstractScatterDevice {
+   protected:
+    std::vector<CartesianCoor3D> subvector_index_;
+    size_t NM = 0;
+    size_t current_subvector_ = 0;
+    double progress() override;
+    void init_subvectors(CartesianCoor3D &q);  // abstract_vectors_scatter_device.cpp:112-175
+
+   public:
+    using AbstractScatterDevice::AbstractScatterDevice;
+    const std::vector<CartesianCoor3D> &subvectors() const { return subvector_index_; }
+};
+
+class AllVectorsScatterDevice : public AbstractVectorsScatterDevice {
+   protected:
+    void stage_data() override;
+    void compute() override;
+
+   public:
+    using AbstractVectorsScatterDevice::AbstractVectorsScatterDevice;
+};
+
+class SelfVectorsScatterDevice : public AbstractVectorsScatterDevice {
+   protected:
+    ModAssignment assignment_;
+    void stage_data() override;
+    void compute() override;
+
+   public:
+    SelfVectorsScatterDevice(std::shared_ptr<ICommunicator> allcomm, std::shared_ptr<ICommunicator> partitioncomm,
+                             Sample &sample, std::vector<CartesianCoor3D> vectors, size_t NAF, IResultSink *sink,
+                             const Params &params, const SgpuBackend &be, sgpu_ctx *ctx);
+};
+
+class MPSphereScatterDevice : public AbstractScatterDevice {
+   protected:
+    std::vector<std::pair<long, long>> multipole_index_;
+    CartesianCoor3D qvector_;
+    size_t NM = 0;
+    void init_moments(CartesianCoor3D &q);  // multipole_scatter_device.cpp:155-165
+    void stage_data() override;
+    void compute() override;
+
+   public:
+    using AbstractScatterDevice::AbstractScatterDevice;
+};
+
+class ScatterDeviceFactory {  // scatter_device_factory.cpp:23-210
+   public:
+    // returns nullptr on spare ranks (scatter_device_factory.cpp:116-120)
+    static IScatterDevice *create(std::shared_ptr<ICommunicator> scatter_comm, Sample &sample, IResultSink *sink,
+                                  std::vector<CartesianCoor3D> &qvectors, const Params &params,
+                                  const SgpuBackend &be = default_backend(), sgpu_ctx *ctx = nullptr);
+};
+
+}  // namespace sassena

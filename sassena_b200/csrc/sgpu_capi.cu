@@ -217,6 +217,15 @@ size_t dsp_work_bytes(const sgpu_ctx *ctx, size_t nt, int dsp_type) {
     return std::max(b, corr_work_bytes(&ctx->plan, 1));
 }
 
+int zero_partial(sgpu_ctx *ctx, int dsp_type, double *d_partial) {
+    if (ctx->mode == 0) return fail(ctx, SGPU_ESTATE, "compute: nothing staged");
+    if (!d_partial) return fail(ctx, SGPU_EINVAL, "compute: d_partial is NULL");
+    int rc = ensure_plan(ctx);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_partial, 0, partial_len(ctx, dsp_type) * sizeof(double), ctx->stream));
+    return SGPU_OK;
+}
+
 int ensure_internal_partial(sgpu_ctx *ctx, int dsp_type) {
     return ensure<double>(ctx, &ctx->d_partial, &ctx->partial_cap, partial_len(ctx, dsp_type));
 }
@@ -238,6 +247,9 @@ int sgpu_init(int device, sgpu_ctx **out) {
         return fail(nullptr, SGPU_ECUDA,
                     std::string("sgpu_init: no CUDA device available (") + cudaGetErrorString(e) +
                         "); this library has no CPU fallback");
+    }
+    if (device == -1) {  // the device this process is already bound to
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
     }
     if (device < 0 || device >= count) return fail(nullptr, SGPU_EINVAL, "sgpu_init: device index out of range");
     CK(cudaSetDevice(device));
@@ -511,6 +523,7 @@ int sgpu_compute_all_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t 
     CK(cudaSetDevice(ctx->device));
     int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
     if (rc) return rc;
+    if (NM == 0) return zero_partial(ctx, dsp_type, d_partial);  // a rank without subvectors contributes zeros
     if (!qvecs) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors: qvecs is NULL");
     if (ctx->mode == 1 && ctx->repr != SGPU_REPR_CARTESIAN)
         return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors: staged frames are not cartesian");
@@ -551,6 +564,7 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
     CK(cudaSetDevice(ctx->device));
     int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
     if (rc) return rc;
+    if (NM == 0) return zero_partial(ctx, dsp_type, d_partial);  // a rank without atoms contributes zeros
     if (!qvecs) return fail(ctx, SGPU_EINVAL, "sgpu_compute_self_vectors: qvecs is NULL");
     if (ctx->mode != 2) return fail(ctx, SGPU_ESTATE, "sgpu_compute_self_vectors: atoms are not staged (stage_atoms first)");
     if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, "sgpu_compute_self_vectors: scattering factors not set for the staged atoms");
@@ -597,6 +611,7 @@ int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, si
     CK(cudaSetDevice(ctx->device));
     int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
     if (rc) return rc;
+    if (NM == 0) return zero_partial(ctx, dsp_type, d_partial);  // a rank without moments contributes zeros
     if (!lm) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: lm is NULL");
     if (ctx->mode == 1 && ctx->repr != SGPU_REPR_SPHERICAL)
         return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: staged frames are not in spherical representation");

@@ -1,0 +1,271 @@
+"""Python face of the C++ host layer (csrc/host): Params, ScatterDeviceFactory::create + IScatterDevice::run,
+communicator adapters for torch.distributed, and the pure host logic.  No compute happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _host
+from ._lib import load_library
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _lib():
+    return load_library()
+
+
+def _ck(rc):
+    if rc:
+        raise HostError(_lib().sass_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host logic
+# ---------------------------------------------------------------------------------------------------------------
+def div_assignment(NN, rank, NAF):
+    o, s, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _ck(_lib().sass_div_assignment(NN, rank, NAF, C.byref(o), C.byref(s), C.byref(m)))
+    return o.value, s.value, m.value
+
+
+def mod_assignment(NN, rank, NAF):
+    o, s, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _ck(_lib().sass_mod_assignment(NN, rank, NAF, C.byref(o), C.byref(s), C.byref(m)))
+    return o.value, s.value, m.value
+
+
+def decomposition_plan(nn, nq, naf, elbytes, maxbytes, utilization=0.95, automatic=True, manual_size=1):
+    p, ps, pen = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _ck(_lib().sass_decomposition_plan(nn, nq, naf, elbytes, maxbytes, utilization, int(automatic), manual_size,
+                                       C.byref(p), C.byref(ps), C.byref(pen)))
+    return p.value, ps.value, pen.value
+
+
+def create_from_scans(scans):
+    """scans: list of dict(base, from, to, points, exponent) -> q-vectors [N][3] (parameters.cpp:1125-1189)."""
+    rows = np.array([[*s.get("base", (1, 0, 0)), s.get("from", 0.0), s.get("to", 1.0), s.get("points", 100),
+                      s.get("exponent", 1.0)] for s in scans], dtype=np.float64).reshape(-1, 7)
+    n = _lib().sass_create_from_scans(_dp(rows), len(rows), None, 0)
+    if n == 0 and _lib().sass_last_error():
+        if len(scans) > 3:
+            raise HostError(_lib().sass_last_error().decode())
+    out = np.zeros((max(n, 1), 3))
+    _lib().sass_create_from_scans(_dp(rows), len(rows), _dp(out), n)
+    return out[:n]
+
+
+class Params:
+    """The part of the scatter.xml Params the hot path reads; keys are the XML paths."""
+
+    def __init__(self, **kv):
+        self.h = C.c_void_p(_lib().sass_params_new())
+        for k, v in kv.items():
+            self.set(k.replace("__", "."), v)
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib().sass_params_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set(self, key, value):
+        if isinstance(value, bool):
+            value = "true" if value else "false"
+        _ck(_lib().sass_params_set(self.h, key.encode(), str(value).encode()))
+        return self
+
+    def set_vectors(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+        _ck(_lib().sass_params_set_vectors(self.h, _dp(v), len(v)))
+        return self
+
+    def set_moments(self, lm):
+        lm = np.ascontiguousarray(lm, dtype=np.int64).reshape(-1, 2)
+        _ck(_lib().sass_params_set_moments(self.h, lm.ctypes.data_as(C.POINTER(C.c_long)), len(lm)))
+        return self
+
+    def create(self):
+        _ck(_lib().sass_params_create(self.h))
+        return self
+
+    @property
+    def vectors(self):
+        n = _lib().sass_params_num_vectors(self.h)
+        out = np.zeros((max(n, 1), 3))
+        _ck(_lib().sass_params_get_vectors(self.h, _dp(out)))
+        return out[:n]
+
+    @property
+    def moments(self):
+        n = _lib().sass_params_num_moments(self.h)
+        out = np.zeros((max(n, 1), 2), dtype=np.int64)
+        _ck(_lib().sass_params_get_moments(self.h, out.ctypes.data_as(C.POINTER(C.c_long))))
+        return out[:n]
+
+    def init_subvectors(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        n = _lib().sass_init_subvectors(self.h, _dp(q), None, 0)
+        out = np.zeros((max(n, 1), 3))
+        _lib().sass_init_subvectors(self.h, _dp(q), _dp(out), n)
+        return out[:n]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# communicators
+# ---------------------------------------------------------------------------------------------------------------
+class _DevPtr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class TorchDistCommunicator:
+    """boost::mpi::communicator stand-in over torch.distributed.  device_memory=True: buffers are CUDA pointers and
+    the group is NCCL; False: host pointers (gloo), used by the CPU tests of the host logic.
+    The C++ side copies the callback table into the communicators it derives with split(), replacing only `user`,
+    so every callback dispatches on the `user` handle through the registry."""
+
+    _registry = {}
+    _next = [1]
+
+    def __init__(self, group=None, device_memory=True):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.device_memory = device_memory
+        self.handle = self._next[0]
+        self._next[0] += 1
+        self._registry[self.handle] = self
+        cls = TorchDistCommunicator
+        self._cbs = (_host.RANK_FN(cls._rank), _host.SIZE_FN(cls._size), _host.ALLREDUCE_FN(cls._allreduce),
+                     _host.BARRIER_FN(cls._barrier), _host.SPLIT_FN(cls._split), _host.RELEASE_FN(cls._release))
+        self.vtbl = _host.CommVtbl(C.c_void_p(self.handle), *self._cbs)
+
+    @classmethod
+    def _get(cls, user):
+        return cls._registry[int(user)]
+
+    @staticmethod
+    def _rank(user):
+        self = TorchDistCommunicator._get(user)
+        return self.dist.get_rank(self.group)
+
+    @staticmethod
+    def _size(user):
+        self = TorchDistCommunicator._get(user)
+        return self.dist.get_world_size(self.group)
+
+    @staticmethod
+    def _allreduce(user, ptr, n):
+        try:
+            import torch
+            self = TorchDistCommunicator._get(user)
+            if self.device_memory:
+                t = torch.as_tensor(_DevPtr(ptr, n), device="cuda")
+                self.dist.all_reduce(t, group=self.group)
+                torch.cuda.synchronize()
+            else:
+                a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))
+                t = torch.from_numpy(a)
+                self.dist.all_reduce(t, group=self.group)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("allreduce callback failed:", e)
+            return 1
+
+    @staticmethod
+    def _barrier(user):
+        try:
+            self = TorchDistCommunicator._get(user)
+            self.dist.barrier(group=self.group)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("barrier callback failed:", e)
+            return 1
+
+    @staticmethod
+    def _split(user, color):
+        # every rank of this communicator calls split: gather the colors, create one group per color in the same
+        # order everywhere.  torch.distributed.new_group must be entered by ALL ranks of the job, so split() is only
+        # valid when called collectively by the whole job (true for the factory: scatter_device_factory.cpp:116,131).
+        try:
+            self = TorchDistCommunicator._get(user)
+            world = self.dist.get_world_size(self.group)
+            colors = [None] * world
+            self.dist.all_gather_object(colors, (int(color), self.dist.get_rank()), group=self.group)
+            # all communicators of the same generation must create the same groups: share the colour table job-wide
+            job = [None] * self.dist.get_world_size()
+            self.dist.all_gather_object(job, sorted(colors))
+            mine = None
+            seen = []
+            for table in job:
+                if table in seen:
+                    continue
+                seen.append(table)
+                for c in sorted(set(col for col, _ in table)):
+                    ranks = sorted(gr for col, gr in table if col == c)
+                    g = self.dist.new_group(ranks=ranks)
+                    if table == sorted(colors) and c == int(color):
+                        mine = g
+            child = TorchDistCommunicator(mine, self.device_memory)
+            return child.handle
+        except Exception as e:  # pragma: no cover
+            print("split callback failed:", e)
+            return None
+
+    @staticmethod
+    def _release(user):
+        TorchDistCommunicator._registry.pop(int(user), None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# run
+# ---------------------------------------------------------------------------------------------------------------
+def run_scatter(params: Params, frames, qvectors, b=None, factors_fn=None, comm: TorchDistCommunicator | None = None,
+                backend=None, ctx=None):
+    """ScatterDeviceFactory::create(...)->run().  frames: float32 [NF][NA][3]; qvectors [NQ][3].
+    Returns (records, has_device, timers): records = list of dict(q, fqt, fq0, fq, fq2) written by partition rank 0."""
+    frames = np.ascontiguousarray(frames, dtype=np.float32)
+    NF, NA, _ = frames.shape
+    q = np.ascontiguousarray(qvectors, dtype=np.float64).reshape(-1, 3)
+    records = []
+
+    def _write(user, qp, fqt, nf, fq, fq2):
+        records.append({"q": np.array([qp[0], qp[1], qp[2]]),
+                        "fqt": np.ctypeslib.as_array(fqt, shape=(2 * nf,)).copy().view(np.complex128),
+                        "fq": complex(fq[0], fq[1]), "fq2": complex(fq2[0], fq2[1])})
+        records[-1]["fq0"] = records[-1]["fqt"][0]
+
+    wcb = _host.WRITE_FN(_write)
+    if factors_fn is not None:
+        def _factors(user, ql, bp, na):
+            np.ctypeslib.as_array(bp, shape=(na,))[:] = factors_fn(ql)
+        fcb = _host.FACTORS_FN(_factors)
+        bptr = None
+    else:
+        fcb = C.cast(None, _host.FACTORS_FN)
+        barr = np.ascontiguousarray(b, dtype=np.float64)
+        bptr = _dp(barr)
+    has = C.c_int(0)
+    timers = C.create_string_buffer(4096)
+    rc = _lib().sass_scatter_run(params.h, C.byref(comm.vtbl) if comm is not None else None,
+                                 C.byref(backend) if backend is not None else None,
+                                 C.c_void_p(ctx) if ctx else None, NA, NF, frames.ctypes.data, bptr, fcb, None,
+                                 _dp(q), len(q), wcb, None, C.byref(has), timers, len(timers))
+    _ck(rc)
+    tm = {}
+    for item in timers.value.decode().split(";"):
+        if "=" in item:
+            k, v = item.split("=")
+            s, c = v.split(":")
+            tm[k] = (float(s), int(c))
+    return records, bool(has.value), tm

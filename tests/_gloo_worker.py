@@ -1,0 +1,55 @@
+"""worker for test_multirank_gloo.py: one rank of a world_size-N gloo job driving the host layer over the
+oracle-bound backend (CPU).  Writes the records gathered on rank 0 to the path in argv[1]."""
+import os
+import pickle
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch.distributed as dist  # noqa: E402
+
+from oracle_backend import OracleBackend  # noqa: E402
+from sassena_b200 import host, synth  # noqa: E402
+
+
+def main():
+    out_path, case = sys.argv[1], sys.argv[2]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    be = OracleBackend()
+    comm = host.TorchDistCommunicator(None, device_memory=False)
+    NA, NF = 23, 12
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3, offset=-10.0)
+    b = synth.factors(NA)
+    qv = host.create_from_scans([{"base": (1, 0, 0), "from": 0.3, "to": 1.5, "points": 5}])
+    p = host.Params()
+    if case.startswith("all"):
+        p.set("scattering.average.orientation.type", "vectors").set("scattering.average.orientation.vectors.type", "file")
+        p.set_vectors(synth.unit_vectors(7, 1))
+    elif case.startswith("self"):
+        p.set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
+        p.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(3, 1))
+    elif case.startswith("mp"):
+        p.set("scattering.average.orientation.type", "multipole")
+        p.set("scattering.average.orientation.multipole.moments.type", "resolution")
+        p.set("scattering.average.orientation.multipole.moments.resolution", 3).set("scattering.dsp.type", "square")
+    if case.endswith("_manual1"):  # partitions of one rank each: every rank owns a |q| subset, no all-reduce
+        p.set("limits.decomposition.partitions.automatic", False).set("limits.decomposition.partitions.size", 1)
+        p.set("limits.decomposition.utilization", 0.0)
+    p.create()
+    recs, has, tm = host.run_scatter(p, xyz, qv, b=b, comm=comm, backend=be.vtbl)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rank, has, recs, sorted(tm)))
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            pickle.dump(gathered, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+"""TEST-ONLY binding of the host layer's backend table (sass_backend_vtbl) to the CPU oracle.
+
+Lets the multi-rank host logic (factory, partitions, staging decomposition, all-reduce of partials, result
+sink) run on CPU with gloo.  "Device" pointers are host pointers here.  The packed partial of this backend is
+[atfinal sum (2 NF) | afinal (2) | a2final (2)] for every dsp type (correlation is linear in the timelines' sums).
+Never imported by the product."""
+import ctypes as C
+
+import numpy as np
+
+from oracle import oracle as o
+from sassena_b200 import _host
+
+_DSP = {0: "autocorrelate", 1: "square", 2: "plain"}
+
+
+class OracleBackend:
+    def __init__(self):
+        self.ctxs = {}
+        self.bufs = {}
+        self.next = 1
+        self.err = b""
+        cbs = dict(
+            init=_host.BE_INIT(self._init), destroy=_host.BE_DESTROY(self._destroy),
+            last_error=_host.BE_LAST_ERROR(self._last_error), synchronize=_host.BE_SYNC(lambda c: 0),
+            stage_frames=_host.BE_STAGE_FRAMES(self._stage_frames), frames_to_spherical=_host.BE_TO_SPH(self._to_sph),
+            stage_atoms=_host.BE_STAGE_ATOMS(self._stage_atoms),
+            stage_atoms_from_frames=_host.BE_STAGE_ATOMS_FF(self._stage_atoms_ff),
+            set_factors=_host.BE_SET_FACTORS(self._set_factors), partial_len=_host.BE_PARTIAL_LEN(self._partial_len),
+            compute_all_vectors_partial=_host.BE_COMPUTE_VEC(self._compute_all),
+            compute_self_vectors_partial=_host.BE_COMPUTE_VEC(self._compute_self),
+            compute_mpsphere_partial=_host.BE_COMPUTE_MP(self._compute_mp), finalize=_host.BE_FINALIZE(self._finalize),
+            device_alloc=_host.BE_ALLOC(self._alloc), device_free=_host.BE_FREE(self._free))
+        self._cbs = cbs
+        self.vtbl = _host.BackendVtbl(**cbs)
+
+    # -- helpers
+    def _ctx(self, c):
+        return self.ctxs[int(c)]
+
+    def _init(self, dev, out):
+        h = self.next
+        self.next += 1
+        self.ctxs[h] = {}
+        out[0] = h
+        return 0
+
+    def _destroy(self, c):
+        self.ctxs.pop(int(c or 0), None)
+
+    def _last_error(self, c):
+        return self.err
+
+    def _stage_frames(self, c, xyz, NF, NA, repr_):
+        a = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(NF, NA, 3)).copy()
+        self._ctx(c).update(mode=1, xyz=a, NF=NF, NA=NA, repr=repr_)
+        return 0
+
+    def _to_sph(self, c):
+        ctx = self._ctx(c)
+        ctx["xyz"] = o.cart_to_spherical(ctx["xyz"])
+        ctx["repr"] = 1
+        return 0
+
+    def _stage_atoms(self, c, xyz, NA, NF):
+        a = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(NA, NF, 3)).copy()
+        self._ctx(c).update(mode=2, xyz=a, NF=NF, NA=NA)
+        return 0
+
+    def _stage_atoms_ff(self, c, xyz, NF, NA, nranks, rank):
+        a = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(NF, NA, 3))
+        off, size, _ = o.mod_assignment(nranks, rank, NA)
+        ids = off + nranks * np.arange(size)
+        self._ctx(c).update(mode=2, xyz=np.ascontiguousarray(a[:, ids].transpose(1, 0, 2)), NF=NF, NA=size)
+        return 0
+
+    def _set_factors(self, c, b, n):
+        self._ctx(c)["b"] = np.ctypeslib.as_array(b, shape=(n,)).copy()
+        return 0
+
+    def _partial_len(self, c, dsp, out):
+        out[0] = 2 * self._ctx(c)["NF"] + 4
+        return 0
+
+    def _store(self, ctx, ptr, fqt, fq, fq2, unscale):
+        NF = ctx["NF"]
+        p = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * NF + 4,))
+        p[:2 * NF] = (fqt * unscale).view(np.float64)
+        p[2 * NF:2 * NF + 2] = (fq.real * unscale, fq.imag * unscale)
+        p[2 * NF + 2:] = (fq2.real * unscale, fq2.imag * unscale)
+
+    def _zero(self, ctx, ptr):
+        np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * ctx["NF"] + 4,))[:] = 0
+
+    def _compute_all(self, c, q, NM, dsp, ptr):
+        ctx = self._ctx(c)
+        if NM == 0:
+            self._zero(ctx, ptr)
+            return 0
+        qv = np.ctypeslib.as_array(q, shape=(NM, 3)).copy()
+        fqt, fq, fq2 = o.compute_all_vectors(ctx["xyz"], ctx["b"], qv, dsp=_DSP[dsp])
+        self._store(ctx, ptr, fqt, fq, fq2, NM)
+        return 0
+
+    def _compute_self(self, c, q, NM, dsp, ptr):
+        ctx = self._ctx(c)
+        if NM == 0:
+            self._zero(ctx, ptr)
+            return 0
+        qv = np.ctypeslib.as_array(q, shape=(NM, 3)).copy()
+        fqt, fq, fq2 = o.compute_self_vectors(ctx["xyz"], ctx["b"], qv, dsp=_DSP[dsp])
+        self._store(ctx, ptr, fqt, fq, fq2, NM)
+        return 0
+
+    def _compute_mp(self, c, ql, lm, NM, dsp, ptr):
+        ctx = self._ctx(c)
+        if NM == 0:
+            self._zero(ctx, ptr)
+            return 0
+        mom = np.ctypeslib.as_array(lm, shape=(NM, 2)).copy()
+        fqt, fq, fq2 = o.compute_mpsphere(ctx["xyz"], ctx["b"], ql, mom, dsp=_DSP[dsp])
+        self._store(ctx, ptr, fqt, fq, fq2, 4 * np.pi)
+        return 0
+
+    def _finalize(self, c, ptr, dsp, method, scale, at, af, a2f):
+        ctx = self._ctx(c)
+        NF = ctx["NF"]
+        p = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * NF + 4,))
+        out = np.ctypeslib.as_array(at, shape=(2 * NF,))
+        out[:] = p[:2 * NF] * scale
+        conj = dsp == 0 and method == 1
+        if conj:
+            out[1::2] *= -1
+        af[0], af[1] = p[2 * NF] * scale, (-1 if conj else 1) * p[2 * NF + 1] * scale
+        a2f[0], a2f[1] = p[2 * NF + 2] * scale, p[2 * NF + 3] * scale
+        return 0
+
+    def _alloc(self, out, nbytes):
+        buf = (C.c_char * max(nbytes, 8))()
+        addr = C.addressof(buf)
+        self.bufs[addr] = buf
+        out[0] = addr
+        return 0
+
+    def _free(self, p):
+        self.bufs.pop(int(p or 0), None)
+        return 0

@@ -326,3 +326,70 @@ def test_launch_counter_and_timers(gpu_ctx):
     assert gpu_ctx.launch_count > n0
     assert gpu_ctx.last_amplitude_ms() > 0
     assert gpu_ctx.last_dsp_ms() > 0
+
+
+def test_golden_fixtures_gpu(gpu_ctx):
+    """the CUDA path against the committed golden vectors (tests/golden, generated by the pinned oracle)"""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "coherent_small.npz"))
+    gpu_ctx.stage_frames(g["xyz"])
+    gpu_ctx.set_factors(g["b"])
+    for dsp, method in (("autocorrelate", "fftw"), ("autocorrelate", "direct"), ("square", "fftw"), ("plain", "fftw")):
+        for i, ql in enumerate(g["qls"]):
+            fqt, fq, fq2 = gpu_ctx.compute_all_vectors(ql * g["u"], dsp=dsp, method=method)
+            assert rel_err(fqt, g[f"all_{dsp}_{method}_{i}_fqt"]) < TOL
+            ref = g[f"all_{dsp}_{method}_{i}_fq"]
+            assert abs(fq - ref[0]) < TOL * abs(g[f"all_{dsp}_{method}_{i}_fqt"][0]) and abs(fq2 - ref[1]) <= TOL * abs(ref[1])
+    g = np.load(os.path.join(gold, "self_small.npz"))
+    gpu_ctx.stage_atoms(g["xyz_by_atom"])
+    gpu_ctx.set_factors(g["b"])
+    for i, ql in enumerate(g["qls"]):
+        fqt, fq, fq2 = gpu_ctx.compute_self_vectors(ql * g["u"])
+        assert rel_err(fqt, g[f"self_{i}_fqt"]) < TOL
+    g = np.load(os.path.join(gold, "mpsphere_small.npz"))
+    gpu_ctx.stage_frames(g["xyz"])
+    gpu_ctx.frames_to_spherical()
+    gpu_ctx.set_factors(g["b"])
+    for i, ql in enumerate(g["qls"]):
+        fqt, fq, fq2 = gpu_ctx.compute_mpsphere(ql, g["moments"])
+        assert rel_err(fqt, g[f"mp_{i}_fqt"]) < TOL
+
+
+def test_host_layer_devices_on_gpu(oracle):
+    """ScatterDeviceFactory::create + device.run() (C++ host layer) over the real CUDA backend: all three devices,
+    several |q| through the runner loop, results through the IResultSink callback."""
+    from sassena_b200 import host
+    NA, NF = 200, 48
+    xyz = synth.trajectory(NF, NA, 30.0, 0.2, 31, offset=-15.0)
+    b = synth.factors(NA)
+    qv = host.create_from_scans([{"base": (1, 0, 0), "from": 0.2, "to": 2.0, "points": 4}])
+    p = host.Params().set("scattering.average.orientation.type", "vectors")
+    p.set("scattering.average.orientation.vectors.resolution", 20).set("scattering.average.orientation.vectors.seed", 5)
+    p.create()
+    recs, has, tm = host.run_scatter(p, xyz, qv, factors_fn=lambda ql: b * (1.0 + 0.1 * ql))
+    assert has and len(recs) == 4 and tm["sd:compute"][1] == 4
+    for r, q in zip(recs, qv):
+        ref = oracle.compute_all_vectors(xyz, b * (1.0 + 0.1 * np.linalg.norm(q)), p.init_subvectors(q), nthreads=4)
+        assert rel_err(r["fqt"], ref[0]) < TOL and abs(r["fq"] - ref[1]) < TOL * abs(ref[0][0])
+        assert r["fq0"] == r["fqt"][0]
+    # cylinder orientation vectors
+    p.set("scattering.average.orientation.vectors.type", "cylinder").set("scattering.average.orientation.axis.x", 1).create()
+    recs, _, _ = host.run_scatter(p, xyz, [[0.3, 0.2, 0.5]], b=b)
+    ref = oracle.compute_all_vectors(xyz, b, p.init_subvectors([0.3, 0.2, 0.5]), nthreads=4)
+    assert rel_err(recs[0]["fqt"], ref[0]) < TOL
+    # self
+    ps = host.Params().set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
+    ps.set("scattering.average.orientation.vectors.resolution", 6).create()
+    recs, _, _ = host.run_scatter(ps, xyz[:, :40], qv[:2], b=b[:40])
+    for r, q in zip(recs, qv[:2]):
+        ref = oracle.compute_self_vectors(xyz[:, :40].transpose(1, 0, 2), b[:40], ps.init_subvectors(q), nthreads=4)
+        assert rel_err(r["fqt"], ref[0]) < TOL
+    # multipole sphere
+    pm = host.Params().set("scattering.average.orientation.type", "multipole")
+    pm.set("scattering.average.orientation.multipole.moments.type", "resolution")
+    pm.set("scattering.average.orientation.multipole.moments.resolution", 5).create()
+    recs, _, _ = host.run_scatter(pm, xyz, qv[1:3], b=b)
+    for r, q in zip(recs, qv[1:3]):
+        ref = oracle.compute_mpsphere(oracle.cart_to_spherical(xyz), b, np.linalg.norm(q), pm.moments, nthreads=4)
+        assert rel_err(r["fqt"], ref[0]) < TOL

@@ -1,0 +1,228 @@
+"""Host layer (C++ mirror of scatter_devices / stager / decomposition, csrc/host) against the oracle restatement and
+the reference's documented behaviour.  CPU only: no compute calls into the CUDA library."""
+import ctypes as C
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+from sassena_b200 import _lib, host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """the C-ABI library loads and exports every symbol include/*.h declares"""
+    lib = _lib.load_library()
+    for hdr in ("sassena_b200.h", "sassena_host.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        names = set(re.findall(r"\b(sgpu_[a-z0-9_]+|sass_[a-z0-9_]+)\s*\(", text))
+        names -= {"sass_factors_fn", "sass_write_fn"}
+        assert len(names) > 10
+        for n in sorted(names):
+            assert hasattr(lib, n), f"{n} declared in {hdr} but not exported"
+    assert lib.sgpu_version().startswith(b"sassena_b200")
+
+
+def test_no_cpu_fallback_without_gpu():
+    """the product fails loudly when there is no CUDA device: no CPU path"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sassena_b200
+    with pytest.raises(sassena_b200.SgpuError) as e:
+        sassena_b200.ScatterContext(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("NN,NAF", list(itertools.product([1, 2, 3, 4, 7, 8, 16], [1, 2, 5, 10, 100, 1001])))
+def test_assignments_match_oracle_and_partition(oracle, NN, NAF):
+    """DivAssignment / ModAssignment (assignment.cpp:27-132): same arithmetic as the oracle, and the ranks' index
+    sets partition [0, NAF)"""
+    seen_div, seen_mod = [], []
+    for r in range(NN):
+        assert host.div_assignment(NN, r, NAF) == oracle.div_assignment(NN, r, NAF)
+        assert host.mod_assignment(NN, r, NAF) == oracle.mod_assignment(NN, r, NAF)
+        off, size, mx = host.div_assignment(NN, r, NAF)
+        seen_div += list(range(off, off + size))
+        assert size <= mx == -(-NAF // NN)
+        off, size, mx = host.mod_assignment(NN, r, NAF)
+        seen_mod += [off + i * NN for i in range(size)]
+    assert seen_div == list(range(NAF))
+    assert sorted(seen_mod) == list(range(NAF))
+
+
+def test_decomposition_plan_worked_example():
+    """config 1 under 4 ranks (NQ=10, NAF=NF=100): ties go to the largest partition"""
+    assert host.decomposition_plan(4, 10, 100, 1000 * 12, 500 << 20) == (1, 4, 0)
+    # manual partition size 2 -> 2 partitions x 2
+    assert host.decomposition_plan(4, 10, 100, 12000, 500 << 20, automatic=False, manual_size=2)[:2] == (2, 2)
+    # memory limit forces more ranks per partition: NAFcycles*elbytes <= limit
+    p, ps, _ = host.decomposition_plan(8, 50, 10000, 1200000, 1250 * 1200000)
+    assert ps == 8 and p == 1
+    with pytest.raises(host.HostError):
+        host.decomposition_plan(8, 50, 10000, 1200000, 100 * 1200000)  # nothing fits
+    with pytest.raises(host.HostError):
+        host.decomposition_plan(7, 3, 5, 10, 1 << 30, utilization=0.99)  # utilisation too low
+
+
+@pytest.mark.parametrize("nn,nq,naf", [(4, 10, 100), (8, 50, 10000), (8, 20, 30000), (3, 7, 11), (16, 5, 3), (6, 1, 1000),
+                                       (5, 200, 1000)])
+def test_decomposition_plan_matches_oracle(oracle, nn, nq, naf):
+    rc, p, ps, pen = oracle.decomposition_plan(nn, nq, naf, 1200, 1 << 40, 0.0)
+    assert rc == 0
+    assert host.decomposition_plan(nn, nq, naf, 1200, 1 << 40, utilization=0.0) == (p, ps, pen)
+
+
+def test_scans_use_float_rounded_fractions(oracle):
+    """create_from_scans (parameters.cpp:1125-1189): powf() fractions, 1/2/3 nested scans"""
+    s1 = [{"base": (1, 0, 0), "from": 0.2, "to": 2.0, "points": 10}]
+    q = host.create_from_scans(s1)
+    assert np.array_equal(q, oracle.qvectors_from_scans(s1))
+    frac = np.float32(np.float32(3.0 / 9.0) ** np.float32(1.0))
+    assert q[3, 0] == 0.2 + float(frac) * (2.0 - 0.2)
+    assert q[3, 0] != 0.2 + (3.0 / 9.0) * 1.8  # not the double-precision fraction
+    s3 = [{"base": (1, 0, 0), "from": 0, "to": 1, "points": 3}, {"base": (0, 1, 0), "from": 0, "to": 2, "points": 2},
+          {"base": (0, 0, 1), "from": 1, "to": 3, "points": 1, "exponent": 2.0}]
+    q3 = host.create_from_scans(s3)
+    assert q3.shape == (6, 3)
+    assert np.array_equal(q3, oracle.qvectors_from_scans(s3))
+    with pytest.raises(host.HostError):
+        host.create_from_scans(s3 + s1)
+
+
+def test_orientation_generators(oracle):
+    """parameters.cpp:930-1034: sphere / cylinder (boost_uniform_on_sphere, raster_linear) / file"""
+    p = host.Params().set("scattering.average.orientation.type", "vectors")
+    p.set("scattering.average.orientation.vectors.resolution", 50).set("scattering.average.orientation.vectors.seed", 7)
+    p.create()
+    v = p.vectors
+    assert v.shape == (50, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-15)
+    assert np.array_equal(v, oracle.uniform_on_sphere(7, 3, 50))
+    p.set("scattering.average.orientation.vectors.type", "cylinder").create()
+    c = p.vectors
+    assert np.array_equal(c, oracle.uniform_on_sphere(7, 2, 50)) and np.all(c[:, 2] == 0)
+    p.set("scattering.average.orientation.vectors.algorithm", "raster_linear")
+    p.set("scattering.average.orientation.vectors.resolution", 1).create()
+    r = p.vectors
+    assert np.array_equal(r, oracle.cylinder_raster_linear(1)) and len(r) in (360, 361)
+    p.set("scattering.average.orientation.vectors.type", "file").set_vectors([[2, 0, 0], [0, 0, 0], [1, 1, 1]]).create()
+    f = p.vectors
+    assert np.allclose(f, [[1, 0, 0], [0, 0, 0], np.ones(3) / np.sqrt(3)])
+    p.set("scattering.average.orientation.vectors.type", "sphere")
+    p.set("scattering.average.orientation.vectors.algorithm", "quad")
+    with pytest.raises(host.HostError):
+        p.create()
+
+
+def test_mt19937_reference_stream(oracle):
+    """boost::mt19937 default-seeded 10000th output is 4123659995 (the generator's published check value)"""
+    s = oracle.mt19937_stream(5489, 10000)
+    assert int(s[-1]) == 4123659995
+
+
+def test_moments_generator(oracle):
+    p = host.Params().set("scattering.average.orientation.type", "multipole")
+    with pytest.raises(host.HostError):
+        p.create()  # moments.type has no default in the reference (parameters.cpp:1037-1079)
+    p.set("scattering.average.orientation.multipole.moments.type", "resolution")
+    p.set("scattering.average.orientation.multipole.moments.resolution", 20).create()
+    m = p.moments
+    assert len(m) == 441 and np.array_equal(m, oracle.moments_sphere(20))
+    assert tuple(m[0]) == (0, 0) and tuple(m[1]) == (1, -1) and tuple(m[-1]) == (20, 20)
+    p.set("scattering.average.orientation.multipole.moments.type", "file").set_moments([[1, 2]])
+    with pytest.raises(host.HostError):
+        p.create()  # |m| > l
+
+
+@pytest.mark.parametrize("axis,q", [((0, 0, 1), (0.3, 0.0, 0.4)), ((1, 1, 0), (0.1, 0.2, 0.3)), ((0, 0, 1), (0, 0, 0.7)),
+                                    ((0, 1, 0), (1.0, 0, 0))])
+def test_init_subvectors(oracle, axis, q):
+    """abstract_vectors_scatter_device.cpp:112-175 for none / sphere / cylinder (incl. the q_r == 0 quirk)"""
+    p = host.Params()
+    assert np.array_equal(p.init_subvectors(q), [q])
+    p.set("scattering.average.orientation.type", "vectors").set("scattering.average.orientation.vectors.resolution", 9)
+    p.create()
+    u = p.vectors
+    assert np.array_equal(p.init_subvectors(q), oracle.init_subvectors("sphere", q, u))
+    for k, a in zip("xyz", axis):
+        p.set(f"scattering.average.orientation.axis.{k}", a)
+    p.set("scattering.average.orientation.vectors.type", "cylinder").create()
+    c = p.vectors
+    got = p.init_subvectors(q)
+    assert np.array_equal(got, oracle.init_subvectors("cylinder", q, c, axis))
+    base = oracle.vector_base(axis)
+    if np.hypot(*(base[:2] @ np.array(q))) == 0:
+        assert len(got) == 1
+    else:
+        # every cylinder subvector keeps the component along the axis and the radial length
+        ez = base[2]
+        assert np.allclose(got @ ez, np.dot(q, ez))
+        assert np.allclose(np.linalg.norm(got - np.outer(got @ ez, ez), axis=1), np.linalg.norm(q - np.dot(q, ez) * ez))
+
+
+def test_params_errors():
+    p = host.Params()
+    with pytest.raises(host.HostError) as e:
+        p.set("scattering.target", "system")
+    assert "obsolete" in str(e.value)
+    with pytest.raises(host.HostError):
+        p.set("no.such.key", 1)
+    p.set("limits.decomposition.partitions.automatic", "TRUE").set("limits.decomposition.partitions.automatic", "0")
+    with pytest.raises(host.HostError):
+        p.set("limits.decomposition.partitions.automatic", "maybe")
+
+
+def test_run_scatter_single_rank_oracle_backend(oracle):
+    """factory + AllVectors/SelfVectors/MPSphere device.run() over the oracle-bound backend table: the host control
+    flow (init_subvectors, factors per |q|, write per |q|, 1/NM and 1/4pi scaling) reproduces the oracle."""
+    from oracle_backend import OracleBackend
+    from sassena_b200 import synth
+    be = OracleBackend()
+    NA, NF = 30, 16
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3, offset=-10.0)
+    b = synth.factors(NA)
+    qv = host.create_from_scans([{"base": (1, 0, 0), "from": 0.3, "to": 1.5, "points": 3}])
+    # coherent, sphere vectors given as file rows; |q|-dependent factors through the callback
+    p = host.Params().set("scattering.average.orientation.type", "vectors")
+    p.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(6, 1)).create()
+    recs, has, tm = host.run_scatter(p, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
+    assert has and len(recs) == 3 and tm["sd:compute"][1] == 3 and "sd:stage" in tm
+    for r, q in zip(recs, qv):
+        ref = oracle.compute_all_vectors(xyz, b * (1 + np.linalg.norm(q)), p.init_subvectors(q))
+        assert np.allclose(r["fqt"], ref[0], rtol=1e-12, atol=1e-12 * abs(ref[0][0]))
+        assert np.isclose(r["fq"], ref[1]) and np.isclose(r["fq2"], ref[2]) and r["fq0"] == r["fqt"][0]
+        assert np.array_equal(r["q"], q)
+    # self, no orientational average, direct method
+    p2 = host.Params().set("scattering.type", "self").set("scattering.dsp.method", "direct")
+    recs, _, _ = host.run_scatter(p2, xyz, qv[:1], b=b, backend=be.vtbl)
+    ref = oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b, qv[:1], method="direct")
+    assert np.allclose(recs[0]["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+    # multipole sphere
+    p3 = host.Params().set("scattering.average.orientation.type", "multipole")
+    p3.set("scattering.average.orientation.multipole.moments.type", "resolution")
+    p3.set("scattering.average.orientation.multipole.moments.resolution", 3).set("scattering.dsp.type", "square").create()
+    recs, _, _ = host.run_scatter(p3, xyz, qv[1:2], b=b, backend=be.vtbl)
+    ref = oracle.compute_mpsphere(oracle.cart_to_spherical(xyz), b, np.linalg.norm(qv[1]), p3.moments, dsp="square")
+    assert np.allclose(recs[0]["fqt"], ref[0], rtol=1e-12)
+    # error sites of the reference
+    with pytest.raises(host.HostError) as e:
+        host.run_scatter(host.Params().set("scattering.dsp.type", "cube"), xyz, qv, b=b, backend=be.vtbl)
+    assert "DSP type not understood" in str(e.value)
+    with pytest.raises(host.HostError) as e:
+        host.run_scatter(host.Params().set("scattering.type", "both"), xyz, qv, b=b, backend=be.vtbl)
+    assert "Must be 'self' or 'all'" in str(e.value)
+    with pytest.raises(host.HostError) as e:
+        host.run_scatter(host.Params(), xyz, np.zeros((0, 3)), b=b, backend=be.vtbl)
+    assert "No qvectors left to compute" in str(e.value)
+    pc = host.Params().set("scattering.average.orientation.type", "multipole")
+    pc.set("scattering.average.orientation.multipole.type", "cylinder")
+    pc.set("scattering.average.orientation.multipole.moments.type", "resolution").create()
+    with pytest.raises(host.HostError):
+        host.run_scatter(pc, xyz, qv, b=b, backend=be.vtbl)
+    with pytest.raises(host.HostError) as e:
+        host.run_scatter(host.Params().set("limits.stage.memory.data", 100), xyz, qv, b=b, backend=be.vtbl)
+    assert "decomposition failed" in str(e.value) or "Insufficient Buffer" in str(e.value)

@@ -1,0 +1,85 @@
+"""N>1 path of the host layer on CPU: world_size 2 and 3 gloo jobs (one process per "GPU") over the oracle-bound
+backend table.  Checks the factory's partitioning, the q-vector / atom / moment sharding inside a partition, the
+all-reduce of packed partials and that exactly the partition-rank-0 processes write results."""
+import os
+import pickle
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from sassena_b200 import host, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(world, case, tmp_path):
+    out = str(tmp_path / f"{case}_{world}.pkl")
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), out, case], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    logs = []
+    for p in procs:
+        o, _ = p.communicate(timeout=120)
+        logs.append(o.decode()[-2000:])
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    return pickle.load(open(out, "rb"))
+
+
+def _reference(oracle, case):
+    NA, NF = 23, 12
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3, offset=-10.0)
+    b = synth.factors(NA)
+    qv = host.create_from_scans([{"base": (1, 0, 0), "from": 0.3, "to": 1.5, "points": 5}])
+    out = []
+    for q in qv:
+        ql = np.linalg.norm(q)
+        if case.startswith("all"):
+            out.append(oracle.compute_all_vectors(xyz, b, ql * synth.unit_vectors(7, 1)))
+        elif case.startswith("self"):
+            out.append(oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b, ql * synth.unit_vectors(3, 1)))
+        else:
+            out.append(oracle.compute_mpsphere(oracle.cart_to_spherical(xyz), b, ql, oracle.moments_sphere(3), dsp="square"))
+    return qv, out
+
+
+@pytest.mark.parametrize("world,case", [(2, "all"), (2, "self"), (2, "mp"), (2, "all_manual1"), (3, "self"),
+                                        (3, "all_manual1")])
+def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
+    gathered = _run(world, case, tmp_path)
+    qv, ref = _reference(oracle, case)
+    records = {}
+    writers = 0
+    for rank, has, recs, timer_keys in gathered:
+        assert has, "no spare ranks expected in these cases"
+        assert "sd:compute" in timer_keys and "sd:stage" in timer_keys
+        writers += 1 if recs else 0
+        for r in recs:
+            key = tuple(np.round(r["q"], 12))
+            assert key not in records, "a |q| was written twice"
+            records[key] = r
+    if case.endswith("_manual1"):
+        assert writers == min(world, len(qv))  # every single-rank partition writes its own |q| subset
+    else:
+        assert writers == 1  # one partition: only its rank 0 writes (abstract_scatter_device.cpp:239-244)
+    assert len(records) == len(qv)
+    for q, (rfqt, rfq, rfq2) in zip(qv, ref):
+        r = records[tuple(np.round(q, 12))]
+        scale = abs(rfqt[0])
+        assert np.max(np.abs(r["fqt"] - rfqt)) < 1e-11 * scale
+        assert abs(r["fq"] - rfq) < 1e-11 * scale
+        assert abs(r["fq2"] - rfq2) < 1e-11 * abs(rfq2)

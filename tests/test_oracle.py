@@ -1,0 +1,166 @@
+"""Pins the CPU oracle (oracle/sassena_oracle.c): the reference ships no golden vectors or asserting tests for this
+path (PARITY UNPINNED), so the port is checked against independent numpy/scipy restatements, the analytic
+known answers KA1-KA5 derived from the cited formulas, and the committed golden fixtures (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.special as sp
+
+from sassena_b200 import synth
+from util import rel_err
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 30, 97, 200, 202, 1000, 2000, 2018, 4096, 6006])
+def test_fft_matches_numpy(oracle, n):
+    """own mixed-radix / Bluestein FFT (stands in for FFTW3) vs numpy.fft, both directions"""
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    assert rel_err(oracle.fft(x, -1), np.fft.fft(x)) < 1e-13
+    assert rel_err(oracle.fft(x, +1), np.fft.ifft(x) * n) < 1e-13
+
+
+@pytest.mark.parametrize("NF", [1, 2, 7, 100, 257])
+def test_autocorrelation_forms(oracle, NF):
+    """smath.cpp:141-156 (fftw) vs numpy; smath.cpp:51-76 (direct) vs an explicit sum; KA4: direct == conj(fftw)"""
+    rng = np.random.default_rng(NF)
+    a = rng.normal(size=NF) + 1j * rng.normal(size=NF)
+    f = oracle.auto_correlate_fftw(a)
+    d = oracle.auto_correlate_direct(a)
+    assert rel_err(f, oracle.np_autocorrelate(a, "fftw")) < 1e-13
+    assert rel_err(d, oracle.np_autocorrelate(a, "direct")) < 1e-13
+    assert rel_err(d, np.conj(f)) < 1e-12
+    # definition check of the fftw form: c[tau] = sum_k conj(a_k) a_{k+tau} / (NF - tau)
+    ref = np.array([np.sum(np.conj(a[:NF - t]) * a[t:]) / (NF - t) for t in range(NF)])
+    assert rel_err(f, ref) < 1e-13
+
+
+def test_special_functions_match_scipy(oracle):
+    """sph_bessel / spherical_harmonic stand-ins for Boost.Math vs scipy.special (same conventions as Boost:
+    theta polar, phi azimuth, Condon-Shortley)"""
+    for l in range(0, 31):
+        for x in np.concatenate([np.logspace(-6, 2.5, 120), [0.0, 1.0, float(l), l + 0.5]]):
+            r = sp.spherical_jn(l, x)
+            v = oracle.sph_bessel(l, x)
+            assert abs(v - r) <= 1e-12 * max(abs(r), 1e-3 / max(x, 1.0)), (l, x, v, r)
+    for n in range(0, 21):
+        for m in range(-n, n + 1):
+            for th, ph in [(0.0, 0.0), (0.3, 1.0), (np.pi / 2, 4.0), (2.9, 6.0), (np.pi, 0.5)]:
+                assert abs(oracle.spherical_harmonic(n, m, th, ph) - sp.sph_harm_y(n, m, th, ph)) < 1e-13
+    # closed forms l<=1
+    assert oracle.spherical_harmonic(0, 0, 0.7, 0.2) == pytest.approx(0.5 / np.sqrt(np.pi))
+    y11 = oracle.spherical_harmonic(1, 1, 0.7, 0.2)
+    assert y11 == pytest.approx(-0.5 * np.sqrt(1.5 / np.pi) * np.sin(0.7) * np.exp(0.2j))
+
+
+def test_amplitudes_and_compute_match_numpy(oracle):
+    """scatter() + dsp() + store() + 1/NM (all_vectors_scatter_device.cpp:231-439) vs vectorised numpy"""
+    NA, NF, NM = 50, 30, 11
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 5)
+    b = synth.factors(NA)
+    q = 1.4 * synth.unit_vectors(NM, 6)
+    for dsp, method in (("autocorrelate", "fftw"), ("autocorrelate", "direct"), ("square", "fftw"), ("plain", "fftw")):
+        fqt, fq, fq2, A = oracle.compute_all_vectors(xyz, b, q, dsp=dsp, method=method, return_amplitudes=True)
+        Anp = oracle.np_amplitudes_all(xyz, b, q)
+        assert rel_err(A, Anp) < 1e-13
+        rfqt, rfq, rfq2 = oracle.np_dsp_store(Anp, dsp, method)
+        assert rel_err(fqt, rfqt) < 1e-12 and abs(fq - rfq) < 1e-12 * abs(rfqt[0]) and abs(fq2 - rfq2) < 1e-12 * abs(rfq2)
+    # threads (the reference's worker threads) and the frame-split ranks do not change the result
+    base = oracle.compute_all_vectors(xyz, b, q)
+    thr = oracle.compute_all_vectors(xyz, b, q, nthreads=4)
+    fs = oracle.compute_all_vectors(xyz, b, q, nthreads=3, framesplit=True)
+    assert np.array_equal(base[0], thr[0]) and np.array_equal(base[0], fs[0])
+
+
+def test_self_matches_numpy(oracle):
+    NA, NF, NM = 9, 25, 4
+    xa = synth.trajectory(NF, NA, 20.0, 0.2, 7, layout=1)
+    b = synth.factors(NA)
+    q = 0.8 * synth.unit_vectors(NM, 8)
+    fqt, fq, fq2 = oracle.compute_self_vectors(xa, b, q)
+    # per-atom timelines: a[n,m,t] = b_n exp(i q_m . r_n(t))
+    ph = np.einsum("ntc,mc->nmt", xa.astype(np.float64), q)
+    T = (b[:, None, None] * np.exp(1j * ph)).reshape(NA * NM, NF)
+    rfqt, rfq, rfq2 = oracle.np_dsp_store(T, norm=1.0 / NM)
+    assert rel_err(fqt, rfqt) < 1e-12 and abs(fq - rfq) < 1e-12 * abs(rfqt[0]) and abs(fq2 - rfq2) < 1e-12 * abs(rfq2)
+
+
+def test_mpsphere_matches_scipy(oracle):
+    """multipole_scatter_device.cpp:467-497 with scipy's j_l and Y_lm; normalisation 1/(4 pi) (:395)"""
+    NA, NF, L = 14, 5, 4
+    xyz = synth.trajectory(NF, NA, 20.0, 0.3, 9, offset=-10.0)
+    sph = oracle.cart_to_spherical(xyz)
+    b = synth.factors(NA)
+    mom = oracle.moments_sphere(L)
+    ql = 0.9
+    fqt, fq, fq2, A = oracle.compute_mpsphere(sph, b, ql, mom, dsp="square", return_amplitudes=True)
+    r, phi, th = (sph[..., i].astype(np.float64) for i in range(3))
+    Aref = np.array([[np.sum(4 * np.pi * (1j ** l) * b * sp.spherical_jn(l, ql * r[f]) * np.conj(sp.sph_harm_y(l, m, th[f], phi[f])))
+                      for f in range(NF)] for l, m in mom])
+    assert rel_err(A, Aref) < 1e-12
+    rfqt, rfq, rfq2 = oracle.np_dsp_store(Aref, "square", norm=1 / (4 * np.pi))
+    assert rel_err(fqt, rfqt) < 1e-12
+    # cart -> spherical conversion (coor3d.cpp:168-215): theta = acos(z/r), phi in [0, 2 pi)
+    x = xyz.astype(np.float64)
+    assert np.allclose(r, np.linalg.norm(x, axis=-1), rtol=1e-6)
+    assert np.all((phi >= 0) & (phi < 2 * np.pi + 1e-6)) and np.all((th >= 0) & (th <= np.pi))
+    assert np.allclose(r * np.sin(th) * np.cos(phi), x[..., 0], atol=1e-4)
+    with pytest.raises(RuntimeError):
+        oracle.compute_mpsphere(sph, b, ql, [[1, 2]])
+
+
+def test_known_answers(oracle):
+    """KA1, KA2, KA3, KA5 of SURVEY 8c"""
+    NF, bb = 40, 6.65
+    static = np.tile(np.array([[1.5, -2.0, 0.25]], dtype=np.float32), (NF, 1, 1))
+    fqt, fq, fq2 = oracle.compute_all_vectors(static, [bb], [[0.3, 0.1, -0.7]])
+    assert np.allclose(fqt, bb ** 2, rtol=1e-13) and fq == pytest.approx(bb ** 2) and fq2 == pytest.approx(bb ** 4)
+    # KA2: linear motion, fftw -> e^{+i q v tau}, direct -> e^{-i q v tau}
+    v = 0.125
+    lin = np.zeros((NF, 1, 3), dtype=np.float32)
+    lin[:, 0, 0] = v * np.arange(NF)
+    tau = np.arange(NF)
+    f = oracle.compute_all_vectors(lin, [bb], [[0.8, 0, 0]], method="fftw")[0]
+    d = oracle.compute_all_vectors(lin, [bb], [[0.8, 0, 0]], method="direct")[0]
+    assert np.allclose(f, bb ** 2 * np.exp(1j * 0.8 * v * tau), atol=1e-12 * bb ** 2)
+    assert np.allclose(d, bb ** 2 * np.exp(-1j * 0.8 * v * tau), atol=1e-12 * bb ** 2)
+    # single atom, any trajectory: fq0 = b^2 exactly (up to rounding)
+    walk = synth.trajectory(NF, 1, 10.0, 0.5, 3)
+    assert oracle.compute_all_vectors(walk, [bb], [[0.4, 0.4, 0.1]])[0][0] == pytest.approx(bb ** 2, rel=1e-13)
+    # KA5: square -> fq = mean_t |A|^2, fq0 = fqt[0]
+    xyz = synth.trajectory(NF, 6, 10.0, 0.5, 4)
+    b6 = synth.factors(6)
+    q = [[0.4, 0.4, 0.1]]
+    sq = oracle.compute_all_vectors(xyz, b6, q, dsp="square", return_amplitudes=True)
+    assert sq[1] == pytest.approx(np.mean(np.abs(sq[3][0]) ** 2))
+    # KA3: two static atoms, multipole sphere average -> Debye formula (to the float32 staging accuracy)
+    d_, ql = 3.0, 1.1
+    two = np.zeros((2, 2, 3), dtype=np.float32)
+    two[:, 0] = (0.5, 0.25, -0.125)
+    two[:, 1] = (0.5, 0.25 + d_, -0.125)
+    bt = np.array([2.0, 3.5])
+    exact = bt[0] ** 2 + bt[1] ** 2 + 2 * bt[0] * bt[1] * np.sin(ql * d_) / (ql * d_)
+    mp = oracle.compute_mpsphere(oracle.cart_to_spherical(two), bt, ql, oracle.moments_sphere(14), dsp="square")
+    assert mp[0][0].real == pytest.approx(exact, rel=1e-6)
+
+
+def test_golden_fixtures(oracle):
+    """the committed golden vectors still come out of the oracle bit-for-bit (to 1e-13)"""
+    g = np.load(os.path.join(GOLD, "coherent_small.npz"))
+    for dsp, method in (("autocorrelate", "fftw"), ("autocorrelate", "direct"), ("square", "fftw"), ("plain", "fftw")):
+        for i, ql in enumerate(g["qls"]):
+            fqt, fq, fq2 = oracle.compute_all_vectors(g["xyz"], g["b"], ql * g["u"], dsp=dsp, method=method)
+            assert rel_err(fqt, g[f"all_{dsp}_{method}_{i}_fqt"]) < 1e-13
+            assert np.allclose([fq, fq2], g[f"all_{dsp}_{method}_{i}_fq"], rtol=1e-12)
+    g = np.load(os.path.join(GOLD, "self_small.npz"))
+    for i, ql in enumerate(g["qls"]):
+        fqt, fq, fq2 = oracle.compute_self_vectors(g["xyz_by_atom"], g["b"], ql * g["u"])
+        assert rel_err(fqt, g[f"self_{i}_fqt"]) < 1e-13
+    g = np.load(os.path.join(GOLD, "mpsphere_small.npz"))
+    for i, ql in enumerate(g["qls"]):
+        fqt, fq, fq2 = oracle.compute_mpsphere(oracle.cart_to_spherical(g["xyz"]), g["b"], ql, g["moments"])
+        assert rel_err(fqt, g[f"mp_{i}_fqt"]) < 1e-13
+    # the synthetic generator itself is part of the fixture contract
+    assert np.array_equal(synth.trajectory(24, 40, 25.0, 0.3, 101), np.load(os.path.join(GOLD, "coherent_small.npz"))["xyz"])
