@@ -336,7 +336,7 @@ def run_ours(args):
         prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                traffic = json.load(open(prof)).get("dram_bytes_per_frame") * NF  # one launch covers all NF frames
             except Exception:
                 traffic = None
         line = {
@@ -350,7 +350,7 @@ def run_ours(args):
             "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": traffic,
-                         "kernel": "amplitude_all_kernel", "kernel_share_of_step": amp_ms_max / ms_max,
+                         "kernel": "amplitude_all_tiled_kernel", "kernel_share_of_step": amp_ms_max / ms_max,
                          "algorithmic_flop_per_eval": FLOP_PER_EVAL,
                          "fp64_pipe_util_executed": evals_rank * FP64_INSTR_PER_EVAL * 2 / amp_s / 1e12 / fp64_peak,
                          "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
