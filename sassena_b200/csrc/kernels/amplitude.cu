@@ -11,6 +11,7 @@
 #include "kernels.hpp"
 #include "sincos_qt.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace sass {
@@ -650,6 +651,21 @@ int launch_synth_trajectory(float *d_xyz, size_t NF, size_t NA, size_t atom0, si
     const float box_scale = box / 16777216.0f;
     synth_trajectory_kernel<<<(unsigned)((NA_out + 127) / 128), 128, 0, st>>>(d_xyz, NF, NA, atom0, atom_stride, NA_out,
                                                                             box_scale, offset, step_scale, seed, layout);
+    return 1;
+}
+
+namespace {
+__global__ void copy_words_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+}  // namespace
+
+int launch_copy_words(void *d_dst, const void *mapped_src, size_t nwords, cudaStream_t st) {
+    if (nwords == 0) return 0;
+    unsigned blocks = (unsigned)std::min<size_t>((nwords + 255) / 256, 592);
+    copy_words_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_dst),
+                                               reinterpret_cast<const uint32_t *>(mapped_src), nwords);
     return 1;
 }
 

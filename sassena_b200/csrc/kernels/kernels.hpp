@@ -23,6 +23,9 @@ int launch_frames_to_atoms(const float *d_frames, float *d_atoms, size_t NF, siz
                            size_t atom0, size_t stride, size_t NA_out, cudaStream_t st);
 int launch_synth_trajectory(float *d_xyz, size_t NF, size_t NA, size_t atom0, size_t atom_stride, size_t NA_out,
                             float box, float offset, float step_scale, uint64_t seed, int layout, cudaStream_t st);
+// SM-driven copy of 4-byte words from mapped pinned host memory (keeps small uploads off the DMA engine, where they
+// would queue behind the stager's bulk copies)
+int launch_copy_words(void *d_dst, const void *mapped_src, size_t nwords, cudaStream_t st);
 // DFMA peak probe; returns flops executed
 double launch_fp64_peak(double *d_sink, int iters, int blocks, cudaStream_t st);
 
@@ -62,5 +65,28 @@ int dsp_elementwise_accumulate(const double2 *d_A, size_t ldA, size_t nt, size_t
 size_t dsp_elementwise_work_bytes(size_t nt);
 // out[i] = in[i]*scale (complex, n entries); acc_out[0..3] = acc[0..3]*scale
 int launch_scale_complex(const double2 *d_in, double2 *d_out, size_t n, double scale, cudaStream_t st);
+
+
+// ---- selffused.cu -------------------------------------------------------------------------------
+// fused self-scattering path (amplitudes + FFT autocorrelation in shared memory), dsp = autocorrelate
+struct SelfPlan {
+    size_t NF = 0;
+    int log2N = 0;   // sub-FFT length N = 2^log2N (<= 4096)
+    size_t N = 0;
+    int R = 0;       // residues; padded length L = R*N >= 2NF-1
+    size_t L = 0;
+    double2 *d_tw = nullptr;  // exp(-2 pi i k / N), k < N
+    double2 *d_w = nullptr;   // weights What[j][pos] (residue-major, digit-reversed position)
+    int *d_freq = nullptr;    // frequency index of a digit-reversed position
+};
+int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches);
+void self_plan_destroy(SelfPlan *p);
+size_t self_work_bytes(const SelfPlan *p, size_t ntl);
+// timelines of local atoms [atom0, atom0+natoms) x NM q-vectors; d_P[L] and d_acc[4] are accumulated (+=)
+int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const double *d_b, const double *d_qs,
+                          size_t NM, size_t atom0, size_t natoms, void *d_work, double *d_P, double *d_acc,
+                          cudaStream_t st);
+int self_finalize(const SelfPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
+                  cudaStream_t st);
 
 }  // namespace sass

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,8 +62,11 @@ struct sgpu_ctx {
     double2 *d_out = nullptr;
     size_t out_cap = 0;
     double *h_acc = nullptr;  // pinned, 4 doubles
+    char *h_up = nullptr;     // pinned + mapped staging area for small uploads (factors, q-vectors, moments)
+    size_t up_cap = 0;
 
     CorrPlan plan;
+    SelfPlan splan;  // fused self path (atoms mode, dsp=autocorrelate)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     bool have_times = false;
@@ -82,7 +86,9 @@ struct sgpu_ctx {
         if (d_partial) cudaFree(d_partial);
         if (d_out) cudaFree(d_out);
         if (h_acc) cudaFreeHost(h_acc);
+        if (h_up) cudaFreeHost(h_up);
         corr_plan_destroy(&plan);
+        self_plan_destroy(&splan);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
@@ -133,6 +139,29 @@ int ensure_work(sgpu_ctx *ctx, size_t bytes) {
     return rc;
 }
 
+// Small host->device upload that does not touch the DMA copy engine: the bytes go through a mapped pinned buffer and a
+// copy kernel on the compute stream.  (A cudaMemcpyAsync would queue behind the stager's multi-GB chunk copies on the
+// H2D engine and serialise staging with compute.)  Synchronous with respect to the host.
+int small_upload(sgpu_ctx *ctx, void *d_dst, const void *src, size_t bytes) {
+    const size_t words = (bytes + 3) / 4;
+    if (ctx->up_cap < words * 4) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_up) CK(cudaFreeHost(ctx->h_up));
+        ctx->h_up = nullptr;
+        ctx->up_cap = 0;
+        const size_t cap = std::max<size_t>(words * 4, (size_t)1 << 20);
+        CK(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_up), cap, cudaHostAllocMapped));
+        ctx->up_cap = cap;
+    }
+    memcpy(ctx->h_up, src, bytes);
+    void *d_view = nullptr;
+    CK(cudaHostGetDevicePointer(&d_view, ctx->h_up, 0));
+    ctx->launches += launch_copy_words(d_dst, d_view, words, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SGPU_OK;
+}
+
 void drop_chunks(sgpu_ctx *ctx) {
     for (auto &c : ctx->chunks) cudaEventDestroy(c.ready);
     ctx->chunks.clear();
@@ -162,7 +191,13 @@ int own_xyz_buffer(sgpu_ctx *ctx, size_t bytes) {
     return SGPU_OK;
 }
 
+int ensure_self_plan(sgpu_ctx *ctx);
+
 int ensure_plan(sgpu_ctx *ctx) {
+    if (ctx->mode == 2) {
+        int rc = ensure_self_plan(ctx);
+        if (rc) return rc;
+    }
     if (ctx->plan.NF == ctx->NF && ctx->plan.d_tw) return SGPU_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     corr_plan_destroy(&ctx->plan);
@@ -172,7 +207,21 @@ int ensure_plan(sgpu_ctx *ctx) {
     return SGPU_OK;
 }
 
+int ensure_self_plan(sgpu_ctx *ctx) {
+    if (ctx->splan.NF == ctx->NF && ctx->splan.d_tw) return SGPU_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    self_plan_destroy(&ctx->splan);
+    int rc = self_plan_create(&ctx->splan, ctx->NF, ctx->stream, &ctx->launches);
+    if (rc == 1) return fail(ctx, SGPU_EINVAL, "number of frames not supported by the self correlation plan");
+    if (rc) return fail(ctx, SGPU_ECUDA, std::string("self_plan_create: ") + cudaGetErrorString(cudaGetLastError()));
+    return SGPU_OK;
+}
+
+// atoms mode + autocorrelate uses the fused self plan (its padded length differs from the four-step plan's)
+bool uses_self_plan(const sgpu_ctx *ctx, int dsp_type) { return ctx->mode == 2 && dsp_type == SGPU_DSP_AUTOCORRELATE; }
+
 size_t partial_len(const sgpu_ctx *ctx, int dsp_type) {
+    if (uses_self_plan(ctx, dsp_type)) return ctx->splan.L + 4;
     return (dsp_type == SGPU_DSP_AUTOCORRELATE ? ctx->plan.L : 2 * ctx->NF) + 4;
 }
 
@@ -192,10 +241,7 @@ int upload_q(sgpu_ctx *ctx, const double *qvecs, size_t NM, size_t pad) {
     for (size_t i = 0; i < NM * 3; i++) ctx->h_qs[i] = qvecs[i] * kTwoOverPi;
     int rc = ensure<double>(ctx, &ctx->d_qs, &ctx->q_cap, NMpad * 3);
     if (rc) return rc;
-    // the host vector is reused by the next call: make the copy synchronous with respect to the host
-    CK(cudaMemcpyAsync(ctx->d_qs, ctx->h_qs.data(), NMpad * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return SGPU_OK;
+    return small_upload(ctx, ctx->d_qs, ctx->h_qs.data(), NMpad * 3 * sizeof(double));
 }
 
 // DSP of nt timelines in d_A (ld = NF) accumulated into the packed partial
@@ -342,7 +388,9 @@ int sgpu_stage_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, int
     rc = own_xyz_buffer(ctx, NF * frame_bytes);
     if (rc) return rc;
     // chunk by frames: big enough that one chunk is many waves of amplitude CTAs, small enough to overlap
-    size_t nfc = std::max<size_t>(1, ((size_t)256 << 20) / frame_bytes);
+    size_t chunk_mb = 256;
+    if (const char *e = getenv("SASSENA_STAGE_CHUNK_MB")) chunk_mb = std::max<size_t>(1, strtoull(e, nullptr, 10));
+    size_t nfc = std::max<size_t>(1, (chunk_mb << 20) / frame_bytes);
     for (size_t f0 = 0; f0 < NF; f0 += nfc) {
         const size_t nf = std::min(nfc, NF - f0);
         sgpu_ctx::Chunk c{f0, nf, nullptr};
@@ -483,8 +531,8 @@ int sgpu_set_factors(sgpu_ctx *ctx, const double *b, size_t n) {
     CK(cudaSetDevice(ctx->device));
     int rc = ensure<double>(ctx, &ctx->d_b, &ctx->b_cap, n);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->d_b, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    rc = small_upload(ctx, ctx->d_b, b, n * sizeof(double));
+    if (rc) return rc;
     ctx->nb = n;
     return SGPU_OK;
 }
@@ -538,6 +586,7 @@ int sgpu_compute_all_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t 
     for (auto &c : ctx->chunks)
         if (cudaEventQuery(c.ready) != cudaSuccess) all_ready = false;
     cudaGetLastError();
+    if (getenv("SASSENA_FORCE_CHUNKED")) all_ready = ctx->chunks.empty();
     if (all_ready) {
         drop_chunks(ctx);
         ctx->launches += launch_amplitude_all(ctx->d_xyz, ctx->d_b, ctx->d_qs, ctx->d_A, ctx->NF, ctx->NA, NM, 0,
@@ -575,11 +624,27 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
     rc = upload_q(ctx, qvecs, NM, 1);
     if (rc) return rc;
 
-    // batch atoms so that amplitudes + FFT scratch fit a memory budget
+    if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
+        // fused path: timelines are generated, transformed and reduced inside the SM (selffused.cu)
+        const SelfPlan &sp = ctx->splan;
+        size_t atoms_per_batch = std::max<size_t>(1, ((size_t)256 << 20) / (NM * (size_t)sp.R * sizeof(double2)));
+        atoms_per_batch = std::min(atoms_per_batch, ctx->NA);
+        rc = ensure_work(ctx, std::max(self_work_bytes(&sp, atoms_per_batch * NM), corr_work_bytes(&ctx->plan, 1)));
+        if (rc) return rc;
+        CK(cudaMemsetAsync(d_partial, 0, partial_len(ctx, dsp_type) * sizeof(double), ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (size_t n0 = 0; n0 < ctx->NA; n0 += atoms_per_batch) {
+            const size_t nn = std::min(atoms_per_batch, ctx->NA - n0);
+            ctx->launches += self_power_accumulate(&sp, ctx->d_xyz, ctx->d_b, ctx->d_qs, NM, n0, nn, ctx->d_work, d_partial,
+                                                   d_partial + sp.L, ctx->stream);
+            CK(cudaGetLastError());
+        }
+    } else {
+    // batch atoms so that amplitudes + scratch fit a memory budget
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>((free_b + ctx->work_cap + ctx->A_cap * sizeof(double2)) / 3, (size_t)24 << 30);
-    const size_t per_tl = corr_work_bytes(&ctx->plan, 1024) / 1024 + ctx->NF * sizeof(double2) + 64;
+    const size_t per_tl = ctx->NF * sizeof(double2) + 64;
     size_t nt_max = std::max<size_t>(budget / per_tl, NM);
     size_t atoms_per_batch = std::max<size_t>(1, nt_max / NM);
     atoms_per_batch = std::min(atoms_per_batch, ctx->NA);
@@ -597,6 +662,7 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
         CK(cudaGetLastError());
         rc = dsp_accumulate(ctx, nn * NM, dsp_type, d_partial);
         if (rc) return rc;
+    }
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
@@ -632,8 +698,8 @@ int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, si
     if (rc) return rc;
     rc = ensure<int>(ctx, &ctx->d_lm, &ctx->lm_cap, NM * 2);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->d_lm, h_lm.data(), NM * 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    rc = small_upload(ctx, ctx->d_lm, h_lm.data(), NM * 2 * sizeof(int));
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->copy_stream));
     drop_chunks(ctx);
     int nsplit = 1;
@@ -669,7 +735,12 @@ int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_
     if (rc) return rc;
     const bool conj = (dsp_type == SGPU_DSP_AUTOCORRELATE && dsp_method == SGPU_METHOD_DIRECT);
     const double *acc;
-    if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
+    if (uses_self_plan(ctx, dsp_type)) {
+        rc = ensure_work(ctx, self_work_bytes(&ctx->splan, 1));
+        if (rc) return rc;
+        ctx->launches += self_finalize(&ctx->splan, d_partial, ctx->d_work, ctx->d_out, scale, conj ? 1 : 0, ctx->stream);
+        acc = d_partial + ctx->splan.L;
+    } else if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
         ctx->launches += corr_finalize(&ctx->plan, d_partial, ctx->d_work, ctx->d_out, scale, conj ? 1 : 0, ctx->stream);
         acc = d_partial + ctx->plan.L;
     } else {

@@ -142,6 +142,25 @@ def test_self_vectors_small(gpu_ctx, oracle, dsp, method):
     assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
 
 
+@pytest.mark.parametrize("NF", [1, 2, 3, 33, 100, 1000, 2049, 5000])
+def test_self_vectors_frame_counts(gpu_ctx, oracle, NF):
+    """fused self path: padded length L = R*N with N = 2^k <= 4096; NF up to several residues (R = 1, 2, 3)"""
+    NA, NM = 3, 2
+    xyz = synth.trajectory(NF, NA, 30.0, 0.1, 17, layout=1)
+    b = synth.factors(NA)
+    q = 1.3 * synth.unit_vectors(NM, 18)
+    gpu_ctx.stage_atoms(xyz)
+    gpu_ctx.set_factors(b)
+    for method in ("fftw", "direct"):
+        fqt, fq, fq2 = gpu_ctx.compute_self_vectors(q, method=method)
+        rfqt, rfq, rfq2 = oracle.compute_self_vectors(xyz, b, q, method="fftw", nthreads=4)
+        if method == "direct":
+            rfqt, rfq = np.conj(rfqt), np.conj(rfq)
+        assert rel_err(fqt, rfqt) < TOL
+        assert abs(fq - rfq) < TOL * abs(rfqt[0])
+        assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
 def test_self_from_frames_modassignment(gpu_ctx, oracle):
     """frame-major input transposed on the GPU for the atoms of rank r under ModAssignment(NN, r, NA);
     the sum of the per-rank partials equals the single-rank result (self...:199-230 reduce)."""
