@@ -28,7 +28,6 @@ namespace {
 
 constexpr int SF_THREADS = 256;
 constexpr int SF_MAX_LOG2N = 12;  // N <= 4096 (64 KB of shared memory per CTA)
-constexpr int SF_SLOTS = (1 << SF_MAX_LOG2N) / SF_THREADS;
 
 __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -89,26 +88,120 @@ __device__ __forceinline__ void fft_dif_r4(double2 *s, int log2N, const double2 
 
 enum { GEN_AMPLITUDE = 0, GEN_WEIGHTS = 1 };
 
+// ---- register-resident radix-16 passes -------------------------------------------------------------------------------
+// The N-point transform (N = 256 .. 4096) is done in at most three passes: radix 16, radix 16, radix N/256.  In a pass a
+// thread loads the R inputs of one butterfly (stride q) into registers, runs an R-point DIF network with compile-time
+// twiddles, applies the inter-pass twiddles W_S^{k c} (c = 1..R-1, built from one table load by a multiplication tree)
+// and stores the results back in place.  Half the shared-memory traffic and barriers of radix-4 passes, and 16
+// independent loads per thread instead of 4.  Shared-memory indices are padded by one element per 16 (phys()) so that
+// the stride-1 pass, where a thread owns 16 consecutive elements, is bank-conflict free.
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ constexpr int bitrev_r(int i, int log2r) {
+    int r = 0;
+    for (int b = 0; b < log2r; b++) r |= ((i >> b) & 1) << (log2r - 1 - b);
+    return r;
+}
+
+// cos/sin of 2 pi m / 16
+__device__ constexpr double kCos16[16] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
+                                          0.0, -0.38268343236508977, -0.70710678118654752, -0.92387953251128674,
+                                          -1.0, -0.92387953251128674, -0.70710678118654752, -0.38268343236508977,
+                                          0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674};
+__device__ constexpr double kSin16[16] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674,
+                                          1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
+                                          0.0, -0.38268343236508977, -0.70710678118654752, -0.92387953251128674,
+                                          -1.0, -0.92387953251128674, -0.70710678118654752, -0.38268343236508977};
+
+// R-point DIF network in registers; on exit x[i] holds frequency bitrev(i).  sign = -1 forward, +1 inverse.
+template <int R, int SIGN>
+__device__ __forceinline__ void fft_regs(double2 (&x)[R]) {
+#pragma unroll
+    for (int len = R; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int blk = 0; blk < R; blk += len) {
+#pragma unroll
+            for (int m = 0; m < half; m++) {
+                const double2 a = x[blk + m], c = x[blk + m + half];
+                x[blk + m] = make_double2(a.x + c.x, a.y + c.y);
+                const double2 d = make_double2(a.x - c.x, a.y - c.y);
+                const int e = m * (16 / len);  // twiddle W_len^m = W_16^e, e in [0, 8)
+                if (e == 0) {
+                    x[blk + m + half] = d;
+                } else if (e == 4) {  // -i (forward) / +i (inverse)
+                    x[blk + m + half] = (SIGN < 0) ? make_double2(d.y, -d.x) : make_double2(-d.y, d.x);
+                } else {
+                    const double wr = kCos16[e], wi = (SIGN < 0) ? -kSin16[e] : kSin16[e];
+                    x[blk + m + half] = make_double2(fma(d.x, wr, -d.y * wi), fma(d.x, wi, d.y * wr));
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double2 csqr(double2 a) { return make_double2(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
+
+// one DIF pass over blocks of span S = 2^LOG2S with radix R (q = S/R); N = 2^LOG2N
+template <int LOG2N, int LOG2S, int R, int SIGN>
+__device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__ tw) {
+    constexpr int N = 1 << LOG2N, S = 1 << LOG2S, q = S / R, NB = N / R;
+    constexpr int LOG2R = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
+    for (int id = threadIdx.x; id < NB; id += SF_THREADS) {
+        const int k = id & (q - 1);
+        const int base = (id / q) * S + k;
+        double2 x[R];
+#pragma unroll
+        for (int m = 0; m < R; m++) x[m] = s[phys(base + m * q)];
+        fft_regs<R, SIGN>(x);
+        if (q > 1) {
+            double2 w[R];  // w[c] = W_S^{k c}
+            w[1] = __ldg(&tw[k * (N / S)]);
+            if (SIGN > 0) w[1].y = -w[1].y;
+#pragma unroll
+            for (int c = 2; c < R; c++) w[c] = (c & (c - 1)) == 0 ? csqr(w[c >> 1]) : cmul2(w[c & (c - 1)], w[c & -c]);
+#pragma unroll
+            for (int i = 1; i < R; i++) x[i] = cmul2(x[i], w[bitrev_r(i, LOG2R)]);
+        }
+#pragma unroll
+        for (int i = 0; i < R; i++) s[phys(base + bitrev_r(i, LOG2R) * q)] = x[i];
+    }
+    __syncthreads();
+}
+
+// full transform: radices 16, 16, N/256 (N >= 256); entry assumes the buffer is complete (does a barrier first)
+template <int LOG2N, int SIGN>
+__device__ __forceinline__ void fft_r16(double2 *s, const double2 *__restrict__ tw) {
+    __syncthreads();
+    fft_pass<LOG2N, LOG2N, 16, SIGN>(s, tw);
+    fft_pass<LOG2N, LOG2N - 4, 16, SIGN>(s, tw);
+    if (LOG2N == 9) fft_pass<LOG2N, 1, 2, SIGN>(s, tw);
+    if (LOG2N == 10) fft_pass<LOG2N, 2, 4, SIGN>(s, tw);
+    if (LOG2N == 11) fft_pass<LOG2N, 3, 8, SIGN>(s, tw);
+    if (LOG2N == 12) fft_pass<LOG2N, 4, 16, SIGN>(s, tw);
+}
+
 // grid = (R, G).  CTA (j, g) handles a contiguous share of the timelines tl < ntl, tl = atom_rel*NM + m.
 //   GEN_AMPLITUDE: accumulate |X|^2 into Ppart[g][j][pos] and a_part[tl][j] = sum_pos |X|^2 * What[j][pos]
 //   GEN_WEIGHTS  : single "timeline" w[tau] = 1/(NF-tau), inverse sign, store X to Wout[j][pos]
-template <int GEN>
-__global__ void __launch_bounds__(SF_THREADS) self_fused_kernel(
+// dynamic shared memory: padded FFT buffer (N + N/16 complex) followed by the power accumulator (N doubles)
+template <int LOG2N, int GEN>
+__global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs, int NF, int NM,
-    size_t atom0, size_t ntl, int log2N, int R, const double2 *__restrict__ tw, const double2 *__restrict__ What,
+    size_t atom0, size_t ntl, int R, const double2 *__restrict__ tw, const double2 *__restrict__ What,
     double *__restrict__ Ppart, double2 *__restrict__ a_part, double2 *__restrict__ Wout) {
     extern __shared__ double2 s[];
     __shared__ double2 red[SF_THREADS / 32];
-    const int N = 1 << log2N;
+    constexpr int N = 1 << LOG2N;
+    double *s_acc = reinterpret_cast<double *>(s + N + N / 16);
     const int j = blockIdx.x;
     const size_t g = blockIdx.y, G = gridDim.y;
     const double L = (double)R * (double)N;
     // residue twiddle in quarter turns per frame index: forward -4 j / L, inverse (weights) +4 j / L
     const double cj = ((GEN == GEN_AMPLITUDE) ? -4.0 : 4.0) * (double)j / L;
 
-    double acc[SF_SLOTS];
-#pragma unroll
-    for (int i = 0; i < SF_SLOTS; i++) acc[i] = 0.0;
+    if (GEN == GEN_AMPLITUDE)
+        for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) s_acc[pos] = 0.0;
 
     // contiguous share of the timelines: a CTA stays on one atom for up to NM consecutive jobs (coordinates cache-hot)
     const size_t per = (ntl + G - 1) / G;
@@ -129,7 +222,7 @@ __global__ void __launch_bounds__(SF_THREADS) self_fused_kernel(
         // y_j[n mod N] += x[n] * exp(-+2 pi i n j / L).  n = tid + 256 i: all passes of one n' belong to the same
         // thread (256 | N), so the shared-memory accumulation is thread-private.  Flat loop, unrolled for ILP.
         if (NF < N)
-            for (int np = NF + threadIdx.x; np < N; np += SF_THREADS) s[np] = make_double2(0.0, 0.0);
+            for (int np = NF + threadIdx.x; np < N; np += SF_THREADS) s[phys(np)] = make_double2(0.0, 0.0);
 #pragma unroll 4
         for (int n = threadIdx.x; n < NF; n += SF_THREADS) {
             double u, amp;
@@ -143,7 +236,7 @@ __global__ void __launch_bounds__(SF_THREADS) self_fused_kernel(
             }
             double sn, cs;
             sincos_qt(u, sn, cs);
-            const int np = n & (N - 1);
+            const int np = phys(n & (N - 1));
             double2 v = make_double2(amp * cs, amp * sn);
             if (n >= N) {
                 const double2 o = s[np];
@@ -152,20 +245,17 @@ __global__ void __launch_bounds__(SF_THREADS) self_fused_kernel(
             }
             s[np] = v;
         }
-        fft_dif_r4(s, log2N, tw, (GEN == GEN_AMPLITUDE) ? -1 : +1);
+        fft_r16<LOG2N, (GEN == GEN_AMPLITUDE) ? -1 : +1>(s, tw);
         if (GEN == GEN_AMPLITUDE) {
             double2 ap = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int i = 0; i < SF_SLOTS; i++) {
-                const int pos = threadIdx.x + i * SF_THREADS;
-                if (pos < N) {
-                    const double2 v = s[pos];
-                    const double pw = fma(v.x, v.x, v.y * v.y);
-                    acc[i] += pw;
-                    const double2 w = __ldg(&What[(size_t)j * N + pos]);
-                    ap.x = fma(pw, w.x, ap.x);
-                    ap.y = fma(pw, w.y, ap.y);
-                }
+#pragma unroll 4
+            for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) {
+                const double2 v = s[phys(pos)];
+                const double pw = fma(v.x, v.x, v.y * v.y);
+                s_acc[pos] += pw;
+                const double2 w = __ldg(&What[(size_t)j * N + pos]);
+                ap.x = fma(pw, w.x, ap.x);
+                ap.y = fma(pw, w.y, ap.y);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -184,15 +274,12 @@ __global__ void __launch_bounds__(SF_THREADS) self_fused_kernel(
                 a_part[tl * R + j] = t;
             }
         } else {
-            for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Wout[(size_t)j * N + pos] = s[pos];
+            for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Wout[(size_t)j * N + pos] = s[phys(pos)];
         }
     }
     if (GEN == GEN_AMPLITUDE) {
-#pragma unroll
-        for (int i = 0; i < SF_SLOTS; i++) {
-            const int pos = threadIdx.x + i * SF_THREADS;
-            if (pos < N) Ppart[(g * R + j) * (size_t)N + pos] = acc[i];
-        }
+        __syncthreads();
+        for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Ppart[(g * R + j) * (size_t)N + pos] = s_acc[pos];
     }
 }
 
@@ -256,17 +343,19 @@ __global__ void __launch_bounds__(1024) sf_reduce_atl_kernel(const double2 *__re
 }
 
 // finalize step 1: per residue j, inverse N-FFT of P_j (stored by digit-reversed position) -> Q_j[t], t < N, natural
+// (P is stored in the radix-16 kernel's position order, freq16; the radix-4 transform used here has its own, freq4)
 __global__ void __launch_bounds__(SF_THREADS) sf_inv_residue_kernel(const double *__restrict__ P, int log2N,
-                                                                    const int *__restrict__ freq_of_pos,
+                                                                    const int *__restrict__ freq16,
+                                                                    const int *__restrict__ freq4,
                                                                     const double2 *__restrict__ tw,
                                                                     double2 *__restrict__ Q) {
     extern __shared__ double2 s[];
     const int N = 1 << log2N;
     const int j = blockIdx.x;
     for (int pos = threadIdx.x; pos < N; pos += SF_THREADS)
-        s[freq_of_pos[pos]] = make_double2(P[(size_t)j * N + pos], 0.0);  // natural frequency order for the DIF input
+        s[freq16[pos]] = make_double2(P[(size_t)j * N + pos], 0.0);  // natural frequency order for the DIF input
     fft_dif_r4(s, log2N, tw, +1);
-    for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Q[(size_t)j * N + freq_of_pos[pos]] = s[pos];
+    for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Q[(size_t)j * N + freq4[pos]] = s[pos];
 }
 
 // finalize step 2: c[tau] = sum_j exp(+2 pi i j tau / L) Q_j[tau mod N]; out = scale * c / (L (NF - tau))
@@ -306,10 +395,60 @@ int freq_of_pos_host(int pos, int log2N) {
     return 4 * freq_of_pos_host(rest, log2N - 2) + quarter;
 }
 
+// position -> frequency of the radix-16 pass sequence (16, 16, N/256)
+int freq16_of_pos_host(int pos, int log2N) {
+    int radices[3] = {16, 16, 1 << (log2N - 8)};
+    int span = 1 << log2N;
+    int freq = 0, mult = 1;
+    for (int pass = 0; pass < 3; pass++) {
+        const int r = radices[pass];
+        if (r == 1) break;
+        const int q = span / r;
+        const int c = pos / q;
+        pos = pos % q;
+        freq += mult * c;
+        mult *= r;
+        span = q;
+    }
+    return freq;
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+size_t sf_smem_bytes(int log2N) {
+    const size_t N = (size_t)1 << log2N;
+    return (N + N / 16) * sizeof(double2) + N * sizeof(double);
+}
+
+template <int GEN>
+void launch_fused(int log2N, dim3 grid, cudaStream_t st, const float *xyz, const double *b, const double *qs, int NF, int NM,
+                  size_t atom0, size_t ntl, int R, const double2 *tw, const double2 *What, double *Ppart,
+                  double2 *a_part, double2 *Wout) {
+    const size_t smem = sf_smem_bytes(log2N);
+#define SF_CASE(LN)                                                                                                    \
+    case LN: {                                                                                                         \
+        static bool attr = false;                                                                                      \
+        if (!attr) {                                                                                                   \
+            cudaFuncSetAttribute(self_fused_kernel<LN, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            attr = true;                                                                                               \
+        }                                                                                                              \
+        self_fused_kernel<LN, GEN><<<grid, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, ntl, R, tw, What, Ppart, \
+                                                                   a_part, Wout);                                     \
+        break;                                                                                                         \
+    }
+    switch (log2N) {
+        SF_CASE(8)
+        SF_CASE(9)
+        SF_CASE(10)
+        SF_CASE(11)
+        SF_CASE(12)
+        default: break;
+    }
+#undef SF_CASE
+}
+
 size_t pick_groups(const SelfPlan *p, size_t ntl) {
-    size_t G = (3 * 148 + p->R - 1) / p->R;
+    size_t G = (2 * 148 + p->R - 1) / p->R;  // two resident CTAs per SM
     if (G > ntl) G = ntl;
     if (G < 1) G = 1;
     if (G > 65535) G = 65535;
@@ -331,16 +470,17 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
     p->L = (size_t)p->R * p->N;
     if (cudaMalloc(&p->d_tw, sizeof(double2) * p->N) != cudaSuccess) return 2;
     if (cudaMalloc(&p->d_w, sizeof(double2) * p->L) != cudaSuccess) return 2;
-    if (cudaMalloc(&p->d_freq, sizeof(int) * p->N) != cudaSuccess) return 2;
-    std::vector<int> f(p->N);
-    for (size_t i = 0; i < p->N; i++) f[i] = freq_of_pos_host((int)i, log2N);
-    cudaMemcpyAsync(p->d_freq, f.data(), sizeof(int) * p->N, cudaMemcpyHostToDevice, st);
+    if (cudaMalloc(&p->d_freq, sizeof(int) * 2 * p->N) != cudaSuccess) return 2;
+    std::vector<int> f(2 * p->N);
+    for (size_t i = 0; i < p->N; i++) {
+        f[i] = freq16_of_pos_host((int)i, log2N);       // order of the fused forward kernel
+        f[p->N + i] = freq_of_pos_host((int)i, log2N);  // order of the radix-4 transform used at finalize
+    }
+    cudaMemcpyAsync(p->d_freq, f.data(), sizeof(int) * 2 * p->N, cudaMemcpyHostToDevice, st);
     sf_twiddle_kernel<<<(unsigned)((p->N + 255) / 256), 256, 0, st>>>(p->d_tw, p->N);
-    cudaFuncSetAttribute(self_fused_kernel<GEN_WEIGHTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(self_fused_kernel<GEN_AMPLITUDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(sf_inv_residue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    self_fused_kernel<GEN_WEIGHTS><<<dim3(p->R, 1), SF_THREADS, sizeof(double2) * p->N, st>>>(
-        nullptr, nullptr, nullptr, (int)NF, 1, 0, 1, log2N, p->R, p->d_tw, nullptr, nullptr, nullptr, p->d_w);
+    launch_fused<GEN_WEIGHTS>(log2N, dim3(p->R, 1), st, nullptr, nullptr, nullptr, (int)NF, 1, 0, 1, p->R, p->d_tw, nullptr,
+                              nullptr, nullptr, p->d_w);
     cudaStreamSynchronize(st);
     if (launches) *launches += 2;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
@@ -374,9 +514,8 @@ int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const d
     double2 *a_part = reinterpret_cast<double2 *>(w);
     w += align256(ntl * p->R * sizeof(double2));
     double2 *a_tl = reinterpret_cast<double2 *>(w);
-    self_fused_kernel<GEN_AMPLITUDE><<<dim3(p->R, (unsigned)G), SF_THREADS, sizeof(double2) * p->N, st>>>(
-        d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, ntl, p->log2N, p->R, p->d_tw, p->d_w, Ppart, a_part,
-        nullptr);
+    launch_fused<GEN_AMPLITUDE>(p->log2N, dim3(p->R, (unsigned)G), st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0,
+                                ntl, p->R, p->d_tw, p->d_w, Ppart, a_part, nullptr);
     sf_reduce_ppart_kernel<<<(unsigned)((p->L + 255) / 256), 256, 0, st>>>(Ppart, G, p->L, d_P);
     const double norm = 1.0 / ((double)p->NF * (double)p->L);
     sf_reduce_apart_kernel<<<(unsigned)((ntl + 255) / 256), 256, 0, st>>>(a_part, ntl, p->R, norm, a_tl);
@@ -387,7 +526,8 @@ int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const d
 int self_finalize(const SelfPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
                   cudaStream_t st) {
     double2 *Q = reinterpret_cast<double2 *>(d_work);
-    sf_inv_residue_kernel<<<p->R, SF_THREADS, sizeof(double2) * p->N, st>>>(d_P, p->log2N, p->d_freq, p->d_tw, Q);
+    sf_inv_residue_kernel<<<p->R, SF_THREADS, sizeof(double2) * p->N, st>>>(d_P, p->log2N, p->d_freq, p->d_freq + p->N,
+                                                                            p->d_tw, Q);
     sf_combine_kernel<<<(unsigned)((p->NF + 127) / 128), 128, 0, st>>>(Q, p->log2N, p->R, p->NF, scale, conj_out, d_out);
     return 2;
 }
