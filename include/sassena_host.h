@@ -96,6 +96,17 @@ size_t sass_create_from_scans(const double *scans, size_t nscans, double *out, s
 /* AbstractVectorsScatterDevice::init_subvectors for q (abstract_vectors_scatter_device.cpp:112-175) */
 size_t sass_init_subvectors(const sass_params *p, const double q[3], double *out, size_t cap);
 
+/* ---- DCD trajectories (reader: src/sample/frames.cpp:272-436; writer layout: src/stager/coordinate_writer.cpp:37-144) --- */
+typedef struct sass_dcd sass_dcd;
+/* opens and indexes the file, then applies first/last/stride like FileFrameset::trim_index (frames.cpp:224-245) */
+int sass_dcd_open(const char *path, size_t first, size_t last, int last_set, size_t stride, sass_dcd **out);
+int sass_dcd_info(const sass_dcd *d, size_t *nframes, size_t *natoms, int *has_unitcell);
+/* frames [first, first+count) of the trimmed index -> out[count][natoms][3] (the stager's frame-major layout) */
+int sass_dcd_read(sass_dcd *d, size_t first, size_t count, float *out);
+void sass_dcd_close(sass_dcd *d);
+/* writes xyz[NF][NA][3] as a CHARMM DCD the reference's reader accepts (stager.dump format) */
+int sass_dcd_write(const char *path, const float *xyz, size_t NF, size_t NA);
+
 #ifdef __cplusplus
 }
 #endif

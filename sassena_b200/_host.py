@@ -69,6 +69,11 @@ SIGNATURES = {
     "sass_decomposition_plan": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double,
                                           C.c_int, C.c_size_t, c_size_p, c_size_p, c_size_p]),
     "sass_create_from_scans": (C.c_size_t, [c_double_p, C.c_size_t, c_double_p, C.c_size_t]),
+    "sass_dcd_open": (C.c_int, [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "sass_dcd_info": (C.c_int, [C.c_void_p, c_size_p, c_size_p, C.POINTER(C.c_int)]),
+    "sass_dcd_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "sass_dcd_close": (None, [C.c_void_p]),
+    "sass_dcd_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sass_init_subvectors": (C.c_size_t, [C.c_void_p, c_double_p, c_double_p, C.c_size_t]),
 }
 

@@ -4,9 +4,15 @@
 #include <cstring>
 #include <string>
 
+#include "dcd.hpp"
 #include "sassena_host.hpp"
 
 using namespace sassena;
+
+struct sass_dcd {
+    sassena::DCDFrameset fs;
+    explicit sass_dcd(const std::string &p) : fs(p) {}
+};
 
 struct sass_params {
     Params params;
@@ -273,6 +279,40 @@ size_t sass_init_subvectors(const sass_params *p, const double q[3], double *out
             }
     });
     return n;
+}
+
+int sass_dcd_open(const char *path, size_t first, size_t last, int last_set, size_t stride, sass_dcd **out) {
+    return guard([&] {
+        if (!path || !out) throw Error("sass_dcd_open: NULL argument");
+        std::unique_ptr<sass_dcd> d(new sass_dcd(path));
+        d->fs.trim_index(first, last, last_set != 0, stride);
+        *out = d.release();
+    });
+}
+int sass_dcd_info(const sass_dcd *d, size_t *nframes, size_t *natoms, int *has_unitcell) {
+    return guard([&] {
+        if (!d) throw Error("sass_dcd_info: NULL argument");
+        if (nframes) *nframes = d->fs.number_of_frames;
+        if (natoms) *natoms = d->fs.number_of_atoms;
+        if (has_unitcell) *has_unitcell = d->fs.has_unitcell() ? 1 : 0;
+    });
+}
+int sass_dcd_read(sass_dcd *d, size_t first, size_t count, float *out) {
+    return guard([&] {
+        if (!d || !out) throw Error("sass_dcd_read: NULL argument");
+        if (first + count > d->fs.number_of_frames) throw Error("sass_dcd_read: frame range out of bounds");
+        d->fs.read_frames(first, count, out);
+    });
+}
+void sass_dcd_close(sass_dcd *d) { delete d; }
+int sass_dcd_write(const char *path, const float *xyz, size_t NF, size_t NA) {
+    return guard([&] {
+        if (!path || !xyz) throw Error("sass_dcd_write: NULL argument");
+        DCDCoordinateWriter w(path, NF, NA);
+        w.init();
+        w.prepare();
+        w.write(xyz, 0, NF);
+    });
 }
 
 }  // extern "C"

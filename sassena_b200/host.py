@@ -62,6 +62,42 @@ def create_from_scans(scans):
     return out[:n]
 
 
+class DCDFile:
+    """DCDFrameset (frames.cpp:272-436) with the frameset's first/last/stride trimming."""
+
+    def __init__(self, path, first=0, last=None, stride=1):
+        h = C.c_void_p()
+        _ck(_lib().sass_dcd_open(str(path).encode(), first, 0 if last is None else last, 0 if last is None else 1,
+                                 stride, C.byref(h)))
+        self.h = h
+        nf, na, uc = C.c_size_t(), C.c_size_t(), C.c_int()
+        _ck(_lib().sass_dcd_info(self.h, C.byref(nf), C.byref(na), C.byref(uc)))
+        self.number_of_frames, self.number_of_atoms, self.has_unitcell = nf.value, na.value, bool(uc.value)
+
+    def read(self, first=0, count=None):
+        count = self.number_of_frames - first if count is None else count
+        out = np.empty((count, self.number_of_atoms, 3), dtype=np.float32)
+        _ck(_lib().sass_dcd_read(self.h, first, count, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            _lib().sass_dcd_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def write_dcd(path, xyz):
+    """xyz float32 [NF][NA][3] -> CHARMM DCD in the layout of the reference's DCDCoordinateWriter."""
+    a = np.ascontiguousarray(xyz, dtype=np.float32)
+    _ck(_lib().sass_dcd_write(str(path).encode(), a.ctypes.data, a.shape[0], a.shape[1]))
+
+
 class Params:
     """The part of the scatter.xml Params the hot path reads; keys are the XML paths."""
 

@@ -226,3 +226,55 @@ def test_run_scatter_single_rank_oracle_backend(oracle):
     with pytest.raises(host.HostError) as e:
         host.run_scatter(host.Params().set("limits.stage.memory.data", 100), xyz, qv, b=b, backend=be.vtbl)
     assert "decomposition failed" in str(e.value) or "Insufficient Buffer" in str(e.value)
+
+
+def test_dcd_roundtrip_and_trimming(tmp_path):
+    """DCD writer (coordinate_writer.cpp layout) -> reader (frames.cpp:272-436): exact round trip, header fields,
+    first/last/stride trimming with the reference's absolute-index stride rule (frames.cpp:224-245)"""
+    import struct
+    from sassena_b200 import synth
+    xyz = synth.trajectory(11, 7, 20.0, 0.3, 5)
+    path = tmp_path / "traj.dcd"
+    host.write_dcd(path, xyz)
+    raw = open(path, "rb").read()
+    assert struct.unpack("<i", raw[:4])[0] == 84 and raw[4:8] == b"CORD" and struct.unpack("<i", raw[88:92])[0] == 84
+    assert struct.unpack("<i", raw[8:12])[0] == 11
+    # 92 header + title (4+4+4) + natoms (4+4+4) ; per frame: cell (4+48+4) + 3*(4+4N+4)
+    assert len(raw) == 92 + 12 + 12 + 11 * (56 + 3 * (8 + 4 * 7))
+    d = host.DCDFile(path)
+    assert (d.number_of_frames, d.number_of_atoms, d.has_unitcell) == (11, 7, True)
+    assert np.array_equal(d.read(), xyz)
+    assert np.array_equal(d.read(3, 2), xyz[3:5])
+    with pytest.raises(host.HostError):
+        d.read(10, 5)
+    # first=3, last=9, stride=2 keeps absolute indices 4, 6, 8 (i % stride == 0, not (i-first) % stride)
+    t = host.DCDFile(path, first=3, last=9, stride=2)
+    assert t.number_of_frames == 3 and np.array_equal(t.read(), xyz[[4, 6, 8]])
+    # a file that is not a DCD
+    bad = tmp_path / "bad.dcd"
+    bad.write_bytes(b"\0" * 200)
+    with pytest.raises(host.HostError) as e:
+        host.DCDFile(bad)
+    assert "appears to not be a DCD file" in str(e.value)
+
+
+def test_dcd_reader_handles_title_and_optional_blocks(tmp_path):
+    """hand-built DCD without the unit-cell block, with an 80-byte title line and with the 4th (ext block 2) record"""
+    import struct
+    NF, NA = 3, 5
+    rng = np.random.default_rng(0)
+    xyz = rng.normal(size=(NF, NA, 3)).astype(np.float32)
+    hdr = struct.pack("<i4siii24sfii", 84, b"CORD", NF, 0, 1, b"\0" * 24, 1.0, 0, 1) + b"\0" * 28 + struct.pack("<ii", 24, 84)
+    assert len(hdr) == 92
+    title = struct.pack("<ii", 84, 1) + b"T" * 80 + struct.pack("<i", 84)
+    natoms = struct.pack("<iii", 4, NA, 4)
+    body = b""
+    for f in range(NF):
+        for c in range(3):
+            body += struct.pack("<i", 4 * NA) + xyz[f, :, c].tobytes() + struct.pack("<i", 4 * NA)
+        body += struct.pack("<i", 4 * NA) + np.zeros(NA, np.float32).tobytes() + struct.pack("<i", 4 * NA)
+    p = tmp_path / "ext2.dcd"
+    p.write_bytes(hdr + title + natoms + body)
+    d = host.DCDFile(p)
+    assert (d.number_of_frames, d.number_of_atoms, d.has_unitcell) == (NF, NA, False)
+    assert np.array_equal(d.read(), xyz)
