@@ -135,7 +135,7 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace ptx
 
-template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0>
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs,
     double2 *__restrict__ A, size_t ldA, int NA, int NM, unsigned ngroups, size_t f0, int use_bulk) {
@@ -205,6 +205,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
         if (active) {
             const float *sx = s_xyz + (size_t)s * TILE * 3;
             const double *sb = s_b + (size_t)s * TILE;
+            if (PAIR) {
+                // two atoms per lane and iteration: 3 x LDS.64 + 1 x LDS.128 instead of 8 loads (24-byte lane stride is
+                // bank-conflict free), half the loop overhead per evaluation
+#pragma unroll 1
+                for (int j = 2 * lane; j < cnt; j += 64) {
+                    const float2 p0 = *reinterpret_cast<const float2 *>(sx + 3 * j);
+                    const float2 p1 = *reinterpret_cast<const float2 *>(sx + 3 * j + 2);
+                    const float2 p2 = *reinterpret_cast<const float2 *>(sx + 3 * j + 4);
+                    const double2 bb = *reinterpret_cast<const double2 *>(sb + j);
+                    const double x0 = (double)p0.x, y0 = (double)p0.y, z0 = (double)p1.x;
+                    const double x1 = (double)p1.y, y1 = (double)p2.x, z1 = (double)p2.y;
+                    const double b0 = bb.x, b1 = (j + 1 < cnt) ? bb.y : 0.0;
+#pragma unroll
+                    for (int k = 0; k < QPT; k++) {
+                        const double u0 = fma(z0, qz[k], fma(y0, qy[k], x0 * qx[k]));
+                        sincos_qt_accumulate3(u0, b0, re[k], im[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < QPT; k++) {
+                        const double u1 = fma(z1, qz[k], fma(y1, qy[k], x1 * qx[k]));
+                        sincos_qt_accumulate3(u1, b1, re[k], im[k]);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int j = lane; j < cnt; j += 32) {
                 const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
@@ -214,6 +238,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
                     const double u = fma(z, qz[k], fma(y, qy[k], x * qx[k]));
                     sincos_qt_accumulate2<ABL>(u, bj, re[k], im[k]);
                 }
+            }
             }
         }
         __syncwarp();
@@ -500,16 +525,15 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters)
 
 }  // namespace
 
-int amplitude_all_qpad() { return 64; }  // every variant covers 64 q-vectors per CTA or a divisor of it
 
 namespace {
-template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0>
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
 int launch_tiled(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
                  size_t NM, size_t f0, size_t nf, cudaStream_t st) {
     const unsigned per_cta = QPT * WARPS;
     const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
-    auto kern = amplitude_all_tiled_kernel<QPT, WARPS, TILE, STAGES, MINB, ABL>;
+    auto kern = amplitude_all_tiled_kernel<QPT, WARPS, TILE, STAGES, MINB, ABL, PAIR>;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -571,6 +595,18 @@ int k1_variant() {
 }
 }  // namespace
 
+// q-vectors per CTA of the active variant: the q array must be zero padded to a multiple of this
+int amplitude_all_qpad() {
+    switch (k1_variant()) {
+        case 7: case 8: case 20: case 21: case 30: case 31: case 32: return 48;
+        case 33: return 72;
+        case 34: return 56;
+        case 9: case 35: return 40;
+        case 2: case 3: case 4: return 32;
+        default: return 64;
+    }
+}
+
 int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
                          size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
     if (nf == 0 || NM == 0) return 0;
@@ -586,6 +622,12 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
         case 21: return launch_tiled<6, 8, 512, 4, 2, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 8: return launch_tiled<6, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 9: return launch_tiled<5, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 30: return launch_tiled<6, 8, 512, 4, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 31: return launch_tiled<6, 8, 1024, 3, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 32: return launch_tiled<6, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 33: return launch_tiled<6, 12, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 34: return launch_tiled<7, 8, 512, 4, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 35: return launch_tiled<5, 8, 512, 4, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 10: return launch_uq<8, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 11: return launch_uq<8, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 12: return launch_uq<6, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);

@@ -131,4 +131,43 @@ __device__ __forceinline__ void sincos_qt_accumulate2(double u, double b, double
     im = fma(b, sm, im);
 }
 
+// Same as sincos_qt_accumulate2 but the odd-quadrant predicate and the two 64-bit selects are written in PTX so that
+// ptxas emits one predicate-producing LOP3 instead of LOP3 + ISETP.
+__device__ __forceinline__ void sincos_qt_accumulate3(double u, double b, double &re, double &im) {
+    const double MAGIC = 6755399441055744.0;
+    double t = u + MAGIC;
+    const int k = __double2loint(t);
+    double kd = t - MAGIC;
+    double f = u - kd;
+    double z = f * f;
+    double S = fma(z, kSinC[5], kSinC[4]);
+    double Cp = fma(z, kCosC[5], kCosC[4]);
+    S = fma(z, S, kSinC[3]);
+    Cp = fma(z, Cp, kCosC[3]);
+    S = fma(z, S, kSinC[2]);
+    Cp = fma(z, Cp, kCosC[2]);
+    S = fma(z, S, kSinC[1]);
+    Cp = fma(z, Cp, kCosC[1]);
+    S = fma(z, S, kSinC[0]);
+    Cp = fma(z, Cp, kCosC[0]);
+    const int ks = k << 30;
+    const double fs = __hiloint2double(__double2hiint(f) ^ ((ks + 0x40000000) & 0x80000000), __double2loint(f));
+    const double sv = fs * S;
+    double cv = fma(z, Cp, 1.0);
+    cv = __hiloint2double(__double2hiint(cv) ^ (ks & 0x80000000), __double2loint(cv));
+    double cm, sm;
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %4, 1;\n"
+        "setp.ne.b32 p, t, 0;\n"
+        "selp.f64 %0, %3, %2, p;\n"
+        "selp.f64 %1, %2, %3, p;\n"
+        "}\n"
+        : "=d"(cm), "=d"(sm)
+        : "d"(cv), "d"(sv), "r"(k));
+    re = fma(b, cm, re);
+    im = fma(b, sm, im);
+}
+
 }  // namespace sass
