@@ -110,6 +110,22 @@ int sgpu_compute_self_vectors(sgpu_ctx *ctx, const double *qvecs, size_t NM, int
 int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type, int dsp_method,
                           double *atfinal, double afinal[2], double a2final[2]);
 
+/* Batched multipole sphere: NQ |q| values in one pass.  The q-independent Y_lm tables are built once per atom tile and
+ * shared by the batch (the reference recomputes them per moment, atom, frame AND |q|).  Outputs are per |q|:
+ * atfinal[NQ][NF][2], afinal[NQ][2], a2final[NQ][2].  Per-|q| scattering factors can be supplied with
+ * sgpu_set_factors_batch(b[NQ][NA]); otherwise the set given to sgpu_set_factors applies to every |q|. */
+int sgpu_set_factors_batch(sgpu_ctx *ctx, const double *b, size_t NQ, size_t n);
+int sgpu_compute_mpsphere_batch(sgpu_ctx *ctx, const double *qlens, size_t NQ, const long *lm, size_t NM, int dsp_type,
+                                int dsp_method, double *atfinal, double *afinal, double *a2final);
+int sgpu_compute_mpsphere_batch_partial(sgpu_ctx *ctx, const double *qlens, size_t NQ, const long *lm, size_t NM,
+                                        int dsp_type, double *d_partials);
+/* Multi-GPU multipole: A_lm is a sum over atoms, so ranks shard ATOMS: each rank writes the amplitudes of its atom
+ * range for NQ |q| values to d_amp ([NQ][NM][NF][2] doubles, device), the caller all-reduces d_amp, and
+ * sgpu_mpsphere_dsp_partial turns the summed amplitudes into NQ packed partials (no second reduction needed). */
+int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, const long *lm, size_t NM, size_t atom_first,
+                             size_t atom_count, double *d_amp);
+int sgpu_mpsphere_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t NQ, size_t NM, int dsp_type, double *d_partials);
+
 /* ---- multi-GPU: partial sums + finalize --------------------------------------------------------- */
 /* The reference reduces atfinal_/afinal_/a2final_ over the partition with three boost::mpi::reduce
  * calls (all_vectors_scatter_device.cpp:335-343, self...:213-221, multipole...:375-383).  Here every

@@ -39,6 +39,11 @@ SIGNATURES = {
     "sgpu_compute_all_vectors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
     "sgpu_compute_self_vectors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
     "sgpu_compute_mpsphere": (C.c_int, [C.c_void_p, C.c_double, c_long_p, C.c_size_t, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "sgpu_set_factors_batch": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_size_t]),
+    "sgpu_compute_mpsphere_batch": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, c_long_p, C.c_size_t, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "sgpu_compute_mpsphere_batch_partial": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, c_long_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "sgpu_mpsphere_amplitudes": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, c_long_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "sgpu_mpsphere_dsp_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
     "sgpu_partial_len": (C.c_int, [C.c_void_p, C.c_int, c_size_p]),
     "sgpu_compute_all_vectors_partial": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p]),
     "sgpu_compute_self_vectors_partial": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p]),

@@ -184,6 +184,29 @@ class ScatterContext:
                                                 _dsp(dsp), _method(method), _dp(at), _dp(af), _dp(a2f)))
         return self._pack(at, af, a2f)
 
+    def set_factors_batch(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        self._ck(self.lib.sgpu_set_factors_batch(self.h, _dp(b), b.shape[0], b.shape[1]))
+
+    def compute_mpsphere_batch(self, qlens, moments, dsp="autocorrelate", method="fftw"):
+        """NQ |q| values in one pass -> list of (fqt, fq, fq2)."""
+        ql = np.ascontiguousarray(qlens, dtype=np.float64).reshape(-1)
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        NQ = len(ql)
+        at, af, a2f = np.zeros((NQ, 2 * self.NF)), np.zeros((NQ, 2)), np.zeros((NQ, 2))
+        self._ck(self.lib.sgpu_compute_mpsphere_batch(self.h, _dp(ql), NQ, lm.ctypes.data_as(C.POINTER(C.c_long)), len(lm),
+                                                      _dsp(dsp), _method(method), _dp(at), _dp(af), _dp(a2f)))
+        return [self._pack(at[i], af[i], a2f[i]) for i in range(NQ)]
+
+    def mpsphere_amplitudes(self, qlens, moments, atom_first, atom_count, d_amp: int):
+        ql = np.ascontiguousarray(qlens, dtype=np.float64).reshape(-1)
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        self._ck(self.lib.sgpu_mpsphere_amplitudes(self.h, _dp(ql), len(ql), lm.ctypes.data_as(C.POINTER(C.c_long)), len(lm),
+                                                   atom_first, atom_count, C.c_void_p(d_amp)))
+
+    def mpsphere_dsp_partial(self, d_amp: int, NQ, NM, d_partials: int, dsp="autocorrelate"):
+        self._ck(self.lib.sgpu_mpsphere_dsp_partial(self.h, C.c_void_p(d_amp), NQ, NM, _dsp(dsp), C.c_void_p(d_partials)))
+
     # -- multi-GPU split
     def partial_len(self, dsp="autocorrelate") -> int:
         n = C.c_size_t()

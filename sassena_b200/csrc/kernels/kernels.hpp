@@ -37,6 +37,14 @@ int launch_multipole_sphere(const float *d_sph, const double *d_b, double ql, co
                             double2 *d_A, size_t ldA, size_t NA, size_t f0, size_t nf, double *d_work,
                             cudaStream_t st);
 
+// batched form: NQ |q| values per pass (Y_lm table shared), atoms [a_first, a_last) only; d_A block q at d_A + q*NM*ldA;
+// d_b: [NQ][b_stride] (b_stride = 0: one factor set for all q); d_work >= multipole_batch_work_doubles() doubles
+int multipole_batch_max();
+size_t multipole_batch_work_doubles(size_t nf, int lmax, size_t natoms, int NQ);
+int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t b_stride, const double *d_qlens, int NQ,
+                                  const int *d_lm, size_t NM, int lmax, double2 *d_A, size_t ldA, size_t NA,
+                                  size_t a_first, size_t a_last, size_t f0, size_t nf, double *d_work, cudaStream_t st);
+
 // ---- correlate.cu -------------------------------------------------------------------------------
 struct CorrPlan {
     size_t NF = 0;   // frames per timeline

@@ -14,7 +14,9 @@
 // a fixed order (no atomics).
 #include "kernels.hpp"
 
+#include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 namespace sass {
@@ -34,6 +36,9 @@ MpTables g_tab[16];  // per device
 
 __host__ __device__ inline int mp_npairs(int lmax) { return (lmax + 1) * (lmax + 2) / 2; }
 __host__ __device__ inline int mp_pair(int lmax, int l, int m) { return m * (lmax + 1) - (m * (m - 1)) / 2 + (l - m); }
+// l-major order used by the batched kernel: a warp of consecutive pairs shares (nearly) one l, so its Bessel operands
+// are a shared-memory broadcast
+__host__ __device__ inline int mp_pair_l(int l, int m) { return (l * (l + 1)) / 2 + m; }
 
 __global__ void __launch_bounds__(MP_THREADS) multipole_sphere_kernel(
     const float *__restrict__ sph, const double *__restrict__ b, double ql, int lmax, int lstart, size_t NA,
@@ -198,6 +203,244 @@ __global__ void multipole_assemble_kernel(const double2 *__restrict__ part, int 
     A[mom * ldA + f0 + fr] = make_double2(FOURPI * ar, FOURPI * ai);
 }
 
+// ---- K5, batched "GEMM" form -------------------------------------------------------------------------------------
+// U[q][l,m] = sum_a B[q][l][a] * Yc[l,m][a],  V likewise with Ys, where B = b_a(q) j_l(q r_a) and
+// (Yc, Ys) = Pbar_lm(theta_a) (cos m phi_a, sin m phi_a).  Y does not depend on |q| and B does not depend on m, so for a
+// tile of atoms both tables are built once in shared memory (Y once per batch of Q |q| values) and the sum over atoms
+// becomes a register-blocked product: a thread owns one (l,m) pair and 2Q accumulators, walks the atoms of its half of
+// the tile and does 2Q DFMAs per atom from one LDS.128 (Y) and Q LDS.64 (B).  No cross-lane reduction exists any
+// more: the sum over atoms is sequential inside the owning thread, across tiles, in a fixed order.
+// Per tile: geometry (sincos) -> table tasks (Legendre column pairs (m, lmax-m): equal length; Bessel ladders with an
+// x-dependent Miller start) spread over all 512 threads -> product phase on 2 x NP threads.
+constexpr int MG_THREADS = 512;
+constexpr int MG_A = 24;        // atoms per tile
+constexpr int MG_GROUPS = 2;    // thread groups of the product phase, MG_A / MG_GROUPS atoms each
+constexpr int MG_APG = MG_A / MG_GROUPS;
+
+// one Legendre/azimuth column: sY[a][pair_l(l,m)] = Pbar_lm(theta) (cos m phi, sin m phi), l = m..lmax
+__device__ __forceinline__ void mg_column(int m, int a, int lmax, int NP, double ct, double st, double c1, double s1,
+                                          const double *__restrict__ cK, const double *__restrict__ cM1,
+                                          const double *__restrict__ cA, const double *__restrict__ cB, double2 *sY) {
+    // st^m and (c1 + i s1)^m by binary powering (short dependency chain)
+    double pw = 1.0, base = st, cm = 1.0, sm = 0.0, rc = c1, rs = s1;
+    for (int e = m; e; e >>= 1) {
+        if (e & 1) {
+            pw *= base;
+            const double t = cm * rc - sm * rs;
+            sm = fma(sm, rc, cm * rs);
+            cm = t;
+        }
+        base *= base;
+        const double t = rc * rc - rs * rs;
+        rs = 2.0 * rc * rs;
+        rc = t;
+    }
+    const double pmm = cK[m] * pw;
+    double p2 = 0.0, p1 = pmm;
+    const int pbase = mp_pair(lmax, m, m);
+    for (int l = m; l <= lmax; l++) {
+        double pl;
+        if (l == m) pl = pmm;
+        else if (l == m + 1) pl = cM1[m] * ct * pmm;
+        else pl = cA[pbase + l - m] * fma(ct, p1, -cB[pbase + l - m] * p2);
+        p2 = p1;
+        p1 = pl;
+        sY[(size_t)a * NP + mp_pair_l(l, m)] = make_double2(pl * cm, pl * sm);
+    }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
+    const float *__restrict__ sph, const double *__restrict__ b, size_t b_stride, const double *__restrict__ qlens,
+    int lmax, int lstart_max, size_t NA, size_t f0, size_t a_first, size_t a_last, size_t atoms_per_split,
+    const double *__restrict__ tab, double2 *__restrict__ part, size_t nf, int q0, int NQ) {
+    extern __shared__ double smem[];
+    const int L1 = lmax + 1;
+    const int NP = mp_npairs(lmax);
+    double2 *sY = reinterpret_cast<double2 *>(smem);              // [MG_A][NP]
+    double *sB = smem + (size_t)2 * MG_A * NP;                    // [MG_A][L1][Q]  (q fastest: one LDS.128 = two |q|)
+    const int BS = L1 * Q + 2;                                    // per-atom stride of sB, padded against bank conflicts
+    double *sGeo = sB + (size_t)MG_A * BS;                        // [MG_A][5]: r, ct, st, c1, s1
+    double *sTab = sGeo + MG_A * 5;                               // recurrence tables: cM1[L1] cK[L1] cA[NP] cB[NP]
+    int *sL = reinterpret_cast<int *>(sTab + 2 * L1 + 2 * NP);    // [NP]: l of pair p
+    const double *cS = tab + 2 * L1 + 2 * NP;
+    const double *cM1 = sTab, *cK = sTab + L1, *cA = sTab + 2 * L1, *cB = sTab + 2 * L1 + NP;
+
+    const int tid = threadIdx.x;
+    // the Legendre recurrence is a serial chain: keep its coefficient tables in shared memory, not behind global loads
+    for (int i = tid; i < L1; i += MG_THREADS) {
+        sTab[i] = __ldg(&tab[L1 + i]);
+        sTab[L1 + i] = __ldg(&tab[2 * L1 + 2 * NP + L1 * MP_SERIES_TERMS + i]);
+    }
+    for (int i = tid; i < NP; i += MG_THREADS) {
+        sTab[2 * L1 + i] = __ldg(&tab[2 * L1 + i]);
+        sTab[2 * L1 + NP + i] = __ldg(&tab[2 * L1 + NP + i]);
+    }
+    const size_t fr = blockIdx.x;
+    const int split = blockIdx.y;
+    for (int m = 0; m <= lmax; m++)
+        for (int l = m + tid; l <= lmax; l += MG_THREADS) sL[mp_pair_l(l, m)] = l;
+    const size_t a_begin = a_first + (size_t)split * atoms_per_split;
+    const size_t a_end = min(a_last, a_begin + atoms_per_split);
+    const float *p = sph + (f0 + fr) * NA * 3;
+    const int NK = L1;  // one task per Legendre column m; short columns first so that the Bessel tasks that wrap
+                        // around to a second round land on threads that finished early
+    const int grp = tid >> 8, tp = tid & 255;
+
+    double2 acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) acc[q] = make_double2(0.0, 0.0);
+
+    for (size_t base = a_begin; base < a_end; base += MG_A) {
+        __syncthreads();  // previous tile fully consumed
+        if (tid < MG_A) {
+            const size_t atom = base + tid;
+            double r = 0.0, phi = 0.0, theta = 0.0;
+            if (atom < a_end) {
+                r = (double)__ldg(&p[3 * atom]);
+                phi = (double)__ldg(&p[3 * atom + 1]);
+                theta = (double)__ldg(&p[3 * atom + 2]);
+            }
+            double st, ct, s1, c1;
+            sincos(theta, &st, &ct);
+            sincos(phi, &s1, &c1);
+            sGeo[tid * 5] = r;
+            sGeo[tid * 5 + 1] = ct;
+            sGeo[tid * 5 + 2] = st;
+            sGeo[tid * 5 + 3] = c1;
+            sGeo[tid * 5 + 4] = s1;
+        }
+        __syncthreads();
+        // table tasks: rows [0, NK): Legendre column m = lmax-row of atom a; rows [NK, NK+Q): Bessel ladder (q, a)
+        for (int id = tid; id < (NK + Q) * MG_A; id += MG_THREADS) {
+            const int a = id % MG_A;
+            const int row = id / MG_A;
+            if (row < NK) {
+                const double ct = sGeo[a * 5 + 1], st = sGeo[a * 5 + 2], c1 = sGeo[a * 5 + 3], s1 = sGeo[a * 5 + 4];
+                mg_column(lmax - row, a, lmax, NP, ct, st, c1, s1, cK, cM1, cA, cB, sY);
+            } else {
+                const int q = row - NK;
+                const size_t atom = base + a;
+                double *J = sB + (size_t)a * BS + q;  // element l at J[l * Q]
+                double bq = 0.0;
+                if (atom < a_end && q0 + q < NQ) bq = __ldg(&b[(size_t)(q0 + q) * b_stride + atom]);
+                const double ql = (q0 + q < NQ) ? __ldg(&qlens[q0 + q]) : 0.0;
+                const double x = ql * sGeo[a * 5];
+                if (x < 0.05) {
+                    // power series, 4 terms are exact to 1e-16 below x = 0.05
+                    const double x2 = x * x;
+                    double pref = bq;
+                    for (int l = 0; l <= lmax; l++) {
+                        if (l > 0) pref *= x / (double)(2 * l + 1);
+                        double term = 1.0, sum = 1.0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            term *= x2 * __ldg(&cS[l * MP_SERIES_TERMS + k]);
+                            sum += term;
+                        }
+                        J[l * Q] = pref * sum;
+                    }
+                } else {
+                    double sn, cs;
+                    sincos(x, &sn, &cs);
+                    const double invx = 1.0 / x;
+                    const double j0 = sn * invx;
+                    const double j1 = (sn * invx - cs) * invx;
+                    if (x >= (double)lmax) {
+                        double jm = j0, jc = j1;
+                        J[0] = bq * j0;
+                        if (lmax >= 1) J[Q] = bq * j1;
+                        for (int l = 1; l < lmax; l++) {
+                            const double jn = fma((double)(2 * l + 1) * invx, jc, -jm);
+                            jm = jc;
+                            jc = jn;
+                            J[(l + 1) * Q] = bq * jn;
+                        }
+                    } else {
+                        // Miller downward recurrence; the start index needed for 1e-14 grows only slowly with x
+                        // (measured: lmax + 2 .. lmax + 19 for x < lmax), use lmax + 8 + 1.5 x
+                        const int lstart = min(lstart_max, lmax + 8 + (int)(1.5 * x));
+                        double jp = 0.0, jc = 1e-300;
+                        for (int k = lstart; k >= 1; k--) {
+                            const double jm = fma((double)(2 * k + 1) * invx, jc, -jp);
+                            jp = jc;
+                            jc = jm;
+                            if (k - 1 <= lmax) J[(k - 1) * Q] = jc;
+                        }
+                        const double scale = bq * ((fabs(j0) >= fabs(j1)) ? j0 / jc : j1 / jp);
+                        for (int l = 0; l <= lmax; l++) J[l * Q] *= scale;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tp < NP) {
+            const int l = sL[tp];
+#pragma unroll 4
+            for (int aa = 0; aa < MG_APG; aa++) {
+                const int a = grp * MG_APG + aa;
+                const double2 y = sY[(size_t)a * NP + tp];
+                const double *Bp = sB + (size_t)a * BS + (size_t)l * Q;
+                if (Q >= 2) {
+#pragma unroll
+                    for (int q = 0; q < Q; q += 2) {
+                        const double2 b2 = *reinterpret_cast<const double2 *>(Bp + q);
+                        acc[q].x = fma(b2.x, y.x, acc[q].x);
+                        acc[q].y = fma(b2.x, y.y, acc[q].y);
+                        acc[q + (Q >= 2 ? 1 : 0)].x = fma(b2.y, y.x, acc[q + (Q >= 2 ? 1 : 0)].x);
+                        acc[q + (Q >= 2 ? 1 : 0)].y = fma(b2.y, y.y, acc[q + (Q >= 2 ? 1 : 0)].y);
+                    }
+                } else {
+                    acc[0].x = fma(Bp[0], y.x, acc[0].x);
+                    acc[0].y = fma(Bp[0], y.y, acc[0].y);
+                }
+            }
+        }
+    }
+    if (tp < NP) {
+#pragma unroll
+        for (int q = 0; q < Q; q++)
+            if (q0 + q < NQ) part[((((size_t)split * MG_GROUPS + grp) * NQ + q0 + q) * nf + fr) * NP + tp] = acc[q];
+    }
+}
+
+// A_q[mom][f0+fr] from part[split][q][fr][pair] (see multipole_assemble_kernel)
+__global__ void multipole_assemble_batch_kernel(const double2 *__restrict__ part, int nsplit, size_t nf, int lmax,
+                                                const int *__restrict__ lm, size_t NM, double2 *__restrict__ A,
+                                                size_t ldA, size_t f0, int q, int NQ) {
+    const size_t fr = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t mom = blockIdx.y;
+    if (fr >= nf || mom >= NM) return;
+    const int l = lm[2 * mom], m = lm[2 * mom + 1];
+    const int am = m < 0 ? -m : m;
+    const int NP = mp_npairs(lmax);
+    const int pi = mp_pair_l(l, am);
+    double u = 0.0, v = 0.0;
+    for (int s = 0; s < nsplit; s++) {
+        const double2 w = part[(((size_t)s * NQ + q) * nf + fr) * NP + pi];
+        u += w.x;
+        v += w.y;
+    }
+    double wr, wi;
+    if (m >= 0) {
+        wr = u;
+        wi = -v;
+    } else {
+        const double sg = (am & 1) ? -1.0 : 1.0;
+        wr = sg * u;
+        wi = sg * v;
+    }
+    const double FOURPI = 12.566370614359172954;
+    double ar, ai;
+    switch (l & 3) {
+        case 0: ar = wr; ai = wi; break;
+        case 1: ar = -wi; ai = wr; break;
+        case 2: ar = -wr; ai = -wi; break;
+        default: ar = wi; ai = -wr; break;
+    }
+    A[mom * ldA + f0 + fr] = make_double2(FOURPI * ar, FOURPI * ai);
+}
+
 int mp_lstart(int lmax) { return lmax + 20 + (int)std::sqrt(60.0 * (lmax + 10)); }
 
 const double *mp_tables(int lmax, cudaStream_t st) {
@@ -211,8 +454,11 @@ const double *mp_tables(int lmax, cudaStream_t st) {
         T.d = nullptr;
     }
     const int np = mp_npairs(lmax);
-    std::vector<double> h(2 * (lmax + 1) + 2 * np + (lmax + 1) * MP_SERIES_TERMS, 0.0);
+    std::vector<double> h(2 * (lmax + 1) + 2 * np + (lmax + 1) * MP_SERIES_TERMS + (lmax + 1), 0.0);
     double *cMM = h.data(), *cM1 = cMM + (lmax + 1), *cA = cM1 + (lmax + 1), *cB = cA + np, *cS = cB + np;
+    double *cK = cS + (lmax + 1) * MP_SERIES_TERMS;  // Pbar_mm = cK[m] * sin^m(theta)
+    cK[0] = std::sqrt(1.0 / (4.0 * M_PI));
+    for (int m = 1; m <= lmax; m++) cK[m] = cK[m - 1] * -std::sqrt((2.0 * m + 1.0) / (2.0 * m));
     for (int m = 0; m <= lmax; m++) {
         if (m > 0) cMM[m] = -std::sqrt((2.0 * m + 1.0) / (2.0 * m));
         cM1[m] = std::sqrt(2.0 * m + 3.0);
@@ -271,6 +517,55 @@ int launch_multipole_sphere(const float *d_sph, const double *d_b, double ql, co
             part, nsplit, nf, lmax, d_lm + 2 * m0, cnt, d_A + m0 * ldA, ldA, f0);
         launches++;
     }
+    return launches;
+}
+
+
+int multipole_batch_max() { return 8; }
+
+size_t multipole_batch_work_doubles(size_t nf, int lmax, size_t natoms, int NQ) {
+    return (size_t)mp_nsplit(nf, natoms) * MG_GROUPS * NQ * nf * mp_npairs(lmax) * 2;
+}
+
+// amplitudes of NQ |q| values at once: d_A[q] has NM timelines of ldA entries, q-th block at d_A + q*NM*ldA.
+// Atoms [a_first, a_last) only (atom sharding over GPUs); d_b: [NQ][b_stride] factors (b_stride = 0: shared).
+int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t b_stride, const double *d_qlens, int NQ,
+                                  const int *d_lm, size_t NM, int lmax, double2 *d_A, size_t ldA, size_t NA,
+                                  size_t a_first, size_t a_last, size_t f0, size_t nf, double *d_work, cudaStream_t st) {
+    if (nf == 0 || NM == 0 || NQ == 0) return 0;
+    if (lmax > MP_LMAX) return -1;
+    const double *tab = mp_tables(lmax, st);
+    if (!tab) return -1;
+    const size_t natoms = a_last > a_first ? a_last - a_first : 0;
+    const int nsplit = mp_nsplit(nf, std::max<size_t>(natoms, 1));
+    size_t per = (natoms + nsplit - 1) / nsplit;
+    per = ((per + MG_A - 1) / MG_A) * MG_A;
+    const int L1 = lmax + 1, NP = mp_npairs(lmax);
+    double2 *part = reinterpret_cast<double2 *>(d_work);
+    int launches = 0;
+    auto run = [&](auto qtag, int q0) {
+        constexpr int Q = decltype(qtag)::value;
+        const size_t smem = ((size_t)2 * MG_A * NP + (size_t)MG_A * (Q * L1 + 2) + MG_A * 5 + 2 * L1 + 2 * NP) * sizeof(double) +
+                            NP * sizeof(int);
+        cudaFuncSetAttribute(multipole_gemm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        multipole_gemm_kernel<Q><<<dim3((unsigned)nf, (unsigned)nsplit), MG_THREADS, smem, st>>>(
+            d_sph, d_b, b_stride, d_qlens, lmax, mp_lstart(lmax), NA, f0, a_first, a_last, per, tab, part, nf, q0, NQ);
+        launches++;
+    };
+    for (int q0 = 0; q0 < NQ;) {
+        const int left = NQ - q0;
+        if (left >= 8) { run(std::integral_constant<int, 8>(), q0); q0 += 8; }
+        else if (left >= 4) { run(std::integral_constant<int, 4>(), q0); q0 += 4; }
+        else if (left >= 2) { run(std::integral_constant<int, 2>(), q0); q0 += 2; }
+        else { run(std::integral_constant<int, 1>(), q0); q0 += 1; }
+    }
+    for (int q = 0; q < NQ; q++)
+        for (size_t m0 = 0; m0 < NM; m0 += 65535) {
+            const size_t cnt = NM - m0 < 65535 ? NM - m0 : 65535;
+            multipole_assemble_batch_kernel<<<dim3((unsigned)((nf + 127) / 128), (unsigned)cnt), 128, 0, st>>>(
+                part, nsplit * MG_GROUPS, nf, lmax, d_lm + 2 * m0, cnt, d_A + ((size_t)q * NM + m0) * ldA, ldA, f0, q, NQ);
+            launches++;
+        }
     return launches;
 }
 

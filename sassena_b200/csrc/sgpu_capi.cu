@@ -50,6 +50,10 @@ struct sgpu_ctx {
     size_t q_cap = 0;
     int *d_lm = nullptr;
     size_t lm_cap = 0;
+    double *d_qlens = nullptr;  // |q| batch of the multipole path
+    size_t qlens_cap = 0;
+    double *d_bq = nullptr;     // per-|q| factors [NQ][NA] (sgpu_set_factors_batch)
+    size_t bq_cap = 0, bq_nq = 0, bq_n = 0;
     std::vector<double> h_qs;
 
     double2 *d_A = nullptr;
@@ -81,6 +85,8 @@ struct sgpu_ctx {
         if (d_b) cudaFree(d_b);
         if (d_qs) cudaFree(d_qs);
         if (d_lm) cudaFree(d_lm);
+        if (d_qlens) cudaFree(d_qlens);
+        if (d_bq) cudaFree(d_bq);
         if (d_A) cudaFree(d_A);
         if (d_work) cudaFree(d_work);
         if (d_partial) cudaFree(d_partial);
@@ -245,12 +251,13 @@ int upload_q(sgpu_ctx *ctx, const double *qvecs, size_t NM, size_t pad) {
 }
 
 // DSP of nt timelines in d_A (ld = NF) accumulated into the packed partial
-int dsp_accumulate(sgpu_ctx *ctx, size_t nt, int dsp_type, double *d_partial) {
+int dsp_accumulate(sgpu_ctx *ctx, size_t nt, int dsp_type, double *d_partial, const double2 *d_A = nullptr) {
+    if (!d_A) d_A = ctx->d_A;
     if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
-        ctx->launches += corr_power_accumulate(&ctx->plan, ctx->d_A, ctx->NF, nt, ctx->d_work, d_partial,
+        ctx->launches += corr_power_accumulate(&ctx->plan, d_A, ctx->NF, nt, ctx->d_work, d_partial,
                                                d_partial + ctx->plan.L, ctx->stream);
     } else {
-        ctx->launches += dsp_elementwise_accumulate(ctx->d_A, ctx->NF, nt, ctx->NF, dsp_type == SGPU_DSP_SQUARE,
+        ctx->launches += dsp_elementwise_accumulate(d_A, ctx->NF, nt, ctx->NF, dsp_type == SGPU_DSP_SQUARE,
                                                     reinterpret_cast<double2 *>(d_partial), d_partial + 2 * ctx->NF,
                                                     ctx->d_work, ctx->stream);
     }
@@ -671,21 +678,14 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
     return SGPU_OK;
 }
 
-int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type,
-                                  double *d_partial) {
-    if (!ctx) return SGPU_EINVAL;
-    CK(cudaSetDevice(ctx->device));
-    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
-    if (rc) return rc;
-    if (NM == 0) return zero_partial(ctx, dsp_type, d_partial);  // a rank without moments contributes zeros
-    if (!lm) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: lm is NULL");
-    if (ctx->mode == 1 && ctx->repr != SGPU_REPR_SPHERICAL)
-        return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: staged frames are not in spherical representation");
+// moments -> device (l, m) ints; returns lmax through *lmax_out.  Mirrors the reference's validity check
+// (multipole_scatter_device.cpp:459-465, parameters.cpp:1101-1113).
+static int upload_moments(sgpu_ctx *ctx, const long *lm, size_t NM, int *lmax_out) {
     int lmax = 0;
     std::vector<int> h_lm(NM * 2);
     for (size_t i = 0; i < NM; i++) {
         const long l = lm[2 * i], m = lm[2 * i + 1];
-        if (l < 0 || std::labs(m) > l)  // multipole_scatter_device.cpp:459-465, parameters.cpp:1101-1113
+        if (l < 0 || std::labs(m) > l)
             return fail(ctx, SGPU_EINVAL,
                         "Combination of Major and minor moment not allowed: l=" + std::to_string(l) + ", m" +
                             std::to_string(m));
@@ -694,28 +694,157 @@ int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, si
         h_lm[2 * i] = (int)l;
         h_lm[2 * i + 1] = (int)m;
     }
-    rc = frames_amplitude_prologue(ctx, "sgpu_compute_mpsphere", NM, dsp_type, d_partial);
-    if (rc) return rc;
-    rc = ensure<int>(ctx, &ctx->d_lm, &ctx->lm_cap, NM * 2);
+    int rc = ensure<int>(ctx, &ctx->d_lm, &ctx->lm_cap, NM * 2);
     if (rc) return rc;
     rc = small_upload(ctx, ctx->d_lm, h_lm.data(), NM * 2 * sizeof(int));
     if (rc) return rc;
+    *lmax_out = lmax;
+    return SGPU_OK;
+}
+
+int sgpu_set_factors_batch(sgpu_ctx *ctx, const double *b, size_t NQ, size_t n) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!b || n == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, "sgpu_set_factors_batch: empty factors");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure<double>(ctx, &ctx->d_bq, &ctx->bq_cap, NQ * n);
+    if (rc) return rc;
+    rc = small_upload(ctx, ctx->d_bq, b, NQ * n * sizeof(double));
+    if (rc) return rc;
+    ctx->bq_nq = NQ;
+    ctx->bq_n = n;
+    return SGPU_OK;
+}
+
+// amplitudes A[q][mom][f] of NQ |q| values over the atoms [atom_first, atom_first+atom_count) into d_amp
+int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, const long *lm, size_t NM, size_t atom_first,
+                             size_t atom_count, double *d_amp) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!qlens || !lm || !d_amp) return fail(ctx, SGPU_EINVAL, "sgpu_mpsphere_amplitudes: NULL argument");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: frames are not staged (stage_frames first)");
+    if (ctx->repr != SGPU_REPR_SPHERICAL)
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: staged frames are not in spherical representation");
+    if (NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: No moments / qvectors to compute");
+    if (atom_first + atom_count > ctx->NA) return fail(ctx, SGPU_EINVAL, "sgpu_mpsphere_amplitudes: atom range out of bounds");
+    // factors: a per-|q| batch if one was set for exactly this NQ, else the single set
+    const double *d_b = ctx->d_b;
+    size_t b_stride = 0;
+    if (ctx->bq_nq == NQ && ctx->bq_n == ctx->NA && ctx->d_bq) {
+        d_b = ctx->d_bq;
+        b_stride = ctx->NA;
+    } else if (ctx->nb != ctx->NA) {
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: scattering factors not set for the staged atoms");
+    }
+    int lmax = 0;
+    int rc = upload_moments(ctx, lm, NM, &lmax);
+    if (rc) return rc;
+    rc = ensure<double>(ctx, &ctx->d_qlens, &ctx->qlens_cap, NQ);
+    if (rc) return rc;
+    rc = small_upload(ctx, ctx->d_qlens, qlens, NQ * sizeof(double));
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->copy_stream));
     drop_chunks(ctx);
-    int nsplit = 1;
-    const size_t mp_work = multipole_work_doubles(ctx->NF, lmax, &nsplit, ctx->NA) * sizeof(double);
-    rc = ensure_work(ctx, std::max(mp_work, dsp_work_bytes(ctx, NM, dsp_type)));
+    double2 *A = reinterpret_cast<double2 *>(d_amp);
+    if (lmax <= 21) {
+        rc = ensure_work(ctx, multipole_batch_work_doubles(ctx->NF, lmax, std::max<size_t>(atom_count, 1), (int)NQ) * sizeof(double));
+        if (rc) return rc;
+        ctx->launches += launch_multipole_sphere_batch(ctx->d_xyz, d_b, b_stride, ctx->d_qlens, (int)NQ, ctx->d_lm, NM, lmax, A,
+                                                       ctx->NF, ctx->NA, atom_first, atom_first + atom_count, 0, ctx->NF,
+                                                       reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+    } else {
+        // more (l,m) pairs than threads of the batched kernel: one pass per |q| with the shuffle-reduction kernel
+        if (atom_first != 0 || atom_count != ctx->NA)
+            return fail(ctx, SGPU_EINVAL, "sgpu_mpsphere_amplitudes: atom sharding needs moments with l <= 21");
+        int nsplit = 1;
+        rc = ensure_work(ctx, multipole_work_doubles(ctx->NF, lmax, &nsplit, ctx->NA) * sizeof(double));
+        if (rc) return rc;
+        for (size_t q = 0; q < NQ; q++)
+            ctx->launches += launch_multipole_sphere(ctx->d_xyz, d_b + q * b_stride, qlens[q], ctx->d_lm, NM, lmax,
+                                                     A + q * NM * ctx->NF, ctx->NF, ctx->NA, 0, ctx->NF,
+                                                     reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+    }
+    CK(cudaGetLastError());
+    return SGPU_OK;
+}
+
+// DSP of the (summed) amplitudes of NQ |q| values: d_partials receives NQ consecutive packed partials
+int sgpu_mpsphere_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t NQ, size_t NM, int dsp_type, double *d_partials) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (!d_amp || !d_partials) return fail(ctx, SGPU_EINVAL, "sgpu_mpsphere_dsp_partial: NULL argument");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_mpsphere_dsp_partial: frames are not staged");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure_work(ctx, dsp_work_bytes(ctx, NM, dsp_type));
+    if (rc) return rc;
+    const size_t plen = partial_len(ctx, dsp_type);
+    CK(cudaMemsetAsync(d_partials, 0, NQ * plen * sizeof(double), ctx->stream));
+    const double2 *A = reinterpret_cast<const double2 *>(d_amp);
+    for (size_t q = 0; q < NQ; q++) {
+        rc = dsp_accumulate(ctx, NM, dsp_type, d_partials + q * plen, A + q * NM * ctx->NF);
+        if (rc) return rc;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_compute_mpsphere_batch_partial(sgpu_ctx *ctx, const double *qlens, size_t NQ, const long *lm, size_t NM,
+                                        int dsp_type, double *d_partials) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: frames are not staged (stage_frames first)");
+    if (NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: No moments / qvectors to compute");
+    rc = ensure<double2>(ctx, &ctx->d_A, &ctx->A_cap, NQ * NM * ctx->NF);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    ctx->launches += launch_multipole_sphere(ctx->d_xyz, ctx->d_b, qlen, ctx->d_lm, NM, lmax, ctx->d_A, ctx->NF, ctx->NA, 0,
-                                             ctx->NF, reinterpret_cast<double *>(ctx->d_work), ctx->stream);
-    CK(cudaGetLastError());
+    rc = sgpu_mpsphere_amplitudes(ctx, qlens, NQ, lm, NM, 0, ctx->NA, reinterpret_cast<double *>(ctx->d_A));
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->A_NM = NM;
-    rc = dsp_accumulate(ctx, NM, dsp_type, d_partial);
+    ctx->A_NM = (NQ == 1) ? NM : 0;
+    rc = sgpu_mpsphere_dsp_partial(ctx, reinterpret_cast<const double *>(ctx->d_A), NQ, NM, dsp_type, d_partials);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
     ctx->have_times = true;
+    return SGPU_OK;
+}
+
+int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type,
+                                  double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (NM == 0) return zero_partial(ctx, dsp_type, d_partial);  // a rank without moments contributes zeros
+    if (!lm) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: lm is NULL");
+    // a per-|q| factor batch does not apply to the single-|q| entry point
+    ctx->bq_nq = 0;
+    return sgpu_compute_mpsphere_batch_partial(ctx, &qlen, 1, lm, NM, dsp_type, d_partial);
+}
+
+int sgpu_compute_mpsphere_batch(sgpu_ctx *ctx, const double *qlens, size_t NQ, const long *lm, size_t NM, int dsp_type,
+                                int dsp_method, double *atfinal, double *afinal, double *a2final) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: frames are not staged (stage_frames first)");
+    if (NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: No moments / qvectors to compute");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    const size_t plen = partial_len(ctx, dsp_type);
+    rc = ensure<double>(ctx, &ctx->d_partial, &ctx->partial_cap, NQ * plen);
+    if (rc) return rc;
+    rc = sgpu_compute_mpsphere_batch_partial(ctx, qlens, NQ, lm, NM, dsp_type, ctx->d_partial);
+    if (rc) return rc;
+    const double scale = 1.0 / (4.0 * 3.14159265358979323846);
+    for (size_t q = 0; q < NQ; q++) {
+        rc = sgpu_finalize(ctx, ctx->d_partial + q * plen, dsp_type, dsp_method, scale, atfinal + q * 2 * ctx->NF,
+                           afinal + 2 * q, a2final + 2 * q);
+        if (rc) return rc;
+    }
     return SGPU_OK;
 }
 

@@ -412,3 +412,68 @@ def test_host_layer_devices_on_gpu(oracle):
     for r, q in zip(recs, qv[1:3]):
         ref = oracle.compute_mpsphere(oracle.cart_to_spherical(xyz), b, np.linalg.norm(q), pm.moments, nthreads=4)
         assert rel_err(r["fqt"], ref[0]) < TOL
+
+
+@pytest.mark.parametrize("L", [0, 1, 6, 20])
+def test_mpsphere_batch_and_atom_sharding(gpu_ctx, oracle, L):
+    """batched multipole sphere (several |q| per pass, per-|q| factors) and the atom-sharded multi-GPU protocol:
+    amplitudes of atom slices summed == full amplitudes; everything vs the oracle"""
+    NA, NF = 137, 9
+    xyz = synth.trajectory(NF, NA, 60.0, 0.3, 23, offset=-30.0)
+    sph = oracle.cart_to_spherical(xyz)
+    b = synth.factors(NA)
+    mom = oracle.moments_sphere(L)
+    qls = np.array([0.01, 0.07, 0.3, 0.9, 1.7, 2.5, 0.5, 0.11, 1.23, 0.02, 3.1])  # 11 = 8 + 2 + 1
+    bq = np.array([b * (1.0 + 0.05 * i) for i in range(len(qls))])
+    from sassena_b200 import REPR_SPHERICAL
+    gpu_ctx.stage_frames(sph, repr=REPR_SPHERICAL)
+    gpu_ctx.set_factors(b)
+    gpu_ctx.set_factors_batch(bq)
+    res = gpu_ctx.compute_mpsphere_batch(qls, mom, dsp="autocorrelate")
+    for i, ql in enumerate(qls):
+        rfqt, rfq, rfq2 = oracle.compute_mpsphere(sph, bq[i], ql, mom, nthreads=4)
+        assert rel_err(res[i][0], rfqt) < TOL
+        assert abs(res[i][1] - rfq) < TOL * abs(rfqt[0])
+        assert abs(res[i][2] - rfq2) <= TOL * abs(rfq2)
+    # single-|q| entry point ignores the batch factors
+    fqt, fq, fq2 = gpu_ctx.compute_mpsphere(qls[3], mom)
+    rfqt, _, _ = oracle.compute_mpsphere(sph, b, qls[3], mom, nthreads=4)
+    assert rel_err(fqt, rfqt) < TOL
+    # atom sharding over 3 logical ranks (DivAssignment over atoms) + summed amplitudes
+    NQ, NM = 3, len(mom)
+    n = NQ * NM * NF * 2
+    d_amp = gpu_ctx.device_alloc(n * 8)
+    total = np.zeros(n)
+    for r in range(3):
+        off, size, _ = oracle.div_assignment(3, r, NA)
+        gpu_ctx.mpsphere_amplitudes(qls[:NQ], mom, off, size, d_amp)
+        gpu_ctx.synchronize()
+        part = np.empty(n)
+        gpu_ctx.memcpy_d2h(part, d_amp)
+        total += part
+    gpu_ctx.memcpy_h2d(d_amp, total)
+    plen = gpu_ctx.partial_len("square")
+    d_part = gpu_ctx.device_alloc(NQ * plen * 8)
+    gpu_ctx.mpsphere_dsp_partial(d_amp, NQ, NM, d_part, dsp="square")
+    for i in range(NQ):
+        fqt, fq, fq2 = gpu_ctx.finalize(d_part + i * plen * 8, 1.0 / (4 * np.pi), dsp="square")
+        rfqt, rfq, rfq2 = oracle.compute_mpsphere(sph, b, qls[i], mom, dsp="square", nthreads=4)
+        assert rel_err(fqt, rfqt) < TOL and abs(fq - rfq) < TOL * abs(rfqt[0])
+    gpu_ctx.device_free(d_amp)
+    gpu_ctx.device_free(d_part)
+
+
+def test_mpsphere_large_l_falls_back(gpu_ctx, oracle):
+    """l > 21 has more (l,m) pairs than the batched kernel has threads: the per-|q| kernel takes over"""
+    NA, NF = 40, 3
+    xyz = synth.trajectory(NF, NA, 40.0, 0.3, 29, offset=-20.0)
+    sph = oracle.cart_to_spherical(xyz)
+    b = synth.factors(NA)
+    mom = np.array([[24, -3], [24, 24], [30, 0], [2, 1]])
+    from sassena_b200 import REPR_SPHERICAL
+    gpu_ctx.stage_frames(sph, repr=REPR_SPHERICAL)
+    gpu_ctx.set_factors(b)
+    res = gpu_ctx.compute_mpsphere_batch([0.4, 1.1], mom, dsp="square")
+    for i, ql in enumerate([0.4, 1.1]):
+        rfqt, rfq, rfq2 = oracle.compute_mpsphere(sph, b, ql, mom, dsp="square")
+        assert rel_err(res[i][0], rfqt) < TOL

@@ -24,7 +24,7 @@ if which in ("all", "self"):
           f"cfg2 (1.2e8 timelines) would take {1.2e8/(tl/dt):.1f} s for all 20 |q|")
     ctx.device_free(d)
 
-if which in ("all", "mp"):
+if which in ("all", "mp", "mpbatch"):
     NA, NF, L = 1000000, int(os.environ.get("MP_NF", 16)), 20
     d = ctx.device_alloc(NA * NF * 12)
     ctx.synth_trajectory(d, NF, NA, 220.0, 0.05, 7, offset=-110.0)
@@ -41,6 +41,13 @@ if which in ("all", "mp"):
             dt = time.time() - t0
         print(f"mpsphere |q|={ql}: {NA} atoms x {NF} frames x {len(mom)} moments: {dt*1e3:.1f} ms (amp {ctx.last_amplitude_ms():.1f} ms) -> "
               f"{NA*NF*len(mom)/dt:.3e} moment-evals/s; cfg4 (1000 frames x 200 |q|) would take {dt/NF*1000*200:.0f} s")
+
+    ql8 = np.linspace(0.01, 0.5, 8)
+    for it in range(2):
+        ctx.synchronize(); t0 = time.time()
+        ctx.compute_mpsphere_batch(ql8, mom, dsp="square")
+        dt = time.time() - t0
+    print(f"mpsphere batch of 8 |q|: {dt*1e3:.1f} ms -> {8*NA*NF*len(mom)/dt:.3e} moment-evals/s; cfg4 would take {dt/NF*1000*200/8:.0f} s")
 
 if which in ("all", "h2d"):
     n = 1 << 30
