@@ -49,6 +49,10 @@ typedef struct sass_backend_vtbl {
     int (*finalize)(sgpu_ctx *, const double *, int, int, double, double *, double *, double *);
     int (*device_alloc)(void **, size_t);
     int (*device_free)(void *);
+    /* batched / atom-sharded multipole path */
+    int (*set_factors_batch)(sgpu_ctx *, const double *, size_t, size_t);
+    int (*mpsphere_amplitudes)(sgpu_ctx *, const double *, size_t, const long *, size_t, size_t, size_t, double *);
+    int (*mpsphere_dsp_partial)(sgpu_ctx *, const double *, size_t, size_t, int, double *);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);

@@ -33,6 +33,9 @@ BE_COMPUTE_VEC = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_in
 BE_COMPUTE_MP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, c_long_p, C.c_size_t, C.c_int, C.c_void_p)
 BE_FINALIZE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p,
                           c_double_p)
+BE_SET_FACTORS_BATCH = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_size_t)
+BE_MP_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_long_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p)
+BE_MP_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -43,7 +46,9 @@ class BackendVtbl(C.Structure):
                 ("stage_atoms_from_frames", BE_STAGE_ATOMS_FF), ("set_factors", BE_SET_FACTORS),
                 ("partial_len", BE_PARTIAL_LEN), ("compute_all_vectors_partial", BE_COMPUTE_VEC),
                 ("compute_self_vectors_partial", BE_COMPUTE_VEC), ("compute_mpsphere_partial", BE_COMPUTE_MP),
-                ("finalize", BE_FINALIZE), ("device_alloc", BE_ALLOC), ("device_free", BE_FREE)]
+                ("finalize", BE_FINALIZE), ("device_alloc", BE_ALLOC), ("device_free", BE_FREE),
+                ("set_factors_batch", BE_SET_FACTORS_BATCH), ("mpsphere_amplitudes", BE_MP_AMPL),
+                ("mpsphere_dsp_partial", BE_MP_DSP)]
 
 
 FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)

@@ -319,7 +319,10 @@ const SgpuBackend &default_backend() {
                                    sgpu_compute_mpsphere_partial,
                                    sgpu_finalize,
                                    sgpu_device_alloc,
-                                   sgpu_device_free};
+                                   sgpu_device_free,
+                                   sgpu_set_factors_batch,
+                                   sgpu_mpsphere_amplitudes,
+                                   sgpu_mpsphere_dsp_partial};
     return be;
 }
 
@@ -673,31 +676,104 @@ void MPSphereScatterDevice::stage_data() {
     factors_.assign(NA, 0.0);
 }
 
-void MPSphereScatterDevice::compute() {
-    CartesianCoor3D q = vectors_[current_vector_];
+MPSphereScatterDevice::~MPSphereScatterDevice() {
+    if (d_amp_) be_.device_free(d_amp_);
+}
+
+// up to `nq` |q| values starting at current_vector_: fills batch_atfinal_/batch_afinal_/batch_a2final_
+void MPSphereScatterDevice::compute_batch(size_t nq) {
     timer_.start("sd:c:init");
-    init_moments(q);
-    sample_.factors(q.length(), factors_.data());
-    ck(be_.set_factors(ctx_, factors_.data(), NA), "sgpu_set_factors");
+    std::vector<double> qlens(nq), fb(nq * NA);
+    for (size_t i = 0; i < nq; i++) {
+        CartesianCoor3D q = vectors_[current_vector_ + i];
+        if (i == 0) init_moments(q);
+        qlens[i] = q.length();
+        sample_.factors(qlens[i], &fb[i * NA]);  // scatterfactors.update(q) per |q|
+    }
+    ck(be_.set_factors_batch(ctx_, fb.data(), nq, NA), "sgpu_set_factors_batch");
     timer_.stop("sd:c:init");
     const int dsp = dsp_type_code();
     dsp_method_code();
     for (auto &mm : multipole_index_)
-        if (labs(mm.second) > mm.first)  // :459-465
+        if (labs(mm.second) > mm.first)  // multipole_scatter_device.cpp:459-465
             throw Error("Combination of Major and minor moment not allowed: l=" + std::to_string(mm.first) + ", m" +
                         std::to_string(mm.second));
-    DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NM);
-    std::vector<long> lm(2 * std::max<size_t>(mine.size(), 1));
-    for (size_t i = 0; i < mine.size(); i++) {
-        lm[2 * i] = multipole_index_[mine[i]].first;
-        lm[2 * i + 1] = multipole_index_[mine[i]].second;
+    std::vector<long> lm(2 * NM);
+    for (size_t i = 0; i < NM; i++) {
+        lm[2 * i] = multipole_index_[i].first;
+        lm[2 * i + 1] = multipole_index_[i].second;
     }
-    double *partial = partial_buffer(dsp);
+    const size_t amp_len = nq * NM * NF * 2;
+    if (amp_len > amp_cap_) {
+        if (d_amp_) be_.device_free(d_amp_);
+        d_amp_ = nullptr;
+        void *pp = nullptr;
+        if (be_.device_alloc(&pp, amp_len * sizeof(double))) throw Error("device allocation of the amplitude buffer failed");
+        d_amp_ = static_cast<double *>(pp);
+        amp_cap_ = amp_len;
+    }
+    // atom decomposition inside the partition: rank r sums over DivAssignment(NNPP, r, NA) atoms
+    DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NA);
     timer_.start("sd:c:block");
-    ck(be_.compute_mpsphere_partial(ctx_, qvector_.length(), lm.data(), mine.size(), dsp, partial),
-       "sgpu_compute_mpsphere_partial");
+    ck(be_.mpsphere_amplitudes(ctx_, qlens.data(), nq, lm.data(), NM, mine.offset(), mine.size(), d_amp_),
+       "sgpu_mpsphere_amplitudes");
     timer_.stop("sd:c:block");
-    reduce_and_finalize(dsp, 1.0 / (4 * M_PI));  // :395-400
+    timer_.start("sd:c:wait");
+    ck(be_.synchronize(ctx_), "sgpu_synchronize");
+    timer_.stop("sd:c:wait");
+    timer_.start("sd:c:reduce");
+    if (partitioncomm_->size() > 1) partitioncomm_->allreduce_sum(d_amp_, amp_len);
+    timer_.stop("sd:c:reduce");
+    size_t plen = 0;
+    ck(be_.partial_len(ctx_, dsp, &plen), "sgpu_partial_len");
+    if (nq * plen > partial_cap_) {
+        if (d_partial_) be_.device_free(d_partial_);
+        d_partial_ = nullptr;
+        void *pp = nullptr;
+        if (be_.device_alloc(&pp, nq * plen * sizeof(double))) throw Error("device allocation of the partial buffer failed");
+        d_partial_ = static_cast<double *>(pp);
+        partial_cap_ = nq * plen;
+    }
+    timer_.start("sd:c:b:dspstore");
+    ck(be_.mpsphere_dsp_partial(ctx_, d_amp_, nq, NM, dsp, d_partial_), "sgpu_mpsphere_dsp_partial");
+    batch_atfinal_.assign(nq, std::vector<double>(2 * NF));
+    batch_afinal_.assign(nq, 0.0);
+    batch_a2final_.assign(nq, 0.0);
+    const double factor = 1.0 / (4 * M_PI);  // :395-400
+    for (size_t i = 0; i < nq; i++) {
+        double af[2], a2f[2];
+        ck(be_.finalize(ctx_, d_partial_ + i * plen, dsp, dsp_method_code(), factor, batch_atfinal_[i].data(), af, a2f),
+           "sgpu_finalize");
+        batch_afinal_[i] = std::complex<double>(af[0], af[1]);
+        batch_a2final_[i] = std::complex<double>(a2f[0], a2f[1]);
+    }
+    timer_.stop("sd:c:b:dspstore");
+}
+
+void MPSphereScatterDevice::compute() {
+    compute_batch(1);
+    atfinal_ = batch_atfinal_[0];
+    afinal_ = batch_afinal_[0];
+    a2final_ = batch_a2final_[0];
+}
+
+void MPSphereScatterDevice::runner() {
+    const size_t BATCH = 8;
+    while (status() == 0) {
+        const size_t nq = std::min(BATCH, vectors_.size() - current_vector_);
+        timer_.start("sd:compute");
+        compute_batch(nq);
+        timer_.stop("sd:compute");
+        for (size_t i = 0; i < nq; i++) {
+            atfinal_ = batch_atfinal_[i];
+            afinal_ = batch_afinal_[i];
+            a2final_ = batch_a2final_[i];
+            timer_.start("sd:write");
+            write();
+            timer_.stop("sd:write");
+            next();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

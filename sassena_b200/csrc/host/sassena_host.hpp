@@ -387,12 +387,22 @@ class MPSphereScatterDevice : public AbstractScatterDevice {
     std::vector<std::pair<long, long>> multipole_index_;
     CartesianCoor3D qvector_;
     size_t NM = 0;
+    double *d_amp_ = nullptr;
+    size_t amp_cap_ = 0;
     void init_moments(CartesianCoor3D &q);  // multipole_scatter_device.cpp:155-165
     void stage_data() override;
     void compute() override;
+    // The runner loop (abstract_scatter_device.cpp:162-173) processes |q| values in batches: Y_lm does not depend on
+    // |q|, so one pass over the atoms serves up to 8 |q|; atoms are sharded over the partition's GPUs and the
+    // amplitudes A_lm[f] are all-reduced BEFORE the DSP (they are sums over atoms).
+    void runner() override;
+    void compute_batch(size_t nq);
+    std::vector<std::vector<double>> batch_atfinal_;
+    std::vector<std::complex<double>> batch_afinal_, batch_a2final_;
 
    public:
     using AbstractScatterDevice::AbstractScatterDevice;
+    ~MPSphereScatterDevice() override;
 };
 
 class ScatterDeviceFactory {  // scatter_device_factory.cpp:23-210

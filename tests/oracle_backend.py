@@ -30,7 +30,9 @@ class OracleBackend:
             compute_all_vectors_partial=_host.BE_COMPUTE_VEC(self._compute_all),
             compute_self_vectors_partial=_host.BE_COMPUTE_VEC(self._compute_self),
             compute_mpsphere_partial=_host.BE_COMPUTE_MP(self._compute_mp), finalize=_host.BE_FINALIZE(self._finalize),
-            device_alloc=_host.BE_ALLOC(self._alloc), device_free=_host.BE_FREE(self._free))
+            device_alloc=_host.BE_ALLOC(self._alloc), device_free=_host.BE_FREE(self._free),
+            set_factors_batch=_host.BE_SET_FACTORS_BATCH(self._set_factors_batch),
+            mpsphere_amplitudes=_host.BE_MP_AMPL(self._mp_amplitudes), mpsphere_dsp_partial=_host.BE_MP_DSP(self._mp_dsp))
         self._cbs = cbs
         self.vtbl = _host.BackendVtbl(**cbs)
 
@@ -76,6 +78,39 @@ class OracleBackend:
 
     def _set_factors(self, c, b, n):
         self._ctx(c)["b"] = np.ctypeslib.as_array(b, shape=(n,)).copy()
+        return 0
+
+    def _set_factors_batch(self, c, b, NQ, n):
+        self._ctx(c)["bq"] = np.ctypeslib.as_array(b, shape=(NQ, n)).copy()
+        return 0
+
+    def _mp_amplitudes(self, c, qlens, NQ, lm, NM, a0, na, out):
+        ctx = self._ctx(c)
+        NF = ctx["NF"]
+        ql = np.ctypeslib.as_array(qlens, shape=(NQ,)).copy()
+        mom = np.ctypeslib.as_array(lm, shape=(NM, 2)).copy()
+        A = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(NQ, NM, NF, 2))
+        for i in range(NQ):
+            if na == 0:
+                A[i] = 0
+                continue
+            b = ctx["bq"][i] if "bq" in ctx and len(ctx["bq"]) == NQ else ctx["b"]
+            *_, amp = o.compute_mpsphere(ctx["xyz"][:, a0:a0 + na], b[a0:a0 + na], ql[i], mom, dsp="plain",
+                                         return_amplitudes=True)
+            A[i] = amp.view(np.float64).reshape(NM, NF, 2)
+        return 0
+
+    def _mp_dsp(self, c, amp, NQ, NM, dsp, ptr):
+        ctx = self._ctx(c)
+        NF = ctx["NF"]
+        A = np.ctypeslib.as_array(C.cast(amp, C.POINTER(C.c_double)), shape=(NQ, NM, NF, 2))
+        plen = 2 * NF + 4
+        P = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(NQ, plen))
+        for i in range(NQ):
+            Ac = np.ascontiguousarray(A[i]).view(np.complex128).reshape(NM, NF)
+            fqt, fq, fq2 = o.np_dsp_store(Ac, _DSP[dsp], "fftw", norm=1.0)
+            P[i, :2 * NF] = np.ascontiguousarray(fqt).view(np.float64)
+            P[i, 2 * NF:] = (fq.real, fq.imag, fq2.real, fq2.imag)
         return 0
 
     def _partial_len(self, c, dsp, out):

@@ -477,3 +477,23 @@ def test_mpsphere_large_l_falls_back(gpu_ctx, oracle):
     for i, ql in enumerate([0.4, 1.1]):
         rfqt, rfq, rfq2 = oracle.compute_mpsphere(sph, b, ql, mom, dsp="square")
         assert rel_err(res[i][0], rfqt) < TOL
+
+
+def test_host_layer_mpsphere_batches_q(oracle):
+    """MPSphereScatterDevice::runner batches |q| values (8 per pass) with per-|q| factors: 11 |q| = 8 + 3"""
+    from sassena_b200 import host
+    NA, NF = 90, 12
+    xyz = synth.trajectory(NF, NA, 50.0, 0.2, 37, offset=-25.0)
+    b = synth.factors(NA)
+    qv = host.create_from_scans([{"base": (0, 1, 0), "from": 0.05, "to": 2.2, "points": 11}])
+    pm = host.Params().set("scattering.average.orientation.type", "multipole")
+    pm.set("scattering.average.orientation.multipole.moments.type", "resolution")
+    pm.set("scattering.average.orientation.multipole.moments.resolution", 4).create()
+    recs, has, tm = host.run_scatter(pm, xyz, qv, factors_fn=lambda ql: b * (1.0 + ql))
+    assert len(recs) == 11 and tm["sd:compute"][1] == 2 and tm["sd:write"][1] == 11
+    sph = oracle.cart_to_spherical(xyz)
+    for r, q in zip(recs, qv):
+        ql = np.linalg.norm(q)
+        ref = oracle.compute_mpsphere(sph, b * (1.0 + ql), ql, pm.moments, nthreads=4)
+        assert np.array_equal(r["q"], q)
+        assert rel_err(r["fqt"], ref[0]) < TOL and abs(r["fq"] - ref[1]) < TOL * abs(ref[0][0])
