@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (B200); run with -m gpu")
+    # the product library is built in-tree by __graft_entry__.build(); build it here too if a fresh checkout runs the
+    # tests first (nvcc cross-compiles without a GPU).  A failed build must fail the tests loudly, not skip them.
+    from sassena_b200 import build as _b
+    if _b.needs_build():
+        _b.build()
 
 
 @pytest.fixture(scope="session")
