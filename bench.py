@@ -164,6 +164,19 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # exactly ONE line may reach stdout (the JSON line): NCCL / torchrun banners go to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _run_ours(args, saved_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+
+
+def _run_ours(args, json_fd):
     import torch
     import torch.distributed as dist
     import sassena_b200
@@ -243,6 +256,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, amp_ms_max = float(t[0]), float(t[1])
+    per_rank = [None] * world
+    if world > 1:
+        dist.all_gather_object(per_rank, {"rank": rank, "step_ms": ms / args.steps, "amp_ms": amp_ms / args.steps,
+                                          "fp64_peak_tflops": fp64_peak})
+    else:
+        per_rank = [{"rank": 0, "step_ms": ms / args.steps, "amp_ms": amp_ms / args.steps, "fp64_peak_tflops": fp64_peak}]
     evals_step = float(NA) * NF * NM
     value = evals_step * args.steps / (ms_max * 1e-3)
 
@@ -362,8 +381,9 @@ def run_ours(args):
             "parity": parity,
             "host_wall_ms_per_step": wall_ms / args.steps,
             "dsp_ms_per_step": dsp_ms / args.steps,
+            "per_rank": per_rank,
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -138,7 +138,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs,
-    double2 *__restrict__ A, size_t ldA, int NA, int NM, unsigned ngroups, size_t f0, int use_bulk) {
+    double2 *__restrict__ A, size_t ldA, int NA, int NM, unsigned ngroups, size_t f0, int use_bulk, int m_base) {
+    // WARPS is the maximum; the launch may use fewer warps per CTA (blockDim.x / 32) so that the q-vectors of a launch
+    // are covered without padding (tail launches).  m_base: first q-vector of this launch.
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_xyz = reinterpret_cast<float *>(smem_raw);                                     // [STAGES][TILE*3]
     double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);     // [STAGES][TILE]
@@ -148,14 +150,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
     const unsigned group = blockIdx.x % ngroups;
     const size_t frame = f0 + blockIdx.x / ngroups;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = (group * WARPS + warp) * QPT;
+    const int nwarps = blockDim.x >> 5;
+    const int m0 = m_base + (group * nwarps + warp) * QPT;
     const float *p = xyz + frame * (size_t)NA * 3;
     const int ntiles = (NA + TILE - 1) / TILE;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
-            ptx::mbar_init(&full[s], use_bulk ? 1u : (unsigned)(WARPS * 32));
-            ptx::mbar_init(&empty[s], (unsigned)WARPS);
+            ptx::mbar_init(&full[s], use_bulk ? 1u : (unsigned)blockDim.x);
+            ptx::mbar_init(&empty[s], (unsigned)nwarps);
         }
         ptx::fence_barrier_init();
     }
@@ -176,10 +179,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
             if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
             float *dx = s_xyz + (size_t)s * TILE * 3;
             const float *sx = p + (size_t)a0 * 3;
-            for (int i = tid; i < cnt * 3; i += WARPS * 32) ptx::cp_async4(dx + i, sx + i);
+            for (int i = tid; i < cnt * 3; i += (int)blockDim.x) ptx::cp_async4(dx + i, sx + i);
             float *db = reinterpret_cast<float *>(s_b + (size_t)s * TILE);
             const float *sb = reinterpret_cast<const float *>(b + a0);
-            for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
+            for (int i = tid; i < cnt * 2; i += (int)blockDim.x) ptx::cp_async4(db + i, sb + i);
             ptx::cp_async_mbar_arrive_noinc(&full[s]);
         }
     };
@@ -528,10 +531,11 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters)
 
 namespace {
 template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
-int launch_tiled(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
-                 size_t NM, size_t f0, size_t nf, cudaStream_t st) {
-    const unsigned per_cta = QPT * WARPS;
-    const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
+int launch_tiled_part(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+                      size_t NM, size_t f0, size_t nf, cudaStream_t st, int m_base, int nvec, int warps) {
+    // covers q-vectors [m_base, m_base + nvec) with CTAs of `warps` warps x QPT vectors
+    const unsigned per_cta = QPT * warps;
+    const unsigned ngroups = (unsigned)((nvec + per_cta - 1) / per_cta);
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
     auto kern = amplitude_all_tiled_kernel<QPT, WARPS, TILE, STAGES, MINB, ABL, PAIR>;
     static bool attr = false;
@@ -546,17 +550,25 @@ int launch_tiled(const float *d_xyz, const double *d_b, const double *d_qs, doub
     const size_t max_frames = (size_t)0x7fffffff / ngroups;
     for (size_t done = 0; done < nf;) {
         size_t cnt = nf - done < max_frames ? nf - done : max_frames;
-        kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups,
-                                                                   f0 + done, use_bulk);
+        kern<<<(unsigned)(cnt * ngroups), warps * 32, smem, st>>>(d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups,
+                                                                  f0 + done, use_bulk, m_base);
         launches++;
         done += cnt;
     }
     return launches;
 }
 
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
+int launch_tiled(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+                 size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    return launch_tiled_part<QPT, WARPS, TILE, STAGES, MINB, ABL, PAIR>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0,
+                                                                        (int)NM, WARPS);
+}
+
 template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
-int launch_uq(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
-              size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+int launch_uq_part(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+                   size_t NM, size_t f0, size_t nf, cudaStream_t st, size_t m_base, size_t nvec) {
+    // q-vectors [m_base, m_base+nvec): every CTA of 8 warps works on QPT vectors and splits the atoms over its warps
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t) + (size_t)WARPS * 2 * QPT * 8;
     auto kern = amplitude_all_uq_kernel<QPT, WARPS, TILE, STAGES, MINB>;
     static bool attr = false;
@@ -568,18 +580,56 @@ int launch_uq(const float *d_xyz, const double *d_b, const double *d_qs, double2
                          ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
     int launches = 0;
     const size_t chunk = (UQ_MAXQ / QPT) * QPT;
-    for (size_t m0 = 0; m0 < NM; m0 += chunk) {
-        const size_t cnt_m = NM - m0 < chunk ? NM - m0 : chunk;
-        const size_t padded = ((cnt_m + QPT - 1) / QPT) * QPT;  // d_qs is zero padded to a multiple of 64 >= QPT multiple
-        cudaMemcpyToSymbolAsync(c_q, d_qs + 3 * m0, padded * 3 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st);
+    for (size_t m0 = 0; m0 < nvec; m0 += chunk) {
+        const size_t cnt_m = nvec - m0 < chunk ? nvec - m0 : chunk;
+        const size_t padded = ((cnt_m + QPT - 1) / QPT) * QPT;  // d_qs carries >= 8 zero vectors of slack past NM
+        cudaMemcpyToSymbolAsync(c_q, d_qs + 3 * (m_base + m0), padded * 3 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st);
         const unsigned ngroups = (unsigned)(padded / QPT);
         const size_t max_frames = (size_t)0x7fffffff / ngroups;
         for (size_t done = 0; done < nf;) {
             size_t cnt = nf - done < max_frames ? nf - done : max_frames;
-            kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_A, ldA, (int)NA, (int)NM, (int)m0,
-                                                                       ngroups, f0 + done, use_bulk);
+            kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_A, ldA, (int)NA, (int)NM,
+                                                                       (int)(m_base + m0), ngroups, f0 + done, use_bulk);
             launches++;
             done += cnt;
+        }
+    }
+    return launches;
+}
+
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
+int launch_uq(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+              size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    return launch_uq_part<QPT, WARPS, TILE, STAGES, MINB>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0, NM);
+}
+
+// default path: full CTAs of 8 warps x 6 vectors (each warp owns 6 vectors), then the remainder r = NM mod 48 with the
+// uniform-q kernel (a CTA owns QPT vectors and its 8 warps split the atoms), QPT in 4..8 chosen to cover r with the
+// least padding.  Keeps full occupancy for any NM: with the subvectors of a |q| sharded over 8 GPUs (62-63 each)
+// padding to 48 would waste 35 %, and small-CTA tail launches ran at 77 % efficiency.
+int launch_tiled_exact(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
+                       size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    int launches = 0;
+    const size_t full = (NM / 48) * 48;
+    if (full > 0)
+        launches += launch_tiled_part<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0, (int)full, 8);
+    const size_t r = NM - full;
+    if (r > 0) {
+        int best_q = 8;
+        size_t best_waste = ((r + 7) / 8) * 8 - r;
+        for (int q = 7; q >= 4; q--) {
+            const size_t w = ((r + q - 1) / q) * q - r;
+            if (w < best_waste) {
+                best_q = q;
+                best_waste = w;
+            }
+        }
+        switch (best_q) {
+            case 8: launches += launch_uq_part<8, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, full, r); break;
+            case 7: launches += launch_uq_part<7, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, full, r); break;
+            case 6: launches += launch_uq_part<6, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, full, r); break;
+            case 5: launches += launch_uq_part<5, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, full, r); break;
+            default: launches += launch_uq_part<4, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, full, r); break;
         }
     }
     return launches;
@@ -598,7 +648,7 @@ int k1_variant() {
 // q-vectors per CTA of the active variant: the q array must be zero padded to a multiple of this
 int amplitude_all_qpad() {
     switch (k1_variant()) {
-        case 7: case 8: case 20: case 21: case 30: case 31: case 32: return 48;
+        case 7: case 8: case 20: case 21: case 30: case 31: case 32: case 36: return 48;
         case 33: return 72;
         case 34: return 56;
         case 9: case 35: return 40;
@@ -617,7 +667,8 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
         case 4: return launch_tiled<8, 4, 512, 4, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 5: return launch_tiled<8, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 6: return launch_tiled<4, 16, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 7: return launch_tiled<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 7: return launch_tiled_exact(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
+        case 36: return launch_tiled<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 20: return launch_tiled<6, 8, 512, 4, 2, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 21: return launch_tiled<6, 8, 512, 4, 2, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
         case 8: return launch_tiled<6, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);

@@ -242,7 +242,7 @@ int check_dsp(sgpu_ctx *ctx, int dsp_type, int dsp_method) {
 
 // upload q-vectors pre-scaled to quarter turns, zero padded to `pad` multiples
 int upload_q(sgpu_ctx *ctx, const double *qvecs, size_t NM, size_t pad) {
-    const size_t NMpad = ((NM + pad - 1) / pad) * pad;
+    const size_t NMpad = ((NM + pad - 1) / pad) * pad + 8;  // + slack: exactly-sized tail launches read < 8 past NM
     ctx->h_qs.assign(NMpad * 3, 0.0);
     for (size_t i = 0; i < NM * 3; i++) ctx->h_qs[i] = qvecs[i] * kTwoOverPi;
     int rc = ensure<double>(ctx, &ctx->d_qs, &ctx->q_cap, NMpad * 3);

@@ -497,3 +497,19 @@ def test_host_layer_mpsphere_batches_q(oracle):
         ref = oracle.compute_mpsphere(sph, b * (1.0 + ql), ql, pm.moments, nthreads=4)
         assert np.array_equal(r["q"], q)
         assert rel_err(r["fqt"], ref[0]) < TOL and abs(r["fq"] - ref[1]) < TOL * abs(ref[0][0])
+
+
+@pytest.mark.parametrize("NM", [1, 5, 47, 48, 49, 62, 63, 96, 125, 143])
+def test_all_vectors_exact_tail_launch(gpu_ctx, oracle, NM):
+    """q-vector counts that are not multiples of the 48-vector CTA: the remainder goes through an exactly-sized tail
+    launch (QPT 4..6, 1..8 warps); counts typical for 2/4/8-GPU sharding of 500 vectors (250, 125, 62/63) included"""
+    NA, NF = 257, 6
+    xyz = synth.trajectory(NF, NA, 25.0, 0.3, 41)
+    b = synth.factors(NA)
+    q = 1.9 * synth.unit_vectors(NM, 42)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    gpu_ctx.compute_all_vectors(q, dsp="plain")
+    A = gpu_ctx.get_amplitudes(NM)
+    *_, Aref = oracle.compute_all_vectors(xyz, b, q, dsp="plain", return_amplitudes=True)
+    assert rel_err(A, Aref) < 1e-12
