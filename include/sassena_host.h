@@ -111,6 +111,32 @@ void sass_dcd_close(sass_dcd *d);
 /* writes xyz[NF][NA][3] as a CHARMM DCD the reference's reader accepts (stager.dump format) */
 int sass_dcd_write(const char *path, const float *xyz, size_t NF, size_t NA);
 
+/* ---- control plane: scatter.xml + db.xml + PDB + DCD -> hot path ("next" row) ------------------------
+ * Replaces, for one process, the flow of the reference executable src/main/sassena.cpp:132-417:
+ *   Params::init/read_xml   src/control/parameters.cpp:64-792
+ *   Database::read_xml      src/control/database.cpp:31-145, evaluation :293-528
+ *   Sample::init            src/sample/sample.cpp:30-101 (PDB atoms, selections, framesets)
+ *   ScatterFactors          src/scatter_devices/scatter_factors.cpp:28-135
+ * Output: <signal_dir>/{qvectors,fqt,fq0,fq,fq2}.npy with the dataset names and shapes of the reference's signal.h5
+ * (src/services/file_writer_service.cpp:44-171); complex values are trailing [2] = (re, im). */
+typedef struct sass_job sass_job;
+int sass_job_load(const char *config_file, sass_job **out);
+void sass_job_free(sass_job *j);
+/* counts: all atoms of the structure, atoms of stager.target, frames, q-vectors */
+int sass_job_info(const sass_job *j, size_t *natoms, size_t *ntarget, size_t *nframes, size_t *nqvectors);
+int sass_job_qvectors(const sass_job *j, double *q_out /* [nqvectors][3] */);
+/* b_j(|q|) for the atoms of stager.target (ScatterFactors::update + get_all) */
+int sass_job_factors(const sass_job *j, double ql, double *b_out /* [ntarget] */);
+/* coordinates as staged: [nframes][ntarget][3]; the pointer stays valid until sass_job_free */
+int sass_job_frames(const sass_job *j, const float **frames);
+/* atom indices of a named selection; *n receives the full count, at most cap ids are stored */
+int sass_job_selection(const sass_job *j, const char *name, size_t *ids, size_t cap, size_t *n);
+/* the Params subset the scatter devices read (borrowed; do not free) */
+const sass_params *sass_job_params(const sass_job *j);
+/* runs every q-vector; comm/backend NULL = single process / the in-library CUDA backend */
+int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
+                 sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap);
+
 #ifdef __cplusplus
 }
 #endif

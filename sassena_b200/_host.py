@@ -80,6 +80,16 @@ SIGNATURES = {
     "sass_dcd_close": (None, [C.c_void_p]),
     "sass_dcd_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sass_init_subvectors": (C.c_size_t, [C.c_void_p, c_double_p, c_double_p, C.c_size_t]),
+    "sass_job_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sass_job_free": (None, [C.c_void_p]),
+    "sass_job_info": (C.c_int, [C.c_void_p, c_size_p, c_size_p, c_size_p, c_size_p]),
+    "sass_job_qvectors": (C.c_int, [C.c_void_p, c_double_p]),
+    "sass_job_factors": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
+    "sass_job_frames": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_float))]),
+    "sass_job_selection": (C.c_int, [C.c_void_p, C.c_char_p, c_size_p, C.c_size_t, c_size_p]),
+    "sass_job_params": (C.c_void_p, [C.c_void_p]),
+    "sass_job_run": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(CommVtbl), C.POINTER(BackendVtbl), C.c_void_p, c_size_p,
+                               C.c_char_p, C.c_size_t]),
 }
 
 

@@ -1,0 +1,160 @@
+// control.hpp — control plane feeding the hot path from real Sassena inputs ("next" row):
+//   scatter.xml  -> Config        reference src/control/parameters.cpp:64-792 (sections sample, stager, scattering, limits, database)
+//   db.xml       -> Database      reference src/control/database.cpp:31-145 (parse), :293-528 (evaluation)
+//   PDB          -> Atoms         reference src/sample/atoms.cpp:64-86
+//   selections   -> index sets    reference src/sample/sample.cpp:30-101, atomselection_reader.cpp:33-118
+//   b_j(|q|)     -> ScatterFactors reference src/scatter_devices/scatter_factors.cpp:28-135
+// XML is read by a small built-in parser (no libxml2 in this image): elements, text, comments, CDATA, the five
+// predefined entities; XPath use is limited to what the reference needs ("//a/b/c", "./x", ".").  XInclude is not
+// supported and raises an error.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <regex>
+#include <string>
+#include <vector>
+
+#include "sassena_host.hpp"
+
+namespace sassena {
+
+// ---- XML --------------------------------------------------------------------------------------------------------
+struct XMLNode {
+    std::string name;
+    std::string text;  // concatenated character data directly inside this element
+    std::vector<XMLNode> children;
+};
+
+class XMLInterface {  // reference src/io/xml_interface.cpp
+    XMLNode root_;
+    const XMLNode *current_ = nullptr;
+
+   public:
+    explicit XMLInterface(const std::string &filename);
+    static XMLNode parse(const std::string &text);
+    std::vector<const XMLNode *> get(const std::string &xpath) const;
+    bool exists(const std::string &xpath) const { return !get(xpath).empty(); }
+    void set_current(const XMLNode *n) { current_ = n; }
+    std::string get_string(const std::string &xpath) const;
+    double get_double(const std::string &xpath) const;
+    size_t get_size(const std::string &xpath) const;
+    long get_long(const std::string &xpath) const;
+    bool get_bool(const std::string &xpath) const;  // true/false in any case, or 1/0 (xml_interface.cpp:56-61)
+};
+
+// ---- Config (scatter.xml) -----------------------------------------------------------------------------------------
+struct SampleSelectionParameters {
+    std::string type = "index";  // index | range | lexical | file
+    std::string name;
+    std::vector<size_t> ids;                // index
+    size_t from = 0, to = 0;                // range (inclusive)
+    std::string expression;                 // lexical / file
+    std::string filepath, format = "pdb", selector = "beta";  // file
+};
+
+struct SampleFramesetParameters {
+    std::string file = "sample.dcd", filepath, format = "dcd";
+    size_t first = 0, last = 0, stride = 1, clones = 1;
+    bool last_set = false;
+};
+
+struct ScatteringBackgroundKappaParameters {
+    std::string selection = "system";
+    double value = 1.0;
+};
+
+struct Config : Params {
+    std::string config_rootpath;
+    // sample
+    std::string structure_file = "sample.pdb", structure_filepath, structure_format = "pdb";
+    std::vector<SampleSelectionParameters> selections;
+    std::vector<SampleFramesetParameters> framesets;
+    // stager
+    std::string stager_target = "system";
+    // scattering
+    std::vector<CartesianCoor3D> qvectors;
+    std::vector<ScatteringVectorsScan> scans;
+    double background_factor = 0.0;
+    std::vector<ScatteringBackgroundKappaParameters> kappas;
+    std::string signal_file = "signal.h5", signal_filepath;
+    bool signal_fqt = true, signal_fq0 = true, signal_fq = true, signal_fq2 = true;
+    // database
+    std::string database_file = "db.xml", database_filepath, database_format = "xml";
+
+    std::string get_filepath(const std::string &fname) const;  // parameters.cpp:41-54
+    void read_xml(const std::string &filename);                // parameters.cpp:64-792
+};
+
+// ---- Database (db.xml) --------------------------------------------------------------------------------------------
+class Database {
+    std::map<std::string, std::string> label2regexp_;  // names/pdb
+    std::map<std::string, size_t> ids_;
+    std::map<size_t, std::string> rids_;
+    size_t next_id_ = 0;
+    std::map<size_t, double> masses_;
+    struct Fn {
+        std::vector<double> v;
+        size_t type = 0;
+    };
+    std::map<size_t, Fn> volumes_, exclusion_, sfactors_;
+    std::map<std::string, std::string> quick_;
+
+   public:
+    void read_xml(const std::string &filename);
+    std::string pdb_name(const std::string &testlabel);  // database.cpp:308-340: exactly one regex must match
+    size_t atom_id(const std::string &label);            // atomIDs.get (registers unknown labels)
+    std::string atom_label(size_t id) const;
+    double mass(size_t id) const;
+    double volume(size_t id) const;                                   // database.cpp:391-411
+    double exclusionfactor(size_t id, double effvolume, double q) const;  // :430-450
+    double sfactor(size_t id, double q) const;                        // :469-528
+};
+
+// ---- Sample ---------------------------------------------------------------------------------------------------------
+struct LoadedSample {
+    std::vector<size_t> atom_ids;  // database element ID per atom (Atoms::ids_)
+    std::map<std::string, std::vector<size_t>> selections;
+    size_t NF = 0;
+    std::vector<float> frames;  // [NF][NA_target][3], reduced to stager.target (CoordinateSets::load, coordinate_sets.cpp:353-357)
+    std::vector<size_t> target;  // atom indices of stager.target
+};
+
+// Atoms::add (atoms.cpp:64-86): "ATOM  " records, name = columns 13-16 trimmed -> database label -> ID
+std::vector<size_t> read_pdb_atoms(const std::string &filename, Database &db);
+// Sample::init (sample.cpp:30-101): selections + the reserved "system" selection
+void init_selections(const Config &cfg, Database &db, LoadedSample &s, const std::string &structure_path);
+// CoordinateSets: framesets (dcd / dcdlist with first/last/stride/clones) reduced to the target selection
+void load_frames(const Config &cfg, LoadedSample &s);
+
+// ScatterFactors (scatter_factors.cpp:28-135): b_j(|q|) = sf - background.factor * excl(ID, kappa*V, |q|)
+class ScatterFactors {
+    const Database &db_;
+    const LoadedSample &sample_;
+    std::vector<double> kappas_;
+    double background_;
+
+   public:
+    ScatterFactors(const Config &cfg, const Database &db, const LoadedSample &s);
+    void update(double ql, double *factors) const;       // one entry per atom of the target selection
+    double compute_background(double ql) const;          // scatter_factors.cpp:104-124
+};
+
+// .npy writer for the interim signal output (datasets named like the HDF5 layout, file_writer_service.cpp:44-171)
+void write_npy(const std::string &path, const double *data, const std::vector<size_t> &shape);
+
+// the `sassena` executable's flow (src/main/sassena.cpp:132-417) for one process / one communicator:
+// load(): config + database + sample;  run(): factory -> device.run() -> signal directory (.npy datasets).
+struct Job {
+    Config cfg;
+    Database db;
+    LoadedSample sample;
+    std::unique_ptr<ScatterFactors> factors;
+    void load(const std::string &config_file);
+    // returns the number of q-vectors this rank wrote; with more than one rank every writing rank stores its rows
+    // under <signal_dir>/rank_<r>/
+    size_t run(const std::string &signal_dir, std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx,
+               std::string *report);
+};
+
+}  // namespace sassena

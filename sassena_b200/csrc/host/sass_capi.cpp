@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 
+#include "control.hpp"
 #include "dcd.hpp"
 #include "sassena_host.hpp"
 
@@ -16,6 +17,11 @@ struct sass_dcd {
 
 struct sass_params {
     Params params;
+};
+
+struct sass_job {
+    sassena::Job job;
+    sass_params params;  // copy of the Params slice of job.cfg for sass_job_params
 };
 
 namespace {
@@ -316,3 +322,82 @@ int sass_dcd_write(const char *path, const float *xyz, size_t NF, size_t NA) {
 }
 
 }  // extern "C"
+
+// ---- control plane ----
+int sass_job_load(const char *config_file, sass_job **out) {
+    return guard([&] {
+        if (!config_file || !out) throw Error("sass_job_load: NULL argument");
+        std::unique_ptr<sass_job> j(new sass_job);
+        j->job.load(config_file);
+        j->params.params = static_cast<const Params &>(j->job.cfg);
+        *out = j.release();
+    });
+}
+
+void sass_job_free(sass_job *j) { delete j; }
+
+int sass_job_info(const sass_job *j, size_t *natoms, size_t *ntarget, size_t *nframes, size_t *nqvectors) {
+    return guard([&] {
+        if (!j) throw Error("sass_job_info: NULL job");
+        if (natoms) *natoms = j->job.sample.atom_ids.size();
+        if (ntarget) *ntarget = j->job.sample.target.size();
+        if (nframes) *nframes = j->job.sample.NF;
+        if (nqvectors) *nqvectors = j->job.cfg.qvectors.size();
+    });
+}
+
+int sass_job_qvectors(const sass_job *j, double *q_out) {
+    return guard([&] {
+        if (!j || !q_out) throw Error("sass_job_qvectors: NULL argument");
+        size_t i = 0;
+        for (auto &q : j->job.cfg.qvectors) {
+            q_out[i++] = q.x;
+            q_out[i++] = q.y;
+            q_out[i++] = q.z;
+        }
+    });
+}
+
+int sass_job_factors(const sass_job *j, double ql, double *b_out) {
+    return guard([&] {
+        if (!j || !b_out) throw Error("sass_job_factors: NULL argument");
+        j->job.factors->update(ql, b_out);
+    });
+}
+
+int sass_job_frames(const sass_job *j, const float **frames) {
+    return guard([&] {
+        if (!j || !frames) throw Error("sass_job_frames: NULL argument");
+        *frames = j->job.sample.frames.data();
+    });
+}
+
+int sass_job_selection(const sass_job *j, const char *name, size_t *ids, size_t cap, size_t *n) {
+    return guard([&] {
+        if (!j || !name || !n) throw Error("sass_job_selection: NULL argument");
+        auto it = j->job.sample.selections.find(name);
+        if (it == j->job.sample.selections.end()) throw Error(std::string("selection not found: ") + name);
+        *n = it->second.size();
+        for (size_t i = 0; i < it->second.size() && i < cap && ids; i++) ids[i] = it->second[i];
+    });
+}
+
+const sass_params *sass_job_params(const sass_job *j) { return j ? &j->params : nullptr; }
+
+int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
+                 sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap) {
+    return guard([&] {
+        if (!j || !signal_dir) throw Error("sass_job_run: NULL argument");
+        std::shared_ptr<ICommunicator> c;
+        if (comm) c = std::make_shared<CallbackCommunicator>(*comm, false);
+        else c = std::make_shared<SingleCommunicator>();
+        const SgpuBackend &be = backend ? *backend : default_backend();
+        std::string rep;
+        size_t n = j->job.run(signal_dir, c, be, ctx, &rep);
+        if (written) *written = n;
+        if (report && report_cap) {
+            strncpy(report, rep.c_str(), report_cap - 1);
+            report[report_cap - 1] = 0;
+        }
+    });
+}

@@ -23,6 +23,17 @@ def _ck(rc):
         raise HostError(_lib().sass_last_error().decode())
 
 
+def _ctxp(ctx):
+    """sgpu_ctx* from None, an int, a c_void_p or a ScatterContext."""
+    if ctx is None:
+        return None
+    if hasattr(ctx, "h"):
+        ctx = ctx.h
+    if isinstance(ctx, C.c_void_p):
+        return ctx
+    return C.c_void_p(int(ctx))
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -108,7 +119,7 @@ class Params:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and not getattr(self, "_borrowed", False):
                 _lib().sass_params_free(self.h)
                 self.h = None
         except Exception:
@@ -295,7 +306,7 @@ def run_scatter(params: Params, frames, qvectors, b=None, factors_fn=None, comm:
     timers = C.create_string_buffer(4096)
     rc = _lib().sass_scatter_run(params.h, C.byref(comm.vtbl) if comm is not None else None,
                                  C.byref(backend) if backend is not None else None,
-                                 C.c_void_p(ctx) if ctx else None, NA, NF, frames.ctypes.data, bptr, fcb, None,
+                                 _ctxp(ctx), NA, NF, frames.ctypes.data, bptr, fcb, None,
                                  _dp(q), len(q), wcb, None, C.byref(has), timers, len(timers))
     _ck(rc)
     tm = {}
@@ -305,3 +316,86 @@ def run_scatter(params: Params, frames, qvectors, b=None, factors_fn=None, comm:
             s, c = v.split(":")
             tm[k] = (float(s), int(c))
     return records, bool(has.value), tm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# control plane: scatter.xml -> signal directory (the `sassena` executable's flow, src/main/sassena.cpp:132-417)
+# ---------------------------------------------------------------------------------------------------------------
+class Job:
+    """scatter.xml + db.xml + PDB + DCD loaded by the native control plane (csrc/host/control.cpp)."""
+
+    def __init__(self, config_file):
+        h = C.c_void_p()
+        _ck(_lib().sass_job_load(str(config_file).encode(), C.byref(h)))
+        self.h = h
+        n = [C.c_size_t() for _ in range(4)]
+        _ck(_lib().sass_job_info(self.h, *[C.byref(x) for x in n]))
+        self.natoms, self.ntarget, self.nframes, self.nqvectors = [x.value for x in n]
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib().sass_job_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def qvectors(self):
+        q = np.empty((self.nqvectors, 3))
+        _ck(_lib().sass_job_qvectors(self.h, _dp(q)))
+        return q
+
+    def factors(self, ql):
+        b = np.empty(self.ntarget)
+        _ck(_lib().sass_job_factors(self.h, float(ql), _dp(b)))
+        return b
+
+    def frames(self):
+        p = C.POINTER(C.c_float)()
+        _ck(_lib().sass_job_frames(self.h, C.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(self.nframes, self.ntarget, 3)).copy()
+
+    def selection(self, name):
+        n = C.c_size_t()
+        _ck(_lib().sass_job_selection(self.h, name.encode(), None, 0, C.byref(n)))
+        ids = np.empty(n.value, dtype=np.uintp)
+        _ck(_lib().sass_job_selection(self.h, name.encode(), ids.ctypes.data_as(_host.c_size_p), n.value, C.byref(n)))
+        return ids.astype(np.int64)
+
+    def params(self):
+        """Borrowed Params view (valid while the job lives)."""
+        p = Params.__new__(Params)
+        p.h = C.c_void_p(_lib().sass_job_params(self.h))
+        p._borrowed = True
+        return p
+
+    def run(self, signal_dir, comm: TorchDistCommunicator | None = None, backend=None, ctx=None):
+        """Runs every q-vector and writes <signal_dir>/{qvectors,fqt,fq0,fq,fq2}.npy.  Returns (written, report)."""
+        n = C.c_size_t()
+        rep = C.create_string_buffer(1024)
+        _ck(_lib().sass_job_run(self.h, str(signal_dir).encode(), C.byref(comm.vtbl) if comm is not None else None,
+                                C.byref(backend) if backend is not None else None, _ctxp(ctx),
+                                C.byref(n), rep, len(rep)))
+        return n.value, rep.value.decode()
+
+
+def load_signal(signal_dir):
+    """Reads a signal directory back: dict of qvectors [N,3], fqt [N,NF] complex, fq0/fq/fq2 [N] complex.
+    Multi-rank runs store each writer's rows under rank_<r>/; they are concatenated in rank order (rows pair up
+    through qvectors, as in the reference's signal.h5)."""
+    import glob
+    import os
+    dirs = [str(signal_dir)]
+    if not os.path.exists(os.path.join(dirs[0], "qvectors.npy")):
+        dirs = sorted(glob.glob(os.path.join(dirs[0], "rank_*")), key=lambda d: int(d.rsplit("_", 1)[1]))
+        dirs = [d for d in dirs if os.path.exists(os.path.join(d, "qvectors.npy"))]
+    out = {}
+    for k in ("qvectors", "fqt", "fq0", "fq", "fq2"):
+        parts = [np.load(os.path.join(d, k + ".npy")) for d in dirs if os.path.exists(os.path.join(d, k + ".npy"))]
+        if parts:
+            a = np.concatenate(parts, axis=0)
+            out[k] = a if k == "qvectors" else a[..., 0] + 1j * a[..., 1]
+    return out

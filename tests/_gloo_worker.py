@@ -22,6 +22,16 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     be = OracleBackend()
     comm = host.TorchDistCommunicator(None, device_memory=False)
+    if case.startswith("job"):  # control plane: argv[3] = scatter.xml, argv[4] = signal directory
+        written, report = host.Job(sys.argv[3]).run(sys.argv[4], comm=comm, backend=be.vtbl)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (rank, written, report))
+        if rank == 0:
+            with open(out_path, "wb") as f:
+                pickle.dump(gathered, f)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     NA, NF = 23, 12
     xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3, offset=-10.0)
     b = synth.factors(NA)

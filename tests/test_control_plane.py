@@ -1,0 +1,340 @@
+"""Control plane ("next" row): scatter.xml + db.xml + PDB + DCD -> the hot path.
+
+CPU tests check the native parser/database/selection/frameset logic (csrc/host/control.cpp) against restatements of the
+reference's formulas written here (database.cpp:391-528, scatter_factors.cpp:56-78) and run the whole flow through the
+oracle-bound backend table; the GPU test runs the same job on the CUDA path and compares with the oracle."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from sassena_b200 import host, synth
+
+ELEMENTS = ["hydrogen", "carbon", "oxygen", "nitrogen"]
+# atom names cycle through these PDB names
+PDB_NAMES = ["H1", "CA", "OW", "N", "HB2", "C", "O", "CB"]
+NAME2EL = {"H1": "hydrogen", "HB2": "hydrogen", "CA": "carbon", "C": "carbon", "CB": "carbon", "OW": "oxygen",
+           "O": "oxygen", "N": "nitrogen"}
+
+DB_XML = """<?xml version="1.0"?>
+<!-- small test database, same schema as the reference's db.xml -->
+<database>
+  <names><pdb>
+    <element><name>hydrogen</name><param>^H.*</param></element>
+    <element><name>carbon</name><param>^C.*</param></element>
+    <element><name>oxygen</name><param>^O.*</param></element>
+    <element><name>nitrogen</name><param>^N.*</param></element>
+  </pdb></names>
+  <masses>
+    <element><name>hydrogen</name><param>1.008</param></element>
+    <element><name>carbon</name><param>12.011</param></element>
+    <element><name>oxygen</name><param>15.999</param></element>
+    <element><name>nitrogen</name><param>14.007</param></element>
+  </masses>
+  <sizes>
+    <element><name>hydrogen</name><type>1</type><param>1.07</param></element>
+    <element><name>carbon</name><type>1</type><param>1.58</param></element>
+    <element><name>oxygen</name><type>2</type><param>1.3</param></element>
+    <element><name>nitrogen</name><type>0</type><param>11.5</param></element>
+  </sizes>
+  <exclusionfactors>
+    <element><name>hydrogen</name><type>2</type><param>1.0</param></element>
+    <element><name>carbon</name><type>2</type><param>0.9</param></element>
+    <element><name>oxygen</name><type>1</type><param>1.1</param></element>
+    <element><name>nitrogen</name><type>0</type><param>3.0</param></element>
+  </exclusionfactors>
+  <scatterfactors>
+    <element><name>hydrogen</name><type>0</type><param>-3.7406</param></element>
+    <element><name>carbon</name><type>2</type>
+      <param>2.31</param><param>20.8439</param><param>1.02</param><param>10.2075</param>
+      <param>1.5886</param><param>0.5687</param><param>0.865</param><param>51.6512</param><param>0.2156</param></element>
+    <element><name>oxygen</name><type>1</type>
+      <param>7.6579</param><param>2.2458</param><param>2.2266</param><param>0</param><param>0</param>
+      <param>2</param><param>2</param><param>4</param><param>0</param><param>0</param>
+      <param>1</param><param>2</param><param>2</param><param>1</param><param>1</param></element>
+    <element><name>nitrogen</name><type>0</type><param>9.36</param></element>
+  </scatterfactors>
+</database>
+"""
+
+
+def pdb_line(i, name, beta=0.0, segid="PROT"):
+    # columns: 1-6 record, 13-16 name, 61-66 beta, 73-76 segid
+    nm = name if len(name) == 4 else " " + name.ljust(3)
+    return "ATOM  %5d %4s ALA A%4d    %8.3f%8.3f%8.3f%6.2f%6.2f      %-4s" % (i + 1, nm, 1, 0.0, 0.0, 0.0, 1.0, beta, segid)
+
+
+def make_case(tmp, NA=24, NF=20, scattering="", sample_extra="", stager="", framesets=None, background=""):
+    tmp = str(tmp)
+    names = [PDB_NAMES[i % len(PDB_NAMES)] for i in range(NA)]
+    with open(os.path.join(tmp, "sample.pdb"), "w") as f:
+        f.write("REMARK test structure\n")
+        for i, n in enumerate(names):
+            f.write(pdb_line(i, n, beta=1.0 if i % 3 == 0 else 0.0, segid="SOLV" if i >= NA // 2 else "PROT") + "\n")
+        f.write("END\n")
+    with open(os.path.join(tmp, "db.xml"), "w") as f:
+        f.write(DB_XML)
+    xyz = synth.trajectory(NF, NA, 15.0, 0.3, 11, offset=-7.5)
+    host.write_dcd(os.path.join(tmp, "traj.dcd"), xyz)
+    if framesets is None:
+        framesets = "<frameset><file>traj.dcd</file><format>dcd</format></frameset>"
+    cfg = f"""<?xml version="1.0" encoding="UTF-8"?>
+<root>
+  <!-- comment before the sample -->
+  <sample>
+    <structure><file>sample.pdb</file><format>pdb</format></structure>
+    <framesets>{framesets}</framesets>
+    {sample_extra}
+  </sample>
+  {stager}
+  <scattering>
+    {background}
+    {scattering}
+  </scattering>
+  <database><file>db.xml</file></database>
+</root>
+"""
+    path = os.path.join(tmp, "scatter.xml")
+    with open(path, "w") as f:
+        f.write(cfg)
+    return path, xyz, names
+
+
+# ---- python restatement of the database evaluation (float32 powf as in the reference) ----
+import ctypes as _C
+import ctypes.util as _Cu
+
+_libm = _C.CDLL(_Cu.find_library("m"))
+_libm.powf.restype = _C.c_float
+_libm.powf.argtypes = [_C.c_float, _C.c_float]
+
+
+def powf(a, b):  # the C library's float pow the reference calls (database.cpp:400-506)
+    return float(_libm.powf(a, b))
+
+
+def ref_volume(el):
+    if el == "hydrogen":
+        return (4.0 / 3.0) * math.pi * powf(1.07, 3)
+    if el == "carbon":
+        return (4.0 / 3.0) * math.pi * powf(1.58, 3)
+    if el == "oxygen":
+        # `using namespace std` + float argument: the reference's sqrt is the float overload and the product of the
+        # two floats is a float product (database.cpp:404)
+        return float(np.sqrt(np.float32(powf(math.pi, 3))) * np.float32(powf(1.3, 3)))
+    return 11.5
+
+
+def ref_excl(el, effv, q):
+    if el in ("hydrogen", "carbon"):
+        v0 = 1.0 if el == "hydrogen" else 0.9
+        return effv * math.exp(-1.0 * powf(effv, 2.0 / 3.0) * powf(q, 2) / (4 * math.pi)) * v0
+    if el == "oxygen":
+        return effv * 1.1
+    return 3.0
+
+
+def ref_sfactor(el, q):
+    if el == "hydrogen":
+        return -3.7406
+    if el == "nitrogen":
+        return 9.36
+    if el == "carbon":
+        v = [2.31, 20.8439, 1.02, 10.2075, 1.5886, 0.5687, 0.865, 51.6512, 0.2156]
+        return sum(v[2 * i] * math.exp(-v[2 * i + 1] * q * q) for i in range(4)) + v[8]
+    v = [7.6579, 2.2458, 2.2266, 0, 0, 2, 2, 4, 0, 0, 1, 2, 2, 1, 1]
+    den = 0.0
+    for j in range(5):
+        j2, j3 = 5 + j, 10 + j
+        if v[j] != 0.0:
+            c = powf(2.0 * v[j] / v[j3], v[j3] + 0.5)
+            c /= math.sqrt(math.factorial(int(2.0 * v[j3])))
+            den += v[j2] * powf(c * powf(q, v[j3] - 1.0) * math.exp(-1.0 * v[j] * q / v[j3]), 2)
+    return den / (4.0 * math.pi)
+
+
+SCAN = """<vectors><type>scans</type><scans>
+  <scan><from>0.4</from><to>1.6</to><points>3</points><base><x>1</x><y>0</y><z>0</z></base></scan>
+</scans></vectors>"""
+
+
+def test_config_selections_framesets_and_scans(tmp_path):
+    sel_pdb = tmp_path / "sel.pdb"
+    ndx = tmp_path / "groups.ndx"
+    sample_extra = """<selections>
+      <selection><type>index</type><name>picked</name><index>3</index><index>5</index><index>8</index></selection>
+      <selection><type>range</type><name>tail</name><from>20</from><to>23</to></selection>
+      <selection><type>lexical</type><name>carbons</name><expression>carbon</expression></selection>
+      <selection><type>file</type><name>flagged</name><file>sel.pdb</file><format>pdb</format></selection>
+      <selection><type>file</type><name>solvent</name><file>sel.pdb</file><format>pdb</format>
+                 <selector>segid</selector><expression>SOLV</expression></selection>
+      <selection><type>file</type><file>groups.ndx</file><format>ndx</format><expression>grp.*</expression></selection>
+      <selection><type>index</type><name>system</name><index>1</index></selection>
+    </selections>"""
+    framesets = """<first>2</first><stride>2</stride>
+      <frameset><file>traj.dcd</file><format>dcd</format><last>12</last></frameset>
+      <frameset><file>traj.dcd</file><format>dcd</format><first>0</first><stride>5</stride><clones>2</clones></frameset>"""
+    cfg, xyz, names = make_case(tmp_path, scattering=SCAN, sample_extra=sample_extra, framesets=framesets,
+                                stager="<stager><target>carbons</target></stager>")
+    # selection files live next to the config (get_filepath, parameters.cpp:41-54)
+    sel_pdb.write_text((tmp_path / "sample.pdb").read_text())
+    ndx.write_text("[ grpA ]\n1 2 3\n4\n[ other ]\n7 8\n[ grpB ]\n10 11\n")
+    job = host.Job(cfg)
+    NA = len(names)
+    assert job.natoms == NA
+    assert list(job.selection("picked")) == [3, 5, 8]
+    assert list(job.selection("tail")) == [20, 21, 22, 23]
+    carbons = [i for i, n in enumerate(names) if NAME2EL[n] == "carbon"]
+    assert list(job.selection("carbons")) == carbons
+    assert list(job.selection("flagged")) == [i for i in range(NA) if i % 3 == 0]
+    assert list(job.selection("solvent")) == list(range(NA // 2, NA))
+    assert list(job.selection("grpA")) == [0, 1, 2, 3] and list(job.selection("grpB")) == [9, 10]
+    with pytest.raises(host.HostError):
+        job.selection("other")
+    # the reserved name is moved aside and "system" is every atom (sample.cpp:88-101)
+    assert list(job.selection("system")) == list(range(NA))
+    assert list(job.selection("system_RENAMED_BY_SASSENA")) == [1]
+    # framesets: defaults first=2 stride=2 (absolute i % stride), frameset 1 last=12 -> 2,4,..,12; frameset 2 overrides
+    # first=0 stride=5 -> 0,5,10,15 twice (clones)
+    idx = [2, 4, 6, 8, 10, 12] + [0, 5, 10, 15] * 2
+    assert job.nframes == len(idx) and job.ntarget == len(carbons)
+    assert np.array_equal(job.frames(), xyz[idx][:, carbons])
+    # scans
+    q = host.create_from_scans([{"base": (1, 0, 0), "from": 0.4, "to": 1.6, "points": 3}])
+    assert job.nqvectors == 3 and np.array_equal(job.qvectors(), q)
+
+
+def test_scatter_factors_match_reference_formulas(tmp_path):
+    bg = """<background><factor>0.0334</factor><kappas>
+      <kappa><selection>solvent</selection><value>1.5</value></kappa></kappas></background>"""
+    extra = """<selections><selection><type>range</type><name>solvent</name><from>12</from><to>23</to></selection>
+      <selection><type>range</type><name>half</name><from>6</from><to>17</to></selection></selections>"""
+    cfg, xyz, names = make_case(tmp_path, scattering=SCAN, background=bg, sample_extra=extra,
+                                stager="<stager><target>half</target></stager>")
+    job = host.Job(cfg)
+    target = list(range(6, 18))
+    for ql in (0.0, 0.7, 2.3):
+        exp = []
+        for i in target:
+            el = NAME2EL[names[i]]
+            kappa = 1.5 if i >= 12 else 1.0
+            exp.append(ref_sfactor(el, ql) - 0.0334 * ref_excl(el, kappa * ref_volume(el), ql))
+        got = job.factors(ql)
+        assert np.allclose(got, exp, rtol=1e-14, atol=0), (ql, got, exp)
+    # no background: plain scattering lengths
+    cfg2, _, names = make_case(tmp_path, scattering=SCAN)
+    j2 = host.Job(cfg2)
+    assert np.allclose(j2.factors(1.1), [ref_sfactor(NAME2EL[n], 1.1) for n in names], rtol=1e-14)
+
+
+def test_config_errors(tmp_path):
+    cfg, _, _ = make_case(tmp_path, scattering=SCAN)
+    text = open(cfg).read()
+
+    def variant(repl, by):
+        p = str(tmp_path / "bad.xml")
+        assert repl in text
+        open(p, "w").write(text.replace(repl, by))
+        return p
+
+    with pytest.raises(host.HostError, match="cannot open"):
+        host.Job(str(tmp_path / "nope.xml"))
+    with pytest.raises(host.HostError, match="XML parse error"):
+        host.Job(variant("</root>", "</toor>"))
+    with pytest.raises(host.HostError, match="Selection type not understood"):
+        host.Job(variant("</framesets>", "</framesets><selections><selection><type>magic</type></selection></selections>"))
+    with pytest.raises(host.HostError, match="not supported"):
+        host.Job(variant("</framesets>", "</framesets><motions><motion><type>linear</type></motion></motions>"))
+    with pytest.raises(host.HostError, match="stager.target"):
+        host.Job(variant("<scattering>", "<stager><target>nobody</target></stager><scattering>"))
+    with pytest.raises(host.HostError, match="No q vectors"):
+        host.Job(variant("<points>3</points>", "<points>0</points>"))
+    with pytest.raises(host.HostError, match="not supported"):
+        host.Job(variant("<format>dcd</format>", "<format>xtc</format>"))
+    with pytest.raises(host.HostError, match="obsolete"):
+        host.Job(variant("<scattering>", "<scattering><target>system</target>"))
+    # unknown and ambiguous atom names (database.cpp:308-340)
+    pdb = str(tmp_path / "sample.pdb")
+    good = open(pdb).read()
+    open(pdb, "w").write(good.replace(" N  ", " XE ", 1))
+    with pytest.raises(host.HostError, match="not recognized"):
+        host.Job(cfg)
+    open(pdb, "w").write(good)
+    db = str(tmp_path / "db.xml")
+    open(db, "w").write(DB_XML.replace("^N.*", "^[NC].*"))
+    with pytest.raises(host.HostError, match="matches"):
+        host.Job(cfg)
+    # atom count mismatch between structure and trajectory
+    open(db, "w").write(DB_XML)
+    open(pdb, "w").write(good.replace("END\n", pdb_line(99, "CA") + "\nEND\n"))
+    with pytest.raises(host.HostError, match="Atom number mismatch"):
+        host.Job(cfg)
+
+
+ORIENT = """<average><orientation><type>vectors</type>
+  <vectors><type>sphere</type><algorithm>boost_uniform_on_sphere</algorithm><resolution>7</resolution><seed>5</seed></vectors>
+</orientation></average>"""
+
+
+def _expected(oracle, job, xyz_t, dsp="autocorrelate"):
+    p = job.params()
+    out = []
+    for q in job.qvectors():
+        b = job.factors(np.linalg.norm(q))
+        out.append(oracle.compute_all_vectors(xyz_t, b, p.init_subvectors(q), dsp=dsp))
+    return out
+
+
+def test_job_run_oracle_backend_writes_signal(tmp_path, oracle):
+    from oracle_backend import OracleBackend
+    extra = "<selections><selection><type>lexical</type><name>heavy</name><expression>carbon|oxygen|nitrogen</expression></selection></selections>"
+    bg = "<background><factor>0.02</factor></background>"
+    cfg, xyz, names = make_case(tmp_path, scattering=SCAN + ORIENT + "<signal><fq2>false</fq2></signal>", sample_extra=extra,
+                                background=bg, stager="<stager><target>heavy</target></stager>")
+    job = host.Job(cfg)
+    heavy = [i for i, n in enumerate(names) if NAME2EL[n] != "hydrogen"]
+    out = tmp_path / "signal"
+    be = OracleBackend()
+    written, report = job.run(out, backend=be.vtbl)
+    assert written == 3 and "target=%d" % len(heavy) in report
+    sig = host.load_signal(out)
+    assert "fq2" not in sig and sig["fqt"].shape == (3, xyz.shape[0])
+    assert np.array_equal(sig["qvectors"], job.qvectors())
+    exp = _expected(oracle, job, xyz[:, heavy])
+    for i, (fqt, fq, fq2) in enumerate(exp):
+        assert np.allclose(sig["fqt"][i], fqt, rtol=1e-12, atol=1e-12 * abs(fqt[0]))
+        assert np.isclose(sig["fq"][i], fq, rtol=1e-12) and sig["fq0"][i] == sig["fqt"][i][0]
+
+
+@pytest.mark.gpu
+def test_job_run_gpu_matches_oracle(tmp_path, oracle, gpu_ctx):
+    from util import TOL, rel_err
+    bg = "<background><factor>0.0334</factor></background>"
+    cfg, xyz, names = make_case(tmp_path, NA=200, NF=64, scattering=SCAN + ORIENT, background=bg)
+    job = host.Job(cfg)
+    out = tmp_path / "signal"
+    written, _ = job.run(out, ctx=gpu_ctx)
+    assert written == 3
+    sig = host.load_signal(out)
+    for i, (fqt, fq, fq2) in enumerate(_expected(oracle, job, xyz)):
+        assert rel_err(sig["fqt"][i], fqt) < TOL
+        assert abs(sig["fq"][i] - fq) <= TOL * abs(fq) and abs(sig["fq2"][i] - fq2) <= TOL * abs(fq2)
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end(tmp_path, oracle):
+    import subprocess
+    import sys
+    dsp = "<dsp><type>square</type></dsp>"
+    cfg, xyz, names = make_case(tmp_path, NA=64, NF=32, scattering=SCAN + ORIENT + dsp)
+    out = tmp_path / "sig"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "sassena_b200.cli", "--config", cfg, "--signal", str(out)], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    from util import TOL, rel_err
+    sig = host.load_signal(out)
+    job = host.Job(cfg)
+    for i, (fqt, fq, fq2) in enumerate(_expected(oracle, job, xyz, dsp="square")):
+        assert rel_err(sig["fqt"][i], fqt) < TOL

@@ -23,14 +23,14 @@ def _free_port():
     return p
 
 
-def _run(world, case, tmp_path):
+def _run(world, case, tmp_path, extra=()):
     out = str(tmp_path / f"{case}_{world}.pkl")
     port = _free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), out, case], env=env,
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), out, case, *extra], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     logs = []
     for p in procs:
@@ -83,3 +83,28 @@ def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
         assert np.max(np.abs(r["fqt"] - rfqt)) < 1e-11 * scale
         assert abs(r["fq"] - rfq) < 1e-11 * scale
         assert abs(r["fq2"] - rfq2) < 1e-11 * abs(rfq2)
+
+
+@pytest.mark.parametrize("manual", [False, True])
+def test_multirank_job_from_config(oracle, tmp_path, manual):
+    """scatter.xml -> Job.run on 2 ranks: one partition of 2 (rank 0 writes all |q|) and, with manual partitions of
+    size 1, two writers; load_signal merges the per-rank rows and they match the oracle."""
+    from test_control_plane import ORIENT, SCAN, make_case
+    limits = ""
+    if manual:
+        limits = ("<limits><decomposition><utilization>0</utilization><partitions><automatic>false</automatic>"
+                  "<size>1</size></partitions></decomposition></limits>")
+    cfg, xyz, names = make_case(tmp_path, scattering=SCAN + ORIENT, stager=limits)
+    sig_dir = tmp_path / "signal"
+    gathered = _run(2, "job", tmp_path, extra=(cfg, str(sig_dir)))
+    written = sorted(w for _, w, _ in gathered)
+    assert written == ([1, 2] if manual else [0, 3])
+    sig = host.load_signal(sig_dir)
+    job = host.Job(cfg)
+    qv = job.qvectors()
+    assert sorted(map(tuple, sig["qvectors"])) == sorted(map(tuple, qv))
+    p = job.params()
+    for i, q in enumerate(sig["qvectors"]):
+        fqt, fq, fq2 = oracle.compute_all_vectors(xyz, job.factors(np.linalg.norm(q)), p.init_subvectors(q))
+        assert np.allclose(sig["fqt"][i], fqt, rtol=1e-11, atol=1e-11 * abs(fqt[0]))
+        assert np.isclose(sig["fq"][i], fq, rtol=1e-11) and np.isclose(sig["fq2"][i], fq2, rtol=1e-11)
