@@ -8,9 +8,12 @@ F(q,t) wall time it implies.  Workload (default): BASELINE configs[2] "coherent 
 (abstract_scatter_device.cpp:162-173): one |q| with its 500 orientation vectors over the full trajectory,
 i.e. amplitudes -> FFT autocorrelation -> orientational average -> fqt/fq/fq2 for that |q| (5e11 evaluations).
 
-N GPUs: one process per GPU (torchrun), coordinates replicated, the 500 subvectors of the step sharded with
-DivAssignment, per-rank packed partials summed with ONE NCCL all-reduce per step, finalize on every rank
-("strong" scaling: total work per step is fixed).
+N GPUs: one process per GPU (torchrun).  The FRAMES are sharded with DivAssignment (the reference's own decomposition,
+all_vectors_scatter_device.cpp:61,248,408): every rank holds and evaluates only its block of the trajectory for all
+500 subvectors, the zero-padded amplitude buffers A[NM][NF] are summed over NVSwitch (one NCCL all-reduce, 80 MB),
+every rank correlates a DivAssignment block of the timelines, and the packed partials are summed with a second
+small all-reduce; finalize on every rank ("strong" scaling: total work per step is fixed).  `--shard vectors` selects
+the alternative with replicated coordinates and sharded subvectors.
 
 `--impl reference` times the CPU oracle (oracle/, the restatement of the reference's loops; the reference
 itself cannot be built in this image) on all host cores on a bounded sample of the same workload.
@@ -204,6 +207,8 @@ def _run_ours(args, json_fd):
     b = synth.factors(NA)
     u = synth.unit_vectors(NM, cfg["vseed"])
     m_off, m_cnt = div_assignment(world, rank, NM)
+    f_off, f_cnt = div_assignment(world, rank, NF)
+    by_frames = world > 1 and args.shard == "frames"
 
     ctx = sassena_b200.ScatterContext(local_rank)
     fp64_peak = ctx.measure_fp64_peak()
@@ -211,10 +216,37 @@ def _run_ours(args, json_fd):
     # synthetic trajectory generated on the device (CPU twin: sassena_b200/synth.py), resident in HBM
     xyz = torch.empty(NF * NA * 3, dtype=torch.float32, device=dev)
     ctx.synth_trajectory(xyz.data_ptr(), NF, NA, cfg["box"], cfg["sigma"], cfg["seed"])
-    ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
-    ctx.set_factors(b)
+    amp = None
+
+    def stage_resident():
+        if by_frames:  # this rank's block of the timeline
+            ctx.stage_frames_device(xyz.data_ptr() + f_off * NA * 12, f_cnt, NA)
+            ctx.set_frame_window(NF, f_off)
+        else:
+            ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
+        ctx.set_factors(b)
+
+    stage_resident()
+    if by_frames:
+        amp = torch.zeros(NM * NF * 2, dtype=torch.float64, device=dev)
     plen = ctx.partial_len("autocorrelate")
     partial = torch.zeros(plen, dtype=torch.float64, device=dev)
+
+    def compute_sharded(q_all):
+        """one |q| on `world` GPUs; coordinates already staged"""
+        if by_frames:
+            ctx.all_vectors_amplitudes(q_all, amp.data_ptr())
+            ctx.synchronize()
+            dist.all_reduce(amp)  # exchange: every rank ends up with the complete timelines
+            torch.cuda.synchronize()
+            ctx.all_vectors_dsp_partial(amp.data_ptr(), m_off, m_cnt, partial.data_ptr())
+        else:
+            ctx.compute_all_vectors_partial(q_all[m_off:m_off + m_cnt], partial.data_ptr())
+        if world > 1:
+            ctx.synchronize()
+            dist.all_reduce(partial)
+            torch.cuda.synchronize()
+        return ctx.finalize(partial.data_ptr(), 1.0 / NM)
 
     def barrier():
         if world > 1:
@@ -223,13 +255,7 @@ def _run_ours(args, json_fd):
         ctx.synchronize()
 
     def step(i):
-        q = qls[i % len(qls)] * u[m_off:m_off + m_cnt]
-        ctx.compute_all_vectors_partial(q, partial.data_ptr())
-        if world > 1:
-            ctx.synchronize()
-            dist.all_reduce(partial)
-            torch.cuda.synchronize()
-        return ctx.finalize(partial.data_ptr(), 1.0 / NM)
+        return compute_sharded(qls[i % len(qls)] * u)
 
     # ---- device-resident measurement ----
     for i in range(args.warmup):
@@ -268,22 +294,23 @@ def _run_ours(args, json_fd):
     # ---- end to end: host buffers in, host results out, every step ----
     e2e = None
     if not args.no_e2e:
-        f_off, f_cnt = div_assignment(world, rank, NF)
-        host = ctx.pinned((f_cnt, NA, 3), np.float32)  # this rank's slice of the trajectory, pinned
+        host = ctx.pinned((f_cnt, NA, 3), np.float32)  # this rank's block of the trajectory, pinned
         ctx.memcpy_d2h(host.array, xyz.data_ptr() + f_off * NA * 12)
-        slice_dev = torch.empty(f_cnt * NA * 3, dtype=torch.float32, device=dev) if world > 1 else None
+        slice_dev = torch.empty(f_cnt * NA * 3, dtype=torch.float32, device=dev) if (world > 1 and not by_frames) else None
         equal = all(div_assignment(world, r, NF)[1] == f_cnt for r in range(world))
 
         def e2e_step(i):
-            q = qls[i % len(qls)] * u[m_off:m_off + m_cnt]
-            if world == 1:
-                # stager: chunked async H2D on the copy stream; the amplitude launches wait per chunk
+            q_all = qls[i % len(qls)] * u
+            if world == 1 or by_frames:
+                # stager: chunked async H2D of this rank's frames on the copy stream; the amplitude launches wait per
+                # chunk, so the copy overlaps the kernel
                 ctx.stage_frames(host.array)
+                if by_frames:
+                    ctx.set_frame_window(NF, f_off)
                 ctx.set_factors(b)
-                ctx.compute_all_vectors_partial(q, partial.data_ptr())
             else:
-                # DataStagerByFrame: every rank loads its DivAssignment slice from the host, the slices are
-                # replicated over NVLink (the reference's stage_fillpartitions broadcast, data_stager.cpp:102-118)
+                # replicated coordinates: every rank loads its DivAssignment slice from the host, the slices are
+                # all-gathered over NVLink (the reference's stage_fillpartitions broadcast, data_stager.cpp:102-118)
                 ctx.memcpy_h2d(slice_dev.data_ptr(), host.array)
                 if equal:
                     dist.all_gather_into_tensor(xyz, slice_dev)
@@ -294,11 +321,7 @@ def _run_ours(args, json_fd):
                 torch.cuda.synchronize()
                 ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
                 ctx.set_factors(b)
-                ctx.compute_all_vectors_partial(q, partial.data_ptr())
-                ctx.synchronize()
-                dist.all_reduce(partial)
-                torch.cuda.synchronize()
-            return ctx.finalize(partial.data_ptr(), 1.0 / NM)
+            return compute_sharded(q_all)
 
         for i in range(min(args.warmup, 2)):
             e2e_step(i)
@@ -313,15 +336,16 @@ def _run_ours(args, json_fd):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
         e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
-               "h2d_bytes_per_step": int(f_cnt * NA * 12 + NA * 8 + m_cnt * 24),
+               "h2d_bytes_per_step": int(f_cnt * NA * 12 + NA * 8 + (NM if by_frames else m_cnt) * 24),
                "d2h_bytes_per_step": int(NF * 16 + 32),
                "ms_per_step": 1e3 * e2e_s / args.steps,
                "note": ("coordinates re-staged from pinned host memory every step (chunked async H2D overlapped "
                         "with the amplitude kernel)" if world == 1 else
+                        "every rank re-stages its own frame block from pinned host memory every step (chunked async H2D "
+                        "overlapped with the amplitude kernel); amplitudes exchanged over NVLink" if by_frames else
                         "every rank H2D's its frame slice each step, slices all-gathered over NVLink, then compute")}
         # restore the resident staging for anything that follows
-        ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
-        ctx.set_factors(b)
+        stage_resident()
         host.free()
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N=1) ----
@@ -349,7 +373,10 @@ def _run_ours(args, json_fd):
 
     if rank == 0:
         amp_s = amp_ms_max * 1e-3
-        evals_rank = float(NA) * NF * div_assignment(world, 0, NM)[1] * args.steps
+        if by_frames:
+            evals_rank = float(NA) * div_assignment(world, 0, NF)[1] * NM * args.steps
+        else:
+            evals_rank = float(NA) * NF * div_assignment(world, 0, NM)[1] * args.steps
         achieved = evals_rank * FLOP_PER_EVAL / amp_s / 1e12
         traffic = None
         prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -364,7 +391,8 @@ def _run_ours(args, json_fd):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NF": NF, "NM_per_q": NM, "NQ": len(qls),
                        "step": "one |q| (compute() of the runner loop): amplitudes + FFT autocorrelation + average",
-                       "parallelism": f"q-vector shard x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"frame shard x{world} + amplitude all-reduce" if by_frames else
+                                       f"q-vector shard x{world}" if world > 1 else "single GPU"),
                        "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
             "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -400,6 +428,8 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override NF (debug; changes the workload)")
     ap.add_argument("--atoms", type=int, default=0, help="override NA (debug; changes the workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle sample, seconds per core")
+    ap.add_argument("--shard", default="frames", choices=["frames", "vectors"],
+                    help="N>1: shard the frames (reference decomposition, default) or the subvectors (replicated coordinates)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -140,6 +140,22 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
                                       double *d_partial);
 int sgpu_compute_mpsphere_partial(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM_local, int dsp_type,
                                   double *d_partial);
+/* ---- frame-sharded coherent path (multi-GPU) ----------------------------------------------------------------------
+ * The reference's AllVectorsScatterDevice gives every rank of a partition a block of FRAMES
+ * (DivAssignment(NNPP, rank, NF), src/scatter_devices/all_vectors_scatter_device.cpp:61,248,408), computes the amplitudes
+ * of those frames (scatterblock()/scatter(), :363-430) and exchanges them with boost::mpi::all_to_all so that whole
+ * timelines can be correlated (exchange(), :170-205; dsp, :293-322).  On the GPU: each rank stages its frame block, declares where the block
+ * sits in the timeline, fills its columns of A[NM][NF_total] (all other columns zero), the ranks sum the buffers
+ * (one NCCL all-reduce over NVSwitch), and each rank correlates a block of the NM timelines into a packed partial
+ * (summed and finalized like the other *_partial results). */
+/* after sgpu_stage_frames*(NF_local frames): they are frames [f_first, f_first+NF_local) of NF_total.  sgpu_partial_len,
+ * sgpu_finalize and the two calls below then work on NF_total-frame timelines. */
+int sgpu_set_frame_window(sgpu_ctx *ctx, size_t NF_total, size_t f_first);
+/* d_amp: device, complex [NM][NF_total]; this rank's columns are written, the others zeroed */
+int sgpu_all_vectors_amplitudes(sgpu_ctx *ctx, const double *qvecs, size_t NM, double *d_amp);
+/* DSP of timelines [m_first, m_first+m_count) of d_amp into a packed partial (m_count == 0 zeroes it) */
+int sgpu_all_vectors_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t m_first, size_t m_count, int dsp_type,
+                                 double *d_partial);
 /* scale = 1/NM_total (vectors) or 1/(4 pi) (multipole sphere). */
 int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_method, double scale,
                   double *atfinal, double afinal[2], double a2final[2]);

@@ -53,6 +53,10 @@ typedef struct sass_backend_vtbl {
     int (*set_factors_batch)(sgpu_ctx *, const double *, size_t, size_t);
     int (*mpsphere_amplitudes)(sgpu_ctx *, const double *, size_t, const long *, size_t, size_t, size_t, double *);
     int (*mpsphere_dsp_partial)(sgpu_ctx *, const double *, size_t, size_t, int, double *);
+    /* frame-sharded coherent path */
+    int (*set_frame_window)(sgpu_ctx *, size_t, size_t);
+    int (*all_vectors_amplitudes)(sgpu_ctx *, const double *, size_t, double *);
+    int (*all_vectors_dsp_partial)(sgpu_ctx *, const double *, size_t, size_t, int, double *);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);
@@ -64,7 +68,8 @@ void sass_params_free(sass_params *p);
 /* keys: scattering.type, scattering.dsp.type, scattering.dsp.method, scattering.average.orientation.type,
  * scattering.average.orientation.axis.{x,y,z}, scattering.average.orientation.vectors.{type,algorithm,resolution,seed},
  * scattering.average.orientation.multipole.type, scattering.average.orientation.multipole.moments.{type,resolution},
- * limits.stage.memory.data, limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size} */
+ * limits.stage.memory.data, limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size},
+ * limits.decomposition.coherent (auto | frames | vectors: how a partition's ranks share one coherent |q|) */
 int sass_params_set(sass_params *p, const char *key, const char *value);
 /* vectors.type=file rows / multipole.moments.type=file rows */
 int sass_params_set_vectors(sass_params *p, const double *xyz, size_t n);

@@ -36,6 +36,9 @@ BE_FINALIZE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c
 BE_SET_FACTORS_BATCH = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_size_t)
 BE_MP_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_long_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p)
 BE_MP_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p)
+BE_SET_WINDOW = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_size_t)
+BE_AV_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_void_p)
+BE_AV_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -48,7 +51,8 @@ class BackendVtbl(C.Structure):
                 ("compute_self_vectors_partial", BE_COMPUTE_VEC), ("compute_mpsphere_partial", BE_COMPUTE_MP),
                 ("finalize", BE_FINALIZE), ("device_alloc", BE_ALLOC), ("device_free", BE_FREE),
                 ("set_factors_batch", BE_SET_FACTORS_BATCH), ("mpsphere_amplitudes", BE_MP_AMPL),
-                ("mpsphere_dsp_partial", BE_MP_DSP)]
+                ("mpsphere_dsp_partial", BE_MP_DSP), ("set_frame_window", BE_SET_WINDOW),
+                ("all_vectors_amplitudes", BE_AV_AMPL), ("all_vectors_dsp_partial", BE_AV_DSP)]
 
 
 FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)

@@ -75,6 +75,7 @@ class ScatterContext:
         self.h = h
         self.device = device
         self.NF = self.NA = 0
+        self._NFt = 0
         self._keep = None  # host array kept alive during async staging
 
     # -- lifecycle
@@ -122,10 +123,12 @@ class ScatterContext:
         self._keep = a
         self._ck(self.lib.sgpu_stage_frames(self.h, a.ctypes.data, a.shape[0], a.shape[1], int(repr)))
         self.NF, self.NA = a.shape[0], a.shape[1]
+        self._NFt = 0
 
     def stage_frames_device(self, d_ptr: int, NF: int, NA: int, repr=REPR_CARTESIAN):
         self._ck(self.lib.sgpu_stage_frames_device(self.h, C.c_void_p(d_ptr), NF, NA, int(repr)))
         self.NF, self.NA = NF, NA
+        self._NFt = 0
 
     def frames_to_spherical(self):
         self._ck(self.lib.sgpu_frames_to_spherical(self.h))
@@ -139,16 +142,19 @@ class ScatterContext:
         self._ck(self.lib.sgpu_stage_atoms(self.h, a.ctypes.data, a.shape[0], a.shape[1]))
         self.synchronize()
         self.NA, self.NF = a.shape[0], a.shape[1]
+        self._NFt = 0
 
     def stage_atoms_device(self, d_ptr: int, NA_local: int, NF: int):
         self._ck(self.lib.sgpu_stage_atoms_device(self.h, C.c_void_p(d_ptr), NA_local, NF))
         self.NA, self.NF = NA_local, NF
+        self._NFt = 0
 
     def stage_atoms_from_frames(self, xyz, nranks=1, rank=0):
         a = np.ascontiguousarray(xyz, dtype=np.float32)
         self._ck(self.lib.sgpu_stage_atoms_from_frames(self.h, a.ctypes.data, a.shape[0], a.shape[1], nranks, rank))
         NA = a.shape[1]
         self.NF = a.shape[0]
+        self._NFt = 0
         self.NA = NA // nranks + (1 if rank < NA % nranks else 0)
 
     def set_factors(self, b):
@@ -157,7 +163,12 @@ class ScatterContext:
 
     # -- compute
     def _outputs(self):
-        return np.zeros(2 * self.NF), np.zeros(2), np.zeros(2)
+        return np.zeros(2 * self.timeline_frames), np.zeros(2), np.zeros(2)
+
+    @property
+    def timeline_frames(self):
+        """frames of the timelines the DSP works on: the window's NF_total if one is set, else the staged NF"""
+        return self._NFt if self._NFt else self.NF
 
     @staticmethod
     def _pack(at, af, a2f):
@@ -208,6 +219,20 @@ class ScatterContext:
         self._ck(self.lib.sgpu_mpsphere_dsp_partial(self.h, C.c_void_p(d_amp), NQ, NM, _dsp(dsp), C.c_void_p(d_partials)))
 
     # -- multi-GPU split
+    # -- frame-sharded coherent path: stage a block of frames, place it in the timeline, exchange amplitudes
+    def set_frame_window(self, NF_total: int, f_first: int):
+        self._ck(self.lib.sgpu_set_frame_window(self.h, int(NF_total), int(f_first)))
+        self._NFt = int(NF_total)
+
+    def all_vectors_amplitudes(self, qvecs, d_amp: int):
+        """d_amp: device complex [NM][NF_total]; this rank's frame columns are written, all others zeroed"""
+        q = np.ascontiguousarray(qvecs, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.sgpu_all_vectors_amplitudes(self.h, _dp(q), len(q), C.c_void_p(d_amp)))
+
+    def all_vectors_dsp_partial(self, d_amp: int, m_first: int, m_count: int, d_partial: int, dsp="autocorrelate"):
+        self._ck(self.lib.sgpu_all_vectors_dsp_partial(self.h, C.c_void_p(d_amp), int(m_first), int(m_count), _dsp(dsp),
+                                                       C.c_void_p(d_partial)))
+
     def partial_len(self, dsp="autocorrelate") -> int:
         n = C.c_size_t()
         self._ck(self.lib.sgpu_partial_len(self.h, _dsp(dsp), C.byref(n)))

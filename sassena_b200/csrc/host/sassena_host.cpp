@@ -322,7 +322,10 @@ const SgpuBackend &default_backend() {
                                    sgpu_device_free,
                                    sgpu_set_factors_batch,
                                    sgpu_mpsphere_amplitudes,
-                                   sgpu_mpsphere_dsp_partial};
+                                   sgpu_mpsphere_dsp_partial,
+                                   sgpu_set_frame_window,
+                                   sgpu_all_vectors_amplitudes,
+                                   sgpu_all_vectors_dsp_partial};
     return be;
 }
 
@@ -356,15 +359,33 @@ std::vector<std::string> Timer::keys() const {
 // ---------------------------------------------------------------------------------------------------------------
 DataStagerByFrame::DataStagerByFrame(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
                                      const SgpuBackend &be, sgpu_ctx *ctx, const Params &params)
-    : m_sample(sample), allcomm_(allcomm), partitioncomm_(partitioncomm), timer_(timer), be_(be), ctx_(ctx), params_(params) {
-    // data_stager.cpp:57-63: every GPU holds all frames here (no frame decomposition inside a partition)
+    : m_sample(sample), allcomm_(allcomm), partitioncomm_(partitioncomm), timer_(timer), be_(be), ctx_(ctx), params_(params) {}
+
+void DataStagerByFrame::stage_block() {
+    DivAssignment mine(partitioncomm_.size(), partitioncomm_.rank(), m_sample.NF);
+    size_t data_bytesize = mine.max() * m_sample.NA * 3 * sizeof(float);  // data_stager.cpp:57-63
+    if (params_.limits.stage_memory_data < data_bytesize)
+        throw Error("Insufficient Buffer size for coordinates (limits.memory.data) Requested (bytes): " +
+                    std::to_string(data_bytesize));
+    if (mine.size() == 0) throw Error("frame decomposition left a rank without frames");
+    timer_.start("st:first");
+    int rc = be_.stage_frames(ctx_, m_sample.frames + mine.offset() * m_sample.NA * 3, mine.size(), m_sample.NA,
+                              SGPU_REPR_CARTESIAN);
+    if (rc) throw Error(std::string("stage_frames: ") + be_.last_error(ctx_));
+    rc = be_.set_frame_window(ctx_, m_sample.NF, mine.offset());
+    if (rc) throw Error(std::string("set_frame_window: ") + be_.last_error(ctx_));
+    timer_.stop("st:first");
+    timer_.start("st:wait");
+    allcomm_.barrier();
+    timer_.stop("st:wait");
+}
+
+void DataStagerByFrame::stage(int repr) {
+    // every GPU of the partition holds all frames
     size_t data_bytesize = m_sample.NF * m_sample.NA * 3 * sizeof(float);
     if (params_.limits.stage_memory_data < data_bytesize)
         throw Error("Insufficient Buffer size for coordinates (limits.memory.data) Requested (bytes): " +
                     std::to_string(data_bytesize));
-}
-
-void DataStagerByFrame::stage(int repr) {
     timer_.start("st:first");
     int rc = be_.stage_frames(ctx_, m_sample.frames, m_sample.NF, m_sample.NA, SGPU_REPR_CARTESIAN);
     if (rc) throw Error(std::string("stage_frames: ") + be_.last_error(ctx_));
@@ -577,10 +598,62 @@ void AbstractVectorsScatterDevice::init_subvectors(CartesianCoor3D &q) {
 // ---------------------------------------------------------------------------------------------------------------
 // AllVectorsScatterDevice (all_vectors_scatter_device.cpp)
 // ---------------------------------------------------------------------------------------------------------------
+AllVectorsScatterDevice::~AllVectorsScatterDevice() {
+    if (d_amp_) be_.device_free(d_amp_);
+}
+
 void AllVectorsScatterDevice::stage_data() {
     DataStagerByFrame data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
-    data_stager.stage(SGPU_REPR_CARTESIAN);
+    const size_t NNPP = partitioncomm_->size();
+    const std::string &mode = params_.limits.coherent_sharding;
+    if (mode != "auto" && mode != "frames" && mode != "vectors")
+        throw Error("limits.decomposition.coherent not understood: " + mode + " (auto, frames, vectors)");
+    // frames: per |q| the ranks exchange A[NM][NF] (16 B per entry) against NA*NF*NM/NNPP evaluations each, so the
+    // exchange is amortised once the sample has some hundred atoms per rank; below that keep the frames replicated
+    frame_sharded_ = NNPP > 1 && NF >= NNPP && (mode == "frames" || (mode == "auto" && NA >= 64 * NNPP));
+    if (frame_sharded_) data_stager.stage_block();
+    else data_stager.stage(SGPU_REPR_CARTESIAN);
     factors_.assign(NA, 0.0);
+}
+
+// Frame decomposition (the reference's own, all_vectors_scatter_device.cpp:245-361): amplitudes of this rank's frames
+// for ALL subvectors, exchange (there: all_to_all per block of NNPP subvectors, :170-205; here: one sum of the
+// zero-padded A over NVSwitch), then every rank correlates DivAssignment(NNPP, rank, NM) of the timelines.
+void AllVectorsScatterDevice::compute_frame_sharded() {
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    std::vector<double> qv(3 * NM);
+    for (size_t i = 0; i < NM; i++) {
+        const CartesianCoor3D &s = subvector_index_[i];
+        qv[3 * i] = s.x;
+        qv[3 * i + 1] = s.y;
+        qv[3 * i + 2] = s.z;
+    }
+    const size_t amp_len = 2 * NM * NF;
+    if (amp_len > amp_cap_) {
+        if (d_amp_) be_.device_free(d_amp_);
+        d_amp_ = nullptr;
+        void *pp = nullptr;
+        if (be_.device_alloc(&pp, amp_len * sizeof(double))) throw Error("device allocation of the amplitude buffer failed");
+        d_amp_ = static_cast<double *>(pp);
+        amp_cap_ = amp_len;
+    }
+    timer_.start("sd:c:block");
+    ck(be_.all_vectors_amplitudes(ctx_, qv.data(), NM, d_amp_), "sgpu_all_vectors_amplitudes");
+    timer_.stop("sd:c:block");
+    timer_.start("sd:c:wait");
+    ck(be_.synchronize(ctx_), "sgpu_synchronize");
+    timer_.stop("sd:c:wait");
+    timer_.start("sd:c:b:exchange");
+    partitioncomm_->allreduce_sum(d_amp_, amp_len);
+    timer_.stop("sd:c:b:exchange");
+    DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NM);
+    double *partial = partial_buffer(dsp);
+    timer_.start("sd:c:b:dspstore");
+    ck(be_.all_vectors_dsp_partial(ctx_, d_amp_, mine.offset(), mine.size(), dsp, partial), "sgpu_all_vectors_dsp_partial");
+    timer_.stop("sd:c:b:dspstore");
+    current_subvector_ = NM;
+    reduce_and_finalize(dsp, 1.0 / subvector_index_.size());
 }
 
 void AllVectorsScatterDevice::compute() {
@@ -591,11 +664,15 @@ void AllVectorsScatterDevice::compute() {
     ck(be_.set_factors(ctx_, factors_.data(), NA), "sgpu_set_factors");
     timer_.stop("sd:c:init");
 
+    current_subvector_ = 0;
+    if (frame_sharded_) {
+        compute_frame_sharded();
+        return;
+    }
     const int dsp = dsp_type_code();
     dsp_method_code();
-    current_subvector_ = 0;
     // q-vector decomposition inside the partition: rank r takes DivAssignment(NNPP, r, NM) of the subvectors
-    // (replaces the reference's frame decomposition + all_to_all, :291-315; every GPU holds all frames)
+    // (every GPU holds all frames; no amplitude exchange, only the packed partial is summed)
     DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NM);
     std::vector<double> qv(3 * std::max<size_t>(mine.size(), 1));
     for (size_t i = 0; i < mine.size(); i++) {

@@ -173,6 +173,11 @@ struct LimitsParameters {
     // limits.stage.memory.data re-targeted: bytes of coordinates one GPU may hold (default 150 GB of the 180 GB HBM3e)
     size_t stage_memory_data = (size_t)150 << 30;
     DecompositionLimits decomposition;
+    // how the ranks of one partition share a coherent |q|: "frames" = each rank holds a block of frames (the
+    // reference's decomposition, all_vectors_scatter_device.cpp:61,248,408), "vectors" = every rank holds all frames
+    // and takes a block of the orientation vectors, "auto" = frames unless the sample is too small to amortise the
+    // amplitude exchange
+    std::string coherent_sharding = "auto";
 };
 
 struct Params {
@@ -268,6 +273,8 @@ class DataStagerByFrame {  // data_stager.cpp:39-129
     DataStagerByFrame(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
                       const SgpuBackend &be, sgpu_ctx *ctx, const Params &params);
     void stage(int repr);  // coordinates end up resident on this rank's GPU, frame-major
+    // frame decomposition inside the partition (data_stager.cpp:57-118): this rank stages DivAssignment(NNPP, rank, NF)
+    void stage_block();
 };
 
 class DataStagerByAtom {  // data_stager.cpp:176-349
@@ -363,11 +370,17 @@ class AbstractVectorsScatterDevice : public AbstractScatterDevice {
 
 class AllVectorsScatterDevice : public AbstractVectorsScatterDevice {
    protected:
+    bool frame_sharded_ = false;
+    double *d_amp_ = nullptr;  // complex A[NM][NF] of the frame-sharded path (device)
+    size_t amp_cap_ = 0;
     void stage_data() override;
     void compute() override;
+    void compute_frame_sharded();
 
    public:
     using AbstractVectorsScatterDevice::AbstractVectorsScatterDevice;
+    ~AllVectorsScatterDevice() override;
+    bool frame_sharded() const { return frame_sharded_; }
 };
 
 class SelfVectorsScatterDevice : public AbstractVectorsScatterDevice {

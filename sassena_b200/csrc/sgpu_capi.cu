@@ -35,6 +35,9 @@ struct sgpu_ctx {
     bool own_xyz = false;
     size_t xyz_cap = 0;  // bytes owned
     size_t NF = 0, NA = 0;
+    // frame window (sgpu_set_frame_window): the staged frames are [f_first, f_first + NF) of a timeline of NFt frames;
+    // NFt == NF unless a window is set.  Amplitude kernels run over NF frames, the DSP over NFt.
+    size_t NFt = 0, f_first = 0;
     int repr = SGPU_REPR_CARTESIAN;
     struct Chunk {
         size_t f0, nf;
@@ -73,6 +76,8 @@ struct sgpu_ctx {
     SelfPlan splan;  // fused self path (atoms mode, dsp=autocorrelate)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+    cudaEvent_t evd0 = nullptr, evd1 = nullptr;  // DSP of the frame-sharded path (separate call)
+    bool dsp_split = false;
     bool have_times = false;
 
     ~sgpu_ctx() {
@@ -100,6 +105,8 @@ struct sgpu_ctx {
         if (ev2) cudaEventDestroy(ev2);
         if (tm0) cudaEventDestroy(tm0);
         if (tm1) cudaEventDestroy(tm1);
+        if (evd0) cudaEventDestroy(evd0);
+        if (evd1) cudaEventDestroy(evd1);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
@@ -204,10 +211,10 @@ int ensure_plan(sgpu_ctx *ctx) {
         int rc = ensure_self_plan(ctx);
         if (rc) return rc;
     }
-    if (ctx->plan.NF == ctx->NF && ctx->plan.d_tw) return SGPU_OK;
+    if (ctx->plan.NF == ctx->NFt && ctx->plan.d_tw) return SGPU_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     corr_plan_destroy(&ctx->plan);
-    int rc = corr_plan_create(&ctx->plan, ctx->NF, ctx->stream, &ctx->launches);
+    int rc = corr_plan_create(&ctx->plan, ctx->NFt, ctx->stream, &ctx->launches);
     if (rc == 1) return fail(ctx, SGPU_EINVAL, "number of frames not supported by the correlation plan (1 <= NF <= 2^21)");
     if (rc) return fail(ctx, SGPU_ECUDA, std::string("corr_plan_create: ") + cudaGetErrorString(cudaGetLastError()));
     return SGPU_OK;
@@ -228,7 +235,7 @@ bool uses_self_plan(const sgpu_ctx *ctx, int dsp_type) { return ctx->mode == 2 &
 
 size_t partial_len(const sgpu_ctx *ctx, int dsp_type) {
     if (uses_self_plan(ctx, dsp_type)) return ctx->splan.L + 4;
-    return (dsp_type == SGPU_DSP_AUTOCORRELATE ? ctx->plan.L : 2 * ctx->NF) + 4;
+    return (dsp_type == SGPU_DSP_AUTOCORRELATE ? ctx->plan.L : 2 * ctx->NFt) + 4;
 }
 
 int check_dsp(sgpu_ctx *ctx, int dsp_type, int dsp_method) {
@@ -254,11 +261,11 @@ int upload_q(sgpu_ctx *ctx, const double *qvecs, size_t NM, size_t pad) {
 int dsp_accumulate(sgpu_ctx *ctx, size_t nt, int dsp_type, double *d_partial, const double2 *d_A = nullptr) {
     if (!d_A) d_A = ctx->d_A;
     if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
-        ctx->launches += corr_power_accumulate(&ctx->plan, d_A, ctx->NF, nt, ctx->d_work, d_partial,
+        ctx->launches += corr_power_accumulate(&ctx->plan, d_A, ctx->NFt, nt, ctx->d_work, d_partial,
                                                d_partial + ctx->plan.L, ctx->stream);
     } else {
-        ctx->launches += dsp_elementwise_accumulate(d_A, ctx->NF, nt, ctx->NF, dsp_type == SGPU_DSP_SQUARE,
-                                                    reinterpret_cast<double2 *>(d_partial), d_partial + 2 * ctx->NF,
+        ctx->launches += dsp_elementwise_accumulate(d_A, ctx->NFt, nt, ctx->NFt, dsp_type == SGPU_DSP_SQUARE,
+                                                    reinterpret_cast<double2 *>(d_partial), d_partial + 2 * ctx->NFt,
                                                     ctx->d_work, ctx->stream);
     }
     CK(cudaGetLastError());
@@ -319,7 +326,8 @@ int sgpu_init(int device, sgpu_ctx **out) {
     if ((e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e2 = cudaEventCreate(&c->ev0)) != cudaSuccess || (e2 = cudaEventCreate(&c->ev1)) != cudaSuccess ||
-        (e2 = cudaEventCreate(&c->ev2)) != cudaSuccess ||
+        (e2 = cudaEventCreate(&c->ev2)) != cudaSuccess || (e2 = cudaEventCreate(&c->evd0)) != cudaSuccess ||
+        (e2 = cudaEventCreate(&c->evd1)) != cudaSuccess ||
         (e2 = cudaHostAlloc(reinterpret_cast<void **>(&c->h_acc), 4 * sizeof(double), cudaHostAllocDefault)) !=
             cudaSuccess) {
         delete c;
@@ -413,6 +421,8 @@ int sgpu_stage_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, int
     }
     ctx->mode = 1;
     ctx->NF = NF;
+    ctx->NFt = NF;
+    ctx->f_first = 0;
     ctx->NA = NA;
     ctx->repr = repr;
     return SGPU_OK;
@@ -430,6 +440,8 @@ int sgpu_stage_frames_device(sgpu_ctx *ctx, const float *d_xyz, size_t NF, size_
     ctx->d_xyz = const_cast<float *>(d_xyz);
     ctx->mode = 1;
     ctx->NF = NF;
+    ctx->NFt = NF;
+    ctx->f_first = 0;
     ctx->NA = NA;
     ctx->repr = repr;
     return SGPU_OK;
@@ -461,6 +473,8 @@ int sgpu_stage_atoms(sgpu_ctx *ctx, const float *xyz, size_t NA_local, size_t NF
     CK(cudaMemcpyAsync(ctx->d_xyz, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->mode = 2;
     ctx->NF = NF;
+    ctx->NFt = NF;
+    ctx->f_first = 0;
     ctx->NA = NA_local;
     ctx->repr = SGPU_REPR_CARTESIAN;
     return SGPU_OK;
@@ -478,6 +492,8 @@ int sgpu_stage_atoms_device(sgpu_ctx *ctx, const float *d_xyz, size_t NA_local, 
     ctx->d_xyz = const_cast<float *>(d_xyz);
     ctx->mode = 2;
     ctx->NF = NF;
+    ctx->NFt = NF;
+    ctx->f_first = 0;
     ctx->NA = NA_local;
     ctx->repr = SGPU_REPR_CARTESIAN;
     return SGPU_OK;
@@ -527,6 +543,8 @@ int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, siz
     CK(cudaGetLastError());
     ctx->mode = 2;
     ctx->NF = NF;
+    ctx->NFt = NF;
+    ctx->f_first = 0;
     ctx->NA = NA_local;
     ctx->repr = SGPU_REPR_CARTESIAN;
     return SGPU_OK;
@@ -560,6 +578,8 @@ int sgpu_partial_len(sgpu_ctx *ctx, int dsp_type, size_t *n_doubles) {
 
 static int frames_amplitude_prologue(sgpu_ctx *ctx, const char *who, size_t NM, int dsp_type, double *d_partial) {
     if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, std::string(who) + ": frames are not staged (stage_frames first)");
+    if (ctx->NFt != ctx->NF)
+        return fail(ctx, SGPU_ESTATE, std::string(who) + ": a frame window is set; use sgpu_all_vectors_amplitudes / _dsp_partial");
     if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, std::string(who) + ": scattering factors not set for the staged atoms");
     if (NM == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
     if (!d_partial) return fail(ctx, SGPU_EINVAL, std::string(who) + ": d_partial is NULL");
@@ -612,6 +632,83 @@ int sgpu_compute_all_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t 
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
     ctx->have_times = true;
+    ctx->dsp_split = false;
+    return SGPU_OK;
+}
+
+/* ---- frame-sharded coherent path ----------------------------------------------------------------------------- */
+
+int sgpu_set_frame_window(sgpu_ctx *ctx, size_t NF_total, size_t f_first) {
+    if (!ctx) return SGPU_EINVAL;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_set_frame_window: frames are not staged (stage_frames first)");
+    if (f_first + ctx->NF > NF_total || NF_total < 1)
+        return fail(ctx, SGPU_EINVAL, "sgpu_set_frame_window: the staged frames do not fit the window");
+    ctx->NFt = NF_total;
+    ctx->f_first = f_first;
+    return SGPU_OK;
+}
+
+int sgpu_all_vectors_amplitudes(sgpu_ctx *ctx, const double *qvecs, size_t NM, double *d_amp) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!qvecs || !d_amp) return fail(ctx, SGPU_EINVAL, "sgpu_all_vectors_amplitudes: NULL argument");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_all_vectors_amplitudes: frames are not staged (stage_frames first)");
+    if (ctx->repr != SGPU_REPR_CARTESIAN)
+        return fail(ctx, SGPU_ESTATE, "sgpu_all_vectors_amplitudes: staged frames are not cartesian");
+    if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, "sgpu_all_vectors_amplitudes: scattering factors not set for the staged atoms");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_all_vectors_amplitudes: No qvectors left to compute");
+    int rc = upload_q(ctx, qvecs, NM, (size_t)amplitude_all_qpad());
+    if (rc) return rc;
+    double2 *A = reinterpret_cast<double2 *>(d_amp);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // columns outside this rank's window stay zero so that a sum over the ranks assembles the timelines
+    if (ctx->NFt != ctx->NF) CK(cudaMemsetAsync(A, 0, NM * ctx->NFt * sizeof(double2), ctx->stream));
+    // the kernels index coordinates and amplitudes by the same frame number: shift the coordinate base so that frame
+    // f_first of the timeline is the first staged frame (only frames inside the window are ever addressed)
+    const float *xyz = ctx->d_xyz - ctx->f_first * ctx->NA * 3;
+    bool all_ready = true;
+    for (auto &c : ctx->chunks)
+        if (cudaEventQuery(c.ready) != cudaSuccess) all_ready = false;
+    cudaGetLastError();
+    if (getenv("SASSENA_FORCE_CHUNKED")) all_ready = ctx->chunks.empty();
+    if (all_ready) {
+        drop_chunks(ctx);
+        ctx->launches += launch_amplitude_all(xyz, ctx->d_b, ctx->d_qs, A, ctx->NFt, ctx->NA, NM, ctx->f_first, ctx->NF, ctx->stream);
+    } else {
+        for (auto &c : ctx->chunks) {
+            CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+            ctx->launches += launch_amplitude_all(xyz, ctx->d_b, ctx->d_qs, A, ctx->NFt, ctx->NA, NM, ctx->f_first + c.f0, c.nf,
+                                                  ctx->stream);
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
+    ctx->A_NM = 0;
+    return SGPU_OK;
+}
+
+int sgpu_all_vectors_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t m_first, size_t m_count, int dsp_type,
+                                 double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (!d_amp || !d_partial) return fail(ctx, SGPU_EINVAL, "sgpu_all_vectors_dsp_partial: NULL argument");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_all_vectors_dsp_partial: frames are not staged");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d_partial, 0, partial_len(ctx, dsp_type) * sizeof(double), ctx->stream));
+    if (m_count == 0) return SGPU_OK;  // a rank without timelines contributes zeros
+    rc = ensure_work(ctx, dsp_work_bytes(ctx, m_count, dsp_type));
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->evd0, ctx->stream));
+    rc = dsp_accumulate(ctx, m_count, dsp_type, d_partial, reinterpret_cast<const double2 *>(d_amp) + m_first * ctx->NFt);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->evd1, ctx->stream));
+    ctx->dsp_split = true;
     return SGPU_OK;
 }
 
@@ -674,6 +771,7 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
     ctx->have_times = true;
+    ctx->dsp_split = false;
     ctx->A_NM = 0;
     return SGPU_OK;
 }
@@ -722,6 +820,7 @@ int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, cons
     CK(cudaSetDevice(ctx->device));
     if (!qlens || !lm || !d_amp) return fail(ctx, SGPU_EINVAL, "sgpu_mpsphere_amplitudes: NULL argument");
     if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: frames are not staged (stage_frames first)");
+    if (ctx->NFt != ctx->NF) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: frame windows are not supported on this path");
     if (ctx->repr != SGPU_REPR_SPHERICAL)
         return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpsphere: staged frames are not in spherical representation");
     if (NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpsphere: No moments / qvectors to compute");
@@ -808,6 +907,7 @@ int sgpu_compute_mpsphere_batch_partial(sgpu_ctx *ctx, const double *qlens, size
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
     ctx->have_times = true;
+    ctx->dsp_split = false;
     return SGPU_OK;
 }
 
@@ -858,7 +958,7 @@ int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_
     if (!d_partial || !atfinal || !afinal || !a2final) return fail(ctx, SGPU_EINVAL, "sgpu_finalize: NULL argument");
     rc = ensure_plan(ctx);
     if (rc) return rc;
-    rc = ensure<double2>(ctx, &ctx->d_out, &ctx->out_cap, ctx->NF);
+    rc = ensure<double2>(ctx, &ctx->d_out, &ctx->out_cap, ctx->NFt);
     if (rc) return rc;
     rc = ensure_work(ctx, corr_work_bytes(&ctx->plan, 1));
     if (rc) return rc;
@@ -873,13 +973,13 @@ int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_
         ctx->launches += corr_finalize(&ctx->plan, d_partial, ctx->d_work, ctx->d_out, scale, conj ? 1 : 0, ctx->stream);
         acc = d_partial + ctx->plan.L;
     } else {
-        ctx->launches += launch_scale_complex(reinterpret_cast<const double2 *>(d_partial), ctx->d_out, ctx->NF, scale,
+        ctx->launches += launch_scale_complex(reinterpret_cast<const double2 *>(d_partial), ctx->d_out, ctx->NFt, scale,
                                               ctx->stream);
-        acc = d_partial + 2 * ctx->NF;
+        acc = d_partial + 2 * ctx->NFt;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_acc, acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(atfinal, ctx->d_out, ctx->NF * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(atfinal, ctx->d_out, ctx->NFt * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     afinal[0] = ctx->h_acc[0] * scale;
     afinal[1] = (conj ? -ctx->h_acc[1] : ctx->h_acc[1]) * scale;
@@ -944,7 +1044,7 @@ int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM,
 
 int sgpu_get_amplitudes(sgpu_ctx *ctx, double *A, size_t NM, size_t NF) {
     if (!ctx || !A) return SGPU_EINVAL;
-    if (ctx->A_NM == 0 || NM != ctx->A_NM || NF != ctx->NF)
+    if (ctx->A_NM == 0 || NM != ctx->A_NM || NF != ctx->NFt)
         return fail(ctx, SGPU_ESTATE, "sgpu_get_amplitudes: no matching amplitudes from the last compute");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(A, ctx->d_A, NM * NF * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -965,6 +1065,11 @@ int sgpu_last_dsp_ms(sgpu_ctx *ctx, float *ms) {
     if (!ctx || !ms) return SGPU_EINVAL;
     if (!ctx->have_times) return fail(ctx, SGPU_ESTATE, "no compute has run yet");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->dsp_split) {
+        CK(cudaEventSynchronize(ctx->evd1));
+        CK(cudaEventElapsedTime(ms, ctx->evd0, ctx->evd1));
+        return SGPU_OK;
+    }
     CK(cudaEventSynchronize(ctx->ev2));
     CK(cudaEventElapsedTime(ms, ctx->ev1, ctx->ev2));
     return SGPU_OK;

@@ -47,6 +47,8 @@ def main():
         p.set("scattering.average.orientation.type", "multipole")
         p.set("scattering.average.orientation.multipole.moments.type", "resolution")
         p.set("scattering.average.orientation.multipole.moments.resolution", 3).set("scattering.dsp.type", "square")
+    if "_frames" in case:  # the reference's frame decomposition inside the partition (amplitude exchange)
+        p.set("limits.decomposition.coherent", "frames")
     if case.endswith("_manual1"):  # partitions of one rank each: every rank owns a |q| subset, no all-reduce
         p.set("limits.decomposition.partitions.automatic", False).set("limits.decomposition.partitions.size", 1)
         p.set("limits.decomposition.utilization", 0.0)

@@ -32,7 +32,10 @@ class OracleBackend:
             compute_mpsphere_partial=_host.BE_COMPUTE_MP(self._compute_mp), finalize=_host.BE_FINALIZE(self._finalize),
             device_alloc=_host.BE_ALLOC(self._alloc), device_free=_host.BE_FREE(self._free),
             set_factors_batch=_host.BE_SET_FACTORS_BATCH(self._set_factors_batch),
-            mpsphere_amplitudes=_host.BE_MP_AMPL(self._mp_amplitudes), mpsphere_dsp_partial=_host.BE_MP_DSP(self._mp_dsp))
+            mpsphere_amplitudes=_host.BE_MP_AMPL(self._mp_amplitudes), mpsphere_dsp_partial=_host.BE_MP_DSP(self._mp_dsp),
+            set_frame_window=_host.BE_SET_WINDOW(self._set_window),
+            all_vectors_amplitudes=_host.BE_AV_AMPL(self._av_amplitudes),
+            all_vectors_dsp_partial=_host.BE_AV_DSP(self._av_dsp))
         self._cbs = cbs
         self.vtbl = _host.BackendVtbl(**cbs)
 
@@ -55,7 +58,38 @@ class OracleBackend:
 
     def _stage_frames(self, c, xyz, NF, NA, repr_):
         a = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(NF, NA, 3)).copy()
-        self._ctx(c).update(mode=1, xyz=a, NF=NF, NA=NA, repr=repr_)
+        self._ctx(c).update(mode=1, xyz=a, NF=NF, NA=NA, repr=repr_, NFt=NF, f_first=0)
+        return 0
+
+    def _set_window(self, c, NF_total, f_first):
+        ctx = self._ctx(c)
+        if ctx.get("mode") != 1 or f_first + ctx["NF"] > NF_total:
+            self.err = b"set_frame_window: bad window"
+            return 1
+        ctx.update(NFt=NF_total, f_first=f_first)
+        return 0
+
+    def _av_amplitudes(self, c, q, NM, out):
+        ctx = self._ctx(c)
+        NFt, f0, NF = ctx["NFt"], ctx["f_first"], ctx["NF"]
+        qv = np.ctypeslib.as_array(q, shape=(NM, 3)).copy()
+        *_, amp = o.compute_all_vectors(ctx["xyz"], ctx["b"], qv, dsp="plain", return_amplitudes=True)
+        A = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(NM, NFt, 2))
+        A[:] = 0
+        A[:, f0:f0 + NF] = np.ascontiguousarray(amp).view(np.float64).reshape(NM, NF, 2)
+        return 0
+
+    def _av_dsp(self, c, amp, m0, mc, dsp, ptr):
+        ctx = self._ctx(c)
+        NFt = ctx["NFt"]
+        if mc == 0:
+            self._zero(ctx, ptr)
+            return 0
+        nm_total = m0 + mc  # rows beyond are not touched
+        A = np.ctypeslib.as_array(C.cast(amp, C.POINTER(C.c_double)), shape=(nm_total, NFt, 2))
+        Ac = np.ascontiguousarray(A[m0:m0 + mc]).view(np.complex128).reshape(mc, NFt)
+        fqt, fq, fq2 = o.np_dsp_store(Ac, _DSP[dsp], "fftw", norm=1.0)
+        self._store(ctx, ptr, fqt, fq, fq2, 1.0)
         return 0
 
     def _to_sph(self, c):
@@ -114,18 +148,19 @@ class OracleBackend:
         return 0
 
     def _partial_len(self, c, dsp, out):
-        out[0] = 2 * self._ctx(c)["NF"] + 4
+        ctx = self._ctx(c)
+        out[0] = 2 * ctx.get("NFt", ctx["NF"]) + 4
         return 0
 
     def _store(self, ctx, ptr, fqt, fq, fq2, unscale):
-        NF = ctx["NF"]
+        NF = ctx.get("NFt", ctx["NF"])
         p = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * NF + 4,))
         p[:2 * NF] = (fqt * unscale).view(np.float64)
         p[2 * NF:2 * NF + 2] = (fq.real * unscale, fq.imag * unscale)
         p[2 * NF + 2:] = (fq2.real * unscale, fq2.imag * unscale)
 
     def _zero(self, ctx, ptr):
-        np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * ctx["NF"] + 4,))[:] = 0
+        np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * ctx.get("NFt", ctx["NF"]) + 4,))[:] = 0
 
     def _compute_all(self, c, q, NM, dsp, ptr):
         ctx = self._ctx(c)
@@ -159,7 +194,7 @@ class OracleBackend:
 
     def _finalize(self, c, ptr, dsp, method, scale, at, af, a2f):
         ctx = self._ctx(c)
-        NF = ctx["NF"]
+        NF = ctx.get("NFt", ctx["NF"])
         p = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * NF + 4,))
         out = np.ctypeslib.as_array(at, shape=(2 * NF,))
         out[:] = p[:2 * NF] * scale

@@ -5,6 +5,7 @@ Tolerance: BASELINE.json north_star — 1e-9 relative on fq / fqt (checked norm-
 import numpy as np
 import pytest
 
+import sassena_b200
 from sassena_b200 import synth
 from util import TOL, rel_err
 
@@ -221,6 +222,59 @@ def test_all_vectors_sharded_equals_single(gpu_ctx, oracle):
         assert abs(fq - single[1]) < 1e-12 * abs(single[0][0])
         rfqt, rfq, rfq2 = oracle.compute_all_vectors(xyz, b, q, dsp=dsp)
         assert rel_err(fqt, rfqt) < TOL
+
+
+@pytest.mark.parametrize("nranks,NF", [(2, 64), (3, 50), (8, 41)])
+def test_all_vectors_frame_sharded_equals_single(gpu_ctx, oracle, nranks, NF):
+    """Frame decomposition (the reference's, all_vectors_scatter_device.cpp:61,170-205,248): k logical GPUs each stage
+    a DivAssignment block of the frames, fill their columns of A[NM][NF], the buffers are summed (the all-reduce),
+    each rank correlates a block of the timelines, the partials are summed and finalized.  == single-GPU result to
+    1e-12 and == oracle to 1e-9, for every dsp type; ragged blocks (NF not divisible) included."""
+    xyz, b, u = small_case(NA=203, NF=NF, NM=37)
+    q = 1.3 * u
+    NM = len(q)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    singles = {dsp: gpu_ctx.compute_all_vectors(q, dsp=dsp) for dsp in ("autocorrelate", "square", "plain")}
+    d_amp = gpu_ctx.device_alloc(NM * NF * 16)
+    A = np.zeros((NM, NF), dtype=np.complex128)
+    part = np.empty((NM, NF), dtype=np.complex128)
+    for r in range(nranks):
+        off, size, _ = oracle.div_assignment(nranks, r, NF)
+        gpu_ctx.stage_frames(xyz[off:off + size])
+        gpu_ctx.set_frame_window(NF, off)
+        gpu_ctx.set_factors(b)
+        gpu_ctx.all_vectors_amplitudes(q, d_amp)
+        gpu_ctx.synchronize()
+        gpu_ctx.memcpy_d2h(part.view(np.float64), d_amp)
+        assert np.all(part[:, :off] == 0) and np.all(part[:, off + size:] == 0)
+        A += part
+    # the fused single-GPU call refuses a windowed state instead of silently correlating a fragment
+    with pytest.raises(sassena_b200.SgpuError):
+        gpu_ctx.compute_all_vectors(q)
+    ref_amp = oracle.compute_all_vectors(xyz, b, q, dsp="plain", return_amplitudes=True)[-1]
+    assert np.max(np.abs(A - ref_amp)) < 1e-11 * np.max(np.abs(ref_amp))
+    gpu_ctx.memcpy_h2d(d_amp, A.view(np.float64))
+    for dsp, single in singles.items():
+        plen = gpu_ctx.partial_len(dsp)
+        d = gpu_ctx.device_alloc(plen * 8)
+        total = np.zeros(plen)
+        for r in range(nranks):
+            off, size, _ = oracle.div_assignment(nranks, r, NM)
+            gpu_ctx.all_vectors_dsp_partial(d_amp, off, size, d, dsp=dsp)
+            gpu_ctx.synchronize()
+            p = np.empty(plen)
+            gpu_ctx.memcpy_d2h(p, d)
+            total += p
+        gpu_ctx.memcpy_h2d(d, total)
+        fqt, fq, fq2 = gpu_ctx.finalize(d, 1.0 / NM, dsp=dsp)
+        gpu_ctx.device_free(d)
+        assert len(fqt) == NF
+        assert rel_err(fqt, single[0]) < 1e-12
+        assert abs(fq - single[1]) < 1e-12 * abs(single[0][0]) and abs(fq2 - single[2]) < 1e-12 * abs(single[2])
+        rfqt, rfq, rfq2 = oracle.compute_all_vectors(xyz, b, q, dsp=dsp)
+        assert rel_err(fqt, rfqt) < TOL
+    gpu_ctx.device_free(d_amp)
 
 
 @pytest.mark.parametrize("dsp", ["autocorrelate", "square"])

@@ -58,7 +58,7 @@ def _reference(oracle, case):
 
 
 @pytest.mark.parametrize("world,case", [(2, "all"), (2, "self"), (2, "mp"), (2, "all_manual1"), (3, "self"),
-                                        (3, "all_manual1")])
+                                        (3, "all_manual1"), (2, "all_frames"), (3, "all_frames")])
 def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
     gathered = _run(world, case, tmp_path)
     qv, ref = _reference(oracle, case)
@@ -67,6 +67,7 @@ def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
     for rank, has, recs, timer_keys in gathered:
         assert has, "no spare ranks expected in these cases"
         assert "sd:compute" in timer_keys and "sd:stage" in timer_keys
+        assert ("sd:c:b:exchange" in timer_keys) == ("_frames" in case)  # amplitude exchange only when frame-sharded
         writers += 1 if recs else 0
         for r in recs:
             key = tuple(np.round(r["q"], 12))

@@ -31,7 +31,15 @@ def main():
     cases = []
     p = host.Params().set("scattering.average.orientation.type", "vectors")
     p.set("scattering.average.orientation.vectors.resolution", 37).create()
-    cases.append(("all", p, lambda q, p=p: o.compute_all_vectors(xyz, b, p.init_subvectors(q), nthreads=4)))
+    p.set("limits.decomposition.coherent", "frames")
+    cases.append(("all (frame-sharded)", p, lambda q, p=p: o.compute_all_vectors(xyz, b, p.init_subvectors(q), nthreads=4)))
+    pv = host.Params().set("scattering.average.orientation.type", "vectors")
+    pv.set("scattering.average.orientation.vectors.resolution", 37).set("limits.decomposition.coherent", "vectors").create()
+    cases.append(("all (vector-sharded)", pv, lambda q, p=pv: o.compute_all_vectors(xyz, b, p.init_subvectors(q), nthreads=4)))
+    pq = host.Params().set("scattering.average.orientation.type", "vectors").set("scattering.dsp.type", "square")
+    pq.set("scattering.average.orientation.vectors.resolution", 21).set("limits.decomposition.coherent", "frames").create()
+    cases.append(("all square (frame-sh.)", pq,
+                  lambda q, p=pq: o.compute_all_vectors(xyz, b, p.init_subvectors(q), dsp="square", nthreads=4)))
     ps = host.Params().set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
     ps.set("scattering.average.orientation.vectors.resolution", 5).create()
     cases.append(("self", ps, lambda q, p=ps: o.compute_self_vectors(xyz.transpose(1, 0, 2), b, p.init_subvectors(q), nthreads=4)))
