@@ -156,6 +156,23 @@ int sgpu_all_vectors_amplitudes(sgpu_ctx *ctx, const double *qvecs, size_t NM, d
 /* DSP of timelines [m_first, m_first+m_count) of d_amp into a packed partial (m_count == 0 zeroes it) */
 int sgpu_all_vectors_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t m_first, size_t m_count, int dsp_type,
                                  double *d_partial);
+/* ---- |q|-scan coherent path ---------------------------------------------------------------------------------------
+ * A scan (scattering.vectors.scans, parameters.cpp:1125-1189) evaluates the same orientation vectors at equally spaced
+ * |q|: q_{n,m} = (s0 + n ds) v_m, n < NQ (init_subvectors scales unit vectors by |q| for sphere/file vectors and the
+ * cylinder construction is linear in |q| for a fixed direction, abstract_vectors_scatter_device.cpp:96-175).  The phases
+ * of one (atom, v_m) pair then form an arithmetic progression and NQ amplitudes cost two sincos evaluations plus NQ-1
+ * complex rotations.  Results are those of NQ sgpu_compute_all_vectors calls with q = (s0 + n ds) v (to ~1e-14).
+ * Factors: sgpu_set_factors (same b for every |q|) or sgpu_set_factors_batch(b[NQ][NA]); if the rows of a batch differ
+ * the general kernel runs once per |q| (same results, no rotation shortcut).
+ * v: host [NM][3] direction vectors (not pre-scaled).  Outputs are NQ consecutive blocks laid out like the single-|q|
+ * calls: atfinal [NQ][NF][2], afinal/a2final [NQ][2], d_partials NQ packed partials, d_amp [NQ][NM][NF_total] complex. */
+int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ, int dsp_type,
+                                  int dsp_method, double *atfinal, double *afinal, double *a2final);
+int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t NM_local, double s0, double ds, size_t NQ,
+                                          int dsp_type, double *d_partials);
+/* frame-window aware (see sgpu_set_frame_window); follow with sgpu_all_vectors_dsp_partial per |q| plane */
+int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ,
+                                     double *d_amp);
 /* scale = 1/NM_total (vectors) or 1/(4 pi) (multipole sphere). */
 int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_method, double scale,
                   double *atfinal, double afinal[2], double a2final[2]);

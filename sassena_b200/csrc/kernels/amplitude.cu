@@ -263,6 +263,142 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
     }
 }
 
+// ---- K1s, |q|-scan variant ---------------------------------------------------------------------------------
+// A Sassena scan evaluates the SAME orientation vectors at equally spaced |q| (scattering.vectors.scans with
+// exponent 1, parameters.cpp:1125-1189; init_subvectors scales unit vectors by |q|,
+// abstract_vectors_scatter_device.cpp:96-175).  For q_{n,m} = (s0 + n ds) v_m the phases of one (atom, v_m) pair form an
+// arithmetic progression, so
+//     exp(i q_{n,m}.r) = exp(i s0 v_m.r) * exp(i ds v_m.r)^n
+// and B consecutive |q| cost two sincos evaluations plus B-1 complex rotations (2 DMUL + 2 DFMA each) instead of
+// B sincos evaluations (19 FP64 instructions each).  |w| = 1 to 1 ulp, so the rotation chain is stable: after B <= 32
+// steps the accumulated relative error is <= ~2 B ulp (7e-15), far inside the 1e-9 tolerance.
+// One warp owns VPT orientation vectors, lanes stride over the atoms of the tile, every thread keeps B x VPT complex
+// accumulators in registers.  Same TMA ring as the tiled kernel.  A is [B][NM][ldA] (strideQ between |q| planes).
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
+    const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ vs, double s0, double ds,
+    double2 *__restrict__ A, size_t ldA, size_t strideQ, int NA, int NM, int nq_valid, unsigned ngroups, size_t f0,
+    int use_bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_xyz = reinterpret_cast<float *>(smem_raw);                                  // [STAGES][TILE*3]
+    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);  // [STAGES][TILE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8));
+    uint64_t *empty = full + STAGES;
+
+    const unsigned group = blockIdx.x % ngroups;
+    const size_t frame = f0 + blockIdx.x / ngroups;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = (group * WARPS + warp) * VPT;
+    const float *p = xyz + frame * (size_t)NA * 3;
+    const int ntiles = (NA + TILE - 1) / TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            ptx::mbar_init(&full[s], use_bulk ? 1u : (unsigned)(WARPS * 32));
+            ptx::mbar_init(&empty[s], (unsigned)WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int s = t % STAGES;
+        const int a0 = t * TILE;
+        const int cnt = min(TILE, NA - a0);
+        if (use_bulk) {
+            if (tid == 0) {
+                if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+                ptx::mbar_expect_tx(&full[s], (unsigned)cnt * 20u);
+                ptx::bulk_g2s(s_xyz + (size_t)s * TILE * 3, p + (size_t)a0 * 3, (unsigned)cnt * 12u, &full[s]);
+                ptx::bulk_g2s(s_b + (size_t)s * TILE, b + a0, (unsigned)cnt * 8u, &full[s]);
+            }
+        } else {
+            if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+            float *dx = s_xyz + (size_t)s * TILE * 3;
+            const float *sx = p + (size_t)a0 * 3;
+            for (int i = tid; i < cnt * 3; i += WARPS * 32) ptx::cp_async4(dx + i, sx + i);
+            float *db = reinterpret_cast<float *>(s_b + (size_t)s * TILE);
+            const float *sb = reinterpret_cast<const float *>(b + a0);
+            for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
+            ptx::cp_async_mbar_arrive_noinc(&full[s]);
+        }
+    };
+    for (int t = 0; t < STAGES - 1 && t < ntiles; t++) issue(t);
+
+    const bool active = m0 < NM;
+    double vx[VPT], vy[VPT], vz[VPT];
+    double re[VPT][B], im[VPT][B];
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+        vx[k] = __ldg(&vs[3 * (m0 + k)]);  // vs is zero padded past NM
+        vy[k] = __ldg(&vs[3 * (m0 + k) + 1]);
+        vz[k] = __ldg(&vs[3 * (m0 + k) + 2]);
+#pragma unroll
+        for (int n = 0; n < B; n++) {
+            re[k][n] = 0.0;
+            im[k][n] = 0.0;
+        }
+    }
+
+    for (int t = 0; t < ntiles; t++) {
+        if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);
+        const int s = t % STAGES;
+        const int cnt = min(TILE, NA - t * TILE);
+        ptx::mbar_wait(&full[s], (unsigned)((t / STAGES) & 1));
+        if (active) {
+            const float *sx = s_xyz + (size_t)s * TILE * 3;
+            const double *sb = s_b + (size_t)s * TILE;
+#pragma unroll 1
+            for (int j = lane; j < cnt; j += 32) {
+                const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
+                const double bj = sb[j];
+#pragma unroll
+                for (int k = 0; k < VPT; k++) {
+                    const double sigma = fma(z, vz[k], fma(y, vy[k], x * vx[k]));  // quarter turns per unit |q|
+                    double sn, cs, sw, cw;
+                    sincos_qt(s0 * sigma, sn, cs);
+                    sincos_qt(ds * sigma, sw, cw);
+                    double zr = bj * cs, zi = bj * sn;
+#pragma unroll
+                    for (int n = 0; n < B; n++) {
+                        re[k][n] += zr;
+                        im[k][n] += zi;
+                        if (n + 1 < B) {
+                            const double t1 = zi * sw, t2 = zi * cw;
+                            const double nr = fma(zr, cw, -t1);
+                            zi = fma(zr, sw, t2);
+                            zr = nr;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    }
+    if (!active) return;
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+#pragma unroll
+        for (int n = 0; n < B; n++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                re[k][n] += __shfl_xor_sync(0xffffffffu, re[k][n], o);
+                im[k][n] += __shfl_xor_sync(0xffffffffu, im[k][n], o);
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < VPT; k++)
+            if (m0 + k < NM) {
+#pragma unroll
+                for (int n = 0; n < B; n++)
+                    if (n < nq_valid) A[(size_t)n * strideQ + (size_t)(m0 + k) * ldA + frame] = make_double2(re[k][n], im[k][n]);
+            }
+    }
+}
+
 // ---- K1, uniform-q variant -------------------------------------------------------------------------------
 // On B200 the FP64 pipe accepts one warp instruction every 2 cycles, but a DFMA whose three operands are all
 // distinct vector registers needs 3 register-file cycles (measured, tools/micro/fp64_micro.cu).  Here the whole
@@ -698,6 +834,82 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
             d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups, f0 + done);
         launches++;
         done += cnt;
+    }
+    return launches;
+}
+
+namespace {
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB>
+int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq_valid,
+                     double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    const unsigned per_cta = VPT * WARPS;
+    const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
+    const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
+    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    const int use_bulk = (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
+    int launches = 0;
+    const size_t max_frames = (size_t)0x7fffffff / ngroups;
+    for (size_t done = 0; done < nf;) {
+        size_t cnt = nf - done < max_frames ? nf - done : max_frames;
+        kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_vs, s0, ds, d_A, ldA, strideQ, (int)NA,
+                                                                  (int)NM, nq_valid, ngroups, f0 + done, use_bulk);
+        launches++;
+        done += cnt;
+    }
+    return launches;
+}
+
+int scan_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SASSENA_SCAN_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+}  // namespace
+
+// largest number of |q| one kernel pass handles; sgpu_* callers may pass any nq (decomposed into passes here)
+int amplitude_scan_qpad() { return 16; }  // vs padding: vectors per CTA (VPT * WARPS) of every variant divides 16
+
+int launch_amplitude_scan(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, size_t nq,
+                          double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf,
+                          cudaStream_t st) {
+    if (nf == 0 || NM == 0 || nq == 0) return 0;
+    int launches = 0;
+    size_t n0 = 0;
+    const int var = scan_variant();
+    while (n0 < nq) {
+        const size_t rem = nq - n0;
+        const double s = s0 + (double)n0 * ds;
+        double2 *A = d_A + n0 * strideQ;
+        size_t step;
+        if (var == 1 && rem >= 32) {
+            step = 32;
+            launches += launch_scan_part<32, 1, 8, 512, 4, 1>(d_xyz, d_b, d_vs, s, ds, 32, A, ldA, strideQ, NA, NM, f0, nf, st);
+        } else if (var == 2 && rem >= 24) {
+            step = 24;
+            launches += launch_scan_part<24, 1, 8, 512, 4, 1>(d_xyz, d_b, d_vs, s, ds, 24, A, ldA, strideQ, NA, NM, f0, nf, st);
+        } else if (var == 3 && rem >= 8) {
+            step = 8;
+            launches += launch_scan_part<8, 2, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, 8, A, ldA, strideQ, NA, NM, f0, nf, st);
+        } else if (rem >= 16) {
+            step = 16;
+            launches += launch_scan_part<16, 1, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, 16, A, ldA, strideQ, NA, NM, f0, nf, st);
+        } else if (rem >= 8) {
+            step = 8;
+            launches += launch_scan_part<8, 1, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, 8, A, ldA, strideQ, NA, NM, f0, nf, st);
+        } else {
+            step = rem < 4 ? rem : 4;
+            launches += launch_scan_part<4, 1, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, (int)step, A, ldA, strideQ, NA, NM, f0, nf, st);
+        }
+        n0 += step;
     }
     return launches;
 }

@@ -14,6 +14,12 @@ int amplitude_all_qpad();
 int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
                          size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st);
 // K2: per-atom timelines a[(n*NM+m)][t] = b_n exp(i q_m . r_n(t)) for local atoms [n0, n0+nn).
+// |q|-scan amplitudes: q_{n,m} = (s0 + n ds) v_m for n < nq.  d_vs: [NMpad][3] direction vectors pre-scaled by 2/pi,
+// zero padded to a multiple of amplitude_scan_qpad().  d_A: [nq][NM][ldA] with strideQ entries between |q| planes.
+int amplitude_scan_qpad();
+int launch_amplitude_scan(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, size_t nq,
+                          double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf,
+                          cudaStream_t st);
 int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,
                           size_t ldA, size_t NF, size_t NM, size_t n0, size_t nn, cudaStream_t st);
 // cart -> (r, phi, theta), in place, n points

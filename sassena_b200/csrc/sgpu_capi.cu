@@ -57,6 +57,7 @@ struct sgpu_ctx {
     size_t qlens_cap = 0;
     double *d_bq = nullptr;     // per-|q| factors [NQ][NA] (sgpu_set_factors_batch)
     size_t bq_cap = 0, bq_nq = 0, bq_n = 0;
+    bool bq_uniform = false;    // every |q| row of the batch holds the same factors
     std::vector<double> h_qs;
 
     double2 *d_A = nullptr;
@@ -402,12 +403,15 @@ int sgpu_stage_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, int
     const size_t frame_bytes = NA * 3 * sizeof(float);
     rc = own_xyz_buffer(ctx, NF * frame_bytes);
     if (rc) return rc;
-    // chunk by frames: big enough that one chunk is many waves of amplitude CTAs, small enough to overlap
-    size_t chunk_mb = 256;
-    if (const char *e = getenv("SASSENA_STAGE_CHUNK_MB")) chunk_mb = std::max<size_t>(1, strtoull(e, nullptr, 10));
+    // chunk by frames.  Every chunk becomes one amplitude launch that waits for its copy, and every launch ends in a
+    // partially filled last wave, so few large chunks are better for the kernel while a small FIRST chunk lets it start
+    // early: sizes grow geometrically (32 MB, x2 per chunk, up to 2 GB).  SASSENA_STAGE_CHUNK_MB fixes the size.
+    size_t chunk_mb = 32, chunk_mb_max = 2048;
+    if (const char *e = getenv("SASSENA_STAGE_CHUNK_MB")) chunk_mb = chunk_mb_max = std::max<size_t>(1, strtoull(e, nullptr, 10));
     size_t nfc = std::max<size_t>(1, (chunk_mb << 20) / frame_bytes);
-    for (size_t f0 = 0; f0 < NF; f0 += nfc) {
-        const size_t nf = std::min(nfc, NF - f0);
+    const size_t nfc_max = std::max<size_t>(1, (chunk_mb_max << 20) / frame_bytes);
+    for (size_t f0 = 0, nf = 0; f0 < NF; f0 += nf, nfc = std::min(2 * nfc, nfc_max)) {
+        nf = std::min(nfc, NF - f0);
         sgpu_ctx::Chunk c{f0, nf, nullptr};
         CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
         cudaError_t e = cudaMemcpyAsync(ctx->d_xyz + f0 * NA * 3, xyz + f0 * NA * 3, nf * frame_bytes,
@@ -712,6 +716,144 @@ int sgpu_all_vectors_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t m_fi
     return SGPU_OK;
 }
 
+/* ---- |q|-scan coherent path ------------------------------------------------------------------------------------ */
+
+namespace {
+// amplitudes of NQ equally spaced |q| along fixed directions into A[NQ][NM][NFt] (this rank's frame columns)
+int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t NM, double s0, double ds, size_t NQ,
+                         double2 *A) {
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, std::string(who) + ": frames are not staged (stage_frames first)");
+    if (ctx->repr != SGPU_REPR_CARTESIAN) return fail(ctx, SGPU_ESTATE, std::string(who) + ": staged frames are not cartesian");
+    if (!v || NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
+    // factors: a per-|q| batch set for exactly this NQ, else the single set
+    const bool batch = ctx->bq_nq == NQ && ctx->bq_n == ctx->NA && ctx->d_bq;
+    if (!batch && ctx->nb != ctx->NA)
+        return fail(ctx, SGPU_ESTATE, std::string(who) + ": scattering factors not set for the staged atoms");
+    const bool uniform = !batch || ctx->bq_uniform;
+    const double *d_b = batch ? ctx->d_bq : ctx->d_b;
+    const size_t NFt = ctx->NFt, strideQ = NM * NFt;
+    if (ctx->NFt != ctx->NF) CK(cudaMemsetAsync(A, 0, NQ * strideQ * sizeof(double2), ctx->stream));
+    const float *xyz = ctx->d_xyz - ctx->f_first * ctx->NA * 3;  // see sgpu_all_vectors_amplitudes
+    int rc;
+    if (uniform) {
+        rc = upload_q(ctx, v, NM, (size_t)amplitude_scan_qpad());  // directions, scaled to quarter turns per unit |q|
+        if (rc) return rc;
+    }
+    bool all_ready = true;
+    for (auto &c : ctx->chunks)
+        if (cudaEventQuery(c.ready) != cudaSuccess) all_ready = false;
+    cudaGetLastError();
+    if (getenv("SASSENA_FORCE_CHUNKED")) all_ready = ctx->chunks.empty();
+    std::vector<sgpu_ctx::Chunk> spans;
+    if (all_ready) {
+        drop_chunks(ctx);
+        spans.push_back(sgpu_ctx::Chunk{0, ctx->NF, nullptr});
+    } else {
+        spans = ctx->chunks;
+    }
+    if (uniform) {
+        for (auto &c : spans) {
+            if (c.ready) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+            ctx->launches += launch_amplitude_scan(xyz, d_b, ctx->d_qs, s0, ds, NQ, A, NFt, strideQ, ctx->NA, NM,
+                                                   ctx->f_first + c.f0, c.nf, ctx->stream);
+        }
+    } else {
+        // factors differ between the |q| values (X-ray form factors, background): one pass of the general kernel per |q|
+        std::vector<double> q(3 * NM);
+        for (size_t n = 0; n < NQ; n++) {
+            const double sn = s0 + (double)n * ds;
+            for (size_t i = 0; i < 3 * NM; i++) q[i] = sn * v[i];
+            rc = upload_q(ctx, q.data(), NM, (size_t)amplitude_all_qpad());
+            if (rc) return rc;
+            for (auto &c : spans) {
+                if (c.ready) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+                ctx->launches += launch_amplitude_all(xyz, d_b + n * ctx->NA, ctx->d_qs, A + n * strideQ, NFt, ctx->NA, NM,
+                                                      ctx->f_first + c.f0, c.nf, ctx->stream);
+            }
+            CK(cudaStreamSynchronize(ctx->stream));  // d_qs is reused by the next |q|
+        }
+    }
+    CK(cudaGetLastError());
+    return SGPU_OK;
+}
+}  // namespace
+
+int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ,
+                                     double *d_amp) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!d_amp) return fail(ctx, SGPU_EINVAL, "sgpu_all_vectors_scan_amplitudes: d_amp is NULL");
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = scan_amplitudes_into(ctx, "sgpu_all_vectors_scan_amplitudes", v, NM, s0, ds, NQ, reinterpret_cast<double2 *>(d_amp));
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
+    ctx->A_NM = 0;
+    return SGPU_OK;
+}
+
+int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ,
+                                          int dsp_type, double *d_partials) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (!d_partials) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors_scan: d_partials is NULL");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors_scan: frames are not staged (stage_frames first)");
+    if (ctx->NFt != ctx->NF)
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors_scan: a frame window is set; use sgpu_all_vectors_scan_amplitudes");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    const size_t plen = partial_len(ctx, dsp_type);
+    if (NM == 0) {  // a rank without subvectors contributes zeros
+        CK(cudaMemsetAsync(d_partials, 0, NQ * plen * sizeof(double), ctx->stream));
+        return SGPU_OK;
+    }
+    rc = ensure<double2>(ctx, &ctx->d_A, &ctx->A_cap, NQ * NM * ctx->NF);
+    if (rc) return rc;
+    rc = ensure_work(ctx, dsp_work_bytes(ctx, NM, dsp_type));
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = scan_amplitudes_into(ctx, "sgpu_compute_all_vectors_scan", v, NM, s0, ds, NQ, ctx->d_A);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->A_NM = (NQ == 1) ? NM : 0;
+    CK(cudaMemsetAsync(d_partials, 0, NQ * plen * sizeof(double), ctx->stream));
+    for (size_t n = 0; n < NQ; n++) {
+        rc = dsp_accumulate(ctx, NM, dsp_type, d_partials + n * plen, ctx->d_A + n * NM * ctx->NF);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
+    return SGPU_OK;
+}
+
+int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ, int dsp_type,
+                                  int dsp_method, double *atfinal, double *afinal, double *a2final) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors_scan: frames are not staged (stage_frames first)");
+    if (NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors_scan: No qvectors left to compute");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    const size_t plen = partial_len(ctx, dsp_type);
+    rc = ensure<double>(ctx, &ctx->d_partial, &ctx->partial_cap, NQ * plen);
+    if (rc) return rc;
+    rc = sgpu_compute_all_vectors_scan_partial(ctx, v, NM, s0, ds, NQ, dsp_type, ctx->d_partial);
+    if (rc) return rc;
+    for (size_t n = 0; n < NQ; n++) {
+        rc = sgpu_finalize(ctx, ctx->d_partial + n * plen, dsp_type, dsp_method, 1.0 / (double)NM, atfinal + n * 2 * ctx->NFt,
+                           afinal + 2 * n, a2final + 2 * n);
+        if (rc) return rc;
+    }
+    return SGPU_OK;
+}
+
 int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, double *d_partial) {
     if (!ctx) return SGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -810,6 +952,9 @@ int sgpu_set_factors_batch(sgpu_ctx *ctx, const double *b, size_t NQ, size_t n) 
     if (rc) return rc;
     ctx->bq_nq = NQ;
     ctx->bq_n = n;
+    ctx->bq_uniform = true;
+    for (size_t q = 1; q < NQ && ctx->bq_uniform; q++)
+        if (memcmp(b, b + q * n, n * sizeof(double)) != 0) ctx->bq_uniform = false;
     return SGPU_OK;
 }
 

@@ -277,6 +277,82 @@ def test_all_vectors_frame_sharded_equals_single(gpu_ctx, oracle, nranks, NF):
     gpu_ctx.device_free(d_amp)
 
 
+@pytest.mark.parametrize("NQ", [1, 3, 4, 8, 16, 21, 37])
+def test_all_vectors_scan_matches_per_q(gpu_ctx, oracle, NQ):
+    """|q|-scan kernel (two sincos + NQ-1 rotations per (atom, direction)): every |q| of the batch equals the per-|q|
+    GPU result to 1e-12 and the oracle to 1e-9; NQ values exercise every pass size (16, 8, 4 and masked remainders)."""
+    xyz, b, u = small_case(NA=301, NF=40, NM=37)
+    s0, ds = 0.3, 0.17
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ)
+    assert fqt.shape == (NQ, 40)
+    for n in sorted({0, NQ // 2, NQ - 1}):
+        q = (s0 + n * ds) * u
+        g = gpu_ctx.compute_all_vectors(q)
+        assert rel_err(fqt[n], g[0]) < 1e-12
+        assert abs(fq[n] - g[1]) < 1e-12 * abs(g[0][0]) and abs(fq2[n] - g[2]) < 1e-12 * abs(g[2])
+        r = oracle.compute_all_vectors(xyz, b, q)
+        assert rel_err(fqt[n], r[0]) < TOL
+        assert abs(fq[n] - r[1]) < TOL * abs(r[0][0]) and abs(fq2[n] - r[2]) < TOL * abs(r[2])
+
+
+@pytest.mark.parametrize("dsp", ["square", "plain"])
+def test_all_vectors_scan_other_dsp_and_unaligned_atoms(gpu_ctx, oracle, dsp):
+    """NA % 4 != 0 takes the cp.async staging path; square / plain dsp; long rotation chain far from the origin"""
+    xyz, b, u = small_case(NA=203, NF=24, NM=19, box=300.0)
+    s0, ds, NQ = 1.1, 0.45, 16
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ, dsp=dsp)
+    for n in (0, 7, 15):
+        r = oracle.compute_all_vectors(xyz, b, (s0 + n * ds) * u, dsp=dsp)
+        assert rel_err(fqt[n], r[0]) < TOL
+        assert abs(fq[n] - r[1]) < TOL * max(abs(r[1]), abs(r[0]).max())
+
+
+def test_all_vectors_scan_per_q_factors(gpu_ctx, oracle):
+    """|q|-dependent factors (X-ray form factors / background): a batch with differing rows falls back to the general
+    kernel per |q|; a batch with identical rows takes the rotation kernel.  Both equal the oracle."""
+    xyz, b, u = small_case(NA=160, NF=16, NM=23)
+    s0, ds, NQ = 0.2, 0.3, 5
+    gpu_ctx.stage_frames(xyz)
+    bq = np.stack([b * (1.0 + 0.1 * n) - 0.05 * n for n in range(NQ)])
+    gpu_ctx.set_factors_batch(bq)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ)
+    for n in range(NQ):
+        r = oracle.compute_all_vectors(xyz, bq[n], (s0 + n * ds) * u)
+        assert rel_err(fqt[n], r[0]) < TOL
+    gpu_ctx.set_factors_batch(np.stack([b] * NQ))
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ)
+    for n in range(NQ):
+        r = oracle.compute_all_vectors(xyz, b, (s0 + n * ds) * u)
+        assert rel_err(fqt[n], r[0]) < TOL
+
+
+def test_all_vectors_scan_frame_window(gpu_ctx, oracle):
+    """scan amplitudes of a frame block land in the right columns of A[NQ][NM][NF_total]"""
+    xyz, b, u = small_case(NA=128, NF=30, NM=11)
+    s0, ds, NQ, NM, NF = 0.4, 0.25, 6, 11, 30
+    d_amp = gpu_ctx.device_alloc(NQ * NM * NF * 16)
+    A = np.zeros((NQ, NM, NF), dtype=np.complex128)
+    part = np.empty_like(A)
+    for r in range(3):
+        off, size, _ = oracle.div_assignment(3, r, NF)
+        gpu_ctx.stage_frames(xyz[off:off + size])
+        gpu_ctx.set_frame_window(NF, off)
+        gpu_ctx.set_factors(b)
+        gpu_ctx.all_vectors_scan_amplitudes(u, s0, ds, NQ, d_amp)
+        gpu_ctx.synchronize()
+        gpu_ctx.memcpy_d2h(part.view(np.float64), d_amp)
+        assert np.all(part[:, :, :off] == 0) and np.all(part[:, :, off + size:] == 0)
+        A += part
+    gpu_ctx.device_free(d_amp)
+    for n in range(NQ):
+        ref = oracle.compute_all_vectors(xyz, b, (s0 + n * ds) * u, dsp="plain", return_amplitudes=True)[-1]
+        assert np.max(np.abs(A[n] - ref)) < 1e-11 * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("dsp", ["autocorrelate", "square"])
 def test_mpsphere_small(gpu_ctx, oracle, dsp):
     """multipole sphere moments (multipole_scatter_device.cpp:428-498), L=6, cartesian input converted on the GPU"""

@@ -1,0 +1,56 @@
+"""Throughput of the |q|-scan amplitude kernel vs the per-|q| kernel on a C3-shaped sample (run on the GPU box).
+SASSENA_SCAN_VARIANT selects the pass size: 0 -> 16, 1 -> 32, 2 -> 24, 3 -> 8 with two directions per warp."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import sassena_b200  # noqa: E402
+from sassena_b200 import synth  # noqa: E402
+
+
+def main():
+    NA = int(os.environ.get("NA", 100000))
+    NF = int(os.environ.get("NF", 600))
+    NM = int(os.environ.get("NM", 500))
+    NQ = int(os.environ.get("NQ", 32))
+    dev = torch.device("cuda", 0)
+    ctx = sassena_b200.ScatterContext(0)
+    xyz = torch.empty(NF * NA * 3, dtype=torch.float32, device=dev)
+    ctx.synth_trajectory(xyz.data_ptr(), NF, NA, 100.0, 0.05, 5)
+    ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
+    b = synth.factors(NA)
+    ctx.set_factors(b)
+    u = synth.unit_vectors(NM, 6)
+    s0, ds = 0.1, 0.1
+    amp = torch.empty(NQ * NM * NF * 2, dtype=torch.float64, device=dev)
+    for rep in range(2):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        ctx.all_vectors_scan_amplitudes(u, s0, ds, NQ, amp.data_ptr())
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        ms = ctx.last_amplitude_ms()
+    evals = float(NA) * NF * NM * NQ
+    print(f"scan variant {os.environ.get('SASSENA_SCAN_VARIANT', '0')}: NQ={NQ} {evals / (ms * 1e-3):.3e} evals/s (kernel {ms:.1f} ms, wall {dt * 1e3:.1f} ms)")
+    # per-|q| kernel for comparison and a spot check
+    a1 = torch.empty(NM * NF * 2, dtype=torch.float64, device=dev)
+    n = NQ - 1
+    for rep in range(2):
+        ctx.all_vectors_amplitudes((s0 + n * ds) * u, a1.data_ptr())
+        ctx.synchronize()
+        ms1 = ctx.last_amplitude_ms()
+    print(f"per-|q| kernel: {float(NA) * NF * NM / (ms1 * 1e-3):.3e} evals/s")
+    torch.cuda.synchronize()
+    ref = a1.view(NM, NF, 2)
+    got = amp.view(NQ, NM, NF, 2)[n]
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print(f"last |q| of the scan vs per-|q| kernel: max rel diff {err:.2e}")
+
+
+if __name__ == "__main__":
+    main()
