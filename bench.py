@@ -4,16 +4,20 @@
 Metric (BASELINE.json): amplitude evaluations/s, one evaluation = one (atom, frame, q-vector) triple, plus the
 F(q,t) wall time it implies.  Workload (default): BASELINE configs[2] "coherent F(q,t): 100k atoms x 10k frames,
 50 |q| x 500 sphere vectors" — the configuration north_star's Target sentence is quoted on; it fits one GPU
-(12 GB of coordinates).  A STEP is one compute() of the reference's runner loop
-(abstract_scatter_device.cpp:162-173): one |q| with its 500 orientation vectors over the full trajectory,
-i.e. amplitudes -> FFT autocorrelation -> orientational average -> fqt/fq/fq2 for that |q| (5e11 evaluations).
+(12 GB of coordinates).
+
+A STEP (default `--mode scan`) is the whole job's hot path: all 50 equally spaced |q| x 500 orientation vectors over
+the full trajectory — amplitudes -> FFT autocorrelation -> orientational average -> fqt/fq/fq2 for every |q|
+(2.5e13 evaluations).  The |q|-scan kernel evaluates the 50 |q| of one (atom, direction) pair with two sincos and a
+3-term recurrence per pass of <= 28 |q| (DESIGN.md "K1s").  `--mode per-q` times the general kernel instead: a step is
+one compute() of the reference's runner loop (abstract_scatter_device.cpp:162-173), one |q| with its 500 vectors.
 
 N GPUs: one process per GPU (torchrun).  The FRAMES are sharded with DivAssignment (the reference's own decomposition,
 all_vectors_scatter_device.cpp:61,248,408): every rank holds and evaluates only its block of the trajectory for all
-500 subvectors, the zero-padded amplitude buffers A[NM][NF] are summed over NVSwitch (one NCCL all-reduce, 80 MB),
-every rank correlates a DivAssignment block of the timelines, and the packed partials are summed with a second
-small all-reduce; finalize on every rank ("strong" scaling: total work per step is fixed).  `--shard vectors` selects
-the alternative with replicated coordinates and sharded subvectors.
+subvectors, the zero-padded amplitude buffers A[NQ][NM][NF] are summed over NVSwitch (one NCCL all-reduce), every rank
+correlates a DivAssignment block of the timelines, and the packed partials are summed with a second small all-reduce;
+finalize on every rank ("strong" scaling: total work per step is fixed).  `--shard vectors` selects the alternative with
+replicated coordinates and sharded subvectors.
 
 `--impl reference` times the CPU oracle (oracle/, the restatement of the reference's loops; the reference
 itself cannot be built in this image) on all host cores on a bounded sample of the same workload.
@@ -36,6 +40,24 @@ import numpy as np  # noqa: E402
 
 FLOP_PER_EVAL = 45.0        # algorithmic FP64 flop per amplitude evaluation
 FP64_INSTR_PER_EVAL = 21.0  # what the kernel executes (sincos_qt.cuh)
+# |q|-scan kernel (DESIGN.md "K1s"): per (atom, direction, pass) a setup of one dot product, two phase scalings, two
+# sincos, the b scaling and one complex rotation; per |q| of the pass one 3-term recurrence step and one accumulation on
+# both components
+SCAN_SETUP_FLOP, SCAN_STEP_FLOP = 65.0, 6.0    # algorithmic FP64 flop
+SCAN_SETUP_INSTR, SCAN_STEP_INSTR = 49.0, 4.0  # executed FP64-pipe instructions
+SCAN_MAX_PASS = 28                             # amplitude.cu launch_amplitude_scan default
+
+
+def scan_passes(nq, max_b=SCAN_MAX_PASS):
+    """pass sizes launch_amplitude_scan uses for nq |q| values (multiples of 4, even shares)"""
+    npass = (nq + max_b - 1) // max_b
+    out, n0 = [], 0
+    for p in range(npass):
+        want = (nq - n0 + (npass - p) - 1) // (npass - p)
+        B = min(32, (want + 3) // 4 * 4)
+        out.append(B)
+        n0 += min(B, nq - n0)
+    return out
 
 WORKLOADS = {
     # name: (config key in sassena_b200.synth.CONFIGS, description)
@@ -204,6 +226,10 @@ def _run_ours(args, json_fd):
         cfg["NA"] = args.atoms
     NA, NF, NM = cfg["NA"], cfg["NF"], cfg["NM"]
     qls = synth.qlengths(*cfg["q"])
+    scan = args.mode == "scan"
+    NQ = len(qls) if scan else 1          # |q| values per step
+    s0, ds = float(qls[0]), float(qls[1] - qls[0])
+    assert np.allclose(qls, s0 + ds * np.arange(len(qls)), rtol=1e-13), "the scan path needs equally spaced |q|"
     b = synth.factors(NA)
     u = synth.unit_vectors(NM, cfg["vseed"])
     m_off, m_cnt = div_assignment(world, rank, NM)
@@ -216,7 +242,6 @@ def _run_ours(args, json_fd):
     # synthetic trajectory generated on the device (CPU twin: sassena_b200/synth.py), resident in HBM
     xyz = torch.empty(NF * NA * 3, dtype=torch.float32, device=dev)
     ctx.synth_trajectory(xyz.data_ptr(), NF, NA, cfg["box"], cfg["sigma"], cfg["seed"])
-    amp = None
 
     def stage_resident():
         if by_frames:  # this rank's block of the timeline
@@ -227,26 +252,9 @@ def _run_ours(args, json_fd):
         ctx.set_factors(b)
 
     stage_resident()
-    if by_frames:
-        amp = torch.zeros(NM * NF * 2, dtype=torch.float64, device=dev)
+    amp = torch.zeros(NQ * NM * NF * 2, dtype=torch.float64, device=dev) if by_frames else None
     plen = ctx.partial_len("autocorrelate")
-    partial = torch.zeros(plen, dtype=torch.float64, device=dev)
-
-    def compute_sharded(q_all):
-        """one |q| on `world` GPUs; coordinates already staged"""
-        if by_frames:
-            ctx.all_vectors_amplitudes(q_all, amp.data_ptr())
-            ctx.synchronize()
-            dist.all_reduce(amp)  # exchange: every rank ends up with the complete timelines
-            torch.cuda.synchronize()
-            ctx.all_vectors_dsp_partial(amp.data_ptr(), m_off, m_cnt, partial.data_ptr())
-        else:
-            ctx.compute_all_vectors_partial(q_all[m_off:m_off + m_cnt], partial.data_ptr())
-        if world > 1:
-            ctx.synchronize()
-            dist.all_reduce(partial)
-            torch.cuda.synchronize()
-        return ctx.finalize(partial.data_ptr(), 1.0 / NM)
+    partial = torch.zeros(NQ * plen, dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
@@ -254,12 +262,35 @@ def _run_ours(args, json_fd):
         torch.cuda.synchronize()
         ctx.synchronize()
 
-    def step(i):
-        return compute_sharded(qls[i % len(qls)] * u)
+    def compute_step(i):
+        """one step on `world` GPUs, coordinates already staged: every |q| of the scan (scan mode) or one |q|"""
+        q0 = s0 if scan else float(qls[i % len(qls)])
+        if world == 1:
+            if scan:
+                return ctx.compute_all_vectors_scan(u, q0, ds, NQ)
+            return ctx.compute_all_vectors(q0 * u)
+        if by_frames:
+            if scan:
+                ctx.all_vectors_scan_amplitudes(u, q0, ds, NQ, amp.data_ptr())
+            else:
+                ctx.all_vectors_amplitudes(q0 * u, amp.data_ptr())
+            ctx.synchronize()
+            dist.all_reduce(amp)  # exchange over NVSwitch: every rank ends up with the complete timelines
+            torch.cuda.synchronize()
+            for n in range(NQ):
+                ctx.all_vectors_dsp_partial(amp.data_ptr() + n * NM * NF * 16, m_off, m_cnt, partial.data_ptr() + n * plen * 8)
+        elif scan:
+            ctx.compute_all_vectors_scan_partial(u[m_off:m_off + m_cnt], q0, ds, NQ, partial.data_ptr())
+        else:
+            ctx.compute_all_vectors_partial(q0 * u[m_off:m_off + m_cnt], partial.data_ptr())
+        ctx.synchronize()
+        dist.all_reduce(partial)
+        torch.cuda.synchronize()
+        return [ctx.finalize(partial.data_ptr() + n * plen * 8, 1.0 / NM) for n in range(NQ)]
 
     # ---- device-resident measurement ----
     for i in range(args.warmup):
-        step(i)
+        compute_step(i)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -270,7 +301,7 @@ def _run_ours(args, json_fd):
     ctx.timer_start()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        res = step(args.warmup + i)
+        compute_step(args.warmup + i)
         amp_ms += ctx.last_amplitude_ms()
         dsp_ms += ctx.last_dsp_ms()
     ms = ctx.timer_stop()
@@ -282,13 +313,12 @@ def _run_ours(args, json_fd):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, amp_ms_max = float(t[0]), float(t[1])
-    per_rank = [None] * world
+    mine = {"rank": rank, "step_ms": ms / args.steps, "amp_ms": amp_ms / args.steps, "fp64_peak_tflops": fp64_peak}
+    per_rank = [mine]
     if world > 1:
-        dist.all_gather_object(per_rank, {"rank": rank, "step_ms": ms / args.steps, "amp_ms": amp_ms / args.steps,
-                                          "fp64_peak_tflops": fp64_peak})
-    else:
-        per_rank = [{"rank": 0, "step_ms": ms / args.steps, "amp_ms": amp_ms / args.steps, "fp64_peak_tflops": fp64_peak}]
-    evals_step = float(NA) * NF * NM
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    evals_step = float(NA) * NF * NM * NQ
     value = evals_step * args.steps / (ms_max * 1e-3)
 
     # ---- end to end: host buffers in, host results out, every step ----
@@ -300,7 +330,6 @@ def _run_ours(args, json_fd):
         equal = all(div_assignment(world, r, NF)[1] == f_cnt for r in range(world))
 
         def e2e_step(i):
-            q_all = qls[i % len(qls)] * u
             if world == 1 or by_frames:
                 # stager: chunked async H2D of this rank's frames on the copy stream; the amplitude launches wait per
                 # chunk, so the copy overlaps the kernel
@@ -321,31 +350,32 @@ def _run_ours(args, json_fd):
                 torch.cuda.synchronize()
                 ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
                 ctx.set_factors(b)
-            return compute_sharded(q_all)
+            return compute_step(i)
 
         for i in range(min(args.warmup, 2)):
             e2e_step(i)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
-            res_e2e = e2e_step(args.warmup + i)
+            e2e_step(args.warmup + i)
         barrier()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
+        nvec_up = NM if (world == 1 or by_frames) else m_cnt
         e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
-               "h2d_bytes_per_step": int(f_cnt * NA * 12 + NA * 8 + (NM if by_frames else m_cnt) * 24),
-               "d2h_bytes_per_step": int(NF * 16 + 32),
+               "h2d_bytes_per_step": int(f_cnt * NA * 12 + NA * 8 + nvec_up * 24),
+               "d2h_bytes_per_step": int(NQ * (NF * 16 + 32)),
                "ms_per_step": 1e3 * e2e_s / args.steps,
                "note": ("coordinates re-staged from pinned host memory every step (chunked async H2D overlapped "
-                        "with the amplitude kernel)" if world == 1 else
+                        "with the amplitude kernel); fqt/fq/fq2 of every |q| of the step read back to the host"
+                        if world == 1 else
                         "every rank re-stages its own frame block from pinned host memory every step (chunked async H2D "
                         "overlapped with the amplitude kernel); amplitudes exchanged over NVLink" if by_frames else
                         "every rank H2D's its frame slice each step, slices all-gathered over NVLink, then compute")}
-        # restore the resident staging for anything that follows
-        stage_resident()
+        stage_resident()  # restore the resident staging for anything that follows
         host.free()
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N=1) ----
@@ -357,7 +387,8 @@ def _run_ours(args, json_fd):
         NF_s, NM_s = cpu_sample_shape(cfg, cores, args.cpu_seconds)
         coords = np.empty((NF_s, NA, 3), dtype=np.float32)
         ctx.memcpy_d2h(coords, xyz.data_ptr())
-        ql = qls[len(qls) // 2]
+        nmid = len(qls) // 2
+        ql = qls[nmid]
         dt, (rfqt, rfq, rfq2), _ = run_cpu_oracle(cfg, NF_s, NM_s, ql, cores, coords)
         sample = (f"{NA} atoms x first {NF_s} frames x {NM_s} of {NM} subvectors of one |q| "
                   f"(amplitudes + FFT autocorrelation + store), {cores} OpenMP threads over subvectors")
@@ -365,24 +396,36 @@ def _run_ours(args, json_fd):
                         "sample": sample, "seconds": dt}
         ctx.stage_frames_device(xyz.data_ptr(), NF_s, NA)
         ctx.set_factors(b)
-        fqt, fq, fq2 = ctx.compute_all_vectors(ql * u[:NM_s])
+        if scan:  # the same kernel as the timed path: the whole scan on the sample, compared at the sampled |q|
+            fqts, fqs, fq2s = ctx.compute_all_vectors_scan(u[:NM_s], s0, ds, len(qls))
+            fqt, fq = fqts[nmid], fqs[nmid]
+        else:
+            fqt, fq, _ = ctx.compute_all_vectors(ql * u[:NM_s])
         parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
-                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9, "vs": "oracle on the CPU sample"}
-        ctx.stage_frames_device(xyz.data_ptr(), NF, NA)
-        ctx.set_factors(b)
+                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9,
+                  "vs": f"oracle on the CPU sample, |q| index {nmid} of the scan"}
+        stage_resident()
 
     if rank == 0:
         amp_s = amp_ms_max * 1e-3
-        if by_frames:
-            evals_rank = float(NA) * div_assignment(world, 0, NF)[1] * NM * args.steps
+        nf0 = div_assignment(world, 0, NF)[1] if by_frames else NF
+        nm0 = NM if (by_frames or world == 1) else div_assignment(world, 0, NM)[1]
+        evals_rank = float(NA) * nf0 * nm0 * NQ * args.steps
+        if scan:
+            passes = scan_passes(NQ)
+            flop_eval = (len(passes) * SCAN_SETUP_FLOP + sum(passes) * SCAN_STEP_FLOP) / NQ
+            instr_eval = (len(passes) * SCAN_SETUP_INSTR + sum(passes) * SCAN_STEP_INSTR) / NQ
+            kernel = "amplitude_scan_kernel"
         else:
-            evals_rank = float(NA) * NF * div_assignment(world, 0, NM)[1] * args.steps
-        achieved = evals_rank * FLOP_PER_EVAL / amp_s / 1e12
+            flop_eval, instr_eval, kernel = FLOP_PER_EVAL, FP64_INSTR_PER_EVAL, "amplitude_all_tiled_kernel"
+        achieved = evals_rank * flop_eval / amp_s / 1e12
         traffic = None
         prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_frame") * NF  # one launch covers all NF frames
+                tj = json.load(open(prof))
+                key = "scan_dram_bytes_per_frame" if scan else "dram_bytes_per_frame"
+                traffic = tj[key] * nf0 if key in tj else None  # one launch covers all frames of the rank
             except Exception:
                 traffic = None
         line = {
@@ -390,16 +433,24 @@ def _run_ours(args, json_fd):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NF": NF, "NM_per_q": NM, "NQ": len(qls),
-                       "step": "one |q| (compute() of the runner loop): amplitudes + FFT autocorrelation + average",
+                       "step": (f"the whole |q| scan ({NQ} equally spaced |q| x {NM} orientation vectors) over the full "
+                                "trajectory: amplitudes + FFT autocorrelation + average for every |q|" if scan else
+                                "one |q| (compute() of the runner loop): amplitudes + FFT autocorrelation + average"),
+                       "mode": args.mode,
                        "parallelism": (f"frame shard x{world} + amplitude all-reduce" if by_frames else
                                        f"q-vector shard x{world}" if world > 1 else "single GPU"),
                        "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
-            "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
+            "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * (len(qls) / NQ),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": traffic,
-                         "kernel": "amplitude_all_tiled_kernel", "kernel_share_of_step": amp_ms_max / ms_max,
-                         "algorithmic_flop_per_eval": FLOP_PER_EVAL,
-                         "fp64_pipe_util_executed": evals_rank * FP64_INSTR_PER_EVAL * 2 / amp_s / 1e12 / fp64_peak,
+                         "kernel": kernel, "kernel_share_of_step": amp_ms_max / ms_max,
+                         "algorithmic_flop_per_eval": flop_eval,
+                         "fp64_pipe_util_executed": evals_rank * instr_eval * 2 / amp_s / 1e12 / fp64_peak,
+                         "per_eval_formulation_equiv_tflops": evals_rank * FLOP_PER_EVAL / amp_s / 1e12,
+                         "note": ("scan kernel: 2 sincos per (atom, direction, pass) + a 3-term recurrence per |q|; its own "
+                                  "flop count is used for `achieved`.  per_eval_formulation_equiv_tflops is what the "
+                                  "reference's one-sincos-per-evaluation formulation (45 flop/eval, SURVEY 8d) would need "
+                                  "for the same evals/s" if scan else "45 flop per evaluation (SURVEY 8d)"),
                          "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
             "cpu_baseline": cpu_baseline,
@@ -421,13 +472,16 @@ def _run_ours(args, json_fd):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override NF (debug; changes the workload)")
     ap.add_argument("--atoms", type=int, default=0, help="override NA (debug; changes the workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle sample, seconds per core")
+    ap.add_argument("--mode", default="scan", choices=["scan", "per-q"],
+                    help="scan: a step is the whole |q| scan through the scan kernel (default); per-q: a step is one |q| "
+                         "through the general kernel")
     ap.add_argument("--shard", default="frames", choices=["frames", "vectors"],
                     help="N>1: shard the frames (reference decomposition, default) or the subvectors (replicated coordinates)")
     ap.add_argument("--no-e2e", action="store_true")

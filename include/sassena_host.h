@@ -57,6 +57,9 @@ typedef struct sass_backend_vtbl {
     int (*set_frame_window)(sgpu_ctx *, size_t, size_t);
     int (*all_vectors_amplitudes)(sgpu_ctx *, const double *, size_t, double *);
     int (*all_vectors_dsp_partial)(sgpu_ctx *, const double *, size_t, size_t, int, double *);
+    /* |q|-scan coherent path */
+    int (*compute_all_vectors_scan_partial)(sgpu_ctx *, const double *, size_t, double, double, size_t, int, double *);
+    int (*all_vectors_scan_amplitudes)(sgpu_ctx *, const double *, size_t, double, double, size_t, double *);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);
@@ -69,7 +72,8 @@ void sass_params_free(sass_params *p);
  * scattering.average.orientation.axis.{x,y,z}, scattering.average.orientation.vectors.{type,algorithm,resolution,seed},
  * scattering.average.orientation.multipole.type, scattering.average.orientation.multipole.moments.{type,resolution},
  * limits.stage.memory.data, limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size},
- * limits.decomposition.coherent (auto | frames | vectors: how a partition's ranks share one coherent |q|) */
+ * limits.decomposition.coherent (auto | frames | vectors: how a partition's ranks share one coherent |q|),
+ * limits.computation.scan (largest |q| batch of the coherent scan path; 0 or 1 = one |q| per pass) */
 int sass_params_set(sass_params *p, const char *key, const char *value);
 /* vectors.type=file rows / multipole.moments.type=file rows */
 int sass_params_set_vectors(sass_params *p, const double *xyz, size_t n);

@@ -39,6 +39,8 @@ BE_MP_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
 BE_SET_WINDOW = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_size_t)
 BE_AV_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_void_p)
 BE_AV_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p)
+BE_AV_SCAN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_double, C.c_double, C.c_size_t, C.c_int, C.c_void_p)
+BE_AV_SCAN_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_double, C.c_double, C.c_size_t, C.c_void_p)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -52,7 +54,8 @@ class BackendVtbl(C.Structure):
                 ("finalize", BE_FINALIZE), ("device_alloc", BE_ALLOC), ("device_free", BE_FREE),
                 ("set_factors_batch", BE_SET_FACTORS_BATCH), ("mpsphere_amplitudes", BE_MP_AMPL),
                 ("mpsphere_dsp_partial", BE_MP_DSP), ("set_frame_window", BE_SET_WINDOW),
-                ("all_vectors_amplitudes", BE_AV_AMPL), ("all_vectors_dsp_partial", BE_AV_DSP)]
+                ("all_vectors_amplitudes", BE_AV_AMPL), ("all_vectors_dsp_partial", BE_AV_DSP),
+                ("compute_all_vectors_scan_partial", BE_AV_SCAN), ("all_vectors_scan_amplitudes", BE_AV_SCAN_AMPL)]
 
 
 FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)

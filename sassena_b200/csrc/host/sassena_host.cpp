@@ -325,7 +325,9 @@ const SgpuBackend &default_backend() {
                                    sgpu_mpsphere_dsp_partial,
                                    sgpu_set_frame_window,
                                    sgpu_all_vectors_amplitudes,
-                                   sgpu_all_vectors_dsp_partial};
+                                   sgpu_all_vectors_dsp_partial,
+                                   sgpu_compute_all_vectors_scan_partial,
+                                   sgpu_all_vectors_scan_amplitudes};
     return be;
 }
 
@@ -687,6 +689,157 @@ void AllVectorsScatterDevice::compute() {
     current_subvector_ = NM;
     timer_.stop("sd:c:block");
     reduce_and_finalize(dsp, 1.0 / subvector_index_.size());  // factor = 1/NM (:355-360)
+}
+
+// Longest run of q-vectors starting at `first` that forms a scan: subvectors(q_n) = (s0 + n ds) v_m for all n, m.
+// Verified numerically on the subvectors the reference's init_subvectors produces, so every orientation type
+// (sphere, file, cylinder, none) qualifies exactly when it has that structure.  Returns 1 when there is none.
+size_t AllVectorsScatterDevice::scan_length(size_t first, std::vector<double> &v, double &s0, double &ds) {
+    const size_t maxn = std::min<size_t>(params_.limits.coherent_scan, vectors_.size() - first);
+    if (maxn < 2) return 1;
+    CartesianCoor3D q0 = vectors_[first], q1 = vectors_[first + 1];
+    s0 = q0.length();
+    const double s1 = q1.length();
+    ds = s1 - s0;
+    if (s0 <= 0.0 || s1 <= 0.0 || ds == 0.0) return 1;
+    init_subvectors(q1);
+    const size_t nm = NM;
+    if (nm < 8) return 1;  // a CTA serves 8-12 directions; below that the per-|q| kernel is the better fit
+    std::vector<CartesianCoor3D> sub1 = subvector_index_;
+    v.resize(3 * nm);
+    for (size_t m = 0; m < nm; m++) {
+        v[3 * m] = sub1[m].x / s1;
+        v[3 * m + 1] = sub1[m].y / s1;
+        v[3 * m + 2] = sub1[m].z / s1;
+    }
+    auto fits = [&](size_t n) {
+        CartesianCoor3D qn = vectors_[first + n];
+        const double sn = s0 + (double)n * ds;
+        if (sn <= 0.0 || std::fabs(qn.length() - sn) > 1e-13 * std::fabs(sn)) return false;
+        init_subvectors(qn);
+        if (NM != nm) return false;
+        const double tol = 4e-16 * std::fabs(sn) * 8;
+        for (size_t m = 0; m < nm; m++) {
+            const CartesianCoor3D &s = subvector_index_[m];
+            if (std::fabs(s.x - sn * v[3 * m]) > tol || std::fabs(s.y - sn * v[3 * m + 1]) > tol ||
+                std::fabs(s.z - sn * v[3 * m + 2]) > tol)
+                return false;
+        }
+        return true;
+    };
+    if (!fits(0)) return 1;
+    size_t n = 2;
+    while (n < maxn && fits(n)) n++;
+    // device memory for the amplitudes of the batch: at most ~1/8 of the coordinate budget
+    const size_t per_q = nm * NF * 2 * sizeof(double);
+    const size_t cap = std::max<size_t>(1, (params_.limits.stage_memory_data / 8) / std::max<size_t>(per_q, 1));
+    return std::min(n, cap);
+}
+
+void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> &v, double s0, double ds) {
+    const size_t nm = v.size() / 3;
+    NM = nm;
+    timer_.start("sd:c:init");
+    std::vector<double> fb(nq * NA);
+    for (size_t n = 0; n < nq; n++) {
+        CartesianCoor3D q = vectors_[current_vector_ + n];
+        sample_.factors(q.length(), &fb[n * NA]);  // scatterfactors.update(q) per |q|
+    }
+    ck(be_.set_factors_batch(ctx_, fb.data(), nq, NA), "sgpu_set_factors_batch");
+    timer_.stop("sd:c:init");
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    size_t plen = 0;
+    ck(be_.partial_len(ctx_, dsp, &plen), "sgpu_partial_len");
+    if (nq * plen > partial_cap_) {
+        if (d_partial_) be_.device_free(d_partial_);
+        d_partial_ = nullptr;
+        void *pp = nullptr;
+        if (be_.device_alloc(&pp, nq * plen * sizeof(double))) throw Error("device allocation of the partial buffer failed");
+        d_partial_ = static_cast<double *>(pp);
+        partial_cap_ = nq * plen;
+    }
+    const size_t NNPP = partitioncomm_->size();
+    DivAssignment mine(NNPP, partitioncomm_->rank(), nm);
+    if (frame_sharded_) {
+        const size_t amp_len = 2 * nq * nm * NF;
+        if (amp_len > amp_cap_) {
+            if (d_amp_) be_.device_free(d_amp_);
+            d_amp_ = nullptr;
+            void *pp = nullptr;
+            if (be_.device_alloc(&pp, amp_len * sizeof(double))) throw Error("device allocation of the amplitude buffer failed");
+            d_amp_ = static_cast<double *>(pp);
+            amp_cap_ = amp_len;
+        }
+        timer_.start("sd:c:block");
+        ck(be_.all_vectors_scan_amplitudes(ctx_, v.data(), nm, s0, ds, nq, d_amp_), "sgpu_all_vectors_scan_amplitudes");
+        timer_.stop("sd:c:block");
+        timer_.start("sd:c:wait");
+        ck(be_.synchronize(ctx_), "sgpu_synchronize");
+        timer_.stop("sd:c:wait");
+        timer_.start("sd:c:b:exchange");
+        partitioncomm_->allreduce_sum(d_amp_, amp_len);
+        timer_.stop("sd:c:b:exchange");
+        timer_.start("sd:c:b:dspstore");
+        for (size_t n = 0; n < nq; n++)
+            ck(be_.all_vectors_dsp_partial(ctx_, d_amp_ + n * 2 * nm * NF, mine.offset(), mine.size(), dsp, d_partial_ + n * plen),
+               "sgpu_all_vectors_dsp_partial");
+        timer_.stop("sd:c:b:dspstore");
+    } else {
+        timer_.start("sd:c:block");
+        ck(be_.compute_all_vectors_scan_partial(ctx_, v.data() + 3 * mine.offset(), mine.size(), s0, ds, nq, dsp, d_partial_),
+           "sgpu_compute_all_vectors_scan_partial");
+        timer_.stop("sd:c:block");
+    }
+    timer_.start("sd:c:wait");
+    ck(be_.synchronize(ctx_), "sgpu_synchronize");
+    timer_.stop("sd:c:wait");
+    timer_.start("sd:c:reduce");
+    if (NNPP > 1) partitioncomm_->allreduce_sum(d_partial_, nq * plen);
+    timer_.stop("sd:c:reduce");
+    batch_atfinal_.assign(nq, std::vector<double>(2 * NF));
+    batch_afinal_.assign(nq, 0.0);
+    batch_a2final_.assign(nq, 0.0);
+    for (size_t n = 0; n < nq; n++) {
+        double af[2], a2f[2];
+        ck(be_.finalize(ctx_, d_partial_ + n * plen, dsp, dsp_method_code(), 1.0 / (double)nm, batch_atfinal_[n].data(), af, a2f),
+           "sgpu_finalize");
+        batch_afinal_[n] = std::complex<double>(af[0], af[1]);
+        batch_a2final_[n] = std::complex<double>(a2f[0], a2f[1]);
+    }
+    scans_++;
+}
+
+void AllVectorsScatterDevice::runner() {
+    std::vector<double> v;
+    while (status() == 0) {
+        double s0 = 0, ds = 0;
+        const size_t nq = scan_length(current_vector_, v, s0, ds);
+        if (nq < 2) {
+            timer_.start("sd:compute");
+            compute();
+            timer_.stop("sd:compute");
+            timer_.start("sd:write");
+            write();
+            timer_.stop("sd:write");
+            next();
+            continue;
+        }
+        timer_.start("sd:compute");
+        timer_.start("sd:c:scan");
+        compute_scan(nq, v, s0, ds);
+        timer_.stop("sd:c:scan");
+        timer_.stop("sd:compute");
+        for (size_t n = 0; n < nq; n++) {
+            atfinal_ = batch_atfinal_[n];
+            afinal_ = batch_afinal_[n];
+            a2final_ = batch_a2final_[n];
+            timer_.start("sd:write");
+            write();
+            timer_.stop("sd:write");
+            next();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -178,6 +178,9 @@ struct LimitsParameters {
     // and takes a block of the orientation vectors, "auto" = frames unless the sample is too small to amortise the
     // amplitude exchange
     std::string coherent_sharding = "auto";
+    // |q|-scan batching of the coherent path: largest number of consecutive q-vectors evaluated in one pass
+    // (0 or 1 disables; limits.computation.scan)
+    size_t coherent_scan = 56;
 };
 
 struct Params {
@@ -376,11 +379,21 @@ class AllVectorsScatterDevice : public AbstractVectorsScatterDevice {
     void stage_data() override;
     void compute() override;
     void compute_frame_sharded();
+    // |q|-scan batching of the runner loop (abstract_scatter_device.cpp:162-173): consecutive q-vectors whose
+    // subvectors are (s0 + n ds) v_m for common directions v_m are evaluated in one pass (two sincos + rotations per
+    // (atom, direction) instead of one sincos per |q|; include/sassena_b200.h "|q|-scan coherent path")
+    void runner() override;
+    size_t scan_length(size_t first, std::vector<double> &v, double &s0, double &ds);
+    void compute_scan(size_t nq, const std::vector<double> &v, double s0, double ds);
+    std::vector<std::vector<double>> batch_atfinal_;
+    std::vector<std::complex<double>> batch_afinal_, batch_a2final_;
+    size_t scans_ = 0;  // number of batched passes taken (diagnostics / tests)
 
    public:
     using AbstractVectorsScatterDevice::AbstractVectorsScatterDevice;
     ~AllVectorsScatterDevice() override;
     bool frame_sharded() const { return frame_sharded_; }
+    size_t scan_batches() const { return scans_; }
 };
 
 class SelfVectorsScatterDevice : public AbstractVectorsScatterDevice {

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
 // steps the accumulated relative error is <= ~2 B ulp (7e-15), far inside the 1e-9 tolerance.
 // One warp owns VPT orientation vectors, lanes stride over the atoms of the tile, every thread keeps B x VPT complex
 // accumulators in registers.  Same TMA ring as the tiled kernel.  A is [B][NM][ldA] (strideQ between |q| planes).
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB>
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ vs, double s0, double ds,
     double2 *__restrict__ A, size_t ldA, size_t strideQ, int NA, int NM, int nq_valid, unsigned ngroups, size_t f0,
@@ -359,15 +359,44 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                     sincos_qt(s0 * sigma, sn, cs);
                     sincos_qt(ds * sigma, sw, cw);
                     double zr = bj * cs, zi = bj * sn;
+                    if (RECUR == 0) {
 #pragma unroll
-                    for (int n = 0; n < B; n++) {
-                        re[k][n] += zr;
-                        im[k][n] += zi;
-                        if (n + 1 < B) {
+                        for (int n = 0; n < B; n++) {
+                            re[k][n] += zr;
+                            im[k][n] += zi;
+                            if (n + 1 < B) {
+                                const double t1 = zi * sw, t2 = zi * cw;
+                                const double nr = fma(zr, cw, -t1);
+                                zi = fma(zr, sw, t2);
+                                zr = nr;
+                            }
+                        }
+                    } else {
+                        // three-term recurrence z_{n+1} = 2 cos(d) z_n - z_{n-1} on both components: 2 DFMA per step.
+                        // A rounding error injected at step k reaches step n with gain |sin((n-k+1)d)/sin d| <= n-k+1, so
+                        // after B steps the error is <= ~B^2/2 ulp of |z| (B = 32: 6e-14) for every d, including d -> 0.
+                        const double c2 = cw + cw;
+                        double pr = zr, pi = zi;  // z_{n-1}
+                        re[k][0] += zr;
+                        im[k][0] += zi;
+                        if (B > 1) {
                             const double t1 = zi * sw, t2 = zi * cw;
                             const double nr = fma(zr, cw, -t1);
                             zi = fma(zr, sw, t2);
                             zr = nr;
+                            re[k][1] += zr;
+                            im[k][1] += zi;
+                        }
+#pragma unroll
+                        for (int n = 2; n < B; n++) {
+                            const double nr = fma(c2, zr, -pr);
+                            const double ni = fma(c2, zi, -pi);
+                            pr = zr;
+                            pi = zi;
+                            zr = nr;
+                            zi = ni;
+                            re[k][n] += zr;
+                            im[k][n] += zi;
                         }
                     }
                 }
@@ -839,13 +868,13 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
 }
 
 namespace {
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB>
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0>
 int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq_valid,
                      double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
     const unsigned per_cta = VPT * WARPS;
     const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
-    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB>;
+    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB, RECUR>;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -865,51 +894,84 @@ int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, 
     return launches;
 }
 
-int scan_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SASSENA_SCAN_VARIANT");
-        v = e ? atoi(e) : 0;
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+struct ScanArgs {
+    const float *d_xyz;
+    const double *d_b, *d_vs;
+    double s, ds;
+    int valid;
+    double2 *A;
+    size_t ldA, strideQ, NA, NM, f0, nf;
+    cudaStream_t st;
+};
+
+template <int B, int WARPS, int MINB, int RECUR>
+int scan_pass(const ScanArgs &a) {
+    return launch_scan_part<B, 1, WARPS, 512, 4, MINB, RECUR>(a.d_xyz, a.d_b, a.d_vs, a.s, a.ds, a.valid, a.A, a.ldA, a.strideQ,
+                                                              a.NA, a.NM, a.f0, a.nf, a.st);
+}
+
+// one pass over `B` |q| values (B in 4, 8, ..., 32); warps = 8 or 12 per CTA
+int scan_dispatch(int B, int warps, int recur, const ScanArgs &a) {
+    if (!recur) {
+        switch (B) {
+            case 4: return scan_pass<4, 8, 2, 0>(a);
+            case 8: return scan_pass<8, 8, 2, 0>(a);
+            case 16: return scan_pass<16, 8, 2, 0>(a);
+            case 24: return scan_pass<24, 8, 1, 0>(a);
+            default: return scan_pass<32, 8, 1, 0>(a);
+        }
     }
-    return v;
+    if (warps == 12) {
+        switch (B) {
+            case 4: return scan_pass<4, 12, 1, 1>(a);
+            case 8: return scan_pass<8, 12, 1, 1>(a);
+            case 12: return scan_pass<12, 12, 1, 1>(a);
+            case 16: return scan_pass<16, 12, 1, 1>(a);
+            case 20: return scan_pass<20, 12, 1, 1>(a);
+            case 24: return scan_pass<24, 12, 1, 1>(a);
+            case 28: return scan_pass<28, 12, 1, 1>(a);
+            default: return scan_pass<32, 12, 1, 1>(a);
+        }
+    }
+    switch (B) {
+        case 4: return scan_pass<4, 8, 2, 1>(a);
+        case 8: return scan_pass<8, 8, 2, 1>(a);
+        case 12: return scan_pass<12, 8, 2, 1>(a);
+        case 16: return scan_pass<16, 8, 2, 1>(a);
+        case 20: return scan_pass<20, 8, 1, 1>(a);
+        case 24: return scan_pass<24, 8, 1, 1>(a);
+        case 28: return scan_pass<28, 8, 1, 1>(a);
+        default: return scan_pass<32, 8, 1, 1>(a);
+    }
 }
 }  // namespace
 
-// largest number of |q| one kernel pass handles; sgpu_* callers may pass any nq (decomposed into passes here)
-int amplitude_scan_qpad() { return 16; }  // vs padding: vectors per CTA (VPT * WARPS) of every variant divides 16
+// d_vs padding: a multiple of the directions per CTA (8 or 12 warps, one direction each)
+int amplitude_scan_qpad() { return 24; }
 
 int launch_amplitude_scan(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, size_t nq,
                           double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf,
                           cudaStream_t st) {
     if (nf == 0 || NM == 0 || nq == 0) return 0;
+    static const int maxB = env_int("SASSENA_SCAN_B", 28), warps = env_int("SASSENA_SCAN_WARPS", 12),
+                     recur = env_int("SASSENA_SCAN_RECUR", 1);
     int launches = 0;
+    // passes of equal size (a multiple of 4, at most maxB): e.g. 50 |q| -> 28 + 24 (2 masked) rather than 24 + 24 + 4
+    const size_t npass = (nq + maxB - 1) / maxB;
     size_t n0 = 0;
-    const int var = scan_variant();
-    while (n0 < nq) {
-        const size_t rem = nq - n0;
-        const double s = s0 + (double)n0 * ds;
-        double2 *A = d_A + n0 * strideQ;
-        size_t step;
-        if (var == 1 && rem >= 32) {
-            step = 32;
-            launches += launch_scan_part<32, 1, 8, 512, 4, 1>(d_xyz, d_b, d_vs, s, ds, 32, A, ldA, strideQ, NA, NM, f0, nf, st);
-        } else if (var == 2 && rem >= 24) {
-            step = 24;
-            launches += launch_scan_part<24, 1, 8, 512, 4, 1>(d_xyz, d_b, d_vs, s, ds, 24, A, ldA, strideQ, NA, NM, f0, nf, st);
-        } else if (var == 3 && rem >= 8) {
-            step = 8;
-            launches += launch_scan_part<8, 2, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, 8, A, ldA, strideQ, NA, NM, f0, nf, st);
-        } else if (rem >= 16) {
-            step = 16;
-            launches += launch_scan_part<16, 1, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, 16, A, ldA, strideQ, NA, NM, f0, nf, st);
-        } else if (rem >= 8) {
-            step = 8;
-            launches += launch_scan_part<8, 1, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, 8, A, ldA, strideQ, NA, NM, f0, nf, st);
-        } else {
-            step = rem < 4 ? rem : 4;
-            launches += launch_scan_part<4, 1, 8, 512, 4, 2>(d_xyz, d_b, d_vs, s, ds, (int)step, A, ldA, strideQ, NA, NM, f0, nf, st);
-        }
-        n0 += step;
+    for (size_t p = 0; p < npass; p++) {
+        const size_t want = (nq - n0 + (npass - p) - 1) / (npass - p);  // even share of what is left
+        int B = (int)((want + 3) / 4) * 4;
+        if (B > 32) B = 32;
+        const size_t valid = std::min<size_t>(B, nq - n0);
+        ScanArgs a{d_xyz, d_b, d_vs, s0 + (double)n0 * ds, ds, (int)valid, d_A + n0 * strideQ, ldA, strideQ, NA, NM, f0, nf, st};
+        launches += scan_dispatch(B, warps, recur, a);
+        n0 += valid;
     }
     return launches;
 }

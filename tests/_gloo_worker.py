@@ -40,6 +40,9 @@ def main():
     if case.startswith("all"):
         p.set("scattering.average.orientation.type", "vectors").set("scattering.average.orientation.vectors.type", "file")
         p.set_vectors(synth.unit_vectors(7, 1))
+    elif case.startswith("scan"):  # >= 8 subvectors: the runner batches the 5 |q| of the scan into one pass
+        p.set("scattering.average.orientation.type", "vectors").set("scattering.average.orientation.vectors.type", "file")
+        p.set_vectors(synth.unit_vectors(9, 1))
     elif case.startswith("self"):
         p.set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
         p.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(3, 1))

@@ -35,7 +35,9 @@ class OracleBackend:
             mpsphere_amplitudes=_host.BE_MP_AMPL(self._mp_amplitudes), mpsphere_dsp_partial=_host.BE_MP_DSP(self._mp_dsp),
             set_frame_window=_host.BE_SET_WINDOW(self._set_window),
             all_vectors_amplitudes=_host.BE_AV_AMPL(self._av_amplitudes),
-            all_vectors_dsp_partial=_host.BE_AV_DSP(self._av_dsp))
+            all_vectors_dsp_partial=_host.BE_AV_DSP(self._av_dsp),
+            compute_all_vectors_scan_partial=_host.BE_AV_SCAN(self._av_scan),
+            all_vectors_scan_amplitudes=_host.BE_AV_SCAN_AMPL(self._av_scan_amplitudes))
         self._cbs = cbs
         self.vtbl = _host.BackendVtbl(**cbs)
 
@@ -77,6 +79,33 @@ class OracleBackend:
         A = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(NM, NFt, 2))
         A[:] = 0
         A[:, f0:f0 + NF] = np.ascontiguousarray(amp).view(np.float64).reshape(NM, NF, 2)
+        return 0
+
+    def _scan_b(self, ctx, NQ, n):
+        return ctx["bq"][n] if "bq" in ctx and len(ctx["bq"]) == NQ else ctx["b"]
+
+    def _av_scan(self, c, v, NM, s0, ds, NQ, dsp, ptr):
+        ctx = self._ctx(c)
+        plen = 2 * ctx["NFt"] + 4
+        for n in range(NQ):
+            p = ptr + n * plen * 8
+            if NM == 0:
+                self._zero(ctx, p)
+                continue
+            qv = (s0 + n * ds) * np.ctypeslib.as_array(v, shape=(NM, 3))
+            fqt, fq, fq2 = o.compute_all_vectors(ctx["xyz"], self._scan_b(ctx, NQ, n), qv, dsp=_DSP[dsp])
+            self._store(ctx, p, fqt, fq, fq2, NM)
+        return 0
+
+    def _av_scan_amplitudes(self, c, v, NM, s0, ds, NQ, out):
+        ctx = self._ctx(c)
+        NFt, f0, NF = ctx["NFt"], ctx["f_first"], ctx["NF"]
+        A = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(NQ, NM, NFt, 2))
+        A[:] = 0
+        for n in range(NQ):
+            qv = (s0 + n * ds) * np.ctypeslib.as_array(v, shape=(NM, 3))
+            *_, amp = o.compute_all_vectors(ctx["xyz"], self._scan_b(ctx, NQ, n), qv, dsp="plain", return_amplitudes=True)
+            A[n, :, f0:f0 + NF] = np.ascontiguousarray(amp).view(np.float64).reshape(NM, NF, 2)
         return 0
 
     def _av_dsp(self, c, amp, m0, mc, dsp, ptr):

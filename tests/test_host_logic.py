@@ -228,6 +228,49 @@ def test_run_scatter_single_rank_oracle_backend(oracle):
     assert "decomposition failed" in str(e.value) or "Insufficient Buffer" in str(e.value)
 
 
+def test_run_scatter_scan_batching(oracle):
+    """AllVectors runner: consecutive q-vectors of a scan (same direction, equal |q| spacing, >= 8 subvectors) are
+    batched into one backend call; a vector that breaks the progression or a different direction ends the batch; the
+    records still arrive one per q-vector, in order, and equal the oracle.  limits.computation.scan=1 disables it."""
+    from oracle_backend import OracleBackend
+    from sassena_b200 import synth
+    be = OracleBackend()
+    NA, NF = 20, 8
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3, offset=-10.0)
+    b = synth.factors(NA)
+    scan = host.create_from_scans([{"base": (1, 2, 0), "from": 0.3, "to": 1.5, "points": 5}])
+    qv = np.concatenate([scan, [[0.0, 0.0, 2.5]], scan[::-1][:2] * 1.7, [[0.0, 0.0, 0.0]]])  # 5 + 1 + 2 + 1 vectors
+
+    def params(**kv):
+        p = host.Params().set("scattering.average.orientation.type", "vectors")
+        p.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(9, 1))
+        for k, v in kv.items():
+            p.set(k.replace("__", "."), v)
+        return p.create()
+
+    p = params()
+    recs, has, tm = host.run_scatter(p, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
+    assert len(recs) == len(qv)
+    # batches: the 5 scan points, then (2.5 z, 1.7*1.5, 1.7*1.2) is no progression -> singles; 2 vectors form the last
+    # candidate batch only if colinear and equally spaced: (1.7*1.5, 1.7*1.2) qualifies; |q| = 0 never does
+    assert tm["sd:c:scan"][1] == 2 and tm["sd:compute"][1] == 2 + 2
+    for r, q in zip(recs, qv):
+        assert np.array_equal(r["q"], q)
+        ref = oracle.compute_all_vectors(xyz, b * (1 + np.linalg.norm(q)), p.init_subvectors(q))
+        assert np.allclose(r["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+        assert np.isclose(r["fq"], ref[1], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+    # cylinder averaging is linear in |q| for a fixed direction: batched too
+    pc = params(scattering__average__orientation__vectors__type="cylinder", scattering__average__orientation__vectors__resolution=11)
+    recs, _, tm = host.run_scatter(pc, xyz, scan, b=b, backend=be.vtbl)
+    assert tm["sd:c:scan"][1] == 1
+    for r, q in zip(recs, scan):
+        ref = oracle.compute_all_vectors(xyz, b, pc.init_subvectors(q))
+        assert np.allclose(r["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+    # switched off
+    recs, _, tm = host.run_scatter(params(limits__computation__scan=1), xyz, scan, b=b, backend=be.vtbl)
+    assert "sd:c:scan" not in tm and tm["sd:compute"][1] == 5 and len(recs) == 5
+
+
 def test_dcd_roundtrip_and_trimming(tmp_path):
     """DCD writer (coordinate_writer.cpp layout) -> reader (frames.cpp:272-436): exact round trip, header fields,
     first/last/stride trimming with the reference's absolute-index stride rule (frames.cpp:224-245)"""

@@ -50,6 +50,8 @@ def _reference(oracle, case):
         ql = np.linalg.norm(q)
         if case.startswith("all"):
             out.append(oracle.compute_all_vectors(xyz, b, ql * synth.unit_vectors(7, 1)))
+        elif case.startswith("scan"):
+            out.append(oracle.compute_all_vectors(xyz, b, ql * synth.unit_vectors(9, 1)))
         elif case.startswith("self"):
             out.append(oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b, ql * synth.unit_vectors(3, 1)))
         else:
@@ -58,7 +60,8 @@ def _reference(oracle, case):
 
 
 @pytest.mark.parametrize("world,case", [(2, "all"), (2, "self"), (2, "mp"), (2, "all_manual1"), (3, "self"),
-                                        (3, "all_manual1"), (2, "all_frames"), (3, "all_frames")])
+                                        (3, "all_manual1"), (2, "all_frames"), (3, "all_frames"), (2, "scan"), (2, "scan_frames"),
+                                        (3, "scan_frames")])
 def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
     gathered = _run(world, case, tmp_path)
     qv, ref = _reference(oracle, case)
@@ -68,6 +71,7 @@ def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
         assert has, "no spare ranks expected in these cases"
         assert "sd:compute" in timer_keys and "sd:stage" in timer_keys
         assert ("sd:c:b:exchange" in timer_keys) == ("_frames" in case)  # amplitude exchange only when frame-sharded
+        assert ("sd:c:scan" in timer_keys) == case.startswith("scan")  # |q| batching needs >= 8 subvectors
         writers += 1 if recs else 0
         for r in recs:
             key = tuple(np.round(r["q"], 12))
