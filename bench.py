@@ -45,18 +45,18 @@ FP64_INSTR_PER_EVAL = 21.0  # what the kernel executes (sincos_qt.cuh
 # both components
 SCAN_SETUP_FLOP, SCAN_STEP_FLOP = 65.0, 6.0    # algorithmic FP64 flop
 SCAN_SETUP_INSTR, SCAN_STEP_INSTR = 49.0, 4.0  # executed FP64-pipe instructions
-SCAN_MAX_PASS = 28                             # amplitude.cu launch_amplitude_scan default
+SCAN_MAX_PASS, SCAN_MAX_PASS_CORR = 28, 16     # amplitude.cu amplitude_scan_max_pass defaults
 
 
 def scan_passes(nq, max_b=SCAN_MAX_PASS):
-    """pass sizes launch_amplitude_scan uses for nq |q| values (multiples of 4, even shares)"""
+    """pass sizes (kernel template B) sgpu_capi.cu plan_scan uses for nq |q| values: even shares, multiples of 4"""
     npass = (nq + max_b - 1) // max_b
     out, n0 = [], 0
     for p in range(npass):
         want = (nq - n0 + (npass - p) - 1) // (npass - p)
-        B = min(32, (want + 3) // 4 * 4)
-        out.append(B)
-        n0 += min(B, nq - n0)
+        L = min(min((want + 3) // 4 * 4, max_b), nq - n0)
+        out.append((L + 3) // 4 * 4)
+        n0 += L
     return out
 
 WORKLOADS = {
@@ -225,11 +225,14 @@ def _run_ours(args, json_fd):
     if args.atoms:
         cfg["NA"] = args.atoms
     NA, NF, NM = cfg["NA"], cfg["NF"], cfg["NM"]
-    qls = synth.qlengths(*cfg["q"])
-    scan = args.mode == "scan"
+    scan = args.mode in ("scan", "scan-rounded")
+    if args.mode == "scan":
+        qls = np.linspace(cfg["q"][0], cfg["q"][1], cfg["q"][2])  # equally spaced |q|: plain scan kernel
+    else:
+        # the reference's scan generator: float-rounded fractions (parameters.cpp:1151), equally spaced to ~1e-8 only;
+        # in scan-rounded mode these take the corrected scan kernel
+        qls = synth.qlengths(*cfg["q"])
     NQ = len(qls) if scan else 1          # |q| values per step
-    s0, ds = float(qls[0]), float(qls[1] - qls[0])
-    assert np.allclose(qls, s0 + ds * np.arange(len(qls)), rtol=1e-13), "the scan path needs equally spaced |q|"
     b = synth.factors(NA)
     u = synth.unit_vectors(NM, cfg["vseed"])
     m_off, m_cnt = div_assignment(world, rank, NM)
@@ -264,14 +267,14 @@ def _run_ours(args, json_fd):
 
     def compute_step(i):
         """one step on `world` GPUs, coordinates already staged: every |q| of the scan (scan mode) or one |q|"""
-        q0 = s0 if scan else float(qls[i % len(qls)])
+        q0 = float(qls[i % len(qls)])
         if world == 1:
             if scan:
-                return ctx.compute_all_vectors_scan(u, q0, ds, NQ)
+                return ctx.compute_all_vectors_scan(u, qls)
             return ctx.compute_all_vectors(q0 * u)
         if by_frames:
             if scan:
-                ctx.all_vectors_scan_amplitudes(u, q0, ds, NQ, amp.data_ptr())
+                ctx.all_vectors_scan_amplitudes(u, qls, amp.data_ptr())
             else:
                 ctx.all_vectors_amplitudes(q0 * u, amp.data_ptr())
             ctx.synchronize()
@@ -280,7 +283,7 @@ def _run_ours(args, json_fd):
             for n in range(NQ):
                 ctx.all_vectors_dsp_partial(amp.data_ptr() + n * NM * NF * 16, m_off, m_cnt, partial.data_ptr() + n * plen * 8)
         elif scan:
-            ctx.compute_all_vectors_scan_partial(u[m_off:m_off + m_cnt], q0, ds, NQ, partial.data_ptr())
+            ctx.compute_all_vectors_scan_partial(u[m_off:m_off + m_cnt], qls, partial.data_ptr())
         else:
             ctx.compute_all_vectors_partial(q0 * u[m_off:m_off + m_cnt], partial.data_ptr())
         ctx.synchronize()
@@ -397,7 +400,7 @@ def _run_ours(args, json_fd):
         ctx.stage_frames_device(xyz.data_ptr(), NF_s, NA)
         ctx.set_factors(b)
         if scan:  # the same kernel as the timed path: the whole scan on the sample, compared at the sampled |q|
-            fqts, fqs, fq2s = ctx.compute_all_vectors_scan(u[:NM_s], s0, ds, len(qls))
+            fqts, fqs, fq2s = ctx.compute_all_vectors_scan(u[:NM_s], qls)
             fqt, fq = fqts[nmid], fqs[nmid]
         else:
             fqt, fq, _ = ctx.compute_all_vectors(ql * u[:NM_s])
@@ -411,11 +414,15 @@ def _run_ours(args, json_fd):
         nf0 = div_assignment(world, 0, NF)[1] if by_frames else NF
         nm0 = NM if (by_frames or world == 1) else div_assignment(world, 0, NM)[1]
         evals_rank = float(NA) * nf0 * nm0 * NQ * args.steps
+        scan_plan = ctx.last_scan_plan() if scan else None
         if scan:
-            passes = scan_passes(NQ)
-            flop_eval = (len(passes) * SCAN_SETUP_FLOP + sum(passes) * SCAN_STEP_FLOP) / NQ
-            instr_eval = (len(passes) * SCAN_SETUP_INSTR + sum(passes) * SCAN_STEP_INSTR) / NQ
-            kernel = "amplitude_scan_kernel"
+            corrected = args.mode == "scan-rounded"
+            passes = scan_passes(NQ, SCAN_MAX_PASS_CORR if corrected else SCAN_MAX_PASS)
+            step_flop = SCAN_STEP_FLOP + (4.0 if corrected else 0.0)    # + D accumulation (2 FMA); E runs on the FP32 pipe
+            step_instr = SCAN_STEP_INSTR + (2.0 if corrected else 0.0)
+            flop_eval = (len(passes) * SCAN_SETUP_FLOP + sum(passes) * step_flop) / NQ
+            instr_eval = (len(passes) * SCAN_SETUP_INSTR + sum(passes) * step_instr) / NQ
+            kernel = "amplitude_scan_kernel" + (" (corrected)" if corrected else "")
         else:
             flop_eval, instr_eval, kernel = FLOP_PER_EVAL, FP64_INSTR_PER_EVAL, "amplitude_all_tiled_kernel"
         achieved = evals_rank * flop_eval / amp_s / 1e12
@@ -436,7 +443,7 @@ def _run_ours(args, json_fd):
                        "step": (f"the whole |q| scan ({NQ} equally spaced |q| x {NM} orientation vectors) over the full "
                                 "trajectory: amplitudes + FFT autocorrelation + average for every |q|" if scan else
                                 "one |q| (compute() of the runner loop): amplitudes + FFT autocorrelation + average"),
-                       "mode": args.mode,
+                       "mode": args.mode, "scan_plan_plain_corrected_single": scan_plan,
                        "parallelism": (f"frame shard x{world} + amplitude all-reduce" if by_frames else
                                        f"q-vector shard x{world}" if world > 1 else "single GPU"),
                        "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
@@ -479,9 +486,10 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override NF (debug; changes the workload)")
     ap.add_argument("--atoms", type=int, default=0, help="override NA (debug; changes the workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle sample, seconds per core")
-    ap.add_argument("--mode", default="scan", choices=["scan", "per-q"],
-                    help="scan: a step is the whole |q| scan through the scan kernel (default); per-q: a step is one |q| "
-                         "through the general kernel")
+    ap.add_argument("--mode", default="scan", choices=["scan", "scan-rounded", "per-q"],
+                    help="scan: a step is the whole scan of equally spaced |q| through the scan kernel (default); "
+                         "scan-rounded: the same with the reference's float-rounded |q| (corrected scan kernel); "
+                         "per-q: a step is one |q| through the general kernel")
     ap.add_argument("--shard", default="frames", choices=["frames", "vectors"],
                     help="N>1: shard the frames (reference decomposition, default) or the subvectors (replicated coordinates)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -157,22 +157,26 @@ int sgpu_all_vectors_amplitudes(sgpu_ctx *ctx, const double *qvecs, size_t NM, d
 int sgpu_all_vectors_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t m_first, size_t m_count, int dsp_type,
                                  double *d_partial);
 /* ---- |q|-scan coherent path ---------------------------------------------------------------------------------------
- * A scan (scattering.vectors.scans, parameters.cpp:1125-1189) evaluates the same orientation vectors at equally spaced
- * |q|: q_{n,m} = (s0 + n ds) v_m, n < NQ (init_subvectors scales unit vectors by |q| for sphere/file vectors and the
- * cylinder construction is linear in |q| for a fixed direction, abstract_vectors_scatter_device.cpp:96-175).  The phases
- * of one (atom, v_m) pair then form an arithmetic progression and NQ amplitudes cost two sincos evaluations plus NQ-1
- * complex rotations.  Results are those of NQ sgpu_compute_all_vectors calls with q = (s0 + n ds) v (to ~1e-14).
- * Factors: sgpu_set_factors (same b for every |q|) or sgpu_set_factors_batch(b[NQ][NA]); if the rows of a batch differ
- * the general kernel runs once per |q| (same results, no rotation shortcut).
- * v: host [NM][3] direction vectors (not pre-scaled).  Outputs are NQ consecutive blocks laid out like the single-|q|
+ * A scan (scattering.vectors.scans, parameters.cpp:1125-1189) evaluates the same orientation vectors at many |q|:
+ * q_{n,m} = s_n v_m, n < NQ (init_subvectors scales unit vectors by |q| for sphere/file vectors and the cylinder
+ * construction is linear in |q| for a fixed direction, abstract_vectors_scatter_device.cpp:96-175).  For equally spaced
+ * s_n the phases of one (atom, v_m) pair form an arithmetic progression, and a pass of up to 28 |q| costs two sincos
+ * evaluations plus a 3-term recurrence instead of one sincos per |q|.  The reference builds scans from FLOAT-rounded
+ * fractions (parameters.cpp:1151), so real scans deviate from a progression by ~1e-8 relative: those take a corrected
+ * kernel (first-order term in FP64, second-order term in FP32, exact to ~1e-13).  Any other spacing, and |q|-dependent
+ * factors whose rows differ, are evaluated one |q| at a time by the general kernel — the call is valid for any s.
+ * Results equal NQ sgpu_compute_all_vectors calls with q = s_n v (to ~1e-13 relative).
+ * Factors: sgpu_set_factors (same b for every |q|) or sgpu_set_factors_batch(b[NQ][NA]).
+ * v: host [NM][3] direction vectors; s: host [NQ].  Outputs are NQ consecutive blocks laid out like the single-|q|
  * calls: atfinal [NQ][NF][2], afinal/a2final [NQ][2], d_partials NQ packed partials, d_amp [NQ][NM][NF_total] complex. */
-int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ, int dsp_type,
+int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, int dsp_type,
                                   int dsp_method, double *atfinal, double *afinal, double *a2final);
-int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t NM_local, double s0, double ds, size_t NQ,
+int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t NM_local, const double *s, size_t NQ,
                                           int dsp_type, double *d_partials);
 /* frame-window aware (see sgpu_set_frame_window); follow with sgpu_all_vectors_dsp_partial per |q| plane */
-int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ,
-                                     double *d_amp);
+int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, double *d_amp);
+/* how the last scan call was evaluated: passes of the plain / corrected scan kernel, |q| values sent to the general kernel */
+int sgpu_last_scan_plan(const sgpu_ctx *ctx, int *plain, int *corrected, int *single);
 /* scale = 1/NM_total (vectors) or 1/(4 pi) (multipole sphere). */
 int sgpu_finalize(sgpu_ctx *ctx, const double *d_partial, int dsp_type, int dsp_method, double scale,
                   double *atfinal, double afinal[2], double a2final[2]);

@@ -58,8 +58,8 @@ typedef struct sass_backend_vtbl {
     int (*all_vectors_amplitudes)(sgpu_ctx *, const double *, size_t, double *);
     int (*all_vectors_dsp_partial)(sgpu_ctx *, const double *, size_t, size_t, int, double *);
     /* |q|-scan coherent path */
-    int (*compute_all_vectors_scan_partial)(sgpu_ctx *, const double *, size_t, double, double, size_t, int, double *);
-    int (*all_vectors_scan_amplitudes)(sgpu_ctx *, const double *, size_t, double, double, size_t, double *);
+    int (*compute_all_vectors_scan_partial)(sgpu_ctx *, const double *, size_t, const double *, size_t, int, double *);
+    int (*all_vectors_scan_amplitudes)(sgpu_ctx *, const double *, size_t, const double *, size_t, double *);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);

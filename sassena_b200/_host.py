@@ -39,8 +39,8 @@ BE_MP_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
 BE_SET_WINDOW = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_size_t)
 BE_AV_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_void_p)
 BE_AV_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p)
-BE_AV_SCAN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_double, C.c_double, C.c_size_t, C.c_int, C.c_void_p)
-BE_AV_SCAN_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_double, C.c_double, C.c_size_t, C.c_void_p)
+BE_AV_SCAN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_int, C.c_void_p)
+BE_AV_SCAN_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_void_p)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 

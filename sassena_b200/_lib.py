@@ -46,13 +46,14 @@ SIGNATURES = {
     "sgpu_set_frame_window": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_all_vectors_amplitudes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_void_p]),
     "sgpu_all_vectors_dsp_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
-    "sgpu_compute_all_vectors_scan": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_double, C.c_double,
+    "sgpu_compute_all_vectors_scan": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double),
                                                C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double),
                                                C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-    "sgpu_compute_all_vectors_scan_partial": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_double,
-                                                       C.c_double, C.c_size_t, C.c_int, C.c_void_p]),
-    "sgpu_all_vectors_scan_amplitudes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_double, C.c_double,
+    "sgpu_compute_all_vectors_scan_partial": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t,
+                                                       C.POINTER(C.c_double), C.c_size_t, C.c_int, C.c_void_p]),
+    "sgpu_all_vectors_scan_amplitudes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double),
                                                   C.c_size_t, C.c_void_p]),
+    "sgpu_last_scan_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sgpu_mpsphere_dsp_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
     "sgpu_partial_len": (C.c_int, [C.c_void_p, C.c_int, c_size_p]),
     "sgpu_compute_all_vectors_partial": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p]),

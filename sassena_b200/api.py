@@ -233,25 +233,33 @@ class ScatterContext:
         self._ck(self.lib.sgpu_all_vectors_dsp_partial(self.h, C.c_void_p(d_amp), int(m_first), int(m_count), _dsp(dsp),
                                                        C.c_void_p(d_partial)))
 
-    # -- |q|-scan coherent path: q_{n,m} = (s0 + n ds) v_m
-    def compute_all_vectors_scan(self, v, s0, ds, NQ, dsp="autocorrelate", method="fftw"):
-        """Returns (fqt [NQ][NF] complex, fq [NQ] complex, fq2 [NQ] complex)."""
+    # -- |q|-scan coherent path: q_{n,m} = s_n v_m
+    def compute_all_vectors_scan(self, v, s, dsp="autocorrelate", method="fftw"):
+        """v: directions [NM][3]; s: |q| values [NQ].  Returns (fqt [NQ][NF] complex, fq [NQ] complex, fq2 [NQ] complex)."""
         v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
-        NF = self.timeline_frames
+        s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1)
+        NF, NQ = self.timeline_frames, len(s)
         at, af, a2f = np.zeros((NQ, 2 * NF)), np.zeros((NQ, 2)), np.zeros((NQ, 2))
-        self._ck(self.lib.sgpu_compute_all_vectors_scan(self.h, _dp(v), len(v), float(s0), float(ds), int(NQ), _dsp(dsp),
-                                                        _method(method), _dp(at), _dp(af), _dp(a2f)))
+        self._ck(self.lib.sgpu_compute_all_vectors_scan(self.h, _dp(v), len(v), _dp(s), NQ, _dsp(dsp), _method(method),
+                                                        _dp(at), _dp(af), _dp(a2f)))
         return at.view(np.complex128).copy(), af.view(np.complex128)[:, 0].copy(), a2f.view(np.complex128)[:, 0].copy()
 
-    def compute_all_vectors_scan_partial(self, v, s0, ds, NQ, d_partials: int, dsp="autocorrelate"):
+    def compute_all_vectors_scan_partial(self, v, s, d_partials: int, dsp="autocorrelate"):
         v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
-        self._ck(self.lib.sgpu_compute_all_vectors_scan_partial(self.h, _dp(v), len(v), float(s0), float(ds), int(NQ),
-                                                                _dsp(dsp), C.c_void_p(d_partials)))
+        s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1)
+        self._ck(self.lib.sgpu_compute_all_vectors_scan_partial(self.h, _dp(v), len(v), _dp(s), len(s), _dsp(dsp),
+                                                                C.c_void_p(d_partials)))
 
-    def all_vectors_scan_amplitudes(self, v, s0, ds, NQ, d_amp: int):
+    def all_vectors_scan_amplitudes(self, v, s, d_amp: int):
         v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
-        self._ck(self.lib.sgpu_all_vectors_scan_amplitudes(self.h, _dp(v), len(v), float(s0), float(ds), int(NQ),
-                                                           C.c_void_p(d_amp)))
+        s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1)
+        self._ck(self.lib.sgpu_all_vectors_scan_amplitudes(self.h, _dp(v), len(v), _dp(s), len(s), C.c_void_p(d_amp)))
+
+    def last_scan_plan(self):
+        """(plain scan passes, corrected scan passes, |q| values through the general kernel) of the last scan call"""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.sgpu_last_scan_plan(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def partial_len(self, dsp="autocorrelate") -> int:
         n = C.c_size_t()

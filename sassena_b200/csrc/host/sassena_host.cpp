@@ -691,52 +691,49 @@ void AllVectorsScatterDevice::compute() {
     reduce_and_finalize(dsp, 1.0 / subvector_index_.size());  // factor = 1/NM (:355-360)
 }
 
-// Longest run of q-vectors starting at `first` that forms a scan: subvectors(q_n) = (s0 + n ds) v_m for all n, m.
+// Longest run of q-vectors starting at `first` that shares its directions: subvectors(q_n) = |q_n| v_m for all n, m.
 // Verified numerically on the subvectors the reference's init_subvectors produces, so every orientation type
-// (sphere, file, cylinder, none) qualifies exactly when it has that structure.  Returns 1 when there is none.
-size_t AllVectorsScatterDevice::scan_length(size_t first, std::vector<double> &v, double &s0, double &ds) {
+// (sphere, file, cylinder, none) qualifies exactly when it has that structure; the spacing of the |q_n| is the
+// backend's business.  Returns 1 when there is no such run.
+size_t AllVectorsScatterDevice::scan_length(size_t first, std::vector<double> &v, std::vector<double> &s) {
     const size_t maxn = std::min<size_t>(params_.limits.coherent_scan, vectors_.size() - first);
-    if (maxn < 2) return 1;
-    CartesianCoor3D q0 = vectors_[first], q1 = vectors_[first + 1];
-    s0 = q0.length();
-    const double s1 = q1.length();
-    ds = s1 - s0;
-    if (s0 <= 0.0 || s1 <= 0.0 || ds == 0.0) return 1;
-    init_subvectors(q1);
+    if (maxn < 4) return 1;  // a pass pays for two sincos per direction: not worth it below 4 |q|
+    CartesianCoor3D q0 = vectors_[first];
+    const double s0 = q0.length();
+    if (s0 <= 0.0) return 1;
+    init_subvectors(q0);
     const size_t nm = NM;
     if (nm < 8) return 1;  // a CTA serves 8-12 directions; below that the per-|q| kernel is the better fit
-    std::vector<CartesianCoor3D> sub1 = subvector_index_;
     v.resize(3 * nm);
     for (size_t m = 0; m < nm; m++) {
-        v[3 * m] = sub1[m].x / s1;
-        v[3 * m + 1] = sub1[m].y / s1;
-        v[3 * m + 2] = sub1[m].z / s1;
+        v[3 * m] = subvector_index_[m].x / s0;
+        v[3 * m + 1] = subvector_index_[m].y / s0;
+        v[3 * m + 2] = subvector_index_[m].z / s0;
     }
-    auto fits = [&](size_t n) {
-        CartesianCoor3D qn = vectors_[first + n];
-        const double sn = s0 + (double)n * ds;
-        if (sn <= 0.0 || std::fabs(qn.length() - sn) > 1e-13 * std::fabs(sn)) return false;
-        init_subvectors(qn);
-        if (NM != nm) return false;
-        const double tol = 4e-16 * std::fabs(sn) * 8;
-        for (size_t m = 0; m < nm; m++) {
-            const CartesianCoor3D &s = subvector_index_[m];
-            if (std::fabs(s.x - sn * v[3 * m]) > tol || std::fabs(s.y - sn * v[3 * m + 1]) > tol ||
-                std::fabs(s.z - sn * v[3 * m + 2]) > tol)
-                return false;
-        }
-        return true;
-    };
-    if (!fits(0)) return 1;
-    size_t n = 2;
-    while (n < maxn && fits(n)) n++;
+    s.assign(1, s0);
     // device memory for the amplitudes of the batch: at most ~1/8 of the coordinate budget
     const size_t per_q = nm * NF * 2 * sizeof(double);
     const size_t cap = std::max<size_t>(1, (params_.limits.stage_memory_data / 8) / std::max<size_t>(per_q, 1));
-    return std::min(n, cap);
+    for (size_t n = 1; n < maxn && n < cap; n++) {
+        CartesianCoor3D qn = vectors_[first + n];
+        const double sn = qn.length();
+        if (sn <= 0.0) break;
+        init_subvectors(qn);
+        if (NM != nm) break;
+        const double tol = 4e-15 * sn;
+        bool ok = true;
+        for (size_t m = 0; m < nm && ok; m++) {
+            const CartesianCoor3D &sv = subvector_index_[m];
+            ok = std::fabs(sv.x - sn * v[3 * m]) <= tol && std::fabs(sv.y - sn * v[3 * m + 1]) <= tol &&
+                 std::fabs(sv.z - sn * v[3 * m + 2]) <= tol;
+        }
+        if (!ok) break;
+        s.push_back(sn);
+    }
+    return s.size() >= 4 ? s.size() : 1;
 }
 
-void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> &v, double s0, double ds) {
+void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> &v, const std::vector<double> &s) {
     const size_t nm = v.size() / 3;
     NM = nm;
     timer_.start("sd:c:init");
@@ -772,7 +769,7 @@ void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> 
             amp_cap_ = amp_len;
         }
         timer_.start("sd:c:block");
-        ck(be_.all_vectors_scan_amplitudes(ctx_, v.data(), nm, s0, ds, nq, d_amp_), "sgpu_all_vectors_scan_amplitudes");
+        ck(be_.all_vectors_scan_amplitudes(ctx_, v.data(), nm, s.data(), nq, d_amp_), "sgpu_all_vectors_scan_amplitudes");
         timer_.stop("sd:c:block");
         timer_.start("sd:c:wait");
         ck(be_.synchronize(ctx_), "sgpu_synchronize");
@@ -787,7 +784,7 @@ void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> 
         timer_.stop("sd:c:b:dspstore");
     } else {
         timer_.start("sd:c:block");
-        ck(be_.compute_all_vectors_scan_partial(ctx_, v.data() + 3 * mine.offset(), mine.size(), s0, ds, nq, dsp, d_partial_),
+        ck(be_.compute_all_vectors_scan_partial(ctx_, v.data() + 3 * mine.offset(), mine.size(), s.data(), nq, dsp, d_partial_),
            "sgpu_compute_all_vectors_scan_partial");
         timer_.stop("sd:c:block");
     }
@@ -811,10 +808,9 @@ void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> 
 }
 
 void AllVectorsScatterDevice::runner() {
-    std::vector<double> v;
+    std::vector<double> v, s;
     while (status() == 0) {
-        double s0 = 0, ds = 0;
-        const size_t nq = scan_length(current_vector_, v, s0, ds);
+        const size_t nq = scan_length(current_vector_, v, s);
         if (nq < 2) {
             timer_.start("sd:compute");
             compute();
@@ -827,7 +823,7 @@ void AllVectorsScatterDevice::runner() {
         }
         timer_.start("sd:compute");
         timer_.start("sd:c:scan");
-        compute_scan(nq, v, s0, ds);
+        compute_scan(nq, v, s);
         timer_.stop("sd:c:scan");
         timer_.stop("sd:compute");
         for (size_t n = 0; n < nq; n++) {

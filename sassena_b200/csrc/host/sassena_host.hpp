@@ -380,11 +380,12 @@ class AllVectorsScatterDevice : public AbstractVectorsScatterDevice {
     void compute() override;
     void compute_frame_sharded();
     // |q|-scan batching of the runner loop (abstract_scatter_device.cpp:162-173): consecutive q-vectors whose
-    // subvectors are (s0 + n ds) v_m for common directions v_m are evaluated in one pass (two sincos + rotations per
-    // (atom, direction) instead of one sincos per |q|; include/sassena_b200.h "|q|-scan coherent path")
+    // subvectors are s_n v_m for common directions v_m go to the backend in one call, which evaluates (nearly) equally
+    // spaced |q| with two sincos + a recurrence per (atom, direction) instead of one sincos per |q|
+    // (include/sassena_b200.h "|q|-scan coherent path")
     void runner() override;
-    size_t scan_length(size_t first, std::vector<double> &v, double &s0, double &ds);
-    void compute_scan(size_t nq, const std::vector<double> &v, double s0, double ds);
+    size_t scan_length(size_t first, std::vector<double> &v, std::vector<double> &s);
+    void compute_scan(size_t nq, const std::vector<double> &v, const std::vector<double> &s);
     std::vector<std::vector<double>> batch_atfinal_;
     std::vector<std::complex<double>> batch_afinal_, batch_a2final_;
     size_t scans_ = 0;  // number of batched passes taken (diagnostics / tests)

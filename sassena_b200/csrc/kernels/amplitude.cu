@@ -274,11 +274,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
 // steps the accumulated relative error is <= ~2 B ulp (7e-15), far inside the 1e-9 tolerance.
 // One warp owns VPT orientation vectors, lanes stride over the atoms of the tile, every thread keeps B x VPT complex
 // accumulators in registers.  Same TMA ring as the tiled kernel.  A is [B][NM][ldA] (strideQ between |q| planes).
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0>
+struct ScanKappa {
+    double k[32];  // (pi/2) * (s_n - (s0 + n ds)): first/second-order phase correction per |q| of the pass (CORR)
+};
+
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ vs, double s0, double ds,
     double2 *__restrict__ A, size_t ldA, size_t strideQ, int NA, int NM, int nq_valid, unsigned ngroups, size_t f0,
-    int use_bulk) {
+    int use_bulk, const ScanKappa kap) {
+    static_assert(!CORR || (RECUR && VPT == 1), "the corrected variant is built on the recurrence form, one direction per warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_xyz = reinterpret_cast<float *>(smem_raw);                                  // [STAGES][TILE*3]
     double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);  // [STAGES][TILE]
@@ -328,6 +333,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     const bool active = m0 < NM;
     double vx[VPT], vy[VPT], vz[VPT];
     double re[VPT][B], im[VPT][B];
+    // CORR: |q| values that deviate from the arithmetic progression by e_n (the reference builds scans from float-rounded
+    // fractions, parameters.cpp:1151).  exp(i (s_n + e_n) sigma) = z_n (1 + i th - th^2/2 + O(th^3)), th = kap_n sigma:
+    // first order needs D_n = sum b sigma z_n (FP64), second order E_n = sum b sigma^2 z_n, whose weight kap^2/2 is
+    // ~1e-10, so an FP32 copy of the recurrence on the FP32 pipe is accurate enough (and free: the FP64 pipe is the bound).
+    double dre[CORR ? B : 1], dim[CORR ? B : 1];
+    float ere[CORR ? B : 1], eim[CORR ? B : 1];
+    if (CORR) {
+#pragma unroll
+        for (int n = 0; n < B; n++) {
+            dre[n] = 0.0;
+            dim[n] = 0.0;
+            ere[n] = 0.f;
+            eim[n] = 0.f;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < VPT; k++) {
         vx[k] = __ldg(&vs[3 * (m0 + k)]);  // vs is zero padded past NM
@@ -377,8 +397,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                         // after B steps the error is <= ~B^2/2 ulp of |z| (B = 32: 6e-14) for every d, including d -> 0.
                         const double c2 = cw + cw;
                         double pr = zr, pi = zi;  // z_{n-1}
+                        float fpr = 0.f, fpi = 0.f, fzr = 0.f, fzi = 0.f, fc2 = 0.f, fs2 = 0.f;
                         re[k][0] += zr;
                         im[k][0] += zi;
+                        if (CORR) {
+                            dre[0] = fma(sigma, zr, dre[0]);
+                            dim[0] = fma(sigma, zi, dim[0]);
+                            const float fs = (float)sigma;
+                            fs2 = fs * fs;
+                            fpr = (float)zr;
+                            fpi = (float)zi;
+                            fc2 = (float)c2;
+                            ere[0] = fmaf(fs2, fpr, ere[0]);
+                            eim[0] = fmaf(fs2, fpi, eim[0]);
+                        }
                         if (B > 1) {
                             const double t1 = zi * sw, t2 = zi * cw;
                             const double nr = fma(zr, cw, -t1);
@@ -386,6 +418,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                             zr = nr;
                             re[k][1] += zr;
                             im[k][1] += zi;
+                            if (CORR) {
+                                dre[1] = fma(sigma, zr, dre[1]);
+                                dim[1] = fma(sigma, zi, dim[1]);
+                                fzr = (float)zr;
+                                fzi = (float)zi;
+                                ere[1] = fmaf(fs2, fzr, ere[1]);
+                                eim[1] = fmaf(fs2, fzi, eim[1]);
+                            }
                         }
 #pragma unroll
                         for (int n = 2; n < B; n++) {
@@ -397,6 +437,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                             zi = ni;
                             re[k][n] += zr;
                             im[k][n] += zi;
+                            if (CORR) {
+                                dre[n] = fma(sigma, zr, dre[n]);
+                                dim[n] = fma(sigma, zi, dim[n]);
+                                const float fnr = fmaf(fc2, fzr, -fpr), fni = fmaf(fc2, fzi, -fpi);
+                                fpr = fzr;
+                                fpi = fzi;
+                                fzr = fnr;
+                                fzi = fni;
+                                ere[n] = fmaf(fs2, fzr, ere[n]);
+                                eim[n] = fmaf(fs2, fzi, eim[n]);
+                            }
                         }
                     }
                 }
@@ -406,6 +457,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
     }
     if (!active) return;
+    if (CORR) {
+        // fold the corrections into the lane sums before the warp reduction
+#pragma unroll
+        for (int n = 0; n < B; n++) {
+            const double kn = kap.k[n], hk = 0.5 * kn * kn;
+            re[0][n] = fma(-hk, (double)ere[n], fma(-kn, dim[n], re[0][n]));
+            im[0][n] = fma(-hk, (double)eim[n], fma(kn, dre[n], im[0][n]));
+        }
+    }
 #pragma unroll
     for (int k = 0; k < VPT; k++) {
 #pragma unroll
@@ -868,13 +928,14 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
 }
 
 namespace {
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0>
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0>
 int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq_valid,
-                     double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+                     double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st,
+                     const ScanKappa &kap = ScanKappa()) {
     const unsigned per_cta = VPT * WARPS;
     const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
-    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB, RECUR>;
+    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB, RECUR, CORR>;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -887,7 +948,7 @@ int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, 
     for (size_t done = 0; done < nf;) {
         size_t cnt = nf - done < max_frames ? nf - done : max_frames;
         kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_vs, s0, ds, d_A, ldA, strideQ, (int)NA,
-                                                                  (int)NM, nq_valid, ngroups, f0 + done, use_bulk);
+                                                                  (int)NM, nq_valid, ngroups, f0 + done, use_bulk, kap);
         launches++;
         done += cnt;
     }
@@ -907,12 +968,13 @@ struct ScanArgs {
     double2 *A;
     size_t ldA, strideQ, NA, NM, f0, nf;
     cudaStream_t st;
+    ScanKappa kap;
 };
 
-template <int B, int WARPS, int MINB, int RECUR>
+template <int B, int WARPS, int MINB, int RECUR, int CORR = 0>
 int scan_pass(const ScanArgs &a) {
-    return launch_scan_part<B, 1, WARPS, 512, 4, MINB, RECUR>(a.d_xyz, a.d_b, a.d_vs, a.s, a.ds, a.valid, a.A, a.ldA, a.strideQ,
-                                                              a.NA, a.NM, a.f0, a.nf, a.st);
+    return launch_scan_part<B, 1, WARPS, 512, 4, MINB, RECUR, CORR>(a.d_xyz, a.d_b, a.d_vs, a.s, a.ds, a.valid, a.A, a.ldA,
+                                                                    a.strideQ, a.NA, a.NM, a.f0, a.nf, a.st, a.kap);
 }
 
 // one pass over `B` |q| values (B in 4, 8, ..., 32); warps = 8 or 12 per CTA
@@ -949,31 +1011,51 @@ int scan_dispatch(int B, int warps, int recur, const ScanArgs &a) {
         default: return scan_pass<32, 8, 1, 1>(a);
     }
 }
+
+// corrected variant: three accumulator sets per |q| (A, D in FP64, E in FP32), so passes are shorter
+int scan_dispatch_corr(int B, int warps, const ScanArgs &a) {
+    if (warps == 12) {
+        switch (B) {
+            case 4: return scan_pass<4, 12, 1, 1, 1>(a);
+            case 8: return scan_pass<8, 12, 1, 1, 1>(a);
+            default: return scan_pass<12, 12, 1, 1, 1>(a);
+        }
+    }
+    switch (B) {
+        case 4: return scan_pass<4, 8, 1, 1, 1>(a);
+        case 8: return scan_pass<8, 8, 1, 1, 1>(a);
+        case 12: return scan_pass<12, 8, 1, 1, 1>(a);
+        case 16: return scan_pass<16, 8, 1, 1, 1>(a);
+        default: return scan_pass<20, 8, 1, 1, 1>(a);
+    }
+}
 }  // namespace
 
 // d_vs padding: a multiple of the directions per CTA (8 or 12 warps, one direction each)
 int amplitude_scan_qpad() { return 24; }
 
-int launch_amplitude_scan(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, size_t nq,
-                          double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf,
-                          cudaStream_t st) {
-    if (nf == 0 || NM == 0 || nq == 0) return 0;
-    static const int maxB = env_int("SASSENA_SCAN_B", 28), warps = env_int("SASSENA_SCAN_WARPS", 12),
-                     recur = env_int("SASSENA_SCAN_RECUR", 1);
-    int launches = 0;
-    // passes of equal size (a multiple of 4, at most maxB): e.g. 50 |q| -> 28 + 24 (2 masked) rather than 24 + 24 + 4
-    const size_t npass = (nq + maxB - 1) / maxB;
-    size_t n0 = 0;
-    for (size_t p = 0; p < npass; p++) {
-        const size_t want = (nq - n0 + (npass - p) - 1) / (npass - p);  // even share of what is left
-        int B = (int)((want + 3) / 4) * 4;
-        if (B > 32) B = 32;
-        const size_t valid = std::min<size_t>(B, nq - n0);
-        ScanArgs a{d_xyz, d_b, d_vs, s0 + (double)n0 * ds, ds, (int)valid, d_A + n0 * strideQ, ldA, strideQ, NA, NM, f0, nf, st};
-        launches += scan_dispatch(B, warps, recur, a);
-        n0 += valid;
+// largest pass (|q| values evaluated by one launch) of the plain / corrected scan kernel
+int amplitude_scan_max_pass(int corrected) {
+    static const int plain = std::min(32, std::max(4, env_int("SASSENA_SCAN_B", 28)));
+    static const int corr = std::min(20, std::max(4, env_int("SASSENA_SCAN_CORR_B", 16)));
+    return corrected ? corr : plain;
+}
+
+int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
+                               const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
+                               size_t f0, size_t nf, cudaStream_t st) {
+    if (nf == 0 || NM == 0 || nq <= 0) return 0;
+    static const int warps = env_int("SASSENA_SCAN_WARPS", 12), recur = env_int("SASSENA_SCAN_RECUR", 1),
+                     cwarps = env_int("SASSENA_SCAN_CORR_WARPS", 8);
+    int B = ((nq + 3) / 4) * 4;
+    ScanArgs a{d_xyz, d_b, d_vs, s0, ds, nq, d_A, ldA, strideQ, NA, NM, f0, nf, st, ScanKappa()};
+    if (kappa) {
+        if (B > 20 || (cwarps == 12 && B > 12)) return -1;
+        for (int n = 0; n < 32; n++) a.kap.k[n] = n < nq ? kappa[n] : 0.0;
+        return scan_dispatch_corr(B, cwarps, a);
     }
-    return launches;
+    if (B > 32) return -1;
+    return scan_dispatch(B, warps, recur, a);
 }
 
 int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,
@@ -1033,6 +1115,26 @@ int launch_copy_words(void *d_dst, const void *mapped_src, size_t nwords, cudaSt
     unsigned blocks = (unsigned)std::min<size_t>((nwords + 255) / 256, 592);
     copy_words_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_dst),
                                                reinterpret_cast<const uint32_t *>(mapped_src), nwords);
+    return 1;
+}
+
+namespace {
+// max |x| over a float buffer: non-negative floats order like their bit patterns, so an integer atomicMax does it
+__global__ void max_abs_kernel(const float *__restrict__ x, size_t n, unsigned *__restrict__ out) {
+    float m = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(&x[i])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+}  // namespace
+
+int launch_max_abs(const float *d_x, size_t n, float *d_out, cudaStream_t st) {
+    cudaMemsetAsync(d_out, 0, sizeof(float), st);
+    if (n == 0) return 0;
+    unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+    max_abs_kernel<<<blocks, 256, 0, st>>>(d_x, n, reinterpret_cast<unsigned *>(d_out));
     return 1;
 }
 

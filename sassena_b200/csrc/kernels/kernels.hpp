@@ -14,12 +14,18 @@ int amplitude_all_qpad();
 int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
                          size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st);
 // K2: per-atom timelines a[(n*NM+m)][t] = b_n exp(i q_m . r_n(t)) for local atoms [n0, n0+nn).
-// |q|-scan amplitudes: q_{n,m} = (s0 + n ds) v_m for n < nq.  d_vs: [NMpad][3] direction vectors pre-scaled by 2/pi,
-// zero padded to a multiple of amplitude_scan_qpad().  d_A: [nq][NM][ldA] with strideQ entries between |q| planes.
+// |q|-scan amplitudes, one pass: q_{n,m} = (s0 + n ds) v_m for n < nq (nq <= amplitude_scan_max_pass()).
+// d_vs: [NMpad][3] direction vectors pre-scaled by 2/pi, zero padded to a multiple of amplitude_scan_qpad().
+// kappa (host, [nq], may be NULL): (pi/2) * (s_n - (s0 + n ds)) for |q| values that are only approximately equally
+// spaced; selects the corrected kernel (exact to third order in kappa_n * sigma).
+// d_A: [nq][NM][ldA] with strideQ entries between |q| planes.  Returns the launch count, -1 if nq is too large.
 int amplitude_scan_qpad();
-int launch_amplitude_scan(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, size_t nq,
-                          double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf,
-                          cudaStream_t st);
+int amplitude_scan_max_pass(int corrected);
+int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
+                               const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
+                               size_t f0, size_t nf, cudaStream_t st);
+// max over the buffer of |x| (n floats); result in *d_out (float, device)
+int launch_max_abs(const float *d_x, size_t n, float *d_out, cudaStream_t st);
 int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,
                           size_t ldA, size_t NF, size_t NM, size_t n0, size_t nn, cudaStream_t st);
 // cart -> (r, phi, theta), in place, n points

@@ -58,6 +58,9 @@ struct sgpu_ctx {
     double *d_bq = nullptr;     // per-|q| factors [NQ][NA] (sgpu_set_factors_batch)
     size_t bq_cap = 0, bq_nq = 0, bq_n = 0;
     bool bq_uniform = false;    // every |q| row of the batch holds the same factors
+    double rmax = 0.0;          // bound of |r| over the staged coordinates (ensure_rmax)
+    bool rmax_valid = false;
+    int scan_kinds[3] = {0, 0, 0};
     std::vector<double> h_qs;
 
     double2 *d_A = nullptr;
@@ -190,6 +193,7 @@ int release_xyz(sgpu_ctx *ctx) {
         ctx->xyz_cap = 0;
     }
     ctx->mode = 0;
+    ctx->rmax_valid = false;
     return SGPU_OK;
 }
 
@@ -719,12 +723,88 @@ int sgpu_all_vectors_dsp_partial(sgpu_ctx *ctx, const double *d_amp, size_t m_fi
 /* ---- |q|-scan coherent path ------------------------------------------------------------------------------------ */
 
 namespace {
-// amplitudes of NQ equally spaced |q| along fixed directions into A[NQ][NM][NFt] (this rank's frame columns)
-int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t NM, double s0, double ds, size_t NQ,
-                         double2 *A) {
+// bound of |r| over the staged coordinates (sqrt(3) * max |component|), computed once per staging
+int ensure_rmax(sgpu_ctx *ctx) {
+    if (ctx->rmax_valid) return SGPU_OK;
+    CK(cudaStreamSynchronize(ctx->copy_stream));  // every staging chunk has to be resident
+    drop_chunks(ctx);
+    float *d_m = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void **>(&d_m), sizeof(float)));
+    ctx->launches += launch_max_abs(ctx->d_xyz, ctx->NF * ctx->NA * 3, d_m, ctx->stream);
+    float m = 0.f;
+    cudaError_t e = cudaMemcpyAsync(&m, d_m, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_m);
+    CK(e);
+    ctx->rmax = 1.7320508075688772 * (double)m;
+    ctx->rmax_valid = true;
+    return SGPU_OK;
+}
+
+struct ScanPass {
+    size_t n0;
+    int nq;
+    double s0, ds;
+    int kind;  // 0 plain scan kernel, 1 corrected scan kernel, 2 general kernel per |q|
+    std::vector<double> kappa;
+};
+
+// Splits NQ |q| values into kernel passes.  Exactly equally spaced values take the plain scan kernel; values within a
+// small deviation of a progression (the reference builds scans from float-rounded fractions, parameters.cpp:1151) take
+// the corrected kernel as long as the neglected third-order phase term (kappa sigma)^3/6 stays below ~5e-12; anything
+// else is evaluated one |q| at a time by the general kernel.
+int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, std::vector<ScanPass> &plan) {
+    plan.clear();
+    auto fit = [&](size_t n0, size_t L, double &s0, double &ds, double &epsmax) {
+        s0 = s[n0];
+        ds = L > 1 ? (s[n0 + L - 1] - s[n0]) / (double)(L - 1) : 0.0;
+        epsmax = 0.0;
+        for (size_t n = 0; n < L; n++) epsmax = std::max(epsmax, std::fabs(s[n0 + n] - (s0 + (double)n * ds)));
+    };
+    double smax = 0.0;
+    for (size_t n = 0; n < NQ; n++) smax = std::max(smax, std::fabs(s[n]));
+    double s0, ds, eps;
+    fit(0, NQ, s0, ds, eps);
+    const bool exact = eps <= 4.5e-16 * smax;
+    if (getenv("SASSENA_SCAN_DISABLE") || NQ < 3) {
+        for (size_t n = 0; n < NQ; n++) plan.push_back(ScanPass{n, 1, s[n], 0.0, 2, {}});
+        return SGPU_OK;
+    }
+    const bool force_corr = getenv("SASSENA_SCAN_FORCE_CORR") != nullptr;
+    const size_t maxB = (size_t)amplitude_scan_max_pass((exact && !force_corr) ? 0 : 1);
+    if (!exact || force_corr) {
+        int rc = ensure_rmax(ctx);
+        if (rc) return rc;
+    }
+    const size_t npass = (NQ + maxB - 1) / maxB;
+    size_t n0 = 0;
+    for (size_t p = 0; p < npass; p++) {
+        const size_t want = (NQ - n0 + (npass - p) - 1) / (npass - p);  // even share of what is left
+        size_t L = std::min<size_t>(std::min<size_t>(((want + 3) / 4) * 4, maxB), NQ - n0);
+        if (exact && !force_corr) {
+            plan.push_back(ScanPass{n0, (int)L, s[0] + (double)n0 * ds, ds, 0, {}});
+        } else {
+            double ps0, pds, peps;
+            fit(n0, L, ps0, pds, peps);
+            const double theta = peps * vmax * ctx->rmax;  // largest phase deviation in radians
+            if (L >= 3 && theta <= 3e-4) {
+                ScanPass sp{n0, (int)L, ps0, pds, 1, {}};
+                for (size_t n = 0; n < L; n++) sp.kappa.push_back(1.5707963267948966 * (s[n0 + n] - (ps0 + (double)n * pds)));
+                plan.push_back(sp);
+            } else {
+                for (size_t n = 0; n < L; n++) plan.push_back(ScanPass{n0 + n, 1, s[n0 + n], 0.0, 2, {}});
+            }
+        }
+        n0 += L;
+    }
+    return SGPU_OK;
+}
+
+// amplitudes of NQ |q| values s[n] along fixed directions into A[NQ][NM][NFt] (this rank's frame columns)
+int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t NM, const double *s, size_t NQ, double2 *A) {
     if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, std::string(who) + ": frames are not staged (stage_frames first)");
     if (ctx->repr != SGPU_REPR_CARTESIAN) return fail(ctx, SGPU_ESTATE, std::string(who) + ": staged frames are not cartesian");
-    if (!v || NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
+    if (!v || !s || NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
     // factors: a per-|q| batch set for exactly this NQ, else the single set
     const bool batch = ctx->bq_nq == NQ && ctx->bq_n == ctx->NA && ctx->d_bq;
     if (!batch && ctx->nb != ctx->NA)
@@ -735,9 +815,16 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
     if (ctx->NFt != ctx->NF) CK(cudaMemsetAsync(A, 0, NQ * strideQ * sizeof(double2), ctx->stream));
     const float *xyz = ctx->d_xyz - ctx->f_first * ctx->NA * 3;  // see sgpu_all_vectors_amplitudes
     int rc;
+    std::vector<ScanPass> plan;
     if (uniform) {
-        rc = upload_q(ctx, v, NM, (size_t)amplitude_scan_qpad());  // directions, scaled to quarter turns per unit |q|
+        double vmax = 0.0;
+        for (size_t m = 0; m < NM; m++)
+            vmax = std::max(vmax, std::sqrt(v[3 * m] * v[3 * m] + v[3 * m + 1] * v[3 * m + 1] + v[3 * m + 2] * v[3 * m + 2]));
+        rc = plan_scan(ctx, s, NQ, vmax, plan);
         if (rc) return rc;
+    } else {
+        // factors differ between the |q| values (X-ray form factors, background): the general kernel per |q|
+        for (size_t n = 0; n < NQ; n++) plan.push_back(ScanPass{n, 1, s[n], 0.0, 2, {}});
     }
     bool all_ready = true;
     for (auto &c : ctx->chunks)
@@ -751,26 +838,37 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
     } else {
         spans = ctx->chunks;
     }
-    if (uniform) {
-        for (auto &c : spans) {
-            if (c.ready) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
-            ctx->launches += launch_amplitude_scan(xyz, d_b, ctx->d_qs, s0, ds, NQ, A, NFt, strideQ, ctx->NA, NM,
-                                                   ctx->f_first + c.f0, c.nf, ctx->stream);
-        }
-    } else {
-        // factors differ between the |q| values (X-ray form factors, background): one pass of the general kernel per |q|
-        std::vector<double> q(3 * NM);
-        for (size_t n = 0; n < NQ; n++) {
-            const double sn = s0 + (double)n * ds;
-            for (size_t i = 0; i < 3 * NM; i++) q[i] = sn * v[i];
+    bool dirs_uploaded = false;
+    std::vector<double> q(3 * NM);
+    ctx->scan_kinds[0] = ctx->scan_kinds[1] = ctx->scan_kinds[2] = 0;
+    for (auto &ps : plan) {
+        ctx->scan_kinds[ps.kind]++;
+        if (ps.kind == 2) {
+            for (size_t i = 0; i < 3 * NM; i++) q[i] = ps.s0 * v[i];
+            CK(cudaStreamSynchronize(ctx->stream));  // d_qs may still be read by the previous pass
             rc = upload_q(ctx, q.data(), NM, (size_t)amplitude_all_qpad());
             if (rc) return rc;
+            dirs_uploaded = false;
             for (auto &c : spans) {
                 if (c.ready) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
-                ctx->launches += launch_amplitude_all(xyz, d_b + n * ctx->NA, ctx->d_qs, A + n * strideQ, NFt, ctx->NA, NM,
-                                                      ctx->f_first + c.f0, c.nf, ctx->stream);
+                ctx->launches += launch_amplitude_all(xyz, d_b + (uniform ? 0 : ps.n0 * ctx->NA), ctx->d_qs, A + ps.n0 * strideQ,
+                                                      NFt, ctx->NA, NM, ctx->f_first + c.f0, c.nf, ctx->stream);
             }
-            CK(cudaStreamSynchronize(ctx->stream));  // d_qs is reused by the next |q|
+            continue;
+        }
+        if (!dirs_uploaded) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            rc = upload_q(ctx, v, NM, (size_t)amplitude_scan_qpad());  // directions, in quarter turns per unit |q|
+            if (rc) return rc;
+            dirs_uploaded = true;
+        }
+        for (auto &c : spans) {
+            if (c.ready) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+            const int l = launch_amplitude_scan_pass(xyz, d_b, ctx->d_qs, ps.s0, ps.ds, ps.nq, ps.kind == 1 ? ps.kappa.data() : nullptr,
+                                                     A + ps.n0 * strideQ, NFt, strideQ, ctx->NA, NM, ctx->f_first + c.f0, c.nf,
+                                                     ctx->stream);
+            if (l < 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": internal error, scan pass too long");
+            ctx->launches += l;
         }
     }
     CK(cudaGetLastError());
@@ -778,13 +876,12 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
 }
 }  // namespace
 
-int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ,
-                                     double *d_amp) {
+int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, double *d_amp) {
     if (!ctx) return SGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
     if (!d_amp) return fail(ctx, SGPU_EINVAL, "sgpu_all_vectors_scan_amplitudes: d_amp is NULL");
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = scan_amplitudes_into(ctx, "sgpu_all_vectors_scan_amplitudes", v, NM, s0, ds, NQ, reinterpret_cast<double2 *>(d_amp));
+    int rc = scan_amplitudes_into(ctx, "sgpu_all_vectors_scan_amplitudes", v, NM, s, NQ, reinterpret_cast<double2 *>(d_amp));
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
@@ -794,8 +891,8 @@ int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, 
     return SGPU_OK;
 }
 
-int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ,
-                                          int dsp_type, double *d_partials) {
+int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, int dsp_type,
+                                          double *d_partials) {
     if (!ctx) return SGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
     int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
@@ -816,7 +913,7 @@ int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t
     rc = ensure_work(ctx, dsp_work_bytes(ctx, NM, dsp_type));
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    rc = scan_amplitudes_into(ctx, "sgpu_compute_all_vectors_scan", v, NM, s0, ds, NQ, ctx->d_A);
+    rc = scan_amplitudes_into(ctx, "sgpu_compute_all_vectors_scan", v, NM, s, NQ, ctx->d_A);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->A_NM = (NQ == 1) ? NM : 0;
@@ -831,7 +928,7 @@ int sgpu_compute_all_vectors_scan_partial(sgpu_ctx *ctx, const double *v, size_t
     return SGPU_OK;
 }
 
-int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, double s0, double ds, size_t NQ, int dsp_type,
+int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, int dsp_type,
                                   int dsp_method, double *atfinal, double *afinal, double *a2final) {
     if (!ctx) return SGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -844,13 +941,23 @@ int sgpu_compute_all_vectors_scan(sgpu_ctx *ctx, const double *v, size_t NM, dou
     const size_t plen = partial_len(ctx, dsp_type);
     rc = ensure<double>(ctx, &ctx->d_partial, &ctx->partial_cap, NQ * plen);
     if (rc) return rc;
-    rc = sgpu_compute_all_vectors_scan_partial(ctx, v, NM, s0, ds, NQ, dsp_type, ctx->d_partial);
+    rc = sgpu_compute_all_vectors_scan_partial(ctx, v, NM, s, NQ, dsp_type, ctx->d_partial);
     if (rc) return rc;
     for (size_t n = 0; n < NQ; n++) {
         rc = sgpu_finalize(ctx, ctx->d_partial + n * plen, dsp_type, dsp_method, 1.0 / (double)NM, atfinal + n * 2 * ctx->NFt,
                            afinal + 2 * n, a2final + 2 * n);
         if (rc) return rc;
     }
+    return SGPU_OK;
+}
+
+/* how the last scan call was evaluated: passes of the plain scan kernel, of the corrected scan kernel, and |q| values
+ * that went through the general kernel one at a time */
+int sgpu_last_scan_plan(const sgpu_ctx *ctx, int *plain, int *corrected, int *single) {
+    if (!ctx) return SGPU_EINVAL;
+    if (plain) *plain = ctx->scan_kinds[0];
+    if (corrected) *corrected = ctx->scan_kinds[1];
+    if (single) *single = ctx->scan_kinds[2];
     return SGPU_OK;
 }
 

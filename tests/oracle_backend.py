@@ -84,7 +84,7 @@ class OracleBackend:
     def _scan_b(self, ctx, NQ, n):
         return ctx["bq"][n] if "bq" in ctx and len(ctx["bq"]) == NQ else ctx["b"]
 
-    def _av_scan(self, c, v, NM, s0, ds, NQ, dsp, ptr):
+    def _av_scan(self, c, v, NM, sv, NQ, dsp, ptr):
         ctx = self._ctx(c)
         plen = 2 * ctx["NFt"] + 4
         for n in range(NQ):
@@ -92,18 +92,18 @@ class OracleBackend:
             if NM == 0:
                 self._zero(ctx, p)
                 continue
-            qv = (s0 + n * ds) * np.ctypeslib.as_array(v, shape=(NM, 3))
+            qv = sv[n] * np.ctypeslib.as_array(v, shape=(NM, 3))
             fqt, fq, fq2 = o.compute_all_vectors(ctx["xyz"], self._scan_b(ctx, NQ, n), qv, dsp=_DSP[dsp])
             self._store(ctx, p, fqt, fq, fq2, NM)
         return 0
 
-    def _av_scan_amplitudes(self, c, v, NM, s0, ds, NQ, out):
+    def _av_scan_amplitudes(self, c, v, NM, sv, NQ, out):
         ctx = self._ctx(c)
         NFt, f0, NF = ctx["NFt"], ctx["f_first"], ctx["NF"]
         A = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(NQ, NM, NFt, 2))
         A[:] = 0
         for n in range(NQ):
-            qv = (s0 + n * ds) * np.ctypeslib.as_array(v, shape=(NM, 3))
+            qv = sv[n] * np.ctypeslib.as_array(v, shape=(NM, 3))
             *_, amp = o.compute_all_vectors(ctx["xyz"], self._scan_b(ctx, NQ, n), qv, dsp="plain", return_amplitudes=True)
             A[n, :, f0:f0 + NF] = np.ascontiguousarray(amp).view(np.float64).reshape(NM, NF, 2)
         return 0

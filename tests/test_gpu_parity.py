@@ -277,63 +277,108 @@ def test_all_vectors_frame_sharded_equals_single(gpu_ctx, oracle, nranks, NF):
     gpu_ctx.device_free(d_amp)
 
 
-@pytest.mark.parametrize("NQ", [1, 3, 4, 8, 16, 21, 37])
+@pytest.mark.parametrize("NQ", [1, 3, 4, 8, 16, 21, 37, 61])
 def test_all_vectors_scan_matches_per_q(gpu_ctx, oracle, NQ):
-    """|q|-scan kernel (two sincos + NQ-1 rotations per (atom, direction)): every |q| of the batch equals the per-|q|
-    GPU result to 1e-12 and the oracle to 1e-9; NQ values exercise every pass size (16, 8, 4 and masked remainders)."""
+    """|q|-scan kernel (two sincos + a 3-term recurrence per (atom, direction)): every |q| of an exactly spaced batch
+    equals the per-|q| GPU result to 1e-11 and the oracle to 1e-9; NQ values exercise every pass size and masking."""
     xyz, b, u = small_case(NA=301, NF=40, NM=37)
-    s0, ds = 0.3, 0.17
+    s = 0.3 + 0.17 * np.arange(NQ)
     gpu_ctx.stage_frames(xyz)
     gpu_ctx.set_factors(b)
-    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+    plain, corr, single = gpu_ctx.last_scan_plan()
+    assert corr == 0 and ((plain >= 1 and single == 0) if NQ >= 3 else single == NQ)
     assert fqt.shape == (NQ, 40)
     for n in sorted({0, NQ // 2, NQ - 1}):
-        q = (s0 + n * ds) * u
+        q = s[n] * u
         g = gpu_ctx.compute_all_vectors(q)
-        assert rel_err(fqt[n], g[0]) < 1e-12
-        assert abs(fq[n] - g[1]) < 1e-12 * abs(g[0][0]) and abs(fq2[n] - g[2]) < 1e-12 * abs(g[2])
+        assert rel_err(fqt[n], g[0]) < 1e-11
+        assert abs(fq[n] - g[1]) < 1e-11 * abs(g[0][0]) and abs(fq2[n] - g[2]) < 1e-11 * abs(g[2])
         r = oracle.compute_all_vectors(xyz, b, q)
         assert rel_err(fqt[n], r[0]) < TOL
         assert abs(fq[n] - r[1]) < TOL * abs(r[0][0]) and abs(fq2[n] - r[2]) < TOL * abs(r[2])
 
 
-@pytest.mark.parametrize("dsp", ["square", "plain"])
-def test_all_vectors_scan_other_dsp_and_unaligned_atoms(gpu_ctx, oracle, dsp):
-    """NA % 4 != 0 takes the cp.async staging path; square / plain dsp; long rotation chain far from the origin"""
-    xyz, b, u = small_case(NA=203, NF=24, NM=19, box=300.0)
-    s0, ds, NQ = 1.1, 0.45, 16
+def test_all_vectors_scan_float_rounded_scan(gpu_ctx, oracle):
+    """The reference builds scans from float-rounded fractions (parameters.cpp:1151): the |q| are equally spaced only to
+    ~1e-8.  Such batches take the corrected kernel (first order in FP64, second order in FP32) and still equal the
+    oracle evaluated at the exact q-vectors; a large box makes the phase deviations as big as they get in practice."""
+    from sassena_b200 import host
+    xyz, b, u = small_case(NA=257, NF=24, NM=19, box=400.0)
+    qv = host.create_from_scans([{"base": (1, 0, 0), "from": 0.1, "to": 5.0, "points": 50}])
+    s = np.linalg.norm(qv, axis=1)
+    assert np.max(np.abs(np.diff(s, 2))) > 1e-9  # not a progression
     gpu_ctx.stage_frames(xyz)
     gpu_ctx.set_factors(b)
-    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ, dsp=dsp)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+    plain, corr, single = gpu_ctx.last_scan_plan()
+    assert plain == 0 and corr >= 3 and single == 0
+    worst = 0.0
+    for n in range(0, 50, 7):
+        r = oracle.compute_all_vectors(xyz, b, s[n] * u)
+        worst = max(worst, rel_err(fqt[n], r[0]))
+        assert abs(fq[n] - r[1]) < TOL * abs(r[0][0])
+    assert worst < 1e-10, worst  # an order of magnitude inside the tolerance
+    # uncorrected, the same batch would miss the tolerance: the deviation is real
+    snapped = np.linspace(s[0], s[-1], 50)
+    r = oracle.compute_all_vectors(xyz, b, snapped[24] * u)
+    assert rel_err(fqt[24], r[0]) > 1e-8
+
+
+def test_all_vectors_scan_arbitrary_spacing_falls_back(gpu_ctx, oracle):
+    """|q| values with no progression at all: the call is still valid, each |q| runs through the general kernel"""
+    xyz, b, u = small_case(NA=120, NF=16, NM=12)
+    s = np.array([0.2, 0.25, 0.7, 0.71, 1.9, 3.3])
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+    assert gpu_ctx.last_scan_plan() == (0, 0, len(s))
+    for n in range(len(s)):
+        r = oracle.compute_all_vectors(xyz, b, s[n] * u)
+        assert rel_err(fqt[n], r[0]) < TOL
+
+
+@pytest.mark.parametrize("dsp", ["square", "plain"])
+def test_all_vectors_scan_other_dsp_and_unaligned_atoms(gpu_ctx, oracle, dsp):
+    """NA % 4 != 0 takes the cp.async staging path; square / plain dsp; long recurrence far from the origin"""
+    xyz, b, u = small_case(NA=203, NF=24, NM=19, box=300.0)
+    s = 1.1 + 0.45 * np.arange(16)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s, dsp=dsp)
     for n in (0, 7, 15):
-        r = oracle.compute_all_vectors(xyz, b, (s0 + n * ds) * u, dsp=dsp)
+        r = oracle.compute_all_vectors(xyz, b, s[n] * u, dsp=dsp)
         assert rel_err(fqt[n], r[0]) < TOL
         assert abs(fq[n] - r[1]) < TOL * max(abs(r[1]), abs(r[0]).max())
 
 
 def test_all_vectors_scan_per_q_factors(gpu_ctx, oracle):
     """|q|-dependent factors (X-ray form factors / background): a batch with differing rows falls back to the general
-    kernel per |q|; a batch with identical rows takes the rotation kernel.  Both equal the oracle."""
+    kernel per |q|; a batch with identical rows takes the scan kernel.  Both equal the oracle."""
     xyz, b, u = small_case(NA=160, NF=16, NM=23)
-    s0, ds, NQ = 0.2, 0.3, 5
+    NQ = 5
+    s = 0.2 + 0.3 * np.arange(NQ)
     gpu_ctx.stage_frames(xyz)
     bq = np.stack([b * (1.0 + 0.1 * n) - 0.05 * n for n in range(NQ)])
     gpu_ctx.set_factors_batch(bq)
-    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+    assert gpu_ctx.last_scan_plan() == (0, 0, NQ)
     for n in range(NQ):
-        r = oracle.compute_all_vectors(xyz, bq[n], (s0 + n * ds) * u)
+        r = oracle.compute_all_vectors(xyz, bq[n], s[n] * u)
         assert rel_err(fqt[n], r[0]) < TOL
     gpu_ctx.set_factors_batch(np.stack([b] * NQ))
-    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s0, ds, NQ)
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+    assert gpu_ctx.last_scan_plan() == (1, 0, 0)
     for n in range(NQ):
-        r = oracle.compute_all_vectors(xyz, b, (s0 + n * ds) * u)
+        r = oracle.compute_all_vectors(xyz, b, s[n] * u)
         assert rel_err(fqt[n], r[0]) < TOL
 
 
 def test_all_vectors_scan_frame_window(gpu_ctx, oracle):
     """scan amplitudes of a frame block land in the right columns of A[NQ][NM][NF_total]"""
     xyz, b, u = small_case(NA=128, NF=30, NM=11)
-    s0, ds, NQ, NM, NF = 0.4, 0.25, 6, 11, 30
+    NQ, NM, NF = 6, 11, 30
+    s = 0.4 + 0.25 * np.arange(NQ)
     d_amp = gpu_ctx.device_alloc(NQ * NM * NF * 16)
     A = np.zeros((NQ, NM, NF), dtype=np.complex128)
     part = np.empty_like(A)
@@ -342,14 +387,14 @@ def test_all_vectors_scan_frame_window(gpu_ctx, oracle):
         gpu_ctx.stage_frames(xyz[off:off + size])
         gpu_ctx.set_frame_window(NF, off)
         gpu_ctx.set_factors(b)
-        gpu_ctx.all_vectors_scan_amplitudes(u, s0, ds, NQ, d_amp)
+        gpu_ctx.all_vectors_scan_amplitudes(u, s, d_amp)
         gpu_ctx.synchronize()
         gpu_ctx.memcpy_d2h(part.view(np.float64), d_amp)
         assert np.all(part[:, :, :off] == 0) and np.all(part[:, :, off + size:] == 0)
         A += part
     gpu_ctx.device_free(d_amp)
     for n in range(NQ):
-        ref = oracle.compute_all_vectors(xyz, b, (s0 + n * ds) * u, dsp="plain", return_amplitudes=True)[-1]
+        ref = oracle.compute_all_vectors(xyz, b, s[n] * u, dsp="plain", return_amplitudes=True)[-1]
         assert np.max(np.abs(A[n] - ref)) < 1e-11 * np.max(np.abs(ref))
 
 
@@ -517,7 +562,7 @@ def test_host_layer_devices_on_gpu(oracle):
     p.set("scattering.average.orientation.vectors.resolution", 20).set("scattering.average.orientation.vectors.seed", 5)
     p.create()
     recs, has, tm = host.run_scatter(p, xyz, qv, factors_fn=lambda ql: b * (1.0 + 0.1 * ql))
-    assert has and len(recs) == 4 and tm["sd:compute"][1] == 4
+    assert has and len(recs) == 4 and tm["sd:compute"][1] == 1 and tm["sd:c:scan"][1] == 1  # one batched |q| scan
     for r, q in zip(recs, qv):
         ref = oracle.compute_all_vectors(xyz, b * (1.0 + 0.1 * np.linalg.norm(q)), p.init_subvectors(q), nthreads=4)
         assert rel_err(r["fqt"], ref[0]) < TOL and abs(r["fq"] - ref[1]) < TOL * abs(ref[0][0])

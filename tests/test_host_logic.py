@@ -229,9 +229,9 @@ def test_run_scatter_single_rank_oracle_backend(oracle):
 
 
 def test_run_scatter_scan_batching(oracle):
-    """AllVectors runner: consecutive q-vectors of a scan (same direction, equal |q| spacing, >= 8 subvectors) are
-    batched into one backend call; a vector that breaks the progression or a different direction ends the batch; the
-    records still arrive one per q-vector, in order, and equal the oracle.  limits.computation.scan=1 disables it."""
+    """AllVectors runner: consecutive q-vectors that share their directions (>= 4 of them, >= 8 subvectors) go to the
+    backend in one call, whatever their spacing; a different direction or |q| = 0 ends the batch; the records still
+    arrive one per q-vector, in order, and equal the oracle.  limits.computation.scan=1 disables it."""
     from oracle_backend import OracleBackend
     from sassena_b200 import synth
     be = OracleBackend()
@@ -251,9 +251,9 @@ def test_run_scatter_scan_batching(oracle):
     p = params()
     recs, has, tm = host.run_scatter(p, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
     assert len(recs) == len(qv)
-    # batches: the 5 scan points, then (2.5 z, 1.7*1.5, 1.7*1.2) is no progression -> singles; 2 vectors form the last
-    # candidate batch only if colinear and equally spaced: (1.7*1.5, 1.7*1.2) qualifies; |q| = 0 never does
-    assert tm["sd:c:scan"][1] == 2 and tm["sd:compute"][1] == 2 + 2
+    # sphere/file averaging only depends on |q|: all 8 non-zero vectors share their subvector directions and form one
+    # batch; |q| = 0 never qualifies
+    assert tm["sd:c:scan"][1] == 1 and tm["sd:compute"][1] == 1 + 1
     for r, q in zip(recs, qv):
         assert np.array_equal(r["q"], q)
         ref = oracle.compute_all_vectors(xyz, b * (1 + np.linalg.norm(q)), p.init_subvectors(q))
@@ -263,6 +263,9 @@ def test_run_scatter_scan_batching(oracle):
     pc = params(scattering__average__orientation__vectors__type="cylinder", scattering__average__orientation__vectors__resolution=11)
     recs, _, tm = host.run_scatter(pc, xyz, scan, b=b, backend=be.vtbl)
     assert tm["sd:c:scan"][1] == 1
+    # ... but not across directions: the cylinder construction depends on the direction of q
+    _, _, tm2 = host.run_scatter(pc, xyz, qv[:8], b=b, backend=be.vtbl)
+    assert tm2["sd:c:scan"][1] == 1 and tm2["sd:compute"][1] == 1 + 3
     for r, q in zip(recs, scan):
         ref = oracle.compute_all_vectors(xyz, b, pc.init_subvectors(q))
         assert np.allclose(r["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))

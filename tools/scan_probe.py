@@ -27,21 +27,24 @@ def main():
     ctx.set_factors(b)
     u = synth.unit_vectors(NM, 6)
     s0, ds = 0.1, 0.1
+    sv = s0 + ds * np.arange(NQ)
+    if os.environ.get('ROUNDED'):  # the reference's float-rounded scan fractions
+        sv = s0 + np.float32(np.arange(NQ) / (NQ - 1)).astype(np.float64) * (ds * (NQ - 1))
     amp = torch.empty(NQ * NM * NF * 2, dtype=torch.float64, device=dev)
     for rep in range(2):
         ctx.synchronize()
         t0 = time.perf_counter()
-        ctx.all_vectors_scan_amplitudes(u, s0, ds, NQ, amp.data_ptr())
+        ctx.all_vectors_scan_amplitudes(u, sv, amp.data_ptr())
         ctx.synchronize()
         dt = time.perf_counter() - t0
         ms = ctx.last_amplitude_ms()
     evals = float(NA) * NF * NM * NQ
-    print(f"scan variant {os.environ.get('SASSENA_SCAN_VARIANT', '0')}: NQ={NQ} {evals / (ms * 1e-3):.3e} evals/s (kernel {ms:.1f} ms, wall {dt * 1e3:.1f} ms)")
+    print(f"scan plan {ctx.last_scan_plan()}: NQ={NQ} {evals / (ms * 1e-3):.3e} evals/s (kernel {ms:.1f} ms, wall {dt * 1e3:.1f} ms)")
     # per-|q| kernel for comparison and a spot check
     a1 = torch.empty(NM * NF * 2, dtype=torch.float64, device=dev)
     n = NQ - 1
     for rep in range(2):
-        ctx.all_vectors_amplitudes((s0 + n * ds) * u, a1.data_ptr())
+        ctx.all_vectors_amplitudes(sv[n] * u, a1.data_ptr())
         ctx.synchronize()
         ms1 = ctx.last_amplitude_ms()
     print(f"per-|q| kernel: {float(NA) * NF * NM / (ms1 * 1e-3):.3e} evals/s")
