@@ -54,9 +54,8 @@ def scan_passes(nq, max_b=SCAN_MAX_PASS):
     out, n0 = [], 0
     for p in range(npass):
         want = (nq - n0 + (npass - p) - 1) // (npass - p)
-        gran = 2 if (want > 20 and max_b > 20) else 4
-        L = min(min((want + gran - 1) // gran * gran, max_b), nq - n0)
-        out.append((L + gran - 1) // gran * gran)
+        L = min(min((want + 3) // 4 * 4, max_b), nq - n0)
+        out.append((L + 3) // 4 * 4)
         n0 += L
     return out
 

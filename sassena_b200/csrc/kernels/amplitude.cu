@@ -995,11 +995,8 @@ int scan_dispatch(int B, int warps, int recur, const ScanArgs &a) {
             case 12: return scan_pass<12, 12, 1, 1>(a);
             case 16: return scan_pass<16, 12, 1, 1>(a);
             case 20: return scan_pass<20, 12, 1, 1>(a);
-            case 22: return scan_pass<22, 12, 1, 1>(a);
             case 24: return scan_pass<24, 12, 1, 1>(a);
-            case 26: return scan_pass<26, 12, 1, 1>(a);
             case 28: return scan_pass<28, 12, 1, 1>(a);
-            case 30: return scan_pass<30, 12, 1, 1>(a);
             default: return scan_pass<32, 12, 1, 1>(a);
         }
     }
@@ -1051,7 +1048,6 @@ int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const doub
     static const int warps = env_int("SASSENA_SCAN_WARPS", 12), recur = env_int("SASSENA_SCAN_RECUR", 1),
                      cwarps = env_int("SASSENA_SCAN_CORR_WARPS", 8);
     int B = ((nq + 3) / 4) * 4;
-    if (!kappa && warps == 12 && recur && nq > 20) B = ((nq + 1) / 2) * 2;  // long passes come in steps of two
     ScanArgs a{d_xyz, d_b, d_vs, s0, ds, nq, d_A, ldA, strideQ, NA, NM, f0, nf, st, ScanKappa()};
     if (kappa) {
         if (B > 20 || (cwarps == 12 && B > 12)) return -1;
