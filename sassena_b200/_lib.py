@@ -81,7 +81,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SASSENA_B200_LIB") or LIB_PATH  # SASSENA_B200_LIB: an alternative build of the library
     if not os.path.exists(p):
         raise LibraryMissing(
             f"{p} not found: build the CUDA extension first (python -m sassena_b200.build or __graft_entry__.build()); "

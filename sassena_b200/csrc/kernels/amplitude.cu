@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
         if (active) {
             const float *sx = s_xyz + (size_t)s * TILE * 3;
             const double *sb = s_b + (size_t)s * TILE;
-#pragma unroll 1
+#pragma unroll 1  // (two atoms in flight per thread measured no faster for the corrected variant)
             for (int j = lane; j < cnt; j += 32) {
                 const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
                 const double bj = sb[j];
