@@ -73,7 +73,9 @@ void sass_params_free(sass_params *p);
  * scattering.average.orientation.multipole.type, scattering.average.orientation.multipole.moments.{type,resolution},
  * limits.stage.memory.data, limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size},
  * limits.decomposition.coherent (auto | frames | vectors: how a partition's ranks share one coherent |q|),
- * limits.computation.scan (largest |q| batch of the coherent scan path; 0 or 1 = one |q| per pass) */
+ * limits.computation.scan (largest |q| batch of the coherent scan path; 0 or 1 = one |q| per pass),
+ * limits.computation.scan_snap (true: |q| equally spaced to within 1e-6 are moved onto the exact progression; off by
+ * default because it changes the q-vectors with respect to the reference's float-rounded scan fractions) */
 int sass_params_set(sass_params *p, const char *key, const char *value);
 /* vectors.type=file rows / multipole.moments.type=file rows */
 int sass_params_set_vectors(sass_params *p, const double *xyz, size_t n);

@@ -428,6 +428,7 @@ void Config::read_xml(const std::string &filename) {
     if (x.exists("//limits/decomposition/partitions/automatic"))
         limits.decomposition.partitions_automatic = x.get_bool("//limits/decomposition/partitions/automatic");
     if (x.exists("//limits/computation/scan")) limits.coherent_scan = x.get_size("//limits/computation/scan");
+    if (x.exists("//limits/computation/scan_snap")) limits.coherent_scan_snap = x.get_bool("//limits/computation/scan_snap");
     if (x.exists("//limits/decomposition/coherent")) limits.coherent_sharding = x.get_string("//limits/decomposition/coherent");
     if (x.exists("//limits/decomposition/partitions/size"))
         limits.decomposition.partitions_size = x.get_size("//limits/decomposition/partitions/size");

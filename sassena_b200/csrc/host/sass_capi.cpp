@@ -97,6 +97,8 @@ int sass_params_set(sass_params *p, const char *key, const char *value) {
         else if (k == "limits.decomposition.utilization") p->params.limits.decomposition.utilization = atof(value);
         else if (k == "limits.decomposition.partitions.automatic")
             p->params.limits.decomposition.partitions_automatic = parse_bool(v);
+        else if (k == "limits.computation.scan_snap")
+            p->params.limits.coherent_scan_snap = parse_bool(v);
         else if (k == "limits.computation.scan")
             p->params.limits.coherent_scan = strtoull(value, nullptr, 10);
         else if (k == "limits.decomposition.coherent")

@@ -730,7 +730,24 @@ size_t AllVectorsScatterDevice::scan_length(size_t first, std::vector<double> &v
         if (!ok) break;
         s.push_back(sn);
     }
-    return s.size() >= 4 ? s.size() : 1;
+    if (s.size() < 4) return 1;
+    if (params_.limits.coherent_scan_snap) {
+        const size_t n = s.size();
+        const double ds = (s[n - 1] - s[0]) / (double)(n - 1);
+        double dev = 0.0, smax = 0.0;
+        for (size_t i = 0; i < n; i++) {
+            dev = std::max(dev, std::fabs(s[i] - (s[0] + (double)i * ds)));
+            smax = std::max(smax, s[i]);
+        }
+        if (dev > 0.0 && dev <= 1e-6 * smax) {
+            for (size_t i = 0; i < n; i++) {
+                const double snew = s[0] + (double)i * ds;
+                vectors_[first + i] = (snew / s[i]) * vectors_[first + i];  // the snapped vector is what gets written
+                s[i] = snew;
+            }
+        }
+    }
+    return s.size();
 }
 
 void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> &v, const std::vector<double> &s) {

@@ -181,6 +181,12 @@ struct LimitsParameters {
     // |q|-scan batching of the coherent path: largest number of consecutive q-vectors evaluated in one pass
     // (0 or 1 disables; limits.computation.scan)
     size_t coherent_scan = 56;
+    // limits.computation.scan_snap: move the |q| of a batch that is equally spaced to within 1e-6 onto the exact
+    // progression (the reference computes scan fractions in float, parameters.cpp:1151, which perturbs them by ~3e-8).
+    // Off by default: it changes the q-vectors (and therefore the results, by ~1e-5 relative) with respect to the
+    // reference; on, such scans take the plain scan kernel instead of the corrected one and the snapped q-vectors are
+    // what is written.
+    bool coherent_scan_snap = false;
 };
 
 struct Params {

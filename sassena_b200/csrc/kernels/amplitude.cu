@@ -278,16 +278,20 @@ struct ScanKappa {
     double k[32];  // (pi/2) * (s_n - (s0 + n ds)): first/second-order phase correction per |q| of the pass (CORR)
 };
 
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0>
+// BVAR: the factors depend on |q| (X-ray form factors, background subtraction): b is [B][b_stride] and every tile
+// stages B factor rows; the recurrence then runs on the unit phasor and the accumulation is a DFMA with b_n.
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0, int BVAR = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ vs, double s0, double ds,
     double2 *__restrict__ A, size_t ldA, size_t strideQ, int NA, int NM, int nq_valid, unsigned ngroups, size_t f0,
-    int use_bulk, const ScanKappa kap) {
+    int use_bulk, const ScanKappa kap, size_t b_stride) {
     static_assert(!CORR || (RECUR && VPT == 1), "the corrected variant is built on the recurrence form, one direction per warp");
+    static_assert(!BVAR || (RECUR && VPT == 1 && !CORR && B <= 31), "the |q|-dependent-factor variant: recurrence form, plain");
+    constexpr int NB = BVAR ? B : 1;  // factor rows per tile
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_xyz = reinterpret_cast<float *>(smem_raw);                                  // [STAGES][TILE*3]
-    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);  // [STAGES][TILE]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8));
+    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);  // [STAGES][NB][TILE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8 * NB));
     uint64_t *empty = full + STAGES;
 
     const unsigned group = blockIdx.x % ngroups;
@@ -306,25 +310,34 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     }
     __syncthreads();
 
+    // Called by every thread at a converged point.  Bulk path: warp 0 issues — lane 0 waits for the slot and posts the
+    // byte count, then lane 0 copies the coordinates and lanes 1..NB one factor row each.
     auto issue = [&](int t) {
         const int s = t % STAGES;
         const int a0 = t * TILE;
         const int cnt = min(TILE, NA - a0);
         if (use_bulk) {
-            if (tid == 0) {
-                if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
-                ptx::mbar_expect_tx(&full[s], (unsigned)cnt * 20u);
-                ptx::bulk_g2s(s_xyz + (size_t)s * TILE * 3, p + (size_t)a0 * 3, (unsigned)cnt * 12u, &full[s]);
-                ptx::bulk_g2s(s_b + (size_t)s * TILE, b + a0, (unsigned)cnt * 8u, &full[s]);
+            if (warp == 0) {
+                if (lane == 0) {
+                    if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
+                    ptx::mbar_expect_tx(&full[s], (unsigned)cnt * (12u + 8u * NB));
+                    ptx::bulk_g2s(s_xyz + (size_t)s * TILE * 3, p + (size_t)a0 * 3, (unsigned)cnt * 12u, &full[s]);
+                }
+                __syncwarp();
+                if (lane >= 1 && lane <= NB)
+                    ptx::bulk_g2s(s_b + ((size_t)s * NB + (lane - 1)) * TILE, b + (size_t)(lane - 1) * b_stride + a0,
+                                  (unsigned)cnt * 8u, &full[s]);
             }
         } else {
             if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
             float *dx = s_xyz + (size_t)s * TILE * 3;
             const float *sx = p + (size_t)a0 * 3;
             for (int i = tid; i < cnt * 3; i += WARPS * 32) ptx::cp_async4(dx + i, sx + i);
-            float *db = reinterpret_cast<float *>(s_b + (size_t)s * TILE);
-            const float *sb = reinterpret_cast<const float *>(b + a0);
-            for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
+            for (int r = 0; r < NB; r++) {
+                float *db = reinterpret_cast<float *>(s_b + ((size_t)s * NB + r) * TILE);
+                const float *sb = reinterpret_cast<const float *>(b + (size_t)r * b_stride + a0);
+                for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
+            }
             ptx::cp_async_mbar_arrive_noinc(&full[s]);
         }
     };
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     // CORR: |q| values that deviate from the arithmetic progression by e_n (the reference builds scans from float-rounded
     // fractions, parameters.cpp:1151).  exp(i (s_n + e_n) sigma) = z_n (1 + i th - th^2/2 + O(th^3)), th = kap_n sigma:
     // first order needs D_n = sum b sigma z_n (FP64), second order E_n = sum b sigma^2 z_n, whose weight kap^2/2 is
-    // ~1e-10, so an FP32 copy of the recurrence on the FP32 pipe is accurate enough (and free: the FP64 pipe is the bound).
+    // ~1e-10, so an FP32 copy of the recurrence on the FP32 pipe is accurate enough (4 issue slots instead of 6 FP64-pipe cycles).
     double dre[CORR ? B : 1], dim[CORR ? B : 1];
     float ere[CORR ? B : 1], eim[CORR ? B : 1];
     if (CORR) {
@@ -367,11 +380,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
         ptx::mbar_wait(&full[s], (unsigned)((t / STAGES) & 1));
         if (active) {
             const float *sx = s_xyz + (size_t)s * TILE * 3;
-            const double *sb = s_b + (size_t)s * TILE;
+            const double *sb = s_b + (size_t)s * NB * TILE;
 #pragma unroll 1  // (two atoms in flight per thread measured no faster for the corrected variant)
             for (int j = lane; j < cnt; j += 32) {
                 const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
-                const double bj = sb[j];
+                const double bj = BVAR ? 1.0 : sb[j];
 #pragma unroll
                 for (int k = 0; k < VPT; k++) {
                     const double sigma = fma(z, vz[k], fma(y, vy[k], x * vx[k]));  // quarter turns per unit |q|
@@ -398,8 +411,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                         const double c2 = cw + cw;
                         double pr = zr, pi = zi;  // z_{n-1}
                         float fpr = 0.f, fpi = 0.f, fzr = 0.f, fzi = 0.f, fc2 = 0.f, fs2 = 0.f;
-                        re[k][0] += zr;
-                        im[k][0] += zi;
+                        if (BVAR) {
+                            const double b0 = sb[j];
+                            re[k][0] = fma(b0, zr, re[k][0]);
+                            im[k][0] = fma(b0, zi, im[k][0]);
+                        } else {
+                            re[k][0] += zr;
+                            im[k][0] += zi;
+                        }
                         if (CORR) {
                             dre[0] = fma(sigma, zr, dre[0]);
                             dim[0] = fma(sigma, zi, dim[0]);
@@ -416,8 +435,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                             const double nr = fma(zr, cw, -t1);
                             zi = fma(zr, sw, t2);
                             zr = nr;
-                            re[k][1] += zr;
-                            im[k][1] += zi;
+                            if (BVAR) {
+                                const double b1 = sb[TILE + j];
+                                re[k][1] = fma(b1, zr, re[k][1]);
+                                im[k][1] = fma(b1, zi, im[k][1]);
+                            } else {
+                                re[k][1] += zr;
+                                im[k][1] += zi;
+                            }
                             if (CORR) {
                                 dre[1] = fma(sigma, zr, dre[1]);
                                 dim[1] = fma(sigma, zi, dim[1]);
@@ -435,8 +460,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
                             pi = zi;
                             zr = nr;
                             zi = ni;
-                            re[k][n] += zr;
-                            im[k][n] += zi;
+                            if (BVAR) {
+                                const double bn = sb[n * TILE + j];
+                                re[k][n] = fma(bn, zr, re[k][n]);
+                                im[k][n] = fma(bn, zi, im[k][n]);
+                            } else {
+                                re[k][n] += zr;
+                                im[k][n] += zi;
+                            }
                             if (CORR) {
                                 dre[n] = fma(sigma, zr, dre[n]);
                                 dim[n] = fma(sigma, zi, dim[n]);
@@ -928,14 +959,14 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
 }
 
 namespace {
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0>
+template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0, int BVAR = 0>
 int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq_valid,
                      double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st,
-                     const ScanKappa &kap = ScanKappa()) {
+                     const ScanKappa &kap = ScanKappa(), size_t b_stride = 0) {
     const unsigned per_cta = VPT * WARPS;
     const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
-    const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
-    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB, RECUR, CORR>;
+    const size_t smem = (size_t)STAGES * TILE * (12 + 8 * (BVAR ? B : 1)) + 2 * STAGES * sizeof(uint64_t);
+    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB, RECUR, CORR, BVAR>;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -948,7 +979,7 @@ int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, 
     for (size_t done = 0; done < nf;) {
         size_t cnt = nf - done < max_frames ? nf - done : max_frames;
         kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_vs, s0, ds, d_A, ldA, strideQ, (int)NA,
-                                                                  (int)NM, nq_valid, ngroups, f0 + done, use_bulk, kap);
+                                                                  (int)NM, nq_valid, ngroups, f0 + done, use_bulk, kap, b_stride);
         launches++;
         done += cnt;
     }
@@ -1012,6 +1043,23 @@ int scan_dispatch(int B, int warps, int recur, const ScanArgs &a) {
     }
 }
 
+// |q|-dependent factors: B factor rows per 128-atom tile in the ring
+template <int B>
+int scan_pass_bvar(const ScanArgs &a, size_t b_stride) {
+    return launch_scan_part<B, 1, 12, 128, 4, 1, 1, 0, 1>(a.d_xyz, a.d_b, a.d_vs, a.s, a.ds, a.valid, a.A, a.ldA, a.strideQ, a.NA,
+                                                          a.NM, a.f0, a.nf, a.st, a.kap, b_stride);
+}
+int scan_dispatch_bvar(int B, const ScanArgs &a, size_t b_stride) {
+    switch (B) {
+        case 4: return scan_pass_bvar<4>(a, b_stride);
+        case 8: return scan_pass_bvar<8>(a, b_stride);
+        case 12: return scan_pass_bvar<12>(a, b_stride);
+        case 16: return scan_pass_bvar<16>(a, b_stride);
+        case 20: return scan_pass_bvar<20>(a, b_stride);
+        default: return scan_pass_bvar<24>(a, b_stride);  // 28 would spill
+    }
+}
+
 // corrected variant: three accumulator sets per |q| (A, D in FP64, E in FP32), so passes are shorter
 int scan_dispatch_corr(int B, int warps, const ScanArgs &a) {
     if (warps == 12) {
@@ -1038,17 +1086,21 @@ int amplitude_scan_qpad() { return 24; }
 int amplitude_scan_max_pass(int corrected) {
     static const int plain = std::min(32, std::max(4, env_int("SASSENA_SCAN_B", 28)));
     static const int corr = std::min(20, std::max(4, env_int("SASSENA_SCAN_CORR_B", 16)));
-    return corrected ? corr : plain;
+    return corrected == 2 ? std::min(plain, 24) : corrected ? corr : plain;  // 2: |q|-dependent factors
 }
 
 int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
                                const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
-                               size_t f0, size_t nf, cudaStream_t st) {
+                               size_t f0, size_t nf, cudaStream_t st, size_t b_stride) {
     if (nf == 0 || NM == 0 || nq <= 0) return 0;
     static const int warps = env_int("SASSENA_SCAN_WARPS", 12), recur = env_int("SASSENA_SCAN_RECUR", 1),
                      cwarps = env_int("SASSENA_SCAN_CORR_WARPS", 8);
     int B = ((nq + 3) / 4) * 4;
     ScanArgs a{d_xyz, d_b, d_vs, s0, ds, nq, d_A, ldA, strideQ, NA, NM, f0, nf, st, ScanKappa()};
+    if (b_stride) {  // d_b holds one factor row per |q| of the pass
+        if (kappa || B > 24) return -1;
+        return scan_dispatch_bvar(B, a, b_stride);
+    }
     if (kappa) {
         if (B > 20 || (cwarps == 12 && B > 12)) return -1;
         for (int n = 0; n < 32; n++) a.kap.k[n] = n < nq ? kappa[n] : 0.0;

@@ -18,12 +18,14 @@ int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_
 // d_vs: [NMpad][3] direction vectors pre-scaled by 2/pi, zero padded to a multiple of amplitude_scan_qpad().
 // kappa (host, [nq], may be NULL): (pi/2) * (s_n - (s0 + n ds)) for |q| values that are only approximately equally
 // spaced; selects the corrected kernel (exact to third order in kappa_n * sigma).
+// b_stride != 0: |q|-dependent factors, d_b points at the row of the pass's first |q|, rows b_stride doubles apart
+// (plain kernel only).
 // d_A: [nq][NM][ldA] with strideQ entries between |q| planes.  Returns the launch count, -1 if nq is too large.
 int amplitude_scan_qpad();
-int amplitude_scan_max_pass(int corrected);
+int amplitude_scan_max_pass(int kind);  // 0 plain, 1 corrected, 2 |q|-dependent factors
 int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
                                const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
-                               size_t f0, size_t nf, cudaStream_t st);
+                               size_t f0, size_t nf, cudaStream_t st, size_t b_stride = 0);
 // max over the buffer of |x| (n floats); result in *d_out (float, device)
 int launch_max_abs(const float *d_x, size_t n, float *d_out, cudaStream_t st);
 int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,

@@ -745,7 +745,7 @@ struct ScanPass {
     size_t n0;
     int nq;
     double s0, ds;
-    int kind;  // 0 plain scan kernel, 1 corrected scan kernel, 2 general kernel per |q|
+    int kind;  // 0 plain scan kernel, 1 corrected scan kernel, 2 general kernel per |q|, 3 plain scan kernel with per-|q| factors
     std::vector<double> kappa;
 };
 
@@ -753,7 +753,7 @@ struct ScanPass {
 // small deviation of a progression (the reference builds scans from float-rounded fractions, parameters.cpp:1151) take
 // the corrected kernel as long as the neglected third-order phase term (kappa sigma)^3/6 stays below ~5e-12; anything
 // else is evaluated one |q| at a time by the general kernel.
-int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, std::vector<ScanPass> &plan) {
+int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, bool uniform_b, std::vector<ScanPass> &plan) {
     plan.clear();
     auto fit = [&](size_t n0, size_t L, double &s0, double &ds, double &epsmax) {
         s0 = s[n0];
@@ -770,8 +770,13 @@ int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, std::vecto
         for (size_t n = 0; n < NQ; n++) plan.push_back(ScanPass{n, 1, s[n], 0.0, 2, {}});
         return SGPU_OK;
     }
-    const bool force_corr = getenv("SASSENA_SCAN_FORCE_CORR") != nullptr;
-    const size_t maxB = (size_t)amplitude_scan_max_pass((exact && !force_corr) ? 0 : 1);
+    if (!uniform_b && !exact) {
+        // |q|-dependent factors AND a float-rounded scan: the correction terms would need the factors too; one |q| at a time
+        for (size_t n = 0; n < NQ; n++) plan.push_back(ScanPass{n, 1, s[n], 0.0, 2, {}});
+        return SGPU_OK;
+    }
+    const bool force_corr = uniform_b && getenv("SASSENA_SCAN_FORCE_CORR") != nullptr;
+    const size_t maxB = (size_t)amplitude_scan_max_pass(!uniform_b ? 2 : (exact && !force_corr) ? 0 : 1);
     if (!exact || force_corr) {
         int rc = ensure_rmax(ctx);
         if (rc) return rc;
@@ -784,7 +789,7 @@ int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, std::vecto
         // 28 with two masked |q|)
         size_t L = std::min<size_t>(std::min<size_t>(((want + 3) / 4) * 4, maxB), NQ - n0);
         if (exact && !force_corr) {
-            plan.push_back(ScanPass{n0, (int)L, s[0] + (double)n0 * ds, ds, 0, {}});
+            plan.push_back(ScanPass{n0, (int)L, s[0] + (double)n0 * ds, ds, uniform_b ? 0 : 3, {}});
         } else {
             double ps0, pds, peps;
             fit(n0, L, ps0, pds, peps);
@@ -818,16 +823,13 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
     const float *xyz = ctx->d_xyz - ctx->f_first * ctx->NA * 3;  // see sgpu_all_vectors_amplitudes
     int rc;
     std::vector<ScanPass> plan;
-    if (uniform) {
-        double vmax = 0.0;
-        for (size_t m = 0; m < NM; m++)
-            vmax = std::max(vmax, std::sqrt(v[3 * m] * v[3 * m] + v[3 * m + 1] * v[3 * m + 1] + v[3 * m + 2] * v[3 * m + 2]));
-        rc = plan_scan(ctx, s, NQ, vmax, plan);
-        if (rc) return rc;
-    } else {
-        // factors differ between the |q| values (X-ray form factors, background): the general kernel per |q|
-        for (size_t n = 0; n < NQ; n++) plan.push_back(ScanPass{n, 1, s[n], 0.0, 2, {}});
-    }
+    double vmax = 0.0;
+    for (size_t m = 0; m < NM; m++)
+        vmax = std::max(vmax, std::sqrt(v[3 * m] * v[3 * m] + v[3 * m + 1] * v[3 * m + 1] + v[3 * m + 2] * v[3 * m + 2]));
+    // factors that differ between the |q| values (X-ray form factors, background) ride along as one row per |q|
+    // (bulk copies need NA % 4 == 0, which also aligns the rows; other NA take the cp.async staging path)
+    rc = plan_scan(ctx, s, NQ, vmax, uniform, plan);
+    if (rc) return rc;
     bool all_ready = true;
     for (auto &c : ctx->chunks)
         if (cudaEventQuery(c.ready) != cudaSuccess) all_ready = false;
@@ -844,7 +846,7 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
     std::vector<double> q(3 * NM);
     ctx->scan_kinds[0] = ctx->scan_kinds[1] = ctx->scan_kinds[2] = 0;
     for (auto &ps : plan) {
-        ctx->scan_kinds[ps.kind]++;
+        ctx->scan_kinds[ps.kind == 3 ? 0 : ps.kind]++;
         if (ps.kind == 2) {
             for (size_t i = 0; i < 3 * NM; i++) q[i] = ps.s0 * v[i];
             CK(cudaStreamSynchronize(ctx->stream));  // d_qs may still be read by the previous pass
@@ -866,9 +868,10 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
         }
         for (auto &c : spans) {
             if (c.ready) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
-            const int l = launch_amplitude_scan_pass(xyz, d_b, ctx->d_qs, ps.s0, ps.ds, ps.nq, ps.kind == 1 ? ps.kappa.data() : nullptr,
-                                                     A + ps.n0 * strideQ, NFt, strideQ, ctx->NA, NM, ctx->f_first + c.f0, c.nf,
-                                                     ctx->stream);
+            const int l = launch_amplitude_scan_pass(xyz, d_b + (ps.kind == 3 ? ps.n0 * ctx->NA : 0), ctx->d_qs, ps.s0, ps.ds, ps.nq,
+                                                     ps.kind == 1 ? ps.kappa.data() : nullptr, A + ps.n0 * strideQ, NFt, strideQ,
+                                                     ctx->NA, NM, ctx->f_first + c.f0, c.nf, ctx->stream,
+                                                     ps.kind == 3 ? ctx->NA : 0);
             if (l < 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": internal error, scan pass too long");
             ctx->launches += l;
         }

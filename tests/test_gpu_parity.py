@@ -352,19 +352,33 @@ def test_all_vectors_scan_other_dsp_and_unaligned_atoms(gpu_ctx, oracle, dsp):
         assert abs(fq[n] - r[1]) < TOL * max(abs(r[1]), abs(r[0]).max())
 
 
-def test_all_vectors_scan_per_q_factors(gpu_ctx, oracle):
-    """|q|-dependent factors (X-ray form factors / background): a batch with differing rows falls back to the general
-    kernel per |q|; a batch with identical rows takes the scan kernel.  Both equal the oracle."""
-    xyz, b, u = small_case(NA=160, NF=16, NM=23)
+@pytest.mark.parametrize("NA", [160, 203])
+def test_all_vectors_scan_per_q_factors(gpu_ctx, oracle, NA):
+    """|q|-dependent factors (X-ray form factors / background): equally spaced |q| take the scan kernel with one factor row
+    per |q| staged next to the coordinates (NA % 4 == 0: TMA rows, otherwise cp.async); a float-rounded scan with
+    differing rows falls back to the general kernel per |q|; identical rows count as uniform.  All equal the oracle."""
+    xyz, b, u = small_case(NA=NA, NF=16, NM=23)
+    for NQ in (5, 27):
+        s = 0.2 + 0.3 * np.arange(NQ)
+        gpu_ctx.stage_frames(xyz)
+        bq = np.stack([b * (1.0 + 0.1 * n) - 0.05 * n for n in range(NQ)])
+        gpu_ctx.set_factors_batch(bq)
+        fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+        plain, corr, single = gpu_ctx.last_scan_plan()
+        assert plain >= 1 and corr == 0 and single == 0
+        for n in range(NQ):
+            r = oracle.compute_all_vectors(xyz, bq[n], s[n] * u)
+            assert rel_err(fqt[n], r[0]) < TOL
+            assert abs(fq[n] - r[1]) < TOL * abs(r[0][0])
     NQ = 5
     s = 0.2 + 0.3 * np.arange(NQ)
-    gpu_ctx.stage_frames(xyz)
-    bq = np.stack([b * (1.0 + 0.1 * n) - 0.05 * n for n in range(NQ)])
+    bq = bq[:NQ]
     gpu_ctx.set_factors_batch(bq)
-    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)
+    s_rounded = s * (1 + 1e-8 * np.array([0, 1, -1, 2, 0]))
+    fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s_rounded)
     assert gpu_ctx.last_scan_plan() == (0, 0, NQ)
     for n in range(NQ):
-        r = oracle.compute_all_vectors(xyz, bq[n], s[n] * u)
+        r = oracle.compute_all_vectors(xyz, bq[n], s_rounded[n] * u)
         assert rel_err(fqt[n], r[0]) < TOL
     gpu_ctx.set_factors_batch(np.stack([b] * NQ))
     fqt, fq, fq2 = gpu_ctx.compute_all_vectors_scan(u, s)

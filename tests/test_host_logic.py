@@ -269,6 +269,18 @@ def test_run_scatter_scan_batching(oracle):
     for r, q in zip(recs, scan):
         ref = oracle.compute_all_vectors(xyz, b, pc.init_subvectors(q))
         assert np.allclose(r["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+    # scan_snap: a float-rounded 7-point scan is moved onto the exact progression and the snapped q-vectors are written
+    rounded = host.create_from_scans([{"base": (0, 1, 0), "from": 0.1, "to": 1.3, "points": 7}])
+    sr = np.linalg.norm(rounded, axis=1)
+    assert np.max(np.abs(np.diff(sr, 2))) > 1e-10
+    recs, _, _ = host.run_scatter(params(limits__computation__scan_snap=True), xyz, rounded, b=b, backend=be.vtbl)
+    snapped = np.array([r["q"] for r in recs])
+    assert np.max(np.abs(np.diff(np.linalg.norm(snapped, axis=1), 2))) < 1e-15
+    assert np.allclose(snapped, rounded, rtol=1e-6) and not np.array_equal(snapped, rounded)
+    ref = oracle.compute_all_vectors(xyz, b, p.init_subvectors(snapped[3]))
+    assert np.allclose(recs[3]["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+    recs, _, _ = host.run_scatter(params(), xyz, rounded, b=b, backend=be.vtbl)
+    assert np.array_equal(np.array([r["q"] for r in recs]), rounded)  # default: the reference's q-vectors, untouched
     # switched off
     recs, _, tm = host.run_scatter(params(limits__computation__scan=1), xyz, scan, b=b, backend=be.vtbl)
     assert "sd:c:scan" not in tm and tm["sd:compute"][1] == 5 and len(recs) == 5

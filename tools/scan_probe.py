@@ -26,6 +26,8 @@ def main():
     b = synth.factors(NA)
     ctx.set_factors(b)
     u = synth.unit_vectors(NM, 6)
+    if os.environ.get('VARB'):  # |q|-dependent factors: one row per |q|
+        ctx.set_factors_batch(np.stack([b * (1.0 + 0.01 * n) for n in range(NQ)]))
     s0, ds = 0.1, 0.1
     sv = s0 + ds * np.arange(NQ)
     if os.environ.get('ROUNDED'):  # the reference's float-rounded scan fractions
