@@ -700,9 +700,52 @@ void load_frames(const Config &cfg, LoadedSample &s) {
             s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
         s.NF += fs.number_of_frames * (clones ? clones : 0);
     };
+    // PDBFrameset (frames.cpp:442-577): frames end at lines starting with "END" (END / ENDMDL), a trailing unterminated
+    // frame counts, coordinates are columns 31-38 / 39-46 / 47-54 of the ATOM records.  A frame without ATOM records (the
+    // "ENDMDL" + "END" tail of multi-model files) is dropped here; the reference would index it as a 0-atom frame.
+    auto add_pdb = [&](const std::string &path, const SampleFramesetParameters &f, size_t clones) {
+        std::ifstream in(path.c_str());
+        if (in.fail()) throw Error("Couldn't open frameset file: " + path);
+        std::vector<std::vector<float>> frames;
+        std::vector<float> cur;
+        std::string line;
+        auto close_frame = [&]() {
+            if (!cur.empty()) {
+                if (cur.size() != natoms * 3)
+                    throw Error("Atom number mismatch (pdb frameset) " + std::to_string(cur.size() / 3) + " vs. (structure) " +
+                                std::to_string(natoms));
+                frames.push_back(cur);
+            }
+            cur.clear();
+        };
+        while (getline(in, line)) {
+            if (line.compare(0, 6, "ATOM  ") == 0) {
+                if (line.size() < 54) throw Error("short ATOM record in " + path);
+                cur.push_back((float)atof(line.substr(30, 8).c_str()));
+                cur.push_back((float)atof(line.substr(38, 8).c_str()));
+                cur.push_back((float)atof(line.substr(46, 8).c_str()));
+            } else if (line.compare(0, 3, "END") == 0) {
+                close_frame();
+            }
+        }
+        close_frame();
+        const size_t before = s.frames.size();
+        size_t kept = 0;
+        for (size_t i = 0; i < frames.size(); i++) {  // FileFrameset::trim_index (frames.cpp:224-245)
+            if (i < f.first || (f.last_set && i > f.last) || (f.stride > 1 && i % f.stride != 0)) continue;
+            for (size_t a = 0; a < NT; a++)
+                for (int c = 0; c < 3; c++) s.frames.push_back(frames[i][3 * s.target[a] + c]);
+            kept++;
+        }
+        const size_t block = s.frames.size() - before;
+        for (size_t c = 1; c < clones; c++) s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
+        s.NF += kept * clones;
+    };
     for (auto &f : cfg.framesets) {
         if (f.clones == 0) continue;
-        if (f.format == "dcd") {
+        if (f.format == "pdb") {
+            add_pdb(f.filepath, f, f.clones);
+        } else if (f.format == "dcd") {
             add_dcd(f.filepath, f, f.clones);
         } else if (f.format == "dcdlist") {
             std::ifstream list(f.filepath.c_str());
@@ -713,7 +756,7 @@ void load_frames(const Config &cfg, LoadedSample &s) {
                 for (size_t c = 0; c < f.clones; c++) add_dcd(cfg.get_filepath(line), f, 1);
             }
         } else {
-            throw Error("frameset format '" + f.format + "' is not supported by this build yet (dcd, dcdlist are)");
+            throw Error("frameset format '" + f.format + "' is not supported by this build yet (dcd, dcdlist, pdb are)");
         }
     }
     if (s.NF < 1) throw Error("No frames available. Aborting");

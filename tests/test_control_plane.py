@@ -205,6 +205,38 @@ def test_config_selections_framesets_and_scans(tmp_path):
     assert job.nqvectors == 3 and np.array_equal(job.qvectors(), q)
 
 
+def test_pdb_frameset(tmp_path):
+    """PDBFrameset (frames.cpp:442-577): frames end at END/ENDMDL lines, an unterminated last frame counts, the
+    ENDMDL+END tail does not add a frame; first/stride/clones apply as for DCD; coordinates come from columns 31-54."""
+    cfg, xyz, names = make_case(tmp_path, NA=12, NF=6, scattering=SCAN,
+                                framesets="<frameset><file>traj.pdb</file><format>pdb</format><first>1</first>"
+                                          "<stride>2</stride><clones>2</clones></frameset>")
+    with open(tmp_path / "traj.pdb", "w") as f:
+        f.write("CRYST1   30.000   30.000   30.000  90.00  90.00  90.00 P 1           1\n")
+        for fr in range(6):
+            f.write("MODEL %8d\n" % (fr + 1))
+            for i, n in enumerate(names):
+                x, y, z = xyz[fr, i]
+                nm = n if len(n) == 4 else " " + n.ljust(3)
+                f.write("ATOM  %5d %4s ALA A%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (i + 1, nm, 1, x, y, z, 1.0, 0.0))
+            f.write("ENDMDL\n" if fr < 5 else "")  # last frame left unterminated
+    job = host.Job(cfg)
+    # frames 1, 3, 5 pass (i >= 1, i % 2 == 0 never true for odd i -> absolute index rule keeps i = 2, 4)
+    keep = [i for i in range(6) if i >= 1 and i % 2 == 0]
+    assert job.nframes == 2 * len(keep)
+    expect = np.round(xyz[keep].astype(np.float64), 3).astype(np.float32)
+    got = job.frames()
+    assert np.allclose(got[:len(keep)], expect, atol=6e-4) and np.array_equal(got[:len(keep)], got[len(keep):])
+    # a terminated tail ("ENDMDL" + "END") does not create an empty frame; a wrong atom count raises
+    with open(tmp_path / "traj.pdb", "a") as f:
+        f.write("ENDMDL\nEND\n")
+    assert host.Job(cfg).nframes == 2 * len(keep)
+    with open(tmp_path / "traj.pdb", "a") as f:
+        f.write("ATOM      1  CA  ALA A   1       1.000   2.000   3.000  1.00  0.00\nEND\n")
+    with pytest.raises(host.HostError, match="Atom number mismatch"):
+        host.Job(cfg)
+
+
 def test_scatter_factors_match_reference_formulas(tmp_path):
     bg = """<background><factor>0.0334</factor><kappas>
       <kappa><selection>solvent</selection><value>1.5</value></kappa></kappas></background>"""
@@ -251,7 +283,7 @@ def test_config_errors(tmp_path):
     with pytest.raises(host.HostError, match="No q vectors"):
         host.Job(variant("<points>3</points>", "<points>0</points>"))
     with pytest.raises(host.HostError, match="not supported"):
-        host.Job(variant("<format>dcd</format>", "<format>xtc</format>"))
+        host.Job(variant("<frameset><file>traj.dcd</file><format>dcd</format>", "<frameset><file>traj.dcd</file><format>xtc</format>"))
     with pytest.raises(host.HostError, match="obsolete"):
         host.Job(variant("<scattering>", "<scattering><target>system</target>"))
     # unknown and ambiguous atom names (database.cpp:308-340)
