@@ -9,7 +9,7 @@ ctx = sassena_b200.ScatterContext(0)
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 if which in ("all", "self"):
-    NA, NF, NM = int(os.environ.get("SELF_NA", 512)), 10000, 200
+    NA, NF, NM = int(os.environ.get("SELF_NA", 512)), int(os.environ.get("SELF_NF", 10000)), 200
     d = ctx.device_alloc(NA * NF * 12)
     ctx.synth_trajectory(d, NF, 30000, 70.0, 0.05, 3, layout=1, NA_out=NA)
     ctx.stage_atoms_device(d, NA, NF)
