@@ -122,6 +122,16 @@ void sass_dcd_close(sass_dcd *d);
 /* writes xyz[NF][NA][3] as a CHARMM DCD the reference's reader accepts (stager.dump format) */
 int sass_dcd_write(const char *path, const float *xyz, size_t NF, size_t NA);
 
+/* ---- GROMACS XTC / TRR trajectories (reference: src/sample/frames.cpp:592-858 through the xdrfile library) ---------
+ * format: "xtc" or "trr".  Coordinates come back in Angstrom, (float)(10.0 * nm), frame-major like sass_dcd_read. */
+typedef struct sass_xdr sass_xdr;
+int sass_xdr_open(const char *path, const char *format, size_t first, size_t last, int last_set, size_t stride,
+                  sass_xdr **out);
+int sass_xdr_info(const sass_xdr *d, size_t *nframes, size_t *natoms);
+/* out[count][natoms][3]; box (may be NULL) [count][9] doubles in Angstrom */
+int sass_xdr_read(sass_xdr *d, size_t first, size_t count, float *out, double *box);
+void sass_xdr_close(sass_xdr *d);
+
 /* ---- control plane: scatter.xml + db.xml + PDB + DCD -> hot path ("next" row) ------------------------
  * Replaces, for one process, the flow of the reference executable src/main/sassena.cpp:132-417:
  *   Params::init/read_xml   src/control/parameters.cpp:64-792

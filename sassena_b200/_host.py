@@ -86,6 +86,10 @@ SIGNATURES = {
     "sass_dcd_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "sass_dcd_close": (None, [C.c_void_p]),
     "sass_dcd_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "sass_xdr_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "sass_xdr_info": (C.c_int, [C.c_void_p, c_size_p, c_size_p]),
+    "sass_xdr_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "sass_xdr_close": (None, [C.c_void_p]),
     "sass_init_subvectors": (C.c_size_t, [C.c_void_p, c_double_p, c_double_p, C.c_size_t]),
     "sass_job_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "sass_job_free": (None, [C.c_void_p]),

@@ -11,6 +11,7 @@
 #include <sstream>
 
 #include "dcd.hpp"
+#include "xdr_traj.hpp"
 
 namespace sassena {
 
@@ -741,10 +742,41 @@ void load_frames(const Config &cfg, LoadedSample &s) {
         for (size_t c = 1; c < clones; c++) s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
         s.NF += kept * clones;
     };
+    // XTCFrameset / TRRFrameset (frames.cpp:592-858).  The reference insists on a pre-built .tnx frame index for these
+    // formats (frames.cpp:133-139); the index is rebuilt in memory here, so none is needed.
+    auto add_xdr = [&](XdrFrameset &fs, const char *what, const SampleFramesetParameters &f, size_t clones) {
+        if (fs.number_of_atoms != natoms)
+            throw Error(std::string("Atom number mismatch (") + what + ") " + std::to_string(fs.number_of_atoms) + " vs. (pdb) " +
+                        std::to_string(natoms));
+        fs.trim_index(f.first, f.last, f.last_set, f.stride);
+        const size_t before = s.frames.size();
+        for (size_t i = 0; i < fs.number_of_frames; i++) {
+            fs.read_frame(i, buf.data());
+            for (size_t a = 0; a < NT; a++)
+                for (int c = 0; c < 3; c++) s.frames.push_back(buf[3 * s.target[a] + c]);
+        }
+        const size_t block = s.frames.size() - before;
+        for (size_t c = 1; c < clones; c++) s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
+        s.NF += fs.number_of_frames * clones;
+    };
     for (auto &f : cfg.framesets) {
         if (f.clones == 0) continue;
         if (f.format == "pdb") {
             add_pdb(f.filepath, f, f.clones);
+        } else if (f.format == "pdblist") {  // frames.cpp:113-126
+            std::ifstream list(f.filepath.c_str());
+            if (list.fail()) throw Error("Couldn't open pdblist file: " + f.filepath);
+            std::string line;
+            while (list >> line) {
+                if (!line.empty() && line[0] == '#') continue;
+                for (size_t c = 0; c < f.clones; c++) add_pdb(cfg.get_filepath(line), f, 1);
+            }
+        } else if (f.format == "xtc") {
+            XTCFrameset fs(f.filepath);
+            add_xdr(fs, "xtc", f, f.clones);
+        } else if (f.format == "trr") {
+            TRRFrameset fs(f.filepath);
+            add_xdr(fs, "trr", f, f.clones);
         } else if (f.format == "dcd") {
             add_dcd(f.filepath, f, f.clones);
         } else if (f.format == "dcdlist") {
@@ -756,7 +788,7 @@ void load_frames(const Config &cfg, LoadedSample &s) {
                 for (size_t c = 0; c < f.clones; c++) add_dcd(cfg.get_filepath(line), f, 1);
             }
         } else {
-            throw Error("frameset format '" + f.format + "' is not supported by this build yet (dcd, dcdlist, pdb are)");
+            throw Error("frameset format '" + f.format + "' is not supported (dcd, dcdlist, pdb, pdblist, xtc, trr are)");
         }
     }
     if (s.NF < 1) throw Error("No frames available. Aborting");

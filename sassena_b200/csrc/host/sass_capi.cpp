@@ -6,10 +6,14 @@
 
 #include "control.hpp"
 #include "dcd.hpp"
+#include "xdr_traj.hpp"
 #include "sassena_host.hpp"
 
 using namespace sassena;
 
+struct sass_xdr {
+    std::unique_ptr<sassena::XdrFrameset> fs;
+};
 struct sass_dcd {
     sassena::DCDFrameset fs;
     explicit sass_dcd(const std::string &p) : fs(p) {}
@@ -326,6 +330,39 @@ int sass_dcd_write(const char *path, const float *xyz, size_t NF, size_t NA) {
         w.write(xyz, 0, NF);
     });
 }
+
+int sass_xdr_open(const char *path, const char *format, size_t first, size_t last, int last_set, size_t stride,
+                  sass_xdr **out) {
+    return guard([&] {
+        if (!path || !format || !out) throw Error("sass_xdr_open: NULL argument");
+        std::unique_ptr<sass_xdr> d(new sass_xdr());
+        const std::string f(format);
+        if (f == "xtc")
+            d->fs.reset(new XTCFrameset(path));
+        else if (f == "trr")
+            d->fs.reset(new TRRFrameset(path));
+        else
+            throw Error("sass_xdr_open: format must be xtc or trr");
+        d->fs->trim_index(first, last, last_set != 0, stride);
+        *out = d.release();
+    });
+}
+int sass_xdr_info(const sass_xdr *d, size_t *nframes, size_t *natoms) {
+    return guard([&] {
+        if (!d) throw Error("sass_xdr_info: NULL argument");
+        if (nframes) *nframes = d->fs->number_of_frames;
+        if (natoms) *natoms = d->fs->number_of_atoms;
+    });
+}
+int sass_xdr_read(sass_xdr *d, size_t first, size_t count, float *out, double *box) {
+    return guard([&] {
+        if (!d || !out) throw Error("sass_xdr_read: NULL argument");
+        if (first + count > d->fs->number_of_frames) throw Error("sass_xdr_read: frame range out of bounds");
+        const size_t na = d->fs->number_of_atoms;
+        for (size_t i = 0; i < count; i++) d->fs->read_frame(first + i, out + i * na * 3, box ? box + 9 * i : nullptr);
+    });
+}
+void sass_xdr_close(sass_xdr *d) { delete d; }
 
 }  // extern "C"
 

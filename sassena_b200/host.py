@@ -103,6 +103,39 @@ class DCDFile:
             pass
 
 
+class XdrFile:
+    """XTCFrameset / TRRFrameset (frames.cpp:592-858): GROMACS trajectories, coordinates in Angstrom."""
+
+    def __init__(self, path, format=None, first=0, last=None, stride=1):
+        if format is None:
+            format = "trr" if str(path).lower().endswith(".trr") else "xtc"
+        h = C.c_void_p()
+        _ck(_lib().sass_xdr_open(str(path).encode(), format.encode(), first, 0 if last is None else last,
+                                 0 if last is None else 1, stride, C.byref(h)))
+        self.h = h
+        nf, na = C.c_size_t(), C.c_size_t()
+        _ck(_lib().sass_xdr_info(self.h, C.byref(nf), C.byref(na)))
+        self.number_of_frames, self.number_of_atoms = nf.value, na.value
+
+    def read(self, first=0, count=None, with_box=False):
+        count = self.number_of_frames - first if count is None else count
+        out = np.empty((count, self.number_of_atoms, 3), dtype=np.float32)
+        box = np.zeros((count, 3, 3)) if with_box else None
+        _ck(_lib().sass_xdr_read(self.h, first, count, out.ctypes.data, box.ctypes.data if with_box else None))
+        return (out, box) if with_box else out
+
+    def close(self):
+        if self.h:
+            _lib().sass_xdr_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def write_dcd(path, xyz):
     """xyz float32 [NF][NA][3] -> CHARMM DCD in the layout of the reference's DCDCoordinateWriter."""
     a = np.ascontiguousarray(xyz, dtype=np.float32)

@@ -283,6 +283,8 @@ def test_config_errors(tmp_path):
     with pytest.raises(host.HostError, match="No q vectors"):
         host.Job(variant("<points>3</points>", "<points>0</points>"))
     with pytest.raises(host.HostError, match="not supported"):
+        host.Job(variant("<frameset><file>traj.dcd</file><format>dcd</format>", "<frameset><file>traj.dcd</file><format>crd</format>"))
+    with pytest.raises(host.HostError, match="appears not to be a XTC file"):
         host.Job(variant("<frameset><file>traj.dcd</file><format>dcd</format>", "<frameset><file>traj.dcd</file><format>xtc</format>"))
     with pytest.raises(host.HostError, match="obsolete"):
         host.Job(variant("<scattering>", "<scattering><target>system</target>"))
