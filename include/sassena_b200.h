@@ -86,6 +86,15 @@ int sgpu_stage_atoms_device(sgpu_ctx *ctx, const float *d_xyz, size_t NA_local, 
 int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t nranks,
                                  size_t rank);
 
+/* The same for a WAVE of atoms: stages atoms atom_first + i*atom_stride, i < count (a slice of a rank's ModAssignment
+ * list), for trajectories whose per-rank share exceeds the coordinate budget (BASELINE config 5: the stager streams
+ * the atoms through the GPU wave by wave; partials are additive over atoms, see sgpu_accumulate). */
+int sgpu_stage_atoms_wave(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t atom_first, size_t atom_stride,
+                          size_t count);
+/* d_dst[i] += d_src[i], i < n doubles in device memory, on the context's compute stream (sums the packed partials of
+ * successive atom waves; fixed order, no atomics). */
+int sgpu_accumulate(sgpu_ctx *ctx, double *d_dst, const double *d_src, size_t n);
+
 /* ScatterFactors::get_all() for the current |q| (src/scatter_devices/scatter_factors.cpp:56-78,100):
  * b has one entry per staged atom (NA for frames, NA_local for atoms, in staged order). */
 int sgpu_set_factors(sgpu_ctx *ctx, const double *b, size_t n);

@@ -60,6 +60,9 @@ typedef struct sass_backend_vtbl {
     /* |q|-scan coherent path */
     int (*compute_all_vectors_scan_partial)(sgpu_ctx *, const double *, size_t, const double *, size_t, int, double *);
     int (*all_vectors_scan_amplitudes)(sgpu_ctx *, const double *, size_t, const double *, size_t, double *);
+    /* atom waves of the self path (trajectory share larger than limits.stage.memory.data) */
+    int (*stage_atoms_wave)(sgpu_ctx *, const float *, size_t, size_t, size_t, size_t, size_t);
+    int (*accumulate)(sgpu_ctx *, double *, const double *, size_t);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);
@@ -71,7 +74,8 @@ void sass_params_free(sass_params *p);
 /* keys: scattering.type, scattering.dsp.type, scattering.dsp.method, scattering.average.orientation.type,
  * scattering.average.orientation.axis.{x,y,z}, scattering.average.orientation.vectors.{type,algorithm,resolution,seed},
  * scattering.average.orientation.multipole.type, scattering.average.orientation.multipole.moments.{type,resolution},
- * limits.stage.memory.data, limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size},
+ * limits.stage.memory.data, limits.stage.stream (self: stream atom waves when the share exceeds the budget; default
+ * true), limits.decomposition.utilization, limits.decomposition.partitions.{automatic,size},
  * limits.decomposition.coherent (auto | frames | vectors: how a partition's ranks share one coherent |q|),
  * limits.computation.scan (largest |q| batch of the coherent scan path; 0 or 1 = one |q| per pass),
  * limits.computation.scan_snap (true: |q| equally spaced to within 1e-6 are moved onto the exact progression; off by

@@ -41,6 +41,8 @@ BE_AV_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_void_p
 BE_AV_DSP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p)
 BE_AV_SCAN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_int, C.c_void_p)
 BE_AV_SCAN_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_void_p)
+BE_STAGE_WAVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t)
+BE_ACCUMULATE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -55,7 +57,8 @@ class BackendVtbl(C.Structure):
                 ("set_factors_batch", BE_SET_FACTORS_BATCH), ("mpsphere_amplitudes", BE_MP_AMPL),
                 ("mpsphere_dsp_partial", BE_MP_DSP), ("set_frame_window", BE_SET_WINDOW),
                 ("all_vectors_amplitudes", BE_AV_AMPL), ("all_vectors_dsp_partial", BE_AV_DSP),
-                ("compute_all_vectors_scan_partial", BE_AV_SCAN), ("all_vectors_scan_amplitudes", BE_AV_SCAN_AMPL)]
+                ("compute_all_vectors_scan_partial", BE_AV_SCAN), ("all_vectors_scan_amplitudes", BE_AV_SCAN_AMPL),
+                ("stage_atoms_wave", BE_STAGE_WAVE), ("accumulate", BE_ACCUMULATE)]
 
 
 FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)

@@ -35,6 +35,8 @@ SIGNATURES = {
     "sgpu_stage_atoms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_from_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "sgpu_stage_atoms_wave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "sgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sgpu_set_factors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),
     "sgpu_compute_all_vectors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
     "sgpu_compute_self_vectors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),

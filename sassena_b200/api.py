@@ -157,6 +157,17 @@ class ScatterContext:
         self._NFt = 0
         self.NA = NA // nranks + (1 if rank < NA % nranks else 0)
 
+    def stage_atoms_wave(self, xyz, atom_first, atom_stride, count):
+        """atoms atom_first + i*atom_stride, i < count, of frame-major xyz [NF][NA][3] (one wave of a streamed self run)"""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        self._ck(self.lib.sgpu_stage_atoms_wave(self.h, a.ctypes.data, a.shape[0], a.shape[1], atom_first, atom_stride, count))
+        self.NF = a.shape[0]
+        self._NFt = 0
+        self.NA = count
+
+    def accumulate(self, d_dst: int, d_src: int, n: int):
+        self._ck(self.lib.sgpu_accumulate(self.h, C.c_void_p(d_dst), C.c_void_p(d_src), n))
+
     def set_factors(self, b):
         b = np.ascontiguousarray(b, dtype=np.float64)
         self._ck(self.lib.sgpu_set_factors(self.h, _dp(b), b.size))

@@ -424,6 +424,7 @@ void Config::read_xml(const std::string &filename) {
     if (x.exists("//scattering/signal/fq2")) signal_fq2 = x.get_bool("//scattering/signal/fq2");
     // ---- limits (parameters.cpp:612-736): the keys the GPU path keeps ----
     if (x.exists("//limits/stage/memory/data")) limits.stage_memory_data = x.get_size("//limits/stage/memory/data");
+    if (x.exists("//limits/stage/stream")) limits.stage_stream = x.get_bool("//limits/stage/stream");
     if (x.exists("//limits/decomposition/utilization"))
         limits.decomposition.utilization = x.get_double("//limits/decomposition/utilization");
     if (x.exists("//limits/decomposition/partitions/automatic"))

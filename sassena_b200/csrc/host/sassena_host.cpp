@@ -327,7 +327,9 @@ const SgpuBackend &default_backend() {
                                    sgpu_all_vectors_amplitudes,
                                    sgpu_all_vectors_dsp_partial,
                                    sgpu_compute_all_vectors_scan_partial,
-                                   sgpu_all_vectors_scan_amplitudes};
+                                   sgpu_all_vectors_scan_amplitudes,
+                                   sgpu_stage_atoms_wave,
+                                   sgpu_accumulate};
     return be;
 }
 
@@ -484,17 +486,18 @@ double *AbstractScatterDevice::partial_buffer(int dsp_type) {
 
 // the three boost::mpi::reduce calls of compute() (all_vectors_scatter_device.cpp:324-352) as one all-reduce of the
 // packed partial, followed by the inverse transform / scaling on every rank (rank 0 of the partition writes)
-void AbstractScatterDevice::reduce_and_finalize(int dsp_type, double scale) {
+void AbstractScatterDevice::reduce_and_finalize(int dsp_type, double scale, double *d_partial) {
+    if (!d_partial) d_partial = d_partial_;
     size_t len = 0;
     ck(be_.partial_len(ctx_, dsp_type, &len), "sgpu_partial_len");
     timer_.start("sd:c:wait");
     ck(be_.synchronize(ctx_), "sgpu_synchronize");
     timer_.stop("sd:c:wait");
     timer_.start("sd:c:reduce");
-    if (partitioncomm_->size() > 1) partitioncomm_->allreduce_sum(d_partial_, len);
+    if (partitioncomm_->size() > 1) partitioncomm_->allreduce_sum(d_partial, len);
     timer_.stop("sd:c:reduce");
     double af[2], a2f[2];
-    ck(be_.finalize(ctx_, d_partial_, dsp_type, dsp_method_code(), scale, atfinal_.data(), af, a2f), "sgpu_finalize");
+    ck(be_.finalize(ctx_, d_partial, dsp_type, dsp_method_code(), scale, atfinal_.data(), af, a2f), "sgpu_finalize");
     afinal_ = std::complex<double>(af[0], af[1]);
     a2final_ = std::complex<double>(a2f[0], a2f[1]);
 }
@@ -865,23 +868,33 @@ SelfVectorsScatterDevice::SelfVectorsScatterDevice(std::shared_ptr<ICommunicator
     : AbstractVectorsScatterDevice(allcomm, partitioncomm, sample, vectors, NAF, sink, params, be, ctx),
       assignment_(partitioncomm->size(), partitioncomm->rank(), NAF) {}
 
-void SelfVectorsScatterDevice::stage_data() {
-    DataStagerByAtom data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
-    data_stager.stage();
-    factors_.assign(NA, 0.0);
+SelfVectorsScatterDevice::~SelfVectorsScatterDevice() {
+    if (d_acc_) be_.device_free(d_acc_);
 }
 
-void SelfVectorsScatterDevice::compute() {
+void SelfVectorsScatterDevice::stage_data() {
+    factors_.assign(NA, 0.0);
+    const size_t atom_bytes = NF * 3 * sizeof(float);
+    const size_t share = assignment_.max() * atom_bytes;  // data_stager.cpp:194-204
+    if (share > params_.limits.stage_memory_data && params_.limits.stage_stream) {
+        // the share does not fit the coordinate budget: waves of as many atoms as do; staged inside runner()
+        streamed_ = true;
+        wave_atoms_ = std::max<size_t>(1, params_.limits.stage_memory_data / atom_bytes);
+        waves_ = (assignment_.size() + wave_atoms_ - 1) / wave_atoms_;
+        return;
+    }
+    DataStagerByAtom data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
+    data_stager.stage();
+}
+
+void SelfVectorsScatterDevice::compute_partial(size_t first, size_t count, int dsp, double *d_out) {
     CartesianCoor3D q = vectors_[current_vector_];
     timer_.start("sd:c:init");
     init_subvectors(q);
     sample_.factors(q.length(), factors_.data());
-    // scatterfactors.get(assignment_[ai]) (:291): factors of this rank's atoms in staged order
-    std::vector<double> mine(std::max<size_t>(assignment_.size(), 1));
-    for (size_t i = 0; i < assignment_.size(); i++) mine[i] = factors_[assignment_[i]];
-    const int dsp = dsp_type_code();
-    dsp_method_code();
-    double *partial = partial_buffer(dsp);
+    // scatterfactors.get(assignment_[ai]) (:291): factors of the staged atoms in staged order
+    std::vector<double> mine(std::max<size_t>(count, 1));
+    for (size_t i = 0; i < count; i++) mine[i] = factors_[assignment_[first + i]];
     std::vector<double> qv(3 * NM);
     for (size_t i = 0; i < NM; i++) {
         qv[3 * i] = subvector_index_[i].x;
@@ -890,15 +903,69 @@ void SelfVectorsScatterDevice::compute() {
     }
     timer_.stop("sd:c:init");
     timer_.start("sd:c:block");
-    if (assignment_.size() > 0) {
-        ck(be_.set_factors(ctx_, mine.data(), assignment_.size()), "sgpu_set_factors");
-        ck(be_.compute_self_vectors_partial(ctx_, qv.data(), NM, dsp, partial), "sgpu_compute_self_vectors_partial");
+    if (count > 0) {
+        ck(be_.set_factors(ctx_, mine.data(), count), "sgpu_set_factors");
+        ck(be_.compute_self_vectors_partial(ctx_, qv.data(), NM, dsp, d_out), "sgpu_compute_self_vectors_partial");
     } else {
         // a rank without atoms contributes zeros: an empty q-list zeroes the partial
-        ck(be_.compute_self_vectors_partial(ctx_, qv.data(), 0, dsp, partial), "sgpu_compute_self_vectors_partial");
+        ck(be_.compute_self_vectors_partial(ctx_, qv.data(), 0, dsp, d_out), "sgpu_compute_self_vectors_partial");
     }
     current_subvector_ = NM;
     timer_.stop("sd:c:block");
+}
+
+// Streamed runner: the reference's loop is |q|-outer with all of the rank's atoms resident (runner(),
+// abstract_scatter_device.cpp:162-173).  When they are not, the loops are exchanged -- every wave of atoms is staged once
+// and evaluated for all |q| of the partition -- and the packed partials, which are sums over atoms, accumulate per |q|.
+// The all-reduce over the partition and the write happen per |q| after the last wave, in the reference's order.
+void SelfVectorsScatterDevice::runner() {
+    if (!streamed_) {
+        AbstractScatterDevice::runner();
+        return;
+    }
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    const size_t nq = vectors_.size();
+    size_t plen = 0;
+    for (size_t w = 0; w < std::max<size_t>(waves_, 1); w++) {
+        const size_t first = w * wave_atoms_;
+        const size_t count = waves_ ? std::min(wave_atoms_, assignment_.size() - first) : 0;
+        timer_.start("sd:stage");
+        if (count > 0) {
+            ck(be_.stage_atoms_wave(ctx_, sample_.frames, NF, NA, assignment_[first], partitioncomm_->size(), count),
+               "sgpu_stage_atoms_wave");
+        }
+        timer_.stop("sd:stage");
+        if (w == 0) {
+            partial_buffer(dsp);
+            ck(be_.partial_len(ctx_, dsp, &plen), "sgpu_partial_len");
+            void *p = nullptr;
+            if (be_.device_alloc(&p, nq * plen * sizeof(double))) throw Error("device allocation of the wave accumulators failed");
+            d_acc_ = static_cast<double *>(p);
+        }
+        timer_.start("sd:compute");
+        for (current_vector_ = 0; current_vector_ < nq; current_vector_++) {
+            double *acc = d_acc_ + current_vector_ * plen;
+            // the first wave writes the accumulator, later waves add to it
+            compute_partial(first, count, dsp, w == 0 ? acc : d_partial_);
+            if (w > 0) ck(be_.accumulate(ctx_, acc, d_partial_, plen), "sgpu_accumulate");
+        }
+        timer_.stop("sd:compute");
+    }
+    for (current_vector_ = 0; current_vector_ < nq;) {
+        init_subvectors(vectors_[current_vector_]);
+        reduce_and_finalize(dsp, 1.0 / subvector_index_.size(), d_acc_ + current_vector_ * plen);  // :233-238
+        timer_.start("sd:write");
+        write();
+        timer_.stop("sd:write");
+        next();
+    }
+}
+
+void SelfVectorsScatterDevice::compute() {
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    compute_partial(0, assignment_.size(), dsp, partial_buffer(dsp));
     reduce_and_finalize(dsp, 1.0 / subvector_index_.size());  // :233-238
 }
 
@@ -1046,7 +1113,9 @@ IScatterDevice *ScatterDeviceFactory::create(std::shared_ptr<ICommunicator> scat
         throw Error("Scattering Interference type not understood. Must be 'self' or 'all'.");
     }
     // every rank evaluates the (deterministic) plan; the reference computes it on rank 0 and broadcasts (:95-102)
-    DecompositionPlan dplan(NN, NQ, NAF, ELBYTESIZE, params.limits.stage_memory_data, params.limits.decomposition);
+    // a self run whose atoms stream through the GPU in waves is not constrained by the coordinate budget
+    const size_t plan_limit = (stype == "self" && params.limits.stage_stream) ? (size_t)-1 : params.limits.stage_memory_data;
+    DecompositionPlan dplan(NN, NQ, NAF, ELBYTESIZE, plan_limit, params.limits.decomposition);
     size_t partitions = dplan.partitions();
     size_t partitionsize = dplan.partitionsize();
 

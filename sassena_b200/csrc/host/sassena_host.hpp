@@ -172,6 +172,10 @@ struct ScatteringParameters {
 struct LimitsParameters {
     // limits.stage.memory.data re-targeted: bytes of coordinates one GPU may hold (default 150 GB of the 180 GB HBM3e)
     size_t stage_memory_data = (size_t)150 << 30;
+    // limits.stage.stream (self scattering): when a rank's share of the trajectory exceeds stage_memory_data the stager
+    // streams its atoms through the GPU in waves (wave-outer, |q|-inner; partials are additive over atoms) instead of
+    // failing like the reference (data_stager.cpp:194-204).  false restores the reference's error.
+    bool stage_stream = true;
     DecompositionLimits decomposition;
     // how the ranks of one partition share a coherent |q|: "frames" = each rank holds a block of frames (the
     // reference's decomposition, all_vectors_scatter_device.cpp:61,248,408), "vectors" = every rank holds all frames
@@ -353,7 +357,8 @@ class AbstractScatterDevice : public IScatterDevice {
     int dsp_type_code() const;
     int dsp_method_code() const;
     double *partial_buffer(int dsp_type);
-    void reduce_and_finalize(int dsp_type, double scale);
+    // d_partial: the packed partial to reduce (default: the device's own partial buffer)
+    void reduce_and_finalize(int dsp_type, double scale, double *d_partial = nullptr);
 
    public:
     AbstractScatterDevice(std::shared_ptr<ICommunicator> allcomm, std::shared_ptr<ICommunicator> partitioncomm,
@@ -406,10 +411,20 @@ class AllVectorsScatterDevice : public AbstractVectorsScatterDevice {
 class SelfVectorsScatterDevice : public AbstractVectorsScatterDevice {
    protected:
     ModAssignment assignment_;
+    // streamed mode (BASELINE config 5): this rank's atoms pass through the GPU in waves of wave_atoms_
+    bool streamed_ = false;
+    size_t wave_atoms_ = 0, waves_ = 0;
+    double *d_acc_ = nullptr;  // [vectors_.size()][partial_len] partials summed over the waves
     void stage_data() override;
     void compute() override;
+    void runner() override;
+    // factors of staged atoms [first, first+count) of assignment_, subvectors of vectors_[current_vector_]: one |q| into d_out
+    void compute_partial(size_t first, size_t count, int dsp, double *d_out);
 
    public:
+    ~SelfVectorsScatterDevice() override;
+    bool streamed() const { return streamed_; }
+    size_t waves() const { return waves_; }
     SelfVectorsScatterDevice(std::shared_ptr<ICommunicator> allcomm, std::shared_ptr<ICommunicator> partitioncomm,
                              Sample &sample, std::vector<CartesianCoor3D> vectors, size_t NAF, IResultSink *sink,
                              const Params &params, const SgpuBackend &be, sgpu_ctx *ctx);

@@ -1162,6 +1162,20 @@ __global__ void copy_words_kernel(uint32_t *__restrict__ dst, const uint32_t *__
 }
 }  // namespace
 
+namespace {
+__global__ void accumulate_kernel(double *__restrict__ dst, const double *__restrict__ src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] += src[i];
+}
+}  // namespace
+
+int launch_accumulate(double *d_dst, const double *d_src, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 592);
+    accumulate_kernel<<<blocks, 256, 0, st>>>(d_dst, d_src, n);
+    return 1;
+}
+
 int launch_copy_words(void *d_dst, const void *mapped_src, size_t nwords, cudaStream_t st) {
     if (nwords == 0) return 0;
     unsigned blocks = (unsigned)std::min<size_t>((nwords + 255) / 256, 592);

@@ -40,6 +40,8 @@ int launch_synth_trajectory(float *d_xyz, size_t NF, size_t NA, size_t atom0, si
 // SM-driven copy of 4-byte words from mapped pinned host memory (keeps small uploads off the DMA engine, where they
 // would queue behind the stager's bulk copies)
 int launch_copy_words(void *d_dst, const void *mapped_src, size_t nwords, cudaStream_t st);
+// dst[i] += src[i]
+int launch_accumulate(double *d_dst, const double *d_src, size_t n, cudaStream_t st);
 // DFMA peak probe; returns flops executed
 double launch_fp64_peak(double *d_sink, int iters, int blocks, cudaStream_t st);
 

@@ -507,18 +507,13 @@ int sgpu_stage_atoms_device(sgpu_ctx *ctx, const float *d_xyz, size_t NA_local, 
     return SGPU_OK;
 }
 
-int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t nranks, size_t rank) {
-    if (!ctx) return SGPU_EINVAL;
-    if (!xyz || NF < 1 || NA < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: No frames / atoms available");
-    if (nranks < 1 || rank >= nranks) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: bad rank / nranks");
+// atoms atom_first + i*stride, i < count, of frame-major host input -> atom-major device layout (transpose on the GPU)
+static int stage_atoms_strided(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t atom_first, size_t stride,
+                               size_t count) {
     CK(cudaSetDevice(ctx->device));
     int rc = release_xyz(ctx);
     if (rc) return rc;
-    // ModAssignment::size (assignment.cpp:82-90)
-    size_t NA_local = NA / nranks;
-    if ((NA % nranks) != 0 && rank < (NA - nranks * (NA / nranks))) NA_local += 1;
-    if (NA_local == 0) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: this rank owns no atoms");
-    rc = own_xyz_buffer(ctx, NA_local * NF * 3 * sizeof(float));
+    rc = own_xyz_buffer(ctx, count * NF * 3 * sizeof(float));
     if (rc) return rc;
     const size_t frame_bytes = NA * 3 * sizeof(float);
     size_t nfc = std::max<size_t>(32, ((size_t)256 << 20) / frame_bytes);
@@ -540,7 +535,7 @@ int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, siz
         CK(cudaMemcpyAsync(tmp, xyz + f0 * NA * 3, nf * frame_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(copied[slot], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, copied[slot], 0));
-        ctx->launches += launch_frames_to_atoms(tmp, ctx->d_xyz, NF, nf, f0, NA, rank, nranks, NA_local, ctx->stream);
+        ctx->launches += launch_frames_to_atoms(tmp, ctx->d_xyz, NF, nf, f0, NA, atom_first, stride, count, ctx->stream);
         CK(cudaEventRecord(consumed[slot], ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -553,8 +548,37 @@ int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, siz
     ctx->NF = NF;
     ctx->NFt = NF;
     ctx->f_first = 0;
-    ctx->NA = NA_local;
+    ctx->NA = count;
     ctx->repr = SGPU_REPR_CARTESIAN;
+    return SGPU_OK;
+}
+
+int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t nranks, size_t rank) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!xyz || NF < 1 || NA < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: No frames / atoms available");
+    if (nranks < 1 || rank >= nranks) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: bad rank / nranks");
+    // ModAssignment::size (assignment.cpp:82-90)
+    size_t NA_local = NA / nranks;
+    if ((NA % nranks) != 0 && rank < (NA - nranks * (NA / nranks))) NA_local += 1;
+    if (NA_local == 0) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_from_frames: this rank owns no atoms");
+    return stage_atoms_strided(ctx, xyz, NF, NA, rank, nranks, NA_local);
+}
+
+int sgpu_stage_atoms_wave(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t atom_first, size_t atom_stride,
+                          size_t count) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!xyz || NF < 1 || NA < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_wave: No frames / atoms available");
+    if (atom_stride < 1 || count < 1 || atom_first + (count - 1) * atom_stride >= NA)
+        return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_wave: atom range outside the trajectory");
+    return stage_atoms_strided(ctx, xyz, NF, NA, atom_first, atom_stride, count);
+}
+
+int sgpu_accumulate(sgpu_ctx *ctx, double *d_dst, const double *d_src, size_t n) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!d_dst || !d_src) return fail(ctx, SGPU_EINVAL, "sgpu_accumulate: NULL buffer");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches += launch_accumulate(d_dst, d_src, n, ctx->stream);
+    CK(cudaGetLastError());
     return SGPU_OK;
 }
 

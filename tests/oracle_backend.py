@@ -37,7 +37,8 @@ class OracleBackend:
             all_vectors_amplitudes=_host.BE_AV_AMPL(self._av_amplitudes),
             all_vectors_dsp_partial=_host.BE_AV_DSP(self._av_dsp),
             compute_all_vectors_scan_partial=_host.BE_AV_SCAN(self._av_scan),
-            all_vectors_scan_amplitudes=_host.BE_AV_SCAN_AMPL(self._av_scan_amplitudes))
+            all_vectors_scan_amplitudes=_host.BE_AV_SCAN_AMPL(self._av_scan_amplitudes),
+            stage_atoms_wave=_host.BE_STAGE_WAVE(self._stage_wave), accumulate=_host.BE_ACCUMULATE(self._accumulate))
         self._cbs = cbs
         self.vtbl = _host.BackendVtbl(**cbs)
 
@@ -137,6 +138,18 @@ class OracleBackend:
         off, size, _ = o.mod_assignment(nranks, rank, NA)
         ids = off + nranks * np.arange(size)
         self._ctx(c).update(mode=2, xyz=np.ascontiguousarray(a[:, ids].transpose(1, 0, 2)), NF=NF, NA=size)
+        return 0
+
+    def _stage_wave(self, c, xyz, NF, NA, first, stride, count):
+        a = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(NF, NA, 3))
+        ids = first + stride * np.arange(count)
+        self.waves_staged = getattr(self, "waves_staged", 0) + 1
+        self._ctx(c).update(mode=2, xyz=np.ascontiguousarray(a[:, ids].transpose(1, 0, 2)), NF=NF, NA=count)
+        return 0
+
+    def _accumulate(self, c, dst, src, n):
+        d = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_double)), shape=(n,))
+        d += np.ctypeslib.as_array(C.cast(src, C.POINTER(C.c_double)), shape=(n,))
         return 0
 
     def _set_factors(self, c, b, n):

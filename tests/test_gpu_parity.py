@@ -603,6 +603,58 @@ def test_host_layer_devices_on_gpu(oracle):
         assert rel_err(r["fqt"], ref[0]) < TOL
 
 
+@pytest.mark.parametrize("dsp", ["autocorrelate", "square"])
+def test_self_streamed_waves_match_resident(oracle, dsp):
+    """BASELINE config 5 shape in small: the rank's atoms exceed limits.stage.memory.data, so the stager streams them
+    through the GPU in waves (sgpu_stage_atoms_wave), every wave is evaluated for all |q| and the packed partials add up
+    (sgpu_accumulate).  Same fqt / fq / fq2 as the resident run (1e-12) and as the oracle (1e-9)."""
+    from sassena_b200 import host
+    NA, NF = 61, 130
+    xyz = synth.trajectory(NF, NA, 30.0, 0.2, 41, offset=-15.0)
+    b = synth.factors(NA)
+    qv = host.create_from_scans([{"base": (0, 1, 0), "from": 0.4, "to": 1.6, "points": 3}])
+    ps = host.Params().set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
+    ps.set("scattering.average.orientation.vectors.resolution", 7).set("scattering.dsp.type", dsp).create()
+    resident, _, _ = host.run_scatter(ps, xyz, qv, factors_fn=lambda ql: b * (1.0 + 0.2 * ql))
+    ps.set("limits.stage.memory.data", 16 * NF * 12)  # 16 atoms per wave -> 4 waves (16, 16, 16, 13)
+    streamed, _, tm = host.run_scatter(ps, xyz, qv, factors_fn=lambda ql: b * (1.0 + 0.2 * ql))
+    assert tm["sd:compute"][1] == 4 and len(streamed) == 3
+    for r, s, q in zip(resident, streamed, qv):
+        ref = oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b * (1.0 + 0.2 * np.linalg.norm(q)), ps.init_subvectors(q),
+                                          dsp=dsp, nthreads=4)
+        assert rel_err(s["fqt"], r["fqt"]) < 1e-12 and abs(s["fq2"] - r["fq2"]) <= 1e-12 * abs(r["fq2"])
+        assert rel_err(s["fqt"], ref[0]) < TOL and abs(s["fq"] - ref[1]) < TOL * abs(ref[0][0])
+        assert abs(s["fq2"] - ref[2]) <= TOL * abs(ref[2])
+
+
+def test_stage_atoms_wave_and_accumulate(gpu_ctx, oracle):
+    """sgpu_stage_atoms_wave stages exactly atoms first + i*stride; sgpu_accumulate adds packed partials; bad ranges fail."""
+    NA, NF, NM = 37, 40, 4
+    frames = synth.trajectory(NF, NA, 30.0, 0.1, 19)
+    b = synth.factors(NA)
+    q = 0.9 * synth.unit_vectors(NM, 3)
+    ids = 2 + 3 * np.arange(11)  # atoms 2, 5, ..., 32
+    gpu_ctx.stage_atoms_wave(frames, 2, 3, 11)
+    gpu_ctx.set_factors(b[ids])
+    fqt, fq, fq2 = gpu_ctx.compute_self_vectors(q)
+    rfqt, rfq, rfq2 = oracle.compute_self_vectors(np.ascontiguousarray(frames[:, ids].transpose(1, 0, 2)), b[ids], q)
+    assert rel_err(fqt, rfqt) < TOL and abs(fq2 - rfq2) <= TOL * abs(rfq2)
+    plen = gpu_ctx.partial_len("autocorrelate")
+    d1, d2 = gpu_ctx.device_alloc(plen * 8), gpu_ctx.device_alloc(plen * 8)
+    gpu_ctx.compute_self_vectors_partial(q, d1)
+    gpu_ctx.compute_self_vectors_partial(q, d2)
+    gpu_ctx.accumulate(d1, d2, plen)
+    gpu_ctx.synchronize()
+    a, c = np.empty(plen), np.empty(plen)
+    gpu_ctx.memcpy_d2h(a, d1)
+    gpu_ctx.memcpy_d2h(c, d2)
+    assert np.array_equal(a, 2 * c)
+    gpu_ctx.device_free(d1)
+    gpu_ctx.device_free(d2)
+    with pytest.raises(Exception, match="outside the trajectory"):
+        gpu_ctx.stage_atoms_wave(frames, 2, 3, 13)  # 2 + 12*3 = 38 >= NA
+
+
 @pytest.mark.parametrize("L", [0, 1, 6, 20])
 def test_mpsphere_batch_and_atom_sharding(gpu_ctx, oracle, L):
     """batched multipole sphere (several |q| per pass, per-|q| factors) and the atom-sharded multi-GPU protocol:

@@ -201,6 +201,24 @@ def test_run_scatter_single_rank_oracle_backend(oracle):
     recs, _, _ = host.run_scatter(p2, xyz, qv[:1], b=b, backend=be.vtbl)
     ref = oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b, qv[:1], method="direct")
     assert np.allclose(recs[0]["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+    # self, streamed: the atoms do not fit limits.stage.memory.data and pass through the device in waves (BASELINE
+    # config 5); same result as the resident run, and the reference's error when streaming is switched off
+    p2s = host.Params().set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
+    p2s.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(4, 5)).create()
+    resident, _, _ = host.run_scatter(p2s, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
+    be.waves_staged = 0
+    p2s.set("limits.stage.memory.data", 7 * NF * 12)  # 7 of the 30 atoms per wave -> 5 waves
+    streamed, _, tms = host.run_scatter(p2s, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
+    assert be.waves_staged == 5 and tms["sd:compute"][1] == 5 and len(streamed) == len(qv)
+    for r, s, q in zip(resident, streamed, qv):
+        ref = oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b * (1 + np.linalg.norm(q)), p2s.init_subvectors(q))
+        assert np.array_equal(s["q"], q)
+        assert np.allclose(s["fqt"], r["fqt"], rtol=1e-12, atol=1e-12 * abs(r["fqt"][0]))
+        assert np.allclose(s["fqt"], ref[0], rtol=1e-11, atol=1e-11 * abs(ref[0][0]))
+        assert np.isclose(s["fq"], ref[1]) and np.isclose(s["fq2"], ref[2])
+    with pytest.raises(host.HostError) as e:
+        host.run_scatter(p2s.set("limits.stage.stream", False), xyz, qv, b=b, backend=be.vtbl)
+    assert "decomposition failed" in str(e.value) or "Insufficient Buffer" in str(e.value)
     # multipole sphere
     p3 = host.Params().set("scattering.average.orientation.type", "multipole")
     p3.set("scattering.average.orientation.multipole.moments.type", "resolution")

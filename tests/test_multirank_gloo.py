@@ -61,7 +61,7 @@ def _reference(oracle, case):
 
 @pytest.mark.parametrize("world,case", [(2, "all"), (2, "self"), (2, "mp"), (2, "all_manual1"), (3, "self"),
                                         (3, "all_manual1"), (2, "all_frames"), (3, "all_frames"), (2, "scan"), (2, "scan_frames"),
-                                        (3, "scan_frames")])
+                                        (3, "scan_frames"), (2, "self_stream"), (3, "self_stream")])
 def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
     gathered = _run(world, case, tmp_path)
     qv, ref = _reference(oracle, case)

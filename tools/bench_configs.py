@@ -1,6 +1,7 @@
 """Measures the BASELINE.json configurations that are NOT the bench.py headline (C1 full; C2, C4 on stated sub-samples with
 linear extrapolation, labelled as such) and the CPU oracle on small samples of the same shapes.  One JSON line per config.
-Usage: python tools/bench_configs.py [C1 C2 C4]"""
+C5 (self, trajectory larger than the coordinate budget) runs through the host layer's streamed stager on a sample of atoms.
+Usage: python tools/bench_configs.py [C1 C2 C4 C5]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,7 +9,7 @@ import sassena_b200
 from sassena_b200 import synth
 from oracle import oracle as o
 
-which = sys.argv[1:] or ["C1", "C2", "C4"]
+which = sys.argv[1:] or ["C1", "C2", "C4", "C5"]
 ctx = sassena_b200.ScatterContext(0)
 cores = o.max_threads()
 
@@ -78,3 +79,41 @@ if "C4" in which:
                       "cpu_sample": f"{na_c} atoms x 2 frames x {len(mom)} moments, {cores} threads", "cpu_s_sample": cpu,
                       "cpu_moment_evals_per_s": na_c * 2 * len(mom) / cpu, "cpu_s_full_extrapolated": cpu * (NA * c["NF"] * c["q"][2]) / (na_c * 2),
                       "max_rel_err_fqt": err}))
+
+if "C5" in which:
+    # streamed self scattering: the sample's coordinates exceed limits.stage.memory.data, so the host layer stages the
+    # atoms in waves (frame-major pinned host buffer -> chunked async H2D -> GPU transpose) and evaluates every wave for
+    # all |q|.  Sample: NA_s atoms x all 50k frames x 2 |q| x 200 vectors, budget = a third of the sample -> 3 waves.
+    from sassena_b200 import host
+    c = synth.CONFIGS["C5"]
+    NA_s, NF, NM, NQ_s = 768, c["NF"], c["NM"], 2
+    d = ctx.device_alloc(NA_s * NF * 12)
+    ctx.synth_trajectory(d, NF, c["NA"], c["box"], c["sigma"], c["seed"], layout=0, NA_out=NA_s)  # frame-major [NF][NA_s][3]
+    pin = ctx.pinned((NF, NA_s, 3)); frames = pin.array  # the stager's pinned host buffer
+    ctx.memcpy_d2h(frames, d); ctx.device_free(d)
+    bf = synth.factors(c["NA"])[:NA_s]
+    qls = synth.qlengths(*c["q"])[9:9 + NQ_s]
+    qv = np.array([[ql, 0.0, 0.0] for ql in qls])
+    p = host.Params().set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
+    p.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(NM, c["vseed"])).create()
+    p.set("limits.stage.memory.data", (NA_s // 3) * NF * 12)
+    t0 = time.perf_counter(); recs, _, tm = host.run_scatter(p, frames, qv, b=bf, ctx=ctx); dt = time.perf_counter() - t0
+    waves = tm["sd:compute"][1]
+    tl = NA_s * NM * NQ_s
+    full1 = tm["sd:compute"][0] / tl * (c["NA"] * NM * c["q"][2])
+    # CPU oracle: a few atoms x 8 vectors of the same trajectory, one |q|
+    na_c, nm_c = max(2, cores // 4), 8
+    xa = np.ascontiguousarray(frames[:, :na_c].transpose(1, 0, 2))
+    u = p.init_subvectors(qv[0])
+    t0 = time.perf_counter(); ref = o.compute_self_vectors(xa, bf[:na_c], u[:nm_c], nthreads=cores); cpu = time.perf_counter() - t0
+    ctx.stage_atoms(xa); ctx.set_factors(bf[:na_c]); got = ctx.compute_self_vectors(u[:nm_c])
+    err = float(np.max(np.abs(got[0] - ref[0])) / np.max(np.abs(ref[0])))
+    print(json.dumps({"config": "C5 self streamed 500k atoms x 50k frames x 20|q| x 200 vectors",
+                      "sample": f"{NA_s} of 500000 atoms x all frames x {NQ_s} |q|, coordinate budget = 1/3 of the sample -> {waves} waves through the streamed stager",
+                      "gpu_s_sample": dt, "stage_s": tm["sd:stage"][0], "compute_s": tm["sd:compute"][0],
+                      "h2d_GBps_staging": frames.nbytes * waves / max(tm["sd:stage"][0], 1e-9) / 1e9,
+                      "gpu_timelines_per_s": tl / tm["sd:compute"][0], "gpu_evals_per_s": tl * NF / tm["sd:compute"][0],
+                      "gpu_s_full_extrapolated_1gpu": full1, "gpu_s_full_extrapolated_8gpu": full1 / 8,
+                      "cpu_sample": f"{na_c} atoms x {nm_c} vectors, {cores} threads", "cpu_s_sample": cpu,
+                      "cpu_timelines_per_s": na_c * nm_c / cpu,
+                      "cpu_s_full_extrapolated": cpu * (c["NA"] * NM * c["q"][2]) / (na_c * nm_c), "max_rel_err_fqt": err}))
