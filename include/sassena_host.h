@@ -136,6 +136,20 @@ int sass_xdr_info(const sass_xdr *d, size_t *nframes, size_t *natoms);
 int sass_xdr_read(sass_xdr *d, size_t first, size_t count, float *out, double *box);
 void sass_xdr_close(sass_xdr *d);
 
+/* ---- HDF5 signal file ("next" row; reference src/services/file_writer_service.cpp:44-171,314-484) ------
+ * A minimal HDF5 container writer/reader (csrc/host/h5mini.cpp): superblock v0, symbol-table groups, float64 datasets
+ * extendible along the q-vector dimension and chunked like the reference's, meta/{rawconfig,config,database}.
+ * sass_h5_read walks a file and reports every dataset: path ("fqt", "meta/config"), kind (0 float64, 1 char array,
+ * 2 string), rank, dims, maxdims (NULL when absent), chunk dims (NULL when contiguous), the values and their byte count. */
+typedef void (*sass_h5_dataset_fn)(void *user, const char *path, int kind, size_t rank, const uint64_t *dims,
+                                   const uint64_t *maxdims, const uint64_t *chunk, const void *data, size_t nbytes);
+int sass_h5_read(const char *path, sass_h5_dataset_fn fn, void *user);
+/* writes a signal file in one call: q [n][3], fqt [n][NF][2], fq / fq2 [n][2] (fq0 = fqt[:,0]); flags bit 0..3 = store
+ * fqt, fq0, fq, fq2; resume != 0 keeps the rows of an existing file (HDF5WriterService::init) and appends */
+int sass_h5_write_signal(const char *path, size_t NF, size_t chunksize, int flags, int resume, const char *rawconfig,
+                         const char *config, const char *database, size_t n, const double *q, const double *fqt,
+                         const double *fq, const double *fq2, size_t *rows_total);
+
 /* ---- control plane: scatter.xml + db.xml + PDB + DCD -> hot path ("next" row) ------------------------
  * Replaces, for one process, the flow of the reference executable src/main/sassena.cpp:132-417:
  *   Params::init/read_xml   src/control/parameters.cpp:64-792
@@ -158,6 +172,8 @@ int sass_job_frames(const sass_job *j, const float **frames);
 int sass_job_selection(const sass_job *j, const char *name, size_t *ids, size_t cap, size_t *n);
 /* the Params subset the scatter devices read (borrowed; do not free) */
 const sass_params *sass_job_params(const sass_job *j);
+/* scattering.signal.file resolved against the configuration file's directory (parameters.cpp:41-54; default signal.h5) */
+const char *sass_job_signal_file(const sass_job *j);
 /* runs every q-vector; comm/backend NULL = single process / the in-library CUDA backend */
 int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
                  sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap);

@@ -2,7 +2,9 @@
 (reference src/main/sassena.cpp:200-260: --config, and the scattering.signal.file override).
 
 One process per GPU: run under `python -m torch.distributed.run --nproc-per-node N -m sassena_b200.cli ...` for N GPUs.
-The signal is written as a directory of .npy datasets named like the reference's signal.h5 datasets."""
+The signal goes to scattering.signal.file (default signal.h5) as an HDF5 file in the reference's layout
+(file_writer_service.cpp:44-171; an existing file is resumed like the reference does), with the per-rank rows kept as
+.npy datasets under <file>.d/.  `--signal DIR` (no .h5 suffix) writes the .npy directory only."""
 import argparse
 import os
 import sys
@@ -11,7 +13,7 @@ import sys
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="sassena_b200")
     ap.add_argument("--config", default="scatter.xml", help="xml configuration file (reference default: scatter.xml)")
-    ap.add_argument("--signal", default=None, help="output directory (default: scattering.signal.file with .npy.d suffix)")
+    ap.add_argument("--signal", default=None, help="output file (.h5) or .npy directory (default: scattering.signal.file)")
     ap.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK or 0)")
     args = ap.parse_args(argv)
 
@@ -31,8 +33,7 @@ def main(argv=None):
     job = host.Job(args.config)
     signal = args.signal
     if signal is None:
-        base = os.path.splitext(os.path.basename(args.config))[0]
-        signal = os.path.join(os.path.dirname(os.path.abspath(args.config)), base + ".signal.d")
+        signal = job.signal_file
     ctx = ScatterContext(dev)
     try:
         written, report = job.run(signal, comm=comm, ctx=ctx)

@@ -11,6 +11,7 @@
 #include <sstream>
 
 #include "dcd.hpp"
+#include "h5mini.hpp"
 #include "xdr_traj.hpp"
 
 namespace sassena {
@@ -253,6 +254,12 @@ void Config::read_xml(const std::string &filename) {
         size_t slash = filename.find_last_of('/');
         config_rootpath = (slash == std::string::npos) ? std::string(".") : filename.substr(0, slash);
     }
+    {
+        std::ifstream in(filename.c_str(), std::ios::binary);
+        std::stringstream ss;
+        ss << in.rdbuf();
+        rawconfig = ss.str();
+    }
     XMLInterface x(filename);
     // ---- sample (parameters.cpp:85-343) ----
     structure_filepath = get_filepath(structure_file);
@@ -424,6 +431,7 @@ void Config::read_xml(const std::string &filename) {
     if (x.exists("//scattering/signal/fq2")) signal_fq2 = x.get_bool("//scattering/signal/fq2");
     // ---- limits (parameters.cpp:612-736): the keys the GPU path keeps ----
     if (x.exists("//limits/stage/memory/data")) limits.stage_memory_data = x.get_size("//limits/stage/memory/data");
+    if (x.exists("//limits/signal/chunksize")) signal_chunksize = x.get_size("//limits/signal/chunksize");
     if (x.exists("//limits/stage/stream")) limits.stage_stream = x.get_bool("//limits/stage/stream");
     if (x.exists("//limits/decomposition/utilization"))
         limits.decomposition.utilization = x.get_double("//limits/decomposition/utilization");
@@ -459,6 +467,12 @@ std::string Database::atom_label(size_t id) const {
 }
 
 void Database::read_xml(const std::string &filename) {
+    {
+        std::ifstream in(filename.c_str(), std::ios::binary);
+        std::stringstream ss;
+        ss << in.rdbuf();
+        rawconfig = ss.str();
+    }
     XMLInterface x(filename);
     auto params = [&](std::vector<double> &values) {
         const XMLNode *el = x.get(".")[0];
@@ -859,6 +873,41 @@ void write_npy(const std::string &path, const double *data, const std::vector<si
     fclose(f);
 }
 
+// reads back what write_npy wrote (little-endian float64, C order); false if the file does not exist
+bool read_npy(const std::string &path, std::vector<double> &data, std::vector<size_t> &shape) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    unsigned char pre[10];
+    if (fread(pre, 1, 10, f) != 10 || memcmp(pre, "\x93NUMPY", 6) != 0) {
+        fclose(f);
+        throw Error("not an npy file: " + path);
+    }
+    const size_t hl = pre[8] | (pre[9] << 8);
+    std::string hdr(hl, ' ');
+    if (fread(&hdr[0], 1, hl, f) != hl || hdr.find("'<f8'") == std::string::npos || hdr.find("False") == std::string::npos) {
+        fclose(f);
+        throw Error("unsupported npy header in " + path);
+    }
+    shape.clear();
+    size_t p = hdr.find("'shape'");
+    p = hdr.find('(', p);
+    const size_t e = hdr.find(')', p);
+    size_t n = 1;
+    for (size_t i = p + 1; i < e;) {
+        while (i < e && !isdigit((unsigned char)hdr[i])) i++;
+        if (i >= e) break;
+        size_t v = 0;
+        while (i < e && isdigit((unsigned char)hdr[i])) v = 10 * v + (hdr[i++] - '0');
+        shape.push_back(v);
+        n *= v;
+    }
+    data.resize(n);
+    const bool ok = n == 0 || fread(data.data(), sizeof(double), n, f) == n;
+    fclose(f);
+    if (!ok) throw Error("short npy file: " + path);
+    return true;
+}
+
 namespace {
 struct Collector : IResultSink {
     size_t NF = 0;
@@ -889,7 +938,7 @@ void Job::load(const std::string &config_file) {
     factors.reset(new ScatterFactors(cfg, db, sample));
 }
 
-size_t Job::run(const std::string &signal_dir, std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx,
+size_t Job::run(const std::string &signal_dir_in, std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx,
                 std::string *report) {
     if (!factors) throw Error("Job::run before Job::load");
     LoadedSample &s = this->sample;
@@ -901,7 +950,32 @@ size_t Job::run(const std::string &signal_dir, std::shared_ptr<ICommunicator> co
     sample.factors = [&](double ql, double *b) { sf.update(ql, b); };
     Collector sink;
     std::vector<CartesianCoor3D> qv = cfg.qvectors;
-    std::unique_ptr<IScatterDevice> dev(ScatterDeviceFactory::create(comm, sample, &sink, qv, cfg, be, ctx));
+    // HDF5 output: <path>.h5 (+ the per-rank rows under <path>.h5.d/)
+    const bool h5mode = signal_dir_in.size() > 3 && signal_dir_in.compare(signal_dir_in.size() - 3, 3, ".h5") == 0;
+    const std::string signal_dir = h5mode ? signal_dir_in + ".d" : signal_dir_in;
+    std::unique_ptr<SignalFileH5> h5file;
+    if (h5mode) {
+        // every rank reads the existing file (same file system) so that all agree on the q-vectors left to compute
+        h5file.reset(new SignalFileH5(signal_dir_in, s.NF, cfg.signal_chunksize, cfg.signal_fqt, cfg.signal_fq0, cfg.signal_fq,
+                                      cfg.signal_fq2));
+        h5file->set_meta(cfg.rawconfig, cfg.rawconfig, db.rawconfig);
+        std::vector<double> old;
+        {
+            std::ifstream probe(signal_dir_in.c_str());
+            if (probe.good()) old = h5file->init();  // only rank 0 creates / rewrites the file (below)
+        }
+        if (!old.empty()) {  // only compute those q vectors which have not been written so far (sassena.cpp:277-291)
+            std::vector<CartesianCoor3D> left;
+            for (auto &q : qv) {
+                bool done = false;
+                for (size_t i = 0; i + 2 < old.size() && !done; i += 3) done = old[i] == q.x && old[i + 1] == q.y && old[i + 2] == q.z;
+                if (!done) left.push_back(q);
+            }
+            qv.swap(left);
+        }
+    }
+    std::unique_ptr<IScatterDevice> dev;
+    if (!qv.empty()) dev.reset(ScatterDeviceFactory::create(comm, sample, &sink, qv, cfg, be, ctx));  // else: "No qvectors left to compute."
     if (dev) dev->run();
     // every writing rank (partition rank 0) stores its rows; rows pair up through qvectors (arrival order, as in the
     // reference's HDF5 file, file_writer_service.cpp:314-484)
@@ -912,12 +986,41 @@ size_t Job::run(const std::string &signal_dir, std::shared_ptr<ICommunicator> co
         dir = signal_dir + "/rank_" + std::to_string(comm->rank());
         mkdir(dir.c_str(), 0777);
     }
-    if (n > 0 || comm->size() == 1) {
+    if (n > 0 || comm->size() == 1 || h5mode) {  // (h5 mode always rewrites: stale rows of an earlier run must not be merged)
         write_npy(dir + "/qvectors.npy", sink.q.data(), {n, 3});
         if (cfg.signal_fqt) write_npy(dir + "/fqt.npy", sink.fqt.data(), {n, s.NF, 2});
         if (cfg.signal_fq0) write_npy(dir + "/fq0.npy", sink.fq0.data(), {n, 2});
         if (cfg.signal_fq) write_npy(dir + "/fq.npy", sink.fq.data(), {n, 2});
         if (cfg.signal_fq2) write_npy(dir + "/fq2.npy", sink.fq2.data(), {n, 2});
+    }
+    comm->barrier();
+    if (h5mode && comm->rank() == 0) {
+        // the reference's writer service runs on world rank 0 and receives the rows of every partition (file_writer_service
+        // .cpp:252-310); here rank 0 collects them from the per-rank row files once all ranks are done
+        for (size_t r = 0; r < comm->size(); r++) {
+            const std::string d = comm->size() > 1 ? signal_dir + "/rank_" + std::to_string(r) : signal_dir;
+            std::vector<size_t> shape;
+            std::vector<double> rq, rfqt, rfq, rfq2;
+            if (!read_npy(d + "/qvectors.npy", rq, shape)) continue;
+            const size_t rows = rq.size() / 3;
+            if (rows == 0) continue;
+            if (cfg.signal_fqt && !read_npy(d + "/fqt.npy", rfqt, shape)) throw Error("missing fqt rows of rank " + std::to_string(r));
+            if (!cfg.signal_fqt) {  // fq0 is taken from fqt[0]; without fqt the fq0 rows stand in
+                std::vector<double> f0;
+                if (cfg.signal_fq0 && !read_npy(d + "/fq0.npy", f0, shape)) throw Error("missing fq0 rows of rank " + std::to_string(r));
+                rfqt.assign(rows * 2 * s.NF, 0.0);
+                for (size_t i = 0; i < rows && !f0.empty(); i++) {
+                    rfqt[i * 2 * s.NF] = f0[2 * i];
+                    rfqt[i * 2 * s.NF + 1] = f0[2 * i + 1];
+                }
+            }
+            if (cfg.signal_fq && !read_npy(d + "/fq.npy", rfq, shape)) throw Error("missing fq rows of rank " + std::to_string(r));
+            if (cfg.signal_fq2 && !read_npy(d + "/fq2.npy", rfq2, shape)) throw Error("missing fq2 rows of rank " + std::to_string(r));
+            const double zero[2] = {0.0, 0.0};
+            for (size_t i = 0; i < rows; i++)
+                h5file->write(&rq[3 * i], &rfqt[i * 2 * s.NF], cfg.signal_fq ? &rfq[2 * i] : zero, cfg.signal_fq2 ? &rfq2[2 * i] : zero);
+        }
+        h5file->flush();
     }
     comm->barrier();
     if (report) {

@@ -79,6 +79,8 @@ struct Config : Params {
     std::vector<ScatteringBackgroundKappaParameters> kappas;
     std::string signal_file = "signal.h5", signal_filepath;
     bool signal_fqt = true, signal_fq0 = true, signal_fq = true, signal_fq2 = true;
+    size_t signal_chunksize = 10000;  // limits.signal.chunksize (parameters.cpp:626)
+    std::string rawconfig;            // the configuration file as read (Params::get_rawconfig, meta/rawconfig + meta/config)
     // database
     std::string database_file = "db.xml", database_filepath, database_format = "xml";
 
@@ -101,6 +103,7 @@ class Database {
     std::map<std::string, std::string> quick_;
 
    public:
+    std::string rawconfig;  // the database file as read (Database::get_config, meta/database)
     void read_xml(const std::string &filename);
     std::string pdb_name(const std::string &testlabel);  // database.cpp:308-340: exactly one regex must match
     size_t atom_id(const std::string &label);            // atomIDs.get (registers unknown labels)
@@ -142,6 +145,7 @@ class ScatterFactors {
 
 // .npy writer for the interim signal output (datasets named like the HDF5 layout, file_writer_service.cpp:44-171)
 void write_npy(const std::string &path, const double *data, const std::vector<size_t> &shape);
+bool read_npy(const std::string &path, std::vector<double> &data, std::vector<size_t> &shape);
 
 // the `sassena` executable's flow (src/main/sassena.cpp:132-417) for one process / one communicator:
 // load(): config + database + sample;  run(): factory -> device.run() -> signal directory (.npy datasets).
@@ -152,7 +156,10 @@ struct Job {
     std::unique_ptr<ScatterFactors> factors;
     void load(const std::string &config_file);
     // returns the number of q-vectors this rank wrote; with more than one rank every writing rank stores its rows
-    // under <signal_dir>/rank_<r>/
+    // under <signal_dir>/rank_<r>/.  A `signal_dir` ending in ".h5" selects the reference's output: the rows go to
+    // "<path>.d/" as above and rank 0 then writes <path> as an HDF5 file in the layout of
+    // file_writer_service.cpp:44-171; if <path> already exists its q-vectors are skipped and its rows kept (resume,
+    // sassena.cpp:270-305).
     size_t run(const std::string &signal_dir, std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx,
                std::string *report);
 };

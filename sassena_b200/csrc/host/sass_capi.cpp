@@ -7,6 +7,7 @@
 #include "control.hpp"
 #include "dcd.hpp"
 #include "xdr_traj.hpp"
+#include "h5mini.hpp"
 #include "sassena_host.hpp"
 
 using namespace sassena;
@@ -365,6 +366,38 @@ int sass_xdr_read(sass_xdr *d, size_t first, size_t count, float *out, double *b
 }
 void sass_xdr_close(sass_xdr *d) { delete d; }
 
+static void h5_walk(const h5::Group &g, const std::string &prefix, sass_h5_dataset_fn fn, void *user) {
+    for (auto &d : g.datasets) {
+        const std::string p = prefix + d.name;
+        const void *data = d.kind == h5::Dataset::F64 ? (const void *)d.f64.data() : (const void *)d.bytes.data();
+        const size_t nbytes = d.kind == h5::Dataset::F64 ? d.f64.size() * sizeof(double) : d.bytes.size();
+        fn(user, p.c_str(), (int)d.kind, d.dims.size(), d.dims.data(), d.maxdims.empty() ? nullptr : d.maxdims.data(),
+           d.chunk.empty() ? nullptr : d.chunk.data(), data, nbytes);
+    }
+    for (auto &s : g.groups) h5_walk(s, prefix + s.name + "/", fn, user);
+}
+
+int sass_h5_read(const char *path, sass_h5_dataset_fn fn, void *user) {
+    return guard([&] {
+        if (!path || !fn) throw Error("sass_h5_read: NULL argument");
+        h5_walk(h5::read_file(path), "", fn, user);
+    });
+}
+
+int sass_h5_write_signal(const char *path, size_t NF, size_t chunksize, int flags, int resume, const char *rawconfig,
+                         const char *config, const char *database, size_t n, const double *q, const double *fqt,
+                         const double *fq, const double *fq2, size_t *rows_total) {
+    return guard([&] {
+        if (!path || (n && (!q || !fqt || !fq || !fq2))) throw Error("sass_h5_write_signal: NULL argument");
+        SignalFileH5 f(path, NF, chunksize, flags & 1, flags & 2, flags & 4, flags & 8);
+        f.set_meta(rawconfig ? rawconfig : "", config ? config : "", database ? database : "");
+        if (resume) f.init();
+        for (size_t i = 0; i < n; i++) f.write(q + 3 * i, fqt + i * 2 * NF, fq + 2 * i, fq2 + 2 * i);
+        f.flush();
+        if (rows_total) *rows_total = f.rows();
+    });
+}
+
 }  // extern "C"
 
 // ---- control plane ----
@@ -427,6 +460,7 @@ int sass_job_selection(const sass_job *j, const char *name, size_t *ids, size_t 
 }
 
 const sass_params *sass_job_params(const sass_job *j) { return j ? &j->params : nullptr; }
+const char *sass_job_signal_file(const sass_job *j) { return j ? j->job.cfg.signal_filepath.c_str() : nullptr; }
 
 int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
                  sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap) {

@@ -365,6 +365,11 @@ class Job:
         _ck(_lib().sass_job_info(self.h, *[C.byref(x) for x in n]))
         self.natoms, self.ntarget, self.nframes, self.nqvectors = [x.value for x in n]
 
+    @property
+    def signal_file(self):
+        """scattering.signal.file resolved like the reference does (default: signal.h5 next to the configuration)"""
+        return _lib().sass_job_signal_file(self.h).decode()
+
     def close(self):
         if getattr(self, "h", None):
             _lib().sass_job_free(self.h)
@@ -413,6 +418,61 @@ class Job:
                                 C.byref(backend) if backend is not None else None, _ctxp(ctx),
                                 C.byref(n), rep, len(rep)))
         return n.value, rep.value.decode()
+
+
+H5_DATASET_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_int, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                            C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t)
+
+
+def read_h5(path, with_layout=False):
+    """Reads an HDF5 file through the built-in minimal reader (csrc/host/h5mini.cpp): dict path -> float64 array /
+    bytes (char arrays) / str (strings).  with_layout=True returns (values, {path: dict(maxdims, chunk)})."""
+    out, layout = {}, {}
+
+    def _cb(user, name, kind, rank, dims, maxdims, chunk, data, nbytes):
+        shape = tuple(int(dims[i]) for i in range(rank))
+        raw = C.string_at(data, nbytes) if nbytes else b""
+        key = name.decode()
+        if kind == 0:
+            out[key] = np.frombuffer(raw, dtype=np.float64).reshape(shape).copy()
+        elif kind == 1:
+            out[key] = raw
+        else:
+            out[key] = raw.decode("latin-1")
+        layout[key] = {"maxdims": tuple(int(maxdims[i]) for i in range(rank)) if maxdims else None,
+                       "chunk": tuple(int(chunk[i]) for i in range(rank)) if chunk else None}
+
+    cb = H5_DATASET_FN(_cb)
+    _ck(_lib().sass_h5_read(str(path).encode(), C.cast(cb, C.c_void_p), None))
+    return (out, layout) if with_layout else out
+
+
+def write_signal_h5(path, qvectors, fqt, fq, fq2, chunksize=10000, resume=False, rawconfig="", config="", database="",
+                    datasets=("fqt", "fq0", "fq", "fq2")):
+    """Writes (or, with resume=True, appends to) a signal file in the reference's HDF5 layout
+    (file_writer_service.cpp:44-171): fqt complex [N][NF], fq / fq2 complex [N]; fq0 = fqt[:, 0]."""
+    q = np.ascontiguousarray(qvectors, dtype=np.float64).reshape(-1, 3)
+    t = np.asarray(fqt, dtype=np.complex128)
+    NF = t.shape[1] if t.ndim == 2 else (t.size // max(len(q), 1))
+    t = np.ascontiguousarray(t.reshape(len(q), NF)).view(np.float64).reshape(len(q), 2 * NF)
+    a = np.ascontiguousarray(np.asarray(fq, dtype=np.complex128).reshape(len(q))).view(np.float64)
+    a2 = np.ascontiguousarray(np.asarray(fq2, dtype=np.complex128).reshape(len(q))).view(np.float64)
+    flags = sum(1 << i for i, k in enumerate(("fqt", "fq0", "fq", "fq2")) if k in datasets)
+    total = C.c_size_t()
+    _ck(_lib().sass_h5_write_signal(str(path).encode(), NF, chunksize, flags, int(resume), rawconfig.encode(),
+                                    config.encode(), database.encode(), len(q), _dp(q), _dp(t), _dp(a), _dp(a2),
+                                    C.byref(total)))
+    return total.value
+
+
+def load_signal_h5(path):
+    """signal.h5 -> the dict load_signal returns (complex fqt / fq0 / fq / fq2)."""
+    d = read_h5(path)
+    out = {"qvectors": d["qvectors"]}
+    for k in ("fqt", "fq0", "fq", "fq2"):
+        if k in d:
+            out[k] = d[k][..., 0] + 1j * d[k][..., 1]
+    return out
 
 
 def load_signal(signal_dir):

@@ -372,3 +372,11 @@ def test_cli_end_to_end(tmp_path, oracle):
     job = host.Job(cfg)
     for i, (fqt, fq, fq2) in enumerate(_expected(oracle, job, xyz, dsp="square")):
         assert rel_err(sig["fqt"][i], fqt) < TOL
+    # default output: scattering.signal.file = signal.h5 next to the configuration, in the reference's HDF5 layout
+    r = subprocess.run([sys.executable, "-m", "sassena_b200.cli", "--config", cfg], cwd=root, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert job.signal_file == str(tmp_path / "signal.h5")
+    h5 = host.load_signal_h5(job.signal_file)
+    assert np.array_equal(h5["qvectors"], sig["qvectors"]) and np.array_equal(h5["fqt"], sig["fqt"])
+    assert np.array_equal(h5["fq0"], sig["fqt"][:, 0]) and np.array_equal(h5["fq2"], sig["fq2"])
