@@ -44,6 +44,7 @@ typedef struct sgpu_ctx sgpu_ctx;
  * multipole_scatter_device.cpp:53; conversion coordinate_set.cpp:303-315) */
 #define SGPU_REPR_CARTESIAN 0
 #define SGPU_REPR_SPHERICAL 1 /* (r, phi, theta) per atom */
+#define SGPU_REPR_CYLINDRICAL 2 /* (r, phi, z) per atom in the basis built on scattering.average.orientation.axis */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 
@@ -118,6 +119,21 @@ int sgpu_compute_self_vectors(sgpu_ctx *ctx, const double *qvecs, size_t NM, int
  * Returns SGPU_EINVAL if |m|>l for any moment (multipole_scatter_device.cpp:459-465). */
 int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM, int dsp_type, int dsp_method,
                           double *atfinal, double afinal[2], double a2final[2]);
+
+/* MPCylinderScatterDevice (multipole_scatter_device.cpp:504-985).  sgpu_frames_to_cylindrical converts the staged
+ * cartesian frames in place to (r, phi, z) in the basis built on `axis` (CylindricalCoordinateSet,
+ * src/sample/coordinate_set.cpp:278-296; basis src/math/coor3d.cpp:278-304), narrowed to float like the stager does.
+ * sgpu_compute_mpcylinder: q[3] is the q-vector (projected onto the same basis, :925-929), moments lm[NM][2] = (l, m)
+ * with l >= 0, 0 <= m <= 3 and m = 0 for l = 0 (parameters.cpp:1082-1102); result scaled by 1/(2 pi) (:866).
+ * sgpu_mpcylinder_amplitudes writes the amplitudes of the atom range to d_amp ([NM][NF][2] doubles, device) for
+ * atom-sharded runs; sgpu_mpsphere_dsp_partial(d_amp, 1, NM, ...) turns the summed amplitudes into a packed partial. */
+int sgpu_frames_to_cylindrical(sgpu_ctx *ctx, const double axis[3]);
+int sgpu_compute_mpcylinder(sgpu_ctx *ctx, const double q[3], const double axis[3], const long *lm, size_t NM, int dsp_type,
+                            int dsp_method, double *atfinal, double afinal[2], double a2final[2]);
+int sgpu_compute_mpcylinder_partial(sgpu_ctx *ctx, const double q[3], const double axis[3], const long *lm, size_t NM,
+                                    int dsp_type, double *d_partial);
+int sgpu_mpcylinder_amplitudes(sgpu_ctx *ctx, const double q[3], const double axis[3], const long *lm, size_t NM,
+                               size_t atom_first, size_t atom_count, double *d_amp);
 
 /* Batched multipole sphere: NQ |q| values in one pass.  The q-independent Y_lm tables are built once per atom tile and
  * shared by the batch (the reference recomputes them per moment, atom, frame AND |q|).  Outputs are per |q|:

@@ -63,6 +63,9 @@ typedef struct sass_backend_vtbl {
     /* atom waves of the self path (trajectory share larger than limits.stage.memory.data) */
     int (*stage_atoms_wave)(sgpu_ctx *, const float *, size_t, size_t, size_t, size_t, size_t);
     int (*accumulate)(sgpu_ctx *, double *, const double *, size_t);
+    /* multipole cylinder */
+    int (*frames_to_cylindrical)(sgpu_ctx *, const double *);
+    int (*mpcylinder_amplitudes)(sgpu_ctx *, const double *, const double *, const long *, size_t, size_t, size_t, double *);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);

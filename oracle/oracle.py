@@ -45,6 +45,7 @@ def lib():
         _lib.orc_scan_unfold.restype = C.c_size_t
         _lib.orc_cylinder_raster_linear.restype = C.c_size_t
         _lib.orc_moments_sphere.restype = C.c_size_t
+        _lib.orc_moments_cylinder.restype = C.c_size_t
         _lib.orc_init_subvectors.restype = C.c_size_t
         _lib.orc_sph_bessel.restype = C.c_double
     return _lib
@@ -273,6 +274,85 @@ def compute_mpsphere(coords_sph, sfs, ql, moments, dsp="autocorrelate", method="
         raise RuntimeError("oracle: DSP type/method not understood")
     r = _res(atfinal, af, a2f)
     return r + (at_out,) if return_amplitudes else r
+
+
+def moments_cylinder(resolution):
+    """(0,0) then (l, 0..3) for l = 1..resolution (parameters.cpp:1062-1070)"""
+    n = lib().orc_moments_cylinder(C.c_long(resolution), None)
+    out = np.zeros((n, 2), dtype=np.int64)
+    lib().orc_moments_cylinder(C.c_long(resolution), _p(out, C.c_long))
+    return out
+
+
+def cart_to_cylindrical(xyz, axis):
+    """float32 [...][3] cartesian -> (r, phi, z) in the basis built on axis, narrowed to float32 like the stager"""
+    a = _f32(xyz)
+    out = np.empty_like(a)
+    ax = _f64(np.asarray(axis, dtype=np.float64))
+    lib().orc_cart_to_cylindrical(_p(a, C.c_float), C.c_size_t(a.size // 3), _p(ax, C.c_double), _p(out, C.c_float))
+    return out
+
+
+def compute_mpcylinder(coords_cyl, sfs, q, axis, moments, dsp="autocorrelate", method="fftw", nthreads=1,
+                       return_amplitudes=False):
+    """coords_cyl float32 [NF][NA][3] holding (r, phi, z); q the q-vector; moments int [NM][2] (l, m in 0..3)."""
+    coords = _f32(coords_cyl)
+    NF, NA, _ = coords.shape
+    sfs = _f64(sfs)
+    qv = _f64(np.asarray(q, dtype=np.float64))
+    ax = _f64(np.asarray(axis, dtype=np.float64))
+    mom = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+    NM = len(mom)
+    atfinal = np.zeros(2 * NF)
+    af, a2f = np.zeros(2), np.zeros(2)
+    at_out = np.zeros((NM, NF), dtype=np.complex128) if return_amplitudes else None
+    rc = lib().orc_compute_mpcylinder(
+        _p(coords, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(sfs, C.c_double), _p(qv, C.c_double), _p(ax, C.c_double),
+        _p(mom, C.c_long), C.c_size_t(NM), C.c_int(_DSP[dsp]), C.c_int(_METHOD[method]), C.c_int(nthreads),
+        _p(atfinal, C.c_double), _p(af, C.c_double), _p(a2f, C.c_double),
+        _p(at_out.view(np.float64), C.c_double) if return_amplitudes else None)
+    if rc == 2:
+        raise RuntimeError("oracle: multipole moment not allowed for the cylinder")
+    if rc:
+        raise RuntimeError("oracle: DSP type/method not understood")
+    r = _res(atfinal, af, a2f)
+    return r + (at_out,) if return_amplitudes else r
+
+
+def np_mpcylinder_amplitudes(coords_cyl, sfs, q, axis, moments):
+    """independent restatement of multipole_scatter_device.cpp:905-985 with scipy.special.jv; A [NM][NF] complex"""
+    from scipy.special import jv
+    base = vector_base(axis)
+    qp = base @ np.asarray(q, dtype=np.float64)
+    qr = np.hypot(qp[0], qp[1])
+    # CylinderCoor3D's azimuth (coor3d.cpp:119-129): the quadrant offsets are FLOAT pi / pi/2 (sign() returns float)
+    if qp[0] != 0.0:
+        qphi = np.arctan(qp[1] / qp[0])
+        if qp[0] < 0.0:
+            qphi += float(np.float32(np.pi)) * (-1.0 if qp[1] < 0.0 else 1.0)
+    elif qp[1] != 0.0:
+        qphi = float(np.float32(np.pi / 2)) * (-1.0 if qp[1] < 0.0 else 1.0)
+    else:
+        qphi = 0.0
+    if qphi < 0:
+        qphi += 2 * np.pi
+    qz = qp[2]
+    c = np.asarray(coords_cyl, dtype=np.float64)
+    r, phi, z = c[..., 0], c[..., 1], c[..., 2]
+    w = np.asarray(sfs)[None, :] * np.exp(1j * np.abs(z * qz))
+    p, psi = r * qr, phi - qphi
+    out = []
+    for l, m in np.asarray(moments).reshape(-1, 2):
+        if l == 0:
+            f = jv(0, p)
+        elif m < 2:
+            n = 2 * l
+            f = np.sqrt(0.5) * 2.0 * (-1.0) ** l * jv(n, p) * (np.cos(n * psi) if m == 0 else np.sin(n * psi))
+        else:
+            n = 2 * l - 1
+            f = 1j * np.sqrt(0.5) * 2.0 * (-1.0) ** (l - 1) * jv(n, p) * (np.cos(n * psi) if m == 2 else np.sin(n * psi))
+        out.append(np.sqrt(2 * np.pi) * np.sum(w * f, axis=1))
+    return np.array(out)
 
 
 def max_threads():

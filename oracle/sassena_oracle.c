@@ -893,6 +893,153 @@ int orc_compute_mpsphere(const float *coords_sph, size_t NF, size_t NA, const do
     return err;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* multipole cylinder                                                                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* include/math/coor3d.hpp:30 -- note the FLOAT arguments and result: sign(M_PI, y) is float-rounded pi */
+static float sign_f(float a, float b) { return (b < 0.0) ? -a : a; }
+
+/* CylinderCoor3D(CartesianCoor3D) -- coor3d.cpp:113-138 */
+static void cart_to_cyl(double x, double y, double z, double *r, double *phi, double *zo) {
+    *r = sqrt(pow(x, 2) + pow(y, 2));
+    double p;
+    if (x != 0.0) {
+        p = atan(y / x);
+        if (x < 0.0) p = sign_f(M_PI, y) + p;
+    } else if (y != 0.0) {
+        p = sign_f(M_PI_2, y);
+    } else {
+        p = 0.0;
+    }
+    p = p < 0 ? 2 * M_PI + p : p;
+    *phi = p;
+    *zo = z;
+}
+
+/* CylindricalCoordinateSet(cs, axis) -- src/sample/coordinate_set.cpp:278-296: project on CartesianVectorBase(axis)
+ * (coor3d.cpp:278-304), convert, then the stager's narrowing to float (data_stager.cpp:111-113).  in: float xyz [n][3] */
+void orc_cart_to_cylindrical(const float *xyz, size_t n, const double axis[3], float *out) {
+    double base[9];
+    orc_vector_base(axis, base);
+    for (size_t i = 0; i < n; i++) {
+        double c[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        double p[3];
+        for (int k = 0; k < 3; k++) p[k] = c[0] * base[3 * k] + c[1] * base[3 * k + 1] + c[2] * base[3 * k + 2];
+        double r, phi, z;
+        cart_to_cyl(p[0], p[1], p[2], &r, &phi, &z);
+        out[3 * i] = (float)r;
+        out[3 * i + 1] = (float)phi;
+        out[3 * i + 2] = (float)z;
+    }
+}
+
+/* MPCylinderScatterDevice::scatter -- multipole_scatter_device.cpp:905-985.  coords float [NF][NA][3] = (r, phi, z).
+ * Boost's cyl_bessel_j is restated with the C library's jn() (both are accurate to a few ulp). */
+void orc_scatter_mpcylinder(const float *coords, size_t NA, size_t f0, size_t f1, const double *sfs, const double q[3],
+                            const double axis[3], long l, long m, double *at /* [NF][2] */) {
+    double base[9];
+    orc_vector_base(axis, base);
+    double qp[3];
+    for (int k = 0; k < 3; k++) qp[k] = q[0] * base[3 * k] + q[1] * base[3 * k + 1] + q[2] * base[3 * k + 2];
+    double qr, qphi, qz;
+    cart_to_cyl(qp[0], qp[1], qp[2], &qr, &qphi, &qz);
+    for (size_t fi = f0; fi < f1; ++fi) {
+        const float *p_data = &coords[fi * NA * 3];
+        cplx A = 0;
+        for (size_t j = 0; j < NA; ++j) {
+            double r = p_data[3 * j];
+            double phi = p_data[3 * j + 1];
+            double z = p_data[3 * j + 2];
+            double esf = sfs[j];
+            double parallel_sign = 1.0;
+            if ((z != 0) && (qz != 0)) parallel_sign = (z * qz) / (fabs(z) * fabs(qz));
+            cplx expi = cexp(I * (parallel_sign * z * qz));
+            double p = r * qr;
+            double psiphi = phi - qphi;
+            if (m == 0 && l == 0) {
+                A += expi * jn(0, p) * esf;
+            } else if (m == 0) {
+                cplx fac1 = 2.0 * powf(-1.0, l) * jn((int)(2 * l), p);
+                A += sqrt(0.5) * fac1 * expi * cos(2 * l * psiphi) * esf;
+            } else if (m == 1) {
+                cplx fac1 = 2.0 * powf(-1.0, l) * jn((int)(2 * l), p);
+                A += sqrt(0.5) * fac1 * expi * sin(2 * l * psiphi) * esf;
+            } else if (m == 2) {
+                cplx fac2 = I * (double)(2.0 * powf(-1.0, l - 1) * jn((int)(2 * l - 1), p));
+                A += sqrt(0.5) * fac2 * expi * cos((2 * l - 1) * psiphi) * esf;
+            } else if (m == 3) {
+                cplx fac2 = I * (double)(2.0 * powf(-1.0, l - 1) * jn((int)(2 * l - 1), p));
+                A += sqrt(0.5) * fac2 * expi * sin((2 * l - 1) * psiphi) * esf;
+            }
+        }
+        double norm = sqrt(2 * M_PI);
+        at[2 * fi] = norm * creal(A);
+        at[2 * fi + 1] = norm * cimag(A);
+    }
+}
+
+/* MPCylinderScatterDevice::compute (NNPP==1) -- multipole_scatter_device.cpp:700-870; norm 1/(2 pi) (:866).
+ * Moment validity: parameters.cpp:1082-1102. */
+int orc_compute_mpcylinder(const float *coords_cyl, size_t NF, size_t NA, const double *sfs, const double q[3],
+                           const double axis[3], const long *moments /* [NM][2] */, size_t NM, int dsp_type, int dsp_method,
+                           int nthreads, double *atfinal, double afinal[2], double a2final[2], double *at_out) {
+    memset(atfinal, 0, NF * 2 * sizeof(double));
+    cplx af = 0, a2f = 0;
+    if (nthreads < 1) nthreads = 1;
+    size_t NT = (size_t)nthreads;
+    for (size_t i = 0; i < NM; i++) {
+        long l = moments[2 * i], m = moments[2 * i + 1];
+        if (l < 0 || m < 0 || m > 3 || (l == 0 && m != 0)) return 2;
+    }
+    double *at_ = (double *)malloc(NF * NT * 2 * sizeof(double));
+    double *nat = (double *)malloc(2 * NF * 2 * sizeof(double));
+    int err = 0;
+    for (size_t i = 0; i < NM; i += NT) {
+        size_t cnt = (NM - i < NT) ? NM - i : NT;
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+        for (size_t j = 0; j < cnt; j++) {
+            orc_scatter_mpcylinder(coords_cyl, NA, 0, NF, sfs, q, axis, moments[2 * (i + j)], moments[2 * (i + j) + 1],
+                                   &at_[((j + i) % NT) * NF * 2]);
+        }
+        for (size_t j = 0; j < cnt; ++j) {
+            const double *pat = &at_[((j + i) % NT) * NF * 2];
+            if (at_out) memcpy(&at_out[(i + j) * NF * 2], pat, NF * 2 * sizeof(double));
+            memcpy(nat, pat, NF * 2 * sizeof(double));
+            memset(&nat[2 * NF], 0, NF * 2 * sizeof(double));
+            err |= dsp(nat, NF, dsp_type, dsp_method);
+            store(nat, NF, atfinal, &af, &a2f);
+        }
+    }
+    free(at_);
+    free(nat);
+    double factor = 1.0 / (2 * M_PI);
+    for (size_t n = 0; n < NF; n++) {
+        atfinal[2 * n] *= factor;
+        atfinal[2 * n + 1] *= factor;
+    }
+    af *= factor;
+    a2f *= factor;
+    afinal[0] = creal(af);
+    afinal[1] = cimag(af);
+    a2final[0] = creal(a2f);
+    a2final[1] = cimag(a2f);
+    return err;
+}
+
+/* moments generator, cylinder branch -- parameters.cpp:1062-1070 */
+size_t orc_moments_cylinder(long resolution, long *out /* [n][2] */) {
+    size_t n = 0;
+    if (out) { out[0] = 0; out[1] = 0; }
+    n++;
+    for (long l = 1; l <= resolution; ++l)
+        for (long m = 0; m <= 3; ++m) {
+            if (out) { out[2 * n] = l; out[2 * n + 1] = m; }
+            n++;
+        }
+    return n;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

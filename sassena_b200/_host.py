@@ -43,6 +43,8 @@ BE_AV_SCAN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p
 BE_AV_SCAN_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_void_p)
 BE_STAGE_WAVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t)
 BE_ACCUMULATE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+BE_TO_CYL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p)
+BE_CYL_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, c_double_p, c_long_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -58,7 +60,8 @@ class BackendVtbl(C.Structure):
                 ("mpsphere_dsp_partial", BE_MP_DSP), ("set_frame_window", BE_SET_WINDOW),
                 ("all_vectors_amplitudes", BE_AV_AMPL), ("all_vectors_dsp_partial", BE_AV_DSP),
                 ("compute_all_vectors_scan_partial", BE_AV_SCAN), ("all_vectors_scan_amplitudes", BE_AV_SCAN_AMPL),
-                ("stage_atoms_wave", BE_STAGE_WAVE), ("accumulate", BE_ACCUMULATE)]
+                ("stage_atoms_wave", BE_STAGE_WAVE), ("accumulate", BE_ACCUMULATE),
+                ("frames_to_cylindrical", BE_TO_CYL), ("mpcylinder_amplitudes", BE_CYL_AMPL)]
 
 
 FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)

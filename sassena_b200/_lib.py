@@ -32,6 +32,12 @@ SIGNATURES = {
     "sgpu_stage_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "sgpu_stage_frames_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "sgpu_frames_to_spherical": (C.c_int, [C.c_void_p]),
+    "sgpu_frames_to_cylindrical": (C.c_int, [C.c_void_p, c_double_p]),
+    "sgpu_compute_mpcylinder": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_long_p, C.c_size_t, C.c_int, C.c_int, c_double_p,
+                                          c_double_p, c_double_p]),
+    "sgpu_compute_mpcylinder_partial": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_long_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "sgpu_mpcylinder_amplitudes": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_long_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                             C.c_void_p]),
     "sgpu_stage_atoms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_from_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),

@@ -206,6 +206,34 @@ class ScatterContext:
                                                 _dsp(dsp), _method(method), _dp(at), _dp(af), _dp(a2f)))
         return self._pack(at, af, a2f)
 
+    def frames_to_cylindrical(self, axis):
+        """staged cartesian frames -> (r, phi, z) in the basis built on `axis` (MPCylinder devices)"""
+        ax = np.ascontiguousarray(axis, dtype=np.float64).reshape(3)
+        self._ck(self.lib.sgpu_frames_to_cylindrical(self.h, _dp(ax)))
+
+    def compute_mpcylinder(self, q, axis, moments, dsp="autocorrelate", method="fftw"):
+        qv = np.ascontiguousarray(q, dtype=np.float64).reshape(3)
+        ax = np.ascontiguousarray(axis, dtype=np.float64).reshape(3)
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        at, af, a2f = self._outputs()
+        self._ck(self.lib.sgpu_compute_mpcylinder(self.h, _dp(qv), _dp(ax), lm.ctypes.data_as(C.POINTER(C.c_long)), len(lm),
+                                                  _dsp(dsp), _method(method), _dp(at), _dp(af), _dp(a2f)))
+        return self._pack(at, af, a2f)
+
+    def compute_mpcylinder_partial(self, q, axis, moments, d_partial: int, dsp="autocorrelate"):
+        qv = np.ascontiguousarray(q, dtype=np.float64).reshape(3)
+        ax = np.ascontiguousarray(axis, dtype=np.float64).reshape(3)
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        self._ck(self.lib.sgpu_compute_mpcylinder_partial(self.h, _dp(qv), _dp(ax), lm.ctypes.data_as(C.POINTER(C.c_long)),
+                                                          len(lm), _dsp(dsp), C.c_void_p(d_partial)))
+
+    def mpcylinder_amplitudes(self, q, axis, moments, atom_first, atom_count, d_amp: int):
+        qv = np.ascontiguousarray(q, dtype=np.float64).reshape(3)
+        ax = np.ascontiguousarray(axis, dtype=np.float64).reshape(3)
+        lm = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+        self._ck(self.lib.sgpu_mpcylinder_amplitudes(self.h, _dp(qv), _dp(ax), lm.ctypes.data_as(C.POINTER(C.c_long)), len(lm),
+                                                     atom_first, atom_count, C.c_void_p(d_amp)))
+
     def set_factors_batch(self, b):
         b = np.ascontiguousarray(b, dtype=np.float64)
         self._ck(self.lib.sgpu_set_factors_batch(self.h, _dp(b), b.shape[0], b.shape[1]))

@@ -329,7 +329,9 @@ const SgpuBackend &default_backend() {
                                    sgpu_compute_all_vectors_scan_partial,
                                    sgpu_all_vectors_scan_amplitudes,
                                    sgpu_stage_atoms_wave,
-                                   sgpu_accumulate};
+                                   sgpu_accumulate,
+                                   sgpu_frames_to_cylindrical,
+                                   sgpu_mpcylinder_amplitudes};
     return be;
 }
 
@@ -1087,6 +1089,72 @@ void MPSphereScatterDevice::runner() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// MPCylinderScatterDevice (multipole_scatter_device.cpp:504-985)
+// ---------------------------------------------------------------------------------------------------------------
+MPCylinderScatterDevice::~MPCylinderScatterDevice() {
+    if (d_amp_) be_.device_free(d_amp_);
+}
+
+void MPCylinderScatterDevice::stage_data() {
+    DataStagerByFrame data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
+    data_stager.stage(SGPU_REPR_CARTESIAN);
+    // sample_.coordinate_sets.set_representation(CYLINDRICAL) (:524): CylindricalCoordinateSet around the orientation axis
+    const CartesianCoor3D &o = params_.scattering.axis;
+    const double axis[3] = {o.x, o.y, o.z};
+    ck(be_.frames_to_cylindrical(ctx_, axis), "sgpu_frames_to_cylindrical");
+    factors_.assign(NA, 0.0);
+}
+
+void MPCylinderScatterDevice::compute() {
+    CartesianCoor3D q = vectors_[current_vector_];
+    timer_.start("sd:c:init");
+    multipole_index_ = params_.scattering.multipole.moments;  // init_moments (:690-700)
+    NM = multipole_index_.size();
+    sample_.factors(q.length(), factors_.data());  // scatterfactors.update(q)
+    ck(be_.set_factors(ctx_, factors_.data(), NA), "sgpu_set_factors");
+    std::vector<long> lm(2 * NM);
+    for (size_t i = 0; i < NM; i++) {
+        lm[2 * i] = multipole_index_[i].first;
+        lm[2 * i + 1] = multipole_index_[i].second;
+    }
+    const int dsp = dsp_type_code();
+    dsp_method_code();
+    const size_t amp_len = NM * NF * 2;
+    if (amp_len > amp_cap_) {
+        if (d_amp_) be_.device_free(d_amp_);
+        d_amp_ = nullptr;
+        void *pp = nullptr;
+        if (be_.device_alloc(&pp, amp_len * sizeof(double))) throw Error("device allocation of the amplitude buffer failed");
+        d_amp_ = static_cast<double *>(pp);
+        amp_cap_ = amp_len;
+    }
+    timer_.stop("sd:c:init");
+    const CartesianCoor3D &o = params_.scattering.axis;
+    const double axis[3] = {o.x, o.y, o.z}, qv[3] = {q.x, q.y, q.z};
+    // atom decomposition inside the partition: rank r sums over DivAssignment(NNPP, r, NA) atoms (the reference splits
+    // the frames, :913-916, and exchanges timelines; amplitudes are sums over atoms, so this needs one all-reduce)
+    DivAssignment mine(partitioncomm_->size(), partitioncomm_->rank(), NA);
+    timer_.start("sd:c:block");
+    ck(be_.mpcylinder_amplitudes(ctx_, qv, axis, lm.data(), NM, mine.offset(), mine.size(), d_amp_), "sgpu_mpcylinder_amplitudes");
+    timer_.stop("sd:c:block");
+    timer_.start("sd:c:wait");
+    ck(be_.synchronize(ctx_), "sgpu_synchronize");
+    timer_.stop("sd:c:wait");
+    timer_.start("sd:c:reduce");
+    if (partitioncomm_->size() > 1) partitioncomm_->allreduce_sum(d_amp_, amp_len);
+    timer_.stop("sd:c:reduce");
+    double *partial = partial_buffer(dsp);
+    timer_.start("sd:c:b:dspstore");
+    ck(be_.mpsphere_dsp_partial(ctx_, d_amp_, 1, NM, dsp, partial), "sgpu_mpsphere_dsp_partial");
+    double af[2], a2f[2];
+    const double factor = 1.0 / (2 * M_PI);  // :866
+    ck(be_.finalize(ctx_, partial, dsp, dsp_method_code(), factor, atfinal_.data(), af, a2f), "sgpu_finalize");
+    afinal_ = std::complex<double>(af[0], af[1]);
+    a2final_ = std::complex<double>(a2f[0], a2f[1]);
+    timer_.stop("sd:c:b:dspstore");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // ScatterDeviceFactory (scatter_device_factory.cpp:23-210)
 // ---------------------------------------------------------------------------------------------------------------
 IScatterDevice *ScatterDeviceFactory::create(std::shared_ptr<ICommunicator> scatter_comm, Sample &sample,
@@ -1145,7 +1213,8 @@ IScatterDevice *ScatterDeviceFactory::create(std::shared_ptr<ICommunicator> scat
                 p_ScatterDevice = new MPSphereScatterDevice(all_comm, partition_comm, sample, thispartition_QIV, NAF,
                                                             sink, params, be, ctx);
             } else if (params.scattering.multipole.type == "cylinder") {
-                throw Error("MPCylinderScatterDevice is not part of the B200 hot path yet (SURVEY 8f-4)");
+                p_ScatterDevice = new MPCylinderScatterDevice(all_comm, partition_comm, sample, thispartition_QIV, NAF,
+                                                              sink, params, be, ctx);
             } else {
                 throw Error("scattering.average.orientation.multipole.type not understood: " +
                             params.scattering.multipole.type);

@@ -453,6 +453,23 @@ class MPSphereScatterDevice : public AbstractScatterDevice {
     ~MPSphereScatterDevice() override;
 };
 
+// MPCylinderScatterDevice (multipole_scatter_device.cpp:504-985): frames staged in cylindrical coordinates around
+// scattering.average.orientation.axis, one pass over the atoms per |q| serves all moments (orders of J_n); atoms are
+// sharded over the partition's GPUs and the amplitudes all-reduced before the DSP, result scaled by 1/(2 pi).
+class MPCylinderScatterDevice : public AbstractScatterDevice {
+   protected:
+    std::vector<std::pair<long, long>> multipole_index_;
+    size_t NM = 0;
+    double *d_amp_ = nullptr;
+    size_t amp_cap_ = 0;
+    void stage_data() override;
+    void compute() override;
+
+   public:
+    using AbstractScatterDevice::AbstractScatterDevice;
+    ~MPCylinderScatterDevice() override;
+};
+
 class ScatterDeviceFactory {  // scatter_device_factory.cpp:23-210
    public:
     // returns nullptr on spare ranks (scatter_device_factory.cpp:116-120)

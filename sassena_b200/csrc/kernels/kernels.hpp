@@ -32,6 +32,14 @@ int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const d
                           size_t ldA, size_t NF, size_t NM, size_t n0, size_t nn, cudaStream_t st);
 // cart -> (r, phi, theta), in place, n points
 int launch_cart_to_spherical(float *d_xyz, size_t n, cudaStream_t st);
+// multipole cylinder (mpcylinder.cu): in-place cartesian -> (r, phi, z) in the basis `base` (rows e_r, e_phi, e_z);
+// amplitudes A[NM][NF] of the cylinder moments lm for one q = (qr, qphi, qz) over atoms [a_first, a_last)
+int launch_cart_to_cylindrical(float *d_xyz, size_t n, const double base[9], cudaStream_t st);
+int mpcylinder_max_order();
+size_t mpcylinder_work_doubles(size_t NF, int nmax, size_t natoms);
+int launch_mpcylinder(const float *d_coords, const double *d_b, double qr, double qphi, double qz, const int *d_lm, size_t NM,
+                      int nmax, double2 *d_A, size_t NF, size_t NA, size_t a_first, size_t a_last, double *d_work,
+                      cudaStream_t st);
 // chunk of frames [nf][NA][3] starting at frame f0 -> [NA_out][NF][3] taking atoms atom0 + i*stride
 int launch_frames_to_atoms(const float *d_frames, float *d_atoms, size_t NF, size_t nf, size_t f0, size_t NA,
                            size_t atom0, size_t stride, size_t NA_out, cudaStream_t st);
@@ -102,14 +110,25 @@ struct SelfPlan {
     double2 *d_tw = nullptr;  // exp(-2 pi i k / N), k < N
     double2 *d_w = nullptr;   // weights What[j][pos] (residue-major, digit-reversed position)
     int *d_freq = nullptr;    // frequency index of a digit-reversed position
+    // split path (R >= 3): R decimated sub-FFTs per timeline + an R-point DFT across them (selffused.cu, "split path")
+    bool split = false;
+    bool reg_combine = false;    // R <= 16: the R-point DFT runs in registers (one thread per position)
+    bool two_stage = false;      // composite R in 17..32: two-stage DFT in registers
+    int S = 0, C = 0;            // positions per combine CTA, number of position slices (C*S = N)
+    double2 *d_twL = nullptr;    // exp(-2 pi i k / L), k < L
+    double2 *d_w2 = nullptr;     // weights in the split layout [k2][pos]
+    int *d_perm = nullptr;       // split index k2*N + pos -> residue-major index j*N + pos' of the same frequency
 };
 int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches);
 void self_plan_destroy(SelfPlan *p);
 size_t self_work_bytes(const SelfPlan *p, size_t ntl);
 // timelines of local atoms [atom0, atom0+natoms) x NM q-vectors; d_P[L] and d_acc[4] are accumulated (+=)
+// dec != 0: the coordinates of every atom are in the split path's decimated order (self_decimate_layout, forward)
 int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const double *d_b, const double *d_qs,
-                          size_t NM, size_t atom0, size_t natoms, void *d_work, double *d_P, double *d_acc,
+                          size_t NM, size_t atom0, size_t natoms, void *d_work, double *d_P, double *d_acc, int dec,
                           cudaStream_t st);
+// natural frame order [n] <-> decimated [r][m] (frames R m + r contiguous per r) for natoms rows, out of place
+int self_decimate_layout(const float *d_src, float *d_dst, size_t natoms, size_t NF, int R, int forward, cudaStream_t st);
 int self_finalize(const SelfPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
                   cudaStream_t st);
 

@@ -20,6 +20,10 @@
 #include "sincos_qt.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace sass {
@@ -143,8 +147,17 @@ __device__ __forceinline__ void fft_regs(double2 (&x)[R]) {
 __device__ __forceinline__ double2 csqr(double2 a) { return make_double2(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
 
 // one DIF pass over blocks of span S = 2^LOG2S with radix R (q = S/R); N = 2^LOG2N
-template <int LOG2N, int LOG2S, int R, int SIGN>
-__device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__ tw) {
+struct GlobalTwiddles {  // exp(-2 pi i t / N) from an N-entry table in global memory
+    const double2 *__restrict__ tw;
+    __device__ __forceinline__ double2 operator()(int t) const { return __ldg(&tw[t]); }
+};
+struct SharedTwiddles {  // the same value as hi[t >> 6] * lo[t & 63] from two small shared-memory tables
+    const double2 *lo, *hi;
+    __device__ __forceinline__ double2 operator()(int t) const { return cmul2(hi[t >> 6], lo[t & 63]); }
+};
+
+template <int LOG2N, int LOG2S, int R, int SIGN, class TW>
+__device__ __forceinline__ void fft_pass(double2 *s, const TW &tw) {
     constexpr int N = 1 << LOG2N, S = 1 << LOG2S, q = S / R, NB = N / R;
     constexpr int LOG2R = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
     for (int id = threadIdx.x; id < NB; id += SF_THREADS) {
@@ -156,7 +169,7 @@ __device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__
         fft_regs<R, SIGN>(x);
         if (q > 1) {
             double2 w[R];  // w[c] = W_S^{k c}
-            w[1] = __ldg(&tw[k * (N / S)]);
+            w[1] = tw(k * (N / S));
             if (SIGN > 0) w[1].y = -w[1].y;
 #pragma unroll
             for (int c = 2; c < R; c++) w[c] = (c & (c - 1)) == 0 ? csqr(w[c >> 1]) : cmul2(w[c & (c - 1)], w[c & -c]);
@@ -170,8 +183,8 @@ __device__ __forceinline__ void fft_pass(double2 *s, const double2 *__restrict__
 }
 
 // full transform: radices 16, 16, N/256 (N >= 256); entry assumes the buffer is complete (does a barrier first)
-template <int LOG2N, int SIGN>
-__device__ __forceinline__ void fft_r16(double2 *s, const double2 *__restrict__ tw) {
+template <int LOG2N, int SIGN, class TW>
+__device__ __forceinline__ void fft_r16(double2 *s, const TW &tw) {
     __syncthreads();
     fft_pass<LOG2N, LOG2N, 16, SIGN>(s, tw);
     fft_pass<LOG2N, LOG2N - 4, 16, SIGN>(s, tw);
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
             }
             s[np] = v;
         }
-        fft_r16<LOG2N, (GEN == GEN_AMPLITUDE) ? -1 : +1>(s, tw);
+        fft_r16<LOG2N, (GEN == GEN_AMPLITUDE) ? -1 : +1>(s, GlobalTwiddles{tw});
         if (GEN == GEN_AMPLITUDE) {
             double2 ap = make_double2(0.0, 0.0);
 #pragma unroll 4
@@ -281,6 +294,495 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
         __syncthreads();
         for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Ppart[(g * R + j) * (size_t)N + pos] = s_acc[pos];
     }
+}
+
+// ---- split path ---------------------------------------------------------------------------------------------------
+// The fused kernel above evaluates exp(i q.r) R times per frame (once per residue).  For R >= 3 the transform is split the
+// other way round: time index n = R m + r, frequency k = k1 + N k2,
+//     X[k1 + N k2] = sum_r exp(-2 pi i r k2 / R) * ( exp(-2 pi i r k1 / L) * Z_r[k1] ),   Z_r = FFT_N( x[R m + r] )_m
+// so every frame is evaluated ONCE (it belongs to exactly one decimated sequence), the R sub-FFTs of a timeline run back to
+// back in one CTA (kernel A, coordinates stay L1/L2-hot), the twiddled Z_r go to a batch buffer in HBM/L2 ([tl][r][pos],
+// coalesced on both sides), and kernel B does the R-point DFT across r for a slice of positions, accumulates |X|^2 per
+// (k2, pos) in shared memory over all its timelines and the store() mean as the weighted sum with What (split layout).
+// The result is permuted back to the residue-major layout at the reduction, so finalize is unchanged.
+
+// frequency held by output position `pos` of fft_r16 (radices 16, 16, N/256): the base-(16,16,N/256) digit reversal
+template <int LOG2N>
+__device__ __forceinline__ int freq16_of_pos(int pos) {
+    constexpr int N = 1 << LOG2N;
+    return (pos / (N / 16)) + 16 * ((pos / (N / 256)) % 16) + 256 * (pos % (N / 256));
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// dec != 0: the atom's frames are stored decimated, [r][m] with sub-sequence r (frames R m + r) contiguous
+// (sgpu keeps owned atom-major buffers in that layout while the split path is in use); otherwise natural order.
+// A CTA walks its (timeline, r) pairs; the coordinates of the next pair are fetched into shared memory with cp.async
+// while the current sub-transform runs, and all twiddles (inter-pass W_N^t and the split's W_L^t) come from small
+// shared-memory tables (hi * lo), so the only global accesses on the critical path are the Z stores.
+template <int LOG2N>
+__global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
+    const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs, int NF, int NM, size_t atom0,
+    size_t tl_first, size_t ntl, int R, int dec, double2 *__restrict__ Zt) {
+    extern __shared__ double2 s[];
+    constexpr int N = 1 << LOG2N;
+    constexpr int NHI = (N >= 64) ? N / 64 : 1;
+    // exp(-2 pi i t / L) = Thi[t >> 8] * Tlo[t & 255];  exp(-2 pi i t / N) = TNhi[t >> 6] * TNlo[t & 63]
+    double2 *Tlo = s + N + N / 16;
+    double2 *Thi = Tlo + 256;
+    const int L = R * N;
+    double2 *TNlo = Thi + (L >> 8);
+    double2 *TNhi = TNlo + 64;
+    float *cbuf = reinterpret_cast<float *>(TNhi + NHI);  // coordinates of one sub-sequence, [m][3]
+    for (int i = threadIdx.x; i < 256 + (L >> 8); i += SF_THREADS) {
+        const int t = (i < 256) ? i : ((i - 256) << 8);
+        double sn, cs;
+        sincospi(-2.0 * (double)t / (double)L, &sn, &cs);
+        Tlo[i] = make_double2(cs, sn);  // Thi follows Tlo
+    }
+    for (int i = threadIdx.x; i < 64 + NHI; i += SF_THREADS) {
+        const int t = (i < 64) ? i : ((i - 64) << 6);
+        double sn, cs;
+        sincospi(-2.0 * (double)t / (double)N, &sn, &cs);
+        TNlo[i] = make_double2(cs, sn);  // TNhi follows TNlo
+    }
+    const SharedTwiddles twN{TNlo, TNhi};
+    const int base = NF / R, rem = NF % R;
+    const size_t G = gridDim.x, g = blockIdx.x;
+    const size_t per = (ntl + G - 1) / G;
+    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
+    const size_t npairs = (t_end > t_begin) ? (t_end - t_begin) * (size_t)R : 0;
+    auto prefetch = [&](size_t pair) {
+        const size_t t = t_begin + pair / R;
+        const int r = (int)(pair % R);
+        const size_t atom = atom0 + (tl_first + t) / NM;
+        const float *p = xyz + atom * (size_t)NF * 3;
+        const int Mr = base + (r < rem ? 1 : 0);
+        if (dec) {
+            const float *pr = p + 3 * (size_t)(r * base + min(r, rem));
+            for (int e = threadIdx.x; e < 3 * Mr; e += SF_THREADS) cp_async4(&cbuf[e], &pr[e]);
+        } else {
+            for (int e = threadIdx.x; e < 3 * Mr; e += SF_THREADS) {
+                const int mm = e / 3, c = e - 3 * mm;
+                cp_async4(&cbuf[e], &p[3 * ((size_t)R * mm + r) + c]);
+            }
+        }
+        cp_async_commit_group();
+    };
+    if (npairs) prefetch(0);
+    for (size_t pair = 0; pair < npairs; pair++) {
+        const size_t t = t_begin + pair / R;
+        const int r = (int)(pair % R);
+        const size_t tl = tl_first + t;
+        const int m = (int)(tl % NM);
+        const double qx = __ldg(&qs[3 * m]), qy = __ldg(&qs[3 * m + 1]), qz = __ldg(&qs[3 * m + 2]);
+        const double bn = __ldg(&b[atom0 + tl / NM]);
+        const int Mr = base + (r < rem ? 1 : 0);
+        cp_async_wait_all();
+        __syncthreads();  // coordinates of this pair are in cbuf; the previous sub-transform has been written out
+#pragma unroll 4
+        for (int mm = threadIdx.x; mm < N; mm += SF_THREADS) {
+            double2 v = make_double2(0.0, 0.0);
+            if (mm < Mr) {
+                const double x = (double)cbuf[3 * mm], y = (double)cbuf[3 * mm + 1], z = (double)cbuf[3 * mm + 2];
+                const double u = fma(z, qz, fma(y, qy, x * qx));
+                double sn, cs;
+                sincos_qt(u, sn, cs);
+                v = make_double2(bn * cs, bn * sn);
+            }
+            s[phys(mm)] = v;
+        }
+        __syncthreads();  // cbuf consumed
+        if (pair + 1 < npairs) prefetch(pair + 1);  // lands while the transform below runs
+        fft_pass<LOG2N, LOG2N, 16, -1>(s, twN);
+        fft_pass<LOG2N, LOG2N - 4, 16, -1>(s, twN);
+        if (LOG2N == 9) fft_pass<LOG2N, 1, 2, -1>(s, twN);
+        if (LOG2N == 10) fft_pass<LOG2N, 2, 4, -1>(s, twN);
+        if (LOG2N == 11) fft_pass<LOG2N, 3, 8, -1>(s, twN);
+        if (LOG2N == 12) fft_pass<LOG2N, 4, 16, -1>(s, twN);
+        double2 *out = Zt + ((t * R + r) << LOG2N);
+#pragma unroll 4
+        for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) {
+            const int th = (r * freq16_of_pos<LOG2N>(pos)) % L;
+            const double2 w = cmul2(Thi[th >> 8], Tlo[th & 255]);
+            out[pos] = cmul2(s[phys(pos)], w);
+        }
+    }
+}
+
+// natural [n] <-> decimated [r][m] order of one atom's frames, out of place: dst[atom][...] = src[atom][...]
+__global__ void sf_decimate_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t natoms, int NF, int R,
+                                   int forward) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= natoms * (size_t)NF) return;
+    const size_t atom = i / NF;
+    const int n = (int)(i - atom * NF);
+    const int base = NF / R, rem = NF % R;
+    const int r = n % R, m = n / R;
+    const size_t d = atom * (size_t)NF + (size_t)(r * base + min(r, rem)) + m;
+    const size_t from = forward ? i : d, to = forward ? d : i;
+    dst[3 * to] = src[3 * from];
+    dst[3 * to + 1] = src[3 * from + 1];
+    dst[3 * to + 2] = src[3 * from + 2];
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// grid = (C, G).  CTA (c, g): positions [c*S, (c+1)*S) of the timelines in its share of the batch.
+// dynamic shared memory: Zs[2][R*S] double2 | Wh[R*S] double2 | acc[R*S] double | Wr[R] double2 | red[2][8] double2
+__global__ void __launch_bounds__(SF_THREADS) self_split_combine_kernel(const double2 *__restrict__ Zt, int N, int R, int S,
+                                                                        size_t ntl, size_t tl_first,
+                                                                        const double2 *__restrict__ What2,
+                                                                        double *__restrict__ Ppart2,
+                                                                        double2 *__restrict__ a_part) {
+    extern __shared__ double2 sm2[];
+    const int RS = R * S;
+    double2 *Zs = sm2;
+    double2 *Wh = Zs + 2 * RS;
+    double *acc = reinterpret_cast<double *>(Wh + RS);
+    double2 *Wr = reinterpret_cast<double2 *>(acc + RS + (RS & 1));
+    double2 *red = Wr + R;
+    const int c = blockIdx.x, C = gridDim.x;
+    const size_t g = blockIdx.y, G = gridDim.y;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < RS; e += SF_THREADS) {
+        const int k2 = e / S, pos = e - k2 * S;
+        Wh[e] = __ldg(&What2[(size_t)k2 * N + c * S + pos]);
+        acc[e] = 0.0;
+    }
+    for (int r = tid; r < R; r += SF_THREADS) {
+        double sn, cs;
+        sincospi(-2.0 * (double)r / (double)R, &sn, &cs);
+        Wr[r] = make_double2(cs, sn);
+    }
+    const size_t per = (ntl + G - 1) / G;
+    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
+    auto prefetch = [&](size_t t, int buf) {
+        const double2 *src = Zt + t * (size_t)R * N + (size_t)c * S;
+        double2 *dst = Zs + buf * RS;
+        for (int e = tid; e < RS; e += SF_THREADS) {
+            const int r = e / S, pos = e - r * S;
+            cp_async16(&dst[e], &src[(size_t)r * N + pos]);
+        }
+        cp_async_commit();
+    };
+    if (t_begin < t_end) prefetch(t_begin, 0);
+    int buf = 0;
+    for (size_t t = t_begin; t < t_end; t++, buf ^= 1) {
+        if (t + 1 < t_end) {
+            prefetch(t + 1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // slice t visible to all; everyone is done with iteration t-1 (its red[] slot is complete)
+        if (tid == 0 && t > t_begin) {  // deferred block sum of the previous timeline
+            const double2 *rd = red + ((buf ^ 1) * (SF_THREADS / 32));
+            double2 sum = rd[0];
+#pragma unroll
+            for (int w = 1; w < SF_THREADS / 32; w++) {
+                sum.x += rd[w].x;
+                sum.y += rd[w].y;
+            }
+            a_part[(tl_first + t - 1) * C + c] = sum;
+        }
+        const double2 *Z = Zs + buf * RS;
+        double2 ap = make_double2(0.0, 0.0);
+        for (int e = tid; e < RS; e += SF_THREADS) {
+            const int k2 = e / S, pos = e - k2 * S;
+            double xr = 0.0, xi = 0.0;
+            int idx = 0;
+            for (int r = 0; r < R; r++) {
+                const double2 z = Z[r * S + pos];
+                const double2 w = Wr[idx];
+                xr = fma(z.x, w.x, fma(-z.y, w.y, xr));
+                xi = fma(z.x, w.y, fma(z.y, w.x, xi));
+                idx += k2;
+                if (idx >= R) idx -= R;
+            }
+            const double pw = fma(xr, xr, xi * xi);
+            acc[e] += pw;
+            const double2 wh = Wh[e];
+            ap.x = fma(pw, wh.x, ap.x);
+            ap.y = fma(pw, wh.y, ap.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ap.x += __shfl_xor_sync(0xffffffffu, ap.x, o);
+            ap.y += __shfl_xor_sync(0xffffffffu, ap.y, o);
+        }
+        if ((tid & 31) == 0) red[buf * (SF_THREADS / 32) + (tid >> 5)] = ap;
+        __syncthreads();  // buffer `buf` may be overwritten by the prefetch of iteration t+1
+    }
+    if (tid == 0 && t_begin < t_end) {
+        const double2 *rd = red + ((buf ^ 1) * (SF_THREADS / 32));
+        double2 sum = rd[0];
+#pragma unroll
+        for (int w = 1; w < SF_THREADS / 32; w++) {
+            sum.x += rd[w].x;
+            sum.y += rd[w].y;
+        }
+        a_part[(tl_first + t_end - 1) * C + c] = sum;
+    }
+    for (int e = tid; e < RS; e += SF_THREADS) {
+        const int k2 = e / S, pos = e - k2 * S;
+        Ppart2[(g * R + k2) * (size_t)N + c * S + pos] = acc[e];
+    }
+}
+
+// Register version for compile-time R: a thread owns one position, keeps its R inputs in registers and evaluates the R
+// outputs with the twiddles exp(-2 pi i k / R) read as constant-bank operands (c_Wr, set at plan creation) -- no index
+// arithmetic and no shared-memory traffic for the matrix.  grid = (C, G) with S = 256 positions per CTA... S == blockDim.
+__constant__ double2 c_Wr[64];
+
+template <int R>
+__global__ void __launch_bounds__(SF_THREADS) self_split_combine_reg_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
+                                                                            size_t tl_first,
+                                                                            const double2 *__restrict__ What2,
+                                                                            double *__restrict__ Ppart2,
+                                                                            double2 *__restrict__ a_part) {
+    constexpr int SLOTS = 8;  // per-warp partial sums of 8 timelines are combined with one barrier
+    __shared__ double2 red[SLOTS][SF_THREADS / 32];
+    const int c = blockIdx.x, C = gridDim.x;
+    const size_t g = blockIdx.y, G = gridDim.y;
+    const int tid = threadIdx.x;
+    const int pos = c * SF_THREADS + tid;
+    double acc[R];
+    double2 wh[R];
+#pragma unroll
+    for (int k2 = 0; k2 < R; k2++) {
+        acc[k2] = 0.0;
+        wh[k2] = __ldg(&What2[(size_t)k2 * N + pos]);
+    }
+    const size_t per = (ntl + G - 1) / G;
+    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
+    double2 z[R], zn[R];
+    if (t_begin < t_end) {
+#pragma unroll
+        for (int r = 0; r < R; r++) zn[r] = Zt[(t_begin * R + r) * (size_t)N + pos];
+    }
+    auto flush = [&](size_t t_first, int count) {  // block sums of `count` timelines starting at t_first
+        __syncthreads();
+        if (tid < count) {
+            double2 sum = red[tid][0];
+#pragma unroll
+            for (int w = 1; w < SF_THREADS / 32; w++) {
+                sum.x += red[tid][w].x;
+                sum.y += red[tid][w].y;
+            }
+            a_part[(tl_first + t_first + tid) * C + c] = sum;
+        }
+        __syncthreads();
+    };
+    int slot = 0;
+    for (size_t t = t_begin; t < t_end; t++) {
+#pragma unroll
+        for (int r = 0; r < R; r++) z[r] = zn[r];
+        if (t + 1 < t_end) {  // software prefetch of the next timeline's inputs
+#pragma unroll
+            for (int r = 0; r < R; r++) zn[r] = Zt[((t + 1) * R + r) * (size_t)N + pos];
+        }
+        double2 ap = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k2 = 0; k2 < R; k2++) {
+            double xr = z[0].x, xi = z[0].y;
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                const int idx = (r * k2) % R;
+                if (idx == 0) {
+                    xr += z[r].x;
+                    xi += z[r].y;
+                } else {
+                    xr = fma(z[r].x, c_Wr[idx].x, fma(-z[r].y, c_Wr[idx].y, xr));
+                    xi = fma(z[r].x, c_Wr[idx].y, fma(z[r].y, c_Wr[idx].x, xi));
+                }
+            }
+            const double pw = fma(xr, xr, xi * xi);
+            acc[k2] += pw;
+            ap.x = fma(pw, wh[k2].x, ap.x);
+            ap.y = fma(pw, wh[k2].y, ap.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ap.x += __shfl_xor_sync(0xffffffffu, ap.x, o);
+            ap.y += __shfl_xor_sync(0xffffffffu, ap.y, o);
+        }
+        if ((tid & 31) == 0) red[slot][tid >> 5] = ap;
+        if (++slot == SLOTS) {
+            flush(t + 1 - SLOTS, SLOTS);
+            slot = 0;
+        }
+    }
+    if (slot) flush(t_end - slot, slot);
+#pragma unroll
+    for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2];
+}
+
+// Two-stage version for composite R = R1*R2 (17..64): r = R2 a + b, k2 = c + R1 d,
+//     X[c + R1 d] = sum_b w_R2^{b d} ( w_R^{b c} sum_a z[R2 a + b] w_R1^{a c} )
+// in place in the thread's R registers (R1^2 R2 + R1 R2^2 complex multiply-adds instead of R^2).  The power accumulators and
+// the weights live in shared memory as thread-private columns [k2][tid].
+template <int R1, int R2>
+__global__ void __launch_bounds__(SF_THREADS) self_split_combine_2s_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
+                                                                           size_t tl_first,
+                                                                           const double2 *__restrict__ What2,
+                                                                           double *__restrict__ Ppart2,
+                                                                           double2 *__restrict__ a_part) {
+    constexpr int R = R1 * R2;
+    extern __shared__ double2 sm3[];
+    double2 *wh = sm3;                                                   // [R][256]
+    double *acc = reinterpret_cast<double *>(wh + R * SF_THREADS);       // [R][256]
+    __shared__ double2 red[2][SF_THREADS / 32];
+    const int c_ = blockIdx.x, C = gridDim.x;
+    const size_t g = blockIdx.y, G = gridDim.y;
+    const int tid = threadIdx.x;
+    const int pos = c_ * SF_THREADS + tid;
+#pragma unroll 1
+    for (int k2 = 0; k2 < R; k2++) {
+        acc[k2 * SF_THREADS + tid] = 0.0;
+        wh[k2 * SF_THREADS + tid] = __ldg(&What2[(size_t)k2 * N + pos]);
+    }
+    const size_t per = (ntl + G - 1) / G;
+    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
+    int buf = 0;
+    for (size_t t = t_begin; t < t_end; t++, buf ^= 1) {
+        double2 z[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) z[r] = Zt[(t * R + r) * (size_t)N + pos];
+        // stage 1: R1-point DFT over a for every b, then the twiddle w_R^{b c}
+#pragma unroll
+        for (int bb = 0; bb < R2; bb++) {
+            double2 y[R1];
+#pragma unroll
+            for (int c = 0; c < R1; c++) {
+                double xr = z[bb].x, xi = z[bb].y;
+#pragma unroll
+                for (int a = 1; a < R1; a++) {
+                    const int idx = (R2 * a * c) % R;
+                    const double2 v = z[R2 * a + bb];
+                    if (idx == 0) {
+                        xr += v.x;
+                        xi += v.y;
+                    } else {
+                        xr = fma(v.x, c_Wr[idx].x, fma(-v.y, c_Wr[idx].y, xr));
+                        xi = fma(v.x, c_Wr[idx].y, fma(v.y, c_Wr[idx].x, xi));
+                    }
+                }
+                const int ti = (bb * c) % R;
+                if (ti == 0) {
+                    y[c] = make_double2(xr, xi);
+                } else {
+                    y[c] = make_double2(fma(xr, c_Wr[ti].x, -xi * c_Wr[ti].y), fma(xr, c_Wr[ti].y, xi * c_Wr[ti].x));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < R1; c++) z[R2 * c + bb] = y[c];  // Y_b[c] stored at slot R2 c + b
+        }
+        // stage 2: R2-point DFT over b for every c; output k2 = c + R1 d
+        double2 ap = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int c = 0; c < R1; c++) {
+#pragma unroll
+            for (int d = 0; d < R2; d++) {
+                double xr = z[R2 * c].x, xi = z[R2 * c].y;
+#pragma unroll
+                for (int bb = 1; bb < R2; bb++) {
+                    const int idx = (R1 * bb * d) % R;
+                    const double2 v = z[R2 * c + bb];
+                    if (idx == 0) {
+                        xr += v.x;
+                        xi += v.y;
+                    } else {
+                        xr = fma(v.x, c_Wr[idx].x, fma(-v.y, c_Wr[idx].y, xr));
+                        xi = fma(v.x, c_Wr[idx].y, fma(v.y, c_Wr[idx].x, xi));
+                    }
+                }
+                const int k2 = c + R1 * d;
+                const double pw = fma(xr, xr, xi * xi);
+                acc[k2 * SF_THREADS + tid] += pw;
+                const double2 w = wh[k2 * SF_THREADS + tid];
+                ap.x = fma(pw, w.x, ap.x);
+                ap.y = fma(pw, w.y, ap.y);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ap.x += __shfl_xor_sync(0xffffffffu, ap.x, o);
+            ap.y += __shfl_xor_sync(0xffffffffu, ap.y, o);
+        }
+        if ((tid & 31) == 0) red[buf][tid >> 5] = ap;
+        __syncthreads();
+        if (tid == 0) {
+            double2 sum = red[buf][0];
+#pragma unroll
+            for (int w = 1; w < SF_THREADS / 32; w++) {
+                sum.x += red[buf][w].x;
+                sum.y += red[buf][w].y;
+            }
+            a_part[(tl_first + t) * C + c_] = sum;
+        }
+    }
+#pragma unroll 1
+    for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2 * SF_THREADS + tid];
+}
+
+template <int R1, int R2>
+void launch_combine_2s(dim3 grid, cudaStream_t st, const double2 *Zt, int N, size_t nt, size_t t0, const double2 *w2, double *Ppart2,
+                       double2 *a_part) {
+    constexpr size_t smem = (size_t)R1 * R2 * SF_THREADS * (sizeof(double2) + sizeof(double));
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(self_split_combine_2s_kernel<R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    self_split_combine_2s_kernel<R1, R2><<<grid, SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+}
+
+// composite R the two-stage kernel is instantiated for: (R1, R2) with R1 <= R2, both <= 8, R <= 32
+struct SplitFactor {
+    int R, R1, R2;
+};
+constexpr SplitFactor kSplitFactors[] = {{18, 3, 6}, {20, 4, 5}, {21, 3, 7}, {24, 4, 6}, {25, 5, 5}, {28, 4, 7}, {30, 5, 6}, {32, 4, 8}};
+
+// P[perm[i]] += sum_g Ppart2[g][i]   (split layout -> residue-major layout; perm is a bijection)
+__global__ void sf_reduce_ppart_perm_kernel(const double *__restrict__ Ppart, size_t G, size_t len, const int *__restrict__ perm,
+                                            double *__restrict__ P) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double sum = 0.0;
+    for (size_t g = 0; g < G; g++) sum += Ppart[g * len + i];
+    P[perm[i]] += sum;
+}
+
+// twP[r*N + pos] = exp(-2 pi i r freq16[pos] / L): the twiddles of the split path in the order the sub-transform leaves
+// its outputs, so that kernel A reads them coalesced
+__global__ void sf_split_twiddle_kernel(double2 *twP, const int *__restrict__ freq16, size_t N, int R) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= N * R) return;
+    const size_t r = i / N, pos = i - r * N;
+    const size_t L = N * R;
+    double sn, cs;
+    sincospi(-2.0 * (double)((r * (size_t)freq16[pos]) % L) / (double)L, &sn, &cs);
+    twP[i] = make_double2(cs, sn);
+}
+
+__global__ void sf_gather_weights_kernel(const double2 *__restrict__ w, const int *__restrict__ perm, size_t len,
+                                         double2 *__restrict__ w2) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < len) w2[i] = w[perm[i]];
 }
 
 // P[i] += sum_g Ppart[g][i]
@@ -467,6 +969,15 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
     p->N = (size_t)1 << log2N;
     p->R = (int)((need + p->N - 1) / p->N);
     if (p->R > 4096) return 1;  // NF > ~8e6 frames
+    // any L >= 2NF-1 yields the same correlation: between 17 and 32 round R up to a value the two-stage combine kernel
+    // of the split path is instantiated for (at most 2 more sub-transforms)
+    if (p->R > 16 && p->R <= 32 && !getenv("SASSENA_SELF_EXACT_R")) {
+        for (const SplitFactor &sf : kSplitFactors)
+            if (sf.R >= p->R) {
+                p->R = sf.R;
+                break;
+            }
+    }
     p->L = (size_t)p->R * p->N;
     if (cudaMalloc(&p->d_tw, sizeof(double2) * p->N) != cudaSuccess) return 2;
     if (cudaMalloc(&p->d_w, sizeof(double2) * p->L) != cudaSuccess) return 2;
@@ -481,8 +992,53 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
     cudaFuncSetAttribute(sf_inv_residue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     launch_fused<GEN_WEIGHTS>(log2N, dim3(p->R, 1), st, nullptr, nullptr, nullptr, (int)NF, 1, 0, 1, p->R, p->d_tw, nullptr,
                               nullptr, nullptr, p->d_w);
-    cudaStreamSynchronize(st);
     if (launches) *launches += 2;
+    // split path tables (R >= 3; SASSENA_SELF_PATH=fused|split overrides for experiments)
+    p->split = p->R >= 3 && p->R <= 64;
+    if (const char *e = getenv("SASSENA_SELF_PATH")) {
+        if (!strcmp(e, "fused")) p->split = false;
+        if (!strcmp(e, "split") && p->R >= 2 && p->R <= 64) p->split = true;
+    }
+    if (p->split) {
+        const bool generic = getenv("SASSENA_SELF_GENERIC_COMBINE") != nullptr;
+        p->reg_combine = p->R <= 16 && !generic;
+        p->two_stage = false;
+        for (const SplitFactor &sf : kSplitFactors) p->two_stage = p->two_stage || (sf.R == p->R && !generic);
+        int S = 256;
+        while (!p->reg_combine && !p->two_stage && S > 8 && (size_t)S * p->R > 2048) S >>= 1;
+        if ((size_t)S > p->N) S = (int)p->N;
+        p->S = S;
+        p->C = (int)(p->N / S);
+        if (p->reg_combine || p->two_stage) {
+            std::vector<double2> wr(64, make_double2(0.0, 0.0));
+            for (int k = 0; k < p->R; k++) {
+                // exact quadrant values, libm elsewhere (accurate to 1 ulp)
+                const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)p->R;
+                wr[k] = make_double2(cos(a), sin(a));
+                if ((4 * k) % p->R == 0) {
+                    const int qd = (4 * k) / p->R;  // multiples of a quarter turn
+                    const double cs[4] = {1, 0, -1, 0}, sn[4] = {0, -1, 0, 1};
+                    wr[k] = make_double2(cs[qd & 3], sn[qd & 3]);
+                }
+            }
+            cudaMemcpyToSymbolAsync(c_Wr, wr.data(), sizeof(double2) * 64, 0, cudaMemcpyHostToDevice, st);
+        }
+        if (cudaMalloc(&p->d_w2, sizeof(double2) * p->L) != cudaSuccess) return 2;
+        if (cudaMalloc(&p->d_perm, sizeof(int) * p->L) != cudaSuccess) return 2;
+        std::vector<int> inv(p->N), perm(p->L);
+        for (size_t i = 0; i < p->N; i++) inv[f[i]] = (int)i;  // frequency -> position of the radix-16 order
+        for (int k2 = 0; k2 < p->R; k2++)
+            for (size_t pos = 0; pos < p->N; pos++) {
+                const size_t freq = (size_t)f[pos] + p->N * k2;  // X[k1 + N k2]
+                const size_t j = freq % p->R, k = freq / p->R;   // = X[R k + j] of the residue-major layout
+                perm[(size_t)k2 * p->N + pos] = (int)(j * p->N + inv[k]);
+            }
+        cudaMemcpyAsync(p->d_perm, perm.data(), sizeof(int) * p->L, cudaMemcpyHostToDevice, st);
+        sf_gather_weights_kernel<<<(unsigned)((p->L + 255) / 256), 256, 0, st>>>(p->d_w, p->d_perm, p->L, p->d_w2);
+        cudaStreamSynchronize(st);  // perm[] is a stack buffer
+        if (launches) *launches += 2;
+    }
+    cudaStreamSynchronize(st);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
@@ -490,23 +1046,146 @@ void self_plan_destroy(SelfPlan *p) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_w) cudaFree(p->d_w);
     if (p->d_freq) cudaFree(p->d_freq);
+    if (p->d_twL) cudaFree(p->d_twL);
+    if (p->d_w2) cudaFree(p->d_w2);
+    if (p->d_perm) cudaFree(p->d_perm);
+    p->d_twL = nullptr;
+    p->d_w2 = nullptr;
+    p->d_perm = nullptr;
+    p->split = false;
     p->d_tw = nullptr;
     p->d_w = nullptr;
     p->d_freq = nullptr;
     p->NF = p->L = 0;
 }
 
+namespace {
+constexpr size_t kSplitZBytes = (size_t)1536 << 20;  // batch buffer of twiddled sub-transforms
+
+size_t split_batch(const SelfPlan *p, size_t ntl) {
+    const size_t per_tl = p->L * sizeof(double2);
+    return std::max<size_t>(1, std::min(ntl, kSplitZBytes / per_tl));
+}
+size_t split_groups_b(const SelfPlan *p, size_t tb) {
+    size_t G = (2 * 148 + p->C - 1) / p->C;  // two combine CTAs per SM
+    if (G > tb) G = tb;
+    return std::max<size_t>(G, 1);
+}
+size_t split_smem_b(const SelfPlan *p) {
+    const size_t RS = (size_t)p->R * p->S;
+    return 3 * RS * sizeof(double2) + (RS + (RS & 1)) * sizeof(double) + p->R * sizeof(double2) +
+           2 * (SF_THREADS / 32) * sizeof(double2);
+}
+
+template <int LOG2N>
+void launch_split_fft(size_t G, cudaStream_t st, const float *xyz, const double *b, const double *qs, int NF, int NM, size_t atom0,
+                      size_t tl_first, size_t ntl, const SelfPlan *p, int dec, double2 *Zt) {
+    // FFT buffer + twiddle tables (256 + L/256 and 64 + N/64 entries) + the coordinates of one sub-sequence
+    constexpr size_t N_ = (size_t)1 << LOG2N;
+    const size_t smem = (N_ + N_ / 16 + 256 + (p->L >> 8) + 64 + (N_ >= 64 ? N_ / 64 : 1)) * sizeof(double2) +
+                        (((p->NF / p->R + 1) * 3 * sizeof(float) + 15) & ~(size_t)15);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(self_split_fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        attr = true;  // tables grow with R, the coordinate buffer with NF/R <= N/2; 113 KB lets two CTAs share an SM
+    }
+    self_split_fft_kernel<LOG2N><<<(unsigned)G, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, tl_first, ntl, p->R, dec, Zt);
+}
+}  // namespace
+
 size_t self_work_bytes(const SelfPlan *p, size_t ntl) {
+    if (p->split) {
+        const size_t tb = split_batch(p, ntl);
+        return align256(tb * p->L * sizeof(double2)) + align256(split_groups_b(p, tb) * p->L * sizeof(double)) +
+               align256(ntl * p->C * sizeof(double2)) + align256(ntl * sizeof(double2)) + align256(p->L * sizeof(double2));
+    }
     const size_t G = pick_groups(p, ntl);
     return align256(G * p->L * sizeof(double)) + align256(ntl * p->R * sizeof(double2)) + align256(ntl * sizeof(double2)) +
            align256(p->L * sizeof(double2));
 }
 
+static int self_power_accumulate_split(const SelfPlan *p, const float *d_xyz_by_atom, const double *d_b, const double *d_qs,
+                                       size_t NM, size_t atom0, size_t natoms, void *d_work, double *d_P, double *d_acc,
+                                       int dec, cudaStream_t st) {
+    const size_t ntl = natoms * NM;
+    const size_t tb = split_batch(p, ntl);
+    const size_t GB = split_groups_b(p, tb);
+    char *w = reinterpret_cast<char *>(d_work);
+    double2 *Zt = reinterpret_cast<double2 *>(w);
+    w += align256(tb * p->L * sizeof(double2));
+    double *Ppart2 = reinterpret_cast<double *>(w);
+    w += align256(GB * p->L * sizeof(double));
+    double2 *a_part = reinterpret_cast<double2 *>(w);
+    w += align256(ntl * p->C * sizeof(double2));
+    double2 *a_tl = reinterpret_cast<double2 *>(w);
+    const size_t smem_b = split_smem_b(p);
+    static size_t configured = 0;
+    if (!p->reg_combine && !p->two_stage && smem_b > configured) {
+        cudaFuncSetAttribute(self_split_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        configured = smem_b;
+    }
+    int launches = 0;
+    for (size_t t0 = 0; t0 < ntl; t0 += tb) {
+        const size_t nt = std::min(tb, ntl - t0);
+        const size_t GA = std::min<size_t>(nt, 2 * 148);  // two sub-transform CTAs per SM (128 registers each)
+        switch (p->log2N) {
+            case 8: launch_split_fft<8>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
+            case 9: launch_split_fft<9>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
+            case 10: launch_split_fft<10>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
+            case 11: launch_split_fft<11>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
+            default: launch_split_fft<12>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
+        }
+        const size_t G = split_groups_b(p, nt);
+        if (p->reg_combine) {
+            const dim3 grid((unsigned)p->C, (unsigned)G);
+#define SF_RCASE(RR)                                                                                                   \
+    case RR:                                                                                                           \
+        self_split_combine_reg_kernel<RR><<<grid, SF_THREADS, 0, st>>>(Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part); \
+        break;
+            switch (p->R) {
+                SF_RCASE(2) SF_RCASE(3) SF_RCASE(4) SF_RCASE(5) SF_RCASE(6) SF_RCASE(7) SF_RCASE(8) SF_RCASE(9) SF_RCASE(10)
+                SF_RCASE(11) SF_RCASE(12) SF_RCASE(13) SF_RCASE(14) SF_RCASE(15) SF_RCASE(16)
+                default: break;
+            }
+#undef SF_RCASE
+        } else if (p->two_stage) {
+            const dim3 grid((unsigned)p->C, (unsigned)G);
+#define SF_2CASE(RR, A, B)                                                                     \
+    case RR:                                                                                   \
+        launch_combine_2s<A, B>(grid, st, Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part);     \
+        break;
+            switch (p->R) {
+                SF_2CASE(18, 3, 6) SF_2CASE(20, 4, 5) SF_2CASE(21, 3, 7) SF_2CASE(24, 4, 6) SF_2CASE(25, 5, 5) SF_2CASE(28, 4, 7)
+                SF_2CASE(30, 5, 6) SF_2CASE(32, 4, 8)
+                default: break;
+            }
+#undef SF_2CASE
+        } else {
+            self_split_combine_kernel<<<dim3((unsigned)p->C, (unsigned)G), SF_THREADS, smem_b, st>>>(Zt, (int)p->N, p->R, p->S, nt,
+                                                                                                t0, p->d_w2, Ppart2, a_part);
+        }
+        sf_reduce_ppart_perm_kernel<<<(unsigned)((p->L + 255) / 256), 256, 0, st>>>(Ppart2, G, p->L, p->d_perm, d_P);
+        launches += 3;
+    }
+    const double norm = 1.0 / ((double)p->NF * (double)p->L);
+    sf_reduce_apart_kernel<<<(unsigned)((ntl + 255) / 256), 256, 0, st>>>(a_part, ntl, p->C, norm, a_tl);
+    sf_reduce_atl_kernel<<<1, 1024, 0, st>>>(a_tl, ntl, d_acc);
+    return launches + 2;
+}
+
+int self_decimate_layout(const float *d_src, float *d_dst, size_t natoms, size_t NF, int R, int forward, cudaStream_t st) {
+    const size_t n = natoms * NF;
+    if (n == 0) return 0;
+    sf_decimate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_src, d_dst, natoms, (int)NF, R, forward);
+    return 1;
+}
+
 int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const double *d_b, const double *d_qs,
-                          size_t NM, size_t atom0, size_t natoms, void *d_work, double *d_P, double *d_acc,
+                          size_t NM, size_t atom0, size_t natoms, void *d_work, double *d_P, double *d_acc, int dec,
                           cudaStream_t st) {
     const size_t ntl = natoms * NM;
     if (ntl == 0) return 0;
+    if (p->split) return self_power_accumulate_split(p, d_xyz_by_atom, d_b, d_qs, NM, atom0, natoms, d_work, d_P, d_acc, dec, st);
     const size_t G = pick_groups(p, ntl);
     char *w = reinterpret_cast<char *>(d_work);
     double *Ppart = reinterpret_cast<double *>(w);

@@ -67,6 +67,8 @@ struct sgpu_ctx {
     size_t A_cap = 0;  // entries
     size_t A_NM = 0;   // timelines held by the last all/mpsphere compute
     void *d_work = nullptr;
+    int atoms_dec_R = 0;  // atoms mode: 0 = frames in natural order, R = decimated [r][m] order of the split self path
+    double cyl_axis[3] = {0, 0, 0};  // axis the staged frames were converted to cylindrical coordinates with
     size_t work_cap = 0;
     double *d_partial = nullptr;
     size_t partial_cap = 0;
@@ -194,6 +196,33 @@ int release_xyz(sgpu_ctx *ctx) {
     }
     ctx->mode = 0;
     ctx->rmax_valid = false;
+    ctx->atoms_dec_R = 0;
+    return SGPU_OK;
+}
+
+// Atoms mode, owned buffer: bring the frames of every atom into decimated order for R (R > 0) or back to natural order
+// (R == 0).  Out of place through a bounce buffer, a batch of atoms at a time.  Adopted (caller-owned) buffers stay natural.
+int set_atoms_layout(sgpu_ctx *ctx, int R) {
+    if (ctx->mode != 2 || ctx->atoms_dec_R == R) return SGPU_OK;
+    if (!ctx->own_xyz) return SGPU_OK;
+    const size_t row = ctx->NF * 3 * sizeof(float);
+    const size_t batch = std::max<size_t>(1, std::min(ctx->NA, ((size_t)256 << 20) / row));
+    int rc = ensure<float>(ctx, &ctx->d_stage_tmp, &ctx->stage_tmp_cap, batch * ctx->NF * 3);
+    if (rc) return rc;
+    for (int pass = 0; pass < 2; pass++) {
+        const int cur = (pass == 0) ? ctx->atoms_dec_R : 0;
+        const int want = (pass == 0) ? 0 : R;  // first back to natural (if decimated for another R), then to R
+        if (cur == want || (pass == 0 && cur == 0) || (pass == 1 && R == 0)) continue;
+        for (size_t a0 = 0; a0 < ctx->NA; a0 += batch) {
+            const size_t na = std::min(batch, ctx->NA - a0);
+            float *rows = ctx->d_xyz + a0 * ctx->NF * 3;
+            CK(cudaMemcpyAsync(ctx->d_stage_tmp, rows, na * row, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->launches += self_decimate_layout(ctx->d_stage_tmp, rows, na, ctx->NF, pass == 0 ? cur : R, pass == 0 ? 0 : 1,
+                                                  ctx->stream);
+        }
+    }
+    CK(cudaGetLastError());
+    ctx->atoms_dec_R = R;
     return SGPU_OK;
 }
 
@@ -459,6 +488,7 @@ int sgpu_frames_to_spherical(sgpu_ctx *ctx) {
     if (!ctx) return SGPU_EINVAL;
     if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: no frames staged");
     if (ctx->repr == SGPU_REPR_SPHERICAL) return SGPU_OK;
+    if (ctx->repr != SGPU_REPR_CARTESIAN) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: staged frames are not cartesian");
     if (!ctx->own_xyz) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: adopted device buffers are read-only");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->copy_stream));
@@ -466,6 +496,53 @@ int sgpu_frames_to_spherical(sgpu_ctx *ctx) {
     ctx->launches += launch_cart_to_spherical(ctx->d_xyz, ctx->NF * ctx->NA, ctx->stream);
     CK(cudaGetLastError());
     ctx->repr = SGPU_REPR_SPHERICAL;
+    return SGPU_OK;
+}
+
+// CartesianVectorBase(axis) (reference src/math/coor3d.cpp:278-298): rows e_r, e_phi, e_z
+static bool vector_base(const double axis[3], double base[9]) {
+    auto len = [](const double *v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    auto cross = [](const double *a, const double *b, double *o) {
+        o[0] = a[1] * b[2] - a[2] * b[1];
+        o[1] = a[2] * b[0] - a[0] * b[2];
+        o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    const double al = len(axis);
+    if (!(al > 0.0)) return false;
+    double ez[3] = {axis[0] / al, axis[1] / al, axis[2] / al};
+    const double ek[3] = {0, 0, 1}, ej[3] = {0, 1, 0};
+    double t[3];
+    cross(ek, ez, t);
+    if (len(t) == 0) cross(ej, ez, t);
+    const double tl = len(t);
+    double er[3] = {t[0] / tl, t[1] / tl, t[2] / tl};
+    double u[3];
+    cross(ez, er, u);
+    const double ul = len(u);
+    for (int c = 0; c < 3; c++) {
+        base[c] = er[c];
+        base[3 + c] = u[c] / ul;
+        base[6 + c] = ez[c];
+    }
+    return true;
+}
+
+int sgpu_frames_to_cylindrical(sgpu_ctx *ctx, const double axis[3]) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!axis) return fail(ctx, SGPU_EINVAL, "sgpu_frames_to_cylindrical: NULL axis");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_cylindrical: no frames staged");
+    if (ctx->repr != SGPU_REPR_CARTESIAN)
+        return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_cylindrical: staged frames are not cartesian");
+    if (!ctx->own_xyz) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_cylindrical: adopted device buffers are read-only");
+    double base[9];
+    if (!vector_base(axis, base)) return fail(ctx, SGPU_EINVAL, "sgpu_frames_to_cylindrical: axis has zero length");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    drop_chunks(ctx);
+    ctx->launches += launch_cart_to_cylindrical(ctx->d_xyz, ctx->NF * ctx->NA, base, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->repr = SGPU_REPR_CYLINDRICAL;
+    for (int i = 0; i < 3; i++) ctx->cyl_axis[i] = axis[i];
     return SGPU_OK;
 }
 
@@ -1009,6 +1086,8 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
     if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
         // fused path: timelines are generated, transformed and reduced inside the SM (selffused.cu)
         const SelfPlan &sp = ctx->splan;
+        rc = set_atoms_layout(ctx, sp.split ? sp.R : 0);  // the split path reads sub-sequences of frames: keep them contiguous
+        if (rc) return rc;
         size_t atoms_per_batch = std::max<size_t>(1, ((size_t)256 << 20) / (NM * (size_t)sp.R * sizeof(double2)));
         atoms_per_batch = std::min(atoms_per_batch, ctx->NA);
         rc = ensure_work(ctx, std::max(self_work_bytes(&sp, atoms_per_batch * NM), corr_work_bytes(&ctx->plan, 1)));
@@ -1018,10 +1097,12 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
         for (size_t n0 = 0; n0 < ctx->NA; n0 += atoms_per_batch) {
             const size_t nn = std::min(atoms_per_batch, ctx->NA - n0);
             ctx->launches += self_power_accumulate(&sp, ctx->d_xyz, ctx->d_b, ctx->d_qs, NM, n0, nn, ctx->d_work, d_partial,
-                                                   d_partial + sp.L, ctx->stream);
+                                                   d_partial + sp.L, ctx->atoms_dec_R == sp.R && sp.split ? 1 : 0, ctx->stream);
             CK(cudaGetLastError());
         }
     } else {
+    rc = set_atoms_layout(ctx, 0);
+    if (rc) return rc;
     // batch atoms so that amplitudes + scratch fit a memory budget
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -1318,6 +1399,108 @@ int sgpu_compute_mpsphere(sgpu_ctx *ctx, double qlen, const long *lm, size_t NM,
     rc = sgpu_compute_mpsphere_partial(ctx, qlen, lm, NM, dsp_type, ctx->d_partial);
     if (rc) return rc;
     const double scale = 1.0 / (4.0 * 3.14159265358979323846);  // multipole_scatter_device.cpp:395
+    return sgpu_finalize(ctx, ctx->d_partial, dsp_type, dsp_method, scale, atfinal, afinal, a2final);
+}
+
+/* ---- multipole cylinder ------------------------------------------------------------------------ */
+
+int sgpu_mpcylinder_amplitudes(sgpu_ctx *ctx, const double q[3], const double axis[3], const long *lm, size_t NM,
+                               size_t atom_first, size_t atom_count, double *d_amp) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (!q || !axis || !lm || !d_amp) return fail(ctx, SGPU_EINVAL, "sgpu_mpcylinder_amplitudes: NULL argument");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: frames are not staged (stage_frames first)");
+    if (ctx->NFt != ctx->NF) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: frame windows are not supported on this path");
+    if (ctx->repr != SGPU_REPR_CYLINDRICAL)
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: staged frames are not in cylindrical representation");
+    if (axis[0] != ctx->cyl_axis[0] || axis[1] != ctx->cyl_axis[1] || axis[2] != ctx->cyl_axis[2])
+        return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: the frames were converted with a different axis");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpcylinder: No moments to compute");
+    if (atom_first + atom_count > ctx->NA) return fail(ctx, SGPU_EINVAL, "sgpu_mpcylinder_amplitudes: atom range out of bounds");
+    if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: scattering factors not set for the staged atoms");
+    // moments: parameters.cpp:1082-1102
+    int nmax = 0;
+    std::vector<int> h_lm(NM * 2);
+    for (size_t i = 0; i < NM; i++) {
+        const long l = lm[2 * i], m = lm[2 * i + 1];
+        if (l < 0) return fail(ctx, SGPU_EINVAL, "Major multipole moment must be >= 0!");
+        if (m < 0 || m > 3) return fail(ctx, SGPU_EINVAL, "Minor multipole moment must be between 0 and 3!");
+        if (l == 0 && m != 0) return fail(ctx, SGPU_EINVAL, "Minor multipole moment must be 0 for Major 0!");
+        const long order = (l == 0) ? 0 : ((m < 2) ? 2 * l : 2 * l - 1);
+        if (order > mpcylinder_max_order()) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpcylinder: Bessel order > 199 not supported");
+        nmax = std::max<int>(nmax, (int)order);
+        h_lm[2 * i] = (int)l;
+        h_lm[2 * i + 1] = (int)m;
+    }
+    int rc = ensure<int>(ctx, &ctx->d_lm, &ctx->lm_cap, NM * 2);
+    if (rc) return rc;
+    rc = small_upload(ctx, ctx->d_lm, h_lm.data(), NM * 2 * sizeof(int));
+    if (rc) return rc;
+    // q in the cylinder basis: CylinderCoor3D(base.project(q)) (multipole_scatter_device.cpp:925-929, coor3d.cpp:113-138)
+    double base[9];
+    if (!vector_base(axis, base)) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpcylinder: axis has zero length");
+    const double px = q[0] * base[0] + q[1] * base[1] + q[2] * base[2];
+    const double py = q[0] * base[3] + q[1] * base[4] + q[2] * base[5];
+    const double pz = q[0] * base[6] + q[1] * base[7] + q[2] * base[8];
+    const double qr = std::sqrt(px * px + py * py);
+    const double PIf = (double)3.14159274101257324f, PI2f = (double)1.57079637050628662f;  // sign() returns float there
+    double qphi = 0.0;
+    if (px != 0.0) {
+        qphi = std::atan(py / px);
+        if (px < 0.0) qphi = ((py < 0.0) ? -PIf : PIf) + qphi;
+    } else if (py != 0.0) {
+        qphi = (py < 0.0) ? -PI2f : PI2f;
+    }
+    if (qphi < 0) qphi = 2 * 3.14159265358979323846 + qphi;
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    drop_chunks(ctx);
+    rc = ensure_work(ctx, mpcylinder_work_doubles(ctx->NF, nmax, std::max<size_t>(atom_count, 1)) * sizeof(double));
+    if (rc) return rc;
+    ctx->launches += launch_mpcylinder(ctx->d_xyz, ctx->d_b, qr, qphi, pz, ctx->d_lm, NM, nmax, reinterpret_cast<double2 *>(d_amp),
+                                       ctx->NF, ctx->NA, atom_first, atom_first + atom_count,
+                                       reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+    CK(cudaGetLastError());
+    return SGPU_OK;
+}
+
+int sgpu_compute_mpcylinder_partial(sgpu_ctx *ctx, const double q[3], const double axis[3], const long *lm, size_t NM,
+                                    int dsp_type, double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: frames are not staged (stage_frames first)");
+    if (NM == 0) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpcylinder: No moments to compute");
+    if (!d_partial) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpcylinder: d_partial is NULL");
+    rc = ensure<double2>(ctx, &ctx->d_A, &ctx->A_cap, NM * ctx->NF);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = sgpu_mpcylinder_amplitudes(ctx, q, axis, lm, NM, 0, ctx->NA, reinterpret_cast<double *>(ctx->d_A));
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->A_NM = NM;
+    rc = sgpu_mpsphere_dsp_partial(ctx, reinterpret_cast<const double *>(ctx->d_A), 1, NM, dsp_type, d_partial);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
+    return SGPU_OK;
+}
+
+int sgpu_compute_mpcylinder(sgpu_ctx *ctx, const double q[3], const double axis[3], const long *lm, size_t NM, int dsp_type,
+                            int dsp_method, double *atfinal, double afinal[2], double a2final[2]) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = check_dsp(ctx, dsp_type, dsp_method);
+    if (rc) return rc;
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, "sgpu_compute_mpcylinder: frames are not staged (stage_frames first)");
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    rc = ensure_internal_partial(ctx, dsp_type);
+    if (rc) return rc;
+    rc = sgpu_compute_mpcylinder_partial(ctx, q, axis, lm, NM, dsp_type, ctx->d_partial);
+    if (rc) return rc;
+    const double scale = 1.0 / (2.0 * 3.14159265358979323846);  // multipole_scatter_device.cpp:866
     return sgpu_finalize(ctx, ctx->d_partial, dsp_type, dsp_method, scale, atfinal, afinal, a2final);
 }
 

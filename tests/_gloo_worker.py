@@ -50,6 +50,11 @@ def main():
         p.set("scattering.average.orientation.type", "multipole")
         p.set("scattering.average.orientation.multipole.moments.type", "resolution")
         p.set("scattering.average.orientation.multipole.moments.resolution", 3).set("scattering.dsp.type", "square")
+    elif case.startswith("cyl"):
+        p.set("scattering.average.orientation.type", "multipole").set("scattering.average.orientation.multipole.type", "cylinder")
+        p.set("scattering.average.orientation.axis.x", 1).set("scattering.average.orientation.axis.z", 1)
+        p.set("scattering.average.orientation.multipole.moments.type", "resolution")
+        p.set("scattering.average.orientation.multipole.moments.resolution", 2)
     if case.endswith("_stream"):  # 12 frames x 12 B = 144 B per atom: waves of 5 atoms (config 5's streamed stager)
         p.set("limits.stage.memory.data", 5 * 144)
     if "_frames" in case:  # the reference's frame decomposition inside the partition (amplitude exchange)

@@ -38,7 +38,8 @@ class OracleBackend:
             all_vectors_dsp_partial=_host.BE_AV_DSP(self._av_dsp),
             compute_all_vectors_scan_partial=_host.BE_AV_SCAN(self._av_scan),
             all_vectors_scan_amplitudes=_host.BE_AV_SCAN_AMPL(self._av_scan_amplitudes),
-            stage_atoms_wave=_host.BE_STAGE_WAVE(self._stage_wave), accumulate=_host.BE_ACCUMULATE(self._accumulate))
+            stage_atoms_wave=_host.BE_STAGE_WAVE(self._stage_wave), accumulate=_host.BE_ACCUMULATE(self._accumulate),
+            frames_to_cylindrical=_host.BE_TO_CYL(self._to_cyl), mpcylinder_amplitudes=_host.BE_CYL_AMPL(self._cyl_amplitudes))
         self._cbs = cbs
         self.vtbl = _host.BackendVtbl(**cbs)
 
@@ -126,6 +127,25 @@ class OracleBackend:
         ctx = self._ctx(c)
         ctx["xyz"] = o.cart_to_spherical(ctx["xyz"])
         ctx["repr"] = 1
+        return 0
+
+    def _to_cyl(self, c, axis):
+        ctx = self._ctx(c)
+        ctx["xyz"] = o.cart_to_cylindrical(ctx["xyz"], [axis[0], axis[1], axis[2]])
+        ctx["repr"] = 2
+        return 0
+
+    def _cyl_amplitudes(self, c, q, axis, lm, NM, a0, na, out):
+        ctx = self._ctx(c)
+        NF = ctx["NF"]
+        mom = np.ctypeslib.as_array(lm, shape=(NM, 2)).copy()
+        A = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(NM, NF, 2))
+        if na == 0:
+            A[:] = 0
+            return 0
+        *_, amp = o.compute_mpcylinder(ctx["xyz"][:, a0:a0 + na], ctx["b"][a0:a0 + na], [q[0], q[1], q[2]],
+                                       [axis[0], axis[1], axis[2]], mom, dsp="plain", return_amplitudes=True)
+        A[:] = amp.view(np.float64).reshape(NM, NF, 2)
         return 0
 
     def _stage_atoms(self, c, xyz, NA, NF):

@@ -162,6 +162,77 @@ def test_self_vectors_frame_counts(gpu_ctx, oracle, NF):
         assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
 
 
+@pytest.mark.parametrize("NF,NA,NM", [(4097, 3, 2), (5000, 7, 5), (6200, 2, 3), (8193, 1, 1), (10000, 5, 40), (12289, 2, 3),
+                                      (33000, 2, 2), (35000, 3, 3), (50000, 2, 3)])
+def test_self_vectors_split_path(gpu_ctx, oracle, NF, NA, NM):
+    """R >= 3 (2NF-1 > 2*4096): the split path -- every frame evaluated once, R decimated sub-FFTs per timeline, an
+    R-point DFT across them, power spectrum permuted back to the residue-major layout -- against the oracle and against
+    the fused kernel (same partial, 1e-12).  NF = 10000 is BASELINE config 2's timeline length (R = 5), NF = 50000 config 5's
+    (R = 25, two-stage 5 x 5 combine); 33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18."""
+    xyz = synth.trajectory(NF, NA, 30.0, 0.1, 17, layout=1)
+    b = synth.factors(NA)
+    q = 1.3 * synth.unit_vectors(NM, 18)
+    gpu_ctx.stage_atoms(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, fq, fq2 = gpu_ctx.compute_self_vectors(q)
+    rfqt, rfq, rfq2 = oracle.compute_self_vectors(xyz, b, q, nthreads=8)
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+    assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
+def test_self_split_layout_roundtrip_and_generic_combine(oracle):
+    """the split path keeps owned atom-major coordinates in decimated frame order; switching to a dsp type that needs
+    the natural order converts back, and again forward.  The generic (any R) combine kernel gives the same result."""
+    import os
+    NF, NA, NM = 9000, 5, 7
+    xyz = synth.trajectory(NF, NA, 30.0, 0.1, 7, layout=1)
+    b = synth.factors(NA)
+    q = 0.8 * synth.unit_vectors(NM, 8)
+    ctx = sassena_b200.ScatterContext(0)
+    ctx.stage_atoms(xyz)
+    ctx.set_factors(b)
+    a1 = ctx.compute_self_vectors(q)
+    s1 = ctx.compute_self_vectors(q, dsp="square")   # natural order again
+    a2 = ctx.compute_self_vectors(q)                 # decimated again
+    ctx.close()
+    ra = oracle.compute_self_vectors(xyz, b, q, nthreads=8)
+    rs = oracle.compute_self_vectors(xyz, b, q, dsp="square", nthreads=8)
+    assert rel_err(a1[0], ra[0]) < TOL and rel_err(s1[0], rs[0]) < TOL and np.array_equal(a1[0], a2[0])
+    os.environ["SASSENA_SELF_GENERIC_COMBINE"] = "1"
+    try:
+        ctx = sassena_b200.ScatterContext(0)
+        ctx.stage_atoms(xyz)
+        ctx.set_factors(b)
+        g = ctx.compute_self_vectors(q)
+        ctx.close()
+    finally:
+        del os.environ["SASSENA_SELF_GENERIC_COMBINE"]
+    assert rel_err(g[0], a1[0]) < 1e-12 and abs(g[2] - a1[2]) <= 1e-12 * abs(a1[2])
+
+
+def test_self_split_equals_fused_kernel(oracle):
+    """the same job through both kernels (SASSENA_SELF_PATH selects at plan creation): packed partials agree to 1e-12"""
+    import os
+    NF, NA, NM = 9000, 6, 12
+    xyz = synth.trajectory(NF, NA, 30.0, 0.1, 5, layout=1)
+    b = synth.factors(NA)
+    q = 0.8 * synth.unit_vectors(NM, 6)
+    res = {}
+    for path in ("fused", "split"):
+        os.environ["SASSENA_SELF_PATH"] = path
+        try:
+            ctx = sassena_b200.ScatterContext(0)
+            ctx.stage_atoms(xyz)
+            ctx.set_factors(b)
+            res[path] = ctx.compute_self_vectors(q)
+            ctx.close()
+        finally:
+            del os.environ["SASSENA_SELF_PATH"]
+    for a, c in zip(res["fused"], res["split"]):
+        assert rel_err(np.atleast_1d(c), np.atleast_1d(a)) < 1e-12
+
+
 def test_self_from_frames_modassignment(gpu_ctx, oracle):
     """frame-major input transposed on the GPU for the atoms of rank r under ModAssignment(NN, r, NA);
     the sum of the per-rank partials equals the single-rank result (self...:199-230 reduce)."""
@@ -593,6 +664,16 @@ def test_host_layer_devices_on_gpu(oracle):
     for r, q in zip(recs, qv[:2]):
         ref = oracle.compute_self_vectors(xyz[:, :40].transpose(1, 0, 2), b[:40], ps.init_subvectors(q), nthreads=4)
         assert rel_err(r["fqt"], ref[0]) < TOL
+    # multipole cylinder (MPCylinderScatterDevice) around a tilted axis
+    pc = host.Params().set("scattering.average.orientation.type", "multipole")
+    pc.set("scattering.average.orientation.multipole.type", "cylinder").set("scattering.average.orientation.axis.y", 1)
+    pc.set("scattering.average.orientation.multipole.moments.type", "resolution")
+    pc.set("scattering.average.orientation.multipole.moments.resolution", 4).create()
+    qc = np.array([[0.3, 0.2, 0.5], [-0.4, 0.0, 0.1]])
+    recs, _, _ = host.run_scatter(pc, xyz, qc, b=b)
+    for r, q in zip(recs, qc):
+        ref = oracle.compute_mpcylinder(oracle.cart_to_cylindrical(xyz, (0, 1, 1)), b, q, (0, 1, 1), pc.moments, nthreads=4)
+        assert rel_err(r["fqt"], ref[0]) < TOL and abs(r["fq"] - ref[1]) < TOL * abs(ref[0][0])
     # multipole sphere
     pm = host.Params().set("scattering.average.orientation.type", "multipole")
     pm.set("scattering.average.orientation.multipole.moments.type", "resolution")
@@ -653,6 +734,68 @@ def test_stage_atoms_wave_and_accumulate(gpu_ctx, oracle):
     gpu_ctx.device_free(d2)
     with pytest.raises(Exception, match="outside the trajectory"):
         gpu_ctx.stage_atoms_wave(frames, 2, 3, 13)  # 2 + 12*3 = 38 >= NA
+
+
+@pytest.mark.parametrize("axis,q,L,NA", [((0, 0, 1), (0.3, -0.4, 0.5), 4, 300), ((1, 1, 0), (-0.7, 0.2, 0.1), 10, 517),
+                                         ((0, 1, 0), (0.0, 0.0, 0.9), 2, 64), ((2, -1, 3), (1.5, 1.0, -2.0), 20, 1000),
+                                         ((0, 0, 1), (-0.05, -0.05, 0.0), 6, 129), ((0, 0, 1), (0.0, 0.9, 0.2), 0, 31)])
+def test_mpcylinder_matches_oracle(gpu_ctx, oracle, axis, q, L, NA):
+    """K6 multipole cylinder: cartesian -> cylindrical conversion on the device (bit-exact with the oracle's float
+    coordinates up to the last ulp of atan), amplitudes of all moments and the full fqt / fq / fq2 against the oracle;
+    Bessel arguments from 0 to ~100 cover both the upward recurrence and the continued-fraction ratios."""
+    NF = 37
+    xyz = synth.trajectory(NF, NA, 60.0, 0.2, 23, offset=-30.0)
+    xyz[0, 0] = 0.0  # an atom at the origin: r = 0, phi = 0
+    xyz[1, 1, :2] = 0.0  # an atom on the z axis
+    b = synth.factors(NA)
+    mom = oracle.moments_cylinder(L)
+    cyl = oracle.cart_to_cylindrical(xyz, axis)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.frames_to_cylindrical(axis)
+    gpu_ctx.set_factors(b)
+    for dsp in ("autocorrelate", "square"):
+        fqt, fq, fq2 = gpu_ctx.compute_mpcylinder(q, axis, mom, dsp=dsp)
+        rfqt, rfq, rfq2 = oracle.compute_mpcylinder(cyl, b, q, axis, mom, dsp=dsp, nthreads=4)
+        assert rel_err(fqt, rfqt) < TOL
+        assert abs(fq - rfq) < TOL * abs(rfqt[0]) and abs(fq2 - rfq2) <= TOL * abs(rfq2)
+    A = gpu_ctx.get_amplitudes(len(mom))
+    *_, RA = oracle.compute_mpcylinder(cyl, b, q, axis, mom, dsp="plain", return_amplitudes=True, nthreads=4)
+    assert np.max(np.abs(A - RA)) < TOL * np.max(np.abs(RA))
+
+
+def test_mpcylinder_atom_sharding_and_errors(gpu_ctx, oracle):
+    """atom ranges sum to the full amplitudes (multi-GPU decomposition of the device); the reference's moment checks"""
+    NA, NF, axis, q = 333, 20, (1.0, 0.0, 1.0), (0.4, 0.3, -0.2)
+    xyz = synth.trajectory(NF, NA, 40.0, 0.2, 29, offset=-20.0)
+    b = synth.factors(NA)
+    mom = oracle.moments_cylinder(5)
+    gpu_ctx.stage_frames(xyz)
+    with pytest.raises(Exception, match="cylindrical representation"):
+        gpu_ctx.set_factors(b)
+        gpu_ctx.compute_mpcylinder(q, axis, mom)
+    gpu_ctx.frames_to_cylindrical(axis)
+    gpu_ctx.set_factors(b)
+    n = len(mom) * NF * 2
+    d = [gpu_ctx.device_alloc(n * 8) for _ in range(3)]
+    parts = []
+    for k, (a0, na) in enumerate([(0, 100), (100, 133), (233, 100)]):
+        gpu_ctx.mpcylinder_amplitudes(q, axis, mom, a0, na, d[k])
+        gpu_ctx.synchronize()
+        h = np.empty(n)
+        gpu_ctx.memcpy_d2h(h, d[k])
+        parts.append(h)
+    total = (parts[0] + parts[1] + parts[2]).view(np.complex128).reshape(len(mom), NF)
+    *_, RA = oracle.compute_mpcylinder(oracle.cart_to_cylindrical(xyz, axis), b, q, axis, mom, dsp="plain",
+                                       return_amplitudes=True, nthreads=4)
+    assert np.max(np.abs(total - RA)) < TOL * np.max(np.abs(RA))
+    for p in d:
+        gpu_ctx.device_free(p)
+    with pytest.raises(Exception, match="between 0 and 3"):
+        gpu_ctx.compute_mpcylinder(q, axis, [[1, 4]])
+    with pytest.raises(Exception, match="must be 0 for Major 0"):
+        gpu_ctx.compute_mpcylinder(q, axis, [[0, 2]])
+    with pytest.raises(Exception, match="different axis"):
+        gpu_ctx.compute_mpcylinder(q, (0, 0, 1), mom)
 
 
 @pytest.mark.parametrize("L", [0, 1, 6, 20])

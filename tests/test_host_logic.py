@@ -236,11 +236,20 @@ def test_run_scatter_single_rank_oracle_backend(oracle):
     with pytest.raises(host.HostError) as e:
         host.run_scatter(host.Params(), xyz, np.zeros((0, 3)), b=b, backend=be.vtbl)
     assert "No qvectors left to compute" in str(e.value)
+    # multipole cylinder around a tilted axis (MPCylinderScatterDevice): 1 + 4*3 moments, result scaled by 1/(2 pi)
     pc = host.Params().set("scattering.average.orientation.type", "multipole")
     pc.set("scattering.average.orientation.multipole.type", "cylinder")
-    pc.set("scattering.average.orientation.multipole.moments.type", "resolution").create()
-    with pytest.raises(host.HostError):
-        host.run_scatter(pc, xyz, qv, b=b, backend=be.vtbl)
+    pc.set("scattering.average.orientation.axis.x", 1).set("scattering.average.orientation.axis.y", 1)
+    pc.set("scattering.average.orientation.axis.z", 0.5)
+    pc.set("scattering.average.orientation.multipole.moments.type", "resolution")
+    pc.set("scattering.average.orientation.multipole.moments.resolution", 3).create()
+    assert len(pc.moments) == 13
+    qc = np.array([[0.3, -0.2, 0.6], [-0.5, 0.1, 0.0]])
+    recs, _, _ = host.run_scatter(pc, xyz, qc, b=b, backend=be.vtbl)
+    for r, q in zip(recs, qc):
+        ref = oracle.compute_mpcylinder(oracle.cart_to_cylindrical(xyz, (1, 1, 0.5)), b, q, (1, 1, 0.5), pc.moments)
+        assert np.allclose(r["fqt"], ref[0], rtol=1e-12, atol=1e-12 * abs(ref[0][0]))
+        assert np.isclose(r["fq"], ref[1]) and np.isclose(r["fq2"], ref[2])
     with pytest.raises(host.HostError) as e:
         host.run_scatter(host.Params().set("limits.stage.memory.data", 100), xyz, qv, b=b, backend=be.vtbl)
     assert "decomposition failed" in str(e.value) or "Insufficient Buffer" in str(e.value)

@@ -52,6 +52,9 @@ def _reference(oracle, case):
             out.append(oracle.compute_all_vectors(xyz, b, ql * synth.unit_vectors(7, 1)))
         elif case.startswith("scan"):
             out.append(oracle.compute_all_vectors(xyz, b, ql * synth.unit_vectors(9, 1)))
+        elif case.startswith("cyl"):
+            out.append(oracle.compute_mpcylinder(oracle.cart_to_cylindrical(xyz, (1, 0, 1)), b, q, (1, 0, 1),
+                                                 oracle.moments_cylinder(2)))
         elif case.startswith("self"):
             out.append(oracle.compute_self_vectors(xyz.transpose(1, 0, 2), b, ql * synth.unit_vectors(3, 1)))
         else:
@@ -61,7 +64,7 @@ def _reference(oracle, case):
 
 @pytest.mark.parametrize("world,case", [(2, "all"), (2, "self"), (2, "mp"), (2, "all_manual1"), (3, "self"),
                                         (3, "all_manual1"), (2, "all_frames"), (3, "all_frames"), (2, "scan"), (2, "scan_frames"),
-                                        (3, "scan_frames"), (2, "self_stream"), (3, "self_stream")])
+                                        (3, "scan_frames"), (2, "self_stream"), (3, "self_stream"), (2, "cyl"), (3, "cyl")])
 def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
     gathered = _run(world, case, tmp_path)
     qv, ref = _reference(oracle, case)

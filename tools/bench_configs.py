@@ -86,7 +86,7 @@ if "C5" in which:
     # all |q|.  Sample: NA_s atoms x all 50k frames x 2 |q| x 200 vectors, budget = a third of the sample -> 3 waves.
     from sassena_b200 import host
     c = synth.CONFIGS["C5"]
-    NA_s, NF, NM, NQ_s = 768, c["NF"], c["NM"], 2
+    NA_s, NF, NM, NQ_s = 6144, c["NF"], c["NM"], 2
     d = ctx.device_alloc(NA_s * NF * 12)
     ctx.synth_trajectory(d, NF, c["NA"], c["box"], c["sigma"], c["seed"], layout=0, NA_out=NA_s)  # frame-major [NF][NA_s][3]
     pin = ctx.pinned((NF, NA_s, 3)); frames = pin.array  # the stager's pinned host buffer
