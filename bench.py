@@ -19,6 +19,11 @@ correlates a DivAssignment block of the timelines, and the packed partials are s
 finalize on every rank ("strong" scaling: total work per step is fixed).  `--shard vectors` selects the alternative with
 replicated coordinates and sharded subvectors.
 
+`--workload C2` measures BASELINE configs[1] (incoherent self scattering, 30k atoms x 10k frames, 20 |q| x 200 vectors)
+at full size: a step is one |q| with its 200 vectors over all atoms (6e6 per-atom timelines: amplitudes + FFT
+autocorrelation in the fused/split self kernels); N GPUs shard the atoms by ModAssignment and all-reduce the packed
+partial (self_vectors_scatter_device.cpp:50,213-221).
+
 `--impl reference` times the CPU oracle (oracle/, the restatement of the reference's loops; the reference
 itself cannot be built in this image) on all host cores on a bounded sample of the same workload.
 """
@@ -61,8 +66,9 @@ def scan_passes(nq, max_b=SCAN_MAX_PASS):
 
 WORKLOADS = {
     # name: (config key in sassena_b200.synth.CONFIGS, description)
-    "C3": "coherent F(q,t): 100k atoms x 10k frames, 50 |q| x 500 sphere vectors (one |q| per step)",
-    "C1": "synthetic 1k-atom box, 100 frames, 10 |q| x 100 sphere vectors, coherent (one |q| per step)",
+    "C3": "coherent F(q,t): 100k atoms x 10k frames, 50 |q| x 500 sphere vectors",
+    "C1": "synthetic 1k-atom box, 100 frames, 10 |q| x 100 sphere vectors, coherent",
+    "C2": "incoherent self F_s(q,t): 30k atoms x 10k frames, 20 |q| x 200 vectors, per-atom FFT correlation (one |q| per step)",
 }
 
 
@@ -194,6 +200,9 @@ def run_ours(args):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
+        from sassena_b200 import synth
+        if synth.CONFIGS[args.workload]["kind"] == "self":
+            return _run_self(args, saved_stdout)
         return _run_ours(args, saved_stdout)
     finally:
         sys.stdout.flush()
@@ -476,6 +485,246 @@ def _run_ours(args, json_fd):
     return 0
 
 
+def mod_assignment_count(NN, rank, N):
+    """ModAssignment (reference src/decomposition/assignment.cpp:82-132): indices rank, rank+NN, ..."""
+    return (N - rank + NN - 1) // NN if rank < N else 0
+
+
+def self_flop_per_timeline(NF):
+    """45 flop per amplitude + one forward 2NF-point FFT per timeline (5 L log2 L); the inverse runs once per
+    |q| on the summed power spectrum and is not counted"""
+    L = 2.0 * NF
+    return FLOP_PER_EVAL * NF + 5.0 * L * np.log2(L)
+
+
+def self_cpu_sample(cfg, cores, target_core_seconds, timelines_per_core_s=70.0):
+    """bounded CPU sample of the self workload: NA_s atoms x NM_s vectors of one |q|, all frames"""
+    scale = 1e4 / cfg["NF"]
+    n = max(cores, int(timelines_per_core_s * scale * cores * target_core_seconds))
+    NM_s = min(cfg["NM"], 16)
+    NA_s = max(cores, (n // NM_s // cores) * cores)
+    return NA_s, NM_s
+
+
+def run_reference_self(args):
+    """--impl reference --workload C2: the oracle's self path (atoms over threads = ModAssignment over ranks)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import oracle as o
+    from sassena_b200 import synth
+    o.build()
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames:
+        cfg["NF"] = args.frames
+    if args.atoms:
+        cfg["NA"] = args.atoms
+    cores = o.max_threads()
+    NA_s, NM_s = self_cpu_sample(cfg, cores, args.cpu_seconds)
+    NF = cfg["NF"]
+    qls = synth.qlengths(*cfg["q"])
+    xa = np.ascontiguousarray(synth.trajectory(NF, NA_s, cfg["box"], cfg["sigma"], cfg["seed"]).transpose(1, 0, 2))
+    b = synth.factors(cfg["NA"])[:NA_s]
+    u = synth.unit_vectors(cfg["NM"], cfg["vseed"])[:NM_s]
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        o.compute_self_vectors(xa, b, qls[i % len(qls)] * u, nthreads=cores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = float(NA_s) * NF * NM_s * len(times) / total
+    sample = (f"{NA_s} of {cfg['NA']} atoms x all {NF} frames x {NM_s} of {cfg['NM']} vectors of one |q| per step (amplitude "
+              f"timelines + FFT autocorrelation + store), {cores} OpenMP threads over atoms")
+    line = {
+        "impl": "reference", "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "NA": cfg["NA"], "NF": NF, "NM": cfg["NM"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def _run_self(args, json_fd):
+    """--workload C2: incoherent self scattering at full size.  A step is one compute() of the runner loop: one |q| with
+    its 200 vectors over ALL atoms (6e6 timelines of 10k frames: amplitudes, FFT autocorrelation, store).  N GPUs: atoms
+    sharded by ModAssignment (self_vectors_scatter_device.cpp:50), one NCCL all-reduce of the packed partial per |q|."""
+    import torch
+    import torch.distributed as dist
+    import sassena_b200
+    from sassena_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames:
+        cfg["NF"] = args.frames
+    if args.atoms:
+        cfg["NA"] = args.atoms
+    NA, NF, NM = cfg["NA"], cfg["NF"], cfg["NM"]
+    qls = synth.qlengths(*cfg["q"])
+    u = synth.unit_vectors(NM, cfg["vseed"])
+    b_all = synth.factors(NA)
+    na_loc = mod_assignment_count(world, rank, NA)
+    b_loc = np.ascontiguousarray(b_all[rank::world])
+
+    ctx = sassena_b200.ScatterContext(local_rank)
+    fp64_peak = ctx.measure_fp64_peak()
+    # this rank's atoms (rank, rank+world, ...), atom-major [na_loc][NF][3], generated on the device (CPU twin in synth.py),
+    # then kept in pinned host memory: the "trajectory on the host" that the end-to-end step stages from
+    gen = torch.empty(na_loc * NF * 3, dtype=torch.float32, device=dev)
+    ctx.synth_trajectory(gen.data_ptr(), NF, NA, cfg["box"], cfg["sigma"], cfg["seed"], layout=1, atom0=rank,
+                         atom_stride=world, NA_out=na_loc)
+    host = ctx.pinned((na_loc, NF, 3), np.float32)
+    ctx.memcpy_d2h(host.array, gen.data_ptr())
+    del gen
+    torch.cuda.empty_cache()
+    ctx.stage_atoms(host.array)  # library-owned buffer: the split path keeps it in its decimated frame order
+    ctx.set_factors(b_loc)
+    plen = ctx.partial_len("autocorrelate")
+    partial = torch.zeros(plen, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def compute_step(i):
+        q = float(qls[i % len(qls)]) * u
+        if world == 1:
+            return ctx.compute_self_vectors(q)
+        ctx.compute_self_vectors_partial(q, partial.data_ptr())
+        ctx.synchronize()
+        dist.all_reduce(partial)  # the three boost::mpi::reduce calls of self_vectors_scatter_device.cpp:213-221
+        torch.cuda.synchronize()
+        return ctx.finalize(partial.data_ptr(), 1.0 / NM)
+
+    for i in range(args.warmup):
+        compute_step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = ctx.launch_count
+    amp_ms = 0.0
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        compute_step(args.warmup + i)
+        amp_ms += ctx.last_amplitude_ms()
+    ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, amp_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, amp_ms_max = float(t[0]), float(t[1])
+    mine = {"rank": rank, "step_ms": ms / args.steps, "kernel_ms": amp_ms / args.steps, "atoms": na_loc,
+            "fp64_peak_tflops": fp64_peak}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    evals_step = float(NA) * NF * NM
+    value = evals_step * args.steps / (ms_max * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(i):
+            ctx.stage_atoms(host.array)  # H2D of this rank's atoms from pinned host memory
+            ctx.set_factors(b_loc)
+            return compute_step(i)
+
+        for i in range(min(args.warmup, 2)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(args.warmup + i)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0])
+        e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
+               "h2d_bytes_per_step": int(na_loc * NF * 12 + na_loc * 8 + NM * 24), "d2h_bytes_per_step": int(NF * 16 + 32),
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "note": "every rank re-stages its atoms from pinned host memory every step (H2D, then the decimated frame "
+                       "order of the split path is rebuilt on the device); fqt/fq/fq2 of the step's |q| read back"}
+
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as o
+        o.build()
+        cores = o.max_threads()
+        NA_s, NM_s = self_cpu_sample(cfg, cores, args.cpu_seconds)
+        ql = qls[len(qls) // 2]
+        xa = np.ascontiguousarray(host.array[:NA_s])
+        t0 = time.perf_counter()
+        rfqt, rfq, rfq2 = o.compute_self_vectors(xa, b_all[:NA_s], ql * u[:NM_s], nthreads=cores)
+        dt = time.perf_counter() - t0
+        sample = (f"{NA_s} of {NA} atoms x all {NF} frames x {NM_s} of {NM} vectors of one |q| (amplitude timelines + FFT "
+                  f"autocorrelation + store), {cores} OpenMP threads over atoms")
+        cpu_baseline = {"value": float(NA_s) * NF * NM_s / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                        "sample": sample, "seconds": dt}
+        ctx.stage_atoms(xa)
+        ctx.set_factors(b_all[:NA_s])
+        fqt, fq, _ = ctx.compute_self_vectors(ql * u[:NM_s])
+        parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
+                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9, "vs": "oracle on the CPU sample"}
+
+    if rank == 0:
+        kern_s = amp_ms_max * 1e-3
+        tl_rank = float(mod_assignment_count(world, 0, NA)) * NM * args.steps
+        achieved = tl_rank * self_flop_per_timeline(NF) / kern_s / 1e12
+        line = {
+            "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NF": NF, "NM_per_q": NM, "NQ": len(qls),
+                       "step": "one |q| (compute() of the runner loop) over all atoms: amplitude timelines, FFT "
+                               "autocorrelation per (atom, vector), store/average",
+                       "parallelism": f"atom shard (ModAssignment) x{world} + all-reduce of the packed partial" if world > 1
+                       else "single GPU",
+                       "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
+            "timelines_per_s": float(NA) * NM * args.steps / (ms_max * 1e-3),
+            "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "kernel": "self_split_fft_kernel + self_split_combine_reg_kernel",
+                         "kernel_share_of_step": amp_ms_max / ms_max,
+                         "algorithmic_flop_per_timeline": self_flop_per_timeline(NF),
+                         "note": "45 flop per amplitude + one forward 2NF-point FFT (5 L log2 L) per timeline (SURVEY 8d); "
+                                 "the kernels transform L = R x 2^k >= 2NF-1 points",
+                         "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry"},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+            "host_wall_ms_per_step": wall_ms / args.steps, "per_rank": per_rank,
+        }
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    host.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -498,6 +747,9 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3) if not args.frames else args.warmup
     if args.impl == "reference":
+        from sassena_b200 import synth
+        if synth.CONFIGS[args.workload]["kind"] == "self":
+            return run_reference_self(args)
         return run_reference(args)
     return run_ours(args)
 

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
 }
 
 // ---- split path ---------------------------------------------------------------------------------------------------
-// The fused kernel above evaluates exp(i q.r) R times per frame (once per residue).  For R >= 3 the transform is split the
+// The fused kernel above evaluates exp(i q.r) R times per frame (once per residue).  For R >= 5 the transform is split the
 // other way round: time index n = R m + r, frequency k = k1 + N k2,
 //     X[k1 + N k2] = sum_r exp(-2 pi i r k2 / R) * ( exp(-2 pi i r k1 / L) * Z_r[k1] ),   Z_r = FFT_N( x[R m + r] )_m
 // so every frame is evaluated ONCE (it belongs to exactly one decimated sequence), the R sub-FFTs of a timeline run back to
@@ -316,6 +316,10 @@ __device__ __forceinline__ int freq16_of_pos(int pos) {
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -357,15 +361,26 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
     const size_t per = (ntl + G - 1) / G;
     const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
     const size_t npairs = (t_end > t_begin) ? (t_end - t_begin) * (size_t)R : 0;
-    auto prefetch = [&](size_t pair) {
+    // The sub-sequence lands at cbuf + mis, mis = its misalignment (in floats) against 16 bytes in global memory, so that
+    // source and destination are congruent and the body moves as 16-byte cp.async; returns mis (0 for the gather).
+    auto prefetch = [&](size_t pair) -> int {
         const size_t t = t_begin + pair / R;
         const int r = (int)(pair % R);
         const size_t atom = atom0 + (tl_first + t) / NM;
         const float *p = xyz + atom * (size_t)NF * 3;
         const int Mr = base + (r < rem ? 1 : 0);
+        int mis = 0;
         if (dec) {
             const float *pr = p + 3 * (size_t)(r * base + min(r, rem));
-            for (int e = threadIdx.x; e < 3 * Mr; e += SF_THREADS) cp_async4(&cbuf[e], &pr[e]);
+            mis = (int)((reinterpret_cast<size_t>(pr) >> 2) & 3);
+            const int n = 3 * Mr;
+            const int head = min((4 - mis) & 3, n);
+            const int nvec = (n - head) >> 2;
+            float *cb = cbuf + mis;
+            for (int e = threadIdx.x; e < nvec; e += SF_THREADS) cp_async16(&cb[head + 4 * e], &pr[head + 4 * e]);
+            if ((int)threadIdx.x < head) cp_async4(&cb[threadIdx.x], &pr[threadIdx.x]);
+            const int et = head + 4 * nvec + (int)threadIdx.x;
+            if (et < n) cp_async4(&cb[et], &pr[et]);
         } else {
             for (int e = threadIdx.x; e < 3 * Mr; e += SF_THREADS) {
                 const int mm = e / 3, c = e - 3 * mm;
@@ -373,9 +388,15 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
             }
         }
         cp_async_commit_group();
+        return mis;
     };
-    if (npairs) prefetch(0);
+    // output position pos = tid + 256 i holds frequency f0(tid) + i * 2^(12 - LOG2N) (freq16_of_pos), so the exponent of the
+    // split twiddle W_L^{r f} advances by a constant per i: one modulo per (thread, pair) instead of one per element
+    static_assert(SF_THREADS == 256 && LOG2N >= 8 && LOG2N <= 12, "incremental twiddle exponent assumes 256 threads, N = 256..4096");
+    const int f0 = freq16_of_pos<LOG2N>(threadIdx.x);
+    int mis_next = npairs ? prefetch(0) : 0;
     for (size_t pair = 0; pair < npairs; pair++) {
+        const float *cb = cbuf + mis_next;
         const size_t t = t_begin + pair / R;
         const int r = (int)(pair % R);
         const size_t tl = tl_first + t;
@@ -389,7 +410,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
         for (int mm = threadIdx.x; mm < N; mm += SF_THREADS) {
             double2 v = make_double2(0.0, 0.0);
             if (mm < Mr) {
-                const double x = (double)cbuf[3 * mm], y = (double)cbuf[3 * mm + 1], z = (double)cbuf[3 * mm + 2];
+                const double x = (double)cb[3 * mm], y = (double)cb[3 * mm + 1], z = (double)cb[3 * mm + 2];
                 const double u = fma(z, qz, fma(y, qy, x * qx));
                 double sn, cs;
                 sincos_qt(u, sn, cs);
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
             s[phys(mm)] = v;
         }
         __syncthreads();  // cbuf consumed
-        if (pair + 1 < npairs) prefetch(pair + 1);  // lands while the transform below runs
+        if (pair + 1 < npairs) mis_next = prefetch(pair + 1);  // lands while the transform below runs
         fft_pass<LOG2N, LOG2N, 16, -1>(s, twN);
         fft_pass<LOG2N, LOG2N - 4, 16, -1>(s, twN);
         if (LOG2N == 9) fft_pass<LOG2N, 1, 2, -1>(s, twN);
@@ -406,11 +427,14 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
         if (LOG2N == 11) fft_pass<LOG2N, 3, 8, -1>(s, twN);
         if (LOG2N == 12) fft_pass<LOG2N, 4, 16, -1>(s, twN);
         double2 *out = Zt + ((t * R + r) << LOG2N);
+        int th = (int)(((long long)r * f0) % L);
+        const int dth = (r << (12 - LOG2N)) % L;
 #pragma unroll 4
         for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) {
-            const int th = (r * freq16_of_pos<LOG2N>(pos)) % L;
             const double2 w = cmul2(Thi[th >> 8], Tlo[th & 255]);
             out[pos] = cmul2(s[phys(pos)], w);
+            th += dth;
+            if (th >= L) th -= L;
         }
     }
 }
@@ -431,10 +455,6 @@ __global__ void sf_decimate_kernel(const float *__restrict__ src, float *__restr
     dst[3 * to + 2] = src[3 * from + 2];
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -631,6 +651,99 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_reg_kernel(cons
     for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2];
 }
 
+// Ring version of the register kernel for R <= 8: the inputs of the next D-1 timelines are in flight as 16-byte cp.async
+// into a shared-memory ring of thread-private columns [stage][r][tid] (a thread reads only what it copied itself, so the
+// ring needs no barrier); 3x the bytes in flight of the register prefetch above -- the kernel is HBM-latency bound.
+template <int R>
+__global__ void __launch_bounds__(SF_THREADS) self_split_combine_ring_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
+                                                                             size_t tl_first,
+                                                                             const double2 *__restrict__ What2,
+                                                                             double *__restrict__ Ppart2,
+                                                                             double2 *__restrict__ a_part) {
+    constexpr int D = (R <= 6) ? 4 : 3;
+    constexpr int SLOTS = 8;
+    extern __shared__ double2 ring[];  // [D][R][SF_THREADS]
+    __shared__ double2 red[SLOTS][SF_THREADS / 32];
+    const int c = blockIdx.x, C = gridDim.x;
+    const size_t g = blockIdx.y, G = gridDim.y;
+    const int tid = threadIdx.x;
+    const int pos = c * SF_THREADS + tid;
+    double acc[R];
+    double2 wh[R];
+#pragma unroll
+    for (int k2 = 0; k2 < R; k2++) {
+        acc[k2] = 0.0;
+        wh[k2] = __ldg(&What2[(size_t)k2 * N + pos]);
+    }
+    const size_t per = (ntl + G - 1) / G;
+    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
+    auto prefetch = [&](size_t t, int stage) {
+        if (t < t_end) {
+#pragma unroll
+            for (int r = 0; r < R; r++) cp_async16(&ring[(stage * R + r) * SF_THREADS + tid], &Zt[(t * R + r) * (size_t)N + pos]);
+        }
+        cp_async_commit();  // (possibly empty) group: keeps the wait count uniform
+    };
+#pragma unroll
+    for (int d = 0; d < D - 1; d++) prefetch(t_begin + d, d);
+    auto flush = [&](size_t t_first, int count) {
+        __syncthreads();
+        if (tid < count) {
+            double2 sum = red[tid][0];
+#pragma unroll
+            for (int w = 1; w < SF_THREADS / 32; w++) {
+                sum.x += red[tid][w].x;
+                sum.y += red[tid][w].y;
+            }
+            a_part[(tl_first + t_first + tid) * C + c] = sum;
+        }
+        __syncthreads();
+    };
+    int slot = 0, stage = 0;
+    for (size_t t = t_begin; t < t_end; t++) {
+        // stage (stage + D - 1) % D was consumed in the previous iteration (its values went through the arithmetic below)
+        prefetch(t + D - 1, stage == 0 ? D - 1 : stage - 1);
+        cp_async_wait<D - 1>();  // the group of timeline t is complete
+        double2 z[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) z[r] = ring[(stage * R + r) * SF_THREADS + tid];
+        stage = (stage + 1 == D) ? 0 : stage + 1;
+        double2 ap = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k2 = 0; k2 < R; k2++) {
+            double xr = z[0].x, xi = z[0].y;
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                const int idx = (r * k2) % R;
+                if (idx == 0) {
+                    xr += z[r].x;
+                    xi += z[r].y;
+                } else {
+                    xr = fma(z[r].x, c_Wr[idx].x, fma(-z[r].y, c_Wr[idx].y, xr));
+                    xi = fma(z[r].x, c_Wr[idx].y, fma(z[r].y, c_Wr[idx].x, xi));
+                }
+            }
+            const double pw = fma(xr, xr, xi * xi);
+            acc[k2] += pw;
+            ap.x = fma(pw, wh[k2].x, ap.x);
+            ap.y = fma(pw, wh[k2].y, ap.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ap.x += __shfl_xor_sync(0xffffffffu, ap.x, o);
+            ap.y += __shfl_xor_sync(0xffffffffu, ap.y, o);
+        }
+        if ((tid & 31) == 0) red[slot][tid >> 5] = ap;
+        if (++slot == SLOTS) {
+            flush(t + 1 - SLOTS, SLOTS);
+            slot = 0;
+        }
+    }
+    if (slot) flush(t_end - slot, slot);
+#pragma unroll
+    for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2];
+}
+
 // Two-stage version for composite R = R1*R2 (17..64): r = R2 a + b, k2 = c + R1 d,
 //     X[c + R1 d] = sum_b w_R2^{b d} ( w_R^{b c} sum_a z[R2 a + b] w_R1^{a c} )
 // in place in the thread's R registers (R1^2 R2 + R1 R2^2 complex multiply-adds instead of R^2).  The power accumulators and
@@ -739,16 +852,53 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_2s_kernel(const
     for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2 * SF_THREADS + tid];
 }
 
+// Timeline groups (grid.y) of a combine kernel with C position slices: as many CTAs as are resident at once, rounded DOWN
+// to whole groups -- a few CTAs more than one wave would double (or, at one CTA per SM, add half to) the kernel's duration.
+// (The process drives one device; residency is cached per kernel instantiation.)
+template <typename Kernel>
+size_t resident_ctas(Kernel kernel, size_t smem) {
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SF_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return (size_t)per_sm * (size_t)sms;
+}
+inline size_t combine_groups(size_t resident, size_t C, size_t cap) { return std::max<size_t>(1, std::min(resident / C, cap)); }
+
 template <int R1, int R2>
-void launch_combine_2s(dim3 grid, cudaStream_t st, const double2 *Zt, int N, size_t nt, size_t t0, const double2 *w2, double *Ppart2,
-                       double2 *a_part) {
+size_t launch_combine_2s(size_t C, size_t gcap, cudaStream_t st, const double2 *Zt, int N, size_t nt, size_t t0, const double2 *w2,
+                         double *Ppart2, double2 *a_part) {
     constexpr size_t smem = (size_t)R1 * R2 * SF_THREADS * (sizeof(double2) + sizeof(double));
-    static bool attr = false;
-    if (!attr) {
+    static size_t resident = 0;
+    if (!resident) {
         cudaFuncSetAttribute(self_split_combine_2s_kernel<R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+        resident = resident_ctas(self_split_combine_2s_kernel<R1, R2>, smem);
     }
-    self_split_combine_2s_kernel<R1, R2><<<grid, SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+    const size_t G = combine_groups(resident, C, gcap);
+    self_split_combine_2s_kernel<R1, R2><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+    return G;
+}
+
+// compile-time R <= 16: ring kernel for R <= 8, register-prefetch kernel above that
+template <int R>
+size_t launch_combine_reg(size_t C, size_t gcap, cudaStream_t st, const double2 *Zt, int N, size_t nt, size_t t0, const double2 *w2,
+                          double *Ppart2, double2 *a_part) {
+    static size_t resident = 0;
+    if constexpr (R <= 8) {
+        constexpr size_t smem = (size_t)((R <= 6) ? 4 : 3) * R * SF_THREADS * sizeof(double2);
+        if (!resident) {
+            cudaFuncSetAttribute(self_split_combine_ring_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            resident = resident_ctas(self_split_combine_ring_kernel<R>, smem);
+        }
+        const size_t G = combine_groups(resident, C, gcap);
+        self_split_combine_ring_kernel<R><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+        return G;
+    } else {
+        if (!resident) resident = resident_ctas(self_split_combine_reg_kernel<R>, 0);
+        const size_t G = combine_groups(resident, C, gcap);
+        self_split_combine_reg_kernel<R><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, 0, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+        return G;
+    }
 }
 
 // composite R the two-stage kernel is instantiated for: (R1, R2) with R1 <= R2, both <= 8, R <= 32
@@ -993,8 +1143,10 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
     launch_fused<GEN_WEIGHTS>(log2N, dim3(p->R, 1), st, nullptr, nullptr, nullptr, (int)NF, 1, 0, 1, p->R, p->d_tw, nullptr,
                               nullptr, nullptr, p->d_w);
     if (launches) *launches += 2;
-    // split path tables (R >= 3; SASSENA_SELF_PATH=fused|split overrides for experiments)
-    p->split = p->R >= 3 && p->R <= 64;
+    // split path tables.  Measured (tools/probe_self.py): at R = 4 (NF = 7000) the fused kernel still wins (73 vs 77 ms per
+    // 4.1e5 timelines), from R = 5 on the split path does (NF = 10000: 97 vs 162 ms; R = 25: 325 vs 1177 ms).
+    // SASSENA_SELF_PATH=fused|split overrides for tests and experiments.
+    p->split = p->R >= 5 && p->R <= 64;
     if (const char *e = getenv("SASSENA_SELF_PATH")) {
         if (!strcmp(e, "fused")) p->split = false;
         if (!strcmp(e, "split") && p->R >= 2 && p->R <= 64) p->split = true;
@@ -1083,7 +1235,7 @@ void launch_split_fft(size_t G, cudaStream_t st, const float *xyz, const double 
     // FFT buffer + twiddle tables (256 + L/256 and 64 + N/64 entries) + the coordinates of one sub-sequence
     constexpr size_t N_ = (size_t)1 << LOG2N;
     const size_t smem = (N_ + N_ / 16 + 256 + (p->L >> 8) + 64 + (N_ >= 64 ? N_ / 64 : 1)) * sizeof(double2) +
-                        (((p->NF / p->R + 1) * 3 * sizeof(float) + 15) & ~(size_t)15);
+                        (((p->NF / p->R + 1) * 3 * sizeof(float) + 16 + 15) & ~(size_t)15);  // + the alignment offset
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(self_split_fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
@@ -1135,12 +1287,11 @@ static int self_power_accumulate_split(const SelfPlan *p, const float *d_xyz_by_
             case 11: launch_split_fft<11>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
             default: launch_split_fft<12>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
         }
-        const size_t G = split_groups_b(p, nt);
+        size_t G = split_groups_b(p, nt);  // upper bound (Ppart2 is sized for it); the launchers pick whole waves
         if (p->reg_combine) {
-            const dim3 grid((unsigned)p->C, (unsigned)G);
-#define SF_RCASE(RR)                                                                                                   \
-    case RR:                                                                                                           \
-        self_split_combine_reg_kernel<RR><<<grid, SF_THREADS, 0, st>>>(Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part); \
+#define SF_RCASE(RR)                                                                                        \
+    case RR:                                                                                                \
+        G = launch_combine_reg<RR>(p->C, G, st, Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part);            \
         break;
             switch (p->R) {
                 SF_RCASE(2) SF_RCASE(3) SF_RCASE(4) SF_RCASE(5) SF_RCASE(6) SF_RCASE(7) SF_RCASE(8) SF_RCASE(9) SF_RCASE(10)
@@ -1149,10 +1300,9 @@ static int self_power_accumulate_split(const SelfPlan *p, const float *d_xyz_by_
             }
 #undef SF_RCASE
         } else if (p->two_stage) {
-            const dim3 grid((unsigned)p->C, (unsigned)G);
-#define SF_2CASE(RR, A, B)                                                                     \
-    case RR:                                                                                   \
-        launch_combine_2s<A, B>(grid, st, Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part);     \
+#define SF_2CASE(RR, A, B)                                                                                  \
+    case RR:                                                                                                \
+        G = launch_combine_2s<A, B>(p->C, G, st, Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part);           \
         break;
             switch (p->R) {
                 SF_2CASE(18, 3, 6) SF_2CASE(20, 4, 5) SF_2CASE(21, 3, 7) SF_2CASE(24, 4, 6) SF_2CASE(25, 5, 5) SF_2CASE(28, 4, 7)

@@ -1,0 +1,51 @@
+"""bench.py contract on the CPU: the reference arm (`--impl reference`, the oracle port on the host cores) prints exactly
+one JSON line with the keys the driver reads, for the coherent and the self workload; helper arithmetic matches the
+host layer's decomposition."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+KEYS = ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches")
+
+
+@pytest.mark.parametrize("workload", ["C3", "C2"])
+def test_reference_arm_prints_one_json_line(workload):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
+                          "--frames", "64", "--atoms", "300", "--steps", "2", "--warmup", "1", "--cpu-seconds", "0.02"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in KEYS:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "evals/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_partition_helpers_match_host_layer():
+    import bench
+    from sassena_b200 import host
+    for NN, N in ((1, 7), (2, 7), (3, 10), (8, 30000), (8, 5)):
+        for r in range(NN):
+            assert bench.div_assignment(NN, r, N) == host.div_assignment(NN, r, N)[:2]
+            assert bench.mod_assignment_count(NN, r, N) == host.mod_assignment(NN, r, N)[1]
+    # pass sizes of the scan kernel cover the batch
+    for nq in (1, 4, 27, 28, 29, 50, 200):
+        assert sum(bench.scan_passes(nq)) >= nq

@@ -164,21 +164,28 @@ def test_self_vectors_frame_counts(gpu_ctx, oracle, NF):
 
 @pytest.mark.parametrize("NF,NA,NM", [(4097, 3, 2), (5000, 7, 5), (6200, 2, 3), (8193, 1, 1), (10000, 5, 40), (12289, 2, 3),
                                       (33000, 2, 2), (35000, 3, 3), (50000, 2, 3)])
-def test_self_vectors_split_path(gpu_ctx, oracle, NF, NA, NM):
-    """R >= 3 (2NF-1 > 2*4096): the split path -- every frame evaluated once, R decimated sub-FFTs per timeline, an
-    R-point DFT across them, power spectrum permuted back to the residue-major layout -- against the oracle and against
-    the fused kernel (same partial, 1e-12).  NF = 10000 is BASELINE config 2's timeline length (R = 5), NF = 50000 config 5's
-    (R = 25, two-stage 5 x 5 combine); 33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18."""
+def test_self_vectors_split_path(oracle, monkeypatch, NF, NA, NM):
+    """2NF-1 > 2*4096 (R >= 3): the split path -- every frame evaluated once, R decimated sub-FFTs per timeline, an
+    R-point DFT across them, power spectrum permuted back to the residue-major layout -- against the oracle, forced with
+    SASSENA_SELF_PATH=split (the library picks it from R = 5 on and the fused kernel below; both are checked).
+    NF = 10000 is BASELINE config 2's timeline length (R = 5), NF = 50000 config 5's (R = 25, two-stage 5 x 5 combine);
+    33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18."""
     xyz = synth.trajectory(NF, NA, 30.0, 0.1, 17, layout=1)
     b = synth.factors(NA)
     q = 1.3 * synth.unit_vectors(NM, 18)
-    gpu_ctx.stage_atoms(xyz)
-    gpu_ctx.set_factors(b)
-    fqt, fq, fq2 = gpu_ctx.compute_self_vectors(q)
     rfqt, rfq, rfq2 = oracle.compute_self_vectors(xyz, b, q, nthreads=8)
-    assert rel_err(fqt, rfqt) < TOL
-    assert abs(fq - rfq) < TOL * abs(rfqt[0])
-    assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+    for path in ("split", None):
+        if path:
+            monkeypatch.setenv("SASSENA_SELF_PATH", path)  # read when the plan for this NF is made
+        else:
+            monkeypatch.delenv("SASSENA_SELF_PATH", raising=False)
+        with sassena_b200.ScatterContext(0) as ctx:
+            ctx.stage_atoms(xyz)
+            ctx.set_factors(b)
+            fqt, fq, fq2 = ctx.compute_self_vectors(q)
+        assert rel_err(fqt, rfqt) < TOL
+        assert abs(fq - rfq) < TOL * abs(rfqt[0])
+        assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
 
 
 def test_self_split_layout_roundtrip_and_generic_combine(oracle):
