@@ -1100,7 +1100,9 @@ void launch_fused(int log2N, dim3 grid, cudaStream_t st, const float *xyz, const
 }
 
 size_t pick_groups(const SelfPlan *p, size_t ntl) {
-    size_t G = (2 * 148 + p->R - 1) / p->R;  // two resident CTAs per SM
+    // two resident CTAs per SM (102 KB shared memory, 128 registers); R * G rounded DOWN to one wave: a handful of CTAs
+    // beyond it would run as a second wave and double the kernel's duration (R = 5: 300 CTAs on 296 slots)
+    size_t G = (2 * 148) / p->R;
     if (G > ntl) G = ntl;
     if (G < 1) G = 1;
     if (G > 65535) G = 65535;
