@@ -332,8 +332,55 @@ void Config::read_xml(const std::string &filename) {
             framesets.push_back(f);
         }
     }
-    if (x.exists("//sample/motions/motion") || x.exists("//sample/alignments/alignment"))
-        throw Error("sample.motions / sample.alignments are not supported by the B200 path yet (SURVEY 8f-4)");
+    auto read_reference = [&](SampleReferenceParameters &r) {  // parameters.cpp:269-280,325-335
+        if (!x.exists("./reference")) return;
+        if (x.exists("./reference/type")) r.type = x.get_string("./reference/type");
+        if (x.exists("./reference/frame")) r.frame = x.get_size("./reference/frame");
+        if (x.exists("./reference/file")) {
+            r.file = x.get_string("./reference/file");
+            r.filepath = get_filepath(r.file);
+        }
+        if (x.exists("./reference/format")) r.format = x.get_string("./reference/format");
+        if (x.exists("./reference/selection")) r.selection = x.get_string("./reference/selection");
+    };
+    for (auto *n : x.get("//sample/motions/motion")) {  // parameters.cpp:234-296
+        x.set_current(n);
+        SampleMotionParameters m;
+        m.reference.type = "instant";
+        m.reference.file = structure_file;
+        m.reference.filepath = get_filepath(structure_file);
+        m.reference.format = structure_format;
+        if (x.exists("./type")) m.type = x.get_string("./type");
+        if (x.exists("./displace")) m.displace = x.get_double("./displace");
+        if (x.exists("./frequency")) m.frequency = x.get_double("./frequency");
+        if (x.exists("./seed")) m.seed = (unsigned long)x.get_size("./seed");
+        if (x.exists("./sampling")) m.sampling = x.get_long("./sampling");
+        if (x.exists("./selection")) m.selection = x.get_string("./selection");
+        if (x.exists("./direction/x")) m.direction.x = x.get_double("./direction/x");
+        if (x.exists("./direction/y")) m.direction.y = x.get_double("./direction/y");
+        if (x.exists("./direction/z")) m.direction.z = x.get_double("./direction/z");
+        m.radius = m.displace * 10;
+        if (x.exists("./radius")) m.radius = x.get_double("./radius");
+        // (the reference takes the selection BEFORE ./selection is read as the default reference selection, :253: "system")
+        m.reference.selection = "system";
+        read_reference(m.reference);
+        motions.push_back(m);
+    }
+    for (auto *n : x.get("//sample/alignments/alignment")) {  // parameters.cpp:298-341
+        x.set_current(n);
+        SampleAlignmentParameters a;
+        if (x.exists("./type")) a.type = x.get_string("./type");
+        if (x.exists("./selection")) a.selection = x.get_string("./selection");
+        if (x.exists("./order")) a.order = x.get_string("./order");
+        a.reference.type = "frame";
+        a.reference.frame = 0;
+        a.reference.file = structure_file;
+        a.reference.filepath = get_filepath(structure_file);
+        a.reference.format = structure_format;
+        a.reference.selection = a.selection;
+        read_reference(a.reference);
+        alignments.push_back(a);
+    }
     // ---- stager (parameters.cpp:345-369) ----
     if (x.exists("//stager/target")) stager_target = x.get_string("//stager/target");
     // ---- scattering (parameters.cpp:372-606) ----
@@ -694,27 +741,36 @@ void init_selections(const Config &cfg, Database &db, LoadedSample &s, const std
     if (s.target.empty()) throw Error("No atoms available. Aborting");
 }
 
-void load_frames(const Config &cfg, LoadedSample &s) {
+void load_frames(const Config &cfg, const Database &db, LoadedSample &s) {
     const size_t natoms = s.atom_ids.size();
     const size_t NT = s.target.size();
     s.frames.clear();
     s.NF = 0;
-    std::vector<float> buf(natoms * 3);
+    // Phase 1 — the frame index: global frame number -> (frameset, frame within it), after first/last/stride and clones,
+    // in the order of the configuration (Frames::add_frameset, frames.cpp:75-160).
+    struct Source {
+        std::shared_ptr<void> keep;                       // the open frameset
+        std::function<void(size_t, float *)> read;        // frame `local` of that frameset -> xyz[natoms*3]
+    };
+    struct Entry {
+        size_t source, local;
+    };
+    std::vector<Source> sources;
+    std::vector<Entry> index;
+    auto add_block = [&](Source src, size_t nframes, size_t clones) {
+        sources.push_back(std::move(src));
+        for (size_t c = 0; c < clones; c++)  // CloneFrameset: the same frames again (frames.cpp:61-67,860-872)
+            for (size_t i = 0; i < nframes; i++) index.push_back({sources.size() - 1, i});
+    };
     auto add_dcd = [&](const std::string &path, const SampleFramesetParameters &f, size_t clones) {
-        DCDFrameset fs(path);
-        if (fs.number_of_atoms != natoms)
-            throw Error("Atom number mismatch (dcd) " + std::to_string(fs.number_of_atoms) + " vs. (pdb) " + std::to_string(natoms));
-        fs.trim_index(f.first, f.last, f.last_set, f.stride);
-        const size_t before = s.frames.size();
-        for (size_t i = 0; i < fs.number_of_frames; i++) {
-            fs.read_frame(i, buf.data());
-            for (size_t a = 0; a < NT; a++)
-                for (int c = 0; c < 3; c++) s.frames.push_back(buf[3 * s.target[a] + c]);
-        }
-        const size_t block = s.frames.size() - before;
-        for (size_t c = 1; c < clones; c++)  // CloneFrameset: the same frames again (frames.cpp:61-67,860-872)
-            s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
-        s.NF += fs.number_of_frames * (clones ? clones : 0);
+        auto fs = std::make_shared<DCDFrameset>(path);
+        if (fs->number_of_atoms != natoms)
+            throw Error("Atom number mismatch (dcd) " + std::to_string(fs->number_of_atoms) + " vs. (pdb) " + std::to_string(natoms));
+        fs->trim_index(f.first, f.last, f.last_set, f.stride);
+        Source src;
+        src.keep = fs;
+        src.read = [fs](size_t i, float *xyz) { fs->read_frame(i, xyz); };
+        add_block(std::move(src), fs->number_of_frames, clones);
     };
     // PDBFrameset (frames.cpp:442-577): frames end at lines starting with "END" (END / ENDMDL), a trailing unterminated
     // frame counts, coordinates are columns 31-38 / 39-46 / 47-54 of the ATOM records.  A frame without ATOM records (the
@@ -722,7 +778,7 @@ void load_frames(const Config &cfg, LoadedSample &s) {
     auto add_pdb = [&](const std::string &path, const SampleFramesetParameters &f, size_t clones) {
         std::ifstream in(path.c_str());
         if (in.fail()) throw Error("Couldn't open frameset file: " + path);
-        std::vector<std::vector<float>> frames;
+        std::vector<std::vector<float>> all;
         std::vector<float> cur;
         std::string line;
         auto close_frame = [&]() {
@@ -730,7 +786,7 @@ void load_frames(const Config &cfg, LoadedSample &s) {
                 if (cur.size() != natoms * 3)
                     throw Error("Atom number mismatch (pdb frameset) " + std::to_string(cur.size() / 3) + " vs. (structure) " +
                                 std::to_string(natoms));
-                frames.push_back(cur);
+                all.push_back(cur);
             }
             cur.clear();
         };
@@ -745,34 +801,27 @@ void load_frames(const Config &cfg, LoadedSample &s) {
             }
         }
         close_frame();
-        const size_t before = s.frames.size();
-        size_t kept = 0;
-        for (size_t i = 0; i < frames.size(); i++) {  // FileFrameset::trim_index (frames.cpp:224-245)
+        auto kept = std::make_shared<std::vector<std::vector<float>>>();
+        for (size_t i = 0; i < all.size(); i++) {  // FileFrameset::trim_index (frames.cpp:224-245)
             if (i < f.first || (f.last_set && i > f.last) || (f.stride > 1 && i % f.stride != 0)) continue;
-            for (size_t a = 0; a < NT; a++)
-                for (int c = 0; c < 3; c++) s.frames.push_back(frames[i][3 * s.target[a] + c]);
-            kept++;
+            kept->push_back(std::move(all[i]));
         }
-        const size_t block = s.frames.size() - before;
-        for (size_t c = 1; c < clones; c++) s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
-        s.NF += kept * clones;
+        Source src;
+        src.keep = kept;
+        src.read = [kept](size_t i, float *xyz) { std::copy((*kept)[i].begin(), (*kept)[i].end(), xyz); };
+        add_block(std::move(src), kept->size(), clones);
     };
     // XTCFrameset / TRRFrameset (frames.cpp:592-858).  The reference insists on a pre-built .tnx frame index for these
     // formats (frames.cpp:133-139); the index is rebuilt in memory here, so none is needed.
-    auto add_xdr = [&](XdrFrameset &fs, const char *what, const SampleFramesetParameters &f, size_t clones) {
-        if (fs.number_of_atoms != natoms)
-            throw Error(std::string("Atom number mismatch (") + what + ") " + std::to_string(fs.number_of_atoms) + " vs. (pdb) " +
+    auto add_xdr = [&](std::shared_ptr<XdrFrameset> fs, const char *what, const SampleFramesetParameters &f, size_t clones) {
+        if (fs->number_of_atoms != natoms)
+            throw Error(std::string("Atom number mismatch (") + what + ") " + std::to_string(fs->number_of_atoms) + " vs. (pdb) " +
                         std::to_string(natoms));
-        fs.trim_index(f.first, f.last, f.last_set, f.stride);
-        const size_t before = s.frames.size();
-        for (size_t i = 0; i < fs.number_of_frames; i++) {
-            fs.read_frame(i, buf.data());
-            for (size_t a = 0; a < NT; a++)
-                for (int c = 0; c < 3; c++) s.frames.push_back(buf[3 * s.target[a] + c]);
-        }
-        const size_t block = s.frames.size() - before;
-        for (size_t c = 1; c < clones; c++) s.frames.insert(s.frames.end(), s.frames.begin() + before, s.frames.begin() + before + block);
-        s.NF += fs.number_of_frames * clones;
+        fs->trim_index(f.first, f.last, f.last_set, f.stride);
+        Source src;
+        src.keep = fs;
+        src.read = [fs](size_t i, float *xyz) { fs->read_frame(i, xyz); };
+        add_block(std::move(src), fs->number_of_frames, clones);
     };
     for (auto &f : cfg.framesets) {
         if (f.clones == 0) continue;
@@ -787,11 +836,9 @@ void load_frames(const Config &cfg, LoadedSample &s) {
                 for (size_t c = 0; c < f.clones; c++) add_pdb(cfg.get_filepath(line), f, 1);
             }
         } else if (f.format == "xtc") {
-            XTCFrameset fs(f.filepath);
-            add_xdr(fs, "xtc", f, f.clones);
+            add_xdr(std::make_shared<XTCFrameset>(f.filepath), "xtc", f, f.clones);
         } else if (f.format == "trr") {
-            TRRFrameset fs(f.filepath);
-            add_xdr(fs, "trr", f, f.clones);
+            add_xdr(std::make_shared<TRRFrameset>(f.filepath), "trr", f, f.clones);
         } else if (f.format == "dcd") {
             add_dcd(f.filepath, f, f.clones);
         } else if (f.format == "dcdlist") {
@@ -806,7 +853,28 @@ void load_frames(const Config &cfg, LoadedSample &s) {
             throw Error("frameset format '" + f.format + "' is not supported (dcd, dcdlist, pdb, pdblist, xtc, trr are)");
         }
     }
-    if (s.NF < 1) throw Error("No frames available. Aborting");
+    const size_t NF = index.size();
+    if (NF < 1) throw Error("No frames available. Aborting");
+    auto load_raw = [&](size_t g, float *xyz) { sources[index[g].source].read(index[g].local, xyz); };
+    // Phase 2 — alignments and motions (CoordinateSets::init, coordinate_sets.cpp:58-243): references are read now
+    CoordinateSetsProcessor proc(cfg, db, s, NF, load_raw);
+    // Phase 3 — CoordinateSets::load per frame (coordinate_sets.cpp:245-357) and the stager's narrowing to float
+    std::vector<float> buf(natoms * 3);
+    std::vector<double> work;
+    s.frames.reserve(NF * NT * 3);
+    for (size_t g = 0; g < NF; g++) {
+        load_raw(g, buf.data());
+        if (proc.active()) {
+            work.assign(buf.begin(), buf.end());
+            proc.apply(g, work);
+            for (size_t a = 0; a < NT; a++)
+                for (int c = 0; c < 3; c++) s.frames.push_back((float)work[3 * s.target[a] + c]);
+        } else {
+            for (size_t a = 0; a < NT; a++)
+                for (int c = 0; c < 3; c++) s.frames.push_back(buf[3 * s.target[a] + c]);
+        }
+    }
+    s.NF = NF;
 }
 
 ScatterFactors::ScatterFactors(const Config &cfg, const Database &db, const LoadedSample &s)
@@ -934,7 +1002,7 @@ void Job::load(const std::string &config_file) {
     if (cfg.structure_format != "pdb") throw Error("structure format not supported: " + cfg.structure_format);
     sample.atom_ids = read_pdb_atoms(cfg.structure_filepath, db);
     init_selections(cfg, db, sample, cfg.structure_filepath);
-    load_frames(cfg, sample);
+    load_frames(cfg, db, sample);
     factors.reset(new ScatterFactors(cfg, db, sample));
 }
 

@@ -59,6 +59,29 @@ struct SampleFramesetParameters {
     bool last_set = false;
 };
 
+// reference structure of an alignment / motion (parameters.cpp:248-281,318-336)
+struct SampleReferenceParameters {
+    std::string type = "frame";  // frame | file | instant
+    size_t frame = 0;
+    std::string file, filepath, format = "pdb", selection = "system";
+};
+
+struct SampleMotionParameters {  // parameters.cpp:234-296
+    std::string type = "linear";  // linear | fixed | oscillation | randomwalk | brownian | rotationalbrownian | localbrownian | none
+    double displace = 0.0, frequency = 0.001, radius = 0.0;
+    CartesianCoor3D direction{1, 0, 0};
+    std::string selection = "system";
+    unsigned long seed = 0;
+    long sampling = 1;
+    SampleReferenceParameters reference;  // default type "instant"
+};
+
+struct SampleAlignmentParameters {  // parameters.cpp:298-341
+    std::string type = "center";  // center | fittrans | fitrottrans | fitrot
+    std::string selection = "system", order = "pre";
+    SampleReferenceParameters reference;  // default type "frame", frame 0
+};
+
 struct ScatteringBackgroundKappaParameters {
     std::string selection = "system";
     double value = 1.0;
@@ -70,6 +93,8 @@ struct Config : Params {
     std::string structure_file = "sample.pdb", structure_filepath, structure_format = "pdb";
     std::vector<SampleSelectionParameters> selections;
     std::vector<SampleFramesetParameters> framesets;
+    std::vector<SampleMotionParameters> motions;
+    std::vector<SampleAlignmentParameters> alignments;
     // stager
     std::string stager_target = "system";
     // scattering
@@ -127,8 +152,51 @@ struct LoadedSample {
 std::vector<size_t> read_pdb_atoms(const std::string &filename, Database &db);
 // Sample::init (sample.cpp:30-101): selections + the reserved "system" selection
 void init_selections(const Config &cfg, Database &db, LoadedSample &s, const std::string &structure_path);
-// CoordinateSets: framesets (dcd / dcdlist with first/last/stride/clones) reduced to the target selection
-void load_frames(const Config &cfg, LoadedSample &s);
+// CoordinateSets: framesets (dcd / dcdlist / pdb / pdblist / xtc / trr with first/last/stride/clones), every frame passed
+// through the alignments and motions of the sample section (CoordinateSets::load, coordinate_sets.cpp:245-368), then
+// reduced to the target selection and narrowed to float (data_stager.cpp:111-113)
+void load_frames(const Config &cfg, const Database &db, LoadedSample &s);
+
+// Motion walkers (reference src/sample/motion_walker.cpp): the 4x4 transform of frame `timepos`, applied to row vectors
+// (x, y, z, 1) * T (CartesianCoordinateSet::transform, coordinate_set.cpp:178-215).
+class MotionWalker {
+   public:
+    virtual ~MotionWalker() {}
+    virtual void transform(size_t timepos, double T[16]) = 0;
+    static MotionWalker *create(const SampleMotionParameters &m);  // nullptr for type "none"; throws for unknown types
+};
+
+// CoordinateSets::load between reading a frame and reducing it to the target (coordinate_sets.cpp:245-353): pre-alignments,
+// motions, post-alignments, all in double on the whole system.
+class CoordinateSetsProcessor {
+   public:
+    struct Alignment {
+        std::string type, selection, reference_selection;
+        bool has_reference = false;
+        std::vector<double> ref;  // [n][3] coordinates of the reference selection
+    };
+    struct Motion {
+        std::string selection, reference_selection;
+        bool has_reference = false;
+        std::vector<double> ref;
+        std::unique_ptr<MotionWalker> walker;
+    };
+    // load_raw(framenumber, xyz[natoms*3]) reads the unprocessed frame (reference type "frame")
+    CoordinateSetsProcessor(const Config &cfg, const Database &db, const LoadedSample &s, size_t NF,
+                            const std::function<void(size_t, float *)> &load_raw);
+    bool active() const { return !pre_.empty() || !post_.empty() || !motions_.empty(); }
+    void apply(size_t framenumber, std::vector<double> &xyz) const;  // xyz[natoms*3] in place
+
+   private:
+    const Database &db_;
+    const LoadedSample &s_;
+    std::vector<Alignment> pre_, post_;
+    std::vector<Motion> motions_;
+    const std::vector<size_t> &sel(const std::string &name) const;
+    std::vector<double> reference_set(const SampleReferenceParameters &r, const Config &cfg, size_t NF,
+                                      const std::function<void(size_t, float *)> &load_raw) const;
+    void align(const Alignment &a, std::vector<double> &xyz) const;
+};
 
 // ScatterFactors (scatter_factors.cpp:28-135): b_j(|q|) = sf - background.factor * excl(ID, kappa*V, |q|)
 class ScatterFactors {

@@ -183,40 +183,6 @@ std::vector<CartesianCoor3D> create_from_scans(const std::vector<ScatteringVecto
     return out;
 }
 
-namespace {
-// boost::uniform_on_sphere<double>(dim) over boost::mt19937 with Boost 1.4x's Box-Muller normal_distribution
-// (one cached value, uniform_01 = x / 2^32).  std::mt19937 is the same engine and seeding as boost::mt19937.
-// BEST EFFORT: the stream of later Boost versions differs; parity runs pass explicit vectors.
-struct UniformOnSphere {
-    std::mt19937 rng;
-    int dim;
-    bool valid = false;
-    double r1 = 0, cached_rho = 0;
-    UniformOnSphere(uint32_t seed, int d) : rng(seed), dim(d) {}
-    double normal() {
-        if (!valid) {
-            r1 = rng() / 4294967296.0;
-            double r2 = rng() / 4294967296.0;
-            cached_rho = std::sqrt(-2.0 * std::log(1.0 - r2));
-            valid = true;
-            return cached_rho * std::cos(2 * M_PI * r1);
-        }
-        valid = false;
-        return cached_rho * std::sin(2 * M_PI * r1);
-    }
-    std::vector<double> operator()() {
-        std::vector<double> v(dim);
-        double sq = 0;
-        for (int d = 0; d < dim; d++) {
-            v[d] = normal();
-            sq += v[d] * v[d];
-        }
-        double inv = 1.0 / std::sqrt(sq);
-        for (auto &c : v) c *= inv;
-        return v;
-    }
-};
-}  // namespace
 
 void OrientationVectorsParameters::create() {
     if (type == "file") {

@@ -19,8 +19,10 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <cmath>
 #include <map>
 #include <memory>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -36,6 +38,47 @@ struct Error : std::runtime_error {
 // reference: sassena::terminate_request (include/exceptions/exceptions.hpp:26-29), thrown when ram_check fails
 struct terminate_request : Error {
     terminate_request() : Error("terminate_request: memory limits exceeded") {}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Boost.Random streams the reference draws from (parameters.cpp:948-959,1002-1013; motion_walker.cpp)
+// ---------------------------------------------------------------------------------------------------------------
+// boost::normal_distribution<double> over boost::mt19937 as Boost 1.4x implements it: Box-Muller with one cached value,
+// uniform_01 = x / 2^32.  std::mt19937 is the same engine and seeding as boost::mt19937.
+// BEST EFFORT: the stream of later Boost versions differs; parity runs pass explicit vectors.
+struct BoostNormal {
+    std::mt19937 rng;
+    bool valid = false;
+    double r1 = 0, cached_rho = 0;
+    explicit BoostNormal(uint32_t seed) : rng(seed) {}
+    double operator()() {
+        if (!valid) {
+            r1 = rng() / 4294967296.0;
+            double r2 = rng() / 4294967296.0;
+            cached_rho = std::sqrt(-2.0 * std::log(1.0 - r2));
+            valid = true;
+            return cached_rho * std::cos(2 * M_PI * r1);
+        }
+        valid = false;
+        return cached_rho * std::sin(2 * M_PI * r1);
+    }
+};
+// boost::uniform_on_sphere<double>(dim): dim normal variates, normalised
+struct UniformOnSphere {
+    BoostNormal normal;
+    int dim;
+    UniformOnSphere(uint32_t seed, int d) : normal(seed), dim(d) {}
+    std::vector<double> operator()() {
+        std::vector<double> v(dim);
+        double sq = 0;
+        for (int d = 0; d < dim; d++) {
+            v[d] = normal();
+            sq += v[d] * v[d];
+        }
+        double inv = 1.0 / std::sqrt(sq);
+        for (auto &c : v) c *= inv;
+        return v;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -276,8 +276,8 @@ def test_config_errors(tmp_path):
         host.Job(variant("</root>", "</toor>"))
     with pytest.raises(host.HostError, match="Selection type not understood"):
         host.Job(variant("</framesets>", "</framesets><selections><selection><type>magic</type></selection></selections>"))
-    with pytest.raises(host.HostError, match="not supported"):
-        host.Job(variant("</framesets>", "</framesets><motions><motion><type>linear</type></motion></motions>"))
+    with pytest.raises(host.HostError, match="Motion type not understood"):
+        host.Job(variant("</framesets>", "</framesets><motions><motion><type>wobble</type></motion></motions>"))
     with pytest.raises(host.HostError, match="stager.target"):
         host.Job(variant("<scattering>", "<stager><target>nobody</target></stager><scattering>"))
     with pytest.raises(host.HostError, match="No q vectors"):
