@@ -213,14 +213,17 @@ __global__ void multipole_assemble_kernel(const double2 *__restrict__ part, int 
 // Per tile: geometry (sincos) -> table tasks (Legendre column pairs (m, lmax-m): equal length; Bessel ladders with an
 // x-dependent Miller start) spread over all 512 threads -> product phase on 2 x NP threads.
 constexpr int MG_THREADS = 512;
-constexpr int MG_A = 24;        // atoms per tile
-constexpr int MG_GROUPS = 2;    // thread groups of the product phase, MG_A / MG_GROUPS atoms each
-constexpr int MG_APG = MG_A / MG_GROUPS;
+constexpr int MG_GROUPS = 2;    // thread groups of the product phase, A / MG_GROUPS atoms of a tile each
+constexpr int MG_ROUNDS = 4;    // rounds of table tasks per tile at most (limits the tile size)
+constexpr int MG_A_MAX = 64;    // atoms per tile: chosen per launch (mg_pick_tile) so that the (lmax+1+Q)*A table tasks fill
+                                // whole rounds of the 512 threads (24 atoms at L = 20, Q = 8 left the second round 36 % full)
 
-// one Legendre/azimuth column: sY[a][pair_l(l,m)] = Pbar_lm(theta) (cos m phi, sin m phi), l = m..lmax
-__device__ __forceinline__ void mg_column(int m, int a, int lmax, int NP, double ct, double st, double c1, double s1,
+// one Legendre/azimuth column: col[pair_l(l,m)] = Pbar_lm(theta) (cos m phi, sin m phi), l = m..lmax, col = sY + a*NP.
+// cAB[pair(lmax,m,m) + l - m] = (A_lm, B_lm) of the three-term recurrence; the pair index advances by l per step
+// (pair_l(l,m) = l(l+1)/2 + m), the first two terms are peeled so that the loop body is branch-free.
+__device__ __forceinline__ void mg_column(int m, int lmax, double ct, double st, double c1, double s1,
                                           const double *__restrict__ cK, const double *__restrict__ cM1,
-                                          const double *__restrict__ cA, const double *__restrict__ cB, double2 *sY) {
+                                          const double2 *__restrict__ cAB, double2 *__restrict__ col) {
     // st^m and (c1 + i s1)^m by binary powering (short dependency chain)
     double pw = 1.0, base = st, cm = 1.0, sm = 0.0, rc = c1, rs = s1;
     for (int e = m; e; e >>= 1) {
@@ -236,16 +239,20 @@ __device__ __forceinline__ void mg_column(int m, int a, int lmax, int NP, double
         rc = t;
     }
     const double pmm = cK[m] * pw;
-    double p2 = 0.0, p1 = pmm;
-    const int pbase = mp_pair(lmax, m, m);
-    for (int l = m; l <= lmax; l++) {
-        double pl;
-        if (l == m) pl = pmm;
-        else if (l == m + 1) pl = cM1[m] * ct * pmm;
-        else pl = cA[pbase + l - m] * fma(ct, p1, -cB[pbase + l - m] * p2);
+    int idx = mp_pair_l(m, m);
+    col[idx] = make_double2(pmm * cm, pmm * sm);
+    if (m == lmax) return;
+    double p2 = pmm, p1 = cM1[m] * ct * pmm;
+    idx += m + 1;
+    col[idx] = make_double2(p1 * cm, p1 * sm);
+    const double2 *ab = cAB + (mp_pair(lmax, m, m) - m);  // ab[l]
+    for (int l = m + 2; l <= lmax; l++) {
+        const double2 c = ab[l];
+        const double pl = c.x * fma(ct, p1, -c.y * p2);
         p2 = p1;
         p1 = pl;
-        sY[(size_t)a * NP + mp_pair_l(l, m)] = make_double2(pl * cm, pl * sm);
+        idx += l;
+        col[idx] = make_double2(pl * cm, pl * sm);
     }
 }
 
@@ -253,18 +260,20 @@ template <int Q>
 __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
     const float *__restrict__ sph, const double *__restrict__ b, size_t b_stride, const double *__restrict__ qlens,
     int lmax, int lstart_max, size_t NA, size_t f0, size_t a_first, size_t a_last, size_t atoms_per_split,
-    const double *__restrict__ tab, double2 *__restrict__ part, size_t nf, int q0, int NQ) {
+    const double *__restrict__ tab, double2 *__restrict__ part, size_t nf, int q0, int NQ, int MG_A) {
     extern __shared__ double smem[];
+    const int MG_APG = MG_A / MG_GROUPS;
     const int L1 = lmax + 1;
     const int NP = mp_npairs(lmax);
     double2 *sY = reinterpret_cast<double2 *>(smem);              // [MG_A][NP]
     double *sB = smem + (size_t)2 * MG_A * NP;                    // [MG_A][L1][Q]  (q fastest: one LDS.128 = two |q|)
     const int BS = L1 * Q + 2;                                    // per-atom stride of sB, padded against bank conflicts
     double *sGeo = sB + (size_t)MG_A * BS;                        // [MG_A][5]: r, ct, st, c1, s1
-    double *sTab = sGeo + MG_A * 5;                               // recurrence tables: cM1[L1] cK[L1] cA[NP] cB[NP]
+    double *sTab = sGeo + MG_A * 5;                               // recurrence tables: cM1[L1] cK[L1] (cA, cB)[NP]
     int *sL = reinterpret_cast<int *>(sTab + 2 * L1 + 2 * NP);    // [NP]: l of pair p
     const double *cS = tab + 2 * L1 + 2 * NP;
-    const double *cM1 = sTab, *cK = sTab + L1, *cA = sTab + 2 * L1, *cB = sTab + 2 * L1 + NP;
+    const double *cM1 = sTab, *cK = sTab + L1;
+    const double2 *cAB = reinterpret_cast<const double2 *>(sTab + 2 * L1);  // (A, B) interleaved: one LDS.128 per step
 
     const int tid = threadIdx.x;
     // the Legendre recurrence is a serial chain: keep its coefficient tables in shared memory, not behind global loads
@@ -273,8 +282,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
         sTab[L1 + i] = __ldg(&tab[2 * L1 + 2 * NP + L1 * MP_SERIES_TERMS + i]);
     }
     for (int i = tid; i < NP; i += MG_THREADS) {
-        sTab[2 * L1 + i] = __ldg(&tab[2 * L1 + i]);
-        sTab[2 * L1 + NP + i] = __ldg(&tab[2 * L1 + NP + i]);
+        sTab[2 * L1 + 2 * i] = __ldg(&tab[2 * L1 + i]);
+        sTab[2 * L1 + 2 * i + 1] = __ldg(&tab[2 * L1 + NP + i]);
     }
     const size_t fr = blockIdx.x;
     const int split = blockIdx.y;
@@ -286,6 +295,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
     const int NK = L1;  // one task per Legendre column m; short columns first so that the Bessel tasks that wrap
                         // around to a second round land on threads that finished early
     const int grp = tid >> 8, tp = tid & 255;
+
+    // this thread's table tasks (the same for every tile): id = tid + k*512 -> (atom a, row)
+    int task_a[MG_ROUNDS], task_row[MG_ROUNDS];
+#pragma unroll
+    for (int k = 0; k < MG_ROUNDS; k++) {
+        const int id = tid + k * MG_THREADS;
+        task_row[k] = (id < (NK + Q) * MG_A) ? id / MG_A : -1;
+        task_a[k] = id % MG_A;
+    }
 
     double2 acc[Q];
 #pragma unroll
@@ -312,12 +330,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
         }
         __syncthreads();
         // table tasks: rows [0, NK): Legendre column m = lmax-row of atom a; rows [NK, NK+Q): Bessel ladder (q, a)
-        for (int id = tid; id < (NK + Q) * MG_A; id += MG_THREADS) {
-            const int a = id % MG_A;
-            const int row = id / MG_A;
+#pragma unroll
+        for (int k = 0; k < MG_ROUNDS; k++) {
+            if (task_row[k] < 0) break;
+            const int a = task_a[k], row = task_row[k];
             if (row < NK) {
                 const double ct = sGeo[a * 5 + 1], st = sGeo[a * 5 + 2], c1 = sGeo[a * 5 + 3], s1 = sGeo[a * 5 + 4];
-                mg_column(lmax - row, a, lmax, NP, ct, st, c1, s1, cK, cM1, cA, cB, sY);
+                mg_column(lmax - row, lmax, ct, st, c1, s1, cK, cM1, cAB, sY + (size_t)a * NP);
             } else {
                 const int q = row - NK;
                 const size_t atom = base + a;
@@ -477,13 +496,26 @@ const double *mp_tables(int lmax, cudaStream_t st) {
     return T.d;
 }
 
+// Atom splits per frame: grid = nf x nsplit CTAs, one CTA per SM (512 threads, ~170 KB shared memory).  At least four waves
+// of the 148 SMs when the atoms allow it, and the count whose last wave is fullest (600 CTAs = 4.05 waves ran as 5).
 int mp_nsplit(size_t nf, size_t NA) {
-    size_t want = (600 + nf - 1) / nf;
+    const size_t SMS = 148;
     size_t cap = (NA + 4 * MP_THREADS - 1) / (4 * MP_THREADS);
-    size_t n = want < cap ? want : cap;
-    if (n < 1) n = 1;
-    if (n > 4096) n = 4096;
-    return (int)n;
+    if (cap < 1) cap = 1;
+    if (cap > 4096) cap = 4096;
+    const size_t lo = std::min(cap, (4 * SMS + nf - 1) / nf);       // first count with >= 4 waves (or all the atoms allow)
+    const size_t hi = std::min(cap, std::max(lo, (8 * SMS + nf - 1) / nf));
+    size_t best = lo;
+    double best_eff = 0.0;
+    for (size_t n = lo; n <= hi; n++) {
+        const size_t ctas = nf * n, waves = (ctas + SMS - 1) / SMS;
+        const double eff = (double)ctas / (double)(waves * SMS);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = n;
+        }
+    }
+    return (int)std::max<size_t>(best, 1);
 }
 
 }  // namespace
@@ -538,18 +570,33 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
     if (!tab) return -1;
     const size_t natoms = a_last > a_first ? a_last - a_first : 0;
     const int nsplit = mp_nsplit(nf, std::max<size_t>(natoms, 1));
-    size_t per = (natoms + nsplit - 1) / nsplit;
-    per = ((per + MG_A - 1) / MG_A) * MG_A;
+    const size_t per = (natoms + nsplit - 1) / nsplit;
     const int L1 = lmax + 1, NP = mp_npairs(lmax);
     double2 *part = reinterpret_cast<double2 *>(d_work);
     int launches = 0;
     auto run = [&](auto qtag, int q0) {
         constexpr int Q = decltype(qtag)::value;
-        const size_t smem = ((size_t)2 * MG_A * NP + (size_t)MG_A * (Q * L1 + 2) + MG_A * 5 + 2 * L1 + 2 * NP) * sizeof(double) +
-                            NP * sizeof(int);
+        auto smem_of = [&](int A) {
+            return ((size_t)2 * A * NP + (size_t)A * (Q * L1 + 2) + A * 5 + 2 * L1 + 2 * NP) * sizeof(double) + NP * sizeof(int);
+        };
+        // tile size: the table phase runs (L1 + Q) * A serial-chain tasks on MG_THREADS threads in whole rounds; take the A
+        // (even, shared memory <= 200 KB) that fills its rounds best, the larger one on ties (fewer barriers per atom)
+        int A = 2;
+        double best = 0.0;
+        for (int c = 2; c <= MG_A_MAX; c += MG_GROUPS) {
+            if (smem_of(c) > (size_t)200 * 1024) break;
+            const int tasks = (L1 + Q) * c, rounds = (tasks + MG_THREADS - 1) / MG_THREADS;
+            if (rounds > MG_ROUNDS) break;
+            const double eff = (double)tasks / ((double)rounds * MG_THREADS);
+            if (eff >= best - 1e-12) {
+                best = eff;
+                A = c;
+            }
+        }
+        const size_t per_tiles = ((per + A - 1) / A) * A;  // splits start on tile boundaries
         cudaFuncSetAttribute(multipole_gemm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        multipole_gemm_kernel<Q><<<dim3((unsigned)nf, (unsigned)nsplit), MG_THREADS, smem, st>>>(
-            d_sph, d_b, b_stride, d_qlens, lmax, mp_lstart(lmax), NA, f0, a_first, a_last, per, tab, part, nf, q0, NQ);
+        multipole_gemm_kernel<Q><<<dim3((unsigned)nf, (unsigned)nsplit), MG_THREADS, smem_of(A), st>>>(
+            d_sph, d_b, b_stride, d_qlens, lmax, mp_lstart(lmax), NA, f0, a_first, a_last, per_tiles, tab, part, nf, q0, NQ, A);
         launches++;
     };
     for (int q0 = 0; q0 < NQ;) {
