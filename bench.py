@@ -693,6 +693,13 @@ def _run_self(args, json_fd):
         kern_s = amp_ms_max * 1e-3
         tl_rank = float(mod_assignment_count(world, 0, NA)) * NM * args.steps
         achieved = tl_rank * self_flop_per_timeline(NF) / kern_s / 1e12
+        traffic = None  # DRAM bytes per step of rank 0, from the ncu capture of the two split kernels (per timeline x timelines)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+            if NF == 10000:  # the capture's timeline length
+                traffic = tj["self_split_dram_bytes_per_timeline"] * tl_rank / args.steps
+        except Exception:
+            traffic = None
         line = {
             "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -706,8 +713,8 @@ def _run_self(args, json_fd):
             "timelines_per_s": float(NA) * NM * args.steps / (ms_max * 1e-3),
             "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "self_split_fft_kernel + self_split_combine_reg_kernel",
+                         "frac": achieved / fp64_peak, "traffic": traffic,
+                         "kernel": "self_split_fft_kernel + self_split_combine_ring_kernel",
                          "kernel_share_of_step": amp_ms_max / ms_max,
                          "algorithmic_flop_per_timeline": self_flop_per_timeline(NF),
                          "note": "45 flop per amplitude + one forward 2NF-point FFT (5 L log2 L) per timeline (SURVEY 8d); "
