@@ -132,7 +132,6 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace ptx
 
 template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>

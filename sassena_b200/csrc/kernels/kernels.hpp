@@ -115,7 +115,6 @@ struct SelfPlan {
     bool reg_combine = false;    // R <= 16: the R-point DFT runs in registers (one thread per position)
     bool two_stage = false;      // composite R in 17..32: two-stage DFT in registers
     int S = 0, C = 0;            // positions per combine CTA, number of position slices (C*S = N)
-    double2 *d_twL = nullptr;    // exp(-2 pi i k / L), k < L
     double2 *d_w2 = nullptr;     // weights in the split layout [k2][pos]
     int *d_perm = nullptr;       // split index k2*N + pos -> residue-major index j*N + pos' of the same frequency
 };

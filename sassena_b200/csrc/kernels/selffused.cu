@@ -917,18 +917,6 @@ __global__ void sf_reduce_ppart_perm_kernel(const double *__restrict__ Ppart, si
     P[perm[i]] += sum;
 }
 
-// twP[r*N + pos] = exp(-2 pi i r freq16[pos] / L): the twiddles of the split path in the order the sub-transform leaves
-// its outputs, so that kernel A reads them coalesced
-__global__ void sf_split_twiddle_kernel(double2 *twP, const int *__restrict__ freq16, size_t N, int R) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= N * R) return;
-    const size_t r = i / N, pos = i - r * N;
-    const size_t L = N * R;
-    double sn, cs;
-    sincospi(-2.0 * (double)((r * (size_t)freq16[pos]) % L) / (double)L, &sn, &cs);
-    twP[i] = make_double2(cs, sn);
-}
-
 __global__ void sf_gather_weights_kernel(const double2 *__restrict__ w, const int *__restrict__ perm, size_t len,
                                          double2 *__restrict__ w2) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -1200,10 +1188,8 @@ void self_plan_destroy(SelfPlan *p) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_w) cudaFree(p->d_w);
     if (p->d_freq) cudaFree(p->d_freq);
-    if (p->d_twL) cudaFree(p->d_twL);
     if (p->d_w2) cudaFree(p->d_w2);
     if (p->d_perm) cudaFree(p->d_perm);
-    p->d_twL = nullptr;
     p->d_w2 = nullptr;
     p->d_perm = nullptr;
     p->split = false;
