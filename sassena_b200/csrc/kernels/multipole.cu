@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
     double2 *sY = reinterpret_cast<double2 *>(smem);              // [MG_A][NP]
     double *sB = smem + (size_t)2 * MG_A * NP;                    // [MG_A][L1][Q]  (q fastest: one LDS.128 = two |q|)
     const int BS = L1 * Q + 2;                                    // per-atom stride of sB, padded against bank conflicts
-    double *sGeo = sB + (size_t)MG_A * BS;                        // [MG_A][5]: r, ct, st, c1, s1
-    double *sTab = sGeo + MG_A * 5;                               // recurrence tables: cM1[L1] cK[L1] (cA, cB)[NP]
+    double *sGeo = sB + (size_t)MG_A * BS;                        // [2][MG_A][5]: r, ct, st, c1, s1 (double-buffered)
+    double *sTab = sGeo + 2 * MG_A * 5;                               // recurrence tables: cM1[L1] cK[L1] (cA, cB)[NP]
     int *sL = reinterpret_cast<int *>(sTab + 2 * L1 + 2 * NP);    // [NP]: l of pair p
     const double *cS = tab + 2 * L1 + 2 * NP;
     const double *cM1 = sTab, *cK = sTab + L1;
@@ -309,10 +309,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
 #pragma unroll
     for (int q = 0; q < Q; q++) acc[q] = make_double2(0.0, 0.0);
 
-    for (size_t base = a_begin; base < a_end; base += MG_A) {
-        __syncthreads();  // previous tile fully consumed
-        if (tid < MG_A) {
-            const size_t atom = base + tid;
+    // geometry of a tile (r, cos/sin theta, cos/sin phi per atom) into sGeo[buf], by the threads (gi, gi+ng, ...)
+    auto geometry = [&](size_t base, int buf, int gi, int ng) {
+        double *g = sGeo + (size_t)buf * MG_A * 5;
+        for (int i = gi; i < MG_A; i += ng) {
+            const size_t atom = base + i;
             double r = 0.0, phi = 0.0, theta = 0.0;
             if (atom < a_end) {
                 r = (double)__ldg(&p[3 * atom]);
@@ -322,20 +323,34 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
             double st, ct, s1, c1;
             sincos(theta, &st, &ct);
             sincos(phi, &s1, &c1);
-            sGeo[tid * 5] = r;
-            sGeo[tid * 5 + 1] = ct;
-            sGeo[tid * 5 + 2] = st;
-            sGeo[tid * 5 + 3] = c1;
-            sGeo[tid * 5 + 4] = s1;
+            g[i * 5] = r;
+            g[i * 5 + 1] = ct;
+            g[i * 5 + 2] = st;
+            g[i * 5 + 3] = c1;
+            g[i * 5 + 4] = s1;
         }
-        __syncthreads();
+    };
+    // The product phase leaves 2 * (256 - NP) threads without a pair; they prepare the NEXT tile's geometry meanwhile
+    // (double-buffered sGeo), so the serial sincos step and its barrier drop out of the tile loop.
+    const int n_idle = MG_GROUPS * (256 - NP);
+    const int idle_index = (tp >= NP) ? grp * (256 - NP) + (tp - NP) : -1;
+    int cur = 0;
+    if (a_begin < a_end) geometry(a_begin, 0, tid, MG_THREADS);
+
+    for (size_t base = a_begin; base < a_end; base += MG_A, cur ^= 1) {
+        const double *geo = sGeo + (size_t)cur * MG_A * 5;
+        if (n_idle == 0 && base > a_begin) {  // (no spare threads: lmax with NP = 256 -- not reachable for lmax <= 21)
+            __syncthreads();
+            geometry(base, cur, tid, MG_THREADS);
+        }
+        __syncthreads();  // previous tile fully consumed; this tile's geometry is in place
         // table tasks: rows [0, NK): Legendre column m = lmax-row of atom a; rows [NK, NK+Q): Bessel ladder (q, a)
 #pragma unroll
         for (int k = 0; k < MG_ROUNDS; k++) {
             if (task_row[k] < 0) break;
             const int a = task_a[k], row = task_row[k];
             if (row < NK) {
-                const double ct = sGeo[a * 5 + 1], st = sGeo[a * 5 + 2], c1 = sGeo[a * 5 + 3], s1 = sGeo[a * 5 + 4];
+                const double ct = geo[a * 5 + 1], st = geo[a * 5 + 2], c1 = geo[a * 5 + 3], s1 = geo[a * 5 + 4];
                 mg_column(lmax - row, lmax, ct, st, c1, s1, cK, cM1, cAB, sY + (size_t)a * NP);
             } else {
                 const int q = row - NK;
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
                 double bq = 0.0;
                 if (atom < a_end && q0 + q < NQ) bq = __ldg(&b[(size_t)(q0 + q) * b_stride + atom]);
                 const double ql = (q0 + q < NQ) ? __ldg(&qlens[q0 + q]) : 0.0;
-                const double x = ql * sGeo[a * 5];
+                const double x = ql * geo[a * 5];
                 if (x < 0.05) {
                     // power series, 4 terms are exact to 1e-16 below x = 0.05
                     const double x2 = x * x;
@@ -393,6 +408,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
             }
         }
         __syncthreads();
+        if (idle_index >= 0 && base + MG_A < a_end) geometry(base + MG_A, cur ^ 1, idle_index, n_idle);
         if (tp < NP) {
             const int l = sL[tp];
 #pragma unroll 4
@@ -577,7 +593,7 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
     auto run = [&](auto qtag, int q0) {
         constexpr int Q = decltype(qtag)::value;
         auto smem_of = [&](int A) {
-            return ((size_t)2 * A * NP + (size_t)A * (Q * L1 + 2) + A * 5 + 2 * L1 + 2 * NP) * sizeof(double) + NP * sizeof(int);
+            return ((size_t)2 * A * NP + (size_t)A * (Q * L1 + 2) + 2 * A * 5 + 2 * L1 + 2 * NP) * sizeof(double) + NP * sizeof(int);
         };
         // tile size: the table phase runs (L1 + Q) * A serial-chain tasks on MG_THREADS threads in whole rounds; take the A
         // (even, shared memory <= 200 KB) that fills its rounds best, the larger one on ties (fewer barriers per atom)

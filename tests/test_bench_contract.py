@@ -49,3 +49,24 @@ def test_bench_partition_helpers_match_host_layer():
     # pass sizes of the scan kernel cover the batch
     for nq in (1, 4, 27, 28, 29, 50, 200):
         assert sum(bench.scan_passes(nq)) >= nq
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [["--atoms", "3000", "--frames", "300"],
+                                   ["--atoms", "3000", "--frames", "300", "--mode", "per-q"],
+                                   ["--workload", "C2", "--atoms", "96", "--frames", "9000"]])
+def test_bench_ours_small_sizes_json_line(extra):
+    """the product arm on a reduced workload (debug overrides): one JSON line with roofline, cpu_baseline, e2e, clocks,
+    launches > 0 and parity against the oracle inside the tolerance"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--cpu-seconds", "0.05"]
+                         + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["n_gpus"] == 1
+    assert d["roofline"]["bound"] == "fp64" and 0 < d["roofline"]["frac"] < 1.5 and d["roofline"]["peak"] > 10
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+    assert d["parity"]["fqt_rel_err"] < 1e-9 and d["parity"]["fq_rel_err"] < 1e-9
+    assert "workload" in d["config"]
