@@ -24,6 +24,10 @@ at full size: a step is one |q| with its 200 vectors over all atoms (6e6 per-ato
 autocorrelation in the fused/split self kernels); N GPUs shard the atoms by ModAssignment and all-reduce the packed
 partial (self_vectors_scatter_device.cpp:50,213-221).
 
+`--workload C4` measures BASELINE configs[3] (multipole sphere averaging, 1M atoms x 1k frames x 200 |q|, l <= 20) at full
+size: a step is one pass of the batched multipole kernel (8 |q| x 441 moments over all atoms and frames); N GPUs shard the
+atoms by DivAssignment and all-reduce the amplitudes before the DSP.
+
 `--impl reference` times the CPU oracle (oracle/, the restatement of the reference's loops; the reference
 itself cannot be built in this image) on all host cores on a bounded sample of the same workload.
 """
@@ -69,6 +73,8 @@ WORKLOADS = {
     "C3": "coherent F(q,t): 100k atoms x 10k frames, 50 |q| x 500 sphere vectors",
     "C1": "synthetic 1k-atom box, 100 frames, 10 |q| x 100 sphere vectors, coherent",
     "C2": "incoherent self F_s(q,t): 30k atoms x 10k frames, 20 |q| x 200 vectors, per-atom FFT correlation (one |q| per step)",
+    "C4": "static SAXS via multipole sphere averaging (MPSphereScatterDevice): 1M atoms, 1k frames, 200 |q|, moments l <= 20 "
+          "(one batch of 8 |q| per step)",
 }
 
 
@@ -203,6 +209,8 @@ def run_ours(args):
         from sassena_b200 import synth
         if synth.CONFIGS[args.workload]["kind"] == "self":
             return _run_self(args, saved_stdout)
+        if synth.CONFIGS[args.workload]["kind"] == "mpsphere":
+            return _run_mpsphere(args, saved_stdout)
         return _run_ours(args, saved_stdout)
     finally:
         sys.stdout.flush()
@@ -732,6 +740,243 @@ def _run_self(args, json_fd):
     return 0
 
 
+MP_BATCH = 8  # |q| values per pass of the batched multipole kernel (MPSphereScatterDevice::runner batches them)
+
+
+def mp_flop_per_atom_frame_q(L, nmom, Q=MP_BATCH):
+    """SURVEY 8(d), multipole sphere: per (atom, frame) one Y_lm table (3 flop per (l, m >= 0) pair by recurrence + one
+    sincos, 36 flop, per m) shared by the |q| of a pass; per |q| one j_l ladder (4 flop per l) and one complex MAC (8 flop)
+    per moment"""
+    pairs = (L + 1) * (L + 2) // 2
+    return (3.0 * pairs + 36.0 * (L + 1)) / Q + 4.0 * (L + 1) + 8.0 * nmom
+
+
+def run_reference_mpsphere(args):
+    """--impl reference --workload C4: the oracle's MPSphere path (Boost.Math calls restated) on a bounded sample."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import oracle as o
+    from sassena_b200 import synth
+    o.build()
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames:
+        cfg["NF"] = args.frames
+    if args.atoms:
+        cfg["NA"] = args.atoms
+    cores = o.max_threads()
+    mom = o.moments_sphere(cfg["L"])
+    NF_s = 2
+    NA_s = int(max(64, min(cfg["NA"], 7.8e7 / 16 * cores * args.cpu_seconds / (NF_s * len(mom)))))
+    xyz = synth.trajectory(NF_s, NA_s, cfg["box"], cfg["sigma"], cfg["seed"], offset=cfg["offset"])
+    sph = o.cart_to_spherical(xyz)
+    b = synth.factors(cfg["NA"])[:NA_s]
+    qls = synth.qlengths(*cfg["q"])
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        o.compute_mpsphere(sph, b, qls[(i * 7) % len(qls)], mom, dsp="square", nthreads=cores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = float(NA_s) * NF_s * len(mom) * len(times) / total
+    sample = (f"{NA_s} of {cfg['NA']} atoms x {NF_s} of {cfg['NF']} frames x {len(mom)} moments of one |q| per step (one "
+              f"sph_bessel + spherical_harmonic evaluation per (moment, atom, frame) as the reference does), {cores} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "NA": cfg["NA"], "NF": cfg["NF"], "moments": len(mom),
+                   "unit_of_work": "one (atom, frame, |q|, moment) amplitude term", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def _run_mpsphere(args, json_fd):
+    """--workload C4: multipole sphere averaging at full size.  A step is one pass of the batched multipole kernel: 8 |q|
+    x 441 moments over all atoms and frames (amplitudes A_lm(q, t), dsp, store).  N GPUs: every rank holds the frames of
+    its DivAssignment block of the ATOMS, the amplitudes (sums over atoms) are all-reduced before the DSP."""
+    import torch
+    import torch.distributed as dist
+    import sassena_b200
+    from sassena_b200 import synth
+    from oracle import oracle as o  # moments list only here; the checker runs further down on rank 0
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames:
+        cfg["NF"] = args.frames
+    if args.atoms:
+        cfg["NA"] = args.atoms
+    NA, NF, L = cfg["NA"], cfg["NF"], cfg["L"]
+    mom = np.array([(0, 0)] + [(l, m) for l in range(1, L + 1) for m in range(-l, l + 1)], dtype=np.int64)  # parameters.cpp:1037-1075
+    NM = len(mom)
+    qls = synth.qlengths(*cfg["q"])
+    batches = [qls[i:i + MP_BATCH] for i in range(0, len(qls) - MP_BATCH + 1, MP_BATCH)]
+    a_off, a_cnt = div_assignment(world, rank, NA)
+    b_loc = np.ascontiguousarray(synth.factors(NA)[a_off:a_off + a_cnt])
+
+    ctx = sassena_b200.ScatterContext(local_rank)
+    fp64_peak = ctx.measure_fp64_peak()
+    gen = torch.empty(NF * a_cnt * 3, dtype=torch.float32, device=dev)
+    ctx.synth_trajectory(gen.data_ptr(), NF, NA, cfg["box"], cfg["sigma"], cfg["seed"], layout=0, atom0=a_off, atom_stride=1,
+                         NA_out=a_cnt, offset=cfg["offset"])
+    host = ctx.pinned((NF, a_cnt, 3), np.float32)  # this rank's atoms of every frame, cartesian, pinned
+    ctx.memcpy_d2h(host.array, gen.data_ptr())
+    del gen
+    torch.cuda.empty_cache()
+
+    def stage():
+        ctx.stage_frames(host.array)   # chunked async H2D into the library's buffer
+        ctx.frames_to_spherical()      # SphericalCoordinateSet on the device (coordinate_set.cpp:303-315)
+
+    stage()
+    amp = torch.zeros(MP_BATCH * NM * NF * 2, dtype=torch.float64, device=dev)
+    plen = ctx.partial_len("square")
+    partial = torch.zeros(MP_BATCH * plen, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def compute_step(i):
+        ql = batches[i % len(batches)]
+        ctx.set_factors_batch(np.tile(b_loc, (len(ql), 1)))
+        if world == 1:
+            return ctx.compute_mpsphere_batch(ql, mom, dsp="square")
+        ctx.mpsphere_amplitudes(ql, mom, 0, a_cnt, amp.data_ptr())
+        ctx.synchronize()
+        dist.all_reduce(amp)  # A_lm(q, t) are sums over atoms: complete them before the DSP
+        torch.cuda.synchronize()
+        ctx.mpsphere_dsp_partial(amp.data_ptr(), len(ql), NM, partial.data_ptr(), dsp="square")
+        return [ctx.finalize(partial.data_ptr() + n * plen * 8, 1.0 / (4 * np.pi), dsp="square") for n in range(len(ql))]
+
+    for i in range(args.warmup):
+        compute_step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = ctx.launch_count
+    amp_ms = 0.0
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        compute_step(args.warmup + i)
+        amp_ms += ctx.last_amplitude_ms()
+    ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, amp_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, amp_ms_max = float(t[0]), float(t[1])
+    mine = {"rank": rank, "step_ms": ms / args.steps, "kernel_ms": amp_ms / args.steps, "atoms": a_cnt, "fp64_peak_tflops": fp64_peak}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    evals_step = float(NA) * NF * MP_BATCH * NM
+    value = evals_step * args.steps / (ms_max * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(i):
+            stage()
+            return compute_step(i)
+
+        for i in range(min(args.warmup, 2)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(args.warmup + i)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0])
+        e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
+               "h2d_bytes_per_step": int(NF * a_cnt * 12 + MP_BATCH * a_cnt * 8 + NM * 16),
+               "d2h_bytes_per_step": int(MP_BATCH * (NF * 16 + 32)), "ms_per_step": 1e3 * e2e_s / args.steps,
+               "note": "every rank re-stages its atoms of all frames from pinned host memory every step (chunked async H2D), "
+                       "converts them to (r, phi, theta) on the device, uploads the factors of the 8 |q| and reads fqt/fq/fq2 back"}
+
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        o.build()
+        cores = o.max_threads()
+        NF_s = 2
+        NA_s = int(max(64, min(NA, 7.8e7 / 16 * cores * args.cpu_seconds / (NF_s * NM))))
+        sph = o.cart_to_spherical(np.ascontiguousarray(host.array[:NF_s, :NA_s]))
+        ql = float(qls[len(qls) // 2])
+        t0 = time.perf_counter()
+        rfqt, rfq, rfq2 = o.compute_mpsphere(sph, b_loc[:NA_s], ql, mom, dsp="square", nthreads=cores)
+        dt = time.perf_counter() - t0
+        sample = (f"{NA_s} of {NA} atoms x {NF_s} of {NF} frames x {NM} moments of one |q| (one sph_bessel + spherical_harmonic "
+                  f"evaluation per (moment, atom, frame) as the reference does), {cores} OpenMP threads")
+        cpu_baseline = {"value": float(NA_s) * NF_s * NM / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                        "sample": sample, "seconds": dt}
+        ctx.stage_frames(sph, repr=sassena_b200.REPR_SPHERICAL)
+        ctx.set_factors(b_loc[:NA_s])
+        fqt, fq, _ = ctx.compute_mpsphere(ql, mom, dsp="square")
+        parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
+                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9, "vs": "oracle on the CPU sample"}
+
+    if rank == 0:
+        kern_s = amp_ms_max * 1e-3
+        evals_rank = float(div_assignment(world, 0, NA)[1]) * NF * MP_BATCH * NM * args.steps
+        flop_eval = mp_flop_per_atom_frame_q(L, NM) / NM
+        achieved = evals_rank * flop_eval / kern_s / 1e12
+        line = {
+            "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NF": NF, "NQ": len(qls), "moments": NM,
+                       "unit_of_work": "one (atom, frame, |q|, moment) amplitude term",
+                       "step": f"one pass of {MP_BATCH} |q| x {NM} moments over all atoms and frames: amplitudes, dsp (square), store",
+                       "parallelism": f"atom shard (DivAssignment) x{world} + all-reduce of the amplitudes" if world > 1 else "single GPU",
+                       "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
+            "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * (len(qls) / MP_BATCH),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None, "kernel": "multipole_gemm_kernel<8>",
+                         "kernel_share_of_step": amp_ms_max / ms_max, "algorithmic_flop_per_eval": flop_eval,
+                         "executed_fp64_flop_per_eval": (3.0 * 231 + 36.0 * 21 + MP_BATCH * (4.0 * 21 + 4.0 * 231)) / (MP_BATCH * NM)
+                         if L == 20 else None,
+                         "note": "algorithmic count of SURVEY 8(d): a Y_lm table per (atom, frame) shared by the |q| of a pass, a "
+                                 "j_l ladder per |q| and one complex MAC (8 flop) per moment; the kernel evaluates only m >= 0 with "
+                                 "real-times-complex products (4 flop per (l, m >= 0) pair), executed_fp64_flop_per_eval states that count",
+                         "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry"},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+            "host_wall_ms_per_step": wall_ms / args.steps, "per_rank": per_rank,
+        }
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    host.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -757,6 +1002,8 @@ def main():
         from sassena_b200 import synth
         if synth.CONFIGS[args.workload]["kind"] == "self":
             return run_reference_self(args)
+        if synth.CONFIGS[args.workload]["kind"] == "mpsphere":
+            return run_reference_mpsphere(args)
         return run_reference(args)
     return run_ours(args)
 

@@ -1206,6 +1206,7 @@ int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, cons
     CK(cudaStreamSynchronize(ctx->copy_stream));
     drop_chunks(ctx);
     double2 *A = reinterpret_cast<double2 *>(d_amp);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (lmax <= 21) {
         rc = ensure_work(ctx, multipole_batch_work_doubles(ctx->NF, lmax, std::max<size_t>(atom_count, 1), (int)NQ) * sizeof(double));
         if (rc) return rc;
@@ -1225,6 +1226,10 @@ int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, cons
                                                      reinterpret_cast<double *>(ctx->d_work), ctx->stream);
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));  // sgpu_last_amplitude_ms: the amplitude kernels of this call
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
     return SGPU_OK;
 }
 

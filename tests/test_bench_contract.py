@@ -15,7 +15,7 @@ KEYS = ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_
         "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches")
 
 
-@pytest.mark.parametrize("workload", ["C3", "C2"])
+@pytest.mark.parametrize("workload", ["C3", "C2", "C4"])
 def test_reference_arm_prints_one_json_line(workload):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
                           "--frames", "64", "--atoms", "300", "--steps", "2", "--warmup", "1", "--cpu-seconds", "0.02"],
@@ -54,7 +54,8 @@ def test_bench_partition_helpers_match_host_layer():
 @pytest.mark.gpu
 @pytest.mark.parametrize("extra", [["--atoms", "3000", "--frames", "300"],
                                    ["--atoms", "3000", "--frames", "300", "--mode", "per-q"],
-                                   ["--workload", "C2", "--atoms", "96", "--frames", "9000"]])
+                                   ["--workload", "C2", "--atoms", "96", "--frames", "9000"],
+                                   ["--workload", "C4", "--atoms", "5000", "--frames", "40"]])
 def test_bench_ours_small_sizes_json_line(extra):
     """the product arm on a reduced workload (debug overrides): one JSON line with roofline, cpu_baseline, e2e, clocks,
     launches > 0 and parity against the oracle inside the tolerance"""
