@@ -1461,10 +1461,15 @@ int sgpu_mpcylinder_amplitudes(sgpu_ctx *ctx, const double q[3], const double ax
     drop_chunks(ctx);
     rc = ensure_work(ctx, mpcylinder_work_doubles(ctx->NF, nmax, std::max<size_t>(atom_count, 1)) * sizeof(double));
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
     ctx->launches += launch_mpcylinder(ctx->d_xyz, ctx->d_b, qr, qphi, pz, ctx->d_lm, NM, nmax, reinterpret_cast<double2 *>(d_amp),
                                        ctx->NF, ctx->NA, atom_first, atom_first + atom_count,
                                        reinterpret_cast<double *>(ctx->d_work), ctx->stream);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));  // sgpu_last_amplitude_ms: the amplitude kernels of this call
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
     return SGPU_OK;
 }
 
@@ -1479,10 +1484,8 @@ int sgpu_compute_mpcylinder_partial(sgpu_ctx *ctx, const double q[3], const doub
     if (!d_partial) return fail(ctx, SGPU_EINVAL, "sgpu_compute_mpcylinder: d_partial is NULL");
     rc = ensure<double2>(ctx, &ctx->d_A, &ctx->A_cap, NM * ctx->NF);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    rc = sgpu_mpcylinder_amplitudes(ctx, q, axis, lm, NM, 0, ctx->NA, reinterpret_cast<double *>(ctx->d_A));
+    rc = sgpu_mpcylinder_amplitudes(ctx, q, axis, lm, NM, 0, ctx->NA, reinterpret_cast<double *>(ctx->d_A));  // records ev0, ev1
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->A_NM = NM;
     rc = sgpu_mpsphere_dsp_partial(ctx, reinterpret_cast<const double *>(ctx->d_A), 1, NM, dsp_type, d_partial);
     if (rc) return rc;
