@@ -380,26 +380,40 @@ __global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
                     const double invx = 1.0 / x;
                     const double j0 = sn * invx;
                     const double j1 = (sn * invx - cs) * invx;
+                    // (2l+1)/x advances by 2/x per step: one DADD instead of an int->double conversion and a DMUL
+                    const double step = 2.0 * invx;
                     if (x >= (double)lmax) {
                         double jm = j0, jc = j1;
                         J[0] = bq * j0;
                         if (lmax >= 1) J[Q] = bq * j1;
+                        double t = 3.0 * invx;
                         for (int l = 1; l < lmax; l++) {
-                            const double jn = fma((double)(2 * l + 1) * invx, jc, -jm);
+                            const double jn = fma(t, jc, -jm);
+                            t += step;
                             jm = jc;
                             jc = jn;
                             J[(l + 1) * Q] = bq * jn;
                         }
                     } else {
                         // Miller downward recurrence; the start index needed for 1e-14 grows only slowly with x
-                        // (measured: lmax + 2 .. lmax + 19 for x < lmax), use lmax + 8 + 1.5 x
+                        // (measured: lmax + 2 .. lmax + 19 for x < lmax), use lmax + 8 + 1.5 x.  Two loops: above lmax + 1
+                        // nothing is kept, below every value is.
                         const int lstart = min(lstart_max, lmax + 8 + (int)(1.5 * x));
                         double jp = 0.0, jc = 1e-300;
-                        for (int k = lstart; k >= 1; k--) {
-                            const double jm = fma((double)(2 * k + 1) * invx, jc, -jp);
+                        double t = (double)(2 * lstart + 1) * invx;
+                        int k = lstart;
+                        for (; k > lmax + 1; k--) {
+                            const double jm = fma(t, jc, -jp);
+                            t -= step;
                             jp = jc;
                             jc = jm;
-                            if (k - 1 <= lmax) J[(k - 1) * Q] = jc;
+                        }
+                        for (; k >= 1; k--) {
+                            const double jm = fma(t, jc, -jp);
+                            t -= step;
+                            jp = jc;
+                            jc = jm;
+                            J[(k - 1) * Q] = jc;
                         }
                         const double scale = bq * ((fabs(j0) >= fabs(j1)) ? j0 / jc : j1 / jp);
                         for (int l = 0; l <= lmax; l++) J[l * Q] *= scale;
