@@ -206,11 +206,37 @@ size_t cyl_smem_bytes(int nmax) {
            (size_t)std::max(nslices, 1) * nord * sizeof(double4);
 }
 
-int cyl_splits(size_t NF, size_t natoms) {
-    // enough CTAs for two waves of 148 SMs when there are few frames; never less than one tile per split
-    size_t want = (2 * 148 + NF - 1) / NF;
-    size_t maxs = std::max<size_t>(1, natoms / CY_TILE);
-    return (int)std::max<size_t>(1, std::min(want, maxs));
+// Atom splits per frame: grid = NF x splits CTAs.  Between one and two waves of the CTAs that are resident at once (occupancy
+// query: registers and the nmax-dependent shared memory), the count whose last wave is fullest; never less than one tile per
+// split.  (A fixed 2 x 148 target left the SMs at 0.68 of one wave: three CTAs fit per SM at nmax = 20.)
+int cyl_splits(size_t NF, size_t natoms, int nmax) {
+    static int cached_nmax = -1;
+    static size_t resident = 2 * 148;
+    if (nmax != cached_nmax) {
+        int per_sm = 1, dev = 0, sms = 148;
+        const size_t smem = cyl_smem_bytes(nmax);
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(mpcylinder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpcylinder_kernel, CY_THREADS, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        resident = (size_t)per_sm * (size_t)sms;
+        cached_nmax = nmax;
+    }
+    const size_t maxs = std::max<size_t>(1, natoms / CY_TILE);
+    const size_t lo = std::min(maxs, std::max<size_t>(1, (resident + NF - 1) / NF));
+    const size_t hi = std::min(maxs, std::max(lo, (2 * resident + NF - 1) / NF));
+    size_t best = lo;
+    double best_eff = 0.0;
+    for (size_t n = lo; n <= hi; n++) {
+        const size_t ctas = NF * n, waves = (ctas + resident - 1) / resident;
+        const double eff = (double)ctas / (double)(waves * resident);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = n;
+        }
+    }
+    return (int)best;
 }
 
 }  // namespace
@@ -225,7 +251,7 @@ int launch_cart_to_cylindrical(float *d_xyz, size_t n, const double base[9], cud
 int mpcylinder_max_order() { return 199; }
 
 size_t mpcylinder_work_doubles(size_t NF, int nmax, size_t natoms) {
-    return (size_t)cyl_splits(NF, natoms) * NF * (nmax + 1) * 4;
+    return (size_t)cyl_splits(NF, natoms, nmax) * NF * (nmax + 1) * 4;
 }
 
 int launch_mpcylinder(const float *d_coords, const double *d_b, double qr, double qphi, double qz, const int *d_lm, size_t NM,
@@ -234,7 +260,7 @@ int launch_mpcylinder(const float *d_coords, const double *d_b, double qr, doubl
     if (NF == 0 || NM == 0) return 0;
     const int nord = nmax + 1;
     const size_t natoms = a_last - a_first;
-    const int S = cyl_splits(NF, std::max<size_t>(natoms, 1));
+    const int S = cyl_splits(NF, std::max<size_t>(natoms, 1), nmax);
     const size_t smem = cyl_smem_bytes(nmax);
     static size_t configured = 0;
     if (smem > configured) {

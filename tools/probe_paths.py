@@ -49,6 +49,24 @@ if which in ("all", "mp", "mpbatch"):
         dt = time.time() - t0
     print(f"mpsphere batch of 8 |q|: {dt*1e3:.1f} ms -> {8*NA*NF*len(mom)/dt:.3e} moment-evals/s; cfg4 would take {dt/NF*1000*200/8:.0f} s")
 
+if which in ("all", "mpcyl"):
+    # multipole cylinder (K6) on a config-4 shaped slice: 1M atoms, moments (0,0) + (l, 0..3) for l <= L
+    NA, NF, L = 1000000, int(os.environ.get("MP_NF", 16)), int(os.environ.get("CYL_L", 10))
+    d = ctx.device_alloc(NA * NF * 12)
+    ctx.synth_trajectory(d, NF, NA, 220.0, 0.05, 7, offset=-110.0)
+    h = np.empty((NF, NA, 3), dtype=np.float32); ctx.memcpy_d2h(h, d); ctx.device_free(d)
+    axis = (0.0, 0.0, 1.0)
+    ctx.stage_frames(h); ctx.frames_to_cylindrical(axis)
+    ctx.set_factors(synth.factors(NA))
+    mom = np.array([(0, 0)] + [(l, m) for l in range(1, L + 1) for m in range(4)])
+    for q in ((0.05, 0.02, 0.03), (0.3, -0.2, 0.25)):
+        for it in range(2):
+            ctx.synchronize(); t0 = time.time()
+            ctx.compute_mpcylinder(q, axis, mom, dsp="square")
+            dt = time.time() - t0
+        print(f"mpcylinder q={q}: {NA} atoms x {NF} frames x {len(mom)} moments (orders <= {2*L}): {dt*1e3:.1f} ms (amp {ctx.last_amplitude_ms():.1f} ms) -> "
+              f"{NA*NF*len(mom)/dt:.3e} moment-evals/s, {NA*NF/dt:.3e} atom-frames/s")
+
 if which in ("all", "h2d"):
     n = 1 << 30
     host = ctx.pinned((n,), np.uint8)
