@@ -427,14 +427,15 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
         if (LOG2N == 11) fft_pass<LOG2N, 3, 8, -1>(s, twN);
         if (LOG2N == 12) fft_pass<LOG2N, 4, 16, -1>(s, twN);
         double2 *out = Zt + ((t * R + r) << LOG2N);
-        int th = (int)(((long long)r * f0) % L);
+        // ... so the twiddle itself advances by a constant factor: w_{i+1} = w_i * W_L^{dth} (N/256 <= 16 steps, ~1e-15)
+        const int th = (int)(((long long)r * f0) % L);
         const int dth = (r << (12 - LOG2N)) % L;
+        double2 w = cmul2(Thi[th >> 8], Tlo[th & 255]);
+        const double2 wstep = cmul2(Thi[dth >> 8], Tlo[dth & 255]);
 #pragma unroll 4
         for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) {
-            const double2 w = cmul2(Thi[th >> 8], Tlo[th & 255]);
             out[pos] = cmul2(s[phys(pos)], w);
-            th += dth;
-            if (th >= L) th -= L;
+            w = cmul2(w, wstep);
         }
     }
 }

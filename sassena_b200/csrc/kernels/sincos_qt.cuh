@@ -31,6 +31,11 @@ namespace sass {
 
 #define SASS_TWO_OVER_PI 0.63661977236758134308
 
+// coefficient tables in constant memory: DFMA takes them as c[bank][offset] operands.  As literals ptxas re-materialises
+// them with two UMOV each inside unrolled loops (9 % of the instructions the split self kernel executed).
+__constant__ double kSinC[6] = {SASS_S0, SASS_S1, SASS_S2, SASS_S3, SASS_S4, SASS_S5};
+__constant__ double kCosC[6] = {SASS_C0, SASS_C1, SASS_C2, SASS_C3, SASS_C4, SASS_C5};
+
 // sin/cos of (pi/2)*u: returns cos in c, sin in s (full quadrant handling).
 __device__ __forceinline__ void sincos_qt(double u, double &s, double &c) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
@@ -39,16 +44,16 @@ __device__ __forceinline__ void sincos_qt(double u, double &s, double &c) {
     double kd = t - MAGIC;
     double f = u - kd;
     double z = f * f;
-    double S = fma(z, SASS_S5, SASS_S4);
-    double Cp = fma(z, SASS_C5, SASS_C4);
-    S = fma(z, S, SASS_S3);
-    Cp = fma(z, Cp, SASS_C3);
-    S = fma(z, S, SASS_S2);
-    Cp = fma(z, Cp, SASS_C2);
-    S = fma(z, S, SASS_S1);
-    Cp = fma(z, Cp, SASS_C1);
-    S = fma(z, S, SASS_S0);
-    Cp = fma(z, Cp, SASS_C0);
+    double S = fma(z, kSinC[5], kSinC[4]);
+    double Cp = fma(z, kCosC[5], kCosC[4]);
+    S = fma(z, S, kSinC[3]);
+    Cp = fma(z, Cp, kCosC[3]);
+    S = fma(z, S, kSinC[2]);
+    Cp = fma(z, Cp, kCosC[2]);
+    S = fma(z, S, kSinC[1]);
+    Cp = fma(z, Cp, kCosC[1]);
+    S = fma(z, S, kSinC[0]);
+    Cp = fma(z, Cp, kCosC[0]);
     double sv = f * S;
     double cv = fma(z, Cp, 1.0);
     bool odd = (k & 1) != 0;
@@ -94,10 +99,7 @@ __device__ __forceinline__ void sincos_qt_accumulate(double u, int bhi, int blo,
 // polynomial value instead of to b, which removes the register-pair moves of sincos_qt_accumulate (ptxas turns
 // predicated FMAs back into FMA+select pairs, so the odd-quadrant swap stays four 32-bit selects):
 //   sign(cos-type term) = bit1(k), sign(sin-type term) = bit1(k+1)   (see DESIGN.md "quadrant algebra").
-// coefficient tables in constant memory: DFMA takes them as c[bank][offset] operands (no register or
-// uniform-register materialisation inside the atom loop)
-__constant__ double kSinC[6] = {SASS_S0, SASS_S1, SASS_S2, SASS_S3, SASS_S4, SASS_S5};
-__constant__ double kCosC[6] = {SASS_C0, SASS_C1, SASS_C2, SASS_C3, SASS_C4, SASS_C5};
+// (coefficient tables kSinC / kCosC in constant memory, see above)
 
 template <int ABL = 0>
 __device__ __forceinline__ void sincos_qt_accumulate2(double u, double b, double &re, double &im) {
