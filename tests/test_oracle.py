@@ -197,3 +197,48 @@ def test_mpcylinder_c_port_matches_scipy_restatement(oracle):
         oracle.compute_mpcylinder(cyl, b, q, axis, [[0, 1]])
     with pytest.raises(RuntimeError):
         oracle.compute_mpcylinder(cyl, b, q, axis, [[2, 4]])
+
+
+def test_orientational_averages_against_closed_forms(oracle):
+    """KA7 of SURVEY 8c and its cylinder analogue: for a static cluster the orientational average of |A(q)|^2 has a closed
+    form -- sphere: Debye, sum_ij b_i b_j sin(q r_ij)/(q r_ij); cylinder about z: sum_ij b_i b_j cos(q_z z_ij) J0(q_r rho_ij).
+    The multipole devices must reproduce it to the float32 staging accuracy, the vector averages within their sampling error
+    (random sphere vectors: Monte Carlo; equidistant cylinder angles: spectrally exact).  The atoms sit at z > 0 with q_z > 0,
+    where the reference's exp(i |z q_z|) phase (multipole_scatter_device.cpp:941-947) coincides with exp(i z q_z)."""
+    from scipy.special import j0
+    rng = np.random.default_rng(3)
+    NA = 6
+    pos = (rng.normal(size=(NA, 3)) * 2.0).astype(np.float32)
+    pos[:, 2] = np.abs(pos[:, 2]) + 0.5
+    xyz = np.tile(pos, (2, 1, 1))
+    b = np.array([2.0, -3.7, 6.6, 5.8, 1.0, 4.2])
+    p64 = pos.astype(np.float64)
+    # sphere
+    ql = 1.2
+    d = np.linalg.norm(p64[:, None, :] - p64[None, :, :], axis=-1)
+    debye = float(np.sum(b[:, None] * b[None, :] * np.sinc(ql * d / np.pi)))
+    mp = oracle.compute_mpsphere(oracle.cart_to_spherical(xyz), b, ql, oracle.moments_sphere(16), dsp="square")
+    assert mp[0][0].real == pytest.approx(debye, rel=1e-6) and abs(mp[0][0].imag) < 1e-9
+    assert mp[1].real == pytest.approx(debye, rel=1e-6)  # static: fq = fq0
+    u = rng.normal(size=(20000, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    vec = oracle.compute_all_vectors(xyz, b, ql * u, dsp="square", nthreads=4)
+    assert vec[0][0].real == pytest.approx(debye, rel=0.03)  # ~1/sqrt(20000) sampling error of |A|^2
+    # cylinder about z
+    q = np.array([0.9, 0.0, 0.7])
+    axis = (0, 0, 1)
+    rho = np.linalg.norm(p64[:, None, :2] - p64[None, :, :2], axis=-1)
+    dz = p64[:, None, 2] - p64[None, :, 2]
+    exact = float(np.sum(b[:, None] * b[None, :] * np.cos(q[2] * dz) * j0(0.9 * rho)))
+    cyl = oracle.cart_to_cylindrical(xyz, axis)
+    for L in (10, 20):
+        mc = oracle.compute_mpcylinder(cyl, b, q, axis, oracle.moments_cylinder(L), dsp="square")
+        assert mc[0][0].real == pytest.approx(exact, rel=1e-6)
+    phi = np.linspace(0, 2 * np.pi, 720, endpoint=False)
+    qv = np.stack([0.9 * np.cos(phi), 0.9 * np.sin(phi), np.full_like(phi, 0.7)], axis=1)
+    vc = oracle.compute_all_vectors(xyz, b, qv, dsp="square", nthreads=4)
+    assert vc[0][0].real == pytest.approx(exact, rel=1e-10)
+    # the same vectors out of the reference's cylinder construction (abstract_vectors_scatter_device.cpp:130-149)
+    sub = oracle.init_subvectors("cylinder", q, orient=np.stack([np.cos(phi), np.sin(phi), np.zeros_like(phi)], axis=1), axis=axis)
+    vs = oracle.compute_all_vectors(xyz, b, sub, dsp="square", nthreads=4)
+    assert vs[0][0].real == pytest.approx(exact, rel=1e-10)
