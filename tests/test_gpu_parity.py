@@ -553,6 +553,44 @@ def test_known_answers(gpu_ctx):
     assert np.allclose(fqt, b[0] ** 2 * np.exp(-1j * 0.8 * v * tau), rtol=0, atol=1e-11 * b[0] ** 2)
 
 
+def test_cluster_averages_closed_forms(gpu_ctx, oracle):
+    """KA7 on the device: for a static cluster the multipole sphere device gives the Debye sum, the multipole cylinder
+    device sum_ij b_i b_j cos(q_z z_ij) J0(q_r rho_ij) (atoms at z > 0, q_z > 0: there the reference's exp(i|z q_z|) phase
+    equals exp(i z q_z)), to the float32 staging accuracy; equidistant cylinder vectors reproduce the latter exactly."""
+    from scipy.special import j0
+    rng = np.random.default_rng(3)
+    NA = 6
+    pos = (rng.normal(size=(NA, 3)) * 2.0).astype(np.float32)
+    pos[:, 2] = np.abs(pos[:, 2]) + 0.5
+    xyz = np.tile(pos, (3, 1, 1))
+    b = np.array([2.0, -3.7, 6.6, 5.8, 1.0, 4.2])
+    p64 = pos.astype(np.float64)
+    ql = 1.2
+    d = np.linalg.norm(p64[:, None, :] - p64[None, :, :], axis=-1)
+    debye = float(np.sum(b[:, None] * b[None, :] * np.sinc(ql * d / np.pi)))
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.frames_to_spherical()
+    gpu_ctx.set_factors(b)
+    fqt, fq, _ = gpu_ctx.compute_mpsphere(ql, oracle.moments_sphere(16), dsp="square")
+    assert fqt[0].real == pytest.approx(debye, rel=1e-6) and fq.real == pytest.approx(debye, rel=1e-6)
+    q = np.array([0.9, 0.0, 0.7])
+    axis = (0, 0, 1)
+    rho = np.linalg.norm(p64[:, None, :2] - p64[None, :, :2], axis=-1)
+    dz = p64[:, None, 2] - p64[None, :, 2]
+    exact = float(np.sum(b[:, None] * b[None, :] * np.cos(q[2] * dz) * j0(0.9 * rho)))
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.frames_to_cylindrical(axis)
+    gpu_ctx.set_factors(b)
+    fqt, _, _ = gpu_ctx.compute_mpcylinder(q, axis, oracle.moments_cylinder(12), dsp="square")
+    assert fqt[0].real == pytest.approx(exact, rel=1e-6)
+    phi = np.linspace(0, 2 * np.pi, 720, endpoint=False)
+    qv = np.stack([0.9 * np.cos(phi), 0.9 * np.sin(phi), np.full_like(phi, 0.7)], axis=1)
+    gpu_ctx.stage_frames(xyz)
+    gpu_ctx.set_factors(b)
+    fqt, _, _ = gpu_ctx.compute_all_vectors(qv, dsp="square")
+    assert fqt[0].real == pytest.approx(exact, rel=1e-10)
+
+
 def test_two_atom_debye(gpu_ctx, oracle):
     """KA3: two static atoms at distance d; sphere average -> b1^2+b2^2+2 b1 b2 sin(qd)/(qd).
     The multipole expansion (L=14) reproduces it to the accuracy the reference's float32 (r,phi,theta) staging
