@@ -383,6 +383,14 @@ void Config::read_xml(const std::string &filename) {
     }
     // ---- stager (parameters.cpp:345-369) ----
     if (x.exists("//stager/target")) stager_target = x.get_string("//stager/target");
+    stager.filepath = get_filepath(stager.file);
+    if (x.exists("//stager/dump")) stager.dump = x.get_bool("//stager/dump");
+    if (x.exists("//stager/file")) {
+        stager.file = x.get_string("//stager/file");
+        stager.filepath = get_filepath(stager.file);
+    }
+    if (x.exists("//stager/format")) stager.format = x.get_string("//stager/format");
+    if (x.exists("//stager/mode")) stager.mode = x.get_string("//stager/mode");  // (the devices force their own mode)
     // ---- scattering (parameters.cpp:372-606) ----
     if (x.exists("//scattering/type")) scattering.type = x.get_string("//scattering/type");
     if (x.exists("//scattering/target")) throw Error("scattering.target is obsolete. Use stager.target instead.");

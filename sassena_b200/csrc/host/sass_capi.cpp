@@ -100,6 +100,9 @@ int sass_params_set(sass_params *p, const char *key, const char *value) {
         else if (k == o + "multipole.moments.resolution") s.multipole.resolution = atol(value);
         else if (k == "limits.stage.memory.data") p->params.limits.stage_memory_data = strtoull(value, nullptr, 10);
         else if (k == "limits.stage.stream") p->params.limits.stage_stream = parse_bool(v);
+        else if (k == "stager.dump") p->params.stager.dump = parse_bool(v);
+        else if (k == "stager.file") p->params.stager.file = p->params.stager.filepath = v;
+        else if (k == "stager.format") p->params.stager.format = v;
         else if (k == "limits.decomposition.utilization") p->params.limits.decomposition.utilization = atof(value);
         else if (k == "limits.decomposition.partitions.automatic")
             p->params.limits.decomposition.partitions_automatic = parse_bool(v);

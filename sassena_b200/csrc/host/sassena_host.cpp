@@ -1,6 +1,8 @@
 // sassena_host.cpp — see sassena_host.hpp.  Reference citations are relative to benlabs/sassena v1.4.2.
 #include "sassena_host.hpp"
 
+#include "dcd.hpp"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -350,6 +352,28 @@ void DataStagerByFrame::stage_block() {
     timer_.start("st:wait");
     allcomm_.barrier();
     timer_.stop("st:wait");
+    if (params_.stager.dump) write(params_.stager.filepath, params_.stager.format);
+}
+
+void DataStagerByFrame::write(const std::string &filename, const std::string &format) {
+    DivAssignment assignment(partitioncomm_.size(), partitioncomm_.rank(), m_sample.NF);
+    if (allcomm_.rank() < partitioncomm_.size()) {  // the first partition writes
+        timer_.start("st:dump");
+        if (format != "dcd") throw Error("Format for coordinate dumping not known: " + format);
+        DCDCoordinateWriter cw(filename, m_sample.NF, m_sample.NA);
+        if (allcomm_.rank() == 0) cw.init();
+        partitioncomm_.barrier();
+        cw.prepare();
+        partitioncomm_.barrier();
+        for (size_t c = 0; c < assignment.max(); ++c) {  // consecutive blocks, one frame per rank and round
+            if (c < assignment.size()) cw.write(m_sample.frames + assignment[c] * m_sample.NA * 3, assignment[c], 1);
+            partitioncomm_.barrier();
+        }
+        timer_.stop("st:dump");
+    }
+    timer_.start("st:wait");
+    allcomm_.barrier();
+    timer_.stop("st:wait");
 }
 
 void DataStagerByFrame::stage(int repr) {
@@ -369,6 +393,7 @@ void DataStagerByFrame::stage(int repr) {
     timer_.start("st:wait");
     allcomm_.barrier();
     timer_.stop("st:wait");
+    if (params_.stager.dump) write(params_.stager.filepath, params_.stager.format);  // the cartesian frames, as the reference's
 }
 
 DataStagerByAtom::DataStagerByAtom(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
@@ -387,6 +412,34 @@ void DataStagerByAtom::stage() {
                                          partitioncomm_.rank());
     if (rc) throw Error(std::string("stage_atoms_from_frames: ") + be_.last_error(ctx_));
     timer_.stop("st:first");
+    timer_.start("st:wait");
+    allcomm_.barrier();
+    timer_.stop("st:wait");
+    if (params_.stager.dump) write(params_.stager.filepath, params_.stager.format);
+}
+
+void DataStagerByAtom::write(const std::string &filename, const std::string &format) {
+    ModAssignment assignment(partitioncomm_.size(), partitioncomm_.rank(), m_sample.NA);
+    if (allcomm_.rank() < partitioncomm_.size()) {
+        timer_.start("st:dump");
+        if (format != "dcd") throw Error("Format for coordinate dumping not known: " + format);
+        DCDCoordinateWriter cw(filename, m_sample.NA, m_sample.NF);  // blocks = atoms, entries = frames
+        if (partitioncomm_.rank() == 0) cw.init();
+        partitioncomm_.barrier();
+        cw.prepare();
+        partitioncomm_.barrier();
+        std::vector<float> line(m_sample.NF * 3);
+        for (size_t c = 0; c < assignment.max(); ++c) {
+            if (c < assignment.size()) {
+                const size_t atom = assignment[c];
+                for (size_t f = 0; f < m_sample.NF; f++)
+                    for (int k = 0; k < 3; k++) line[3 * f + k] = m_sample.frames[(f * m_sample.NA + atom) * 3 + k];
+                cw.write(line.data(), atom, 1);
+            }
+            partitioncomm_.barrier();
+        }
+        timer_.stop("st:dump");
+    }
     timer_.start("st:wait");
     allcomm_.barrier();
     timer_.stop("st:wait");

@@ -236,9 +236,16 @@ struct LimitsParameters {
     bool coherent_scan_snap = false;
 };
 
+// stager section (parameters.cpp:345-369): dump = write the staged coordinates to `filepath` (data_stager.cpp:91-94,233-238)
+struct StagerParameters {
+    bool dump = false;
+    std::string file = "dump.dcd", filepath = "dump.dcd", format = "dcd", mode = "frames";
+};
+
 struct Params {
     ScatteringParameters scattering;
     LimitsParameters limits;
+    StagerParameters stager;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -331,6 +338,8 @@ class DataStagerByFrame {  // data_stager.cpp:39-129
     void stage(int repr);  // coordinates end up resident on this rank's GPU, frame-major
     // frame decomposition inside the partition (data_stager.cpp:57-118): this rank stages DivAssignment(NNPP, rank, NF)
     void stage_block();
+    // stager.dump (data_stager.cpp:131-165): the first partition writes the frames as a DCD file, rank r its DivAssignment block
+    void write(const std::string &filename, const std::string &format);
 };
 
 class DataStagerByAtom {  // data_stager.cpp:176-349
@@ -345,6 +354,9 @@ class DataStagerByAtom {  // data_stager.cpp:176-349
     DataStagerByAtom(Sample &sample, ICommunicator &allcomm, ICommunicator &partitioncomm, Timer &timer,
                      const SgpuBackend &be, sgpu_ctx *ctx, const Params &params);
     void stage();  // ModAssignment(partition size, partition rank, NA) atoms, atom-major on the GPU
+    // stager.dump (data_stager.cpp:352-391): a DCD file of NA "frames" with NF "atoms" each (the atom-major staging layout),
+    // rank r of the first partition writes the timelines of its ModAssignment atoms
+    void write(const std::string &filename, const std::string &format);
 };
 
 // ---------------------------------------------------------------------------------------------------------------

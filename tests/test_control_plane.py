@@ -380,3 +380,32 @@ def test_cli_end_to_end(tmp_path, oracle):
     h5 = host.load_signal_h5(job.signal_file)
     assert np.array_equal(h5["qvectors"], sig["qvectors"]) and np.array_equal(h5["fqt"], sig["fqt"])
     assert np.array_equal(h5["fq0"], sig["fqt"][:, 0]) and np.array_equal(h5["fq2"], sig["fq2"])
+
+
+@pytest.mark.parametrize("kind", ["all", "self"])
+def test_stager_dump_writes_the_staged_coordinates(tmp_path, oracle, kind):
+    """stager.dump (data_stager.cpp:91-94,131-165,233-238,352-391): the staged coordinates of stager.target as a DCD file --
+    frame-major for the coherent / multipole devices, and NA "frames" of NF "atoms" (the atom-major staging layout) for
+    the self device"""
+    from oracle_backend import OracleBackend
+    cfg, xyz, names = make_case(
+        tmp_path, NA=12, NF=7,
+        sample_extra="<selections><selection><type>range</type><name>part</name><from>2</from><to>9</to></selection></selections>",
+        stager="<stager><target>part</target><dump>true</dump><file>staged.dcd</file><format>dcd</format></stager>",
+        scattering=f"<type>{kind}</type><vectors><type>single</type><single><x>0.5</x><y>0</y><z>0</z></single></vectors>"
+                   "<average><orientation><type>none</type></orientation></average>")
+    job = host.Job(cfg)
+    fr = job.frames()
+    assert fr.shape == (7, 8, 3)
+    n, _ = job.run(str(tmp_path / "sig"), backend=OracleBackend().vtbl)
+    assert n == 1
+    got = host.DCDFile(str(tmp_path / "staged.dcd")).read()
+    if kind == "all":
+        assert got.shape == fr.shape and np.array_equal(got, fr)
+    else:
+        assert got.shape == (8, 7, 3) and np.array_equal(got, fr.transpose(1, 0, 2))
+    # unknown format: the reference's error
+    bad = str(tmp_path / "bad.xml")
+    open(bad, "w").write(open(cfg).read().replace("<format>dcd</format></stager>", "<format>xyz</format></stager>"))
+    with pytest.raises(host.HostError, match="Format for coordinate dumping not known"):
+        host.Job(bad).run(str(tmp_path / "sig2"), backend=OracleBackend().vtbl)
