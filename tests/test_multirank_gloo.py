@@ -116,3 +116,25 @@ def test_multirank_job_from_config(oracle, tmp_path, manual):
         fqt, fq, fq2 = oracle.compute_all_vectors(xyz, job.factors(np.linalg.norm(q)), p.init_subvectors(q))
         assert np.allclose(sig["fqt"][i], fqt, rtol=1e-11, atol=1e-11 * abs(fqt[0]))
         assert np.isclose(sig["fq"][i], fq, rtol=1e-11) and np.isclose(sig["fq2"][i], fq2, rtol=1e-11)
+
+
+@pytest.mark.parametrize("world,kind", [(2, "all"), (3, "all"), (2, "self"), (3, "self")])
+def test_multirank_stager_dump(oracle, tmp_path, world, kind):
+    """stager.dump on several ranks: every rank of the partition writes its own frames (DivAssignment, coherent with the
+    reference's frame decomposition) or atom timelines (ModAssignment, self) into one DCD file (data_stager.cpp:131-165,352-391)"""
+    from test_control_plane import make_case
+    stager = "<stager><dump>true</dump><file>staged.dcd</file></stager>"
+    # uneven blocks on purpose (9 frames / 11 atoms over 2 or 3 ranks): the utilization threshold is lowered for it
+    stager += ("<limits><decomposition><utilization>0.5</utilization>"
+               + ("<coherent>frames</coherent>" if kind == "all" else "") + "</decomposition></limits>")
+    cfg, xyz, names = make_case(
+        tmp_path, NA=11, NF=9, stager=stager,
+        scattering=f"<type>{kind}</type><vectors><type>single</type><single><x>0.5</x><y>0</y><z>0</z></single></vectors>"
+                   "<average><orientation><type>none</type></orientation></average>")
+    gathered = _run(world, "job", tmp_path, extra=(cfg, str(tmp_path / "signal")))
+    assert sorted(w for _, w, _ in gathered) == [0] * (world - 1) + [1]
+    got = host.DCDFile(str(tmp_path / "staged.dcd")).read()
+    if kind == "all":
+        assert np.array_equal(got, xyz)
+    else:
+        assert np.array_equal(got, xyz.transpose(1, 0, 2))
