@@ -394,3 +394,76 @@ def np_dsp_store(A, dsp="autocorrelate", method="fftw", norm=None):
     a = T.mean(axis=1)
     norm = (1.0 / M) if norm is None else norm
     return T.sum(0) * norm, a.sum() * norm, (a * np.conj(a)).sum() * norm
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref/libsmath_ref.so: the REFERENCE's own smath.cpp / coor3d.cpp / assignment.cpp compiled where they lie
+# (make -C oracle ref; shims under oracle/shim stand in for the headers they merely include).  Checker of the checker.
+# ---------------------------------------------------------------------------------------------
+_REF_SMATH = os.path.join(_HERE, "_ref", "libsmath_ref.so")
+_ref = None
+
+
+def have_ref_smath():
+    return os.path.exists(_REF_SMATH)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF_SMATH)
+    return _ref
+
+
+def ref_auto_correlate_direct(x, vector_overload=False):
+    a = np.ascontiguousarray(x, dtype=np.complex128).copy()
+    f = ref_lib().ref_auto_correlate_direct_vec if vector_overload else ref_lib().ref_auto_correlate_direct
+    f(_p(a.view(np.float64), C.c_double), C.c_size_t(len(a)))
+    return a
+
+
+def ref_auto_correlate_fftw(x):
+    NF = len(x)
+    a = np.zeros(2 * NF, dtype=np.complex128)
+    a[:NF] = x
+    ref_lib().ref_auto_correlate_fftw(_p(a.view(np.float64), C.c_double), C.c_size_t(NF))
+    return a[:NF].copy()
+
+
+def ref_square_elements(x):
+    a = np.ascontiguousarray(x, dtype=np.complex128).copy()
+    ref_lib().ref_square_elements(_p(a.view(np.float64), C.c_double), C.c_size_t(len(a)))
+    return a
+
+
+def ref_cart_to_spherical(xyz):
+    """double [n][3] -> (r, phi, theta) by SphericalCoor3D(CartesianCoor3D), in double (the stager narrows afterwards)"""
+    a = _f64(xyz).reshape(-1, 3)
+    out = np.empty_like(a)
+    for i in range(len(a)):
+        ref_lib().ref_cart_to_spherical(_p(a[i], C.c_double), _p(out[i], C.c_double))
+    return out
+
+
+def ref_cart_to_cylindrical(xyz, axis):
+    a = _f64(xyz).reshape(-1, 3)
+    ax = _f64(np.asarray(axis, dtype=np.float64))
+    out = np.empty_like(a)
+    for i in range(len(a)):
+        ref_lib().ref_cart_to_cylindrical(_p(a[i], C.c_double), _p(ax, C.c_double), _p(out[i], C.c_double))
+    return out
+
+
+def ref_vector_base(axis):
+    out = np.zeros((3, 3))
+    ref_lib().ref_vector_base(_p(_f64(np.asarray(axis, dtype=np.float64)), C.c_double), _p(out, C.c_double))
+    return out
+
+
+def ref_assignment(mod, NN, rank, NAF):
+    """(offset, size, max, indices) of the reference's ModAssignment (mod=True) / DivAssignment"""
+    o, s, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    idx = np.zeros(max(NAF, 1), dtype=np.uintp)
+    ref_lib().ref_assignment(C.c_int(1 if mod else 0), C.c_size_t(NN), C.c_size_t(rank), C.c_size_t(NAF), C.byref(o), C.byref(s),
+                             C.byref(m), idx.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(len(idx)))
+    return o.value, s.value, m.value, idx[:s.value].astype(np.int64)

@@ -5,11 +5,18 @@
  * this file.  It is the checker used by tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.
  *
- * PARITY UNPINNED: the reference (benlabs/sassena v1.4.2) ships no golden vectors or
- * asserting tests for this path (tests/unit_broadcast.cpp asserts nothing) and cannot be
- * built in this image (needs Boost, FFTW3, MPI, HDF5, libxml2 — all absent).  This port
- * follows the reference loops cited per function and is pinned instead by analytic
- * known-answer tests and by numpy/scipy cross-checks (tests/test_oracle_*.py).
+ * PARITY PARTLY PINNED: the reference (benlabs/sassena v1.4.2) ships no golden vectors or
+ * asserting tests for this path (tests/unit_broadcast.cpp asserts nothing) and its scatter
+ * devices cannot be built in this image (Boost, FFTW3, MPI, HDF5, libxml2 are all absent).
+ * What CAN be built from the reference's own sources is, and pins the matching functions here:
+ *   src/math/smath.cpp            (direct + FFT autocorrelation, square)      orc_auto_correlate_*, dsp
+ *   src/math/coor3d.cpp           (cart -> spherical / cylindrical, the base) orc_cart_to_*, orc_vector_base
+ *   src/decomposition/assignment.cpp (Div / ModAssignment)                    orc_div/mod_assignment
+ *   vendor/xdrfile-1.1.1          (XTC / TRR codec; pins the product's readers)
+ * (oracle/Makefile target `ref`, shims in oracle/shim, fixtures tests/golden/ref_smath.npz).
+ * The amplitude loops, the store/normalise steps and the multipole special functions remain
+ * UNPINNED by reference output: they follow the reference loops cited per function and are
+ * pinned by analytic known-answer tests and numpy/scipy cross-checks (tests/test_oracle.py).
  *
  * Third-party arithmetic that is not in /root/reference and is restated here:
  *   FFTW3 (unpinned version)         -> own mixed-radix / Bluestein complex FFT

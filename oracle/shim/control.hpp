@@ -1,0 +1,1 @@
+/* control.hpp — empty SHIM: src/math/smath.cpp includes it but uses nothing of it (the real one needs Boost) */

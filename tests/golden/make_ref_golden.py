@@ -1,0 +1,52 @@
+"""Golden vectors produced by the REFERENCE's own code: oracle/_ref/libsmath_ref.so is the reference's src/math/smath.cpp,
+src/math/coor3d.cpp and src/decomposition/assignment.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
+Run in the build container (needs /root/reference); writes tests/golden/ref_smath.npz, which travels with the repo and
+pins the oracle's restatements on machines without the reference (tests/test_oracle.py::test_oracle_pinned_to_reference_build).
+
+    python tests/golden/make_ref_golden.py
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as o  # noqa: E402
+
+subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+rng = np.random.default_rng(20261017)
+out = {}
+# correlation / square: timelines of several lengths (odd, even, prime, power of two), complex128
+for i, NF in enumerate((1, 2, 3, 8, 17, 100, 257)):
+    x = rng.normal(size=NF) + 1j * rng.normal(size=NF)
+    out[f"corr_{i}_x"] = x
+    out[f"corr_{i}_direct"] = o.ref_auto_correlate_direct(x)
+    out[f"corr_{i}_direct_vec"] = o.ref_auto_correlate_direct(x, vector_overload=True)
+    out[f"corr_{i}_fftw"] = o.ref_auto_correlate_fftw(x)
+    out[f"corr_{i}_square"] = o.ref_square_elements(x)
+# coordinate conversions: random points, points on the axes / in the coordinate planes / at the origin
+pts = np.concatenate([rng.normal(size=(200, 3)) * 30.0,
+                      np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 2, 0], [0, -2, 0], [0, 0, 3], [0, 0, -3], [1, 1, 0], [-1, 1, 0],
+                                [-1, -1, 0], [1, -1, 0], [0, 1, 1], [0, -1, -1], [1e-30, 0, 1], [5, 0, -1e-20]], dtype=np.float64)])
+pts = pts.astype(np.float32).astype(np.float64)  # what a frame holds
+out["pts"] = pts
+out["sph"] = o.ref_cart_to_spherical(pts)
+axes = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0], [1, 1, 0], [2, -1, 3], [0, 0, -2], [-1, -1, -1], [1e-3, 0, 1]], dtype=np.float64)
+out["axes"] = axes
+out["bases"] = np.array([o.ref_vector_base(a) for a in axes])
+out["cyl"] = np.array([o.ref_cart_to_cylindrical(pts, a) for a in axes])
+# assignments: (NN, NAF) grid, every rank
+rows = []
+for NN in (1, 2, 3, 4, 7, 8, 16):
+    for NAF in (1, 2, 5, 8, 9, 23, 100, 1000):
+        for rank in range(NN):
+            for mod in (0, 1):
+                off, size, mx, idx = o.ref_assignment(bool(mod), NN, rank, NAF)
+                first = int(idx[0]) if size else -1
+                last = int(idx[-1]) if size else -1
+                rows.append((mod, NN, rank, NAF, off, size, mx, first, last, int(idx.sum())))
+out["assignments"] = np.array(rows, dtype=np.int64)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_smath.npz"), **out)
+print("wrote tests/golden/ref_smath.npz:", len(out), "arrays,", len(rows), "assignment rows")

@@ -242,3 +242,71 @@ def test_orientational_averages_against_closed_forms(oracle):
     sub = oracle.init_subvectors("cylinder", q, orient=np.stack([np.cos(phi), np.sin(phi), np.zeros_like(phi)], axis=1), axis=axis)
     vs = oracle.compute_all_vectors(xyz, b, sub, dsp="square", nthreads=4)
     assert vs[0][0].real == pytest.approx(exact, rel=1e-10)
+
+
+def _ref_golden():
+    return np.load(os.path.join(GOLD, "ref_smath.npz"))
+
+
+def test_oracle_pinned_to_reference_build(oracle):
+    """tests/golden/ref_smath.npz holds outputs of the REFERENCE's own src/math/smath.cpp, src/math/coor3d.cpp and
+    src/decomposition/assignment.cpp, compiled where they lie (oracle/_ref/libsmath_ref.so, tests/golden/make_ref_golden.py).
+    The oracle's restatements must reproduce them: the direct correlation, the square and the integer partitions bit for
+    bit; the FFT form to rounding (the build's FFTW3 shim runs the oracle's DFT, so what is pinned there is the reference's
+    padding / power spectrum / normalisation, not FFTW's arithmetic); the coordinate conversions after the stager's
+    narrowing to float.  Also confirms SURVEY 8a-a4 on the reference's own code: its fftw_complex direct form is the
+    complex conjugate of its FFT form, its std::vector overload is not."""
+    g = _ref_golden()
+    for i in range(7):
+        x = g[f"corr_{i}_x"]
+        d = oracle.auto_correlate_direct(x)
+        assert np.array_equal(d, g[f"corr_{i}_direct"]), i
+        f = oracle.auto_correlate_fftw(x)
+        scale = np.max(np.abs(g[f"corr_{i}_fftw"]))
+        assert np.max(np.abs(f - g[f"corr_{i}_fftw"])) <= 1e-15 * scale
+        assert np.array_equal(x * np.conj(x), g[f"corr_{i}_square"]) or np.allclose(x * np.conj(x), g[f"corr_{i}_square"], rtol=1e-16)
+        # a4: direct == conj(fftw) to rounding; the unused vector overload == fftw
+        assert np.max(np.abs(g[f"corr_{i}_direct"] - np.conj(g[f"corr_{i}_fftw"]))) <= 1e-13 * scale
+        assert np.max(np.abs(g[f"corr_{i}_direct_vec"] - g[f"corr_{i}_fftw"])) <= 1e-13 * scale
+    pts = g["pts"].astype(np.float32)
+    assert np.array_equal(oracle.cart_to_spherical(pts), g["sph"].astype(np.float32))
+    for a, base, cyl in zip(g["axes"], g["bases"], g["cyl"]):
+        assert np.array_equal(oracle.vector_base(a), base)
+        assert np.array_equal(oracle.cart_to_cylindrical(pts, a), cyl.astype(np.float32))
+    for mod, NN, rank, NAF, off, size, mx, first, last, total in g["assignments"]:
+        got = (oracle.mod_assignment if mod else oracle.div_assignment)(int(NN), int(rank), int(NAF))
+        assert got == (off, size, mx), (mod, NN, rank, NAF)
+        if size:  # indices: Div = offset + i, Mod = rank + i * NN (assignment.cpp:36-50,91-105)
+            idx = rank + NN * np.arange(size) if mod else off + np.arange(size)
+            assert (idx[0], idx[-1], idx.sum()) == (first, last, total)
+
+
+def test_host_layer_partitions_match_reference_build():
+    """the PRODUCT's DivAssignment / ModAssignment (csrc/host/sassena_host.cpp) against the reference build's fixtures"""
+    from sassena_b200 import host
+    g = _ref_golden()
+    for mod, NN, rank, NAF, off, size, mx, first, last, total in g["assignments"]:
+        got = (host.mod_assignment if mod else host.div_assignment)(int(NN), int(rank), int(NAF))
+        assert got == (off, size, mx), (mod, NN, rank, NAF)
+
+
+def test_reference_build_live(oracle):
+    """where oracle/_ref/libsmath_ref.so exists (built from /root/reference by `make -C oracle ref`): fresh random inputs
+    through the reference's own code and through the oracle"""
+    if not oracle.have_ref_smath():
+        pytest.skip("oracle/_ref/libsmath_ref.so not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(7)
+    for NF in (5, 64, 129, 1000):
+        x = rng.normal(size=NF) + 1j * rng.normal(size=NF)
+        assert np.array_equal(oracle.auto_correlate_direct(x), oracle.ref_auto_correlate_direct(x))
+        r = oracle.ref_auto_correlate_fftw(x)
+        assert np.max(np.abs(oracle.auto_correlate_fftw(x) - r)) <= 1e-15 * np.max(np.abs(r))
+    pts = (rng.normal(size=(500, 3)) * 50).astype(np.float32)
+    assert np.array_equal(oracle.cart_to_spherical(pts), oracle.ref_cart_to_spherical(pts.astype(np.float64)).astype(np.float32))
+    for axis in ((0, 0, 1), (3, -2, 0.5), (1, 1, 1)):
+        assert np.array_equal(oracle.cart_to_cylindrical(pts, axis),
+                              oracle.ref_cart_to_cylindrical(pts.astype(np.float64), axis).astype(np.float32))
+    for NN, NAF in ((5, 33), (8, 30000), (3, 2)):
+        for rank in range(NN):
+            assert oracle.div_assignment(NN, rank, NAF) == oracle.ref_assignment(False, NN, rank, NAF)[:3]
+            assert oracle.mod_assignment(NN, rank, NAF) == oracle.ref_assignment(True, NN, rank, NAF)[:3]
