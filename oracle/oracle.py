@@ -78,6 +78,13 @@ def mod_assignment(NN, rank, NAF):
     return o.value, s.value, m.value
 
 
+def decomposition_penalty(NN, NQ, NAF, NNpP, elbytes=1):
+    """DecompositionParameters(...).penalty() (decomposition_plan.cpp:28-66)"""
+    a, b, c, d = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    return lib().orc_decomposition_penalty(C.c_size_t(NN), C.c_size_t(NQ), C.c_size_t(NAF), C.c_size_t(NNpP), C.c_size_t(elbytes),
+                                           C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+
+
 def decomposition_plan(nn, nq, naf, elbytes, maxbytes, min_utilization=0.95):
     p, ps, pen = C.c_size_t(), C.c_size_t(), C.c_size_t()
     rc = lib().orc_decomposition_plan(C.c_size_t(nn), C.c_size_t(nq), C.c_size_t(naf), C.c_size_t(elbytes),
@@ -467,3 +474,20 @@ def ref_assignment(mod, NN, rank, NAF):
     ref_lib().ref_assignment(C.c_int(1 if mod else 0), C.c_size_t(NN), C.c_size_t(rank), C.c_size_t(NAF), C.byref(o), C.byref(s),
                              C.byref(m), idx.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(len(idx)))
     return o.value, s.value, m.value, idx[:s.value].astype(np.int64)
+
+
+def ref_decomposition_penalty(NN, NQ, NAF, NNpP):
+    f = ref_lib().ref_decomposition_penalty
+    f.restype = C.c_size_t
+    return f(C.c_size_t(NN), C.c_size_t(NQ), C.c_size_t(NAF), C.c_size_t(NNpP))
+
+
+def ref_decomposition_plan(nn, nq, naf, elbytes, maxbytes, automatic=True, manual_size=1, utilization=0.95):
+    """(partitions, partitionsize, penalty, colors) out of the reference's DecompositionPlan.  ONLY for inputs with a valid
+    plan -- the reference fails with a bare `throw;`, which terminates the process."""
+    p, ps, pen = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    col = np.zeros(nn, dtype=np.uintp)
+    ref_lib().ref_decomposition_plan(C.c_size_t(nn), C.c_size_t(nq), C.c_size_t(naf), C.c_size_t(elbytes), C.c_size_t(maxbytes),
+                                     C.c_int(1 if automatic else 0), C.c_size_t(manual_size), C.c_double(utilization),
+                                     C.byref(p), C.byref(ps), C.byref(pen), col.ctypes.data_as(C.POINTER(C.c_size_t)))
+    return p.value, ps.value, pen.value, col.astype(np.int64)

@@ -96,3 +96,26 @@ void ref_assignment(int mod, size_t NN, size_t rank, size_t NAF, size_t *offset,
     }
 }
 }
+
+// ---- the reference's own src/decomposition/decomposition_plan.cpp -------------------------------------------------------------
+#include "control.hpp"
+#include "decomposition/decomposition_plan.hpp"
+
+extern "C" {
+// DecompositionParameters(NN, NQ, NAF, NNpP, elbytesize).penalty()                 decomposition_plan.cpp:28-66
+size_t ref_decomposition_penalty(size_t NN, size_t NQ, size_t NAF, size_t NNpP) { return DecompositionParameters(NN, NQ, NAF, NNpP, 1).penalty(); }
+// DecompositionPlan(nn, nq, naf, elbytesize, nmaxbytesize) with the three Params values it reads.  ONLY for inputs that have a
+// valid plan: the reference reports failure with a bare `throw;`, which terminates the process.    decomposition_plan.cpp:69-157
+void ref_decomposition_plan(size_t nn, size_t nq, size_t naf, size_t elbytes, size_t maxbytes, int automatic, size_t manual_size,
+                            double utilization, size_t *partitions, size_t *partitionsize, size_t *penalty, size_t *colors) {
+    Params::Inst()->limits.decomposition.partitions.automatic = automatic != 0;
+    Params::Inst()->limits.decomposition.partitions.size = manual_size;
+    Params::Inst()->limits.decomposition.utilization = utilization;
+    DecompositionPlan dp(nn, nq, naf, elbytes, maxbytes);
+    *partitions = dp.partitions();
+    *partitionsize = dp.partitionsize();
+    *penalty = DecompositionParameters(nn, nq, naf, dp.partitionsize(), elbytes).penalty();  // (DecompositionPlan::penalty() is declared but not defined in the reference)
+    std::vector<size_t> c = dp.colors();
+    for (size_t i = 0; i < c.size(); i++) colors[i] = c[i];
+}
+}

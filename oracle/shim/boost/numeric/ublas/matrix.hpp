@@ -1,0 +1,1 @@
+/* boost/numeric/ublas/matrix.hpp — empty SHIM: included by the reference's decomposition_plan.hpp, nothing of it is used by the code built here */

@@ -1,5 +1,5 @@
 """Golden vectors produced by the REFERENCE's own code: oracle/_ref/libsmath_ref.so is the reference's src/math/smath.cpp,
-src/math/coor3d.cpp and src/decomposition/assignment.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
+src/math/coor3d.cpp, src/decomposition/assignment.cpp and src/decomposition/decomposition_plan.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
 Run in the build container (needs /root/reference); writes tests/golden/ref_smath.npz, which travels with the repo and
 pins the oracle's restatements on machines without the reference (tests/test_oracle.py::test_oracle_pinned_to_reference_build).
 
@@ -48,5 +48,30 @@ for NN in (1, 2, 3, 4, 7, 8, 16):
                 last = int(idx[-1]) if size else -1
                 rows.append((mod, NN, rank, NAF, off, size, mx, first, last, int(idx.sum())))
 out["assignments"] = np.array(rows, dtype=np.int64)
+# decomposition: penalties on a grid, and the automatic / manual plans wherever one exists (the oracle's own search screens
+# the inputs: the reference reports "no plan" with a bare `throw;` that would terminate this script)
+pen = []
+for NN in (1, 2, 3, 4, 8, 16, 64):
+    for NQ in (1, 2, 5, 20, 50):
+        for NAF in (1, 7, 100, 10000):
+            for NNpP in sorted({1, 2, 3, NN // 2 if NN > 1 else 1, NN}):
+                if NNpP <= NN:
+                    pen.append((NN, NQ, NAF, NNpP, o.ref_decomposition_penalty(NN, NQ, NAF, NNpP)))
+out["penalties"] = np.array(pen, dtype=np.int64)
+plans = []
+for NN in (1, 2, 3, 4, 8, 16, 64):
+    for NQ in (1, 2, 5, 20, 50):
+        for NAF in (1, 7, 100, 10000):
+            for maxbytes in (10 ** 12, 12 * 100000 * 20):
+                el = 12 * 100000
+                rc, part, psize, _ = o.decomposition_plan(NN, NQ, NAF, el, maxbytes, 0.0)
+                if rc != 0:
+                    continue
+                rp, rps, rpen, col = o.ref_decomposition_plan(NN, NQ, NAF, el, maxbytes, True, 1, 0.0)
+                plans.append((NN, NQ, NAF, el, maxbytes, 1, 1, rp, rps, rpen, int((col * (np.arange(NN) + 1)).sum())))
+            for manual in (1, 2, 5):
+                rp, rps, rpen, col = o.ref_decomposition_plan(NN, NQ, NAF, 12, 10 ** 12, False, manual, 0.0)
+                plans.append((NN, NQ, NAF, 12, 10 ** 12, 0, manual, rp, rps, rpen, int((col * (np.arange(NN) + 1)).sum())))
+out["plans"] = np.array(plans, dtype=np.int64)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_smath.npz"), **out)
-print("wrote tests/golden/ref_smath.npz:", len(out), "arrays,", len(rows), "assignment rows")
+print("wrote tests/golden/ref_smath.npz:", len(out), "arrays,", len(rows), "assignment rows,", len(pen), "penalties,", len(plans), "plans")

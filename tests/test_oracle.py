@@ -310,3 +310,24 @@ def test_reference_build_live(oracle):
         for rank in range(NN):
             assert oracle.div_assignment(NN, rank, NAF) == oracle.ref_assignment(False, NN, rank, NAF)[:3]
             assert oracle.mod_assignment(NN, rank, NAF) == oracle.ref_assignment(True, NN, rank, NAF)[:3]
+
+
+def test_decomposition_pinned_to_reference_build(oracle):
+    """penalties and plans recorded from the reference's own src/decomposition/decomposition_plan.cpp (oracle/_ref build):
+    the oracle's restatement and the PRODUCT's DecompositionPlan (csrc/host/sassena_host.cpp) reproduce partitions, partition
+    size and penalty for the automatic search and for manual partition sizes"""
+    from sassena_b200 import host
+    g = _ref_golden()
+    for NN, NQ, NAF, NNpP, pen in g["penalties"]:
+        assert oracle.decomposition_penalty(int(NN), int(NQ), int(NAF), int(NNpP)) == pen
+    nauto = 0
+    for NN, NQ, NAF, el, maxb, automatic, manual, part, psize, pen, colsum in g["plans"]:
+        got = host.decomposition_plan(int(NN), int(NQ), int(NAF), int(el), int(maxb), 0.0, bool(automatic), int(manual))
+        assert got == (part, psize, pen), (NN, NQ, NAF, maxb, automatic, manual)
+        # colors = rank / partition size (decomposition_plan.cpp:163-184)
+        assert int(((np.arange(NN) // psize) * (np.arange(NN) + 1)).sum()) == colsum
+        if automatic:
+            rc, opart, opsize, open_ = oracle.decomposition_plan(int(NN), int(NQ), int(NAF), int(el), int(maxb), 0.0)
+            assert (rc, opart, opsize, open_) == (0, part, psize, pen)
+            nauto += 1
+    assert nauto > 100
