@@ -491,3 +491,14 @@ def ref_decomposition_plan(nn, nq, naf, elbytes, maxbytes, automatic=True, manua
                                      C.c_int(1 if automatic else 0), C.c_size_t(manual_size), C.c_double(utilization),
                                      C.byref(p), C.byref(ps), C.byref(pen), col.ctypes.data_as(C.POINTER(C.c_size_t)))
     return p.value, ps.value, pen.value, col.astype(np.int64)
+
+
+def ref_dcd_write(path, xyz, split=None):
+    """the reference's DCDCoordinateWriter (coordinate_writer.cpp): float [blocks][entries][3] -> DCD file; `split`: written
+    in two pieces (blocks [split, n) first), the way two ranks of a partition write it"""
+    a = np.ascontiguousarray(xyz, dtype=np.float32)
+    p = a.ctypes.data_as(C.POINTER(C.c_float))
+    if split is None:
+        ref_lib().ref_dcd_write(str(path).encode(), p, C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]))
+    else:
+        ref_lib().ref_dcd_write_split(str(path).encode(), p, C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]), C.c_size_t(split))

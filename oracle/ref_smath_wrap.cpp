@@ -119,3 +119,26 @@ void ref_decomposition_plan(size_t nn, size_t nq, size_t naf, size_t elbytes, si
     for (size_t i = 0; i < c.size(); i++) colors[i] = c[i];
 }
 }
+
+// ---- the reference's own src/stager/coordinate_writer.cpp (DCD layout of stager.dump) ------------------------------------------
+#include "stager/coordinate_writer.hpp"
+
+extern "C" {
+// DCDCoordinateWriter(file, blocks, entries): init(); prepare(); write(data, 0, blocks)      coordinate_writer.cpp:30-144
+// data: float [blocks][entries][3] (coor_t = float)
+void ref_dcd_write(const char *path, float *data, size_t blocks, size_t entries) {
+    DCDCoordinateWriter w(path, blocks, entries);
+    w.init();
+    w.prepare();
+    w.write(data, 0, blocks);
+}
+// the same file written in two pieces the way a 2-rank partition does (data_stager.cpp:148-160): blocks [0, split) and [split, blocks)
+void ref_dcd_write_split(const char *path, float *data, size_t blocks, size_t entries, size_t split) {
+    DCDCoordinateWriter w0(path, blocks, entries), w1(path, blocks, entries);
+    w0.init();
+    w0.prepare();
+    w1.prepare();
+    w1.write(data + split * entries * 3, split, blocks - split);
+    w0.write(data, 0, split);
+}
+}

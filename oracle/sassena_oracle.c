@@ -13,6 +13,7 @@
  *   src/math/coor3d.cpp           (cart -> spherical / cylindrical, the base) orc_cart_to_*, orc_vector_base
  *   src/decomposition/assignment.cpp (Div / ModAssignment)                    orc_div/mod_assignment
  *   src/decomposition/decomposition_plan.cpp (penalty, partition search)      orc_decomposition_*
+ *   src/stager/coordinate_writer.cpp (DCD writer; pins the product's DCD writer and reader)
  *   vendor/xdrfile-1.1.1          (XTC / TRR codec; pins the product's readers)
  * (oracle/Makefile target `ref`, shims in oracle/shim, fixtures tests/golden/ref_smath.npz).
  * The amplitude loops, the store/normalise steps and the multipole special functions remain

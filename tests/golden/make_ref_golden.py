@@ -1,5 +1,6 @@
 """Golden vectors produced by the REFERENCE's own code: oracle/_ref/libsmath_ref.so is the reference's src/math/smath.cpp,
-src/math/coor3d.cpp, src/decomposition/assignment.cpp and src/decomposition/decomposition_plan.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
+src/math/coor3d.cpp, src/decomposition/assignment.cpp, src/decomposition/decomposition_plan.cpp and
+src/stager/coordinate_writer.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
 Run in the build container (needs /root/reference); writes tests/golden/ref_smath.npz, which travels with the repo and
 pins the oracle's restatements on machines without the reference (tests/test_oracle.py::test_oracle_pinned_to_reference_build).
 
@@ -73,5 +74,10 @@ for NN in (1, 2, 3, 4, 8, 16, 64):
                 rp, rps, rpen, col = o.ref_decomposition_plan(NN, NQ, NAF, 12, 10 ** 12, False, manual, 0.0)
                 plans.append((NN, NQ, NAF, 12, 10 ** 12, 0, manual, rp, rps, rpen, int((col * (np.arange(NN) + 1)).sum())))
 out["plans"] = np.array(plans, dtype=np.int64)
+# a DCD file out of the reference's own DCDCoordinateWriter (src/stager/coordinate_writer.cpp), written in two pieces
+from sassena_b200 import synth  # noqa: E402
+dcd_xyz = synth.trajectory(7, 13, 20.0, 0.3, 5)
+out["dcd_xyz"] = dcd_xyz
+o.ref_dcd_write(os.path.join(ROOT, "tests", "golden", "ref_writer.dcd"), dcd_xyz, split=3)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_smath.npz"), **out)
 print("wrote tests/golden/ref_smath.npz:", len(out), "arrays,", len(rows), "assignment rows,", len(pen), "penalties,", len(plans), "plans")

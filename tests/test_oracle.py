@@ -331,3 +331,28 @@ def test_decomposition_pinned_to_reference_build(oracle):
             assert (rc, opart, opsize, open_) == (0, part, psize, pen)
             nauto += 1
     assert nauto > 100
+
+
+def test_dcd_layout_pinned_to_reference_writer(tmp_path, oracle):
+    """tests/golden/ref_writer.dcd was written by the reference's own DCDCoordinateWriter (src/stager/coordinate_writer.cpp,
+    oracle/_ref build; two pieces, as two ranks of a partition write it).  The product's DCD writer reproduces the file
+    byte for byte and its reader returns the coordinates that went in."""
+    from sassena_b200 import host
+    g = _ref_golden()
+    xyz = g["dcd_xyz"]
+    ref_bytes = open(os.path.join(GOLD, "ref_writer.dcd"), "rb").read()
+    mine = str(tmp_path / "mine.dcd")
+    host.write_dcd(mine, xyz)
+    assert open(mine, "rb").read() == ref_bytes
+    f = host.DCDFile(os.path.join(GOLD, "ref_writer.dcd"))
+    assert (f.number_of_frames, f.number_of_atoms) == xyz.shape[:2]
+    assert np.array_equal(f.read(), xyz)
+    if oracle.have_ref_smath():  # live: other shapes
+        rng = np.random.default_rng(11)
+        for NF, NA in ((1, 1), (3, 50), (40, 7)):
+            a = rng.normal(size=(NF, NA, 3)).astype(np.float32) * 20
+            p = str(tmp_path / f"ref_{NF}_{NA}.dcd")
+            oracle.ref_dcd_write(p, a)
+            host.write_dcd(mine, a)
+            assert open(mine, "rb").read() == open(p, "rb").read()
+            assert np.array_equal(host.DCDFile(p).read(), a)
