@@ -108,6 +108,11 @@ int sass_scatter_run(const sass_params *p, const sass_comm_vtbl *comm, const sas
                      char *timers, size_t timers_cap);
 
 /* ---- host logic, unit-testable ---------------------------------------------------------------------------------- */
+/* sample.motions walkers (reference src/sample/motion_walker.cpp, coordinate_sets.cpp:120-148): the 4x4 transform (row major,
+ * applied to row vectors (x, y, z, 1) * T) of frames 0 .. n-1.  type: "linear" | "fixed" | "oscillation" | "randomwalk" |
+ * "brownian" | "localbrownian" | "rotationalbrownian" */
+int sass_motion_transforms(const char *type, double displace, double frequency, double radius, unsigned long seed, long sampling,
+                           const double dir[3], size_t n, double *out /* [n][16] */);
 int sass_div_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max);
 int sass_mod_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max);
 int sass_decomposition_plan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize, double utilization,

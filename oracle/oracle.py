@@ -502,3 +502,16 @@ def ref_dcd_write(path, xyz, split=None):
         ref_lib().ref_dcd_write(str(path).encode(), p, C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]))
     else:
         ref_lib().ref_dcd_write_split(str(path).encode(), p, C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]), C.c_size_t(split))
+
+
+_WALKERS = {"linear": 0, "fixed": 1, "oscillation": 2, "randomwalk": 3, "brownian": 4, "localbrownian": 5, "rotationalbrownian": 6}
+
+
+def ref_motion_transforms(kind, n, displace=0.0, frequency=0.001, radius=0.0, seed=0, sampling=1, direction=(1, 0, 0)):
+    """the reference's own motion walkers (src/sample/motion_walker.cpp over the uBLAS / Boost.Random shims): [n][4][4]"""
+    d = _f64(np.asarray(direction, dtype=np.float64))
+    out = np.zeros((n, 4, 4))
+    rc = ref_lib().ref_motion_transforms(C.c_int(_WALKERS[kind]), C.c_double(displace), C.c_double(frequency), C.c_double(radius),
+                                         C.c_ulong(seed), C.c_long(sampling), _p(d, C.c_double), C.c_size_t(n), _p(out, C.c_double))
+    assert rc == 0
+    return out

@@ -142,3 +142,33 @@ void ref_dcd_write_split(const char *path, float *data, size_t blocks, size_t en
     w0.write(data, 0, split);
 }
 }
+
+// ---- the reference's own src/sample/motion_walker.cpp (over the uBLAS / Boost.Random shims) -----------------------------------
+#include "sample/motion_walker.hpp"
+
+extern "C" {
+// transform(t) of a walker for t = 0 .. n-1: out[t] = the 4x4 matrix, row major.  type: 0 linear, 1 fixed, 2 oscillation,
+// 3 randomwalk, 4 brownian, 5 localbrownian, 6 rotationalbrownian (coordinate_sets.cpp:120-148 picks them by name)
+int ref_motion_transforms(int type, double displace, double frequency, double radius, unsigned long seed, long sampling,
+                          const double dir[3], size_t n, double *out) {
+    CartesianCoor3D d(dir[0], dir[1], dir[2]);
+    MotionWalker *w = NULL;
+    switch (type) {
+        case 0: w = new LinearMotionWalker(displace, sampling, d); break;
+        case 1: w = new FixedMotionWalker(displace, d); break;
+        case 2: w = new OscillationMotionWalker(displace, frequency, sampling, d); break;
+        case 3: w = new RandomMotionWalker(displace, seed, sampling, d); break;
+        case 4: w = new BrownianMotionWalker(displace, seed, sampling, d); break;
+        case 5: w = new LocalBrownianMotionWalker(radius, displace, seed, sampling, d); break;
+        case 6: w = new RotationalBrownianMotionWalker(displace, seed, sampling); break;
+        default: return 1;
+    }
+    for (size_t t = 0; t < n; t++) {
+        boost::numeric::ublas::matrix<double> T = w->transform(t);
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) out[16 * t + 4 * i + j] = T(i, j);
+    }
+    delete w;
+    return 0;
+}
+}

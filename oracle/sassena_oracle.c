@@ -14,6 +14,7 @@
  *   src/decomposition/assignment.cpp (Div / ModAssignment)                    orc_div/mod_assignment
  *   src/decomposition/decomposition_plan.cpp (penalty, partition search)      orc_decomposition_*
  *   src/stager/coordinate_writer.cpp (DCD writer; pins the product's DCD writer and reader)
+ *   src/sample/motion_walker.cpp  (sample.motions walkers; pins the product's)
  *   vendor/xdrfile-1.1.1          (XTC / TRR codec; pins the product's readers)
  * (oracle/Makefile target `ref`, shims in oracle/shim, fixtures tests/golden/ref_smath.npz).
  * The amplitude loops, the store/normalise steps and the multipole special functions remain

@@ -1,1 +1,48 @@
-/* boost/numeric/ublas/matrix.hpp — empty SHIM: included by the reference's decomposition_plan.hpp, nothing of it is used by the code built here */
+/* boost/numeric/ublas/matrix.hpp — minimal SHIM of the uBLAS dense matrix for the reference's src/sample/motion_walker.cpp:
+ * matrix<T>(r, c) with (i, j) access, identity_matrix<T>, prod(matrix, matrix) (inner sum in index order, as uBLAS does).
+ * decomposition_plan.hpp includes the header without using it. */
+#ifndef ORACLE_SHIM_UBLAS_MATRIX_HPP
+#define ORACLE_SHIM_UBLAS_MATRIX_HPP
+#include <cstddef>
+#include <vector>
+namespace boost { namespace numeric { namespace ublas {
+template <class T>
+class identity_matrix {
+    std::size_t n_;
+   public:
+    explicit identity_matrix(std::size_t n) : n_(n) {}
+    identity_matrix(std::size_t n, std::size_t) : n_(n) {}
+    std::size_t size1() const { return n_; }
+};
+template <class T>
+class matrix {
+    std::size_t r_, c_;
+    std::vector<T> d_;
+   public:
+    matrix() : r_(0), c_(0) {}
+    matrix(std::size_t r, std::size_t c) : r_(r), c_(c), d_(r * c) {}
+    matrix(const identity_matrix<T> &I) { *this = I; }
+    matrix &operator=(const identity_matrix<T> &I) {
+        r_ = c_ = I.size1();
+        d_.assign(r_ * c_, T(0));
+        for (std::size_t i = 0; i < r_; i++) d_[i * c_ + i] = T(1);
+        return *this;
+    }
+    T &operator()(std::size_t i, std::size_t j) { return d_[i * c_ + j]; }
+    const T &operator()(std::size_t i, std::size_t j) const { return d_[i * c_ + j]; }
+    std::size_t size1() const { return r_; }
+    std::size_t size2() const { return c_; }
+};
+template <class T>
+matrix<T> prod(const matrix<T> &a, const matrix<T> &b) {
+    matrix<T> c(a.size1(), b.size2());
+    for (std::size_t i = 0; i < a.size1(); i++)
+        for (std::size_t j = 0; j < b.size2(); j++) {
+            T t = T(0);
+            for (std::size_t k = 0; k < a.size2(); k++) t += a(i, k) * b(k, j);
+            c(i, j) = t;
+        }
+    return c;
+}
+}}}  // namespace boost::numeric::ublas
+#endif

@@ -1,0 +1,1 @@
+/* boost/serialization/string.hpp — empty SHIM: the reference's serialize() templates are never instantiated in the code built here */

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sass_scatter_run": (C.c_int, [C.c_void_p, C.POINTER(CommVtbl), C.POINTER(BackendVtbl), C.c_void_p, C.c_size_t,
                                    C.c_size_t, C.c_void_p, c_double_p, FACTORS_FN, C.c_void_p, c_double_p, C.c_size_t,
                                    WRITE_FN, C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
+    "sass_motion_transforms": (C.c_int, [C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_ulong, C.c_long,
+                                         C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double)]),
     "sass_div_assignment": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_size_p, c_size_p, c_size_p]),
     "sass_mod_assignment": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_size_p, c_size_p, c_size_p]),
     "sass_decomposition_plan": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double,

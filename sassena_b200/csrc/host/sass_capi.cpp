@@ -214,6 +214,23 @@ int sass_scatter_run(const sass_params *p, const sass_comm_vtbl *comm, const sas
     });
 }
 
+int sass_motion_transforms(const char *type, double displace, double frequency, double radius, unsigned long seed, long sampling,
+                           const double dir[3], size_t n, double *out) {
+    return guard([&] {
+        SampleMotionParameters m;
+        m.type = type;
+        m.displace = displace;
+        m.frequency = frequency;
+        m.radius = radius;
+        m.seed = seed;
+        m.sampling = sampling;
+        m.direction = CartesianCoor3D(dir[0], dir[1], dir[2]);
+        std::unique_ptr<MotionWalker> w(MotionWalker::create(m));
+        if (!w) throw Error("Motion type none has no walker");
+        for (size_t t = 0; t < n; t++) w->transform(t, out + 16 * t);
+    });
+}
+
 int sass_div_assignment(size_t NN, size_t rank, size_t NAF, size_t *offset, size_t *size, size_t *max) {
     return guard([&] {
         DivAssignment a(NN, rank, NAF);

@@ -41,6 +41,15 @@ def _dp(a):
 # ---------------------------------------------------------------------------------------------------------------
 # host logic
 # ---------------------------------------------------------------------------------------------------------------
+def motion_transforms(kind, n, displace=0.0, frequency=0.001, radius=0.0, seed=0, sampling=1, direction=(1, 0, 0)):
+    """4x4 transforms (row vectors: (x, y, z, 1) @ T) of frames 0..n-1 of a sample.motions walker (motion_walker.cpp)."""
+    d = np.ascontiguousarray(direction, dtype=np.float64)
+    out = np.zeros((n, 4, 4))
+    _ck(_lib().sass_motion_transforms(kind.encode(), float(displace), float(frequency), float(radius), int(seed), int(sampling),
+                                      _dp(d), n, _dp(out)))
+    return out
+
+
 def div_assignment(NN, rank, NAF):
     o, s, m = C.c_size_t(), C.c_size_t(), C.c_size_t()
     _ck(_lib().sass_div_assignment(NN, rank, NAF, C.byref(o), C.byref(s), C.byref(m)))

@@ -1,6 +1,6 @@
 """Golden vectors produced by the REFERENCE's own code: oracle/_ref/libsmath_ref.so is the reference's src/math/smath.cpp,
-src/math/coor3d.cpp, src/decomposition/assignment.cpp, src/decomposition/decomposition_plan.cpp and
-src/stager/coordinate_writer.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
+src/math/coor3d.cpp, src/decomposition/assignment.cpp, src/decomposition/decomposition_plan.cpp,
+src/stager/coordinate_writer.cpp and src/sample/motion_walker.cpp compiled where they lie (make -C oracle ref, shims in oracle/shim).
 Run in the build container (needs /root/reference); writes tests/golden/ref_smath.npz, which travels with the repo and
 pins the oracle's restatements on machines without the reference (tests/test_oracle.py::test_oracle_pinned_to_reference_build).
 
@@ -79,5 +79,13 @@ from sassena_b200 import synth  # noqa: E402
 dcd_xyz = synth.trajectory(7, 13, 20.0, 0.3, 5)
 out["dcd_xyz"] = dcd_xyz
 o.ref_dcd_write(os.path.join(ROOT, "tests", "golden", "ref_writer.dcd"), dcd_xyz, split=3)
+# motion walkers: the reference's own src/sample/motion_walker.cpp over the uBLAS / Boost.Random shims (the random streams are
+# the shims' Boost-1.4x restatement; what is pinned is how the walkers consume and accumulate them)
+WALK = [dict(displace=0.37, frequency=0.013, radius=1.5, seed=7, sampling=3, direction=(1.0, 2.0, -2.0)),
+        dict(displace=2.0, frequency=0.25, radius=20.0, seed=12345, sampling=1, direction=(0.0, 0.0, 1.0))]
+for kind in ("linear", "fixed", "oscillation", "randomwalk", "brownian", "localbrownian", "rotationalbrownian"):
+    for i, kw in enumerate(WALK):
+        out[f"walk_{kind}_{i}"] = o.ref_motion_transforms(kind, 60, **kw)
+out["walk_params"] = np.array([[k["displace"], k["frequency"], k["radius"], k["seed"], k["sampling"], *k["direction"]] for k in WALK])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_smath.npz"), **out)
 print("wrote tests/golden/ref_smath.npz:", len(out), "arrays,", len(rows), "assignment rows,", len(pen), "penalties,", len(plans), "plans")

@@ -313,3 +313,30 @@ def test_motion_continues_over_clones_and_runs_through_the_hot_path(tmp_path, or
     want = oracle.compute_all_vectors(fr, b, np.array([[0.7, 0.0, 0.0]]), nthreads=2)[0]
     got = fqt[0, :, 0] + 1j * fqt[0, :, 1]
     assert np.max(np.abs(got - want)) < 1e-9 * np.max(np.abs(want))
+
+
+KINDS = ("linear", "fixed", "oscillation", "randomwalk", "brownian", "localbrownian", "rotationalbrownian")
+
+
+def test_walkers_pinned_to_reference_build(oracle):
+    """tests/golden/ref_smath.npz holds the 4x4 transforms of the reference's own walkers (src/sample/motion_walker.cpp compiled
+    where it lies over the uBLAS / Boost.Random shims, oracle/_ref build).  The product's walkers reproduce them bit for bit:
+    translation vectors, the sampling discards, the cumulative sums, the redraw loop of localbrownian, the rotation products.
+    (The random streams themselves are the shims' Boost-1.4x restatement -- the same one the product uses -- so the streams are
+    not pinned, their use is.)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_smath.npz"))
+    for i, row in enumerate(g["walk_params"]):
+        kw = dict(displace=row[0], frequency=row[1], radius=row[2], seed=int(row[3]), sampling=int(row[4]), direction=tuple(row[5:8]))
+        for kind in KINDS:
+            want = g[f"walk_{kind}_{i}"]
+            got = host.motion_transforms(kind, len(want), **kw)
+            assert np.array_equal(got, want), (kind, i)
+    if oracle.have_ref_smath():  # live: other parameters
+        for kind in KINDS:
+            kw = dict(displace=0.9, frequency=0.07, radius=4.0, seed=99, sampling=2, direction=(-1.0, 0.5, 0.25))
+            assert np.array_equal(host.motion_transforms(kind, 25, **kw), oracle.ref_motion_transforms(kind, 25, **kw)), kind
+    with pytest.raises(host.HostError, match="Motion type not understood"):
+        host.motion_transforms("wobble", 3)
+    with pytest.raises(host.HostError, match="radius size for local brownian"):
+        host.motion_transforms("localbrownian", 3, displace=2.0, radius=1.0)
