@@ -515,3 +515,25 @@ def ref_motion_transforms(kind, n, displace=0.0, frequency=0.001, radius=0.0, se
                                          C.c_ulong(seed), C.c_long(sampling), _p(d, C.c_double), C.c_size_t(n), _p(out, C.c_double))
     assert rc == 0
     return out
+
+
+def ref_scatter_run(kind, frames, b, qvectors, orient=None, vectors_type="file", axis=(0, 0, 1), dsp="autocorrelate", method="fftw",
+                    threads=1):
+    """the REFERENCE's own AllVectorsScatterDevice ("all") / SelfVectorsScatterDevice ("self") for one rank (oracle/_ref build over
+    the shims).  frames float32 [NF][NA][3]; orient: unit vectors [NM][3] or None.  Returns (qvectors written, fqt, fq, fq2)."""
+    fr = _f32(frames)
+    NF, NA, _ = fr.shape
+    bb = _f64(b)
+    qv = _f64(qvectors).reshape(-1, 3)
+    NQ = len(qv)
+    ori = np.zeros((0, 3)) if orient is None else _f64(orient).reshape(-1, 3)
+    ax = _f64(np.asarray(axis, dtype=np.float64))
+    fqt, fq, fq2, qout = np.zeros((NQ, NF, 2)), np.zeros((NQ, 2)), np.zeros((NQ, 2)), np.zeros((NQ, 3))
+    f = ref_lib().ref_scatter_run
+    f.restype = C.c_size_t
+    n = f(C.c_int(0 if kind == "all" else 1), _p(fr, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(bb, C.c_double),
+          _p(qv, C.c_double), C.c_size_t(NQ), vectors_type.encode(), _p(ori, C.c_double), C.c_size_t(len(ori)), _p(ax, C.c_double),
+          dsp.encode(), method.encode(), C.c_size_t(threads), _p(fqt, C.c_double), _p(fq, C.c_double), _p(fq2, C.c_double),
+          _p(qout, C.c_double))
+    assert n == NQ
+    return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]

@@ -6,6 +6,7 @@
 #include <cstddef>
 #include <vector>
 namespace boost { namespace numeric { namespace ublas {
+namespace detail {}  /* (all_vectors_scatter_device.cpp has a using-directive for it) */
 template <class T>
 class identity_matrix {
     std::size_t n_;

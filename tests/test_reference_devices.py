@@ -1,0 +1,91 @@
+"""Parity against the REFERENCE's OWN scatter devices.  tests/golden/ref_devices.npz holds fqt / fq / fq2 written by the
+reference's AllVectorsScatterDevice and SelfVectorsScatterDevice — its own amplitude loops, stagers, alignpad, DSP (smath.cpp),
+store, final scaling, init_subvectors (file / sphere / cylinder / no averaging) — compiled where they lie for one MPI rank over
+the shims in oracle/shim (tests/golden/make_ref_devices_golden.py).
+
+* CPU: the oracle reproduces every case BIT FOR BIT (so the oracle IS the reference's arithmetic for these devices);
+* GPU: the CUDA path, through the C-ABI, agrees with the reference's own output within the north-star tolerance 1e-9;
+* where oracle/_ref exists, fresh inputs go through the reference devices live."""
+import os
+
+import numpy as np
+import pytest
+
+import sassena_b200
+from sassena_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_devices.npz")
+TOL = 1e-9
+
+
+def _subvectors(oracle, g, vt, q):
+    if vt == "none":
+        return np.array([q])
+    if vt == "cylinder":
+        return oracle.init_subvectors("cylinder", q, orient=g["cyl"], axis=g["axis"])
+    return oracle.init_subvectors("sphere", q, orient=g["u"])  # file and sphere: |q| * unit vector
+
+
+def test_oracle_reproduces_reference_devices_bit_for_bit(oracle):
+    g = np.load(GOLD)
+    xyz, b = g["xyz"], g["b"]
+    xa = np.ascontiguousarray(xyz.transpose(1, 0, 2))
+    for k, (kind, vt, dsp, method) in enumerate(g["cases"]):
+        for i, q in enumerate(g["qv"]):
+            sub = _subvectors(oracle, g, vt, q)
+            if kind == "all":
+                fqt, fq, fq2 = oracle.compute_all_vectors(xyz, b, sub, dsp=dsp, method=method)
+            else:
+                fqt, fq, fq2 = oracle.compute_self_vectors(xa, b, sub, dsp=dsp, method=method)
+            assert np.array_equal(fqt, g[f"case{k}_fqt"][i]), (kind, vt, dsp, method, i)
+            assert fq == g[f"case{k}_fq"][i] and fq2 == g[f"case{k}_fq2"][i], (kind, vt, dsp, method, i)
+
+
+def test_reference_devices_live(oracle):
+    if not oracle.have_ref_smath():
+        pytest.skip("oracle/_ref/libsmath_ref.so not built (no /root/reference on this machine)")
+    NF, NA = 19, 31
+    xyz = synth.trajectory(NF, NA, 18.0, 0.4, 77)
+    b = synth.factors(NA)
+    u = synth.unit_vectors(5, 9)
+    qv = np.array([[1.1, -0.3, 0.2]])
+    for kind in ("all", "self"):
+        for threads in (1, 4):
+            q, fqt, fq, fq2 = oracle.ref_scatter_run(kind, xyz, b, qv, orient=u, vectors_type="sphere", threads=threads)
+            sub = np.linalg.norm(qv[0]) * u
+            if kind == "all":
+                r = oracle.compute_all_vectors(xyz, b, oracle.init_subvectors("sphere", qv[0], orient=u))
+            else:
+                r = oracle.compute_self_vectors(np.ascontiguousarray(xyz.transpose(1, 0, 2)), b,
+                                                oracle.init_subvectors("sphere", qv[0], orient=u))
+            assert np.array_equal(fqt[0], r[0]) and fq[0] == r[1] and fq2[0] == r[2], (kind, threads)
+            assert np.allclose(sub, oracle.init_subvectors("sphere", qv[0], orient=u), rtol=1e-15)
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_reference_devices(oracle):
+    """the product (CUDA kernels through the C-ABI) against the reference's own devices' output, every committed case"""
+    g = np.load(GOLD)
+    xyz, b = g["xyz"], g["b"]
+    xa = np.ascontiguousarray(xyz.transpose(1, 0, 2))
+    worst = 0.0
+    with sassena_b200.ScatterContext(0) as ctx:
+        for k, (kind, vt, dsp, method) in enumerate(g["cases"]):
+            if kind == "all":
+                ctx.stage_frames(xyz)
+            else:
+                ctx.stage_atoms(xa)
+            ctx.set_factors(b)
+            for i, q in enumerate(g["qv"]):
+                sub = _subvectors(oracle, g, vt, q)
+                if kind == "all":
+                    fqt, fq, fq2 = ctx.compute_all_vectors(sub, dsp=dsp, method=method)
+                else:
+                    fqt, fq, fq2 = ctx.compute_self_vectors(sub, dsp=dsp, method=method)
+                rfqt, rfq, rfq2 = g[f"case{k}_fqt"][i], g[f"case{k}_fq"][i], g[f"case{k}_fq2"][i]
+                scale = np.max(np.abs(rfqt))
+                e = np.max(np.abs(fqt - rfqt)) / scale
+                worst = max(worst, e)
+                assert e < TOL, (kind, vt, dsp, method, i, e)
+                assert abs(fq - rfq) < TOL * scale and abs(fq2 - rfq2) <= TOL * max(abs(rfq2), 1e-300), (kind, vt, dsp, method, i)
+    print("worst fqt rel. err vs the reference's own devices:", worst)
