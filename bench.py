@@ -146,7 +146,17 @@ def cpu_sample_shape(cfg, cores, target_core_seconds, evals_per_core_s=2.4e7):
     return NF_s, NM_s
 
 
+def cpu_reference_kind():
+    """"reference": oracle/_ref/libsmath_ref.so (the reference's OWN scatter devices, stagers and DSP built for one rank over the
+    shims in oracle/shim; it travels with the repository snapshot) is there; "port": only the oracle restatement is."""
+    from oracle import oracle as o
+    return "reference" if o.have_ref_smath() else "port"
+
+
 def run_cpu_oracle(cfg, NF_s, NM_s, ql, threads, coords=None):
+    """coherent CPU leg on the bounded sample: the reference's own AllVectorsScatterDevice with `threads` worker threads
+    (limits.computation.threads) when its build is present -- timed by the reference's own "sd:runner" timer, i.e. compute + write
+    without staging -- else the oracle port with `threads` OpenMP threads"""
     from oracle import oracle as o
     from sassena_b200 import synth
     o.build()
@@ -154,11 +164,33 @@ def run_cpu_oracle(cfg, NF_s, NM_s, ql, threads, coords=None):
         coords = synth.trajectory(NF_s, cfg["NA"], cfg["box"], cfg["sigma"], cfg["seed"])
     b = synth.factors(cfg["NA"])
     u = synth.unit_vectors(cfg["NM"], cfg["vseed"])[:NM_s]
+    if cpu_reference_kind() == "reference":
+        _, fqt, fq, fq2 = o.ref_scatter_run("all", coords, b, [[ql, 0.0, 0.0]], orient=u, vectors_type="file", threads=threads)
+        return o.ref_timer_seconds("sd:runner"), (fqt[0], fq[0], fq2[0]), coords
     q = ql * u
     t0 = time.perf_counter()
     res = o.compute_all_vectors(coords, b, q, nthreads=threads)
     dt = time.perf_counter() - t0
     return dt, res, coords
+
+
+def run_cpu_self(xa, b, q_unit, ql, threads):
+    """self CPU leg: the oracle port with `threads` OpenMP threads over atoms -- the reference's rank parallelism (ModAssignment
+    over MPI ranks).  The reference's own SelfVectorsScatterDevice builds too (oracle/_ref) and the port reproduces it bit for
+    bit (tests/test_reference_devices.py), but inside one rank it runs the per-timeline FFT autocorrelation serially on the main
+    thread, and in that build the FFT behind FFTW's API is the oracle's DFT: timing it would not be the reference with FFTW.
+    xa float32 [NA_s][NF][3] atom-major"""
+    from oracle import oracle as o
+    t0 = time.perf_counter()
+    res = o.compute_self_vectors(xa, b, ql * q_unit, nthreads=threads)
+    return time.perf_counter() - t0, res
+
+
+def cpu_sample_note(threads, kind=None):
+    if (kind or cpu_reference_kind()) == "reference":
+        return (f"the reference's own scatter device (oracle/_ref build, one rank, limits.computation.threads = {threads} worker "
+                "threads; its sd:runner timer: compute + write, staging excluded)")
+    return f"oracle port, {threads} OpenMP threads"
 
 
 def run_reference(args):
@@ -185,14 +217,14 @@ def run_reference(args):
     evals = float(cfg["NA"]) * NF_s * NM_s * len(times)
     value = evals / total
     sample = (f"{cfg['NA']} atoms x first {NF_s} frames x {NM_s} of {cfg['NM']} subvectors of one |q| per step "
-              f"(amplitudes + FFT autocorrelation + store), {cores} OpenMP threads over subvectors")
+              f"(amplitudes + FFT autocorrelation + store); " + cpu_sample_note(cores))
     line = {
         "impl": "reference", "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "NA": cfg["NA"], "NF": cfg["NF"], "NM": cfg["NM"],
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": cpu_reference_kind(), "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -411,8 +443,8 @@ def _run_ours(args, json_fd):
         ql = qls[nmid]
         dt, (rfqt, rfq, rfq2), _ = run_cpu_oracle(cfg, NF_s, NM_s, ql, cores, coords)
         sample = (f"{NA} atoms x first {NF_s} frames x {NM_s} of {NM} subvectors of one |q| "
-                  f"(amplitudes + FFT autocorrelation + store), {cores} OpenMP threads over subvectors")
-        cpu_baseline = {"value": float(NA) * NF_s * NM_s / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                  f"(amplitudes + FFT autocorrelation + store); " + cpu_sample_note(cores))
+        cpu_baseline = {"value": float(NA) * NF_s * NM_s / dt, "unit": "evals/s", "cores": cores, "kind": cpu_reference_kind(),
                         "sample": sample, "seconds": dt}
         ctx.stage_frames_device(xyz.data_ptr(), NF_s, NA)
         ctx.set_factors(b)
@@ -423,7 +455,8 @@ def _run_ours(args, json_fd):
             fqt, fq, _ = ctx.compute_all_vectors(ql * u[:NM_s])
         parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
                   "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9,
-                  "vs": f"oracle on the CPU sample, |q| index {nmid} of the scan"}
+                  "vs": ("the reference's own AllVectorsScatterDevice (oracle/_ref build)" if cpu_reference_kind() == "reference"
+                         else "oracle") + f" on the CPU sample, |q| index {nmid} of the scan"}
         stage_resident()
 
     if rank == 0:
@@ -535,14 +568,13 @@ def run_reference_self(args):
     u = synth.unit_vectors(cfg["NM"], cfg["vseed"])[:NM_s]
     times = []
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        o.compute_self_vectors(xa, b, qls[i % len(qls)] * u, nthreads=cores)
+        dt, _ = run_cpu_self(xa, b, u, qls[i % len(qls)], cores)
         if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
     total = sum(times)
     value = float(NA_s) * NF * NM_s * len(times) / total
     sample = (f"{NA_s} of {cfg['NA']} atoms x all {NF} frames x {NM_s} of {cfg['NM']} vectors of one |q| per step (amplitude "
-              f"timelines + FFT autocorrelation + store), {cores} OpenMP threads over atoms")
+              f"timelines + FFT autocorrelation + store); " + cpu_sample_note(cores, "port") + " over atoms")
     line = {
         "impl": "reference", "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
@@ -684,18 +716,18 @@ def _run_self(args, json_fd):
         NA_s, NM_s = self_cpu_sample(cfg, cores, args.cpu_seconds)
         ql = qls[len(qls) // 2]
         xa = np.ascontiguousarray(host.array[:NA_s])
-        t0 = time.perf_counter()
-        rfqt, rfq, rfq2 = o.compute_self_vectors(xa, b_all[:NA_s], ql * u[:NM_s], nthreads=cores)
-        dt = time.perf_counter() - t0
+        dt, (rfqt, rfq, rfq2) = run_cpu_self(xa, b_all[:NA_s], u[:NM_s], ql, cores)
         sample = (f"{NA_s} of {NA} atoms x all {NF} frames x {NM_s} of {NM} vectors of one |q| (amplitude timelines + FFT "
-                  f"autocorrelation + store), {cores} OpenMP threads over atoms")
+                  f"autocorrelation + store); " + cpu_sample_note(cores, "port") + " over atoms")
         cpu_baseline = {"value": float(NA_s) * NF * NM_s / dt, "unit": "evals/s", "cores": cores, "kind": "port",
                         "sample": sample, "seconds": dt}
         ctx.stage_atoms(xa)
         ctx.set_factors(b_all[:NA_s])
         fqt, fq, _ = ctx.compute_self_vectors(ql * u[:NM_s])
         parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
-                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9, "vs": "oracle on the CPU sample"}
+                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9,
+                  "vs": "oracle on the CPU sample (the oracle reproduces the reference's own SelfVectorsScatterDevice bit for bit, "
+                        "tests/test_reference_devices.py)"}
 
     if rank == 0:
         kern_s = amp_ms_max * 1e-3

@@ -537,3 +537,10 @@ def ref_scatter_run(kind, frames, b, qvectors, orient=None, vectors_type="file",
           _p(qout, C.c_double))
     assert n == NQ
     return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
+
+
+def ref_timer_seconds(key):
+    """seconds the last ref_scatter_run spent under one of the reference's timer keys ("sd:stage", "sd:runner", "sd:compute", ...)"""
+    f = ref_lib().ref_timer_seconds
+    f.restype = C.c_double
+    return f(key.encode())

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "control.hpp"
+#include "report/timer.hpp"
 #include "sample.hpp"
 #include "scatter_devices/all_vectors_scatter_device.hpp"
 #include "scatter_devices/self_vectors_scatter_device.hpp"
@@ -66,6 +67,10 @@ size_t ref_scatter_run(int kind, const float *frames, size_t NF, size_t NA, cons
     sample.atoms.selections["system"] = &system;
     sample.coordinate_sets.shim_set(frames, NF, NA, p->scattering.average.orientation.axis);
 
+    {
+        std::lock_guard<std::mutex> l(ShimTimerTable::Inst().m);
+        ShimTimerTable::Inst().sum.clear();
+    }
     Factors fac = {b};
     ShimFactorSource::Inst().cb = on_factors;
     ShimFactorSource::Inst().user = &fac;
@@ -87,5 +92,12 @@ size_t ref_scatter_run(int kind, const float *frames, size_t NF, size_t NA, cons
     ShimWriterSink::Inst().cb = nullptr;
     ShimFactorSource::Inst().cb = nullptr;
     return out.count;
+}
+
+// wall-clock seconds the last ref_scatter_run spent under a timer key of the reference ("sd:stage", "sd:runner", "sd:compute", ...)
+double ref_timer_seconds(const char *key) {
+    std::lock_guard<std::mutex> l(ShimTimerTable::Inst().m);
+    std::map<std::string, double>::iterator it = ShimTimerTable::Inst().sum.find(key);
+    return it == ShimTimerTable::Inst().sum.end() ? 0.0 : it->second;
 }
 }

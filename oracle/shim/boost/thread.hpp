@@ -14,6 +14,13 @@ struct thread_interrupted {};
 namespace shim_detail {
 struct tstate {
     std::atomic<bool> interrupt{false};
+    std::mutex m;                                 // guards `waiting`
+    std::condition_variable *waiting = nullptr;   // the condition variable this thread is blocked on, if any
+    void request() {
+        interrupt = true;
+        std::lock_guard<std::mutex> l(m);
+        if (waiting) waiting->notify_all();
+    }
 };
 inline tstate *&current() {
     static thread_local tstate *p = nullptr;
@@ -21,6 +28,21 @@ inline tstate *&current() {
 }
 inline void interruption_point() {
     if (current() && current()->interrupt.load()) throw thread_interrupted();
+}
+// blocks on cv (woken by notify; a 20 ms timeout only covers the window in which an interrupt request could be missed)
+inline void interruptible_wait(std::condition_variable &cv, std::unique_lock<std::mutex> &l) {
+    interruption_point();
+    tstate *st = current();
+    if (st) {
+        std::lock_guard<std::mutex> g(st->m);
+        st->waiting = &cv;
+    }
+    cv.wait_for(l, std::chrono::milliseconds(20));
+    if (st) {
+        std::lock_guard<std::mutex> g(st->m);
+        st->waiting = nullptr;
+    }
+    interruption_point();
 }
 }  // namespace shim_detail
 using std::bind;
@@ -43,11 +65,8 @@ class condition_variable {
    public:
     void notify_all() { cv_.notify_all(); }
     void notify_one() { cv_.notify_one(); }
-    void wait(mutex::scoped_lock &l) {  // an interruption point; may wake spuriously (callers loop on their predicate)
-        shim_detail::interruption_point();
-        cv_.wait_for(l.l_, std::chrono::milliseconds(1));
-        shim_detail::interruption_point();
-    }
+    // an interruption point; may wake spuriously (callers loop on their predicate)
+    void wait(mutex::scoped_lock &l) { shim_detail::interruptible_wait(cv_, l.l_); }
 };
 class barrier {
     std::mutex m_;
@@ -64,10 +83,7 @@ class barrier {
             cv_.notify_all();
             return true;
         }
-        while (gen == generation_) {
-            shim_detail::interruption_point();
-            cv_.wait_for(l, std::chrono::milliseconds(1));
-        }
+        while (gen == generation_) shim_detail::interruptible_wait(cv_, l);
         return false;
     }
 };
@@ -89,11 +105,11 @@ class thread {
     }
     ~thread() {  // (Boost detaches; here the interrupted worker is joined so that nothing outlives the device)
         if (t_.joinable()) {
-            st_->interrupt = true;
+            st_->request();
             t_.join();
         }
     }
-    void interrupt() { st_->interrupt = true; }
+    void interrupt() { st_->request(); }
     void join() { if (t_.joinable()) t_.join(); }
     id get_id() const { return t_.get_id(); }
 };
