@@ -5,21 +5,18 @@
  * this file.  It is the checker used by tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.
  *
- * PARITY PARTLY PINNED: the reference (benlabs/sassena v1.4.2) ships no golden vectors or
- * asserting tests for this path (tests/unit_broadcast.cpp asserts nothing) and its scatter
- * devices cannot be built in this image (Boost, FFTW3, MPI, HDF5, libxml2 are all absent).
- * What CAN be built from the reference's own sources is, and pins the matching functions here:
- *   src/math/smath.cpp            (direct + FFT autocorrelation, square)      orc_auto_correlate_*, dsp
- *   src/math/coor3d.cpp           (cart -> spherical / cylindrical, the base) orc_cart_to_*, orc_vector_base
- *   src/decomposition/assignment.cpp (Div / ModAssignment)                    orc_div/mod_assignment
- *   src/decomposition/decomposition_plan.cpp (penalty, partition search)      orc_decomposition_*
- *   src/stager/coordinate_writer.cpp (DCD writer; pins the product's DCD writer and reader)
- *   src/sample/motion_walker.cpp  (sample.motions walkers; pins the product's)
- *   vendor/xdrfile-1.1.1          (XTC / TRR codec; pins the product's readers)
- * (oracle/Makefile target `ref`, shims in oracle/shim, fixtures tests/golden/ref_smath.npz).
- * The amplitude loops, the store/normalise steps and the multipole special functions remain
- * UNPINNED by reference output: they follow the reference loops cited per function and are
- * pinned by analytic known-answer tests and numpy/scipy cross-checks (tests/test_oracle.py).
+ * PARITY PINNED TO THE REFERENCE'S OWN CODE for the coherent and self devices: the reference
+ * (benlabs/sassena v1.4.2) ships no golden vectors or asserting tests for this path and its
+ * build system cannot be used here (Boost, FFTW3, MPI, HDF5, libxml2 are absent), but its
+ * translation units compile where they lie over the shim headers in oracle/shim (make -C oracle
+ * ref -> oracle/_ref/libsmath_ref.so): AllVectorsScatterDevice, SelfVectorsScatterDevice with
+ * their abstract bases, the stagers, smath.cpp, coor3d.cpp, assignment.cpp, decomposition_plan.cpp,
+ * coordinate_writer.cpp, motion_walker.cpp.  orc_compute_all_vectors / orc_compute_self_vectors
+ * reproduce the reference devices' fqt / fq / fq2 BIT FOR BIT (tests/test_reference_devices.py,
+ * fixtures tests/golden/ref_devices.npz); the helper functions likewise (tests/test_oracle.py).
+ * UNPINNED by reference output: the multipole devices (they need Boost.Math), ScatterFactors /
+ * Database and the Boost.Random streams -- pinned by scipy cross-checks, closed forms and
+ * restated formulas.  vendor/xdrfile-1.1.1 pins the product's XTC / TRR readers.
  *
  * Third-party arithmetic that is not in /root/reference and is restated here:
  *   FFTW3 (unpinned version)         -> own mixed-radix / Bluestein complex FFT
