@@ -150,7 +150,10 @@ def cpu_reference_kind():
     """"reference": oracle/_ref/libsmath_ref.so (the reference's OWN scatter devices, stagers and DSP built for one rank over the
     shims in oracle/shim; it travels with the repository snapshot) is there; "port": only the oracle restatement is."""
     from oracle import oracle as o
-    return "reference" if o.have_ref_smath() else "port"
+    return "reference" if (o.have_ref_smath() and not _REF_BUILD_FAILED) else "port"
+
+
+_REF_BUILD_FAILED = False  # set when oracle/_ref is present but could not be loaded / run on this box: the port is timed, and says so
 
 
 def run_cpu_oracle(cfg, NF_s, NM_s, ql, threads, coords=None):
@@ -165,8 +168,13 @@ def run_cpu_oracle(cfg, NF_s, NM_s, ql, threads, coords=None):
     b = synth.factors(cfg["NA"])
     u = synth.unit_vectors(cfg["NM"], cfg["vseed"])[:NM_s]
     if cpu_reference_kind() == "reference":
-        _, fqt, fq, fq2 = o.ref_scatter_run("all", coords, b, [[ql, 0.0, 0.0]], orient=u, vectors_type="file", threads=threads)
-        return o.ref_timer_seconds("sd:runner"), (fqt[0], fq[0], fq2[0]), coords
+        try:
+            _, fqt, fq, fq2 = o.ref_scatter_run("all", coords, b, [[ql, 0.0, 0.0]], orient=u, vectors_type="file", threads=threads)
+            return o.ref_timer_seconds("sd:runner"), (fqt[0], fq[0], fq2[0]), coords
+        except (OSError, AttributeError, RuntimeError) as e:  # e.g. a stale .so from another toolchain
+            global _REF_BUILD_FAILED
+            _REF_BUILD_FAILED = True
+            print(f"bench: oracle/_ref present but unusable ({e!r}); timing the oracle port instead", file=sys.stderr)
     q = ql * u
     t0 = time.perf_counter()
     res = o.compute_all_vectors(coords, b, q, nthreads=threads)
