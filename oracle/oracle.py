@@ -539,6 +539,28 @@ def ref_scatter_run(kind, frames, b, qvectors, orient=None, vectors_type="file",
     return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
 
 
+def ref_multipole_run(kind, frames, b, qvectors, moments, axis=(0, 0, 1), dsp="autocorrelate", method="fftw", threads=1):
+    """the REFERENCE's own MPSphereScatterDevice ("sphere") / MPCylinderScatterDevice ("cylinder") for one rank (oracle/_ref build
+    over the shims; Boost.Math's sph_bessel / spherical_harmonic / cyl_bessel_j served by the oracle's restatements).  frames
+    float32 [NF][NA][3] CARTESIAN (the device asks its sample for the spherical / cylindrical representation); moments int
+    [NMOM][2].  Returns (qvectors written, fqt, fq, fq2)."""
+    fr = _f32(frames)
+    NF, NA, _ = fr.shape
+    bb = _f64(b)
+    qv = _f64(qvectors).reshape(-1, 3)
+    NQ = len(qv)
+    mom = np.ascontiguousarray(moments, dtype=np.int64).reshape(-1, 2)
+    ax = _f64(np.asarray(axis, dtype=np.float64))
+    fqt, fq, fq2, qout = np.zeros((NQ, NF, 2)), np.zeros((NQ, 2)), np.zeros((NQ, 2)), np.zeros((NQ, 3))
+    f = ref_lib().ref_multipole_run
+    f.restype = C.c_size_t
+    n = f(C.c_int(2 if kind == "sphere" else 3), _p(fr, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(bb, C.c_double),
+          _p(qv, C.c_double), C.c_size_t(NQ), _p(mom, C.c_long), C.c_size_t(len(mom)), _p(ax, C.c_double), dsp.encode(),
+          method.encode(), C.c_size_t(threads), _p(fqt, C.c_double), _p(fq, C.c_double), _p(fq2, C.c_double), _p(qout, C.c_double))
+    assert n == NQ
+    return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
+
+
 def ref_timer_seconds(key):
     """seconds the last ref_scatter_run spent under one of the reference's timer keys ("sd:stage", "sd:runner", "sd:compute", ...)"""
     f = ref_lib().ref_timer_seconds

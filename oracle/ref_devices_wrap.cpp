@@ -1,5 +1,5 @@
 // ref_devices_wrap.cpp — runs the REFERENCE's own scatter devices (src/scatter_devices/{abstract_scatter_device,
-// abstract_vectors_scatter_device,all_vectors_scatter_device,self_vectors_scatter_device}.cpp) with its own stagers
+// abstract_vectors_scatter_device,all_vectors_scatter_device,self_vectors_scatter_device,multipole_scatter_device}.cpp) with its own stagers
 // (src/stager/data_stager.cpp) and DSP (src/math/smath.cpp), compiled where they lie for ONE MPI rank over the shims in
 // oracle/shim (communicator, worker threads, Params values, Sample served from arrays, factors and result sink as callbacks,
 // FFTW3 API over the oracle's DFT).  Test infrastructure: pins the oracle's compute_all_vectors / compute_self_vectors —
@@ -13,6 +13,7 @@
 #include "report/timer.hpp"
 #include "sample.hpp"
 #include "scatter_devices/all_vectors_scatter_device.hpp"
+#include "scatter_devices/multipole_scatter_device.hpp"
 #include "scatter_devices/self_vectors_scatter_device.hpp"
 
 namespace {
@@ -24,6 +25,14 @@ struct AllDev : AllVectorsScatterDevice {
 struct SelfDev : SelfVectorsScatterDevice {
     using SelfVectorsScatterDevice::SelfVectorsScatterDevice;
     ~SelfDev() {}
+};
+struct MPSphereDev : MPSphereScatterDevice {
+    using MPSphereScatterDevice::MPSphereScatterDevice;
+    ~MPSphereDev() {}
+};
+struct MPCylinderDev : MPCylinderScatterDevice {
+    using MPCylinderScatterDevice::MPCylinderScatterDevice;
+    ~MPCylinderDev() {}
 };
 struct Out {
     double *fqt, *fq, *fq2, *qout;
@@ -87,6 +96,55 @@ size_t ref_scatter_run(int kind, const float *frames, size_t NF, size_t NA, cons
         dev.run();
     } else {
         SelfDev dev(comm, comm, sample, vectors, NA, ep, ep);
+        dev.run();
+    }
+    ShimWriterSink::Inst().cb = nullptr;
+    ShimFactorSource::Inst().cb = nullptr;
+    return out.count;
+}
+
+// The reference's multipole devices (src/scatter_devices/multipole_scatter_device.cpp; Boost.Math's three special functions
+// served by the oracle's restatements, see shim/boost/math/special_functions.hpp).  kind: 2 = MPSphereScatterDevice,
+// 3 = MPCylinderScatterDevice.  frames: float [NF][NA][3] cartesian (the device asks the sample for its own representation),
+// moments: NMOM pairs (l, m).  Outputs as ref_scatter_run.
+size_t ref_multipole_run(int kind, const float *frames, size_t NF, size_t NA, const double *b, const double *qvectors, size_t NQ,
+                         const long *moments, size_t NMOM, const double axis[3], const char *dsp_type, const char *dsp_method,
+                         size_t threads, double *fqt, double *fq, double *fq2, double *qout) {
+    Params *p = Params::Inst();
+    p->scattering.dsp.type = dsp_type;
+    p->scattering.dsp.method = dsp_method;
+    p->scattering.average.orientation.multipole.moments.clear();
+    for (size_t i = 0; i < NMOM; i++)
+        p->scattering.average.orientation.multipole.moments.push_back(std::make_pair(moments[2 * i], moments[2 * i + 1]));
+    p->scattering.average.orientation.axis = CartesianCoor3D(axis[0], axis[1], axis[2]);
+    p->limits.computation.threads = threads;
+    p->stager.target = "system";
+    p->stager.dump = false;
+
+    Sample sample;
+    ShimRangeSelection system(NA);
+    sample.atoms.selections["system"] = &system;
+    sample.coordinate_sets.shim_set(frames, NF, NA, p->scattering.average.orientation.axis);
+    {
+        std::lock_guard<std::mutex> l(ShimTimerTable::Inst().m);
+        ShimTimerTable::Inst().sum.clear();
+    }
+    Factors fac = {b};
+    ShimFactorSource::Inst().cb = on_factors;
+    ShimFactorSource::Inst().user = &fac;
+    Out out = {fqt, fq, fq2, qout, NF, 0};
+    ShimWriterSink::Inst().cb = on_write;
+    ShimWriterSink::Inst().user = &out;
+
+    std::vector<CartesianCoor3D> vectors;
+    for (size_t i = 0; i < NQ; i++) vectors.push_back(CartesianCoor3D(qvectors[3 * i], qvectors[3 * i + 1], qvectors[3 * i + 2]));
+    boost::mpi::communicator comm;
+    boost::asio::ip::tcp::endpoint ep;
+    if (kind == 2) {
+        MPSphereDev dev(comm, comm, sample, vectors, NF, ep, ep);
+        dev.run();
+    } else {
+        MPCylinderDev dev(comm, comm, sample, vectors, NF, ep, ep);
         dev.run();
     }
     ShimWriterSink::Inst().cb = nullptr;

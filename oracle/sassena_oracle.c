@@ -688,14 +688,12 @@ void orc_spherical_harmonic(long n, long m, double theta, double phi, double *re
 void orc_scatter_mpsphere(const float *coords, size_t NA, size_t f0, size_t f1, const double *sfs,
                           double ql, long l, long m, double *at /* [NF][2] */) {
     double M_PI_four = 4 * M_PI;
-    /* pow(complex(0,1), l) */
-    cplx il;
-    switch (((l % 4) + 4) % 4) {
-        case 0: il = 1; break;
-        case 1: il = I; break;
-        case 2: il = -1; break;
-        default: il = -I; break;
-    }
+    /* pow(complex<double>(0,1.0), l) -- multipole_scatter_device.cpp:483.  Under C++11 and later libstdc++ resolves this to
+     * pow(complex<double>, double) = polar(exp(l * log|i|), l * arg(i)) = (cos(l pi/2), sin(l pi/2)) in double arithmetic, i.e.
+     * i^l with a ~6e-17 residue in the component that is zero analytically (the C++98 overload pow(complex, int) multiplied
+     * exactly).  The reference built here (oracle/_ref, g++ 13) does the former; restated so that the oracle reproduces it
+     * bit for bit.  The product kernels use the exact i^l: the difference is ~1e-16 relative. */
+    cplx il = cos((double)l * M_PI_2) + I * sin((double)l * M_PI_2);
     for (size_t fi = f0; fi < f1; ++fi) {
         const float *p_data = &coords[fi * NA * 3];
         cplx A = 0;

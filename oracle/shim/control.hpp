@@ -4,6 +4,7 @@
 #define ORACLE_SHIM_CONTROL_HPP
 #include <cstddef>
 #include <string>
+#include <utility>
 #include <vector>
 #include "math/coor3d.hpp"
 #include "exceptions/exceptions.hpp"
@@ -17,7 +18,9 @@ struct ShimMonitor { size_t sampling = 1; };
 struct ShimServices { ShimMonitor monitor; };
 struct ShimLimits { ShimDecomposition decomposition; ShimComputation computation; ShimStage stage; ShimServices services; };
 struct ShimVectors : public std::vector<CartesianCoor3D> { std::string type = "file"; };
-struct ShimOrientation { std::string type = "vectors"; ShimVectors vectors; CartesianCoor3D axis = CartesianCoor3D(0, 0, 1); };
+struct ShimMoments : public std::vector<std::pair<long, long> > {};
+struct ShimMultipole { ShimMoments moments; };
+struct ShimOrientation { std::string type = "vectors"; ShimVectors vectors; ShimMultipole multipole; CartesianCoor3D axis = CartesianCoor3D(0, 0, 1); };
 struct ShimAverage { ShimOrientation orientation; };
 struct ShimDsp { std::string type = "autocorrelate", method = "fftw"; };
 struct ShimScattering { ShimDsp dsp; ShimAverage average; };
