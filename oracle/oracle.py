@@ -561,6 +561,51 @@ def ref_multipole_run(kind, frames, b, qvectors, moments, axis=(0, 0, 1), dsp="a
     return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
 
 
+# the reference's own Database tables (src/control/database.cpp in oracle/_ref; entry points oracle/ref_db_wrap.cpp)
+REF_DB_TABLES = {"sizes": 0, "exclusionfactors": 1, "scatterfactors": 2}
+
+
+def ref_db_reg(table, ID, constants, function_type):
+    c = _f64(np.asarray(constants, dtype=np.float64))
+    ref_lib().ref_db_reg(C.c_int(REF_DB_TABLES[table]), C.c_size_t(ID), _p(c, C.c_double), C.c_size_t(len(c)), C.c_size_t(function_type))
+
+
+def ref_db_volume(ID):
+    f = ref_lib().ref_db_volume
+    f.restype = C.c_double
+    return f(C.c_size_t(ID))
+
+
+def ref_db_exclusion(ID, effvolume, q):
+    f = ref_lib().ref_db_exclusion
+    f.restype = C.c_double
+    return f(C.c_size_t(ID), C.c_double(effvolume), C.c_double(q))
+
+
+def ref_db_sfactor(ID, q):
+    f = ref_lib().ref_db_sfactor
+    f.restype = C.c_double
+    return f(C.c_size_t(ID), C.c_double(q))
+
+
+def ref_db_effective(ID, q, kappa, background_sl):
+    """ScatterFactors::update for one atom (scatter_factors.cpp:56-78) over the reference's Database"""
+    f = ref_lib().ref_db_effective
+    f.restype = C.c_double
+    return f(C.c_size_t(ID), C.c_double(q), C.c_double(kappa), C.c_double(background_sl))
+
+
+def ref_db_name_reg(label, regexp):
+    ref_lib().ref_db_name_reg(label.encode(), regexp.encode())
+
+
+def ref_db_name_get(testlabel):
+    """element label of a PDB atom name the database knows (unknown names end in the reference's bare `throw;`)"""
+    buf = C.create_string_buffer(256)
+    ref_lib().ref_db_name_get(testlabel.encode(), buf, C.c_size_t(256))
+    return buf.value.decode()
+
+
 def ref_timer_seconds(key):
     """seconds the last ref_scatter_run spent under one of the reference's timer keys ("sd:stage", "sd:runner", "sd:compute", ...)"""
     f = ref_lib().ref_timer_seconds

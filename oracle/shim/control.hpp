@@ -27,12 +27,14 @@ struct ShimScattering { ShimDsp dsp; ShimAverage average; };
 struct ShimStager { bool dump = false; std::string filepath = "dump.dcd", format = "dcd", target = "system"; };
 struct ShimDebugPrint { bool orientations = false; };
 struct ShimDebug { ShimDebugPrint print; };
+struct ShimDatabase { std::string type = "file", filepath = "db.xml", format = "xml"; };
 class Params {
    public:
     ShimLimits limits;
     ShimScattering scattering;
     ShimStager stager;
     ShimDebug debug;
+    ShimDatabase database;
     static Params *Inst() {
         static Params p;
         return &p;

@@ -154,6 +154,28 @@ def ref_sfactor(el, q):
     return den / (4.0 * math.pi)
 
 
+# ---- the same tables for the reference's own Database (oracle/_ref build of src/control/database.cpp) ----
+REF_DB_ELEMENTS = ["hydrogen", "carbon", "oxygen", "nitrogen"]
+REF_DB_TABLES = {
+    "sizes": {"hydrogen": (1, [1.07]), "carbon": (1, [1.58]), "oxygen": (2, [1.3]), "nitrogen": (0, [11.5])},
+    "exclusionfactors": {"hydrogen": (2, [1.0]), "carbon": (2, [0.9]), "oxygen": (1, [1.1]), "nitrogen": (0, [3.0])},
+    "scatterfactors": {"hydrogen": (0, [-3.7406]),
+                       "carbon": (2, [2.31, 20.8439, 1.02, 10.2075, 1.5886, 0.5687, 0.865, 51.6512, 0.2156]),
+                       "oxygen": (1, [7.6579, 2.2458, 2.2266, 0, 0, 2, 2, 4, 0, 0, 1, 2, 2, 1, 1]), "nitrogen": (0, [9.36])},
+}
+REF_DB_NAMES = {"hydrogen": "^H.*", "carbon": "^C.*", "oxygen": "^O.*", "nitrogen": "^N.*"}
+REF_DB_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_database.npz")
+
+
+def register_reference_database(o):
+    """DB_XML's tables registered through the reference's own reg() methods (its XML reader needs libxml2)"""
+    for table, rows in REF_DB_TABLES.items():
+        for i, el in enumerate(REF_DB_ELEMENTS):
+            o.ref_db_reg(table, i, rows[el][1], rows[el][0])
+    for el, rx in REF_DB_NAMES.items():
+        o.ref_db_name_reg(el, rx)
+
+
 SCAN = """<vectors><type>scans</type><scans>
   <scan><from>0.4</from><to>1.6</to><points>3</points><base><x>1</x><y>0</y><z>0</z></base></scan>
 </scans></vectors>"""
@@ -258,6 +280,47 @@ def test_scatter_factors_match_reference_formulas(tmp_path):
     cfg2, _, names = make_case(tmp_path, scattering=SCAN)
     j2 = host.Job(cfg2)
     assert np.allclose(j2.factors(1.1), [ref_sfactor(NAME2EL[n], 1.1) for n in names], rtol=1e-14)
+
+
+def test_database_restatement_equals_reference_database(oracle):
+    """the formulas restated above (and with them the powf / float-sqrt roundings they claim) against values evaluated by the
+    reference's own database.cpp (tests/golden/ref_database.npz, tests/golden/make_ref_database_golden.py): bit for bit; live
+    where oracle/_ref is built"""
+    g = np.load(REF_DB_GOLD)
+    assert list(g["elements"]) == REF_DB_ELEMENTS
+    bg = float(g["background"])
+    for i, el in enumerate(REF_DB_ELEMENTS):
+        assert ref_volume(el) == g["volume"][i], el
+        for c, ql in enumerate(g["q"]):
+            assert ref_sfactor(el, float(ql)) == g["sfactor"][i, c], (el, ql)
+            for k, kappa in enumerate(g["kappa"]):
+                e = ref_excl(el, float(kappa) * ref_volume(el), float(ql))
+                assert e == g["exclusion"][i, k, c], (el, ql, kappa)
+                assert ref_sfactor(el, float(ql)) - bg * e == g["effective"][i, k, c], (el, ql, kappa)
+    assert [NAME2EL[n] for n in g["names"]] == list(g["resolved"])
+    if oracle.have_ref_smath():
+        register_reference_database(oracle)
+        for i, el in enumerate(REF_DB_ELEMENTS):
+            assert oracle.ref_db_volume(i) == g["volume"][i]
+            assert oracle.ref_db_effective(i, 0.9, 1.25, 0.05) == \
+                ref_sfactor(el, 0.9) - 0.05 * ref_excl(el, 1.25 * ref_volume(el), 0.9)
+        assert all(oracle.ref_db_name_get(n) == NAME2EL[n] for n in NAME2EL)
+
+
+def test_product_scatter_factors_equal_reference_database(tmp_path):
+    """csrc/host/control.cpp (Database + ScatterFactors::update through sass_job_factors) against the reference's own
+    database.cpp values: bit for bit, for every atom of the target selection, with and without background / kappas"""
+    g = np.load(REF_DB_GOLD)
+    bgxml = """<background><factor>0.0334</factor><kappas>
+      <kappa><selection>solvent</selection><value>1.5</value></kappa></kappas></background>"""
+    extra = """<selections><selection><type>range</type><name>solvent</name><from>12</from><to>23</to></selection></selections>"""
+    cfg, _, names = make_case(tmp_path, scattering=SCAN, background=bgxml, sample_extra=extra)
+    job = host.Job(cfg)
+    el_index = {e: i for i, e in enumerate(REF_DB_ELEMENTS)}
+    for c, ql in enumerate(g["q"]):
+        got = job.factors(float(ql))
+        exp = [g["effective"][el_index[NAME2EL[n]], 1 if i >= 12 else 0, c] for i, n in enumerate(names)]
+        assert np.array_equal(got, exp), (ql, got, exp)
 
 
 def test_config_errors(tmp_path):
