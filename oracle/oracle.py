@@ -561,6 +561,60 @@ def ref_multipole_run(kind, frames, b, qvectors, moments, axis=(0, 0, 1), dsp="a
     return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
 
 
+# the reference's own generators (src/control/parameters.cpp:930-1189 in oracle/_ref/libparams_ref.so; oracle/ref_params_wrap.cpp)
+_REF_PARAMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libparams_ref.so")
+_ref_params = None
+
+
+def have_ref_params():
+    return os.path.exists(_REF_PARAMS)
+
+
+def ref_params_lib():
+    global _ref_params
+    if _ref_params is None:
+        _ref_params = C.CDLL(_REF_PARAMS)
+    return _ref_params
+
+
+def ref_orientation_vectors(type, algorithm="boost_uniform_on_sphere", resolution=100, seed=0, filepath=""):
+    f = ref_params_lib().ref_orientation_vectors
+    f.restype = C.c_size_t
+    args = (type.encode(), algorithm.encode(), C.c_size_t(resolution), C.c_ulong(seed), filepath.encode())
+    n = f(*args, None, C.c_size_t(0))
+    out = np.zeros((n, 3))
+    f(*args, _p(out, C.c_double), C.c_size_t(n))
+    return out
+
+
+def ref_multipole_moments(multipole_type, resolution=20, type="resolution", filepath=""):
+    f = ref_params_lib().ref_multipole_moments
+    f.restype = C.c_size_t
+    args = (multipole_type.encode(), type.encode(), C.c_long(resolution), filepath.encode())
+    n = f(*args, None, C.c_size_t(0))
+    out = np.zeros((n, 2), dtype=np.int64)
+    f(*args, _p(out, C.c_long), C.c_size_t(n))
+    return out
+
+
+def ref_scan_vectors(scans):
+    """scans: list of dicts (base, from, to, points, exponent) as qvectors_from_scans takes them"""
+    n = len(scans)
+    fr = _f64(np.array([s["from"] for s in scans], dtype=np.float64))
+    to = _f64(np.array([s["to"] for s in scans], dtype=np.float64))
+    pts = np.ascontiguousarray([s.get("points", 100) for s in scans], dtype=np.uint64)
+    ex = _f64(np.array([s.get("exponent", 1.0) for s in scans], dtype=np.float64))
+    base = _f64(np.array([s.get("base", (1, 0, 0)) for s in scans], dtype=np.float64).reshape(-1, 3))
+    f = ref_params_lib().ref_scan_vectors
+    f.restype = C.c_size_t
+    args = (C.c_size_t(n), _p(fr, C.c_double), _p(to, C.c_double), pts.ctypes.data_as(C.POINTER(C.c_size_t)), _p(ex, C.c_double),
+            _p(base, C.c_double))
+    cnt = f(*args, None, C.c_size_t(0))
+    out = np.zeros((cnt, 3))
+    f(*args, _p(out, C.c_double), C.c_size_t(cnt))
+    return out
+
+
 # the reference's own Database tables (src/control/database.cpp in oracle/_ref; entry points oracle/ref_db_wrap.cpp)
 REF_DB_TABLES = {"sizes": 0, "exclusionfactors": 1, "scatterfactors": 2}
 

@@ -92,6 +92,7 @@ class thread {
     std::thread t_;
    public:
     typedef std::thread::id id;
+    static unsigned hardware_concurrency() { return std::thread::hardware_concurrency(); }
     template <class F>
     explicit thread(F f) : st_(new shim_detail::tstate) {
         std::shared_ptr<shim_detail::tstate> st = st_;
