@@ -615,6 +615,45 @@ def ref_scan_vectors(scans):
     return out
 
 
+# the reference's own structure / selection readers (atoms.cpp, atomselection_reader.cpp, atomselection.cpp; ref_sample_wrap.cpp)
+def ref_sample_name_reg(label, regexp):
+    ref_params_lib().ref_sample_name_reg(label.encode(), regexp.encode())
+
+
+def ref_atoms_labels(pdbfile):
+    """database label of every ATOM record of a PDB structure file (Atoms::add, atoms.cpp:64-86)"""
+    f = ref_params_lib().ref_atoms_labels
+    f.restype = C.c_size_t
+    buf = C.create_string_buffer(1 << 20)
+    n = f(pdbfile.encode(), buf, C.c_size_t(1 << 20))
+    labels = buf.value.decode().split("\n")[:-1]
+    assert len(labels) == n
+    return labels
+
+
+def _ref_sel(fn, *args):
+    fn.restype = C.c_size_t
+    n = fn(*args, None, C.c_size_t(0))
+    if n == C.c_size_t(-1).value:
+        return None
+    out = np.zeros(n, dtype=np.uint64)
+    fn(*args, out.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(n))
+    return out.astype(np.int64)
+
+
+def ref_select_pdb(file, selector, expression):
+    return _ref_sel(ref_params_lib().ref_select_pdb, file.encode(), selector.encode(), expression.encode())
+
+
+def ref_select_ndx(file, selector, expression, group):
+    """one group of the ndx file after the expression filter, or None when the reference did not create it"""
+    return _ref_sel(ref_params_lib().ref_select_ndx, file.encode(), selector.encode(), expression.encode(), group.encode())
+
+
+def ref_select_range(first, last):
+    return _ref_sel(ref_params_lib().ref_select_range, C.c_size_t(first), C.c_size_t(last))
+
+
 # the reference's own Database tables (src/control/database.cpp in oracle/_ref; entry points oracle/ref_db_wrap.cpp)
 REF_DB_TABLES = {"sizes": 0, "exclusionfactors": 1, "scatterfactors": 2}
 

@@ -693,9 +693,13 @@ static std::map<std::string, std::vector<size_t>> read_ndx_selection(const std::
         if (pos != std::string::npos) {
             size_t pos2 = line.find("]");
             if (pos2 == std::string::npos) throw Error("ndx file is missing closing bracket");
-            std::stringstream cs(line.substr(pos + 1, pos2 - pos - 1));
-            cs >> name;
-            name = trim(name);
+            // atomselection_reader.cpp:51-54 takes pos2 - pos characters after the '[', i.e. up to AND INCLUDING the ']', and keeps
+            // the first whitespace-delimited token: "[ grpA ]" is named "grpA", but "[grpB]" is named "grpB]".  Kept as is: the
+            // names are what a configuration refers to (pinned against the reference's reader in tests/test_control_plane.py).
+            std::stringstream cs(line.substr(pos + 1, pos2 - pos));
+            std::string cleanname;
+            cs >> cleanname;
+            name = trim(cleanname);
         } else if (!name.empty() && std::regex_match(name, expr)) {
             std::stringstream ls(line);
             size_t index = 0;

@@ -227,6 +227,53 @@ def test_config_selections_framesets_and_scans(tmp_path):
     assert job.nqvectors == 3 and np.array_equal(job.qvectors(), q)
 
 
+def test_selections_equal_reference_readers(tmp_path, oracle):
+    """structure and selection readers against the REFERENCE's own atoms.cpp / atomselection_reader.cpp / atomselection.cpp
+    (oracle/_ref/libparams_ref.so; live only where the reference is present -- the readers take files, so there is no fixture
+    beyond the expectations spelled out in test_config_selections_framesets_and_scans)"""
+    if not oracle.have_ref_params():
+        pytest.skip("oracle/_ref/libparams_ref.so not built (no /root/reference on this machine)")
+    sample_extra = """<selections>
+      <selection><type>range</type><name>tail</name><from>20</from><to>23</to></selection>
+      <selection><type>lexical</type><name>carbons</name><expression>carbon</expression></selection>
+      <selection><type>lexical</type><name>heavy</name><expression>(carbon|oxygen|nitrogen)</expression></selection>
+      <selection><type>file</type><name>flagged</name><file>sel.pdb</file><format>pdb</format></selection>
+      <selection><type>file</type><name>b0</name><file>sel.pdb</file><format>pdb</format><selector>beta</selector>
+                 <expression>0\\.00</expression></selection>
+      <selection><type>file</type><name>solvent</name><file>sel.pdb</file><format>pdb</format>
+                 <selector>segid</selector><expression>SOLV</expression></selection>
+      <selection><type>file</type><name>anyseg</name><file>sel.pdb</file><format>pdb</format>
+                 <selector>segid</selector><expression>(SOLV|PROT)</expression></selection>
+      <selection><type>file</type><file>groups.ndx</file><format>ndx</format><expression>grp.*</expression></selection>
+    </selections>"""
+    cfg, xyz, names = make_case(tmp_path, scattering=SCAN, sample_extra=sample_extra)
+    pdb = str(tmp_path / "sel.pdb")
+    ndx = str(tmp_path / "groups.ndx")
+    (tmp_path / "sel.pdb").write_text((tmp_path / "sample.pdb").read_text())
+    (tmp_path / "groups.ndx").write_text("[ grpA ]\n1 2 3\n4\n[ other ]\n7 8\n[grpB]\n10 11\n\n[ grpC ] trailing\n24\n")
+    job = host.Job(cfg)
+    for el, rx in REF_DB_NAMES.items():
+        oracle.ref_sample_name_reg(el, rx)
+    labels = oracle.ref_atoms_labels(str(tmp_path / "sample.pdb"))  # Atoms::add: PDB names -> database labels
+    assert labels == [NAME2EL[n] for n in names] and job.natoms == len(labels)
+    # lexical: the product selects the INDICES of the atoms whose label matches (the reference pushes the element ID, DESIGN 7)
+    assert list(job.selection("carbons")) == [i for i, l in enumerate(labels) if l == "carbon"]
+    assert list(job.selection("heavy")) == [i for i, l in enumerate(labels) if l != "hydrogen"]
+    assert np.array_equal(job.selection("tail"), oracle.ref_select_range(20, 23))
+    assert np.array_equal(job.selection("flagged"), oracle.ref_select_pdb(pdb, "beta", "1|1\\.0|1\\.00"))
+    assert np.array_equal(job.selection("b0"), oracle.ref_select_pdb(pdb, "beta", "0\\.00"))
+    assert np.array_equal(job.selection("solvent"), oracle.ref_select_pdb(pdb, "segid", "SOLV"))
+    assert np.array_equal(job.selection("anyseg"), oracle.ref_select_pdb(pdb, "segid", "(SOLV|PROT)"))
+    # "[grpB]" without blanks is named "grpB]" by the reference (it keeps the closing bracket, atomselection_reader.cpp:51-54)
+    for grp in ("grpA", "grpB]", "grpC"):
+        assert np.array_equal(job.selection(grp), oracle.ref_select_ndx(ndx, "name", "grp.*", grp)), grp
+    assert list(job.selection("grpB]")) == [9, 10] and list(job.selection("grpC")) == [23]
+    assert oracle.ref_select_ndx(ndx, "name", "grp.*", "other") is None and oracle.ref_select_ndx(ndx, "name", "grp.*", "grpB") is None
+    for absent in ("other", "grpB"):
+        with pytest.raises(host.HostError):
+            job.selection(absent)
+
+
 def test_pdb_frameset(tmp_path):
     """PDBFrameset (frames.cpp:442-577): frames end at END/ENDMDL lines, an unterminated last frame counts, the
     ENDMDL+END tail does not add a frame; first/stride/clones apply as for DCD; coordinates come from columns 31-54."""
