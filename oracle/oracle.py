@@ -654,6 +654,20 @@ def ref_select_range(first, last):
     return _ref_sel(ref_params_lib().ref_select_range, C.c_size_t(first), C.c_size_t(last))
 
 
+def ref_frames_read(format, file, first=0, last=0, last_set=False, stride=1):
+    """the reference's own DCD / PDB / XTC / TRR frameset (frames.cpp; generate_index + trim_index + read_frame) -> float64
+    [nframes][natoms][3]"""
+    f = ref_params_lib().ref_frames_read
+    f.restype = C.c_size_t
+    na = C.c_size_t(0)
+    args = (format.encode(), str(file).encode(), C.c_size_t(first), C.c_size_t(last), C.c_int(1 if last_set else 0), C.c_size_t(stride))
+    n = f(*args, C.byref(na), None, C.c_size_t(0))
+    assert n != C.c_size_t(-1).value, "unknown format"
+    out = np.zeros((n, na.value, 3))
+    f(*args, C.byref(na), _p(out, C.c_double), C.c_size_t(n))
+    return out
+
+
 # the reference's own Database tables (src/control/database.cpp in oracle/_ref; entry points oracle/ref_db_wrap.cpp)
 REF_DB_TABLES = {"sizes": 0, "exclusionfactors": 1, "scatterfactors": 2}
 
