@@ -3,8 +3,11 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 ``--impl reference`` legs.  The product package (sassena_b200/) never imports this module.
 
-PARITY UNPINNED (see the header of sassena_oracle.c): the reference has no golden vectors and cannot be
-built here, so the C port is pinned by analytic known answers and by the numpy/scipy functions below.
+PARITY PINNED to the reference's own code (see the header of sassena_oracle.c and DESIGN.md section 2): the reference ships
+no golden vectors, but its scatter devices (all / self / multipole sphere / multipole cylinder), stagers, DSP, generators,
+database and readers compile where they lie over the shims in oracle/shim* -> oracle/_ref/*.so; the ref_* functions below
+run them, tests/golden/ref_*.npz hold their output, and the C port reproduces the devices bit for bit.  Analytic known
+answers and the numpy / scipy functions below remain as independent cross-checks (special-function values, FFT).
 """
 from __future__ import annotations
 

@@ -5,18 +5,23 @@
  * this file.  It is the checker used by tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.
  *
- * PARITY PINNED TO THE REFERENCE'S OWN CODE for the coherent and self devices: the reference
+ * PARITY PINNED TO THE REFERENCE'S OWN CODE for all four scatter devices: the reference
  * (benlabs/sassena v1.4.2) ships no golden vectors or asserting tests for this path and its
  * build system cannot be used here (Boost, FFTW3, MPI, HDF5, libxml2 are absent), but its
  * translation units compile where they lie over the shim headers in oracle/shim (make -C oracle
- * ref -> oracle/_ref/libsmath_ref.so): AllVectorsScatterDevice, SelfVectorsScatterDevice with
- * their abstract bases, the stagers, smath.cpp, coor3d.cpp, assignment.cpp, decomposition_plan.cpp,
- * coordinate_writer.cpp, motion_walker.cpp.  orc_compute_all_vectors / orc_compute_self_vectors
- * reproduce the reference devices' fqt / fq / fq2 BIT FOR BIT (tests/test_reference_devices.py,
- * fixtures tests/golden/ref_devices.npz); the helper functions likewise (tests/test_oracle.py).
- * UNPINNED by reference output: the multipole devices (they need Boost.Math), ScatterFactors /
- * Database and the Boost.Random streams -- pinned by scipy cross-checks, closed forms and
- * restated formulas.  vendor/xdrfile-1.1.1 pins the product's XTC / TRR readers.
+ * ref -> oracle/_ref/libsmath_ref.so, libparams_ref.so): AllVectorsScatterDevice,
+ * SelfVectorsScatterDevice, MPSphereScatterDevice, MPCylinderScatterDevice with their abstract
+ * bases, the stagers, smath.cpp, coor3d.cpp, assignment.cpp, decomposition_plan.cpp,
+ * coordinate_writer.cpp, motion_walker.cpp, database.cpp, parameters.cpp (generators), atoms.cpp,
+ * atomselection*.cpp, frames.cpp.  orc_compute_all_vectors / orc_compute_self_vectors /
+ * orc_compute_mpsphere / orc_compute_mpcylinder reproduce the reference devices' fqt / fq / fq2
+ * BIT FOR BIT (tests/test_reference_devices.py, fixtures tests/golden/ref_devices.npz,
+ * ref_multipole_devices.npz); the helper functions and generators likewise (tests/test_oracle.py,
+ * tests/test_reference_params.py).
+ * NOT pinned by reference output: the VALUES of Boost.Math's sph_bessel / spherical_harmonic /
+ * cyl_bessel_j (the reference's multipole code is built over this file's restatements of them;
+ * scipy cross-checks and closed-form cluster averages pin the values), FFTW's arithmetic, and
+ * the Boost.Random streams.  vendor/xdrfile-1.1.1 pins the product's XTC / TRR readers.
  *
  * Third-party arithmetic that is not in /root/reference and is restated here:
  *   FFTW3 (unpinned version)         -> own mixed-radix / Bluestein complex FFT

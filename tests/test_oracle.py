@@ -1,6 +1,8 @@
-"""Pins the CPU oracle (oracle/sassena_oracle.c): the reference ships no golden vectors or asserting tests for this
-path (PARITY UNPINNED), so the port is checked against independent numpy/scipy restatements, the analytic
-known answers KA1-KA5 derived from the cited formulas, and the committed golden fixtures (tests/golden)."""
+"""Pins the CPU oracle (oracle/sassena_oracle.c).  The reference ships no golden vectors or asserting tests for this path
+(SURVEY 8c); the pins are the reference's own code built in oracle/_ref (fixtures tests/golden/ref_*.npz written by it:
+smath / coor3d / assignment here, the scatter devices in tests/test_reference_devices.py, the generators in
+tests/test_reference_params.py), plus independent numpy / scipy restatements and the analytic known answers KA1-KA5, KA7
+derived from the cited formulas."""
 import os
 
 import numpy as np
