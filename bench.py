@@ -28,8 +28,11 @@ partial (self_vectors_scatter_device.cpp:50,213-221).
 size: a step is one pass of the batched multipole kernel (8 |q| x 441 moments over all atoms and frames); N GPUs shard the
 atoms by DivAssignment and all-reduce the amplitudes before the DSP.
 
-`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's loops; the reference
-itself cannot be built in this image) on all host cores on a bounded sample of the same workload.
+`--impl reference` times the reference's CPU implementation on all host cores on a bounded sample of the same workload: for the
+coherent workload the reference's OWN AllVectorsScatterDevice (oracle/_ref: its sources compiled where they lie over shim
+headers, since its build system cannot be used in this image); for the self and multipole workloads the oracle port, which
+reproduces the reference's devices bit for bit (their oracle/_ref builds run over the oracle's DFT / special functions instead
+of FFTW / Boost.Math, so timing them would not be timing the reference).
 """
 from __future__ import annotations
 
@@ -792,7 +795,9 @@ def mp_flop_per_atom_frame_q(L, nmom, Q=MP_BATCH):
 
 
 def run_reference_mpsphere(args):
-    """--impl reference --workload C4: the oracle's MPSphere path (Boost.Math calls restated) on a bounded sample."""
+    """--impl reference --workload C4: the oracle's MPSphere path on a bounded sample.  It reproduces the reference's own
+    MPSphereScatterDevice bit for bit (tests/test_reference_devices.py); that device's oracle/_ref build evaluates sph_bessel /
+    spherical_harmonic through the oracle's restatements (Boost.Math is absent), so the port is what is timed: kind "port"."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     from oracle import oracle as o
