@@ -671,6 +671,19 @@ def ref_frames_read(format, file, first=0, last=0, last_set=False, stride=1):
     return out
 
 
+def ref_coordinate_set(xyz, sel=None, trans=(0, 0, 0), repr="cartesian", axis=(0, 0, 1)):
+    """the reference's own CartesianCoordinateSet(frame, selection) -> translate -> Spherical / CylindricalCoordinateSet
+    (coordinate_set.cpp); xyz [natoms][3] -> double [nsel][3]"""
+    a = _f64(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+    idx = np.ascontiguousarray(np.arange(len(a)) if sel is None else sel, dtype=np.uint64)
+    out = np.zeros((len(idx), 3))
+    ref_params_lib().ref_coordinate_set(_p(a, C.c_double), C.c_size_t(len(a)), idx.ctypes.data_as(C.POINTER(C.c_size_t)),
+                                        C.c_size_t(len(idx)), _p(_f64(np.asarray(trans, dtype=np.float64)), C.c_double),
+                                        C.c_int({"cartesian": 10, "spherical": 20, "cylindrical": 30}[repr]),
+                                        _p(_f64(np.asarray(axis, dtype=np.float64)), C.c_double), _p(out, C.c_double))
+    return out
+
+
 # the reference's own Database tables (src/control/database.cpp in oracle/_ref; entry points oracle/ref_db_wrap.cpp)
 REF_DB_TABLES = {"sizes": 0, "exclusionfactors": 1, "scatterfactors": 2}
 

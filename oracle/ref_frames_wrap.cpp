@@ -58,3 +58,37 @@ size_t ref_frames_read(const char *format, const char *file, size_t first, size_
     return n;
 }
 }
+
+// ---- the reference's own coordinate sets (src/sample/coordinate_set.cpp): a frame reduced to a selection, translated, then
+// changed to the spherical / cylindrical representation the multipole devices stage (:278-315) ----
+#include "sample/atomselection.hpp"
+#include "sample/coordinate_set.hpp"
+extern "C" {
+// xyz: double [natoms][3] (a Frame); sel: nsel atom indices; trans: translation applied to the set; repr 10 cartesian,
+// 20 spherical (r, phi, theta), 30 cylindrical (r, phi, z) on `axis`.  out: double [nsel][3]
+void ref_coordinate_set(const double *xyz, size_t natoms, const size_t *sel, size_t nsel, const double trans[3], int repr,
+                        const double axis[3], double *out) {
+    Frame fr;
+    fr.number_of_atoms = natoms;
+    for (size_t i = 0; i < natoms; i++) {
+        fr.x.push_back(xyz[3 * i]);
+        fr.y.push_back(xyz[3 * i + 1]);
+        fr.z.push_back(xyz[3 * i + 2]);
+    }
+    IndexAtomselection s(std::vector<size_t>(sel, sel + nsel));
+    CartesianCoordinateSet cs(fr, &s);
+    cs.translate(CartesianCoor3D(trans[0], trans[1], trans[2]));
+    CoordinateSet *res = &cs;
+    SphericalCoordinateSet *sph = NULL;
+    CylindricalCoordinateSet *cyl = NULL;
+    if (repr == 20) res = sph = new SphericalCoordinateSet(cs);
+    if (repr == 30) res = cyl = new CylindricalCoordinateSet(cs, CartesianCoor3D(axis[0], axis[1], axis[2]));
+    for (size_t i = 0; i < res->size(); i++) {
+        out[3 * i] = res->c1[i];
+        out[3 * i + 1] = res->c2[i];
+        out[3 * i + 2] = res->c3[i];
+    }
+    delete sph;
+    delete cyl;
+}
+}

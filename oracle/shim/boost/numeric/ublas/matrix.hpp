@@ -45,5 +45,26 @@ matrix<T> prod(const matrix<T> &a, const matrix<T> &b) {
         }
     return c;
 }
+/* dense vector and row-vector x matrix product (coordinate_set.cpp:161-173), inner sum in index order */
+template <class T>
+class vector {
+    std::vector<T> d_;
+   public:
+    vector() {}
+    explicit vector(std::size_t n) : d_(n) {}
+    T &operator()(std::size_t i) { return d_[i]; }
+    const T &operator()(std::size_t i) const { return d_[i]; }
+    std::size_t size() const { return d_.size(); }
+};
+template <class T>
+vector<T> prod(const vector<T> &v, const matrix<T> &m) {
+    vector<T> r(m.size2());
+    for (std::size_t j = 0; j < m.size2(); j++) {
+        T t = T(0);
+        for (std::size_t i = 0; i < m.size1(); i++) t += v(i) * m(i, j);
+        r(j) = t;
+    }
+    return r;
+}
 }}}  // namespace boost::numeric::ublas
 #endif

@@ -76,3 +76,27 @@ def test_pdb_frameset_equals_reference(ref, tmp_path):
     job = host.Job(cfg)
     assert job.nframes == len(r) == 6
     assert np.array_equal(job.frames(), r.astype(np.float32))
+
+
+def test_coordinate_set_conversions_equal_reference(ref):
+    """the oracle's cart_to_spherical / cart_to_cylindrical (the inputs of the multipole devices and the checker of the device-side
+    conversion kernels) against the reference's own CartesianCoordinateSet(frame, selection) -> translate -> Spherical /
+    CylindricalCoordinateSet (coordinate_set.cpp:278-315) after the stager's narrowing to float: bit for bit, including atoms at
+    the origin, on the axes and in every quadrant"""
+    xyz = synth.trajectory(1, 64, 30.0, 0.5, 3, offset=-15.0)[0]
+    xyz[0] = 0
+    xyz[1, :2] = 0
+    xyz[2, 0] = 0
+    xyz[3, 1] = 0
+    xyz[4] = [-1, 0, 0]
+    xyz[5] = [0, -2, 0]
+    xyz[6] = [0, 0, -3]
+    sel = np.array([0, 1, 2, 3, 4, 5, 6, 7, 11, 30, 49, 63])
+    assert np.array_equal(ref.ref_coordinate_set(xyz, sel), xyz[sel].astype(np.float64))
+    t = np.array([1.5, -2.25, 0.125])
+    assert np.array_equal(ref.ref_coordinate_set(xyz, sel, trans=t), xyz[sel].astype(np.float64) + t)
+    assert np.array_equal(ref.ref_coordinate_set(xyz, sel, repr="spherical").astype(np.float32), ref.cart_to_spherical(xyz[sel]))
+    assert np.array_equal(ref.ref_coordinate_set(xyz, repr="spherical").astype(np.float32), ref.cart_to_spherical(xyz))
+    for axis in ((0, 0, 1), (0.3, -0.2, 1.0), (1, 1, 0), (0, 1, 0), (-1, 0, 0)):
+        assert np.array_equal(ref.ref_coordinate_set(xyz, sel, repr="cylindrical", axis=axis).astype(np.float32),
+                              ref.cart_to_cylindrical(xyz[sel], axis)), axis
