@@ -2,37 +2,40 @@
 """bench.py — headline benchmark of the Sassena scattering hot path on B200.
 
 Metric (BASELINE.json): amplitude evaluations/s, one evaluation = one (atom, frame, q-vector) triple, plus the
-F(q,t) wall time it implies.  Workload (default): BASELINE configs[2] "coherent F(q,t): 100k atoms x 10k frames,
-50 |q| x 500 sphere vectors" — the configuration north_star's Target sentence is quoted on; it fits one GPU
-(12 GB of coordinates).
+F(q,t) wall time it implies.  The headline workload is BASELINE configs[2] "coherent F(q,t): 100k atoms x 10k frames,
+50 |q| x 500 sphere vectors" — the configuration north_star's Target sentence is quoted on; it fits one GPU (12 GB of
+coordinates).
 
-A STEP (default `--mode scan`) is the whole job's hot path: all 50 equally spaced |q| x 500 orientation vectors over
-the full trajectory — amplitudes -> FFT autocorrelation -> orientational average -> fqt/fq/fq2 for every |q|
-(2.5e13 evaluations).  The |q|-scan kernel evaluates the 50 |q| of one (atom, direction) pair with two sincos and a
-3-term recurrence per pass of <= 28 |q| (DESIGN.md "K1s").  `--mode per-q` times the general kernel instead: a step is
-one compute() of the reference's runner loop (abstract_scatter_device.cpp:162-173), one |q| with its 500 vectors.
+A STEP is the whole job's hot path: all 50 |q| x 500 orientation vectors over the full trajectory — amplitudes -> FFT
+autocorrelation -> orientational average -> fqt/fq/fq2 for every |q| (2.5e13 evaluations).  The |q| list is what the
+reference's own scan generator produces (`synth.qlengths` = ScatteringVectorsParameters::create_from_scans,
+parameters.cpp:1125-1189: float-rounded fractions), so the library plans the corrected symmetric scan kernel for it
+(DESIGN.md "K1s").  The same scan on exactly equally spaced |q| (np.linspace; plain symmetric kernel) is reported beside it
+under `workloads.C3_equally_spaced`; `--mode per-q` times the general kernel instead (one |q| per step).
 
-N GPUs: one process per GPU (torchrun).  The FRAMES are sharded with DivAssignment (the reference's own decomposition,
-all_vectors_scatter_device.cpp:61,248,408): every rank holds and evaluates only its block of the trajectory for all
-subvectors, the zero-padded amplitude buffers A[NQ][NM][NF] are summed over NVSwitch (one NCCL all-reduce), every rank
-correlates a DivAssignment block of the timelines, and the packed partials are summed with a second small all-reduce;
-finalize on every rank ("strong" scaling: total work per step is fixed).  `--shard vectors` selects the alternative with
-replicated coordinates and sharded subvectors.
+The default invocation also measures, each with its own roofline / e2e / parity / cpu_baseline under `workloads`:
+  C2   BASELINE configs[1], incoherent self scattering 30k atoms x 10k frames, at full size: a step is one |q| with its 200
+       vectors over all atoms (6e6 per-atom timelines: amplitudes + FFT autocorrelation in the self kernels);
+  C4   BASELINE configs[3], multipole sphere averaging 1M atoms x 1k frames, at full size: a step is one pass of the batched
+       multipole kernel (8 |q| x 441 moments over all atoms and frames);
+  C5s  a bounded sample of BASELINE configs[4] (stager-streamed self scattering, 50k frames): C5S_ATOMS atoms stream from
+       pinned host memory through the double-buffered wave stager while the previous wave is evaluated.
+`--workload C2|C4|C5s|C3|C1` runs one of them alone as the top-level line; `--workload C5` runs config 5 at full size
+(500k atoms x 50k frames, `--nq` |q| values; needs 8 GPUs and ~300 GB of host memory).
 
-`--workload C2` measures BASELINE configs[1] (incoherent self scattering, 30k atoms x 10k frames, 20 |q| x 200 vectors)
-at full size: a step is one |q| with its 200 vectors over all atoms (6e6 per-atom timelines: amplitudes + FFT
-autocorrelation in the fused/split self kernels); N GPUs shard the atoms by ModAssignment and all-reduce the packed
-partial (self_vectors_scatter_device.cpp:50,213-221).
+N GPUs: one process per GPU (torchrun), total work fixed ("strong").  Coherent: the FRAMES are sharded with DivAssignment (the
+reference's own decomposition, all_vectors_scatter_device.cpp:61,248,408), the per-rank amplitude blocks are exchanged over
+NVLink so that every rank correlates a DivAssignment block of the timelines, and the packed partials are summed with one
+small all-reduce (`--shard vectors`: replicated coordinates, sharded subvectors, no amplitude exchange).  Self: atoms sharded
+by ModAssignment, one all-reduce of the packed partial (self_vectors_scatter_device.cpp:50,213-221).  Multipole: atoms sharded
+by DivAssignment, amplitudes all-reduced before the DSP.
 
-`--workload C4` measures BASELINE configs[3] (multipole sphere averaging, 1M atoms x 1k frames x 200 |q|, l <= 20) at full
-size: a step is one pass of the batched multipole kernel (8 |q| x 441 moments over all atoms and frames); N GPUs shard the
-atoms by DivAssignment and all-reduce the amplitudes before the DSP.
-
-`--impl reference` times the reference's CPU implementation on all host cores on a bounded sample of the same workload: for the
-coherent workload the reference's OWN AllVectorsScatterDevice (oracle/_ref: its sources compiled where they lie over shim
-headers, since its build system cannot be used in this image); for the self and multipole workloads the oracle port, which
-reproduces the reference's devices bit for bit (their oracle/_ref builds run over the oracle's DFT / special functions instead
-of FFTW / Boost.Math, so timing them would not be timing the reference).
+`--impl reference` times the reference's CPU implementation on ALL host cores (len(os.sched_getaffinity(0)), never
+OMP_NUM_THREADS — torchrun sets that to 1) on a bounded sample of the same workload: for the coherent workload the reference's
+OWN AllVectorsScatterDevice (oracle/_ref: its sources compiled where they lie over shim headers, since its build system
+cannot be used in this image); for the self and multipole workloads the oracle port, which reproduces the reference's devices
+bit for bit (their oracle/_ref builds run over the oracle's DFT / special functions instead of FFTW / Boost.Math, so timing
+them would not be timing the reference).
 """
 from __future__ import annotations
 

@@ -18,8 +18,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
-    "--shared",
 ]
+OBJDIR = os.path.join(HERE, "build")  # git-ignored; one object per source so that an edit recompiles one file
 
 
 def sources():
@@ -29,32 +29,56 @@ def sources():
     return srcs
 
 
-def _deps():
-    d = sources()
+def _headers():
+    d = []
     for pat in ("kernels/*.hpp", "kernels/*.cuh", "host/*.hpp", "*.hpp"):
         d += glob.glob(os.path.join(CSRC, pat))
     d.append(os.path.join(HERE, "..", "include", "sassena_b200.h"))
     d.append(os.path.join(HERE, "..", "include", "sassena_host.h"))
+    d.append(os.path.abspath(__file__))
     return [p for p in d if os.path.exists(p)]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _obj(src):
+    return os.path.join(OBJDIR, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(p) > t for p in _deps())
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def needs_build() -> bool:
+    return _stale(LIB, sources() + _headers())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     env = dict(os.environ)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdrs = _headers()
     # the image exports CC/CXX pointing at a wrapper compiler; nvcc should use the system g++
-    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-I", CSRC,
-                                                           "-o", LIB] + sources()
+    base = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-I", CSRC]
+
+    def compile_one(src):
+        obj = _obj(src)
+        if force or _stale(obj, [src] + hdrs):
+            cmd = base + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd, env=env)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = base + ["--shared", "-o", LIB] + objs
     if verbose:
-        print(" ".join(cmd))
+        print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd, env=env)
     return LIB
 

@@ -9,81 +9,16 @@
 // the q-group index is the fastest grid dimension so a frame stays L2-hot across its q-groups.
 // FP64-pipe bound: 21 FP64 instructions per (atom, frame, q-vector), see sincos_qt.cuh.
 #include "kernels.hpp"
+#include "ptx.cuh"
 #include "sincos_qt.cuh"
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 namespace sass {
 
 namespace {
-
-constexpr int K1_QPT = 8;    // q-vectors per warp
-constexpr int K1_WARPS = 8;  // warps per CTA  -> 64 q-vectors per CTA
-
-template <int QPT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) amplitude_all_kernel(
-    const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs,
-    double2 *__restrict__ A, size_t ldA, int NA, int NM, unsigned ngroups, size_t f0) {
-    const unsigned group = blockIdx.x % ngroups;
-    const size_t frame = f0 + blockIdx.x / ngroups;
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int m0 = (group * WARPS + warp) * QPT;
-    if (m0 >= NM) return;
-
-    double qx[QPT], qy[QPT], qz[QPT], re[QPT], im[QPT];
-#pragma unroll
-    for (int k = 0; k < QPT; k++) {
-        qx[k] = __ldg(&qs[3 * (m0 + k)]);
-        qy[k] = __ldg(&qs[3 * (m0 + k) + 1]);
-        qz[k] = __ldg(&qs[3 * (m0 + k) + 2]);
-        re[k] = 0.0;
-        im[k] = 0.0;
-    }
-    const float *p = xyz + frame * (size_t)NA * 3;
-
-    int j = lane;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    double bj = 0.0;
-    if (j < NA) {
-        fx = __ldg(&p[3 * j]);
-        fy = __ldg(&p[3 * j + 1]);
-        fz = __ldg(&p[3 * j + 2]);
-        bj = __ldg(&b[j]);
-    }
-    while (j < NA) {
-        const double x = (double)fx, y = (double)fy, z = (double)fz;
-        const int bhi = __double2hiint(bj), blo = __double2loint(bj);
-        // prefetch the next atom of this lane while the FP64 pipe works on the current one
-        const int jn = j + 32;
-        if (jn < NA) {
-            fx = __ldg(&p[3 * jn]);
-            fy = __ldg(&p[3 * jn + 1]);
-            fz = __ldg(&p[3 * jn + 2]);
-            bj = __ldg(&b[jn]);
-        }
-#pragma unroll
-        for (int k = 0; k < QPT; k++) {
-            const double u = fma(z, qz[k], fma(y, qy[k], x * qx[k]));
-            sincos_qt_accumulate(u, bhi, blo, re[k], im[k]);
-        }
-        j = jn;
-    }
-#pragma unroll
-    for (int k = 0; k < QPT; k++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            re[k] += __shfl_xor_sync(0xffffffffu, re[k], o);
-            im[k] += __shfl_xor_sync(0xffffffffu, im[k], o);
-        }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < QPT; k++)
-            if (m0 + k < NM) A[(size_t)(m0 + k) * ldA + frame] = make_double2(re[k], im[k]);
-    }
-}
 
 // ---- K1, tiled variant: TMA bulk-staged atom tiles + mbarrier ring --------------------------------------
 // Same mapping as above (CTA = one frame x WARPS*QPT q-vectors) but the atoms of the frame stream through a
@@ -93,48 +28,8 @@ __global__ void __launch_bounds__(WARPS * 32) amplitude_all_kernel(
 // the same tile, so every coordinate is fetched from L2/HBM once per CTA and the consumer side sees ~30-cycle
 // LDS latency instead of global-load latency.  Frames whose byte offset is not 16-byte aligned (NA % 4 != 0)
 // use 4-byte cp.async (LDGSTS) by all threads on the same barriers (cp.async.mbarrier.arrive.noinc).
-namespace ptx {
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-}  // namespace ptx
 
-template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs,
     double2 *__restrict__ A, size_t ldA, int NA, int NM, unsigned ngroups, size_t f0, int use_bulk, int m_base) {
@@ -207,30 +102,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
         if (active) {
             const float *sx = s_xyz + (size_t)s * TILE * 3;
             const double *sb = s_b + (size_t)s * TILE;
-            if (PAIR) {
-                // two atoms per lane and iteration: 3 x LDS.64 + 1 x LDS.128 instead of 8 loads (24-byte lane stride is
-                // bank-conflict free), half the loop overhead per evaluation
-#pragma unroll 1
-                for (int j = 2 * lane; j < cnt; j += 64) {
-                    const float2 p0 = *reinterpret_cast<const float2 *>(sx + 3 * j);
-                    const float2 p1 = *reinterpret_cast<const float2 *>(sx + 3 * j + 2);
-                    const float2 p2 = *reinterpret_cast<const float2 *>(sx + 3 * j + 4);
-                    const double2 bb = *reinterpret_cast<const double2 *>(sb + j);
-                    const double x0 = (double)p0.x, y0 = (double)p0.y, z0 = (double)p1.x;
-                    const double x1 = (double)p1.y, y1 = (double)p2.x, z1 = (double)p2.y;
-                    const double b0 = bb.x, b1 = (j + 1 < cnt) ? bb.y : 0.0;
-#pragma unroll
-                    for (int k = 0; k < QPT; k++) {
-                        const double u0 = fma(z0, qz[k], fma(y0, qy[k], x0 * qx[k]));
-                        sincos_qt_accumulate3(u0, b0, re[k], im[k]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < QPT; k++) {
-                        const double u1 = fma(z1, qz[k], fma(y1, qy[k], x1 * qx[k]));
-                        sincos_qt_accumulate3(u1, b1, re[k], im[k]);
-                    }
-                }
-            } else {
 #pragma unroll 1
             for (int j = lane; j < cnt; j += 32) {
                 const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
@@ -238,9 +109,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
 #pragma unroll
                 for (int k = 0; k < QPT; k++) {
                     const double u = fma(z, qz[k], fma(y, qy[k], x * qx[k]));
-                    sincos_qt_accumulate2<ABL>(u, bj, re[k], im[k]);
+                    sincos_qt_accumulate2(u, bj, re[k], im[k]);
                 }
-            }
             }
         }
         __syncwarp();
@@ -262,41 +132,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_all_tiled_kernel(
     }
 }
 
-// ---- K1s, |q|-scan variant ---------------------------------------------------------------------------------
-// A Sassena scan evaluates the SAME orientation vectors at equally spaced |q| (scattering.vectors.scans with
-// exponent 1, parameters.cpp:1125-1189; init_subvectors scales unit vectors by |q|,
-// abstract_vectors_scatter_device.cpp:96-175).  For q_{n,m} = (s0 + n ds) v_m the phases of one (atom, v_m) pair form an
-// arithmetic progression, so
-//     exp(i q_{n,m}.r) = exp(i s0 v_m.r) * exp(i ds v_m.r)^n
-// and B consecutive |q| cost two sincos evaluations plus B-1 complex rotations (2 DMUL + 2 DFMA each) instead of
-// B sincos evaluations (19 FP64 instructions each).  |w| = 1 to 1 ulp, so the rotation chain is stable: after B <= 32
-// steps the accumulated relative error is <= ~2 B ulp (7e-15), far inside the 1e-9 tolerance.
-// One warp owns VPT orientation vectors, lanes stride over the atoms of the tile, every thread keeps B x VPT complex
-// accumulators in registers.  Same TMA ring as the tiled kernel.  A is [B][NM][ldA] (strideQ between |q| planes).
-struct ScanKappa {
-    double k[32];  // (pi/2) * (s_n - (s0 + n ds)): first/second-order phase correction per |q| of the pass (CORR)
-};
-
-// BVAR: the factors depend on |q| (X-ray form factors, background subtraction): b is [B][b_stride] and every tile
-// stages B factor rows; the recurrence then runs on the unit phasor and the accumulation is a DFMA with b_n.
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0, int BVAR = 0>
-__global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
+// ---- K1s with |q|-dependent factors ---------------------------------------------------------------------------
+// The |q|-scan kernels proper live in scan_sym.cu.  When the scattering factors depend on |q| (X-ray form factors,
+// background subtraction: scatter_factors.cpp:56-78) the symmetric form does not apply (the two |q| of a pair carry different
+// b), so this kernel runs the complex three-term recurrence z_{n+1} = 2 cos(ds sigma) z_n - z_{n-1} on the UNIT phasor of one
+// (atom, direction) pair and accumulates b_n z_n with one factor row per |q| staged next to the coordinates: per evaluation
+// 2 DFMA (recurrence) + 2 DFMA (accumulation).  A rounding error injected at step k reaches step n with gain
+// |sin((n-k+1) d)/sin d| <= n-k+1, so after B <= 24 steps the error is <= ~B^2/2 ulp.  One warp = one direction, lanes stride
+// over the atoms of the tile; b is [B][b_stride]; A is [B][NM][ldA] (strideQ between |q| planes).
+template <int B, int WARPS, int TILE, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) amplitude_scan_bvar_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ vs, double s0, double ds,
     double2 *__restrict__ A, size_t ldA, size_t strideQ, int NA, int NM, int nq_valid, unsigned ngroups, size_t f0,
-    int use_bulk, const ScanKappa kap, size_t b_stride) {
-    static_assert(!CORR || (RECUR && VPT == 1), "the corrected variant is built on the recurrence form, one direction per warp");
-    static_assert(!BVAR || (RECUR && VPT == 1 && !CORR && B <= 31), "the |q|-dependent-factor variant: recurrence form, plain");
-    constexpr int NB = BVAR ? B : 1;  // factor rows per tile
+    int use_bulk, size_t b_stride) {
+    static_assert(B >= 2 && B <= 31, "one factor row per lane 1..B of the issuing warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_xyz = reinterpret_cast<float *>(smem_raw);                                  // [STAGES][TILE*3]
-    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);  // [STAGES][NB][TILE]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8 * NB));
+    double *s_b = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * TILE * 3 * 4);  // [STAGES][B][TILE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TILE * (3 * 4 + 8 * B));
     uint64_t *empty = full + STAGES;
 
     const unsigned group = blockIdx.x % ngroups;
     const size_t frame = f0 + blockIdx.x / ngroups;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = (group * WARPS + warp) * VPT;
+    const int m0 = group * WARPS + warp;
     const float *p = xyz + frame * (size_t)NA * 3;
     const int ntiles = (NA + TILE - 1) / TILE;
 
@@ -310,7 +169,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     __syncthreads();
 
     // Called by every thread at a converged point.  Bulk path: warp 0 issues — lane 0 waits for the slot and posts the
-    // byte count, then lane 0 copies the coordinates and lanes 1..NB one factor row each.
+    // byte count, then lane 0 copies the coordinates and lanes 1..B one factor row each.
     auto issue = [&](int t) {
         const int s = t % STAGES;
         const int a0 = t * TILE;
@@ -319,12 +178,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
             if (warp == 0) {
                 if (lane == 0) {
                     if (t >= STAGES) ptx::mbar_wait(&empty[s], (unsigned)((t / STAGES - 1) & 1));
-                    ptx::mbar_expect_tx(&full[s], (unsigned)cnt * (12u + 8u * NB));
+                    ptx::mbar_expect_tx(&full[s], (unsigned)cnt * (12u + 8u * B));
                     ptx::bulk_g2s(s_xyz + (size_t)s * TILE * 3, p + (size_t)a0 * 3, (unsigned)cnt * 12u, &full[s]);
                 }
                 __syncwarp();
-                if (lane >= 1 && lane <= NB)
-                    ptx::bulk_g2s(s_b + ((size_t)s * NB + (lane - 1)) * TILE, b + (size_t)(lane - 1) * b_stride + a0,
+                if (lane >= 1 && lane <= B)
+                    ptx::bulk_g2s(s_b + ((size_t)s * B + (lane - 1)) * TILE, b + (size_t)(lane - 1) * b_stride + a0,
                                   (unsigned)cnt * 8u, &full[s]);
             }
         } else {
@@ -332,8 +191,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
             float *dx = s_xyz + (size_t)s * TILE * 3;
             const float *sx = p + (size_t)a0 * 3;
             for (int i = tid; i < cnt * 3; i += WARPS * 32) ptx::cp_async4(dx + i, sx + i);
-            for (int r = 0; r < NB; r++) {
-                float *db = reinterpret_cast<float *>(s_b + ((size_t)s * NB + r) * TILE);
+            for (int r = 0; r < B; r++) {
+                float *db = reinterpret_cast<float *>(s_b + ((size_t)s * B + r) * TILE);
                 const float *sb = reinterpret_cast<const float *>(b + (size_t)r * b_stride + a0);
                 for (int i = tid; i < cnt * 2; i += WARPS * 32) ptx::cp_async4(db + i, sb + i);
             }
@@ -343,34 +202,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
     for (int t = 0; t < STAGES - 1 && t < ntiles; t++) issue(t);
 
     const bool active = m0 < NM;
-    double vx[VPT], vy[VPT], vz[VPT];
-    double re[VPT][B], im[VPT][B];
-    // CORR: |q| values that deviate from the arithmetic progression by e_n (the reference builds scans from float-rounded
-    // fractions, parameters.cpp:1151).  exp(i (s_n + e_n) sigma) = z_n (1 + i th - th^2/2 + O(th^3)), th = kap_n sigma:
-    // first order needs D_n = sum b sigma z_n (FP64), second order E_n = sum b sigma^2 z_n, whose weight kap^2/2 is
-    // ~1e-10, so an FP32 copy of the recurrence on the FP32 pipe is accurate enough (4 issue slots instead of 6 FP64-pipe cycles).
-    double dre[CORR ? B : 1], dim[CORR ? B : 1];
-    float ere[CORR ? B : 1], eim[CORR ? B : 1];
-    if (CORR) {
+    const double vx = __ldg(&vs[3 * m0]), vy = __ldg(&vs[3 * m0 + 1]), vz = __ldg(&vs[3 * m0 + 2]);  // zero padded past NM
+    double re[B], im[B];
 #pragma unroll
-        for (int n = 0; n < B; n++) {
-            dre[n] = 0.0;
-            dim[n] = 0.0;
-            ere[n] = 0.f;
-            eim[n] = 0.f;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < VPT; k++) {
-        vx[k] = __ldg(&vs[3 * (m0 + k)]);  // vs is zero padded past NM
-        vy[k] = __ldg(&vs[3 * (m0 + k) + 1]);
-        vz[k] = __ldg(&vs[3 * (m0 + k) + 2]);
-#pragma unroll
-        for (int n = 0; n < B; n++) {
-            re[k][n] = 0.0;
-            im[k][n] = 0.0;
-        }
-    }
+    for (int n = 0; n < B; n++) re[n] = im[n] = 0.0;
 
     for (int t = 0; t < ntiles; t++) {
         if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);
@@ -379,107 +214,38 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
         ptx::mbar_wait(&full[s], (unsigned)((t / STAGES) & 1));
         if (active) {
             const float *sx = s_xyz + (size_t)s * TILE * 3;
-            const double *sb = s_b + (size_t)s * NB * TILE;
-#pragma unroll 1  // (two atoms in flight per thread measured no faster for the corrected variant)
+            const double *sb = s_b + (size_t)s * B * TILE;
+#pragma unroll 1
             for (int j = lane; j < cnt; j += 32) {
                 const double x = (double)sx[3 * j], y = (double)sx[3 * j + 1], z = (double)sx[3 * j + 2];
-                const double bj = BVAR ? 1.0 : sb[j];
+                const double sigma = fma(z, vz, fma(y, vy, x * vx));  // quarter turns per unit |q|
+                double zi, zr, sw, cw;
+                sincos_qt(s0 * sigma, zi, zr);
+                sincos_qt(ds * sigma, sw, cw);
+                const double c2 = cw + cw;
+                double pr = zr, pi = zi;  // z_{n-1}
+                re[0] = fma(sb[j], zr, re[0]);
+                im[0] = fma(sb[j], zi, im[0]);
+                {
+                    const double t1 = zi * sw, t2 = zi * cw;
+                    const double nr = fma(zr, cw, -t1);
+                    zi = fma(zr, sw, t2);
+                    zr = nr;
+                    const double b1 = sb[TILE + j];
+                    re[1] = fma(b1, zr, re[1]);
+                    im[1] = fma(b1, zi, im[1]);
+                }
 #pragma unroll
-                for (int k = 0; k < VPT; k++) {
-                    const double sigma = fma(z, vz[k], fma(y, vy[k], x * vx[k]));  // quarter turns per unit |q|
-                    double sn, cs, sw, cw;
-                    sincos_qt(s0 * sigma, sn, cs);
-                    sincos_qt(ds * sigma, sw, cw);
-                    double zr = bj * cs, zi = bj * sn;
-                    if (RECUR == 0) {
-#pragma unroll
-                        for (int n = 0; n < B; n++) {
-                            re[k][n] += zr;
-                            im[k][n] += zi;
-                            if (n + 1 < B) {
-                                const double t1 = zi * sw, t2 = zi * cw;
-                                const double nr = fma(zr, cw, -t1);
-                                zi = fma(zr, sw, t2);
-                                zr = nr;
-                            }
-                        }
-                    } else {
-                        // three-term recurrence z_{n+1} = 2 cos(d) z_n - z_{n-1} on both components: 2 DFMA per step.
-                        // A rounding error injected at step k reaches step n with gain |sin((n-k+1)d)/sin d| <= n-k+1, so
-                        // after B steps the error is <= ~B^2/2 ulp of |z| (B = 32: 6e-14) for every d, including d -> 0.
-                        const double c2 = cw + cw;
-                        double pr = zr, pi = zi;  // z_{n-1}
-                        float fpr = 0.f, fpi = 0.f, fzr = 0.f, fzi = 0.f, fc2 = 0.f, fs2 = 0.f;
-                        if (BVAR) {
-                            const double b0 = sb[j];
-                            re[k][0] = fma(b0, zr, re[k][0]);
-                            im[k][0] = fma(b0, zi, im[k][0]);
-                        } else {
-                            re[k][0] += zr;
-                            im[k][0] += zi;
-                        }
-                        if (CORR) {
-                            dre[0] = fma(sigma, zr, dre[0]);
-                            dim[0] = fma(sigma, zi, dim[0]);
-                            const float fs = (float)sigma;
-                            fs2 = fs * fs;
-                            fpr = (float)zr;
-                            fpi = (float)zi;
-                            fc2 = (float)c2;
-                            ere[0] = fmaf(fs2, fpr, ere[0]);
-                            eim[0] = fmaf(fs2, fpi, eim[0]);
-                        }
-                        if (B > 1) {
-                            const double t1 = zi * sw, t2 = zi * cw;
-                            const double nr = fma(zr, cw, -t1);
-                            zi = fma(zr, sw, t2);
-                            zr = nr;
-                            if (BVAR) {
-                                const double b1 = sb[TILE + j];
-                                re[k][1] = fma(b1, zr, re[k][1]);
-                                im[k][1] = fma(b1, zi, im[k][1]);
-                            } else {
-                                re[k][1] += zr;
-                                im[k][1] += zi;
-                            }
-                            if (CORR) {
-                                dre[1] = fma(sigma, zr, dre[1]);
-                                dim[1] = fma(sigma, zi, dim[1]);
-                                fzr = (float)zr;
-                                fzi = (float)zi;
-                                ere[1] = fmaf(fs2, fzr, ere[1]);
-                                eim[1] = fmaf(fs2, fzi, eim[1]);
-                            }
-                        }
-#pragma unroll
-                        for (int n = 2; n < B; n++) {
-                            const double nr = fma(c2, zr, -pr);
-                            const double ni = fma(c2, zi, -pi);
-                            pr = zr;
-                            pi = zi;
-                            zr = nr;
-                            zi = ni;
-                            if (BVAR) {
-                                const double bn = sb[n * TILE + j];
-                                re[k][n] = fma(bn, zr, re[k][n]);
-                                im[k][n] = fma(bn, zi, im[k][n]);
-                            } else {
-                                re[k][n] += zr;
-                                im[k][n] += zi;
-                            }
-                            if (CORR) {
-                                dre[n] = fma(sigma, zr, dre[n]);
-                                dim[n] = fma(sigma, zi, dim[n]);
-                                const float fnr = fmaf(fc2, fzr, -fpr), fni = fmaf(fc2, fzi, -fpi);
-                                fpr = fzr;
-                                fpi = fzi;
-                                fzr = fnr;
-                                fzi = fni;
-                                ere[n] = fmaf(fs2, fzr, ere[n]);
-                                eim[n] = fmaf(fs2, fzi, eim[n]);
-                            }
-                        }
-                    }
+                for (int n = 2; n < B; n++) {
+                    const double nr = fma(c2, zr, -pr);
+                    const double ni = fma(c2, zi, -pi);
+                    pr = zr;
+                    pi = zi;
+                    zr = nr;
+                    zi = ni;
+                    const double bn = sb[n * TILE + j];
+                    re[n] = fma(bn, zr, re[n]);
+                    im[n] = fma(bn, zi, im[n]);
                 }
             }
         }
@@ -487,34 +253,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) amplitude_scan_kernel(
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
     }
     if (!active) return;
-    if (CORR) {
-        // fold the corrections into the lane sums before the warp reduction
 #pragma unroll
-        for (int n = 0; n < B; n++) {
-            const double kn = kap.k[n], hk = 0.5 * kn * kn;
-            re[0][n] = fma(-hk, (double)ere[n], fma(-kn, dim[n], re[0][n]));
-            im[0][n] = fma(-hk, (double)eim[n], fma(kn, dre[n], im[0][n]));
-        }
-    }
+    for (int n = 0; n < B; n++) {
 #pragma unroll
-    for (int k = 0; k < VPT; k++) {
-#pragma unroll
-        for (int n = 0; n < B; n++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                re[k][n] += __shfl_xor_sync(0xffffffffu, re[k][n], o);
-                im[k][n] += __shfl_xor_sync(0xffffffffu, im[k][n], o);
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            re[n] += __shfl_xor_sync(0xffffffffu, re[n], o);
+            im[n] += __shfl_xor_sync(0xffffffffu, im[n], o);
         }
     }
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < VPT; k++)
-            if (m0 + k < NM) {
-#pragma unroll
-                for (int n = 0; n < B; n++)
-                    if (n < nq_valid) A[(size_t)n * strideQ + (size_t)(m0 + k) * ldA + frame] = make_double2(re[k][n], im[k][n]);
-            }
+        for (int n = 0; n < B; n++)
+            if (n < nq_valid) A[(size_t)n * strideQ + (size_t)m0 * ldA + frame] = make_double2(re[n], im[n]);
     }
 }
 
@@ -785,27 +535,33 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters)
 
 
 namespace {
-template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: it is set before every launch (a library call
+// of well under a microsecond) rather than once per process, so a second context on another device gets it too.
+template <typename Kern>
+bool allow_smem(Kern kern, size_t smem) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+}
+
+// TMA bulk copies need 16-byte aligned global addresses: frame stride NA*12 bytes and the base pointers
+bool bulk_ok(const float *d_xyz, const double *d_b, size_t NA) {
+    return (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
+}
+
+template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
 int launch_tiled_part(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
-                      size_t NM, size_t f0, size_t nf, cudaStream_t st, int m_base, int nvec, int warps) {
-    // covers q-vectors [m_base, m_base + nvec) with CTAs of `warps` warps x QPT vectors
-    const unsigned per_cta = QPT * warps;
+                      size_t NM, size_t f0, size_t nf, cudaStream_t st, int m_base, int nvec) {
+    // covers q-vectors [m_base, m_base + nvec) with CTAs of WARPS warps x QPT vectors
+    const unsigned per_cta = QPT * WARPS;
     const unsigned ngroups = (unsigned)((nvec + per_cta - 1) / per_cta);
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t);
-    auto kern = amplitude_all_tiled_kernel<QPT, WARPS, TILE, STAGES, MINB, ABL, PAIR>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    // TMA bulk copies need 16-byte aligned global addresses: frame stride NA*12 bytes and the base pointers
-    const int use_bulk = (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
+    auto kern = amplitude_all_tiled_kernel<QPT, WARPS, TILE, STAGES, MINB>;
+    if (!allow_smem(kern, smem)) return 0;
+    const int use_bulk = bulk_ok(d_xyz, d_b, NA);
     int launches = 0;
-    const size_t max_frames = (size_t)0x7fffffff / ngroups;
+    const size_t max_frames = (size_t)0x7fffffff / ngroups;  // grid.x is limited to 2^31-1
     for (size_t done = 0; done < nf;) {
         size_t cnt = nf - done < max_frames ? nf - done : max_frames;
-        kern<<<(unsigned)(cnt * ngroups), warps * 32, smem, st>>>(d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups,
+        kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups,
                                                                   f0 + done, use_bulk, m_base);
         launches++;
         done += cnt;
@@ -813,12 +569,14 @@ int launch_tiled_part(const float *d_xyz, const double *d_b, const double *d_qs,
     return launches;
 }
 
-template <int QPT, int WARPS, int TILE, int STAGES, int MINB, int ABL = 0, int PAIR = 0>
-int launch_tiled(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
-                 size_t NM, size_t f0, size_t nf, cudaStream_t st) {
-    return launch_tiled_part<QPT, WARPS, TILE, STAGES, MINB, ABL, PAIR>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0,
-                                                                        (int)NM, WARPS);
-}
+// The uniform-q kernel reads its q-vectors from the __constant__ buffer c_q, one copy per device and shared by every context
+// and stream on it: uses are serialised per device (an event recorded after the last launch, waited for before the next
+// upload), so two ScatterContexts on one GPU cannot overwrite each other's vectors.
+struct UqGuard {
+    std::mutex mu;
+    cudaEvent_t last[64] = {};
+};
+UqGuard g_uq;
 
 template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
 int launch_uq_part(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
@@ -826,18 +584,19 @@ int launch_uq_part(const float *d_xyz, const double *d_b, const double *d_qs, do
     // q-vectors [m_base, m_base+nvec): every CTA of 8 warps works on QPT vectors and splits the atoms over its warps
     const size_t smem = (size_t)STAGES * TILE * 20 + 2 * STAGES * sizeof(uint64_t) + (size_t)WARPS * 2 * QPT * 8;
     auto kern = amplitude_all_uq_kernel<QPT, WARPS, TILE, STAGES, MINB>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    const int use_bulk = (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
+    if (!allow_smem(kern, smem)) return 0;
+    const int use_bulk = bulk_ok(d_xyz, d_b, NA);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_uq.mu);
+    cudaEvent_t &ev = g_uq.last[dev & 63];
+    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     int launches = 0;
     const size_t chunk = (UQ_MAXQ / QPT) * QPT;
     for (size_t m0 = 0; m0 < nvec; m0 += chunk) {
         const size_t cnt_m = nvec - m0 < chunk ? nvec - m0 : chunk;
         const size_t padded = ((cnt_m + QPT - 1) / QPT) * QPT;  // d_qs carries >= 8 zero vectors of slack past NM
+        cudaStreamWaitEvent(st, ev, 0);
         cudaMemcpyToSymbolAsync(c_q, d_qs + 3 * (m_base + m0), padded * 3 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st);
         const unsigned ngroups = (unsigned)(padded / QPT);
         const size_t max_frames = (size_t)0x7fffffff / ngroups;
@@ -848,26 +607,24 @@ int launch_uq_part(const float *d_xyz, const double *d_b, const double *d_qs, do
             launches++;
             done += cnt;
         }
+        cudaEventRecord(ev, st);
     }
     return launches;
 }
+}  // namespace
 
-template <int QPT, int WARPS, int TILE, int STAGES, int MINB>
-int launch_uq(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
-              size_t NM, size_t f0, size_t nf, cudaStream_t st) {
-    return launch_uq_part<QPT, WARPS, TILE, STAGES, MINB>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0, NM);
-}
+// q-vectors per CTA of the tiled kernel: the q array must be zero padded to a multiple of this
+int amplitude_all_qpad() { return 48; }
 
-// default path: full CTAs of 8 warps x 6 vectors (each warp owns 6 vectors), then the remainder r = NM mod 48 with the
-// uniform-q kernel (a CTA owns QPT vectors and its 8 warps split the atoms), QPT in 4..8 chosen to cover r with the
-// least padding.  Keeps full occupancy for any NM: with the subvectors of a |q| sharded over 8 GPUs (62-63 each)
-// padding to 48 would waste 35 %, and small-CTA tail launches ran at 77 % efficiency.
-int launch_tiled_exact(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA, size_t NA,
-                       size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+// Full CTAs of 8 warps x 6 vectors (each warp owns 6 vectors), then the remainder r = NM mod 48 with the uniform-q kernel (a
+// CTA owns QPT vectors and its 8 warps split the atoms), QPT in 4..8 chosen to cover r with the least padding.  Keeps full
+// occupancy for any NM: with the subvectors of a |q| sharded over 8 GPUs (62-63 each) padding to 48 would waste 35 %.
+int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
+                         size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
+    if (nf == 0 || NM == 0) return 0;
     int launches = 0;
     const size_t full = (NM / 48) * 48;
-    if (full > 0)
-        launches += launch_tiled_part<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0, (int)full, 8);
+    if (full > 0) launches += launch_tiled_part<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st, 0, (int)full);
     const size_t r = NM - full;
     if (r > 0) {
         int best_q = 8;
@@ -890,223 +647,56 @@ int launch_tiled_exact(const float *d_xyz, const double *d_b, const double *d_qs
     return launches;
 }
 
-int k1_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SASSENA_K1_VARIANT");
-        v = e ? atoi(e) : 7;
-    }
-    return v;
-}
-}  // namespace
-
-// q-vectors per CTA of the active variant: the q array must be zero padded to a multiple of this
-int amplitude_all_qpad() {
-    switch (k1_variant()) {
-        case 7: case 8: case 20: case 21: case 30: case 31: case 32: case 36: return 48;
-        case 33: return 72;
-        case 34: return 56;
-        case 9: case 35: return 40;
-        case 2: case 3: case 4: return 32;
-        default: return 64;
-    }
-}
-
-int launch_amplitude_all(const float *d_xyz, const double *d_b, const double *d_qs, double2 *d_A, size_t ldA,
-                         size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st) {
-    if (nf == 0 || NM == 0) return 0;
-    switch (k1_variant()) {
-        case 1: return launch_tiled<8, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 2: return launch_tiled<4, 8, 512, 4, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 3: return launch_tiled<4, 8, 512, 4, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 4: return launch_tiled<8, 4, 512, 4, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 5: return launch_tiled<8, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 6: return launch_tiled<4, 16, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 7: return launch_tiled_exact(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 36: return launch_tiled<6, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 20: return launch_tiled<6, 8, 512, 4, 2, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 21: return launch_tiled<6, 8, 512, 4, 2, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 8: return launch_tiled<6, 8, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 9: return launch_tiled<5, 8, 512, 4, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 30: return launch_tiled<6, 8, 512, 4, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 31: return launch_tiled<6, 8, 1024, 3, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 32: return launch_tiled<6, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 33: return launch_tiled<6, 12, 512, 4, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 34: return launch_tiled<7, 8, 512, 4, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 35: return launch_tiled<5, 8, 512, 4, 2, 0, 1>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 10: return launch_uq<8, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 11: return launch_uq<8, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 12: return launch_uq<6, 8, 1024, 3, 3>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 13: return launch_uq<4, 8, 1024, 3, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 14: return launch_uq<8, 4, 1024, 3, 4>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        case 15: return launch_uq<10, 8, 1024, 3, 2>(d_xyz, d_b, d_qs, d_A, ldA, NA, NM, f0, nf, st);
-        default: break;
-    }
-    const unsigned per_cta = K1_QPT * K1_WARPS;
-    const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
-    int launches = 0;
-    // grid.x is limited to 2^31-1: chunk frames if needed
-    const size_t max_frames = (size_t)0x7fffffff / ngroups;
-    for (size_t done = 0; done < nf;) {
-        size_t cnt = nf - done < max_frames ? nf - done : max_frames;
-        amplitude_all_kernel<K1_QPT, K1_WARPS><<<(unsigned)(cnt * ngroups), K1_WARPS * 32, 0, st>>>(
-            d_xyz, d_b, d_qs, d_A, ldA, (int)NA, (int)NM, ngroups, f0 + done);
-        launches++;
-        done += cnt;
-    }
-    return launches;
-}
-
 namespace {
-template <int B, int VPT, int WARPS, int TILE, int STAGES, int MINB, int RECUR = 0, int CORR = 0, int BVAR = 0>
-int launch_scan_part(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq_valid,
-                     double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st,
-                     const ScanKappa &kap = ScanKappa(), size_t b_stride = 0) {
-    const unsigned per_cta = VPT * WARPS;
-    const unsigned ngroups = (unsigned)((NM + per_cta - 1) / per_cta);
-    const size_t smem = (size_t)STAGES * TILE * (12 + 8 * (BVAR ? B : 1)) + 2 * STAGES * sizeof(uint64_t);
-    auto kern = amplitude_scan_kernel<B, VPT, WARPS, TILE, STAGES, MINB, RECUR, CORR, BVAR>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    const int use_bulk = (NA % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(d_b) & 15) == 0);
-    int launches = 0;
-    const size_t max_frames = (size_t)0x7fffffff / ngroups;
-    for (size_t done = 0; done < nf;) {
-        size_t cnt = nf - done < max_frames ? nf - done : max_frames;
-        kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_vs, s0, ds, d_A, ldA, strideQ, (int)NA,
-                                                                  (int)NM, nq_valid, ngroups, f0 + done, use_bulk, kap, b_stride);
-        launches++;
-        done += cnt;
-    }
-    return launches;
-}
-
-int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
-struct ScanArgs {
-    const float *d_xyz;
-    const double *d_b, *d_vs;
-    double s, ds;
-    int valid;
-    double2 *A;
-    size_t ldA, strideQ, NA, NM, f0, nf;
-    cudaStream_t st;
-    ScanKappa kap;
-};
-
-template <int B, int WARPS, int MINB, int RECUR, int CORR = 0>
-int scan_pass(const ScanArgs &a) {
-    return launch_scan_part<B, 1, WARPS, 512, 4, MINB, RECUR, CORR>(a.d_xyz, a.d_b, a.d_vs, a.s, a.ds, a.valid, a.A, a.ldA,
-                                                                    a.strideQ, a.NA, a.NM, a.f0, a.nf, a.st, a.kap);
-}
-
-// one pass over `B` |q| values (B in 4, 8, ..., 32); warps = 8 or 12 per CTA
-int scan_dispatch(int B, int warps, int recur, const ScanArgs &a) {
-    if (!recur) {
-        switch (B) {
-            case 4: return scan_pass<4, 8, 2, 0>(a);
-            case 8: return scan_pass<8, 8, 2, 0>(a);
-            case 16: return scan_pass<16, 8, 2, 0>(a);
-            case 24: return scan_pass<24, 8, 1, 0>(a);
-            default: return scan_pass<32, 8, 1, 0>(a);
-        }
-    }
-    if (warps == 12) {
-        switch (B) {
-            case 4: return scan_pass<4, 12, 1, 1>(a);
-            case 8: return scan_pass<8, 12, 1, 1>(a);
-            case 12: return scan_pass<12, 12, 1, 1>(a);
-            case 16: return scan_pass<16, 12, 1, 1>(a);
-            case 20: return scan_pass<20, 12, 1, 1>(a);
-            case 24: return scan_pass<24, 12, 1, 1>(a);
-            case 28: return scan_pass<28, 12, 1, 1>(a);
-            default: return scan_pass<32, 12, 1, 1>(a);
-        }
-    }
-    switch (B) {
-        case 4: return scan_pass<4, 8, 2, 1>(a);
-        case 8: return scan_pass<8, 8, 2, 1>(a);
-        case 12: return scan_pass<12, 8, 2, 1>(a);
-        case 16: return scan_pass<16, 8, 2, 1>(a);
-        case 20: return scan_pass<20, 8, 1, 1>(a);
-        case 24: return scan_pass<24, 8, 1, 1>(a);
-        case 28: return scan_pass<28, 8, 1, 1>(a);
-        default: return scan_pass<32, 8, 1, 1>(a);
-    }
-}
-
 // |q|-dependent factors: B factor rows per 128-atom tile in the ring
 template <int B>
-int scan_pass_bvar(const ScanArgs &a, size_t b_stride) {
-    return launch_scan_part<B, 1, 12, 128, 4, 1, 1, 0, 1>(a.d_xyz, a.d_b, a.d_vs, a.s, a.ds, a.valid, a.A, a.ldA, a.strideQ, a.NA,
-                                                          a.NM, a.f0, a.nf, a.st, a.kap, b_stride);
-}
-int scan_dispatch_bvar(int B, const ScanArgs &a, size_t b_stride) {
-    switch (B) {
-        case 4: return scan_pass_bvar<4>(a, b_stride);
-        case 8: return scan_pass_bvar<8>(a, b_stride);
-        case 12: return scan_pass_bvar<12>(a, b_stride);
-        case 16: return scan_pass_bvar<16>(a, b_stride);
-        case 20: return scan_pass_bvar<20>(a, b_stride);
-        default: return scan_pass_bvar<24>(a, b_stride);  // 28 would spill
+int launch_scan_bvar(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq_valid,
+                     double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM, size_t f0, size_t nf, cudaStream_t st,
+                     size_t b_stride) {
+    constexpr int WARPS = 12, TILE = 128, STAGES = 4;
+    const unsigned ngroups = (unsigned)((NM + WARPS - 1) / WARPS);
+    const size_t smem = (size_t)STAGES * TILE * (12 + 8 * B) + 2 * STAGES * sizeof(uint64_t);
+    auto kern = amplitude_scan_bvar_kernel<B, WARPS, TILE, STAGES>;
+    if (!allow_smem(kern, smem)) return -1;
+    const int use_bulk = bulk_ok(d_xyz, d_b, NA) && (b_stride % 2 == 0);
+    int launches = 0;
+    const size_t max_frames = (size_t)0x7fffffff / ngroups;
+    for (size_t done = 0; done < nf;) {
+        size_t cnt = nf - done < max_frames ? nf - done : max_frames;
+        kern<<<(unsigned)(cnt * ngroups), WARPS * 32, smem, st>>>(d_xyz, d_b, d_vs, s0, ds, d_A, ldA, strideQ, (int)NA, (int)NM,
+                                                                  nq_valid, ngroups, f0 + done, use_bulk, b_stride);
+        launches++;
+        done += cnt;
     }
-}
-
-// corrected variant: three accumulator sets per |q| (A, D in FP64, E in FP32), so passes are shorter
-int scan_dispatch_corr(int B, int warps, const ScanArgs &a) {
-    if (warps == 12) {
-        switch (B) {
-            case 4: return scan_pass<4, 12, 1, 1, 1>(a);
-            case 8: return scan_pass<8, 12, 1, 1, 1>(a);
-            default: return scan_pass<12, 12, 1, 1, 1>(a);
-        }
-    }
-    switch (B) {
-        case 4: return scan_pass<4, 8, 1, 1, 1>(a);
-        case 8: return scan_pass<8, 8, 1, 1, 1>(a);
-        case 12: return scan_pass<12, 8, 1, 1, 1>(a);
-        case 16: return scan_pass<16, 8, 1, 1, 1>(a);
-        default: return scan_pass<20, 8, 1, 1, 1>(a);
-    }
+    return launches;
 }
 }  // namespace
 
 // d_vs padding: a multiple of the directions per CTA (8 or 12 warps, one direction each)
 int amplitude_scan_qpad() { return 24; }
 
-// largest pass (|q| values evaluated by one launch) of the plain / corrected scan kernel
-int amplitude_scan_max_pass(int corrected) {
-    static const int plain = std::min(32, std::max(4, env_int("SASSENA_SCAN_B", 28)));
-    static const int corr = std::min(20, std::max(4, env_int("SASSENA_SCAN_CORR_B", 16)));
-    return corrected == 2 ? std::min(plain, 24) : corrected ? corr : plain;  // 2: |q|-dependent factors
-}
+// largest pass (|q| values evaluated by one launch): 0 plain, 1 corrected (scan_sym.cu), 2 |q|-dependent factors
+int amplitude_scan_max_pass(int kind) { return kind == 2 ? 24 : amplitude_scan_sym_max_pass(kind); }
 
 int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
                                const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
                                size_t f0, size_t nf, cudaStream_t st, size_t b_stride) {
     if (nf == 0 || NM == 0 || nq <= 0) return 0;
-    static const int warps = env_int("SASSENA_SCAN_WARPS", 12), recur = env_int("SASSENA_SCAN_RECUR", 1),
-                     cwarps = env_int("SASSENA_SCAN_CORR_WARPS", 8);
-    int B = ((nq + 3) / 4) * 4;
-    ScanArgs a{d_xyz, d_b, d_vs, s0, ds, nq, d_A, ldA, strideQ, NA, NM, f0, nf, st, ScanKappa()};
-    if (b_stride) {  // d_b holds one factor row per |q| of the pass
-        if (kappa || B > 24) return -1;
-        return scan_dispatch_bvar(B, a, b_stride);
+    if (!b_stride)
+        return launch_amplitude_scan_sym_pass(d_xyz, d_b, d_vs, s0, ds, nq, kappa, d_A, ldA, strideQ, NA, NM, f0, nf, st);
+    // d_b holds one factor row per |q| of the pass
+    if (kappa || nq > 24) return -1;
+#define SASS_BVAR(BB) \
+    return launch_scan_bvar<BB>(d_xyz, d_b, d_vs, s0, ds, nq, d_A, ldA, strideQ, NA, NM, f0, nf, st, b_stride)
+    switch (((std::max(nq, 2) + 3) / 4) * 4) {
+        case 4: SASS_BVAR(4);
+        case 8: SASS_BVAR(8);
+        case 12: SASS_BVAR(12);
+        case 16: SASS_BVAR(16);
+        case 20: SASS_BVAR(20);
+        default: SASS_BVAR(24);
     }
-    if (kappa) {
-        if (B > 20 || (cwarps == 12 && B > 12)) return -1;
-        for (int n = 0; n < 32; n++) a.kap.k[n] = n < nq ? kappa[n] : 0.0;
-        return scan_dispatch_corr(B, cwarps, a);
-    }
-    if (B > 32) return -1;
-    return scan_dispatch(B, warps, recur, a);
+#undef SASS_BVAR
 }
 
 int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,

@@ -338,11 +338,8 @@ int run_colfft(const CorrPlan *p, const void *in, size_t ld_in, size_t ntl, int 
     const int cols = pick_cols(p->log2N1, p->log2N2);
     const size_t smem = ((size_t)cols << p->log2N1) * sizeof(double2);
     const unsigned ntiles = (1u << p->log2N2) / cols;
-    static bool attr_set = false;
-    if (!attr_set || smem > 48 * 1024) {
-        cudaFuncSetAttribute(corr_colfft_kernel<LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    // per-device attribute, set before every launch (see amplitude.cu allow_smem)
+    cudaFuncSetAttribute(corr_colfft_kernel<LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int launches = 0;
     const size_t max_tl = (size_t)0x7fffffff / ntiles;
     for (size_t done = 0; done < ntl;) {
@@ -430,11 +427,7 @@ int corr_power_accumulate(const CorrPlan *p, const double2 *d_A, size_t ldA, siz
     int n = run_colfft<LOAD_TIMELINE>(p, d_A, ldA, nt, -1, Y, st);
     const size_t per_chunk = (nt + chunks - 1) / chunks;
     const size_t smem = sizeof(double2) << p->log2N2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(corr_rowfft_kernel<OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(corr_rowfft_kernel<OUT_POWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     corr_rowfft_kernel<OUT_POWER><<<dim3((unsigned)N1, (unsigned)chunks), FFT_THREADS, smem, st>>>(
         Y, nt, per_chunk, p->NF, p->log2N1, p->log2N2, p->d_tw, ilog2_ceil(p->Nmax), -1, p->d_w, Ppart, a_part, nullptr,
         1.0, 0);
@@ -450,11 +443,7 @@ int corr_finalize(const CorrPlan *p, const double *d_P, void *d_work, double2 *d
     double2 *Y = reinterpret_cast<double2 *>(d_work);
     int n = run_colfft<LOAD_REALPERM>(p, d_P, p->L, 1, +1, Y, st);
     const size_t smem = sizeof(double2) << p->log2N2;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(corr_rowfft_kernel<OUT_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(corr_rowfft_kernel<OUT_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     corr_rowfft_kernel<OUT_FINAL><<<dim3(1u << p->log2N1, 1), FFT_THREADS, smem, st>>>(
         Y, 1, 1, p->NF, p->log2N1, p->log2N2, p->d_tw, ilog2_ceil(p->Nmax), +1, nullptr, nullptr, nullptr, d_out, scale,
         conj_out);

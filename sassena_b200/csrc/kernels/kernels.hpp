@@ -26,6 +26,17 @@ int amplitude_scan_max_pass(int kind);  // 0 plain, 1 corrected, 2 |q|-dependent
 int launch_amplitude_scan_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
                                const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
                                size_t f0, size_t nf, cudaStream_t st, size_t b_stride = 0);
+// (pi/2) * (s_n - (s0 + n ds)): first/second-order phase correction per |q| of a pass of the corrected scan kernel
+struct ScanKappa {
+    double k[32];
+};
+// symmetric (Chebyshev) form of the scan kernel, scan_sym.cu: passes of up to amplitude_scan_sym_max_pass(corrected) |q|
+// values, uniform factors only; same arguments as launch_amplitude_scan_pass
+int amplitude_scan_sym_qpad();
+int amplitude_scan_sym_max_pass(int corrected);
+int launch_amplitude_scan_sym_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
+                                   const double *kappa, double2 *d_A, size_t ldA, size_t strideQ, size_t NA, size_t NM,
+                                   size_t f0, size_t nf, cudaStream_t st);
 // max over the buffer of |x| (n floats); result in *d_out (float, device)
 int launch_max_abs(const float *d_x, size_t n, float *d_out, cudaStream_t st);
 int launch_amplitude_self(const float *d_xyz_by_atom, const double *d_b, const double *d_qs, double2 *d_A,

@@ -1068,11 +1068,7 @@ void launch_fused(int log2N, dim3 grid, cudaStream_t st, const float *xyz, const
     const size_t smem = sf_smem_bytes(log2N);
 #define SF_CASE(LN)                                                                                                    \
     case LN: {                                                                                                         \
-        static bool attr = false;                                                                                      \
-        if (!attr) {                                                                                                   \
-            cudaFuncSetAttribute(self_fused_kernel<LN, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            attr = true;                                                                                               \
-        }                                                                                                              \
+        cudaFuncSetAttribute(self_fused_kernel<LN, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         self_fused_kernel<LN, GEN><<<grid, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, ntl, R, tw, What, Ppart, \
                                                                    a_part, Wout);                                     \
         break;                                                                                                         \
@@ -1225,11 +1221,8 @@ void launch_split_fft(size_t G, cudaStream_t st, const float *xyz, const double 
     constexpr size_t N_ = (size_t)1 << LOG2N;
     const size_t smem = (N_ + N_ / 16 + 256 + (p->L >> 8) + 64 + (N_ >= 64 ? N_ / 64 : 1)) * sizeof(double2) +
                         (((p->NF / p->R + 1) * 3 * sizeof(float) + 16 + 15) & ~(size_t)15);  // + the alignment offset
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(self_split_fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        attr = true;  // tables grow with R, the coordinate buffer with NF/R <= N/2; 113 KB lets two CTAs share an SM
-    }
+    // tables grow with R, the coordinate buffer with NF/R <= N/2; 113 KB lets two CTAs share an SM (per-device attribute)
+    cudaFuncSetAttribute(self_split_fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     self_split_fft_kernel<LOG2N><<<(unsigned)G, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, tl_first, ntl, p->R, dec, Zt);
 }
 }  // namespace

@@ -65,43 +65,10 @@ __device__ __forceinline__ void sincos_qt(double u, double &s, double &c) {
     s = __hiloint2double(shi, __double2loint(sm));
 }
 
-// re += b*cos((pi/2)u), im += b*sin((pi/2)u); the quadrant sign is folded into b's sign bit.
-__device__ __forceinline__ void sincos_qt_accumulate(double u, int bhi, int blo, double &re, double &im) {
-    const double MAGIC = 6755399441055744.0;
-    double t = u + MAGIC;
-    int k = __double2loint(t);
-    double kd = t - MAGIC;
-    double f = u - kd;
-    double z = f * f;
-    double S = fma(z, SASS_S5, SASS_S4);
-    double Cp = fma(z, SASS_C5, SASS_C4);
-    S = fma(z, S, SASS_S3);
-    Cp = fma(z, Cp, SASS_C3);
-    S = fma(z, S, SASS_S2);
-    Cp = fma(z, Cp, SASS_C2);
-    S = fma(z, S, SASS_S1);
-    Cp = fma(z, Cp, SASS_C1);
-    S = fma(z, S, SASS_S0);
-    Cp = fma(z, Cp, SASS_C0);
-    double sv = f * S;
-    double cv = fma(z, Cp, 1.0);
-    bool odd = (k & 1) != 0;
-    double cm = odd ? sv : cv;
-    double sm = odd ? cv : sv;
-    double bc = __hiloint2double(bhi ^ (((k + 1) & 2) << 30), blo);
-    double bs = __hiloint2double(bhi ^ ((k & 2) << 30), blo);
-    re = fma(bc, cm, re);
-    im = fma(bs, sm, im);
-}
-
-
-// Variant used by the tiled kernel: the quadrant signs are applied to f (odd polynomial) and to the even
-// polynomial value instead of to b, which removes the register-pair moves of sincos_qt_accumulate (ptxas turns
-// predicated FMAs back into FMA+select pairs, so the odd-quadrant swap stays four 32-bit selects):
-//   sign(cos-type term) = bit1(k), sign(sin-type term) = bit1(k+1)   (see DESIGN.md "quadrant algebra").
-// (coefficient tables kSinC / kCosC in constant memory, see above)
-
-template <int ABL = 0>
+// re += b*cos((pi/2)u), im += b*sin((pi/2)u).  The quadrant signs are applied to f (odd polynomial) and to the even
+// polynomial value rather than to b, which keeps register-pair moves out of the loop (ptxas turns predicated FMAs back
+// into FMA+select pairs, so the odd-quadrant swap stays four 32-bit selects):
+//   sign(cos-type term) = bit1(k), sign(sin-type term) = bit1(k+1)   (DESIGN.md "quadrant algebra").
 __device__ __forceinline__ void sincos_qt_accumulate2(double u, double b, double &re, double &im) {
     const double MAGIC = 6755399441055744.0;
     double t = u + MAGIC;
@@ -120,54 +87,15 @@ __device__ __forceinline__ void sincos_qt_accumulate2(double u, double b, double
     S = fma(z, S, kSinC[0]);
     Cp = fma(z, Cp, kCosC[0]);
     const int ks = k << 30;
-    // signed odd part: (+-f) * S      (ABL != 0: timing ablations only, results are wrong)
-    const double fs = (ABL >= 2) ? f : __hiloint2double(__double2hiint(f) ^ ((ks + 0x40000000) & 0x80000000), __double2loint(f));
-    const double sv = fs * S;
-    double cv = fma(z, Cp, 1.0);
-    if (ABL < 2) cv = __hiloint2double(__double2hiint(cv) ^ (ks & 0x80000000), __double2loint(cv));
-    // odd quadrant: (re, im) += b*(sv, cv); even: += b*(cv, sv)
-    const bool odd = (ABL >= 1) ? false : ((k & 1) != 0);
-    const double cm = odd ? sv : cv;
-    const double sm = odd ? cv : sv;
-    re = fma(b, cm, re);
-    im = fma(b, sm, im);
-}
-
-// Same as sincos_qt_accumulate2 but the odd-quadrant predicate and the two 64-bit selects are written in PTX so that
-// ptxas emits one predicate-producing LOP3 instead of LOP3 + ISETP.
-__device__ __forceinline__ void sincos_qt_accumulate3(double u, double b, double &re, double &im) {
-    const double MAGIC = 6755399441055744.0;
-    double t = u + MAGIC;
-    const int k = __double2loint(t);
-    double kd = t - MAGIC;
-    double f = u - kd;
-    double z = f * f;
-    double S = fma(z, kSinC[5], kSinC[4]);
-    double Cp = fma(z, kCosC[5], kCosC[4]);
-    S = fma(z, S, kSinC[3]);
-    Cp = fma(z, Cp, kCosC[3]);
-    S = fma(z, S, kSinC[2]);
-    Cp = fma(z, Cp, kCosC[2]);
-    S = fma(z, S, kSinC[1]);
-    Cp = fma(z, Cp, kCosC[1]);
-    S = fma(z, S, kSinC[0]);
-    Cp = fma(z, Cp, kCosC[0]);
-    const int ks = k << 30;
+    // signed odd part: (+-f) * S
     const double fs = __hiloint2double(__double2hiint(f) ^ ((ks + 0x40000000) & 0x80000000), __double2loint(f));
     const double sv = fs * S;
     double cv = fma(z, Cp, 1.0);
     cv = __hiloint2double(__double2hiint(cv) ^ (ks & 0x80000000), __double2loint(cv));
-    double cm, sm;
-    asm("{\n"
-        ".reg .pred p;\n"
-        ".reg .b32 t;\n"
-        "and.b32 t, %4, 1;\n"
-        "setp.ne.b32 p, t, 0;\n"
-        "selp.f64 %0, %3, %2, p;\n"
-        "selp.f64 %1, %2, %3, p;\n"
-        "}\n"
-        : "=d"(cm), "=d"(sm)
-        : "d"(cv), "d"(sv), "r"(k));
+    // odd quadrant: (re, im) += b*(sv, cv); even: += b*(cv, sv)
+    const bool odd = (k & 1) != 0;
+    const double cm = odd ? sv : cv;
+    const double sm = odd ? cv : sv;
     re = fma(b, cm, re);
     im = fma(b, sm, im);
 }

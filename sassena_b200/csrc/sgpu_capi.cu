@@ -886,9 +886,9 @@ int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, bool unifo
     size_t n0 = 0;
     for (size_t p = 0; p < npass; p++) {
         const size_t want = (NQ - n0 + (npass - p) - 1) / (npass - p);  // even share of what is left
-        // pass lengths the kernels are instantiated for: multiples of 4 (a 26-|q| instantiation measured slower than
-        // 28 with two masked |q|)
-        size_t L = std::min<size_t>(std::min<size_t>(((want + 3) / 4) * 4, maxB), NQ - n0);
+        // the symmetric scan kernel takes any pass length (2K+1 slots; an even length masks one); the kernel for
+        // |q|-dependent factors is instantiated for multiples of 4
+        size_t L = std::min<size_t>(std::min<size_t>(uniform_b ? want : ((want + 3) / 4) * 4, maxB), NQ - n0);
         if (exact && !force_corr) {
             plan.push_back(ScanPass{n0, (int)L, s[0] + (double)n0 * ds, ds, uniform_b ? 0 : 3, {}});
         } else {
