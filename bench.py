@@ -54,33 +54,59 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 FLOP_PER_EVAL = 45.0        # algorithmic FP64 flop per amplitude evaluation
-FP64_INSTR_PER_EVAL = 21.0  # what the kernel executes (sincos_qt.cuh)
-# |q|-scan kernel (DESIGN.md "K1s"): per (atom, direction, pass) a setup of one dot product, two phase scalings, two
-# sincos, the b scaling and one complex rotation; per |q| of the pass one 3-term recurrence step and one accumulation on
-# both components
-SCAN_SETUP_FLOP, SCAN_STEP_FLOP = 65.0, 6.0    # algorithmic FP64 flop
-SCAN_SETUP_INSTR, SCAN_STEP_INSTR = 49.0, 4.0  # executed FP64-pipe instructions
-SCAN_MAX_PASS, SCAN_MAX_PASS_CORR = 28, 16     # amplitude.cu amplitude_scan_max_pass defaults
+FP64_INSTR_PER_EVAL = 21.0  # what the general kernel executes (sincos_qt.cuh)
+# symmetric |q|-scan kernel (DESIGN.md "K1s", scan_sym.cu): per (atom, direction, pass) a set-up of one dot product, two
+# phase scalings, two sincos and the b scaling (+ sigma z0 and the FP32 seeds for float-rounded scans); per PAIR of |q| two
+# real Chebyshev recurrence steps and four real accumulations (+ four for the first-order correction sums)
+SCAN_SETUP_INSTR, SCAN_SETUP_INSTR_CORR = 38.0, 40.0   # executed FP64-pipe instructions (SASS count of the hot loop)
+SCAN_PAIR_INSTR, SCAN_PAIR_INSTR_CORR = 6.0, 10.0
+SCAN_SETUP_FLOP = 65.0                                 # algorithmic FP64 flop of the set-up (as round 1)
+SCAN_MAX_PASS, SCAN_MAX_PASS_CORR = 29, 17             # scan_sym.cu amplitude_scan_sym_max_pass
 
 
 def scan_passes(nq, max_b=SCAN_MAX_PASS):
-    """pass sizes (kernel template B) sgpu_capi.cu plan_scan uses for nq |q| values: even shares, multiples of 4"""
+    """pass lengths sgpu_capi.cu plan_scan uses for nq |q| values: even shares, at most max_b"""
     npass = (nq + max_b - 1) // max_b
     out, n0 = [], 0
     for p in range(npass):
         want = (nq - n0 + (npass - p) - 1) // (npass - p)
-        L = min(min((want + 3) // 4 * 4, max_b), nq - n0)
-        out.append((L + 3) // 4 * 4)
+        L = min(want, max_b, nq - n0)
+        out.append(L)
         n0 += L
     return out
 
+
+def scan_work_per_eval(nq, corrected):
+    """(algorithmic flop, executed FP64-pipe instructions) per evaluation of a scan of nq |q| values: a pass of L values runs
+    K = L // 2 pairs (an even L leaves one slot of the 2K+1 masked) plus the centre term"""
+    passes = scan_passes(nq, SCAN_MAX_PASS_CORR if corrected else SCAN_MAX_PASS)
+    pair = SCAN_PAIR_INSTR_CORR if corrected else SCAN_PAIR_INSTR
+    setup = SCAN_SETUP_INSTR_CORR if corrected else SCAN_SETUP_INSTR
+    instr = sum(setup + pair * max(1, L // 2) for L in passes)
+    # flop: a DFMA is two flop, the set-up as counted in round 1 (65) plus the correction products
+    flop = sum(SCAN_SETUP_FLOP + (6.0 if corrected else 0.0) + 2.0 * pair * max(1, L // 2) for L in passes)
+    return flop / nq, instr / nq
+
+
+def host_cores():
+    """threads of the CPU legs: every core this process may run on -- never OMP_NUM_THREADS, which torchrun sets to 1"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 WORKLOADS = {
-    # name: (config key in sassena_b200.synth.CONFIGS, description)
+    # name: description (config key in sassena_b200.synth.CONFIGS)
     "C3": "coherent F(q,t): 100k atoms x 10k frames, 50 |q| x 500 sphere vectors",
     "C1": "synthetic 1k-atom box, 100 frames, 10 |q| x 100 sphere vectors, coherent",
     "C2": "incoherent self F_s(q,t): 30k atoms x 10k frames, 20 |q| x 200 vectors, per-atom FFT correlation (one |q| per step)",
     "C4": "static SAXS via multipole sphere averaging (MPSphereScatterDevice): 1M atoms, 1k frames, 200 |q|, moments l <= 20 "
           "(one batch of 8 |q| per step)",
+    "C5": "stager-streamed 500k atoms x 50k frames self scattering (trajectory exceeds one GPU's HBM), atom-sharded with NCCL "
+          "allreduce",
+    "C5s": "bounded sample of: stager-streamed 500k atoms x 50k frames self scattering (waves of atoms streamed from pinned "
+           "host memory, double-buffered), atom-sharded with NCCL allreduce",
 }
 
 
@@ -209,8 +235,6 @@ def cpu_sample_note(threads, kind=None):
 
 def run_reference(args):
     """--impl reference: the reference algorithm on the host cores (oracle port; rank 0 only)."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return 0
     from oracle import oracle as o
     from sassena_b200 import synth
     cfg = dict(synth.CONFIGS[args.workload])
@@ -218,7 +242,7 @@ def run_reference(args):
         cfg["NF"] = args.frames
     if args.atoms:
         cfg["NA"] = args.atoms
-    cores = o.max_threads()
+    cores = host_cores()
     NF_s, NM_s = cpu_sample_shape(cfg, cores, args.cpu_seconds)
     qls = synth.qlengths(*cfg["q"])
     coords = synth.trajectory(NF_s, cfg["NA"], cfg["box"], cfg["sigma"], cfg["seed"])
@@ -242,8 +266,79 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line
+
+
+def ncu_figures(key):
+    """figures of the committed ncu captures (profiles/ncu_figures.json: per kernel the FP64 pipe utilisation and DRAM bytes
+    the summaries under profiles/ state), so that the line quotes the profiler's number next to the modelled one"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_figures.json")))
+        return d.get(key, {})
+    except Exception:
+        return {}
+
+
+class Env:
+    """one process per GPU: rank / world from torchrun's environment, NCCL process group for N > 1"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if args.gpus > 1 and self.world == 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+    def attach(self, ctx):
+        """give the context the job's NCCL communicator (inside the library): rank 0's unique id is broadcast through
+        torch.distributed -- plumbing only, every data-path collective then runs on the library's streams"""
+        if self.world > 1:
+            import sassena_b200
+            box = [sassena_b200.comm_unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(box, src=0)
+            ctx.comm_init(box[0], self.world, self.rank)
+
+    def free_cached(self):
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
+def sub_args(args, workload, **over):
+    """arguments of a secondary workload of the default invocation: few steps, bounded CPU sample"""
+    a = argparse.Namespace(**vars(args))
+    a.workload = workload
+    a.steps = min(args.steps, 3)
+    a.warmup = 3 if not (args.frames or args.atoms) else min(args.warmup, 3)
+    a.cpu_seconds = min(args.cpu_seconds, 4.0)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def run_workload(env, a):
+    from sassena_b200 import synth
+    if a.workload in ("C5", "C5s"):
+        return bench_streamed_self(env, a)
+    kind = synth.CONFIGS[a.workload]["kind"]
+    if kind == "self":
+        return bench_self(env, a)
+    if kind == "mpsphere":
+        return bench_mpsphere(env, a)
+    return bench_coherent(env, a)
 
 
 def run_ours(args):
@@ -252,35 +347,46 @@ def run_ours(args):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
-        from sassena_b200 import synth
-        if synth.CONFIGS[args.workload]["kind"] == "self":
-            return _run_self(args, saved_stdout)
-        if synth.CONFIGS[args.workload]["kind"] == "mpsphere":
-            return _run_mpsphere(args, saved_stdout)
-        return _run_ours(args, saved_stdout)
+        env = Env(args)
+        if args.workload == "all":
+            # headline: config 3 on the reference's own |q| generator; then the other north-star workloads, short
+            line = run_workload(env, sub_args(args, "C3", steps=args.steps, warmup=args.warmup, cpu_seconds=args.cpu_seconds))
+            subs = {}
+            plan = [("C3_equally_spaced", sub_args(args, "C3", mode="scan", no_cpu=True)),
+                    ("C2", sub_args(args, "C2")), ("C4", sub_args(args, "C4")), ("C5s", sub_args(args, "C5s"))]
+            for name, a in plan:
+                if name in args.skip:
+                    continue
+                env.free_cached()
+                t0 = time.perf_counter()
+                try:
+                    sub = run_workload(env, a)
+                except Exception as e:  # a secondary workload must not take the headline line down with it
+                    sub = {"error": repr(e)[:400]} if env.rank == 0 else None
+                    print(f"bench: workload {name} failed: {e!r}", file=sys.stderr)
+                if sub is not None:
+                    sub["bench_wall_s"] = time.perf_counter() - t0
+                    subs[name] = sub
+            if line is not None:
+                line["workloads"] = subs
+        else:
+            line = run_workload(env, args)
+        if line is not None:
+            os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+        env.close()
+        return 0
     finally:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
 
 
-def _run_ours(args, json_fd):
-    import torch
-    import torch.distributed as dist
+def bench_coherent(env, args):
+    """coherent workloads (C3, C1): returns the JSON line as a dict on rank 0, None elsewhere"""
     import sassena_b200
     from sassena_b200 import synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    torch, dist = env.torch, env.dist
+    world, rank, local_rank, dev = env.world, env.rank, env.local_rank, env.dev
 
     cfg = dict(synth.CONFIGS[args.workload])
     if args.frames:
@@ -290,10 +396,10 @@ def _run_ours(args, json_fd):
     NA, NF, NM = cfg["NA"], cfg["NF"], cfg["NM"]
     scan = args.mode in ("scan", "scan-rounded")
     if args.mode == "scan":
-        qls = np.linspace(cfg["q"][0], cfg["q"][1], cfg["q"][2])  # equally spaced |q|: plain scan kernel
+        qls = np.linspace(cfg["q"][0], cfg["q"][1], cfg["q"][2])  # exactly equally spaced |q|: plain scan kernel
     else:
         # the reference's scan generator: float-rounded fractions (parameters.cpp:1151), equally spaced to ~1e-8 only;
-        # in scan-rounded mode these take the corrected scan kernel
+        # the library plans the corrected scan kernel for them (default mode, "scan-rounded")
         qls = synth.qlengths(*cfg["q"])
     NQ = len(qls) if scan else 1          # |q| values per step
     b = synth.factors(NA)
@@ -303,6 +409,7 @@ def _run_ours(args, json_fd):
     by_frames = world > 1 and args.shard == "frames"
 
     ctx = sassena_b200.ScatterContext(local_rank)
+    env.attach(ctx)
     fp64_peak = ctx.measure_fp64_peak()
 
     # synthetic trajectory generated on the device (CPU twin: sassena_b200/synth.py), resident in HBM
@@ -318,7 +425,6 @@ def _run_ours(args, json_fd):
         ctx.set_factors(b)
 
     stage_resident()
-    amp = torch.zeros(NQ * NM * NF * 2, dtype=torch.float64, device=dev) if by_frames else None
     plen = ctx.partial_len("autocorrelate")
     partial = torch.zeros(NQ * plen, dtype=torch.float64, device=dev)
 
@@ -336,22 +442,18 @@ def _run_ours(args, json_fd):
                 return ctx.compute_all_vectors_scan(u, qls)
             return ctx.compute_all_vectors(q0 * u)
         if by_frames:
+            # local amplitudes -> exchange over NVLink (grouped ncclSend/ncclRecv, overlapped with the next pass) -> DSP of this
+            # rank's timelines -> all-reduce of the packed partials: all inside the library, no host synchronisation
             if scan:
-                ctx.all_vectors_scan_amplitudes(u, qls, amp.data_ptr())
+                ctx.compute_all_vectors_scan_sharded(u, qls, partial.data_ptr())
             else:
-                ctx.all_vectors_amplitudes(q0 * u, amp.data_ptr())
-            ctx.synchronize()
-            dist.all_reduce(amp)  # exchange over NVSwitch: every rank ends up with the complete timelines
-            torch.cuda.synchronize()
-            for n in range(NQ):
-                ctx.all_vectors_dsp_partial(amp.data_ptr() + n * NM * NF * 16, m_off, m_cnt, partial.data_ptr() + n * plen * 8)
-        elif scan:
-            ctx.compute_all_vectors_scan_partial(u[m_off:m_off + m_cnt], qls, partial.data_ptr())
+                ctx.compute_all_vectors_sharded(q0 * u, partial.data_ptr())
         else:
-            ctx.compute_all_vectors_partial(q0 * u[m_off:m_off + m_cnt], partial.data_ptr())
-        ctx.synchronize()
-        dist.all_reduce(partial)
-        torch.cuda.synchronize()
+            if scan:
+                ctx.compute_all_vectors_scan_partial(u[m_off:m_off + m_cnt], qls, partial.data_ptr())
+            else:
+                ctx.compute_all_vectors_partial(q0 * u[m_off:m_off + m_cnt], partial.data_ptr())
+            ctx.comm_allreduce(partial.data_ptr(), NQ * plen)
         return [ctx.finalize(partial.data_ptr() + n * plen * 8, 1.0 / NM) for n in range(NQ)]
 
     # ---- device-resident measurement ----
@@ -418,11 +520,12 @@ def _run_ours(args, json_fd):
                 ctx.set_factors(b)
             return compute_step(i)
 
-        for i in range(min(args.warmup, 2)):
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for i in range(min(args.warmup, 1)):
             e2e_step(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(e2e_steps):
             e2e_step(args.warmup + i)
         barrier()
         e2e_s = time.perf_counter() - t0
@@ -431,10 +534,10 @@ def _run_ours(args, json_fd):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
         nvec_up = NM if (world == 1 or by_frames) else m_cnt
-        e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
+        e2e = {"value": evals_step * e2e_steps / e2e_s, "unit": "evals/s",
                "h2d_bytes_per_step": int(f_cnt * NA * 12 + NA * 8 + nvec_up * 24),
                "d2h_bytes_per_step": int(NQ * (NF * 16 + 32)),
-               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
                "note": ("coordinates re-staged from pinned host memory every step (chunked async H2D overlapped "
                         "with the amplitude kernel); fqt/fq/fq2 of every |q| of the step read back to the host"
                         if world == 1 else
@@ -449,7 +552,7 @@ def _run_ours(args, json_fd):
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as o
-        cores = o.max_threads()
+        cores = host_cores()
         NF_s, NM_s = cpu_sample_shape(cfg, cores, args.cpu_seconds)
         coords = np.empty((NF_s, NA, 3), dtype=np.float32)
         ctx.memcpy_d2h(coords, xyz.data_ptr())
@@ -480,35 +583,28 @@ def _run_ours(args, json_fd):
         evals_rank = float(NA) * nf0 * nm0 * NQ * args.steps
         scan_plan = ctx.last_scan_plan() if scan else None
         if scan:
-            corrected = args.mode == "scan-rounded"
-            passes = scan_passes(NQ, SCAN_MAX_PASS_CORR if corrected else SCAN_MAX_PASS)
-            step_flop = SCAN_STEP_FLOP + (4.0 if corrected else 0.0)    # + D accumulation (2 FMA); E runs on the FP32 pipe
-            step_instr = SCAN_STEP_INSTR + (2.0 if corrected else 0.0)
-            flop_eval = (len(passes) * SCAN_SETUP_FLOP + sum(passes) * step_flop) / NQ
-            instr_eval = (len(passes) * SCAN_SETUP_INSTR + sum(passes) * step_instr) / NQ
-            kernel = "amplitude_scan_kernel" + (" (corrected)" if corrected else "")
+            corrected = bool(scan_plan) and scan_plan[1] > 0  # what the library planned for this |q| list
+            flop_eval, instr_eval = scan_work_per_eval(NQ, corrected)
+            kernel = "amplitude_scan_sym_kernel" + (" (corrected: float-rounded scan)" if corrected else "")
         else:
             flop_eval, instr_eval, kernel = FLOP_PER_EVAL, FP64_INSTR_PER_EVAL, "amplitude_all_tiled_kernel"
         achieved = evals_rank * flop_eval / amp_s / 1e12
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(prof):
-            try:
-                tj = json.load(open(prof))
-                key = "scan_dram_bytes_per_frame" if scan else "dram_bytes_per_frame"
-                traffic = tj[key] * nf0 if key in tj else None  # one launch covers all frames of the rank
-            except Exception:
-                traffic = None
+        ncu = ncu_figures("scan_corrected" if (scan and corrected) else "scan_plain" if scan else "k1_tiled")
+        traffic = ncu.get("dram_bytes_per_frame", None)
+        traffic = traffic * nf0 if traffic is not None else None  # one launch covers all frames of the rank
         line = {
             "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NF": NF, "NM_per_q": NM, "NQ": len(qls),
-                       "step": (f"the whole |q| scan ({NQ} equally spaced |q| x {NM} orientation vectors) over the full "
+                       "step": (f"the whole |q| scan ({NQ} |q| x {NM} orientation vectors) over the full "
                                 "trajectory: amplitudes + FFT autocorrelation + average for every |q|" if scan else
                                 "one |q| (compute() of the runner loop): amplitudes + FFT autocorrelation + average"),
-                       "mode": args.mode, "scan_plan_plain_corrected_single": scan_plan,
-                       "parallelism": (f"frame shard x{world} + amplitude all-reduce" if by_frames else
+                       "mode": args.mode,
+                       "q_list": ("the reference's scan generator (float-rounded fractions, parameters.cpp:1151)"
+                                  if args.mode != "scan" else "np.linspace (exactly equally spaced)"),
+                       "scan_plan_plain_corrected_single": scan_plan,
+                       "parallelism": (f"frame shard x{world} + amplitude exchange over NVLink" if by_frames else
                                        f"q-vector shard x{world}" if world > 1 else "single GPU"),
                        "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
             "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * (len(qls) / NQ),
@@ -516,12 +612,17 @@ def _run_ours(args, json_fd):
                          "frac": achieved / fp64_peak, "traffic": traffic,
                          "kernel": kernel, "kernel_share_of_step": amp_ms_max / ms_max,
                          "algorithmic_flop_per_eval": flop_eval,
+                         "fp64_instr_per_eval_executed": instr_eval,
                          "fp64_pipe_util_executed": evals_rank * instr_eval * 2 / amp_s / 1e12 / fp64_peak,
-                         "per_eval_formulation_equiv_tflops": evals_rank * FLOP_PER_EVAL / amp_s / 1e12,
-                         "note": ("scan kernel: 2 sincos per (atom, direction, pass) + a 3-term recurrence per |q|; its own "
-                                  "flop count is used for `achieved`.  per_eval_formulation_equiv_tflops is what the "
-                                  "reference's one-sincos-per-evaluation formulation (45 flop/eval, SURVEY 8d) would need "
-                                  "for the same evals/s" if scan else "45 flop per evaluation (SURVEY 8d)"),
+                         "fp64_pipe_util_ncu": ncu.get("fp64_pipe_pct"), "ncu_source": ncu.get("source"),
+                         "survey_8d_flop_per_eval": FLOP_PER_EVAL,
+                         "frac_by_survey_8d_count": evals_rank * FLOP_PER_EVAL / amp_s / 1e12 / fp64_peak,
+                         "note": ("symmetric scan kernel: 2 sincos per (atom, direction, pass) + two real Chebyshev recurrence "
+                                  "steps and four (corrected: eight) real accumulations per PAIR of |q|; `achieved` counts the "
+                                  "flop this formulation needs.  frac_by_survey_8d_count prices the same evaluations at SURVEY "
+                                  "8(d)'s one-sincos-per-evaluation figure (45 flop) and therefore exceeds 1: the kernel does "
+                                  "not execute that work.  fp64_pipe_util_ncu is sm__inst_executed_pipe_fp64 of the committed "
+                                  "capture" if scan else "45 flop per evaluation (SURVEY 8d)"),
                          "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
             "cpu_baseline": cpu_baseline,
@@ -533,11 +634,11 @@ def _run_ours(args, json_fd):
             "dsp_ms_per_step": dsp_ms / args.steps,
             "per_rank": per_rank,
         }
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        line = None
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    del xyz, partial
+    return line
 
 
 def mod_assignment_count(NN, rank, N):
@@ -563,8 +664,6 @@ def self_cpu_sample(cfg, cores, target_core_seconds, timelines_per_core_s=70.0):
 
 def run_reference_self(args):
     """--impl reference --workload C2: the oracle's self path (atoms over threads = ModAssignment over ranks)."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return 0
     from oracle import oracle as o
     from sassena_b200 import synth
     o.build()
@@ -573,7 +672,7 @@ def run_reference_self(args):
         cfg["NF"] = args.frames
     if args.atoms:
         cfg["NA"] = args.atoms
-    cores = o.max_threads()
+    cores = host_cores()
     NA_s, NM_s = self_cpu_sample(cfg, cores, args.cpu_seconds)
     NF = cfg["NF"]
     qls = synth.qlengths(*cfg["q"])
@@ -598,30 +697,17 @@ def run_reference_self(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line
 
 
-def _run_self(args, json_fd):
+def bench_self(env, args):
     """--workload C2: incoherent self scattering at full size.  A step is one compute() of the runner loop: one |q| with
     its 200 vectors over ALL atoms (6e6 timelines of 10k frames: amplitudes, FFT autocorrelation, store).  N GPUs: atoms
     sharded by ModAssignment (self_vectors_scatter_device.cpp:50), one NCCL all-reduce of the packed partial per |q|."""
-    import torch
-    import torch.distributed as dist
     import sassena_b200
     from sassena_b200 import synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    torch, dist = env.torch, env.dist
+    world, rank, local_rank, dev = env.world, env.rank, env.local_rank, env.dev
     cfg = dict(synth.CONFIGS[args.workload])
     if args.frames:
         cfg["NF"] = args.frames
@@ -635,6 +721,7 @@ def _run_self(args, json_fd):
     b_loc = np.ascontiguousarray(b_all[rank::world])
 
     ctx = sassena_b200.ScatterContext(local_rank)
+    env.attach(ctx)
     fp64_peak = ctx.measure_fp64_peak()
     # this rank's atoms (rank, rank+world, ...), atom-major [na_loc][NF][3], generated on the device (CPU twin in synth.py),
     # then kept in pinned host memory: the "trajectory on the host" that the end-to-end step stages from
@@ -661,9 +748,7 @@ def _run_self(args, json_fd):
         if world == 1:
             return ctx.compute_self_vectors(q)
         ctx.compute_self_vectors_partial(q, partial.data_ptr())
-        ctx.synchronize()
-        dist.all_reduce(partial)  # the three boost::mpi::reduce calls of self_vectors_scatter_device.cpp:213-221
-        torch.cuda.synchronize()
+        ctx.comm_allreduce(partial.data_ptr(), plen)  # the three boost::mpi::reduce calls of self_vectors_scatter_device.cpp:213-221
         return ctx.finalize(partial.data_ptr(), 1.0 / NM)
 
     for i in range(args.warmup):
@@ -704,20 +789,21 @@ def _run_self(args, json_fd):
             ctx.set_factors(b_loc)
             return compute_step(i)
 
-        for i in range(min(args.warmup, 2)):
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for i in range(min(args.warmup, 1)):
             e2e_step(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(e2e_steps):
             e2e_step(args.warmup + i)
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
-        e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
+        e2e = {"value": evals_step * e2e_steps / e2e_s, "unit": "evals/s", "steps": e2e_steps,
                "h2d_bytes_per_step": int(na_loc * NF * 12 + na_loc * 8 + NM * 24), "d2h_bytes_per_step": int(NF * 16 + 32),
-               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "ms_per_step": 1e3 * e2e_s / e2e_steps,
                "note": "every rank re-stages its atoms from pinned host memory every step (H2D, then the decimated frame "
                        "order of the split path is rebuilt on the device); fqt/fq/fq2 of the step's |q| read back"}
 
@@ -726,7 +812,7 @@ def _run_self(args, json_fd):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as o
         o.build()
-        cores = o.max_threads()
+        cores = host_cores()
         NA_s, NM_s = self_cpu_sample(cfg, cores, args.cpu_seconds)
         ql = qls[len(qls) // 2]
         xa = np.ascontiguousarray(host.array[:NA_s])
@@ -778,12 +864,223 @@ def _run_self(args, json_fd):
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
             "host_wall_ms_per_step": wall_ms / args.steps, "per_rank": per_rank,
         }
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        line = None
     host.free()
     ctx.close()
+    return line
+
+
+def bench_streamed_self(env, args):
+    """--workload C5s / C5: BASELINE configs[4], stager-streamed self scattering (50k frames).  The rank's atoms (ModAssignment)
+    sit atom-major in PINNED HOST memory and pass through the GPU in waves: sgpu_stage_atoms_prefetch queues wave w+1 on the
+    copy stream while wave w is evaluated for every |q| of the step (sgpu_stage_atoms_swap, no host synchronisation); the packed
+    partials -- sums over atoms -- accumulate per |q| on the device, one all-reduce + finalize per |q| after the last wave
+    (self_vectors_scatter_device.cpp:213-238; DataStagerByAtom's buffering, data_stager.cpp:249-338, as a pipeline).
+    C5s: a bounded sample (args.c5s_atoms atoms, one |q| per step) for the default invocation.  C5: all 500k atoms, args.nq |q|
+    per step -- 300 GB of pinned host memory over the ranks, meant for 8 GPUs."""
+    import sassena_b200
+    from sassena_b200 import synth
+    torch, dist = env.torch, env.dist
+    world, rank, local_rank, dev = env.world, env.rank, env.local_rank, env.dev
+    full = args.workload == "C5"
+    cfg = dict(synth.CONFIGS["C5"])
+    if args.frames:
+        cfg["NF"] = args.frames
+    NA = cfg["NA"] if full else min(cfg["NA"], args.c5s_atoms)
+    if args.atoms:
+        NA = args.atoms
+    NF, NM = cfg["NF"], cfg["NM"]
+    qls_all = synth.qlengths(*cfg["q"])
+    NQ = min(len(qls_all), max(1, args.nq)) if full else 1
+    u = synth.unit_vectors(NM, cfg["vseed"])
+    b_all = synth.factors(cfg["NA"])
+    na_loc = mod_assignment_count(world, rank, NA)
+    b_loc = np.ascontiguousarray(b_all[rank:NA:world])
+    atom_bytes = NF * 12
+    W = args.wave_atoms or max(64, int(2.0e9 // atom_bytes) // 64 * 64)  # ~2 GB per wave buffer
+    W = max(1, min(W, na_loc))
+    nwaves = (na_loc + W - 1) // W
+
+    ctx = sassena_b200.ScatterContext(local_rank)
+    env.attach(ctx)
+    fp64_peak = ctx.measure_fp64_peak()
+    free0, total_mem = torch.cuda.mem_get_info()
+    # this rank's atoms, atom-major, generated wave by wave on the device (CPU twin: synth.py) into the pinned host buffer
+    # the stager streams from
+    t0 = time.perf_counter()
+    host = ctx.pinned((na_loc, NF, 3), np.float32)
+    gen = torch.empty(W * NF * 3, dtype=torch.float32, device=dev)
+    for w in range(nwaves):
+        first, cnt = w * W, min(W, na_loc - w * W)
+        ctx.synth_trajectory(gen.data_ptr(), NF, cfg["NA"], cfg["box"], cfg["sigma"], cfg["seed"], layout=1,
+                             atom0=rank + first * world, atom_stride=world, NA_out=cnt)
+        ctx.memcpy_d2h(host.array[first:first + cnt], gen.data_ptr())
+    del gen
+    torch.cuda.empty_cache()
+    gen_s = time.perf_counter() - t0
+
+    plen = None
+    acc = partial = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    kern_ms = [0.0]
+
+    def stream_step(i):
+        """all waves of this rank for the NQ |q| of step i; returns the finalized (fqt, fq, fq2) per |q|"""
+        nonlocal plen, acc, partial
+        qs = [float(qls_all[(i * NQ + n) % len(qls_all)]) for n in range(NQ)]
+        ctx.stage_atoms_prefetch(host.array[0:min(W, na_loc)])
+        for w in range(nwaves):
+            first, cnt = w * W, min(W, na_loc - w * W)
+            ctx.stage_atoms_swap()
+            if w + 1 < nwaves:
+                ctx.stage_atoms_prefetch(host.array[first + cnt:min(first + cnt + W, na_loc)])
+            ctx.set_factors(b_loc[first:first + cnt])
+            if plen is None:
+                plen = ctx.partial_len("autocorrelate")
+                acc = torch.zeros(NQ * plen, dtype=torch.float64, device=dev)
+                partial = torch.zeros(plen, dtype=torch.float64, device=dev)
+            for n, ql in enumerate(qs):
+                dst = acc.data_ptr() + n * plen * 8
+                if w == 0:
+                    ctx.compute_self_vectors_partial(ql * u, dst)
+                else:
+                    ctx.compute_self_vectors_partial(ql * u, partial.data_ptr())
+                    ctx.accumulate(dst, partial.data_ptr(), plen)
+                kern_ms[0] += ctx.last_amplitude_ms()
+        if world > 1:
+            ctx.comm_allreduce(acc.data_ptr(), NQ * plen)  # the three boost::mpi::reduce calls of self_vectors_scatter_device.cpp:213-221
+        return [ctx.finalize(acc.data_ptr() + n * plen * 8, 1.0 / NM) for n in range(NQ)]
+
+    for i in range(args.warmup):
+        stream_step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = ctx.launch_count
+    kern_ms[0] = 0.0
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    res = None
+    for i in range(args.steps):
+        res = stream_step(args.warmup + i)
+    ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if rank == 0 else None
+    free1, _ = torch.cuda.mem_get_info()
+    hbm_used = max(0, free0 - free1)
+    # the wall clock (host, barrier on both sides) is the step time here: copies and kernels run on two streams
+    t = torch.tensor([wall_ms, ms, kern_ms[0], float(hbm_used)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.destroy_process_group()
-    return 0
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max, ms_max, kern_max, hbm_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    mine = {"rank": rank, "step_ms": wall_ms / args.steps, "compute_stream_ms": ms / args.steps, "kernel_ms": kern_ms[0] / args.steps,
+            "atoms": na_loc, "waves": nwaves, "hbm_bytes": int(hbm_used), "library_buffers_bytes": ctx.device_bytes(),
+            "pinned_host_bytes": int(na_loc * atom_bytes), "generate_s": gen_s}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    evals_step = float(NA) * NF * NM * NQ
+    value = evals_step * args.steps / (wall_max * 1e-3)
+
+    # the same atoms resident in HBM (when they fit beside the wave buffers): what the streaming costs
+    resident = None
+    if not full and na_loc * atom_bytes < 0.5 * free1:
+        ctx.stage_atoms(host.array)
+        ctx.set_factors(b_loc)
+        pr = torch.zeros(plen, dtype=torch.float64, device=dev)
+        ql = float(qls_all[(args.warmup + args.steps - 1) % len(qls_all)])
+        ctx.compute_self_vectors_partial(ql * u, pr.data_ptr())
+        barrier()
+        ctx.timer_start()
+        ctx.compute_self_vectors_partial(ql * u, pr.data_ptr())
+        rms = ctx.timer_stop()
+        barrier()
+        if world > 1:
+            ctx.comm_allreduce(pr.data_ptr(), plen)
+        rres = ctx.finalize(pr.data_ptr(), 1.0 / NM)
+        tr = torch.tensor([rms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        resident = {"value": float(NA) * NF * NM / (float(tr[0]) * 1e-3), "ms": float(tr[0]),
+                    "streamed_vs_resident_rel_err": float(np.max(np.abs(res[-1][0] - rres[0])) / np.max(np.abs(rres[0]))),
+                    "note": "the sample staged once and evaluated for the step's last |q| without streaming"}
+
+    cpu_baseline = parity = None
+    if rank == 0 and not args.no_cpu and (world == 1 or full):
+        from oracle import oracle as o
+        o.build()
+        cores = host_cores()
+        NA_s, NM_s = self_cpu_sample(cfg, cores, args.cpu_seconds)
+        NA_s = min(NA_s, na_loc)
+        ql = float(qls_all[len(qls_all) // 2])
+        xa = np.ascontiguousarray(host.array[:NA_s])
+        dt, (rfqt, rfq, rfq2) = run_cpu_self(xa, b_loc[:NA_s], u[:NM_s], ql, cores)
+        sample = (f"{NA_s} atoms x all {NF} frames x {NM_s} of {NM} vectors of one |q| (amplitude timelines + FFT "
+                  f"autocorrelation + store); " + cpu_sample_note(cores, "port") + " over atoms")
+        cpu_baseline = {"value": float(NA_s) * NF * NM_s / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                        "sample": sample, "seconds": dt}
+        ctx.stage_atoms(xa)
+        ctx.set_factors(b_loc[:NA_s])
+        fqt, fq, _ = ctx.compute_self_vectors(ql * u[:NM_s])
+        parity = {"fqt_rel_err": float(np.max(np.abs(fqt - rfqt)) / np.max(np.abs(rfqt))),
+                  "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9,
+                  "vs": "oracle on the CPU sample: this rank's first atoms of the streamed trajectory (the oracle reproduces "
+                        "the reference's own SelfVectorsScatterDevice bit for bit, tests/test_reference_devices.py)"}
+
+    if rank == 0:
+        tl_rank = float(mod_assignment_count(world, 0, NA)) * NM * NQ * args.steps
+        achieved = tl_rank * self_flop_per_timeline(NF) / (kern_max * 1e-3) / 1e12
+        h2d = int(na_loc * atom_bytes + na_loc * 8 + NQ * NM * 24)
+        line = {
+            "metric": "amplitude evals/s (atom*frame*q-vector)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "NA": NA, "NA_config": cfg["NA"], "NF": NF, "NM_per_q": NM,
+                       "NQ_per_step": NQ, "NQ_config": len(qls_all), "wave_atoms": W, "waves_per_rank": nwaves,
+                       "step": f"every atom of the {'configuration' if full else 'sample'} streamed once from pinned host memory "
+                               f"(waves of {W} atoms, double-buffered) and evaluated for {NQ} |q| x {NM} vectors: amplitude "
+                               "timelines, FFT autocorrelation per (atom, vector), accumulation over waves, all-reduce, finalize",
+                       "parallelism": f"atom shard (ModAssignment) x{world} + all-reduce of the packed partials" if world > 1
+                       else "single GPU",
+                       "cache": f"inputs ({NA * atom_bytes / 1e9:.1f} GB of coordinates) stream from the host every step"},
+            "timelines_per_s": float(NA) * NM * NQ * args.steps / (wall_max * 1e-3),
+            "fqt_wall_time_s_all_q": wall_max / args.steps * 1e-3 * (len(qls_all) / NQ) * (cfg["NA"] / NA),
+            "staging": {"h2d_bytes_per_step_per_rank": int(na_loc * atom_bytes),
+                        "kernel_share_of_step": kern_max / wall_max,
+                        "overlap": "wave w+1 is copied on the copy stream while wave w is evaluated; a step's wall time minus its "
+                                   "kernel time is what staging, launches and the final reduce add",
+                        "hbm_high_water_bytes": int(hbm_max), "resident": resident},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "kernel": "self_split_fft_kernel + self_split_combine_*",
+                         "kernel_share_of_step": kern_max / wall_max,
+                         "algorithmic_flop_per_timeline": self_flop_per_timeline(NF),
+                         "note": "45 flop per amplitude + one forward 2NF-point FFT (5 L log2 L) per timeline (SURVEY 8d)",
+                         "peak_source": "measured live: dependency-free DFMA chains on all SMs (sgpu_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry"},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(NQ * (NF * 16 + 32)),
+                    "ms_per_step": wall_max / args.steps,
+                    "note": "the streamed step IS end to end: every step copies all of the rank's atoms from pinned host memory "
+                            "(inside the timed region, overlapped with the kernels) and reads fqt/fq/fq2 of its |q| back"},
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "per_rank": per_rank,
+        }
+    else:
+        line = None
+    host.free()
+    ctx.close()
+    return line
 
 
 MP_BATCH = 8  # |q| values per pass of the batched multipole kernel (MPSphereScatterDevice::runner batches them)
@@ -801,8 +1098,6 @@ def run_reference_mpsphere(args):
     """--impl reference --workload C4: the oracle's MPSphere path on a bounded sample.  It reproduces the reference's own
     MPSphereScatterDevice bit for bit (tests/test_reference_devices.py); that device's oracle/_ref build evaluates sph_bessel /
     spherical_harmonic through the oracle's restatements (Boost.Math is absent), so the port is what is timed: kind "port"."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return 0
     from oracle import oracle as o
     from sassena_b200 import synth
     o.build()
@@ -811,7 +1106,7 @@ def run_reference_mpsphere(args):
         cfg["NF"] = args.frames
     if args.atoms:
         cfg["NA"] = args.atoms
-    cores = o.max_threads()
+    cores = host_cores()
     mom = o.moments_sphere(cfg["L"])
     NF_s = 2
     NA_s = int(max(64, min(cfg["NA"], 7.8e7 / 16 * cores * args.cpu_seconds / (NF_s * len(mom)))))
@@ -839,31 +1134,17 @@ def run_reference_mpsphere(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line
 
 
-def _run_mpsphere(args, json_fd):
+def bench_mpsphere(env, args):
     """--workload C4: multipole sphere averaging at full size.  A step is one pass of the batched multipole kernel: 8 |q|
     x 441 moments over all atoms and frames (amplitudes A_lm(q, t), dsp, store).  N GPUs: every rank holds the frames of
     its DivAssignment block of the ATOMS, the amplitudes (sums over atoms) are all-reduced before the DSP."""
-    import torch
-    import torch.distributed as dist
     import sassena_b200
     from sassena_b200 import synth
-    from oracle import oracle as o  # moments list only here; the checker runs further down on rank 0
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    torch, dist = env.torch, env.dist
+    world, rank, local_rank, dev = env.world, env.rank, env.local_rank, env.dev
     cfg = dict(synth.CONFIGS[args.workload])
     if args.frames:
         cfg["NF"] = args.frames
@@ -878,6 +1159,7 @@ def _run_mpsphere(args, json_fd):
     b_loc = np.ascontiguousarray(synth.factors(NA)[a_off:a_off + a_cnt])
 
     ctx = sassena_b200.ScatterContext(local_rank)
+    env.attach(ctx)
     fp64_peak = ctx.measure_fp64_peak()
     gen = torch.empty(NF * a_cnt * 3, dtype=torch.float32, device=dev)
     ctx.synth_trajectory(gen.data_ptr(), NF, NA, cfg["box"], cfg["sigma"], cfg["seed"], layout=0, atom0=a_off, atom_stride=1,
@@ -908,9 +1190,7 @@ def _run_mpsphere(args, json_fd):
         if world == 1:
             return ctx.compute_mpsphere_batch(ql, mom, dsp="square")
         ctx.mpsphere_amplitudes(ql, mom, 0, a_cnt, amp.data_ptr())
-        ctx.synchronize()
-        dist.all_reduce(amp)  # A_lm(q, t) are sums over atoms: complete them before the DSP
-        torch.cuda.synchronize()
+        ctx.comm_allreduce(amp.data_ptr(), amp.numel())  # A_lm(q, t) are sums over atoms: complete them before the DSP
         ctx.mpsphere_dsp_partial(amp.data_ptr(), len(ql), NM, partial.data_ptr(), dsp="square")
         return [ctx.finalize(partial.data_ptr() + n * plen * 8, 1.0 / (4 * np.pi), dsp="square") for n in range(len(ql))]
 
@@ -950,28 +1230,30 @@ def _run_mpsphere(args, json_fd):
             stage()
             return compute_step(i)
 
-        for i in range(min(args.warmup, 2)):
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for i in range(min(args.warmup, 1)):
             e2e_step(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(e2e_steps):
             e2e_step(args.warmup + i)
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
-        e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
+        e2e = {"value": evals_step * e2e_steps / e2e_s, "unit": "evals/s", "steps": e2e_steps,
                "h2d_bytes_per_step": int(NF * a_cnt * 12 + MP_BATCH * a_cnt * 8 + NM * 16),
-               "d2h_bytes_per_step": int(MP_BATCH * (NF * 16 + 32)), "ms_per_step": 1e3 * e2e_s / args.steps,
+               "d2h_bytes_per_step": int(MP_BATCH * (NF * 16 + 32)), "ms_per_step": 1e3 * e2e_s / e2e_steps,
                "note": "every rank re-stages its atoms of all frames from pinned host memory every step (chunked async H2D), "
                        "converts them to (r, phi, theta) on the device, uploads the factors of the 8 |q| and reads fqt/fq/fq2 back"}
 
     cpu_baseline = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as o  # the checker: rank 0, N = 1 only
         o.build()
-        cores = o.max_threads()
+        cores = host_cores()
         NF_s = 2
         NA_s = int(max(64, min(NA, 7.8e7 / 16 * cores * args.cpu_seconds / (NF_s * NM))))
         sph = o.cart_to_spherical(np.ascontiguousarray(host.array[:NF_s, :NA_s]))
@@ -1017,12 +1299,40 @@ def _run_mpsphere(args, json_fd):
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
             "host_wall_ms_per_step": wall_ms / args.steps, "per_rank": per_rank,
         }
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        line = None
     host.free()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return line
+
+
+def reference_line(args):
+    """--impl reference: rank 0 alone runs the CPU arm and prints; the other ranks exit without work"""
+    from sassena_b200 import synth
+
+    def one(a):
+        cfg_name = "C5" if a.workload == "C5s" else a.workload
+        a = argparse.Namespace(**vars(a))
+        a.workload = cfg_name
+        kind = synth.CONFIGS[cfg_name]["kind"]
+        if kind == "self":
+            return run_reference_self(a)
+        if kind == "mpsphere":
+            return run_reference_mpsphere(a)
+        return run_reference(a)
+
+    if args.workload != "all":
+        return one(args)
+    line = one(sub_args(args, "C3", steps=args.steps, warmup=args.warmup, cpu_seconds=args.cpu_seconds))
+    subs = {}
+    for name in ("C2", "C4", "C5s"):
+        if name in args.skip:
+            continue
+        a = sub_args(args, name, warmup=1)
+        a.steps = min(a.steps, 2)
+        subs[name] = one(a)
+    line["workloads"] = subs
+    return line
 
 
 def main():
@@ -1031,28 +1341,34 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS),
+                    help="all (default): config 3 as the headline line plus C3 on equally spaced |q|, C2, C4 and the streamed C5 "
+                         "sample under `workloads`; or one workload alone")
+    ap.add_argument("--skip", default="", help="comma-separated secondary workloads to leave out of --workload all")
     ap.add_argument("--frames", type=int, default=0, help="override NF (debug; changes the workload)")
     ap.add_argument("--atoms", type=int, default=0, help="override NA (debug; changes the workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle sample, seconds per core")
-    ap.add_argument("--mode", default="scan", choices=["scan", "scan-rounded", "per-q"],
-                    help="scan: a step is the whole scan of equally spaced |q| through the scan kernel (default); "
-                         "scan-rounded: the same with the reference's float-rounded |q| (corrected scan kernel); "
-                         "per-q: a step is one |q| through the general kernel")
+    ap.add_argument("--mode", default="scan-rounded", choices=["scan", "scan-rounded", "per-q"],
+                    help="scan-rounded (default): a step is the whole scan with the |q| list of the reference's generator "
+                         "(float-rounded fractions -> corrected scan kernel); scan: exactly equally spaced |q| (plain scan "
+                         "kernel); per-q: a step is one |q| through the general kernel")
     ap.add_argument("--shard", default="frames", choices=["frames", "vectors"],
                     help="N>1: shard the frames (reference decomposition, default) or the subvectors (replicated coordinates)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end (host buffers) measurement, at most --steps")
+    ap.add_argument("--nq", type=int, default=2, help="--workload C5: |q| values evaluated (of the configuration's 20)")
+    ap.add_argument("--c5s-atoms", type=int, default=8192, help="atoms of the streamed sample workload C5s (all ranks together)")
+    ap.add_argument("--wave-atoms", type=int, default=0, help="C5 / C5s: atoms per streamed wave (0: chosen from the frame count)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    args.skip = [x for x in args.skip.split(",") if x]
     if args.warmup < 3 and args.impl == "ours":
-        args.warmup = max(args.warmup, 3) if not args.frames else args.warmup
+        args.warmup = max(args.warmup, 3) if not (args.frames or args.atoms) else args.warmup
     if args.impl == "reference":
-        from sassena_b200 import synth
-        if synth.CONFIGS[args.workload]["kind"] == "self":
-            return run_reference_self(args)
-        if synth.CONFIGS[args.workload]["kind"] == "mpsphere":
-            return run_reference_mpsphere(args)
-        return run_reference(args)
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        print(json.dumps(reference_line(args)))
+        return 0
     return run_ours(args)
 
 

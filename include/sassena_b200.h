@@ -92,6 +92,21 @@ int sgpu_stage_atoms_from_frames(sgpu_ctx *ctx, const float *xyz, size_t NF, siz
  * the atoms through the GPU wave by wave; partials are additive over atoms, see sgpu_accumulate). */
 int sgpu_stage_atoms_wave(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA, size_t atom_first, size_t atom_stride,
                           size_t count);
+/* Double-buffered wave streaming (DataStagerByAtom's cyclic buffering, data_stager.cpp:249-338, turned into a copy/compute
+ * pipeline): xyz is host float [count][NF][3] — a block of this rank's atoms in atom-major order, in pinned memory
+ * (sgpu_host_alloc) for a truly asynchronous copy.  sgpu_stage_atoms_prefetch queues the H2D copy of the block into the
+ * context's BACK wave buffer on the copy stream and returns at once; it waits (on the device) only for the compute calls
+ * that still read that buffer.  sgpu_stage_atoms_swap makes the prefetched block the staged atoms: compute calls queued
+ * after it wait (on the device) for the copy and then see NA_local = count atoms of NF frames.  The usual loop:
+ *     prefetch(wave 0); for w: swap(); if (w+1 < waves) prefetch(wave w+1); for q: compute_self_vectors_partial(...)
+ * so that wave w+1 travels over PCIe while wave w is evaluated.  Both buffers belong to the context (2 x the largest block
+ * seen); xyz of a prefetched block must stay valid until the matching swap's first compute call has returned. */
+int sgpu_stage_atoms_prefetch(sgpu_ctx *ctx, const float *xyz, size_t count, size_t NF);
+int sgpu_stage_atoms_swap(sgpu_ctx *ctx);
+/* Bytes of device memory currently held by the context's buffers (coordinates, wave buffers, amplitudes, work areas):
+ * the per-GPU HBM high-water mark of a streamed run. */
+int sgpu_device_bytes(sgpu_ctx *ctx, size_t *bytes);
+
 /* d_dst[i] += d_src[i], i < n doubles in device memory, on the context's compute stream (sums the packed partials of
  * successive atom waves; fixed order, no atomics). */
 int sgpu_accumulate(sgpu_ctx *ctx, double *d_dst, const double *d_src, size_t n);
@@ -231,6 +246,33 @@ int sgpu_device_alloc(void **d_ptr, size_t bytes);
 int sgpu_device_free(void *d_ptr);
 int sgpu_memcpy_d2h(sgpu_ctx *ctx, void *dst, const void *d_src, size_t bytes);
 int sgpu_memcpy_h2d(sgpu_ctx *ctx, void *d_dst, const void *src, size_t bytes);
+
+/* ---- the partition's communicator inside the library (NCCL over NVLink / NVSwitch) -----------------------------------
+ * Replaces the boost::mpi communicator of one partition (scatter_device_factory.cpp:117-120) for device-resident data.
+ * One process per GPU: one rank obtains a unique id (sgpu_comm_get_unique_id, 128 bytes), hands it to the others by any
+ * means (torch.distributed, a file, MPI), and every rank calls sgpu_comm_init — a collective (ncclCommInitRank).  All
+ * communication then runs on the context's streams with no host synchronisation.  libnccl.so.2 is bound at run time. */
+int sgpu_comm_get_unique_id(char *id128);
+int sgpu_comm_init(sgpu_ctx *ctx, const char *id128, int nranks, int rank);
+/* adopt a communicator the caller owns (an ncclComm_t, e.g. the host layer's partition communicator) */
+int sgpu_comm_adopt(sgpu_ctx *ctx, void *nccl_comm, int nranks, int rank);
+int sgpu_comm_destroy(sgpu_ctx *ctx);
+int sgpu_comm_info(sgpu_ctx *ctx, int *nranks, int *rank);
+/* in-place sum of n doubles in device memory over the ranks, queued on the compute stream: the three boost::mpi::reduce
+ * calls of all_vectors_scatter_device.cpp:335-343 / self_vectors_scatter_device.cpp:213-221 as one all-reduce of the packed
+ * partial, and the amplitude sum of the atom-sharded multipole path. */
+int sgpu_comm_allreduce(sgpu_ctx *ctx, double *d_buf, size_t n);
+/* AllVectorsScatterDevice::compute with the FRAMES sharded over the partition (NNPP > 1: all_vectors_scatter_device.cpp:
+ * 61,248,408).  Every rank has staged its DivAssignment block of the frames (sgpu_set_frame_window).  The ranks evaluate
+ * their blocks, exchange them so that every rank holds complete timelines of its DivAssignment block of the subvectors
+ * (grouped ncclSend/ncclRecv = the reference's all_to_all, :169-184; assembling the pieces = its alignpad, :186-207; each
+ * rank sends 1/N of its amplitudes to each peer instead of summing a zero-padded buffer), correlate them and sum the packed
+ * partials.  The exchange of a pass overlaps the next pass's amplitudes.  On return (asynchronously) d_partials holds the
+ * REDUCED partials on every rank: [NQ][sgpu_partial_len] for the scan form, one partial for the single-|q| form; pass them
+ * to sgpu_finalize.  Collective: every rank of the communicator must call with the same arguments. */
+int sgpu_compute_all_vectors_scan_sharded(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, int dsp_type,
+                                          double *d_partials);
+int sgpu_compute_all_vectors_sharded(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, double *d_partial);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,19 @@ typedef struct sass_comm_vtbl {
     int (*barrier)(void *user);
     void *(*split)(void *user, int color); /* boost::mpi::communicator::split; returns the new `user` handle */
     void (*release)(void *user);
+    /* optional (may be NULL): the ncclComm_t behind this communicator.  When present, the frame-sharded coherent device hands
+     * it to the library (sgpu_comm_adopt) and exchanges amplitudes with ncclSend/ncclRecv on the device streams. */
+    void *(*nccl_comm)(void *user);
 } sass_comm_vtbl;
+
+/* A communicator implemented inside the library on NCCL (one process per GPU): every callback is native code, so
+ * sass_scatter_run / sass_job_run drive a multi-GPU run without any Python on the path.  One rank creates the id
+ * (sass_comm_nccl_unique_id) and distributes it — sass_comm_nccl_bootstrap_file does that through a file on a single
+ * node: rank 0 writes `path`, the others wait for it.  sass_comm_nccl_create is collective (ncclCommInitRank); split() is
+ * ncclCommSplit; all-reduces run on a stream of the communicator's own and are complete on return. */
+int sass_comm_nccl_unique_id(char id128[128]);
+int sass_comm_nccl_bootstrap_file(const char *path, int nranks, int rank, double timeout_s, char id128[128]);
+int sass_comm_nccl_create(const char id128[128], int nranks, int rank, int device, sass_comm_vtbl *out);
 
 /* The C-ABI (sassena_b200.h) as a table.  NULL selects the library's own sgpu_* functions; tests bind the table
  * to the CPU oracle to exercise the multi-rank host logic without a GPU. */
@@ -66,6 +78,15 @@ typedef struct sass_backend_vtbl {
     /* multipole cylinder */
     int (*frames_to_cylindrical)(sgpu_ctx *, const double *);
     int (*mpcylinder_amplitudes)(sgpu_ctx *, const double *, const double *, const long *, size_t, size_t, size_t, double *);
+    /* double-buffered atom waves of the self path: pinned host blocks [count][NF][3] -> back buffer, then swap */
+    int (*stage_atoms_prefetch)(sgpu_ctx *, const float *, size_t, size_t);
+    int (*stage_atoms_swap)(sgpu_ctx *);
+    int (*host_alloc)(void **, size_t);
+    int (*host_free)(void *);
+    /* optional (may be NULL): NCCL inside the library for the frame-sharded coherent path */
+    int (*comm_adopt)(sgpu_ctx *, void *, int, int);
+    int (*compute_all_vectors_scan_sharded)(sgpu_ctx *, const double *, size_t, const double *, size_t, int, double *);
+    int (*compute_all_vectors_sharded)(sgpu_ctx *, const double *, size_t, int, double *);
 } sass_backend_vtbl;
 
 const char *sass_last_error(void);

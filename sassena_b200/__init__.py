@@ -8,5 +8,5 @@ a thin ctypes binding used by tests and bench.py; it contains no compute and no 
 from ._lib import load_library, LibraryMissing  # noqa: F401
 from .api import (  # noqa: F401
     DSP_AUTOCORRELATE, DSP_PLAIN, DSP_SQUARE, METHOD_DIRECT, METHOD_FFTW, REPR_CARTESIAN, REPR_SPHERICAL,
-    ScatterContext, SgpuError,
+    ScatterContext, SgpuError, comm_unique_id,
 )

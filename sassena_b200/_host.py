@@ -11,11 +11,12 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 SPLIT_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int)
 RELEASE_FN = C.CFUNCTYPE(None, C.c_void_p)
+NCCL_COMM_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p)
 
 
 class CommVtbl(C.Structure):
     _fields_ = [("user", C.c_void_p), ("rank", RANK_FN), ("size", SIZE_FN), ("allreduce_sum", ALLREDUCE_FN),
-                ("barrier", BARRIER_FN), ("split", SPLIT_FN), ("release", RELEASE_FN)]
+                ("barrier", BARRIER_FN), ("split", SPLIT_FN), ("release", RELEASE_FN), ("nccl_comm", NCCL_COMM_FN)]
 
 
 # backend table: same order as sass_backend_vtbl
@@ -45,6 +46,8 @@ BE_STAGE_WAVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_siz
 BE_ACCUMULATE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 BE_TO_CYL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p)
 BE_CYL_AMPL = C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, c_double_p, c_long_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p)
+BE_PREFETCH = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t)
+BE_SWAP = C.CFUNCTYPE(C.c_int, C.c_void_p)
 BE_ALLOC = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_size_t)
 BE_FREE = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -61,13 +64,22 @@ class BackendVtbl(C.Structure):
                 ("all_vectors_amplitudes", BE_AV_AMPL), ("all_vectors_dsp_partial", BE_AV_DSP),
                 ("compute_all_vectors_scan_partial", BE_AV_SCAN), ("all_vectors_scan_amplitudes", BE_AV_SCAN_AMPL),
                 ("stage_atoms_wave", BE_STAGE_WAVE), ("accumulate", BE_ACCUMULATE),
-                ("frames_to_cylindrical", BE_TO_CYL), ("mpcylinder_amplitudes", BE_CYL_AMPL)]
+                ("frames_to_cylindrical", BE_TO_CYL), ("mpcylinder_amplitudes", BE_CYL_AMPL),
+                ("stage_atoms_prefetch", BE_PREFETCH), ("stage_atoms_swap", BE_SWAP),
+                ("host_alloc", BE_ALLOC), ("host_free", BE_FREE),
+                ("comm_adopt", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int)),
+                ("compute_all_vectors_scan_sharded",
+                 C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_int, C.c_void_p)),
+                ("compute_all_vectors_sharded", C.CFUNCTYPE(C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p))]
 
 
 FACTORS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, c_double_p, C.c_size_t)
 WRITE_FN = C.CFUNCTYPE(None, C.c_void_p, c_double_p, c_double_p, C.c_size_t, c_double_p, c_double_p)
 
 SIGNATURES = {
+    "sass_comm_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "sass_comm_nccl_bootstrap_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_char_p]),
+    "sass_comm_nccl_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sass_last_error": (C.c_char_p, []),
     "sass_params_new": (C.c_void_p, []),
     "sass_params_free": (None, [C.c_void_p]),

@@ -41,6 +41,17 @@ SIGNATURES = {
     "sgpu_stage_atoms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_from_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "sgpu_comm_get_unique_id": (C.c_int, [C.c_char_p]),
+    "sgpu_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "sgpu_comm_adopt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "sgpu_comm_destroy": (C.c_int, [C.c_void_p]),
+    "sgpu_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sgpu_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sgpu_compute_all_vectors_scan_sharded": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, c_double_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "sgpu_compute_all_vectors_sharded": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "sgpu_stage_atoms_prefetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "sgpu_stage_atoms_swap": (C.c_int, [C.c_void_p]),
+    "sgpu_device_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "sgpu_stage_atoms_wave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
     "sgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sgpu_set_factors": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t]),

@@ -165,6 +165,22 @@ class ScatterContext:
         self._NFt = 0
         self.NA = count
 
+    def stage_atoms_prefetch(self, xyz_block):
+        """queue the H2D copy of a block of atoms (host float32 [count][NF][3], pinned for an asynchronous copy) into the
+        back wave buffer; returns at once.  The array must stay alive until the matching swap's first compute has returned."""
+        a = xyz_block
+        assert a.dtype == np.float32 and a.ndim == 3 and a.shape[2] == 3 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.sgpu_stage_atoms_prefetch(self.h, a.ctypes.data, a.shape[0], a.shape[1]))
+
+    def stage_atoms_swap(self):
+        """make the prefetched block the staged atoms (no host synchronisation)"""
+        self._ck(self.lib.sgpu_stage_atoms_swap(self.h))
+
+    def device_bytes(self) -> int:
+        n = C.c_size_t(0)
+        self._ck(self.lib.sgpu_device_bytes(self.h, C.byref(n)))
+        return int(n.value)
+
     def accumulate(self, d_dst: int, d_src: int, n: int):
         self._ck(self.lib.sgpu_accumulate(self.h, C.c_void_p(d_dst), C.c_void_p(d_src), n))
 
@@ -289,6 +305,31 @@ class ScatterContext:
         self._ck(self.lib.sgpu_compute_all_vectors_scan_partial(self.h, _dp(v), len(v), _dp(s), len(s), _dsp(dsp),
                                                                 C.c_void_p(d_partials)))
 
+    # ---- the partition's NCCL communicator inside the library
+    def comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        """collective: every rank of the partition calls it with the id rank 0 obtained from comm_unique_id()"""
+        assert len(unique_id) == 128
+        self._ck(self.lib.sgpu_comm_init(self.h, unique_id, nranks, rank))
+
+    def comm_destroy(self):
+        self._ck(self.lib.sgpu_comm_destroy(self.h))
+
+    def comm_allreduce(self, d_buf: int, n: int):
+        """in-place sum of n doubles in device memory over the ranks, on the compute stream (no host synchronisation)"""
+        self._ck(self.lib.sgpu_comm_allreduce(self.h, C.c_void_p(d_buf), n))
+
+    def compute_all_vectors_scan_sharded(self, v, s, d_partials: int, dsp="autocorrelate"):
+        """frame-sharded coherent scan: local amplitudes, exchange over NVLink, DSP of this rank's timelines, all-reduce of the
+        packed partials; d_partials [len(s)][partial_len] holds the reduced partials on every rank"""
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
+        s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1)
+        self._ck(self.lib.sgpu_compute_all_vectors_scan_sharded(self.h, _dp(v), len(v), _dp(s), len(s), _dsp(dsp),
+                                                                C.c_void_p(d_partials)))
+
+    def compute_all_vectors_sharded(self, qvecs, d_partial: int, dsp="autocorrelate"):
+        q = np.ascontiguousarray(qvecs, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.sgpu_compute_all_vectors_sharded(self.h, _dp(q), len(q), _dsp(dsp), C.c_void_p(d_partial)))
+
     def all_vectors_scan_amplitudes(self, v, s, d_amp: int):
         v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 3)
         s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1)
@@ -377,3 +418,12 @@ class ScatterContext:
         self._ck(self.lib.sgpu_synth_trajectory(self.h, C.c_void_p(d_ptr), NF, NA, atom0, atom_stride, NA_out,
                                                 C.c_float(box), C.c_float(offset), C.c_float(step_scale(sigma)),
                                                 C.c_uint64(seed), layout))
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (one rank creates it, all ranks pass it to ScatterContext.comm_init)"""
+    buf = C.create_string_buffer(128)
+    rc = load_library().sgpu_comm_get_unique_id(buf)
+    if rc:
+        raise SgpuError(rc, "sgpu_comm_get_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw

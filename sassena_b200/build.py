@@ -24,7 +24,7 @@ OBJDIR = os.path.join(HERE, "build")  # git-ignored; one object per source so th
 
 def sources():
     srcs = sorted(glob.glob(os.path.join(CSRC, "kernels", "*.cu")))
-    srcs += sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    srcs += sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(CSRC, "*.cpp")))
     srcs += sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp")))
     return srcs
 
@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = base + ["--shared", "-o", LIB] + objs
+    cmd = base + ["--shared", "-o", LIB] + objs + ["-ldl"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd, env=env)

@@ -1,7 +1,11 @@
 // control.cpp — see control.hpp.  Reference citations are relative to benlabs/sassena v1.4.2.
 #include "control.hpp"
 
+#include <dirent.h>
 #include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
 
 #include <cmath>
 #include <cstdio>
@@ -487,6 +491,8 @@ void Config::read_xml(const std::string &filename) {
     // ---- limits (parameters.cpp:612-736): the keys the GPU path keeps ----
     if (x.exists("//limits/stage/memory/data")) limits.stage_memory_data = x.get_size("//limits/stage/memory/data");
     if (x.exists("//limits/signal/chunksize")) signal_chunksize = x.get_size("//limits/signal/chunksize");
+    if (x.exists("//limits/services/signal/times/serverflush"))
+        signal_flush_seconds = x.get_size("//limits/services/signal/times/serverflush");
     if (x.exists("//limits/stage/stream")) limits.stage_stream = x.get_bool("//limits/stage/stream");
     if (x.exists("//limits/decomposition/utilization"))
         limits.decomposition.utilization = x.get_double("//limits/decomposition/utilization");
@@ -989,9 +995,82 @@ bool read_npy(const std::string &path, std::vector<double> &data, std::vector<si
 }
 
 namespace {
+// Row journal: every result row is appended to <dir>/rows.journal and flushed to the file system the moment the device hands
+// it over, so a run that dies keeps every q-vector it has finished (the reference's HDF5WriterService appends rows as the
+// partitions deliver them, file_writer_service.cpp:314-484, which is what makes its resume logic, sassena.cpp:270-305, useful).
+// Record = q(3) | fq(2) | fq2(2) | fqt(2 NF) doubles, preceded once by a header {magic, NF}.
+const double kJournalMagic = 20260117.5;
+
+struct RowJournal {
+    FILE *f = nullptr;
+    std::string path;
+    void open(const std::string &p, size_t NF) {
+        path = p;
+        f = fopen(p.c_str(), "wb");
+        if (!f) throw Error("cannot create " + p);
+        const double hdr[2] = {kJournalMagic, (double)NF};
+        fwrite(hdr, sizeof(double), 2, f);
+        fflush(f);
+    }
+    void append(const double q[3], const double *fqt, size_t NF, const double fq[2], const double fq2[2]) {
+        if (!f) return;
+        fwrite(q, sizeof(double), 3, f);
+        fwrite(fq, sizeof(double), 2, f);
+        fwrite(fq2, sizeof(double), 2, f);
+        fwrite(fqt, sizeof(double), 2 * NF, f);
+        fflush(f);
+        fsync(fileno(f));
+    }
+    void close() {
+        if (f) fclose(f);
+        f = nullptr;
+    }
+    ~RowJournal() { close(); }
+};
+
+// complete records of a journal (a torn last record -- the process died inside append -- is dropped); false if absent
+bool read_journal(const std::string &path, size_t NF, std::vector<double> &rows) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    double hdr[2];
+    rows.clear();
+    if (fread(hdr, sizeof(double), 2, f) == 2 && hdr[0] == kJournalMagic && (size_t)hdr[1] == NF) {
+        const size_t rec = 7 + 2 * NF;
+        std::vector<double> r(rec);
+        while (fread(r.data(), sizeof(double), rec, f) == rec) rows.insert(rows.end(), r.begin(), r.end());
+    }
+    fclose(f);
+    return true;
+}
+
+// names in `dir` that start with `prefix`
+std::vector<std::string> list_dir(const std::string &dir, const std::string &prefix) {
+    std::vector<std::string> out;
+    if (DIR *d = opendir(dir.c_str())) {
+        while (dirent *e = readdir(d)) {
+            const std::string n = e->d_name;
+            if (n != "." && n != ".." && n.compare(0, prefix.size(), prefix) == 0) out.push_back(n);
+        }
+        closedir(d);
+    }
+    return out;
+}
+
+void remove_rank_dirs(const std::string &signal_dir) {
+    for (const std::string &n : list_dir(signal_dir, "rank_")) {
+        const std::string d = signal_dir + "/" + n;
+        for (const std::string &fn : list_dir(d, "")) unlink((d + "/" + fn).c_str());
+        rmdir(d.c_str());
+    }
+}
+
 struct Collector : IResultSink {
     size_t NF = 0;
     std::vector<double> q, fqt, fq0, fq, fq2;
+    RowJournal *journal = nullptr;
+    SignalFileH5 *h5 = nullptr;  // single-rank HDF5 runs append to the file as they go and flush it periodically
+    size_t flush_seconds = 600;
+    std::chrono::steady_clock::time_point last_flush = std::chrono::steady_clock::now();
     void write(CartesianCoor3D qv, const double *t, size_t nf, std::complex<double> a, std::complex<double> a2) override {
         NF = nf;
         q.push_back(qv.x);
@@ -1004,6 +1083,16 @@ struct Collector : IResultSink {
         fq.push_back(a.imag());
         fq2.push_back(a2.real());
         fq2.push_back(a2.imag());
+        const double qq[3] = {qv.x, qv.y, qv.z}, f1[2] = {a.real(), a.imag()}, f2[2] = {a2.real(), a2.imag()};
+        if (journal) journal->append(qq, t, nf, f1, f2);
+        if (h5) {
+            h5->write(qq, t, f1, f2);
+            const auto now = std::chrono::steady_clock::now();
+            if (std::chrono::duration<double>(now - last_flush).count() >= (double)flush_seconds) {
+                h5->flush();  // file_writer_service.cpp:292-295: flush when serverflush seconds have passed
+                last_flush = now;
+            }
+        }
     }
 };
 }  // namespace
@@ -1034,15 +1123,49 @@ size_t Job::run(const std::string &signal_dir_in, std::shared_ptr<ICommunicator>
     const bool h5mode = signal_dir_in.size() > 3 && signal_dir_in.compare(signal_dir_in.size() - 3, 3, ".h5") == 0;
     const std::string signal_dir = h5mode ? signal_dir_in + ".d" : signal_dir_in;
     std::unique_ptr<SignalFileH5> h5file;
+    bool h5_loaded = false;  // the writer holds the rows of an existing file
     if (h5mode) {
         // every rank reads the existing file (same file system) so that all agree on the q-vectors left to compute
         h5file.reset(new SignalFileH5(signal_dir_in, s.NF, cfg.signal_chunksize, cfg.signal_fqt, cfg.signal_fq0, cfg.signal_fq,
                                       cfg.signal_fq2));
         h5file->set_meta(cfg.rawconfig, cfg.rawconfig, db.rawconfig);
-        std::vector<double> old;
+        // rows an interrupted run left in its journals go into the file first (rank 0), so that every rank then sees them as
+        // done; stale per-rank directories of an earlier run are removed
+        if (comm->rank() == 0) {
+            std::vector<std::string> journals;
+            for (const std::string &n : list_dir(signal_dir, "rank_")) journals.push_back(signal_dir + "/" + n + "/rows.journal");
+            journals.push_back(signal_dir + "/rows.journal");
+            bool opened = false;
+            std::vector<double> have;
+            for (const std::string &jp : journals) {
+                std::vector<double> rows;
+                if (!read_journal(jp, s.NF, rows) || rows.empty()) continue;
+                if (!opened) {
+                    have = h5file->init();
+                    opened = true;
+                }
+                const size_t rec = 7 + 2 * s.NF;
+                for (size_t i = 0; i + rec <= rows.size(); i += rec) {
+                    const double *r = &rows[i];
+                    bool done = false;
+                    for (size_t k = 0; k + 2 < have.size() && !done; k += 3) done = have[k] == r[0] && have[k + 1] == r[1] && have[k + 2] == r[2];
+                    if (done) continue;
+                    h5file->write(r, r + 7, r + 3, r + 5);
+                    have.insert(have.end(), r, r + 3);
+                }
+            }
+            if (opened) h5file->flush();
+            for (const std::string &jp : journals) unlink(jp.c_str());
+            remove_rank_dirs(signal_dir);
+        }
+        comm->barrier();
+        std::vector<double> old;  // (init() below re-reads the file, recovered rows included)
         {
             std::ifstream probe(signal_dir_in.c_str());
-            if (probe.good()) old = h5file->init();  // only rank 0 creates / rewrites the file (below)
+            if (probe.good()) {
+                old = h5file->init();  // only rank 0 creates / rewrites the file (below)
+                h5_loaded = true;
+            }
         }
         if (!old.empty()) {  // only compute those q vectors which have not been written so far (sassena.cpp:277-291)
             std::vector<CartesianCoor3D> left;
@@ -1054,18 +1177,32 @@ size_t Job::run(const std::string &signal_dir_in, std::shared_ptr<ICommunicator>
             qv.swap(left);
         }
     }
-    std::unique_ptr<IScatterDevice> dev;
-    if (!qv.empty()) dev.reset(ScatterDeviceFactory::create(comm, sample, &sink, qv, cfg, be, ctx));  // else: "No qvectors left to compute."
-    if (dev) dev->run();
-    // every writing rank (partition rank 0) stores its rows; rows pair up through qvectors (arrival order, as in the
-    // reference's HDF5 file, file_writer_service.cpp:314-484)
+    // every writing rank (partition rank 0) journals its rows as they arrive; rows pair up through qvectors (arrival order,
+    // as in the reference's HDF5 file, file_writer_service.cpp:314-484)
     mkdir(signal_dir.c_str(), 0777);
-    const size_t n = sink.q.size() / 3;
+    if (!h5mode) {  // stale per-rank directories of an earlier run must not be mistaken for this run's rows
+        if (comm->rank() == 0) remove_rank_dirs(signal_dir);
+        comm->barrier();
+    }
     std::string dir = signal_dir;
     if (comm->size() > 1) {
         dir = signal_dir + "/rank_" + std::to_string(comm->rank());
         mkdir(dir.c_str(), 0777);
     }
+    RowJournal journal;
+    journal.open(dir + "/rows.journal", s.NF);
+    sink.journal = &journal;
+    sink.flush_seconds = cfg.signal_flush_seconds;
+    const bool h5direct = h5mode && comm->size() == 1;  // one rank: rows go straight into the HDF5 writer, flushed periodically
+    if (h5direct) {
+        if (!h5_loaded) h5file->init();
+        sink.h5 = h5file.get();
+    }
+    std::unique_ptr<IScatterDevice> dev;
+    if (!qv.empty()) dev.reset(ScatterDeviceFactory::create(comm, sample, &sink, qv, cfg, be, ctx));  // else: "No qvectors left to compute."
+    if (dev) dev->run();
+    journal.close();
+    const size_t n = sink.q.size() / 3;
     if (n > 0 || comm->size() == 1 || h5mode) {  // (h5 mode always rewrites: stale rows of an earlier run must not be merged)
         write_npy(dir + "/qvectors.npy", sink.q.data(), {n, 3});
         if (cfg.signal_fqt) write_npy(dir + "/fqt.npy", sink.fqt.data(), {n, s.NF, 2});
@@ -1074,33 +1211,25 @@ size_t Job::run(const std::string &signal_dir_in, std::shared_ptr<ICommunicator>
         if (cfg.signal_fq2) write_npy(dir + "/fq2.npy", sink.fq2.data(), {n, 2});
     }
     comm->barrier();
-    if (h5mode && comm->rank() == 0) {
+    if (h5direct) {
+        h5file->flush();
+        unlink(journal.path.c_str());
+    } else if (h5mode && comm->rank() == 0) {
         // the reference's writer service runs on world rank 0 and receives the rows of every partition (file_writer_service
-        // .cpp:252-310); here rank 0 collects them from the per-rank row files once all ranks are done
+        // .cpp:252-310); here rank 0 collects them from the per-rank journals once all ranks are done
+        if (!h5_loaded) h5file->init();
+        const size_t rec = 7 + 2 * s.NF;
         for (size_t r = 0; r < comm->size(); r++) {
-            const std::string d = comm->size() > 1 ? signal_dir + "/rank_" + std::to_string(r) : signal_dir;
-            std::vector<size_t> shape;
-            std::vector<double> rq, rfqt, rfq, rfq2;
-            if (!read_npy(d + "/qvectors.npy", rq, shape)) continue;
-            const size_t rows = rq.size() / 3;
-            if (rows == 0) continue;
-            if (cfg.signal_fqt && !read_npy(d + "/fqt.npy", rfqt, shape)) throw Error("missing fqt rows of rank " + std::to_string(r));
-            if (!cfg.signal_fqt) {  // fq0 is taken from fqt[0]; without fqt the fq0 rows stand in
-                std::vector<double> f0;
-                if (cfg.signal_fq0 && !read_npy(d + "/fq0.npy", f0, shape)) throw Error("missing fq0 rows of rank " + std::to_string(r));
-                rfqt.assign(rows * 2 * s.NF, 0.0);
-                for (size_t i = 0; i < rows && !f0.empty(); i++) {
-                    rfqt[i * 2 * s.NF] = f0[2 * i];
-                    rfqt[i * 2 * s.NF + 1] = f0[2 * i + 1];
-                }
-            }
-            if (cfg.signal_fq && !read_npy(d + "/fq.npy", rfq, shape)) throw Error("missing fq rows of rank " + std::to_string(r));
-            if (cfg.signal_fq2 && !read_npy(d + "/fq2.npy", rfq2, shape)) throw Error("missing fq2 rows of rank " + std::to_string(r));
-            const double zero[2] = {0.0, 0.0};
-            for (size_t i = 0; i < rows; i++)
-                h5file->write(&rq[3 * i], &rfqt[i * 2 * s.NF], cfg.signal_fq ? &rfq[2 * i] : zero, cfg.signal_fq2 ? &rfq2[2 * i] : zero);
+            const std::string jp = (comm->size() > 1 ? signal_dir + "/rank_" + std::to_string(r) : signal_dir) + "/rows.journal";
+            std::vector<double> rows;
+            if (!read_journal(jp, s.NF, rows)) continue;
+            for (size_t i = 0; i + rec <= rows.size(); i += rec) h5file->write(&rows[i], &rows[i + 7], &rows[i + 3], &rows[i + 5]);
         }
         h5file->flush();
+        for (size_t r = 0; r < comm->size(); r++)
+            unlink(((comm->size() > 1 ? signal_dir + "/rank_" + std::to_string(r) : signal_dir) + "/rows.journal").c_str());
+    } else if (!h5mode) {
+        unlink(journal.path.c_str());  // the .npy datasets above hold the rows
     }
     comm->barrier();
     if (report) {

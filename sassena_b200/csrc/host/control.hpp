@@ -105,6 +105,7 @@ struct Config : Params {
     std::string signal_file = "signal.h5", signal_filepath;
     bool signal_fqt = true, signal_fq0 = true, signal_fq = true, signal_fq2 = true;
     size_t signal_chunksize = 10000;  // limits.signal.chunksize (parameters.cpp:626)
+    size_t signal_flush_seconds = 600;  // limits.services.signal.times.serverflush (parameters.cpp:628,703-705)
     std::string rawconfig;            // the configuration file as read (Params::get_rawconfig, meta/rawconfig + meta/config)
     // database
     std::string database_file = "db.xml", database_filepath, database_format = "xml";

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <random>
 
@@ -299,7 +300,14 @@ const SgpuBackend &default_backend() {
                                    sgpu_stage_atoms_wave,
                                    sgpu_accumulate,
                                    sgpu_frames_to_cylindrical,
-                                   sgpu_mpcylinder_amplitudes};
+                                   sgpu_mpcylinder_amplitudes,
+                                   sgpu_stage_atoms_prefetch,
+                                   sgpu_stage_atoms_swap,
+                                   sgpu_host_alloc,
+                                   sgpu_host_free,
+                                   sgpu_comm_adopt,
+                                   sgpu_compute_all_vectors_scan_sharded,
+                                   sgpu_compute_all_vectors_sharded};
     return be;
 }
 
@@ -640,6 +648,14 @@ void AllVectorsScatterDevice::stage_data() {
     if (frame_sharded_) data_stager.stage_block();
     else data_stager.stage(SGPU_REPR_CARTESIAN);
     factors_.assign(NA, 0.0);
+    // a partition communicator that is an NCCL communicator goes to the library: the amplitude exchange then runs as
+    // grouped ncclSend/ncclRecv on the device streams (all_to_all + alignpad, all_vectors_scatter_device.cpp:169-207)
+    nccl_sharded_ = false;
+    if (frame_sharded_ && partitioncomm_->nccl_comm() && be_.comm_adopt && be_.compute_all_vectors_scan_sharded &&
+        be_.compute_all_vectors_sharded) {
+        ck(be_.comm_adopt(ctx_, partitioncomm_->nccl_comm(), (int)NNPP, (int)partitioncomm_->rank()), "sgpu_comm_adopt");
+        nccl_sharded_ = true;
+    }
 }
 
 // Frame decomposition (the reference's own, all_vectors_scatter_device.cpp:245-361): amplitudes of this rank's frames
@@ -654,6 +670,22 @@ void AllVectorsScatterDevice::compute_frame_sharded() {
         qv[3 * i] = s.x;
         qv[3 * i + 1] = s.y;
         qv[3 * i + 2] = s.z;
+    }
+    if (nccl_sharded_) {
+        // amplitudes, exchange, DSP of this rank's timelines and the reduction of the packed partial inside the library
+        double *partial = partial_buffer(dsp);
+        timer_.start("sd:c:block");
+        ck(be_.compute_all_vectors_sharded(ctx_, qv.data(), NM, dsp, partial), "sgpu_compute_all_vectors_sharded");
+        timer_.stop("sd:c:block");
+        timer_.start("sd:c:b:exchange");
+        ck(be_.synchronize(ctx_), "sgpu_synchronize");
+        timer_.stop("sd:c:b:exchange");
+        current_subvector_ = NM;
+        double af[2], a2f[2];
+        ck(be_.finalize(ctx_, partial, dsp, dsp_method_code(), 1.0 / subvector_index_.size(), atfinal_.data(), af, a2f), "sgpu_finalize");
+        afinal_ = std::complex<double>(af[0], af[1]);
+        a2final_ = std::complex<double>(a2f[0], a2f[1]);
+        return;
     }
     const size_t amp_len = 2 * NM * NF;
     if (amp_len > amp_cap_) {
@@ -799,7 +831,17 @@ void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> 
     }
     const size_t NNPP = partitioncomm_->size();
     DivAssignment mine(NNPP, partitioncomm_->rank(), nm);
-    if (frame_sharded_) {
+    bool reduced = false;
+    if (frame_sharded_ && nccl_sharded_) {
+        timer_.start("sd:c:block");
+        ck(be_.compute_all_vectors_scan_sharded(ctx_, v.data(), nm, s.data(), nq, dsp, d_partial_),
+           "sgpu_compute_all_vectors_scan_sharded");
+        timer_.stop("sd:c:block");
+        timer_.start("sd:c:b:exchange");
+        ck(be_.synchronize(ctx_), "sgpu_synchronize");
+        timer_.stop("sd:c:b:exchange");
+        reduced = true;  // the library has summed the packed partials over the partition
+    } else if (frame_sharded_) {
         const size_t amp_len = 2 * nq * nm * NF;
         if (amp_len > amp_cap_) {
             if (d_amp_) be_.device_free(d_amp_);
@@ -833,7 +875,7 @@ void AllVectorsScatterDevice::compute_scan(size_t nq, const std::vector<double> 
     ck(be_.synchronize(ctx_), "sgpu_synchronize");
     timer_.stop("sd:c:wait");
     timer_.start("sd:c:reduce");
-    if (NNPP > 1) partitioncomm_->allreduce_sum(d_partial_, nq * plen);
+    if (NNPP > 1 && !reduced) partitioncomm_->allreduce_sum(d_partial_, nq * plen);
     timer_.stop("sd:c:reduce");
     batch_atfinal_.assign(nq, std::vector<double>(2 * NF));
     batch_afinal_.assign(nq, 0.0);
@@ -891,6 +933,46 @@ SelfVectorsScatterDevice::SelfVectorsScatterDevice(std::shared_ptr<ICommunicator
 
 SelfVectorsScatterDevice::~SelfVectorsScatterDevice() {
     if (d_acc_) be_.device_free(d_acc_);
+    if (h_atoms_) be_.host_free(h_atoms_);
+}
+
+// DataStagerByAtom for a share that does not fit the coordinate budget (data_stager.cpp:214-349 stops there, :194-204): this
+// rank's atoms are gathered ONCE from the frame-major trajectory into an atom-major pinned host buffer [n_local][NF][3]
+// (tiles of frames x atoms so that both sides move whole cache lines; host threads), from which contiguous blocks of atoms
+// then stream to the GPU.
+void SelfVectorsScatterDevice::gather_atoms_to_host() {
+    const size_t nloc = assignment_.size();
+    if (nloc == 0) return;
+    void *p = nullptr;
+    if (be_.host_alloc(&p, nloc * NF * 3 * sizeof(float))) throw Error("pinned host allocation of the rank's atoms failed");
+    h_atoms_ = static_cast<float *>(p);
+    const float *frames = sample_.frames;
+    const size_t TF = 64, TA = 256;
+    const size_t ntiles = (nloc + TA - 1) / TA;
+    const unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)std::min<size_t>(ntiles, 16)));
+    auto work = [&](unsigned tid) {
+        for (size_t ta = tid; ta < ntiles; ta += nthreads) {
+            const size_t a0 = ta * TA, a1 = std::min(nloc, a0 + TA);
+            for (size_t f0 = 0; f0 < NF; f0 += TF) {
+                const size_t f1 = std::min(NF, f0 + TF);
+                for (size_t a = a0; a < a1; a++) {
+                    const size_t src_atom = assignment_[a];
+                    float *dst = h_atoms_ + (a * NF + f0) * 3;
+                    for (size_t f = f0; f < f1; f++) {
+                        const float *src = frames + (f * NA + src_atom) * 3;
+                        dst[0] = src[0];
+                        dst[1] = src[1];
+                        dst[2] = src[2];
+                        dst += 3;
+                    }
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &t : pool) t.join();
 }
 
 void SelfVectorsScatterDevice::stage_data() {
@@ -899,9 +981,13 @@ void SelfVectorsScatterDevice::stage_data() {
     const size_t share = assignment_.max() * atom_bytes;  // data_stager.cpp:194-204
     if (share > params_.limits.stage_memory_data && params_.limits.stage_stream) {
         // the share does not fit the coordinate budget: waves of as many atoms as do; staged inside runner()
+        // two wave buffers live on the device: half the budget each
         streamed_ = true;
-        wave_atoms_ = std::max<size_t>(1, params_.limits.stage_memory_data / atom_bytes);
+        wave_atoms_ = std::max<size_t>(1, params_.limits.stage_memory_data / (2 * atom_bytes));
         waves_ = (assignment_.size() + wave_atoms_ - 1) / wave_atoms_;
+        timer_.start("sd:stage");
+        gather_atoms_to_host();
+        timer_.stop("sd:stage");
         return;
     }
     DataStagerByAtom data_stager(sample_, *allcomm_, *partitioncomm_, timer_, be_, ctx_, params_);
@@ -948,13 +1034,20 @@ void SelfVectorsScatterDevice::runner() {
     dsp_method_code();
     const size_t nq = vectors_.size();
     size_t plen = 0;
+    auto wave_count = [&](size_t w) { return waves_ ? std::min(wave_atoms_, assignment_.size() - w * wave_atoms_) : (size_t)0; };
+    auto prefetch = [&](size_t w) {
+        if (w < waves_ && wave_count(w) > 0)
+            ck(be_.stage_atoms_prefetch(ctx_, h_atoms_ + w * wave_atoms_ * NF * 3, wave_count(w), NF), "sgpu_stage_atoms_prefetch");
+    };
+    prefetch(0);
     for (size_t w = 0; w < std::max<size_t>(waves_, 1); w++) {
         const size_t first = w * wave_atoms_;
-        const size_t count = waves_ ? std::min(wave_atoms_, assignment_.size() - first) : 0;
+        const size_t count = wave_count(w);
         timer_.start("sd:stage");
         if (count > 0) {
-            ck(be_.stage_atoms_wave(ctx_, sample_.frames, NF, NA, assignment_[first], partitioncomm_->size(), count),
-               "sgpu_stage_atoms_wave");
+            // wave w becomes the staged atoms; wave w+1 starts travelling while w is evaluated (double buffering)
+            ck(be_.stage_atoms_swap(ctx_), "sgpu_stage_atoms_swap");
+            prefetch(w + 1);
         }
         timer_.stop("sd:stage");
         if (w == 0) {
@@ -1209,10 +1302,13 @@ IScatterDevice *ScatterDeviceFactory::create(std::shared_ptr<ICommunicator> scat
     size_t allcommsize = partitions * partitionsize;
     int allcommflag = scatter_comm->rank() < allcommsize ? 1 : 0;
     std::shared_ptr<ICommunicator> all_comm = scatter_comm->split(allcommflag);
+    // The reference splits all_comm by partitionID (:117-120).  Here BOTH splits are collectives over scatter_comm, with a
+    // colour of their own for the ranks the plan leaves spare: a communicator whose split is job-wide under the hood
+    // (torch.distributed new_group, ncclCommSplit) would otherwise wait forever for the spare ranks, which return below.
+    // Ranks keep their order, and a partition's ranks are contiguous, so partition_comm is the same group either way.
+    size_t partitionID = allcommflag ? (all_comm->rank() * partitions) / allcommsize : partitions;
+    std::shared_ptr<ICommunicator> partition_comm = scatter_comm->split((int)partitionID);
     if (allcommflag == 0) return nullptr;
-
-    size_t partitionID = (all_comm->rank() * partitions) / allcommsize;
-    std::shared_ptr<ICommunicator> partition_comm = all_comm->split((int)partitionID);
 
     DivAssignment qindex_assignment(partitions, partitionID, qvectors.size());
     std::vector<CartesianCoor3D> thispartition_QIV;

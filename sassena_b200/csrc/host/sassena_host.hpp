@@ -261,6 +261,8 @@ class ICommunicator {
     virtual void barrier() = 0;
     // boost::mpi::communicator::split(color): ranks with equal color form a new communicator, ordered by old rank
     virtual std::shared_ptr<ICommunicator> split(int color) = 0;
+    // the ncclComm_t behind the communicator, if any (lets the library exchange amplitudes on the device streams)
+    virtual void *nccl_comm() { return nullptr; }
 };
 
 class SingleCommunicator : public ICommunicator {
@@ -285,6 +287,7 @@ class CallbackCommunicator : public ICommunicator {
     void allreduce_sum(double *d, size_t n) override;
     void barrier() override;
     std::shared_ptr<ICommunicator> split(int color) override;
+    void *nccl_comm() override { return v_.nccl_comm ? v_.nccl_comm(v_.user) : nullptr; }
 };
 
 // the C-ABI as a table (sass_backend_vtbl, include/sassena_host.h), so that the host logic can be exercised
@@ -440,6 +443,7 @@ class AbstractVectorsScatterDevice : public AbstractScatterDevice {
 class AllVectorsScatterDevice : public AbstractVectorsScatterDevice {
    protected:
     bool frame_sharded_ = false;
+    bool nccl_sharded_ = false;  // the partition communicator is NCCL: exchange and reduction run inside the library
     double *d_amp_ = nullptr;  // complex A[NM][NF] of the frame-sharded path (device)
     size_t amp_cap_ = 0;
     void stage_data() override;
@@ -470,6 +474,8 @@ class SelfVectorsScatterDevice : public AbstractVectorsScatterDevice {
     bool streamed_ = false;
     size_t wave_atoms_ = 0, waves_ = 0;
     double *d_acc_ = nullptr;  // [vectors_.size()][partial_len] partials summed over the waves
+    float *h_atoms_ = nullptr;  // pinned, [assignment_.size()][NF][3]: this rank's atoms, atom-major (streamed mode)
+    void gather_atoms_to_host();
     void stage_data() override;
     void compute() override;
     void runner() override;

@@ -23,6 +23,7 @@
 #include "kernels.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace sass {
 
@@ -367,6 +368,20 @@ size_t pick_chunks(const CorrPlan *p, size_t ntl) {
 int corr_plan_create(CorrPlan *p, size_t NF, cudaStream_t st, uint64_t *launches) {
     if (NF == 0) return 1;
     p->NF = NF;
+    p->in_sm = false;
+    if (2 * NF - 1 <= 4096 && !getenv("SASSENA_DSP_FOURSTEP")) {
+        // the padded timeline fits one SM: single-kernel DSP (selffused.cu), see CorrPlan::in_sm
+        int rc = self_plan_create(&p->sm, NF, st, launches);
+        if (rc) return rc;
+        if (p->sm.R == 1) {
+            p->in_sm = true;
+            p->L = p->sm.L;
+            p->d_tw = p->sm.d_tw;  // aliases: the context tests d_tw to see whether a plan exists
+            p->d_w = p->sm.d_w;
+            return 0;
+        }
+        self_plan_destroy(&p->sm);
+    }
     int log2L = ilog2_ceil(2 * NF);
     if (log2L < 1) log2L = 1;
     if (log2L > 2 * MAX_LOG2_SUB) return 1;  // NF > 2^21 frames not supported by the two-pass plan
@@ -394,6 +409,14 @@ int corr_plan_create(CorrPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
 }
 
 void corr_plan_destroy(CorrPlan *p) {
+    if (p->in_sm) {
+        self_plan_destroy(&p->sm);
+        p->in_sm = false;
+        p->d_tw = nullptr;
+        p->d_w = nullptr;
+        p->NF = p->L = 0;
+        return;
+    }
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_w) cudaFree(p->d_w);
     p->d_tw = nullptr;
@@ -404,6 +427,7 @@ void corr_plan_destroy(CorrPlan *p) {
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 size_t corr_work_bytes(const CorrPlan *p, size_t nt) {
+    if (p->in_sm) return std::max(self_loaded_work_bytes(&p->sm, nt), self_work_bytes(&p->sm, 1));
     const size_t N1 = (size_t)1 << p->log2N1;
     const size_t chunks = pick_chunks(p, nt);
     return align256(nt * p->L * sizeof(double2)) + align256(chunks * p->L * sizeof(double)) +
@@ -413,6 +437,7 @@ size_t corr_work_bytes(const CorrPlan *p, size_t nt) {
 int corr_power_accumulate(const CorrPlan *p, const double2 *d_A, size_t ldA, size_t nt, void *d_work, double *d_P,
                           double *d_acc, cudaStream_t st) {
     if (nt == 0) return 0;
+    if (p->in_sm) return self_power_accumulate_loaded(&p->sm, d_A, ldA, nt, d_work, d_P, d_acc, st);
     const size_t N1 = (size_t)1 << p->log2N1;
     const size_t chunks = pick_chunks(p, nt);
     char *w = reinterpret_cast<char *>(d_work);
@@ -440,6 +465,7 @@ int corr_power_accumulate(const CorrPlan *p, const double2 *d_A, size_t ldA, siz
 
 int corr_finalize(const CorrPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
                   cudaStream_t st) {
+    if (p->in_sm) return self_finalize(&p->sm, d_P, d_work, d_out, scale, conj_out, st);
     double2 *Y = reinterpret_cast<double2 *>(d_work);
     int n = run_colfft<LOAD_REALPERM>(p, d_P, p->L, 1, +1, Y, st);
     const size_t smem = sizeof(double2) << p->log2N2;

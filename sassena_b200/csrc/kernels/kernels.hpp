@@ -80,36 +80,6 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
                                   const int *d_lm, size_t NM, int lmax, double2 *d_A, size_t ldA, size_t NA,
                                   size_t a_first, size_t a_last, size_t f0, size_t nf, double *d_work, cudaStream_t st);
 
-// ---- correlate.cu -------------------------------------------------------------------------------
-struct CorrPlan {
-    size_t NF = 0;   // frames per timeline
-    size_t L = 0;    // padded FFT length (power of two >= 2*NF)
-    int log2N1 = 0;  // L = N1*N2, column FFT length N1 (strided), row FFT length N2 (contiguous)
-    int log2N2 = 0;
-    double2 *d_tw = nullptr;  // W_Nmax^k, k < Nmax/2  (Nmax = max(N1,N2)), forward sign
-    double2 *d_w = nullptr;   // weights What'[k1*N2+k2] for a_m = sum_k P[k] What[k] / (NF*L)
-    size_t Nmax = 0;
-};
-int corr_plan_create(CorrPlan *p, size_t NF, cudaStream_t st, uint64_t *launches);
-void corr_plan_destroy(CorrPlan *p);
-// bytes of scratch needed for nt timelines
-size_t corr_work_bytes(const CorrPlan *p, size_t nt);
-// DSP=autocorrelate over nt timelines A[nt][ldA] (first NF entries valid).  Accumulates (+=) into
-//   d_P[L] (power spectrum, internal [k1][k2] order), d_acc[4] = {sum a_re, sum a_im, sum |a|^2, 0}.
-int corr_power_accumulate(const CorrPlan *p, const double2 *d_A, size_t ldA, size_t nt, void *d_work, double *d_P,
-                          double *d_acc, cudaStream_t st);
-// inverse transform of the summed power spectrum: d_out[tau] = scale * c[tau]/(L*(NF-tau)), tau<NF;
-// conj_out negates the imaginary part (dsp.method=direct).  d_work >= corr_work_bytes(p,1).
-int corr_finalize(const CorrPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
-                  cudaStream_t st);
-// DSP=square / plain: d_at[NF] += sum_m f(A[m][t]); d_acc += {sum_m mean_t, sum_m |mean_t|^2}
-int dsp_elementwise_accumulate(const double2 *d_A, size_t ldA, size_t nt, size_t NF, int square, double2 *d_at,
-                               double *d_acc, void *d_work, cudaStream_t st);
-size_t dsp_elementwise_work_bytes(size_t nt);
-// out[i] = in[i]*scale (complex, n entries); acc_out[0..3] = acc[0..3]*scale
-int launch_scale_complex(const double2 *d_in, double2 *d_out, size_t n, double scale, cudaStream_t st);
-
-
 // ---- selffused.cu -------------------------------------------------------------------------------
 // fused self-scattering path (amplitudes + FFT autocorrelation in shared memory), dsp = autocorrelate
 struct SelfPlan {
@@ -141,5 +111,45 @@ int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const d
 int self_decimate_layout(const float *d_src, float *d_dst, size_t natoms, size_t NF, int R, int forward, cudaStream_t st);
 int self_finalize(const SelfPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
                   cudaStream_t st);
+// the same DSP for nt timelines that already exist in memory, A[nt][ldA] (first NF entries valid); needs p->R == 1
+size_t self_loaded_work_bytes(const SelfPlan *p, size_t nt);
+int self_power_accumulate_loaded(const SelfPlan *p, const double2 *d_A, size_t ldA, size_t nt, void *d_work, double *d_P,
+                                 double *d_acc, cudaStream_t st);
+
+
+// ---- correlate.cu -------------------------------------------------------------------------------
+struct CorrPlan {
+    size_t NF = 0;   // frames per timeline
+    size_t L = 0;    // padded FFT length (power of two >= 2*NF)
+    int log2N1 = 0;  // L = N1*N2, column FFT length N1 (strided), row FFT length N2 (contiguous)
+    int log2N2 = 0;
+    double2 *d_tw = nullptr;  // W_Nmax^k, k < Nmax/2  (Nmax = max(N1,N2)), forward sign
+    double2 *d_w = nullptr;   // weights What'[k1*N2+k2] for a_m = sum_k P[k] What[k] / (NF*L)
+    size_t Nmax = 0;
+    // short timelines (2NF-1 <= 4096): the whole transform fits one SM's shared memory, so the DSP runs in ONE kernel that
+    // reads every timeline once and never writes the spectrum (the in-SM FFT of the self path, selffused.cu) instead of
+    // the two-pass four-step FFT through HBM.  L, the layout of P and finalize are then the embedded self plan's.
+    bool in_sm = false;
+    SelfPlan sm;
+};
+int corr_plan_create(CorrPlan *p, size_t NF, cudaStream_t st, uint64_t *launches);
+void corr_plan_destroy(CorrPlan *p);
+// bytes of scratch needed for nt timelines
+size_t corr_work_bytes(const CorrPlan *p, size_t nt);
+// DSP=autocorrelate over nt timelines A[nt][ldA] (first NF entries valid).  Accumulates (+=) into
+//   d_P[L] (power spectrum, internal [k1][k2] order), d_acc[4] = {sum a_re, sum a_im, sum |a|^2, 0}.
+int corr_power_accumulate(const CorrPlan *p, const double2 *d_A, size_t ldA, size_t nt, void *d_work, double *d_P,
+                          double *d_acc, cudaStream_t st);
+// inverse transform of the summed power spectrum: d_out[tau] = scale * c[tau]/(L*(NF-tau)), tau<NF;
+// conj_out negates the imaginary part (dsp.method=direct).  d_work >= corr_work_bytes(p,1).
+int corr_finalize(const CorrPlan *p, const double *d_P, void *d_work, double2 *d_out, double scale, int conj_out,
+                  cudaStream_t st);
+// DSP=square / plain: d_at[NF] += sum_m f(A[m][t]); d_acc += {sum_m mean_t, sum_m |mean_t|^2}
+int dsp_elementwise_accumulate(const double2 *d_A, size_t ldA, size_t nt, size_t NF, int square, double2 *d_at,
+                               double *d_acc, void *d_work, cudaStream_t st);
+size_t dsp_elementwise_work_bytes(size_t nt);
+// out[i] = in[i]*scale (complex, n entries); acc_out[0..3] = acc[0..3]*scale
+int launch_scale_complex(const double2 *d_in, double2 *d_out, size_t n, double scale, cudaStream_t st);
+
 
 }  // namespace sass

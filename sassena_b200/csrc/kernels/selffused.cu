@@ -90,7 +90,7 @@ __device__ __forceinline__ void fft_dif_r4(double2 *s, int log2N, const double2 
     __syncthreads();
 }
 
-enum { GEN_AMPLITUDE = 0, GEN_WEIGHTS = 1 };
+enum { GEN_AMPLITUDE = 0, GEN_WEIGHTS = 1, GEN_LOAD = 2 };
 
 // ---- register-resident radix-16 passes -------------------------------------------------------------------------------
 // The N-point transform (N = 256 .. 4096) is done in at most three passes: radix 16, radix 16, radix N/256.  In a pass a
@@ -197,12 +197,15 @@ __device__ __forceinline__ void fft_r16(double2 *s, const TW &tw) {
 // grid = (R, G).  CTA (j, g) handles a contiguous share of the timelines tl < ntl, tl = atom_rel*NM + m.
 //   GEN_AMPLITUDE: accumulate |X|^2 into Ppart[g][j][pos] and a_part[tl][j] = sum_pos |X|^2 * What[j][pos]
 //   GEN_WEIGHTS  : single "timeline" w[tau] = 1/(NF-tau), inverse sign, store X to Wout[j][pos]
+//   GEN_LOAD     : like GEN_AMPLITUDE, but timeline tl is read from Ain[tl * ldA + n], n < NF (R == 1: no residue twiddle)
 // dynamic shared memory: padded FFT buffer (N + N/16 complex) followed by the power accumulator (N doubles)
 template <int LOG2N, int GEN>
 __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs, int NF, int NM,
     size_t atom0, size_t ntl, int R, const double2 *__restrict__ tw, const double2 *__restrict__ What,
-    double *__restrict__ Ppart, double2 *__restrict__ a_part, double2 *__restrict__ Wout) {
+    double *__restrict__ Ppart, double2 *__restrict__ a_part, double2 *__restrict__ Wout, const double2 *__restrict__ Ain,
+    size_t ldA) {
+    constexpr bool ACC = (GEN != GEN_WEIGHTS);  // accumulate power spectra and the store() means
     extern __shared__ double2 s[];
     __shared__ double2 red[SF_THREADS / 32];
     constexpr int N = 1 << LOG2N;
@@ -211,9 +214,9 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
     const size_t g = blockIdx.y, G = gridDim.y;
     const double L = (double)R * (double)N;
     // residue twiddle in quarter turns per frame index: forward -4 j / L, inverse (weights) +4 j / L
-    const double cj = ((GEN == GEN_AMPLITUDE) ? -4.0 : 4.0) * (double)j / L;
+    const double cj = ((GEN != GEN_WEIGHTS) ? -4.0 : 4.0) * (double)j / L;
 
-    if (GEN == GEN_AMPLITUDE)
+    if (ACC)
         for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) s_acc[pos] = 0.0;
 
     // contiguous share of the timelines: a CTA stays on one atom for up to NM consecutive jobs (coordinates cache-hot)
@@ -236,8 +239,13 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
         // thread (256 | N), so the shared-memory accumulation is thread-private.  Flat loop, unrolled for ILP.
         if (NF < N)
             for (int np = NF + threadIdx.x; np < N; np += SF_THREADS) s[phys(np)] = make_double2(0.0, 0.0);
+        if (GEN == GEN_LOAD) {
+            const double2 *src = Ain + tl * ldA;
 #pragma unroll 4
-        for (int n = threadIdx.x; n < NF; n += SF_THREADS) {
+            for (int n = threadIdx.x; n < NF; n += SF_THREADS) s[phys(n)] = __ldg(&src[n]);
+        }
+#pragma unroll 4
+        for (int n = threadIdx.x; n < (GEN == GEN_LOAD ? 0 : NF); n += SF_THREADS) {
             double u, amp;
             if (GEN == GEN_AMPLITUDE) {
                 const double x = (double)__ldg(&p[3 * n]), y = (double)__ldg(&p[3 * n + 1]), z = (double)__ldg(&p[3 * n + 2]);
@@ -258,8 +266,8 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
             }
             s[np] = v;
         }
-        fft_r16<LOG2N, (GEN == GEN_AMPLITUDE) ? -1 : +1>(s, GlobalTwiddles{tw});
-        if (GEN == GEN_AMPLITUDE) {
+        fft_r16<LOG2N, ACC ? -1 : +1>(s, GlobalTwiddles{tw});
+        if (ACC) {
             double2 ap = make_double2(0.0, 0.0);
 #pragma unroll 4
             for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) {
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
             for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Wout[(size_t)j * N + pos] = s[phys(pos)];
         }
     }
-    if (GEN == GEN_AMPLITUDE) {
+    if (ACC) {
         __syncthreads();
         for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) Ppart[(g * R + j) * (size_t)N + pos] = s_acc[pos];
     }
@@ -1064,13 +1072,13 @@ size_t sf_smem_bytes(int log2N) {
 template <int GEN>
 void launch_fused(int log2N, dim3 grid, cudaStream_t st, const float *xyz, const double *b, const double *qs, int NF, int NM,
                   size_t atom0, size_t ntl, int R, const double2 *tw, const double2 *What, double *Ppart,
-                  double2 *a_part, double2 *Wout) {
+                  double2 *a_part, double2 *Wout, const double2 *Ain = nullptr, size_t ldA = 0) {
     const size_t smem = sf_smem_bytes(log2N);
 #define SF_CASE(LN)                                                                                                    \
     case LN: {                                                                                                         \
         cudaFuncSetAttribute(self_fused_kernel<LN, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         self_fused_kernel<LN, GEN><<<grid, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, ntl, R, tw, What, Ppart, \
-                                                                   a_part, Wout);                                     \
+                                                                   a_part, Wout, Ain, ldA);                           \
         break;                                                                                                         \
     }
     switch (log2N) {
@@ -1331,6 +1339,37 @@ int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const d
     const double norm = 1.0 / ((double)p->NF * (double)p->L);
     sf_reduce_apart_kernel<<<(unsigned)((ntl + 255) / 256), 256, 0, st>>>(a_part, ntl, p->R, norm, a_tl);
     sf_reduce_atl_kernel<<<1, 1024, 0, st>>>(a_tl, ntl, d_acc);
+    return 4;
+}
+
+// DSP of timelines that already exist in memory (the coherent and multipole devices' A[nt][ldA]) with the in-SM transform:
+// every timeline is read once (16 NF bytes, the algorithmic minimum), nothing else touches HBM.  R == 1 only (2NF-1 <= 4096).
+static size_t loaded_groups(size_t nt) {
+    // whole waves of resident CTAs (two per SM by the launch bounds); a CTA keeps its power accumulator across its timelines
+    return std::max<size_t>(1, std::min<size_t>(nt, 2 * 148));
+}
+size_t self_loaded_work_bytes(const SelfPlan *p, size_t nt) {
+    const size_t G = loaded_groups(nt);
+    return align256(G * p->L * sizeof(double)) + align256(nt * sizeof(double2)) + align256(nt * sizeof(double2)) +
+           align256(p->L * sizeof(double2));
+}
+int self_power_accumulate_loaded(const SelfPlan *p, const double2 *d_A, size_t ldA, size_t nt, void *d_work, double *d_P,
+                                 double *d_acc, cudaStream_t st) {
+    if (nt == 0) return 0;
+    if (p->R != 1) return -1;
+    const size_t G = loaded_groups(nt);
+    char *w = reinterpret_cast<char *>(d_work);
+    double *Ppart = reinterpret_cast<double *>(w);
+    w += align256(G * p->L * sizeof(double));
+    double2 *a_part = reinterpret_cast<double2 *>(w);
+    w += align256(nt * sizeof(double2));
+    double2 *a_tl = reinterpret_cast<double2 *>(w);
+    launch_fused<GEN_LOAD>(p->log2N, dim3(1, (unsigned)G), st, nullptr, nullptr, nullptr, (int)p->NF, 1, 0, nt, 1, p->d_tw, p->d_w,
+                           Ppart, a_part, nullptr, d_A, ldA);
+    sf_reduce_ppart_kernel<<<(unsigned)((p->L + 255) / 256), 256, 0, st>>>(Ppart, G, p->L, d_P);
+    const double norm = 1.0 / ((double)p->NF * (double)p->L);
+    sf_reduce_apart_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a_part, nt, 1, norm, a_tl);
+    sf_reduce_atl_kernel<<<1, 1024, 0, st>>>(a_tl, nt, d_acc);
     return 4;
 }
 

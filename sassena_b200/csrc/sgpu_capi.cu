@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels/kernels.hpp"
+#include "nccl_api.hpp"
 
 using namespace sass;
 
@@ -46,6 +47,15 @@ struct sgpu_ctx {
     std::vector<Chunk> chunks;  // pending async staging chunks (frames mode)
     float *d_stage_tmp = nullptr;
     size_t stage_tmp_cap = 0;
+    // double-buffered wave streaming (sgpu_stage_atoms_prefetch / _swap)
+    float *d_wave[2] = {nullptr, nullptr};
+    size_t wave_cap = 0;           // floats per wave buffer
+    int wave_front = 0;            // buffer compute calls read (when wave_staged)
+    bool wave_staged = false;      // d_xyz points at d_wave[wave_front]
+    bool wave_pending = false;     // a prefetch is queued into the back buffer
+    size_t wave_pending_count = 0, wave_pending_NF = 0;
+    cudaEvent_t wave_ready[2] = {nullptr, nullptr};  // copy stream: H2D into the buffer done
+    cudaEvent_t wave_free[2] = {nullptr, nullptr};   // compute stream: every reader of the buffer queued so far is done
 
     double *d_b = nullptr;
     size_t nb = 0, b_cap = 0;
@@ -78,6 +88,16 @@ struct sgpu_ctx {
     char *h_up = nullptr;     // pinned + mapped staging area for small uploads (factors, q-vectors, moments)
     size_t up_cap = 0;
 
+    // NCCL communicator of the partition (sgpu_comm_init): exchange of the frame-sharded coherent path, all-reduces
+    ncclComm_t comm = nullptr;
+    bool comm_owned = true;
+    int comm_size = 1, comm_rank = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_pass = nullptr, comm_done = nullptr;
+    double2 *d_xloc = nullptr, *d_xrecv = nullptr, *d_xtl = nullptr;  // local amplitudes, received pieces, assembled timelines
+    size_t xloc_cap = 0, xrecv_cap = 0, xtl_cap = 0;
+    float comm_last_ms = 0.f;
+
     CorrPlan plan;
     SelfPlan splan;  // fused self path (atoms mode, dsp=autocorrelate)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -92,7 +112,21 @@ struct sgpu_ctx {
         if (copy_stream) cudaStreamSynchronize(copy_stream);
         for (auto &c : chunks) cudaEventDestroy(c.ready);
         if (own_xyz && d_xyz) cudaFree(d_xyz);
+        if (comm && comm_owned) {
+            if (const NcclApi *api = nccl_api(nullptr)) api->CommDestroy(comm);
+        }
+        if (comm_stream) cudaStreamDestroy(comm_stream);
+        if (comm_pass) cudaEventDestroy(comm_pass);
+        if (comm_done) cudaEventDestroy(comm_done);
+        if (d_xloc) cudaFree(d_xloc);
+        if (d_xrecv) cudaFree(d_xrecv);
+        if (d_xtl) cudaFree(d_xtl);
         if (d_stage_tmp) cudaFree(d_stage_tmp);
+        for (int i = 0; i < 2; i++) {
+            if (d_wave[i]) cudaFree(d_wave[i]);
+            if (wave_ready[i]) cudaEventDestroy(wave_ready[i]);
+            if (wave_free[i]) cudaEventDestroy(wave_free[i]);
+        }
         if (d_b) cudaFree(d_b);
         if (d_qs) cudaFree(d_qs);
         if (d_lm) cudaFree(d_lm);
@@ -194,6 +228,7 @@ int release_xyz(sgpu_ctx *ctx) {
         ctx->d_xyz = nullptr;
         ctx->xyz_cap = 0;
     }
+    ctx->wave_staged = false;
     ctx->mode = 0;
     ctx->rmax_valid = false;
     ctx->atoms_dec_R = 0;
@@ -204,7 +239,7 @@ int release_xyz(sgpu_ctx *ctx) {
 // (R == 0).  Out of place through a bounce buffer, a batch of atoms at a time.  Adopted (caller-owned) buffers stay natural.
 int set_atoms_layout(sgpu_ctx *ctx, int R) {
     if (ctx->mode != 2 || ctx->atoms_dec_R == R) return SGPU_OK;
-    if (!ctx->own_xyz) return SGPU_OK;
+    if (!ctx->own_xyz && !ctx->wave_staged) return SGPU_OK;
     const size_t row = ctx->NF * 3 * sizeof(float);
     const size_t batch = std::max<size_t>(1, std::min(ctx->NA, ((size_t)256 << 20) / row));
     int rc = ensure<float>(ctx, &ctx->d_stage_tmp, &ctx->stage_tmp_cap, batch * ctx->NF * 3);
@@ -650,6 +685,94 @@ int sgpu_stage_atoms_wave(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA,
     return stage_atoms_strided(ctx, xyz, NF, NA, atom_first, atom_stride, count);
 }
 
+int sgpu_stage_atoms_prefetch(sgpu_ctx *ctx, const float *xyz, size_t count, size_t NF) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!xyz || NF < 1 || count < 1) return fail(ctx, SGPU_EINVAL, "sgpu_stage_atoms_prefetch: No frames / atoms available");
+    if (ctx->wave_pending) return fail(ctx, SGPU_ESTATE, "sgpu_stage_atoms_prefetch: a prefetched wave is waiting for sgpu_stage_atoms_swap");
+    CK(cudaSetDevice(ctx->device));
+    const size_t need = count * NF * 3;
+    if (need > ctx->wave_cap) {
+        // grow both buffers: nothing may be in flight on either
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->wave_staged) {
+            ctx->wave_staged = false;
+            ctx->d_xyz = nullptr;
+            ctx->mode = 0;
+        }
+        for (int i = 0; i < 2; i++) {
+            if (ctx->d_wave[i]) CK(cudaFree(ctx->d_wave[i]));
+            ctx->d_wave[i] = nullptr;
+        }
+        ctx->wave_cap = 0;
+        for (int i = 0; i < 2; i++) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_wave[i]), need * sizeof(float)));
+        ctx->wave_cap = need;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (!ctx->wave_ready[i]) CK(cudaEventCreateWithFlags(&ctx->wave_ready[i], cudaEventDisableTiming));
+        if (!ctx->wave_free[i]) CK(cudaEventCreateWithFlags(&ctx->wave_free[i], cudaEventDisableTiming));
+    }
+    const int back = ctx->wave_staged ? (ctx->wave_front ^ 1) : ctx->wave_front;
+    // readers of the back buffer (the wave before the staged one) were all queued before the swap that retired it
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->wave_free[back], 0));
+    CK(cudaMemcpyAsync(ctx->d_wave[back], xyz, need * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->wave_ready[back], ctx->copy_stream));
+    ctx->wave_pending = true;
+    ctx->wave_pending_count = count;
+    ctx->wave_pending_NF = NF;
+    return SGPU_OK;
+}
+
+int sgpu_stage_atoms_swap(sgpu_ctx *ctx) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!ctx->wave_pending) return fail(ctx, SGPU_ESTATE, "sgpu_stage_atoms_swap: no prefetched wave (sgpu_stage_atoms_prefetch first)");
+    CK(cudaSetDevice(ctx->device));
+    const int back = ctx->wave_staged ? (ctx->wave_front ^ 1) : ctx->wave_front;
+    if (ctx->wave_staged) {
+        // everything queued so far on the compute stream may read the front buffer: it is free once that has run
+        CK(cudaEventRecord(ctx->wave_free[ctx->wave_front], ctx->stream));
+    } else {
+        // leaving another staging mode: queued work may still read the old coordinates (no host sync needed for the swap
+        // itself, but release_xyz drops chunk events and the frames-mode state)
+        int rc = release_xyz(ctx);
+        if (rc) return rc;
+        if (ctx->own_xyz && ctx->d_xyz) {
+            CK(cudaFree(ctx->d_xyz));
+            ctx->d_xyz = nullptr;
+            ctx->xyz_cap = 0;
+        }
+        ctx->own_xyz = false;
+    }
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->wave_ready[back], 0));
+    ctx->wave_front = back;
+    ctx->wave_staged = true;
+    ctx->wave_pending = false;
+    ctx->d_xyz = ctx->d_wave[back];
+    ctx->own_xyz = false;
+    ctx->xyz_cap = 0;
+    ctx->mode = 2;
+    ctx->NF = ctx->wave_pending_NF;
+    ctx->NFt = ctx->NF;
+    ctx->f_first = 0;
+    ctx->NA = ctx->wave_pending_count;
+    ctx->repr = SGPU_REPR_CARTESIAN;
+    ctx->atoms_dec_R = 0;  // a fresh wave arrives in natural frame order
+    ctx->rmax_valid = false;
+    ctx->nb = 0;           // factors belong to the previous wave's atoms
+    return SGPU_OK;
+}
+
+int sgpu_device_bytes(sgpu_ctx *ctx, size_t *bytes) {
+    if (!ctx || !bytes) return SGPU_EINVAL;
+    size_t n = 0;
+    if (ctx->own_xyz) n += ctx->xyz_cap;
+    n += ctx->stage_tmp_cap * sizeof(float) + 2 * ctx->wave_cap * sizeof(float);
+    n += ctx->b_cap * sizeof(double) + ctx->q_cap * sizeof(double) + ctx->bq_cap * sizeof(double);
+    n += ctx->A_cap * sizeof(double2) + ctx->work_cap + ctx->partial_cap * sizeof(double) + ctx->out_cap * sizeof(double2);
+    *bytes = n;
+    return SGPU_OK;
+}
+
 int sgpu_accumulate(sgpu_ctx *ctx, double *d_dst, const double *d_src, size_t n) {
     if (!ctx) return SGPU_EINVAL;
     if (!d_dst || !d_src) return fail(ctx, SGPU_EINVAL, "sgpu_accumulate: NULL buffer");
@@ -909,7 +1032,13 @@ int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, bool unifo
 }
 
 // amplitudes of NQ |q| values s[n] along fixed directions into A[NQ][NM][NFt] (this rank's frame columns)
-int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t NM, const double *s, size_t NQ, double2 *A) {
+extern "C++" {
+// compact: A is this rank's block only, [NQ][NM][NF] (row stride = the staged frames), for the exchange of the sharded path;
+// otherwise A is [NQ][NM][NFt] with the columns outside the frame window zeroed.  after_pass(n0, nq) runs after the launches
+// of every pass have been queued (the sharded path starts that pass's exchange there).
+template <class AfterPass>
+int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t NM, const double *s, size_t NQ, double2 *A,
+                         bool compact, AfterPass after_pass) {
     if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, std::string(who) + ": frames are not staged (stage_frames first)");
     if (ctx->repr != SGPU_REPR_CARTESIAN) return fail(ctx, SGPU_ESTATE, std::string(who) + ": staged frames are not cartesian");
     if (!v || !s || NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
@@ -919,8 +1048,10 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
         return fail(ctx, SGPU_ESTATE, std::string(who) + ": scattering factors not set for the staged atoms");
     const bool uniform = !batch || ctx->bq_uniform;
     const double *d_b = batch ? ctx->d_bq : ctx->d_b;
-    const size_t NFt = ctx->NFt, strideQ = NM * NFt;
-    if (ctx->NFt != ctx->NF) CK(cudaMemsetAsync(A, 0, NQ * strideQ * sizeof(double2), ctx->stream));
+    // the kernels index coordinates and amplitudes by the same (timeline) frame number: compact output shifts the base
+    const size_t NFt = compact ? ctx->NF : ctx->NFt, strideQ = NM * NFt;
+    if (compact) A -= ctx->f_first;
+    else if (ctx->NFt != ctx->NF) CK(cudaMemsetAsync(A, 0, NQ * strideQ * sizeof(double2), ctx->stream));
     const float *xyz = ctx->d_xyz - ctx->f_first * ctx->NA * 3;  // see sgpu_all_vectors_amplitudes
     int rc;
     std::vector<ScanPass> plan;
@@ -959,6 +1090,8 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
                 ctx->launches += launch_amplitude_all(xyz, d_b + (uniform ? 0 : ps.n0 * ctx->NA), ctx->d_qs, A + ps.n0 * strideQ,
                                                       NFt, ctx->NA, NM, ctx->f_first + c.f0, c.nf, ctx->stream);
             }
+            rc = after_pass(ps.n0, (size_t)ps.nq);
+            if (rc) return rc;
             continue;
         }
         if (!dirs_uploaded) {
@@ -976,8 +1109,130 @@ int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t
             if (l < 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": internal error, scan pass too long");
             ctx->launches += l;
         }
+        rc = after_pass(ps.n0, (size_t)ps.nq);
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
+    return SGPU_OK;
+}
+
+}  // extern "C++"
+
+int scan_amplitudes_into(sgpu_ctx *ctx, const char *who, const double *v, size_t NM, const double *s, size_t NQ, double2 *A) {
+    return scan_amplitudes_into(ctx, who, v, NM, s, NQ, A, false, [](size_t, size_t) { return 0; });
+}
+
+// DivAssignment (reference src/decomposition/assignment.cpp:27-35)
+void div_block(size_t NN, size_t rank, size_t N, size_t *off, size_t *cnt) {
+    *off = (rank * N) / NN;
+    *cnt = ((rank + 1) * N) / NN - *off;
+}
+
+#define NCK(call)                                                                                              \
+    do {                                                                                                       \
+        ncclResult_t r__ = (call);                                                                             \
+        if (r__ != ncclSuccess) return fail(ctx, SGPU_ECUDA, std::string(#call) + ": " + api->GetErrorString(r__)); \
+    } while (0)
+
+// pieces received from rank s, [s][n][m_local][f of s] -> timelines T[n][m_local][NFt]: the reference's alignpad
+// (all_vectors_scatter_device.cpp:186-207) after its all_to_all (:169-184); rows beyond NF need no padding here because the
+// column FFT treats them as zeros
+__global__ void assemble_timelines_kernel(const double2 *__restrict__ R, double2 *__restrict__ T, size_t NQ, size_t mc, size_t NFt,
+                                          int NN) {
+    // grid: (frames / 256, NQ * mc); every thread moves one (n, m, f) entry
+    const size_t f = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (f >= NFt) return;
+    const size_t row = blockIdx.y;  // n * mc + m
+    const size_t n = row / mc, m = row - n * mc;
+    // rank owning frame f: blocks are contiguous, off_s = s NFt / NN
+    int s = (int)(((f + 1) * (size_t)NN - 1) / NFt);
+    while ((size_t)s * NFt / NN > f) s--;
+    while (((size_t)(s + 1) * NFt) / NN <= f) s++;
+    const size_t off = (size_t)s * NFt / NN, cnt = ((size_t)(s + 1) * NFt) / NN - off;
+    T[row * NFt + f] = R[NQ * mc * off + (n * mc + m) * cnt + (f - off)];
+}
+
+// exchange of the |q| planes [n0, n0 + nq) of the local amplitudes A_loc[NQ][NM][nf] on the communication stream: to rank s
+// go the rows of ITS timeline block, from rank s come this rank's rows of ITS frame block (grouped ncclSend / ncclRecv = the
+// all_to_all of all_vectors_scatter_device.cpp:181).  The own block is a device copy.
+int exchange_planes(sgpu_ctx *ctx, const NcclApi *api, size_t NQ, size_t NM, size_t n0, size_t nq) {
+    const size_t NN = (size_t)ctx->comm_size, me = (size_t)ctx->comm_rank, nf = ctx->NF, NFt = ctx->NFt;
+    size_t m_off, mc;
+    div_block(NN, me, NM, &m_off, &mc);
+    CK(cudaEventRecord(ctx->comm_pass, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_pass, 0));
+    NCK(api->GroupStart());
+    for (size_t s = 0; s < NN; s++) {
+        size_t ms_off, ms_cnt, fs_off, fs_cnt;
+        div_block(NN, s, NM, &ms_off, &ms_cnt);
+        div_block(NN, s, NFt, &fs_off, &fs_cnt);
+        for (size_t n = n0; n < n0 + nq; n++) {
+            const double2 *src = ctx->d_xloc + (n * NM + ms_off) * nf;           // rows of rank s's timelines, my frames
+            double2 *dst = ctx->d_xrecv + NQ * mc * fs_off + n * mc * fs_cnt;    // my rows, rank s's frames
+            if (s == me) {
+                if (mc > 0 && nf > 0) CK(cudaMemcpyAsync(dst, src, mc * nf * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->comm_stream));
+                continue;
+            }
+            if (ms_cnt > 0 && nf > 0) NCK(api->Send(src, 2 * ms_cnt * nf, ncclFloat64, (int)s, ctx->comm, ctx->comm_stream));
+            if (mc > 0 && fs_cnt > 0) NCK(api->Recv(dst, 2 * mc * fs_cnt, ncclFloat64, (int)s, ctx->comm, ctx->comm_stream));
+        }
+    }
+    NCK(api->GroupEnd());
+    return SGPU_OK;
+}
+
+// after the amplitudes of all NQ planes have been exchanged: assemble this rank's timelines, correlate them, sum the packed
+// partials over the ranks (the three boost::mpi::reduce calls of all_vectors_scatter_device.cpp:335-343 as one all-reduce)
+int sharded_dsp_and_reduce(sgpu_ctx *ctx, const NcclApi *api, size_t NQ, size_t NM, int dsp_type, double *d_partials) {
+    const size_t NN = (size_t)ctx->comm_size, me = (size_t)ctx->comm_rank, NFt = ctx->NFt;
+    size_t m_off, mc;
+    div_block(NN, me, NM, &m_off, &mc);
+    const size_t plen = partial_len(ctx, dsp_type);
+    CK(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0));
+    CK(cudaMemsetAsync(d_partials, 0, NQ * plen * sizeof(double), ctx->stream));
+    if (mc > 0) {
+        dim3 grid((unsigned)((NFt + 255) / 256), (unsigned)(NQ * mc));
+        assemble_timelines_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_xrecv, ctx->d_xtl, NQ, mc, NFt, (int)NN);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        for (size_t n = 0; n < NQ; n++) {
+            int rc = dsp_accumulate(ctx, mc, dsp_type, d_partials + n * plen, ctx->d_xtl + n * mc * NFt);
+            if (rc) return rc;
+        }
+    }
+    NCK(api->AllReduce(d_partials, d_partials, NQ * plen, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    return SGPU_OK;
+}
+
+int sharded_prologue(sgpu_ctx *ctx, const char *who, const NcclApi **api_out, size_t NQ, size_t NM, int dsp_type, double *d_partials) {
+    std::string err;
+    const NcclApi *api = nccl_api(&err);
+    if (!api) return fail(ctx, SGPU_ESTATE, std::string(who) + ": " + err);
+    if (!ctx->comm) return fail(ctx, SGPU_ESTATE, std::string(who) + ": no communicator (sgpu_comm_init first)");
+    if (ctx->mode != 1) return fail(ctx, SGPU_ESTATE, std::string(who) + ": frames are not staged (stage_frames first)");
+    if (!d_partials) return fail(ctx, SGPU_EINVAL, std::string(who) + ": d_partials is NULL");
+    if (NM == 0 || NQ == 0) return fail(ctx, SGPU_EINVAL, std::string(who) + ": No qvectors left to compute");
+    size_t f_off, f_cnt;
+    div_block((size_t)ctx->comm_size, (size_t)ctx->comm_rank, ctx->NFt, &f_off, &f_cnt);
+    if (f_off != ctx->f_first || f_cnt != ctx->NF)
+        return fail(ctx, SGPU_ESTATE, std::string(who) + ": the staged frames are not this rank's DivAssignment block of the "
+                                                         "timeline (sgpu_set_frame_window)");
+    int rc = check_dsp(ctx, dsp_type, SGPU_METHOD_FFTW);
+    if (rc) return rc;
+    rc = ensure_plan(ctx);
+    if (rc) return rc;
+    size_t m_off, mc;
+    div_block((size_t)ctx->comm_size, (size_t)ctx->comm_rank, NM, &m_off, &mc);
+    rc = ensure<double2>(ctx, &ctx->d_xloc, &ctx->xloc_cap, NQ * NM * ctx->NF);
+    if (rc) return rc;
+    rc = ensure<double2>(ctx, &ctx->d_xrecv, &ctx->xrecv_cap, NQ * mc * ctx->NFt);
+    if (rc) return rc;
+    rc = ensure<double2>(ctx, &ctx->d_xtl, &ctx->xtl_cap, NQ * mc * ctx->NFt);
+    if (rc) return rc;
+    rc = ensure_work(ctx, dsp_work_bytes(ctx, std::max<size_t>(mc, 1), dsp_type));
+    if (rc) return rc;
+    *api_out = api;
     return SGPU_OK;
 }
 }  // namespace
@@ -990,6 +1245,145 @@ int sgpu_all_vectors_scan_amplitudes(sgpu_ctx *ctx, const double *v, size_t NM, 
     int rc = scan_amplitudes_into(ctx, "sgpu_all_vectors_scan_amplitudes", v, NM, s, NQ, reinterpret_cast<double2 *>(d_amp));
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
+    ctx->A_NM = 0;
+    return SGPU_OK;
+}
+
+/* ---- NCCL inside the library: the partition's communicator ----------------------------------------------------- */
+int sgpu_comm_get_unique_id(char *id128) {
+    sgpu_ctx *ctx = nullptr;
+    if (!id128) return fail(nullptr, SGPU_EINVAL, "sgpu_comm_get_unique_id: NULL");
+    std::string err;
+    const NcclApi *api = nccl_api(&err);
+    if (!api) return fail(nullptr, SGPU_ESTATE, err);
+    ncclUniqueId id;
+    NCK(api->GetUniqueId(&id));
+    memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return SGPU_OK;
+}
+
+int sgpu_comm_init(sgpu_ctx *ctx, const char *id128, int nranks, int rank) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, SGPU_EINVAL, "sgpu_comm_init: bad arguments");
+    std::string err;
+    const NcclApi *api = nccl_api(&err);
+    if (!api) return fail(ctx, SGPU_ESTATE, "sgpu_comm_init: " + err);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm) {
+        int rc = sgpu_comm_destroy(ctx);
+        if (rc) return rc;
+    }
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    NCK(api->CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->comm_owned = true;
+    ctx->comm_size = nranks;
+    ctx->comm_rank = rank;
+    if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    if (!ctx->comm_pass) CK(cudaEventCreateWithFlags(&ctx->comm_pass, cudaEventDisableTiming));
+    if (!ctx->comm_done) CK(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+    return SGPU_OK;
+}
+
+int sgpu_comm_adopt(sgpu_ctx *ctx, void *nccl_comm, int nranks, int rank) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!nccl_comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, SGPU_EINVAL, "sgpu_comm_adopt: bad arguments");
+    std::string err;
+    const NcclApi *api = nccl_api(&err);
+    if (!api) return fail(ctx, SGPU_ESTATE, "sgpu_comm_adopt: " + err);
+    CK(cudaSetDevice(ctx->device));
+    int rc = sgpu_comm_destroy(ctx);
+    if (rc) return rc;
+    ctx->comm = static_cast<ncclComm_t>(nccl_comm);
+    ctx->comm_owned = false;
+    ctx->comm_size = nranks;
+    ctx->comm_rank = rank;
+    if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    if (!ctx->comm_pass) CK(cudaEventCreateWithFlags(&ctx->comm_pass, cudaEventDisableTiming));
+    if (!ctx->comm_done) CK(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+    return SGPU_OK;
+}
+
+int sgpu_comm_destroy(sgpu_ctx *ctx) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!ctx->comm) return SGPU_OK;
+    const NcclApi *api = nccl_api(nullptr);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
+    if (api && ctx->comm_owned) NCK(api->CommDestroy(ctx->comm));
+    ctx->comm_owned = true;
+    ctx->comm = nullptr;
+    ctx->comm_size = 1;
+    ctx->comm_rank = 0;
+    return SGPU_OK;
+}
+
+int sgpu_comm_info(sgpu_ctx *ctx, int *nranks, int *rank) {
+    if (!ctx) return SGPU_EINVAL;
+    if (nranks) *nranks = ctx->comm ? ctx->comm_size : 1;
+    if (rank) *rank = ctx->comm ? ctx->comm_rank : 0;
+    return SGPU_OK;
+}
+
+int sgpu_comm_allreduce(sgpu_ctx *ctx, double *d_buf, size_t n) {
+    if (!ctx) return SGPU_EINVAL;
+    if (!d_buf) return fail(ctx, SGPU_EINVAL, "sgpu_comm_allreduce: NULL buffer");
+    if (!ctx->comm) return fail(ctx, SGPU_ESTATE, "sgpu_comm_allreduce: no communicator (sgpu_comm_init first)");
+    const NcclApi *api = nccl_api(nullptr);
+    CK(cudaSetDevice(ctx->device));
+    if (n) NCK(api->AllReduce(d_buf, d_buf, n, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    return SGPU_OK;
+}
+
+int sgpu_compute_all_vectors_scan_sharded(sgpu_ctx *ctx, const double *v, size_t NM, const double *s, size_t NQ, int dsp_type,
+                                          double *d_partials) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const NcclApi *api = nullptr;
+    int rc = sharded_prologue(ctx, "sgpu_compute_all_vectors_scan_sharded", &api, NQ, NM, dsp_type, d_partials);
+    if (rc) return rc;
+    if (!v || !s) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors_scan_sharded: NULL argument");
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // every pass's planes leave for their owners while the next pass is evaluated
+    rc = scan_amplitudes_into(ctx, "sgpu_compute_all_vectors_scan_sharded", v, NM, s, NQ, ctx->d_xloc, true,
+                              [&](size_t n0, size_t nq) { return exchange_planes(ctx, api, NQ, NM, n0, nq); });
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = sharded_dsp_and_reduce(ctx, api, NQ, NM, dsp_type, d_partials);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    ctx->have_times = true;
+    ctx->dsp_split = false;
+    ctx->A_NM = 0;
+    return SGPU_OK;
+}
+
+int sgpu_compute_all_vectors_sharded(sgpu_ctx *ctx, const double *qvecs, size_t NM, int dsp_type, double *d_partial) {
+    if (!ctx) return SGPU_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const NcclApi *api = nullptr;
+    int rc = sharded_prologue(ctx, "sgpu_compute_all_vectors_sharded", &api, 1, NM, dsp_type, d_partial);
+    if (rc) return rc;
+    if (!qvecs) return fail(ctx, SGPU_EINVAL, "sgpu_compute_all_vectors_sharded: qvecs is NULL");
+    if (ctx->repr != SGPU_REPR_CARTESIAN) return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors_sharded: staged frames are not cartesian");
+    if (ctx->nb != ctx->NA) return fail(ctx, SGPU_ESTATE, "sgpu_compute_all_vectors_sharded: scattering factors not set for the staged atoms");
+    rc = upload_q(ctx, qvecs, NM, (size_t)amplitude_all_qpad());
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const float *xyz = ctx->d_xyz - ctx->f_first * ctx->NA * 3;
+    double2 *A = ctx->d_xloc - ctx->f_first;
+    for (auto &c : ctx->chunks) CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+    ctx->launches += launch_amplitude_all(xyz, ctx->d_b, ctx->d_qs, A, ctx->NF, ctx->NA, NM, ctx->f_first, ctx->NF, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = exchange_planes(ctx, api, 1, NM, 0, 1);
+    if (rc) return rc;
+    rc = sharded_dsp_and_reduce(ctx, api, 1, NM, dsp_type, d_partial);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
     ctx->have_times = true;
     ctx->dsp_split = false;

@@ -316,6 +316,44 @@ class TorchDistCommunicator:
         TorchDistCommunicator._registry.pop(int(user), None)
 
 
+class NcclCommunicator:
+    """the library's own communicator on NCCL (csrc/host/nccl_comm.cpp): all callbacks are native code, torch.distributed (or
+    anything else) is only used to hand the 128-byte unique id from rank 0 to the others.  With it the frame-sharded
+    coherent device exchanges amplitudes inside the library (ncclSend/ncclRecv on the device streams)."""
+
+    def __init__(self, unique_id: bytes, nranks: int, rank: int, device: int):
+        assert len(unique_id) == 128
+        self.vtbl = _host.CommVtbl()
+        if _lib().sass_comm_nccl_create(unique_id, nranks, rank, device, C.byref(self.vtbl)) != 0:
+            raise RuntimeError("sass_comm_nccl_create failed (libnccl.so.2 not loadable, or ncclCommInitRank failed)")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        if _lib().sass_comm_nccl_unique_id(buf) != 0:
+            raise RuntimeError("sass_comm_nccl_unique_id failed")
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        """bootstrap over an initialised torch.distributed job: rank 0's id is broadcast, then ncclCommInitRank"""
+        import torch.distributed as dist
+        box = [cls.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(box[0], dist.get_world_size(), dist.get_rank(), device)
+
+    def close(self):
+        if getattr(self, "vtbl", None) is not None and self.vtbl.user:
+            self.vtbl.release(self.vtbl.user)
+            self.vtbl.user = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # run
 # ---------------------------------------------------------------------------------------------------------------

@@ -55,10 +55,13 @@ def main():
         p.set("scattering.average.orientation.axis.x", 1).set("scattering.average.orientation.axis.z", 1)
         p.set("scattering.average.orientation.multipole.moments.type", "resolution")
         p.set("scattering.average.orientation.multipole.moments.resolution", 2)
-    if case.endswith("_stream"):  # 12 frames x 12 B = 144 B per atom: waves of 5 atoms (config 5's streamed stager)
-        p.set("limits.stage.memory.data", 5 * 144)
+    if case.endswith("_stream"):  # 12 frames x 12 B = 144 B per atom: two wave buffers of 5 atoms (config 5's streamed stager)
+        p.set("limits.stage.memory.data", 10 * 144)
     if "_frames" in case:  # the reference's frame decomposition inside the partition (amplitude exchange)
         p.set("limits.decomposition.coherent", "frames")
+    if case.endswith("_manual2"):  # partitions of two ranks: with three ranks one is left spare (scatter_device_factory.cpp:104-116)
+        p.set("limits.decomposition.partitions.automatic", False).set("limits.decomposition.partitions.size", 2)
+        p.set("limits.decomposition.utilization", 0.0)
     if case.endswith("_manual1"):  # partitions of one rank each: every rank owns a |q| subset, no all-reduce
         p.set("limits.decomposition.partitions.automatic", False).set("limits.decomposition.partitions.size", 1)
         p.set("limits.decomposition.utilization", 0.0)

@@ -39,7 +39,9 @@ class OracleBackend:
             compute_all_vectors_scan_partial=_host.BE_AV_SCAN(self._av_scan),
             all_vectors_scan_amplitudes=_host.BE_AV_SCAN_AMPL(self._av_scan_amplitudes),
             stage_atoms_wave=_host.BE_STAGE_WAVE(self._stage_wave), accumulate=_host.BE_ACCUMULATE(self._accumulate),
-            frames_to_cylindrical=_host.BE_TO_CYL(self._to_cyl), mpcylinder_amplitudes=_host.BE_CYL_AMPL(self._cyl_amplitudes))
+            frames_to_cylindrical=_host.BE_TO_CYL(self._to_cyl), mpcylinder_amplitudes=_host.BE_CYL_AMPL(self._cyl_amplitudes),
+            stage_atoms_prefetch=_host.BE_PREFETCH(self._prefetch), stage_atoms_swap=_host.BE_SWAP(self._swap),
+            host_alloc=_host.BE_ALLOC(self._alloc), host_free=_host.BE_FREE(self._free))
         self._cbs = cbs
         self.vtbl = _host.BackendVtbl(**cbs)
 
@@ -165,6 +167,25 @@ class OracleBackend:
         ids = first + stride * np.arange(count)
         self.waves_staged = getattr(self, "waves_staged", 0) + 1
         self._ctx(c).update(mode=2, xyz=np.ascontiguousarray(a[:, ids].transpose(1, 0, 2)), NF=NF, NA=count)
+        return 0
+
+    def _prefetch(self, c, xyz, count, NF):
+        ctx = self._ctx(c)
+        if ctx.get("pending") is not None:
+            self.err = b"a prefetched wave is waiting for the swap"
+            return 5
+        ctx["pending"] = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(count, NF, 3)).copy()
+        return 0
+
+    def _swap(self, c):
+        ctx = self._ctx(c)
+        a = ctx.get("pending")
+        if a is None:
+            self.err = b"no prefetched wave"
+            return 5
+        ctx["pending"] = None
+        self.waves_staged = getattr(self, "waves_staged", 0) + 1
+        ctx.update(mode=2, xyz=a, NF=a.shape[1], NA=a.shape[0])
         return 0
 
     def _accumulate(self, c, dst, src, n):

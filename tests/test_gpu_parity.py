@@ -742,7 +742,7 @@ def test_self_streamed_waves_match_resident(oracle, dsp):
     ps = host.Params().set("scattering.type", "self").set("scattering.average.orientation.type", "vectors")
     ps.set("scattering.average.orientation.vectors.resolution", 7).set("scattering.dsp.type", dsp).create()
     resident, _, _ = host.run_scatter(ps, xyz, qv, factors_fn=lambda ql: b * (1.0 + 0.2 * ql))
-    ps.set("limits.stage.memory.data", 16 * NF * 12)  # 16 atoms per wave -> 4 waves (16, 16, 16, 13)
+    ps.set("limits.stage.memory.data", 32 * NF * 12)  # two wave buffers of 16 atoms -> 4 waves (16, 16, 16, 13)
     streamed, _, tm = host.run_scatter(ps, xyz, qv, factors_fn=lambda ql: b * (1.0 + 0.2 * ql))
     assert tm["sd:compute"][1] == 4 and len(streamed) == 3
     for r, s, q in zip(resident, streamed, qv):

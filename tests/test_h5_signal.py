@@ -175,3 +175,39 @@ def test_job_writes_signal_h5_and_resumes(tmp_path, oracle):
     s5 = host.load_signal_h5(sig)
     assert s5["qvectors"].shape == (5, 3) and np.array_equal(s5["fqt"][:3], s["fqt"])
     assert sorted(np.round(s5["qvectors"][:, 0], 6)) == [0.5, 0.75, 1.0, 1.25, 1.5]
+
+
+def test_interrupted_run_is_recovered_from_the_row_journal(tmp_path, oracle):
+    """Rows are journaled as the device delivers them (the reference's writer appends as partitions deliver,
+    file_writer_service.cpp:314-484).  A run that died after two q-vectors leaves <signal>.h5.d/rows.journal behind and no
+    usable signal file; the next run takes those rows over and computes only the rest (sassena.cpp:270-305)."""
+    from oracle_backend import OracleBackend
+    from test_control_plane import ORIENT, make_case
+    be = OracleBackend()
+    scan = "<vectors><type>scans</type><scans><scan><from>0.5</from><to>1.5</to><points>5</points><base><x>1</x><y>0</y><z>0</z></base></scan></scans></vectors>"
+    cfg, xyz, names = make_case(tmp_path, scattering=scan + ORIENT)
+    sig = tmp_path / "signal.h5"
+    written, _ = host.Job(cfg).run(sig, backend=be.vtbl)
+    assert written == 5 and not os.path.exists(str(sig) + ".d/rows.journal")  # a finished run leaves no journal
+    full = host.load_signal_h5(sig)
+    NF = full["fqt"].shape[1]
+    # the interrupted run: no signal file, a journal with rows 1 and 3 and a torn third record
+    os.remove(sig)
+    rec = []
+    for i in (1, 3):
+        rec += list(full["qvectors"][i]) + [full["fq"][i].real, full["fq"][i].imag, full["fq2"][i].real, full["fq2"][i].imag]
+        rec += list(full["fqt"][i].view(np.float64))
+    blob = np.array([20260117.5, float(NF)] + rec + [1.0, 2.0, 3.0], dtype="<f8").tobytes()
+    os.makedirs(str(sig) + ".d", exist_ok=True)
+    with open(str(sig) + ".d/rows.journal", "wb") as f:
+        f.write(blob)
+    written, _ = host.Job(cfg).run(sig, backend=be.vtbl)
+    assert written == 3
+    got = host.load_signal_h5(sig)
+    assert got["qvectors"].shape == (5, 3)
+    assert np.array_equal(got["qvectors"][:2], full["qvectors"][[1, 3]]) and np.array_equal(got["fqt"][:2], full["fqt"][[1, 3]])
+    order = [int(np.argmin(np.abs(full["qvectors"][:, 0] - q[0]))) for q in got["qvectors"]]
+    assert sorted(order) == [0, 1, 2, 3, 4]
+    for row, i in enumerate(order):
+        assert np.allclose(got["fqt"][row], full["fqt"][i], rtol=1e-13, atol=0) and np.isclose(got["fq2"][row], full["fq2"][i])
+    assert not os.path.exists(str(sig) + ".d/rows.journal")

@@ -207,7 +207,7 @@ def test_run_scatter_single_rank_oracle_backend(oracle):
     p2s.set("scattering.average.orientation.vectors.type", "file").set_vectors(synth.unit_vectors(4, 5)).create()
     resident, _, _ = host.run_scatter(p2s, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
     be.waves_staged = 0
-    p2s.set("limits.stage.memory.data", 7 * NF * 12)  # 7 of the 30 atoms per wave -> 5 waves
+    p2s.set("limits.stage.memory.data", 14 * NF * 12)  # two wave buffers of 7 of the 30 atoms -> 5 waves
     streamed, _, tms = host.run_scatter(p2s, xyz, qv, factors_fn=lambda ql: b * (1 + ql), backend=be.vtbl)
     assert be.waves_staged == 5 and tms["sd:compute"][1] == 5 and len(streamed) == len(qv)
     for r, s, q in zip(resident, streamed, qv):

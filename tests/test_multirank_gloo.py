@@ -93,6 +93,25 @@ def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
         assert abs(r["fq2"] - rfq2) < 1e-11 * abs(rfq2)
 
 
+@pytest.mark.parametrize("case", ["all_manual2", "self_manual2"])
+def test_spare_rank_does_not_hang_the_partition_split(oracle, tmp_path, case):
+    """three ranks, manual partitions of two: the plan uses ranks 0-1 and leaves rank 2 spare (the reference allows this,
+    scatter_device_factory.cpp:104-116).  The spare rank returns without a device and the others must not wait for it in the
+    second communicator split."""
+    gathered = _run(3, case, tmp_path)
+    qv, ref = _reference(oracle, case)
+    assert sorted(has for _, has, _, _ in gathered) == [False, True, True]
+    records = {}
+    for rank, has, recs, _ in gathered:
+        assert has or not recs
+        for r in recs:
+            records[tuple(np.round(r["q"], 12))] = r
+    assert len(records) == len(qv)
+    for q, (rfqt, rfq, rfq2) in zip(qv, ref):
+        r = records[tuple(np.round(q, 12))]
+        assert np.max(np.abs(r["fqt"] - rfqt)) < 1e-11 * abs(rfqt[0]) and abs(r["fq"] - rfq) < 1e-11 * abs(rfqt[0])
+
+
 @pytest.mark.parametrize("manual", [False, True])
 def test_multirank_job_from_config(oracle, tmp_path, manual):
     """scatter.xml -> Job.run on 2 ranks: one partition of 2 (rank 0 writes all |q|) and, with manual partitions of

@@ -1,5 +1,7 @@
-"""Multi-GPU parity check, run under torchrun (one process per GPU, NCCL): the C++ host layer's factory + devices
-with a torch.distributed communicator against the CPU oracle.  Usage:
+"""Multi-GPU parity check, run under torchrun (one process per GPU, NCCL): the C++ host layer's factory + devices against the
+CPU oracle, once with the library's own NCCL communicator (native callbacks; the frame-sharded coherent device then exchanges
+amplitudes inside the library) and once with a torch.distributed communicator (Python callbacks; amplitude all-reduce), plus
+the C-ABI's sharded scan called directly.  Usage:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/multigpu_check.py
 """
 import os
@@ -52,19 +54,57 @@ def main():
     pp.set("limits.decomposition.partitions.automatic", False).set("limits.decomposition.partitions.size", 1)
     pp.set("limits.decomposition.utilization", 0.0)
     cases.append(("all, 1-GPU partitions", pp, lambda q, p=pp: o.compute_all_vectors(xyz, b, p.init_subvectors(q), nthreads=4)))
-    for name, prm, ref_fn in cases:
-        recs, has, tm = host.run_scatter(prm, xyz, qv, b=b, comm=comm)
-        allrecs = [None] * world
-        dist.all_gather_object(allrecs, recs)
-        if rank == 0:
-            flat = [r for rr in allrecs for r in rr]
-            assert len(flat) == len(qv), (name, len(flat))
-            err = 0.0
-            for r in flat:
-                ref = ref_fn(r["q"])
-                err = max(err, float(np.max(np.abs(r["fqt"] - ref[0])) / np.max(np.abs(ref[0]))))
-            worst = max(worst, err)
-            print(f"[{world} GPUs] {name:24s} writers={sum(1 for rr in allrecs if rr)} max rel err vs oracle = {err:.2e}")
+    native = host.NcclCommunicator.from_torch_distributed(local)
+    for cname, cm in (("native NCCL comm", native), ("torch.distributed comm", comm)):
+        for name, prm, ref_fn in cases:
+            recs, has, tm = host.run_scatter(prm, xyz, qv, b=b, comm=cm)
+            allrecs = [None] * world
+            dist.all_gather_object(allrecs, recs)
+            if rank == 0:
+                flat = [r for rr in allrecs for r in rr]
+                assert len(flat) == len(qv), (name, len(flat))
+                err = 0.0
+                for r in flat:
+                    ref = ref_fn(r["q"])
+                    err = max(err, float(np.max(np.abs(r["fqt"] - ref[0])) / np.max(np.abs(ref[0]))))
+                worst = max(worst, err)
+                print(f"[{world} GPUs, {cname}] {name:24s} writers={sum(1 for rr in allrecs if rr)} max rel err vs oracle = {err:.2e}")
+    native.close()
+
+    # the C-ABI directly: frame-sharded scan with the exchange inside the library (float-rounded |q|: corrected kernel)
+    import sassena_b200
+    NA2, NF2, NM2 = 3000, 203, 61  # frame and subvector counts that do not divide evenly
+    xyz2 = synth.trajectory(NF2, NA2, 60.0, 0.1, 7)
+    b2 = synth.factors(NA2)
+    u2 = synth.unit_vectors(NM2, 3)
+    qls = synth.qlengths(0.1, 3.0, 19)
+    ctx = sassena_b200.ScatterContext(local)
+    box = [sassena_b200.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], world, rank)
+    f_off, f_cnt = (rank * NF2) // world, ((rank + 1) * NF2) // world - (rank * NF2) // world
+    ctx.stage_frames(np.ascontiguousarray(xyz2[f_off:f_off + f_cnt]))
+    ctx.set_frame_window(NF2, f_off)
+    ctx.set_factors(b2)
+    plen = ctx.partial_len("autocorrelate")
+    part = torch.zeros(len(qls) * plen, dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        ctx.compute_all_vectors_scan_sharded(u2, qls, part.data_ptr())
+    ctx.synchronize()
+    got = [ctx.finalize(part.data_ptr() + n * plen * 8, 1.0 / NM2) for n in range(len(qls))]
+    ctx.compute_all_vectors_sharded(qls[3] * u2, part.data_ptr())
+    one = ctx.finalize(part.data_ptr(), 1.0 / NM2)
+    if rank == 0:
+        err = 0.0
+        for n in (0, 3, len(qls) - 1):
+            ref = o.compute_all_vectors(xyz2, b2, qls[n] * u2, nthreads=8)
+            err = max(err, float(np.max(np.abs(got[n][0] - ref[0])) / np.max(np.abs(ref[0]))),
+                      float(abs(got[n][1] - ref[1]) / abs(ref[0][0])))
+            if n == 3:
+                err = max(err, float(np.max(np.abs(one[0] - ref[0])) / np.max(np.abs(ref[0]))))
+        worst = max(worst, err)
+        print(f"[{world} GPUs] C-ABI sharded scan / single |q| (plan {ctx.last_scan_plan()}) max rel err vs oracle = {err:.2e}")
+    ctx.close()
     if rank == 0:
         assert worst < 1e-9, worst
         print("multigpu_check OK")
