@@ -103,6 +103,9 @@ int sgpu_stage_atoms_wave(sgpu_ctx *ctx, const float *xyz, size_t NF, size_t NA,
  * seen); xyz of a prefetched block must stay valid until the matching swap's first compute call has returned. */
 int sgpu_stage_atoms_prefetch(sgpu_ctx *ctx, const float *xyz, size_t count, size_t NF);
 int sgpu_stage_atoms_swap(sgpu_ctx *ctx);
+/* What is staged: frames NF and atoms NA of the staged block, NF_total = frames of the timelines the DSP works on (the
+ * frame window's total if one is set, else NF).  Output buffers of compute / finalize hold NF_total complex entries. */
+int sgpu_staged_shape(const sgpu_ctx *ctx, size_t *NF, size_t *NA, size_t *NF_total);
 /* Bytes of device memory currently held by the context's buffers (coordinates, wave buffers, amplitudes, work areas):
  * the per-GPU HBM high-water mark of a streamed run. */
 int sgpu_device_bytes(sgpu_ctx *ctx, size_t *bytes);

@@ -542,6 +542,29 @@ def ref_scatter_run(kind, frames, b, qvectors, orient=None, vectors_type="file",
     return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
 
 
+def ref_scatter_run_ranks(kind, nranks, frames, b, qvectors, orient=None, vectors_type="file", axis=(0, 0, 1), dsp="autocorrelate",
+                          method="fftw", threads=1):
+    """the REFERENCE's own scatter device on `nranks` ranks of one partition (threads over the shared-memory communicator shim):
+    its frame decomposition with all_to_all + alignpad ("all"), its atom decomposition with the staged transposition of
+    DataStagerByAtom ("self") and the reductions to partition rank 0 run as written.  Returns like ref_scatter_run."""
+    fr = _f32(frames)
+    NF, NA, _ = fr.shape
+    bb = _f64(b)
+    qv = _f64(qvectors).reshape(-1, 3)
+    NQ = len(qv)
+    ori = np.zeros((0, 3)) if orient is None else _f64(orient).reshape(-1, 3)
+    ax = _f64(np.asarray(axis, dtype=np.float64))
+    fqt, fq, fq2, qout = np.zeros((NQ, NF, 2)), np.zeros((NQ, 2)), np.zeros((NQ, 2)), np.zeros((NQ, 3))
+    f = ref_lib().ref_scatter_run_ranks
+    f.restype = C.c_size_t
+    n = f(C.c_int(0 if kind == "all" else 1), C.c_int(nranks), _p(fr, C.c_float), C.c_size_t(NF), C.c_size_t(NA), _p(bb, C.c_double),
+          _p(qv, C.c_double), C.c_size_t(NQ), vectors_type.encode(), _p(ori, C.c_double), C.c_size_t(len(ori)), _p(ax, C.c_double),
+          dsp.encode(), method.encode(), C.c_size_t(threads), _p(fqt, C.c_double), _p(fq, C.c_double), _p(fq2, C.c_double),
+          _p(qout, C.c_double))
+    assert n == NQ, n
+    return qout, fqt[..., 0] + 1j * fqt[..., 1], fq[:, 0] + 1j * fq[:, 1], fq2[:, 0] + 1j * fq2[:, 1]
+
+
 def ref_multipole_run(kind, frames, b, qvectors, moments, axis=(0, 0, 1), dsp="autocorrelate", method="fftw", threads=1):
     """the REFERENCE's own MPSphereScatterDevice ("sphere") / MPCylinderScatterDevice ("cylinder") for one rank (oracle/_ref build
     over the shims; Boost.Math's sph_bessel / spherical_harmonic / cyl_bessel_j served by the oracle's restatements).  frames

@@ -103,6 +103,71 @@ size_t ref_scatter_run(int kind, const float *frames, size_t NF, size_t NA, cons
     return out.count;
 }
 
+// The same devices on `nranks` ranks of ONE partition, every rank a thread over the shared-memory communicator of
+// shim/boost/mpi.hpp: the reference's own multi-rank code runs -- DivAssignment of the frames + all_to_all + alignpad for the
+// coherent device (all_vectors_scatter_device.cpp:169-207,291-315), ModAssignment of the atoms + the staged transposition of
+// DataStagerByAtom for the self device (data_stager.cpp:249-338), the reductions to partition rank 0 (:335-343).  Partition
+// rank 0 writes.  Arguments and outputs as ref_scatter_run; `threads` worker threads per rank.
+size_t ref_scatter_run_ranks(int kind, int nranks, const float *frames, size_t NF, size_t NA, const double *b, const double *qvectors,
+                             size_t NQ, const char *vectors_type, const double *orient, size_t NM, const double axis[3],
+                             const char *dsp_type, const char *dsp_method, size_t threads, double *fqt, double *fq, double *fq2,
+                             double *qout) {
+    Params *p = Params::Inst();
+    p->scattering.dsp.type = dsp_type;
+    p->scattering.dsp.method = dsp_method;
+    p->scattering.average.orientation.vectors.clear();
+    p->scattering.average.orientation.vectors.type = vectors_type;
+    for (size_t i = 0; i < NM; i++)
+        p->scattering.average.orientation.vectors.push_back(CartesianCoor3D(orient[3 * i], orient[3 * i + 1], orient[3 * i + 2]));
+    p->scattering.average.orientation.axis = CartesianCoor3D(axis[0], axis[1], axis[2]);
+    p->limits.computation.threads = threads;
+    p->stager.target = "system";
+    p->stager.dump = false;
+    {
+        std::lock_guard<std::mutex> l(ShimTimerTable::Inst().m);
+        ShimTimerTable::Inst().sum.clear();
+    }
+    Factors fac = {b};
+    ShimFactorSource::Inst().cb = on_factors;
+    ShimFactorSource::Inst().user = &fac;
+    Out out = {fqt, fq, fq2, qout, NF, 0};
+    ShimWriterSink::Inst().cb = on_write;
+    ShimWriterSink::Inst().user = &out;
+    std::vector<CartesianCoor3D> vectors;
+    for (size_t i = 0; i < NQ; i++) vectors.push_back(CartesianCoor3D(qvectors[3 * i], qvectors[3 * i + 1], qvectors[3 * i + 2]));
+
+    std::shared_ptr<boost::mpi::shim_detail::World> world = std::make_shared<boost::mpi::shim_detail::World>(nranks);
+    std::vector<std::thread> ranks;
+    std::vector<int> failed((size_t)nranks, 0);
+    for (int r = 0; r < nranks; r++) {
+        ranks.emplace_back([&, r]() {
+            try {
+                Sample sample;
+                ShimRangeSelection system(NA);
+                sample.atoms.selections["system"] = &system;
+                sample.coordinate_sets.shim_set(frames, NF, NA, Params::Inst()->scattering.average.orientation.axis);
+                boost::mpi::communicator allcomm(world, r), partitioncomm(world, r);
+                boost::asio::ip::tcp::endpoint ep;
+                if (kind == 0) {
+                    AllDev dev(allcomm, partitioncomm, sample, vectors, NF, ep, ep);
+                    dev.run();
+                } else {
+                    SelfDev dev(allcomm, partitioncomm, sample, vectors, NA, ep, ep);
+                    dev.run();
+                }
+            } catch (...) {
+                failed[(size_t)r] = 1;
+            }
+        });
+    }
+    for (auto &t : ranks) t.join();
+    ShimWriterSink::Inst().cb = nullptr;
+    ShimFactorSource::Inst().cb = nullptr;
+    for (int f : failed)
+        if (f) return (size_t)-1;
+    return out.count;
+}
+
 // The reference's multipole devices (src/scatter_devices/multipole_scatter_device.cpp; Boost.Math's three special functions
 // served by the oracle's restatements, see shim/boost/math/special_functions.hpp).  kind: 2 = MPSphereScatterDevice,
 // 3 = MPCylinderScatterDevice.  frames: float [NF][NA][3] cartesian (the device asks the sample for its own representation),

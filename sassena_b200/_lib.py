@@ -51,6 +51,7 @@ SIGNATURES = {
     "sgpu_compute_all_vectors_sharded": (C.c_int, [C.c_void_p, c_double_p, C.c_size_t, C.c_int, C.c_void_p]),
     "sgpu_stage_atoms_prefetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     "sgpu_stage_atoms_swap": (C.c_int, [C.c_void_p]),
+    "sgpu_staged_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "sgpu_device_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "sgpu_stage_atoms_wave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
     "sgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

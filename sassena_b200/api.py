@@ -171,10 +171,13 @@ class ScatterContext:
         a = xyz_block
         assert a.dtype == np.float32 and a.ndim == 3 and a.shape[2] == 3 and a.flags["C_CONTIGUOUS"]
         self._ck(self.lib.sgpu_stage_atoms_prefetch(self.h, a.ctypes.data, a.shape[0], a.shape[1]))
+        self._pending_wave = (a.shape[0], a.shape[1])
 
     def stage_atoms_swap(self):
         """make the prefetched block the staged atoms (no host synchronisation)"""
         self._ck(self.lib.sgpu_stage_atoms_swap(self.h))
+        self.NA, self.NF = self._pending_wave  # the output buffers of finalize / compute are sized from these
+        self._NFt = 0
 
     def device_bytes(self) -> int:
         n = C.c_size_t(0)
@@ -195,7 +198,10 @@ class ScatterContext:
     @property
     def timeline_frames(self):
         """frames of the timelines the DSP works on: the window's NF_total if one is set, else the staged NF"""
-        return self._NFt if self._NFt else self.NF
+        # asked of the library, not tracked here: an output buffer sized from a stale shape would be overrun by finalize
+        nf, na, nft = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self._ck(self.lib.sgpu_staged_shape(self.h, C.byref(nf), C.byref(na), C.byref(nft)))
+        return int(nft.value) if nft.value else (self._NFt if self._NFt else self.NF)
 
     @staticmethod
     def _pack(at, af, a2f):

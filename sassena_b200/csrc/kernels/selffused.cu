@@ -932,13 +932,27 @@ __global__ void sf_gather_weights_kernel(const double2 *__restrict__ w, const in
     if (i < len) w2[i] = w[perm[i]];
 }
 
-// P[i] += sum_g Ppart[g][i]
-__global__ void sf_reduce_ppart_kernel(const double *__restrict__ Ppart, size_t G, size_t len, double *__restrict__ P) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= len) return;
-    double sum = 0.0;
-    for (size_t g = 0; g < G; g++) sum += Ppart[g * len + i];
-    P[i] += sum;
+// P[i] += sum_g Ppart[g][i].  Block (64, 4): thread (x, y) sums the partials g = y, y + 4, ... of entry i = 64 blockIdx.x + x
+// with four loads in flight, the four strands are combined in a fixed order (bit-reproducible, no atomics).  (One thread
+// per entry walking all G partials was 43 us for G = 296, L = 2048: 8 CTAs of dependent loads.)
+__global__ void __launch_bounds__(256) sf_reduce_ppart_kernel(const double *__restrict__ Ppart, size_t G, size_t len,
+                                                              double *__restrict__ P) {
+    __shared__ double sh[4][64];
+    const size_t i = blockIdx.x * (size_t)64 + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (i < len) {
+        size_t g = threadIdx.y;
+        for (; g + 12 < G; g += 16) {
+            s0 += Ppart[g * len + i];
+            s1 += Ppart[(g + 4) * len + i];
+            s2 += Ppart[(g + 8) * len + i];
+            s3 += Ppart[(g + 12) * len + i];
+        }
+        for (; g < G; g += 4) s0 += Ppart[g * len + i];
+    }
+    sh[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.y == 0 && i < len) P[i] += (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
 }
 
 // a_tl[tl] = norm * sum_j a_part[tl][j]
@@ -1335,7 +1349,7 @@ int self_power_accumulate(const SelfPlan *p, const float *d_xyz_by_atom, const d
     double2 *a_tl = reinterpret_cast<double2 *>(w);
     launch_fused<GEN_AMPLITUDE>(p->log2N, dim3(p->R, (unsigned)G), st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0,
                                 ntl, p->R, p->d_tw, p->d_w, Ppart, a_part, nullptr);
-    sf_reduce_ppart_kernel<<<(unsigned)((p->L + 255) / 256), 256, 0, st>>>(Ppart, G, p->L, d_P);
+    sf_reduce_ppart_kernel<<<(unsigned)((p->L + 63) / 64), dim3(64, 4), 0, st>>>(Ppart, G, p->L, d_P);
     const double norm = 1.0 / ((double)p->NF * (double)p->L);
     sf_reduce_apart_kernel<<<(unsigned)((ntl + 255) / 256), 256, 0, st>>>(a_part, ntl, p->R, norm, a_tl);
     sf_reduce_atl_kernel<<<1, 1024, 0, st>>>(a_tl, ntl, d_acc);
@@ -1366,7 +1380,7 @@ int self_power_accumulate_loaded(const SelfPlan *p, const double2 *d_A, size_t l
     double2 *a_tl = reinterpret_cast<double2 *>(w);
     launch_fused<GEN_LOAD>(p->log2N, dim3(1, (unsigned)G), st, nullptr, nullptr, nullptr, (int)p->NF, 1, 0, nt, 1, p->d_tw, p->d_w,
                            Ppart, a_part, nullptr, d_A, ldA);
-    sf_reduce_ppart_kernel<<<(unsigned)((p->L + 255) / 256), 256, 0, st>>>(Ppart, G, p->L, d_P);
+    sf_reduce_ppart_kernel<<<(unsigned)((p->L + 63) / 64), dim3(64, 4), 0, st>>>(Ppart, G, p->L, d_P);
     const double norm = 1.0 / ((double)p->NF * (double)p->L);
     sf_reduce_apart_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a_part, nt, 1, norm, a_tl);
     sf_reduce_atl_kernel<<<1, 1024, 0, st>>>(a_tl, nt, d_acc);

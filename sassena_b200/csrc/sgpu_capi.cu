@@ -762,6 +762,14 @@ int sgpu_stage_atoms_swap(sgpu_ctx *ctx) {
     return SGPU_OK;
 }
 
+int sgpu_staged_shape(const sgpu_ctx *ctx, size_t *NF, size_t *NA, size_t *NF_total) {
+    if (!ctx) return SGPU_EINVAL;
+    if (NF) *NF = ctx->mode ? ctx->NF : 0;
+    if (NA) *NA = ctx->mode ? ctx->NA : 0;
+    if (NF_total) *NF_total = ctx->mode ? ctx->NFt : 0;
+    return SGPU_OK;
+}
+
 int sgpu_device_bytes(sgpu_ctx *ctx, size_t *bytes) {
     if (!ctx || !bytes) return SGPU_EINVAL;
     size_t n = 0;

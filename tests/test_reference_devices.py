@@ -169,3 +169,74 @@ def test_cuda_path_matches_reference_devices(oracle):
                 assert e < TOL, (kind, vt, dsp, method, i, e)
                 assert abs(fq - rfq) < TOL * scale and abs(fq2 - rfq2) <= TOL * max(abs(rfq2), 1e-300), (kind, vt, dsp, method, i)
     print("worst fqt rel. err vs the reference's own devices:", worst)
+
+
+@pytest.mark.parametrize("kind,nranks", [("all", 2), ("all", 3), ("self", 2), ("self", 3)])
+def test_reference_multirank_branches_live(oracle, kind, nranks):
+    """The reference's own NNPP > 1 code as the oracle: its devices on 2 and 3 ranks of one partition (threads over the
+    shared-memory communicator of oracle/shim/boost/mpi.hpp) -- DivAssignment of the frames + all_to_all + alignpad
+    (all_vectors_scatter_device.cpp:169-207,291-315), ModAssignment of the atoms + DataStagerByAtom's staged transposition
+    (data_stager.cpp:249-338), the reductions to partition rank 0 -- give what its one-rank run and the oracle give (the sums
+    over ranks come in another order, hence 1e-13 instead of bit for bit)."""
+    if not oracle.have_ref_smath():
+        pytest.skip("oracle/_ref/libsmath_ref.so not built (no /root/reference on this machine)")
+    NF, NA = 23, 37  # neither divides by 2 or 3: ragged frame / atom blocks
+    xyz = synth.trajectory(NF, NA, 20.0, 0.2, 3, offset=-10.0)
+    b = synth.factors(NA)
+    u = synth.unit_vectors(7, 1)
+    qv = np.array([[0.7, 0.0, 0.0], [1.3, 0.2, 0.0]])
+    for dsp, method in (("autocorrelate", "fftw"), ("autocorrelate", "direct"), ("square", "fftw")):
+        one = oracle.ref_scatter_run(kind, xyz, b, qv, orient=u, dsp=dsp, method=method, threads=2)
+        many = oracle.ref_scatter_run_ranks(kind, nranks, xyz, b, qv, orient=u, dsp=dsp, method=method, threads=2)
+        assert np.array_equal(many[0], one[0])
+        for i, q in enumerate(qv):
+            sub = np.linalg.norm(q) * u
+            if kind == "all":
+                ofqt, ofq, ofq2 = oracle.compute_all_vectors(xyz, b, sub, dsp=dsp, method=method)
+            else:
+                ofqt, ofq, ofq2 = oracle.compute_self_vectors(np.ascontiguousarray(xyz.transpose(1, 0, 2)), b, sub, dsp=dsp, method=method)
+            scale = np.max(np.abs(one[1][i]))
+            assert np.max(np.abs(many[1][i] - one[1][i])) < 1e-13 * scale
+            assert np.max(np.abs(many[1][i] - ofqt)) < 1e-13 * scale
+            assert abs(many[2][i] - ofq) < 1e-13 * scale and abs(many[3][i] - ofq2) < 1e-13 * abs(ofq2)
+
+
+@pytest.mark.gpu
+def test_cuda_frame_sharded_path_matches_reference_multirank(oracle):
+    """the product's frame-sharded coherent path (frame windows + amplitude exchange + DSP of a timeline block, here the three
+    ranks' shares evaluated one after the other on one GPU and summed) against the REFERENCE's own three-rank run"""
+    if not oracle.have_ref_smath():
+        pytest.skip("oracle/_ref/libsmath_ref.so not built (no /root/reference on this machine)")
+    import torch
+    NF, NA, NM, NN = 47, 301, 13, 3
+    xyz = synth.trajectory(NF, NA, 30.0, 0.2, 11)
+    b = synth.factors(NA)
+    u = synth.unit_vectors(NM, 4)
+    qv = np.array([[0.9, 0.1, 0.0]])
+    ref = oracle.ref_scatter_run_ranks("all", NN, xyz, b, qv, orient=u, threads=2)
+    sub = np.linalg.norm(qv[0]) * u
+    with sassena_b200.ScatterContext(0) as ctx:
+        amp = torch.zeros(NM * NF * 2, dtype=torch.float64, device="cuda")
+        tmp = torch.zeros_like(amp)
+        for r in range(NN):  # every rank's frame block -> its columns of A (zero elsewhere); the sum assembles the timelines
+            f0, f1 = (r * NF) // NN, ((r + 1) * NF) // NN
+            ctx.stage_frames(np.ascontiguousarray(xyz[f0:f1]))
+            ctx.set_frame_window(NF, f0)
+            ctx.set_factors(b)
+            ctx.all_vectors_amplitudes(sub, tmp.data_ptr())
+            ctx.synchronize()
+            amp += tmp
+        torch.cuda.synchronize()
+        plen = ctx.partial_len("autocorrelate")
+        total = torch.zeros(plen, dtype=torch.float64, device="cuda")
+        part = torch.zeros(plen, dtype=torch.float64, device="cuda")
+        for r in range(NN):  # every rank's DivAssignment block of the timelines
+            m0, m1 = (r * NM) // NN, ((r + 1) * NM) // NN
+            ctx.all_vectors_dsp_partial(amp.data_ptr(), m0, m1 - m0, part.data_ptr())
+            ctx.synchronize()
+            total += part
+        torch.cuda.synchronize()
+        fqt, fq, fq2 = ctx.finalize(total.data_ptr(), 1.0 / NM)
+    scale = np.max(np.abs(ref[1][0]))
+    assert np.max(np.abs(fqt - ref[1][0])) < TOL * scale
+    assert abs(fq - ref[2][0]) < TOL * scale and abs(fq2 - ref[3][0]) < TOL * abs(ref[3][0])
