@@ -526,9 +526,18 @@ int sgpu_frames_to_spherical(sgpu_ctx *ctx) {
     if (ctx->repr != SGPU_REPR_CARTESIAN) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: staged frames are not cartesian");
     if (!ctx->own_xyz) return fail(ctx, SGPU_ESTATE, "sgpu_frames_to_spherical: adopted device buffers are read-only");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->copy_stream));
-    drop_chunks(ctx);
-    ctx->launches += launch_cart_to_spherical(ctx->d_xyz, ctx->NF * ctx->NA, ctx->stream);
+    if (ctx->chunks.empty()) {
+        ctx->launches += launch_cart_to_spherical(ctx->d_xyz, ctx->NF * ctx->NA, ctx->stream);
+    } else {
+        // staging chunks still in flight: convert every chunk as it lands (the compute stream waits per chunk, the host does
+        // not), and let the chunk's event from now on mean "converted", so that the multipole kernel can start on the first
+        // chunks while the last ones are still crossing PCIe
+        for (auto &c : ctx->chunks) {
+            CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+            ctx->launches += launch_cart_to_spherical(ctx->d_xyz + c.f0 * ctx->NA * 3, c.nf * ctx->NA, ctx->stream);
+            CK(cudaEventRecord(c.ready, ctx->stream));
+        }
+    }
     CK(cudaGetLastError());
     ctx->repr = SGPU_REPR_SPHERICAL;
     return SGPU_OK;
@@ -1605,17 +1614,33 @@ int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, cons
     if (rc) return rc;
     rc = small_upload(ctx, ctx->d_qlens, qlens, NQ * sizeof(double));
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->copy_stream));
-    drop_chunks(ctx);
     double2 *A = reinterpret_cast<double2 *>(d_amp);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (lmax <= 21) {
         rc = ensure_work(ctx, multipole_batch_work_doubles(ctx->NF, lmax, std::max<size_t>(atom_count, 1), (int)NQ) * sizeof(double));
         if (rc) return rc;
-        ctx->launches += launch_multipole_sphere_batch(ctx->d_xyz, d_b, b_stride, ctx->d_qlens, (int)NQ, ctx->d_lm, NM, lmax, A,
-                                                       ctx->NF, ctx->NA, atom_first, atom_first + atom_count, 0, ctx->NF,
-                                                       reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+        // one launch over all frames if every staging chunk has landed (and been converted), else one launch per chunk as
+        // the chunks arrive: staging overlaps the kernel (as the coherent amplitude kernels do)
+        bool all_ready = true;
+        for (auto &c : ctx->chunks)
+            if (cudaEventQuery(c.ready) != cudaSuccess) all_ready = false;
+        cudaGetLastError();
+        if (all_ready) {
+            drop_chunks(ctx);
+            ctx->launches += launch_multipole_sphere_batch(ctx->d_xyz, d_b, b_stride, ctx->d_qlens, (int)NQ, ctx->d_lm, NM, lmax, A,
+                                                           ctx->NF, ctx->NA, atom_first, atom_first + atom_count, 0, ctx->NF,
+                                                           reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+        } else {
+            for (auto &c : ctx->chunks) {
+                CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+                ctx->launches += launch_multipole_sphere_batch(ctx->d_xyz, d_b, b_stride, ctx->d_qlens, (int)NQ, ctx->d_lm, NM, lmax,
+                                                               A, ctx->NF, ctx->NA, atom_first, atom_first + atom_count, c.f0, c.nf,
+                                                               reinterpret_cast<double *>(ctx->d_work), ctx->stream);
+            }
+        }
     } else {
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        drop_chunks(ctx);
         // more (l,m) pairs than threads of the batched kernel: one pass per |q| with the shuffle-reduction kernel
         if (atom_first != 0 || atom_count != ctx->NA)
             return fail(ctx, SGPU_EINVAL, "sgpu_mpsphere_amplitudes: atom sharding needs moments with l <= 21");
