@@ -107,21 +107,22 @@ __device__ __forceinline__ constexpr int bitrev_r(int i, int log2r) {
     return r;
 }
 
-// cos/sin of 2 pi m / 16
-__device__ constexpr double kCos16[16] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
+// cos/sin of 2 pi m / 16.  In constant memory: the butterflies take them as c[bank][offset] operands; as constexpr
+// literals ptxas materialises them in registers outside the loops (spilled in the split kernel: 30 reloads per transform)
+__constant__ double kCos16[16] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
                                           0.0, -0.38268343236508977, -0.70710678118654752, -0.92387953251128674,
                                           -1.0, -0.92387953251128674, -0.70710678118654752, -0.38268343236508977,
                                           0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674};
-__device__ constexpr double kSin16[16] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674,
+__constant__ double kSin16[16] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674,
                                           1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
                                           0.0, -0.38268343236508977, -0.70710678118654752, -0.92387953251128674,
                                           -1.0, -0.92387953251128674, -0.70710678118654752, -0.38268343236508977};
 
 // R-point DIF network in registers; on exit x[i] holds frequency bitrev(i).  sign = -1 forward, +1 inverse.
-template <int R, int SIGN>
+template <int R, int SIGN, int LEN0 = R>
 __device__ __forceinline__ void fft_regs(double2 (&x)[R]) {
 #pragma unroll
-    for (int len = R; len >= 2; len >>= 1) {
+    for (int len = LEN0; len >= 2; len >>= 1) {
         const int half = len >> 1;
 #pragma unroll
         for (int blk = 0; blk < R; blk += len) {
@@ -151,11 +152,6 @@ struct GlobalTwiddles {  // exp(-2 pi i t / N) from an N-entry table in global m
     const double2 *__restrict__ tw;
     __device__ __forceinline__ double2 operator()(int t) const { return __ldg(&tw[t]); }
 };
-struct SharedTwiddles {  // the same value as hi[t >> 6] * lo[t & 63] from two small shared-memory tables
-    const double2 *lo, *hi;
-    __device__ __forceinline__ double2 operator()(int t) const { return cmul2(hi[t >> 6], lo[t & 63]); }
-};
-
 template <int LOG2N, int LOG2S, int R, int SIGN, class TW>
 __device__ __forceinline__ void fft_pass(double2 *s, const TW &tw) {
     constexpr int N = 1 << LOG2N, S = 1 << LOG2S, q = S / R, NB = N / R;
@@ -314,13 +310,6 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_fused_kernel(
 // (k2, pos) in shared memory over all its timelines and the store() mean as the weighted sum with What (split layout).
 // The result is permuted back to the residue-major layout at the reduction, so finalize is unchanged.
 
-// frequency held by output position `pos` of fft_r16 (radices 16, 16, N/256): the base-(16,16,N/256) digit reversal
-template <int LOG2N>
-__device__ __forceinline__ int freq16_of_pos(int pos) {
-    constexpr int N = 1 << LOG2N;
-    return (pos / (N / 16)) + 16 * ((pos / (N / 256)) % 16) + 256 * (pos % (N / 256));
-}
-
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
@@ -332,118 +321,252 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// dec != 0: the atom's frames are stored decimated, [r][m] with sub-sequence r (frames R m + r) contiguous
-// (sgpu keeps owned atom-major buffers in that layout while the split path is in use); otherwise natural order.
-// A CTA walks its (timeline, r) pairs; the coordinates of the next pair are fetched into shared memory with cp.async
-// while the current sub-transform runs, and all twiddles (inter-pass W_N^t and the split's W_L^t) come from small
-// shared-memory tables (hi * lo), so the only global accesses on the critical path are the Z stores.
-template <int LOG2N>
-__global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft_kernel(
+// ---- split path, kernel A ----------------------------------------------------------------------------------------------
+// N = 4096 = 16^3 (the split path only runs with R >= 2, i.e. 2NF-1 > 4096).  Index algebra: n = 256 n1 + 16 n2 + n3,
+// k = k1 + 16 k2 + 256 k3,
+//     X[k] = sum_n3 W_16^{n3 k3} W_256^{n3 k2} [ sum_n2 W_16^{n2 k2} W_N^{k1 (16 n2 + n3)} [ sum_n1 W_16^{n1 k1} x[n] ] ].
+//   pass 1  thread (n2, n3) = tid: the amplitudes x[256 n1 + tid], n1 < 8, are evaluated straight into registers (a
+//           decimated sub-sequence has at most N/2 frames: n1 >= 8 is the zero pad, so the first DIF stage of the 16-point
+//           network degenerates to 8 twiddle products), twiddled by W_N^{k1 tid} and written to shared memory;
+//   pass 2  thread (k1, n3): 16-point transform over n2 in place, twiddled by W_256^{n3 k2};
+//   pass 3  thread (k1, k2) = tid: 16-point transform over n3, times the split twiddle W_L^{r k} (and the atom's factor),
+//           stored straight to Z in NATURAL frequency order: Z[tid + 256 k3] is coalesced.
+// Shared-memory layout  (k1 ^ (n3 & 7)) + 16 n3 + 256 (n2 | k2): every access of the three passes is conflict free
+// without padding.  Pass 3 of one sub-transform and pass 1 of the next touch the same 512 elements per warp and every warp
+// fetches its own coordinates, so a sub-transform costs two CTA barriers (after pass 1 and after pass 2).  All twiddle powers w^k, k < 16, come from two interleaved
+// three-term recurrences w_{k+2} = 2 cos(2 theta) w_k - w_{k-2} (one FMA per component; error <= 1.2e-14, checked in
+// tools/check_twiddle_recurrence.py) seeded by thread constants, instead of table loads and complex products.
+__device__ __forceinline__ constexpr int bitrev4(int i) {
+    return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
+}
+
+// emit(k, x[bitrev4(k)] * z_k), k = 0..15, where z_k = z0 * g^k, |g| = 1, given z0, z1 = z0 * g and cg2 = 2 Re g.
+// UNIT0: z0 == 1.  Every product is handed to `emit` (a store) as soon as it exists, so the stores of a pass are spread
+// over the recurrence instead of queueing up behind it.
+template <bool UNIT0, class Emit>
+__device__ __forceinline__ void twiddle16(const double2 (&x)[16], double2 z0, double2 z1, double cg2, Emit &&emit) {
+    double2 pa = z0, pb = z1;
+    double2 wa = make_double2(fma(cg2, z1.x, -z0.x), fma(cg2, z1.y, -z0.y));  // z2
+    double2 wb = make_double2(fma(cg2, wa.x, -z1.x), fma(cg2, wa.y, -z1.y));  // z3
+    const double C2 = fma(cg2, cg2, -2.0);                                    // 2 cos(2 theta)
+    emit(0, UNIT0 ? x[0] : cmul2(x[0], z0));
+    emit(1, cmul2(x[bitrev4(1)], z1));
+    emit(2, cmul2(x[bitrev4(2)], wa));
+    emit(3, cmul2(x[bitrev4(3)], wb));
+#pragma unroll
+    for (int k = 4; k < 16; k += 2) {
+        const double2 na = make_double2(fma(C2, wa.x, -pa.x), fma(C2, wa.y, -pa.y));
+        pa = wa;
+        wa = na;
+        emit(k, cmul2(x[bitrev4(k)], wa));
+        const double2 nb = make_double2(fma(C2, wb.x, -pb.x), fma(C2, wb.y, -pb.y));
+        pb = wb;
+        wb = nb;
+        emit(k + 1, cmul2(x[bitrev4(k + 1)], wb));
+    }
+}
+
+// 16-point forward DIF network whose inputs 8..15 are zero: the first stage is x[m + 8] = x[m] W_16^m
+__device__ __forceinline__ void fft16_upper_zero(double2 (&x)[16]) {
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const double2 d = x[m];
+        if (m == 0) {
+            x[8] = d;
+        } else if (m == 4) {
+            x[12] = make_double2(d.y, -d.x);
+        } else {
+            const double wr = kCos16[m], wi = -kSin16[m];
+            x[m + 8] = make_double2(fma(d.x, wr, -d.y * wi), fma(d.x, wi, d.y * wr));
+        }
+    }
+    fft_regs<16, -1, 8>(x);
+}
+
+__global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft12_kernel(
     const float *__restrict__ xyz, const double *__restrict__ b, const double *__restrict__ qs, int NF, int NM, size_t atom0,
     size_t tl_first, size_t ntl, int R, int dec, double2 *__restrict__ Zt) {
     extern __shared__ double2 s[];
-    constexpr int N = 1 << LOG2N;
-    constexpr int NHI = (N >= 64) ? N / 64 : 1;
-    // exp(-2 pi i t / L) = Thi[t >> 8] * Tlo[t & 255];  exp(-2 pi i t / N) = TNhi[t >> 6] * TNlo[t & 63]
-    double2 *Tlo = s + N + N / 16;
+    constexpr int N = 4096;
+    // exp(-2 pi i t / L) = Thi[t >> 8] * Tlo[t & 255]
+    double2 *Tlo = s + N;
     double2 *Thi = Tlo + 256;
     const int L = R * N;
-    double2 *TNlo = Thi + (L >> 8);
-    double2 *TNhi = TNlo + 64;
-    float *cbuf = reinterpret_cast<float *>(TNhi + NHI);  // coordinates of one sub-sequence, [m][3]
-    for (int i = threadIdx.x; i < 256 + (L >> 8); i += SF_THREADS) {
+    double *qb = reinterpret_cast<double *>(Thi + (L >> 8));  // (q', b) of the current and the next timeline, 2 x 4 doubles
+    float *cbuf = reinterpret_cast<float *>(qb + 8);           // coordinates of one sub-sequence, [m][3]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256 + (L >> 8); i += SF_THREADS) {
         const int t = (i < 256) ? i : ((i - 256) << 8);
         double sn, cs;
         sincospi(-2.0 * (double)t / (double)L, &sn, &cs);
         Tlo[i] = make_double2(cs, sn);  // Thi follows Tlo
     }
-    for (int i = threadIdx.x; i < 64 + NHI; i += SF_THREADS) {
-        const int t = (i < 64) ? i : ((i - 64) << 6);
-        double sn, cs;
-        sincospi(-2.0 * (double)t / (double)N, &sn, &cs);
-        TNlo[i] = make_double2(cs, sn);  // TNhi follows TNlo
-    }
-    const SharedTwiddles twN{TNlo, TNhi};
+    // thread constants: W_N^{tid} (pass 1) and W_256^{tid >> 4} (pass 2)
+    double2 w1, w2;
+    sincospi(-2.0 * (double)tid / 4096.0, &w1.y, &w1.x);
+    sincospi(-2.0 * (double)(tid >> 4) / 256.0, &w2.y, &w2.x);
+    const int lo4 = tid & 15, hi4 = tid >> 4;
+    const int i1 = (16 * tid) | (tid & 7);            // pass 1 stores s[i1 ^ k1]
+    const int i2 = (lo4 ^ (hi4 & 7)) + 16 * hi4;      // pass 2: s[i2 + 256 n2], in place
+    const int i3 = 256 * hi4;                         // pass 3: s[i3 + 16 n3 + (k1 ^ (n3 & 7))]
+
     const int base = NF / R, rem = NF % R;
-    const size_t G = gridDim.x, g = blockIdx.x;
-    const size_t per = (ntl + G - 1) / G;
-    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
-    const size_t npairs = (t_end > t_begin) ? (t_end - t_begin) * (size_t)R : 0;
+    // the (timeline, r) sub-transforms of the launch are dealt out evenly, CTA g takes [g P / G, (g + 1) P / G): whole
+    // timelines per CTA cost up to 26 % at R = 25 (3.16 timelines per CTA means 4 for some)
+    const size_t P = ntl * (size_t)R;
+    const size_t p_begin = (size_t)(((unsigned __int128)blockIdx.x * P) / gridDim.x);
+    const size_t p_end = (size_t)(((unsigned __int128)(blockIdx.x + 1) * P) / gridDim.x);
+    if (p_begin >= p_end) return;
     // The sub-sequence lands at cbuf + mis, mis = its misalignment (in floats) against 16 bytes in global memory, so that
     // source and destination are congruent and the body moves as 16-byte cp.async; returns mis (0 for the gather).
-    auto prefetch = [&](size_t pair) -> int {
-        const size_t t = t_begin + pair / R;
-        const int r = (int)(pair % R);
-        const size_t atom = atom0 + (tl_first + t) / NM;
-        const float *p = xyz + atom * (size_t)NF * 3;
+    // Every WARP fetches exactly the frames it evaluates in pass 1 (rows 256 n1 + 32 warp .. + 32, i.e. the 16-byte chunks
+    // 192 n1 + 24 warp + lane, lane < 24, plus one more when the rows straddle chunk boundaries), so the arrival of the
+    // coordinates is a warp-local matter (cp.async.wait_group + __syncwarp) and needs no CTA barrier.
+    const int lane = tid & 31;
+    const int gl = 96 * (tid >> 5) + 4 * lane;
+    auto prefetch = [&](const float *p, int r) -> int {
         const int Mr = base + (r < rem ? 1 : 0);
         int mis = 0;
         if (dec) {
             const float *pr = p + 3 * (size_t)(r * base + min(r, rem));
             mis = (int)((reinterpret_cast<size_t>(pr) >> 2) & 3);
-            const int n = 3 * Mr;
-            const int head = min((4 - mis) & 3, n);
-            const int nvec = (n - head) >> 2;
-            float *cb = cbuf + mis;
-            for (int e = threadIdx.x; e < nvec; e += SF_THREADS) cp_async16(&cb[head + 4 * e], &pr[head + 4 * e]);
-            if ((int)threadIdx.x < head) cp_async4(&cb[threadIdx.x], &pr[threadIdx.x]);
-            const int et = head + 4 * nvec + (int)threadIdx.x;
-            if (et < n) cp_async4(&cb[et], &pr[et]);
+            const float *pa = pr - mis;      // 16-byte aligned: shifted index g is pa[g] in global memory and cbuf[g] here
+            const int g_end = mis + 3 * Mr;  // valid shifted indices: [mis, g_end)
+            if (lane < 24 + (mis != 0 ? 1 : 0)) {
+#pragma unroll
+                for (int n1 = 0; n1 < 8; n1++) {
+                    const int gi = gl + 768 * n1;
+                    if (gi >= mis && gi + 4 <= g_end) {
+                        cp_async16(&cbuf[gi], &pa[gi]);
+                    } else if (gi < g_end) {  // the first and the last chunk of the sub-sequence
+#pragma unroll 1
+                        for (int i = 0; i < 4; i++)
+                            if (gi + i >= mis && gi + i < g_end) cp_async4(&cbuf[gi + i], &pa[gi + i]);
+                    }
+                }
+            }
         } else {
-            for (int e = threadIdx.x; e < 3 * Mr; e += SF_THREADS) {
-                const int mm = e / 3, c = e - 3 * mm;
-                cp_async4(&cbuf[e], &p[3 * ((size_t)R * mm + r) + c]);
+#pragma unroll 1
+            for (int n1 = 0; n1 < 8; n1++) {
+                const int f = 256 * n1 + tid;
+                if (f < Mr) {
+                    const float *src = p + 3 * ((size_t)R * f + r);
+                    cp_async4(&cbuf[3 * f], src);
+                    cp_async4(&cbuf[3 * f + 1], src + 1);
+                    cp_async4(&cbuf[3 * f + 2], src + 2);
+                }
             }
         }
-        cp_async_commit_group();
         return mis;
     };
-    // output position pos = tid + 256 i holds frequency f0(tid) + i * 2^(12 - LOG2N) (freq16_of_pos), so the exponent of the
-    // split twiddle W_L^{r f} advances by a constant per i: one modulo per (thread, pair) instead of one per element
-    static_assert(SF_THREADS == 256 && LOG2N >= 8 && LOG2N <= 12, "incremental twiddle exponent assumes 256 threads, N = 256..4096");
-    const int f0 = freq16_of_pos<LOG2N>(threadIdx.x);
-    int mis_next = npairs ? prefetch(0) : 0;
-    for (size_t pair = 0; pair < npairs; pair++) {
-        const float *cb = cbuf + mis_next;
-        const size_t t = t_begin + pair / R;
-        const int r = (int)(pair % R);
-        const size_t tl = tl_first + t;
-        const int m = (int)(tl % NM);
-        const double qx = __ldg(&qs[3 * m]), qy = __ldg(&qs[3 * m + 1]), qz = __ldg(&qs[3 * m + 2]);
-        const double bn = __ldg(&b[atom0 + tl / NM]);
-        const int Mr = base + (r < rem ? 1 : 0);
-        cp_async_wait_all();
-        __syncthreads();  // coordinates of this pair are in cbuf; the previous sub-transform has been written out
-#pragma unroll 4
-        for (int mm = threadIdx.x; mm < N; mm += SF_THREADS) {
-            double2 v = make_double2(0.0, 0.0);
-            if (mm < Mr) {
-                const double x = (double)cb[3 * mm], y = (double)cb[3 * mm + 1], z = (double)cb[3 * mm + 2];
-                const double u = fma(z, qz, fma(y, qy, x * qx));
-                double sn, cs;
-                sincos_qt(u, sn, cs);
-                v = make_double2(bn * cs, bn * sn);
-            }
-            s[phys(mm)] = v;
+    // (q', b) of timeline (arel, m) into slot `slot` of qb: threads 0..3 (warp 0), 8 bytes each, in the current cp.async group
+    auto prefetch_qb = [&](size_t arel_, int m_, int slot) {
+        if (tid < 4) {
+            const double *src = (tid < 3) ? (qs + 3 * m_ + tid) : (b + atom0 + arel_);
+            const unsigned d = (unsigned)__cvta_generic_to_shared(qb + 4 * slot + tid);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
         }
-        __syncthreads();  // cbuf consumed
-        if (pair + 1 < npairs) mis_next = prefetch(pair + 1);  // lands while the transform below runs
-        fft_pass<LOG2N, LOG2N, 16, -1>(s, twN);
-        fft_pass<LOG2N, LOG2N - 4, 16, -1>(s, twN);
-        if (LOG2N == 9) fft_pass<LOG2N, 1, 2, -1>(s, twN);
-        if (LOG2N == 10) fft_pass<LOG2N, 2, 4, -1>(s, twN);
-        if (LOG2N == 11) fft_pass<LOG2N, 3, 8, -1>(s, twN);
-        if (LOG2N == 12) fft_pass<LOG2N, 4, 16, -1>(s, twN);
-        double2 *out = Zt + ((t * R + r) << LOG2N);
-        // ... so the twiddle itself advances by a constant factor: w_{i+1} = w_i * W_L^{dth} (N/256 <= 16 steps, ~1e-15)
-        const int th = (int)(((long long)r * f0) % L);
-        const int dth = (r << (12 - LOG2N)) % L;
-        double2 w = cmul2(Thi[th >> 8], Tlo[th & 255]);
-        const double2 wstep = cmul2(Thi[dth >> 8], Tlo[dth & 255]);
-#pragma unroll 4
-        for (int pos = threadIdx.x; pos < N; pos += SF_THREADS) {
-            out[pos] = cmul2(s[phys(pos)], w);
-            w = cmul2(w, wstep);
+    };
+    // (atom, q-vector) of the CTA's first timeline; advanced incrementally afterwards (no division inside the loop)
+    const size_t t_first = p_begin / (size_t)R;
+    int r = (int)(p_begin - t_first * (size_t)R);
+    size_t arel = (tl_first + t_first) / (size_t)NM;
+    int m = (int)((tl_first + t_first) - arel * (size_t)NM);
+    const float *p = xyz + (atom0 + arel) * (size_t)NF * 3;
+    prefetch_qb(arel, m, 0);
+    int mis_next = prefetch(p, r);
+    cp_async_commit_group();
+    cp_async_wait_all();
+    __syncthreads();  // tables and the first timeline's (q', b) are visible to every warp
+    double2 *out = Zt + (p_begin << 12);
+    int slot = 0;
+    double qx = 0.0, qy = 0.0, qz = 0.0, bn = 0.0;
+    for (size_t pair = p_begin; pair < p_end; pair++, out += N) {
+        if (pair == p_begin || r == 0) {  // the CTA's first pair of a timeline
+            if (pair != p_begin + 1) {    // staged: by the blocking fetch above, or two pairs ago (see below)
+                qx = qb[4 * slot], qy = qb[4 * slot + 1], qz = qb[4 * slot + 2], bn = qb[4 * slot + 3];
+            } else {  // the CTA's share began with the last sub-transform of the previous timeline: nothing was staged yet
+                qx = __ldg(&qs[3 * m]), qy = __ldg(&qs[3 * m + 1]), qz = __ldg(&qs[3 * m + 2]), bn = __ldg(&b[atom0 + arel]);
+            }
+        }
+        const float *cb = cbuf + mis_next;
+        const int Mr = base + (r < rem ? 1 : 0);
+        double2 x[16];
+        // the twiddle powers below are rebuilt per sub-transform on purpose (2 x 28 FMAs): hoisted out of the loop they
+        // are 60 live doubles per thread, i.e. spills whose reloads miss the L1 left over beside 2 x 94 KB of shared memory
+        asm volatile("" : "+d"(w1.x), "+d"(w1.y), "+d"(w2.x), "+d"(w2.y));
+        // this warp's coordinates are in cbuf (it fetched them itself), and pass 3 of the previous pair has read the
+        // part of the FFT buffer pass 1 is about to overwrite: both read and written by this warp only (elements
+        // [512 warp, 512 warp + 512)), so a warp-level synchronisation is all that is needed here
+        cp_async_wait_all();
+        __syncwarp();
+        // ---- pass 1: amplitudes of frames tid + 256 n1 in registers, pruned 16-point transform over n1.  Branch free
+        // (clamped index + select) so that the eight evaluations interleave; rows beyond the sub-sequence are skipped
+        // by CTA-uniform tests
+        const int rows = (Mr + 255) >> 8;
+        if (rows == 8) {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; n1++) {
+                const int mm = tid + 256 * n1, mc = min(mm, Mr - 1);
+                const double cx = (double)cb[3 * mc], cy = (double)cb[3 * mc + 1], cz = (double)cb[3 * mc + 2];
+                double2 v;
+                sincos_qt(fma(cz, qz, fma(cy, qy, cx * qx)), v.y, v.x);
+                x[n1] = (n1 < 7 || mm < Mr) ? v : make_double2(0.0, 0.0);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; n1++) {
+                const int mm = tid + 256 * n1;
+                double2 v = make_double2(0.0, 0.0);
+                if (n1 < rows) {
+                    const int mc = min(mm, Mr - 1);
+                    const double cx = (double)cb[3 * mc], cy = (double)cb[3 * mc + 1], cz = (double)cb[3 * mc + 2];
+                    sincos_qt(fma(cz, qz, fma(cy, qy, cx * qx)), v.y, v.x);
+                    if (mm >= Mr) v = make_double2(0.0, 0.0);
+                }
+                x[n1] = v;
+            }
+        }
+        fft16_upper_zero(x);
+        twiddle16<true>(x, make_double2(1.0, 0.0), w1, w1.x + w1.x, [&](int k1, double2 v) { s[i1 ^ k1] = v; });
+        __syncthreads();  // cbuf consumed by every warp, pass 1 complete
+        const int r_this = r;
+        if (pair + 1 < p_end) {  // the next pair's coordinates land while passes 2 and 3 run
+            if (++r == R) {      // ... it opens the next timeline
+                r = 0;
+                slot ^= 1;
+                if (++m == NM) {
+                    m = 0;
+                    arel++;
+                }
+                p = xyz + (atom0 + arel) * (size_t)NF * 3;
+            } else if (r + 1 == R && pair + 2 < p_end) {
+                // this timeline's last pair comes next and the CTA goes on to the timeline after it: that one's (q', b)
+                // join this cp.async group, are waited for by warp 0 at the top of the next pair and published to the
+                // other warps by that pair's barrier above
+                const bool wrap = (m + 1 == NM);
+                prefetch_qb(arel + (wrap ? 1 : 0), wrap ? 0 : m + 1, slot ^ 1);
+            }
+            mis_next = prefetch(p, r);
+        }
+        cp_async_commit_group();
+        // ---- pass 2: over n2, in place
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) x[n2] = s[i2 + 256 * n2];
+        fft_regs<16, -1>(x);
+        twiddle16<true>(x, make_double2(1.0, 0.0), w2, w2.x + w2.x, [&](int k2, double2 v) { s[i2 + 256 * k2] = v; });
+        __syncthreads();
+        // ---- pass 3: over n3; split twiddle b * W_L^{r (tid + 256 k3)} = h * g^k3, g = W_L^{256 r} = Thi[r]
+#pragma unroll
+        for (int n3 = 0; n3 < 16; n3++) x[n3] = s[i3 + 16 * n3 + (lo4 ^ (n3 & 7))];
+        fft_regs<16, -1>(x);
+        {
+            const int th = r_this * tid;  // < 64 * 256 <= L
+            double2 h = cmul2(Thi[th >> 8], Tlo[th & 255]);
+            h.x *= bn;
+            h.y *= bn;
+            const double2 gg = Thi[r_this];
+            twiddle16<false>(x, h, cmul2(h, gg), gg.x + gg.x, [&](int k3, double2 v) { out[tid + 256 * k3] = v; });
         }
     }
 }
@@ -1190,7 +1313,7 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
         for (size_t i = 0; i < p->N; i++) inv[f[i]] = (int)i;  // frequency -> position of the radix-16 order
         for (int k2 = 0; k2 < p->R; k2++)
             for (size_t pos = 0; pos < p->N; pos++) {
-                const size_t freq = (size_t)f[pos] + p->N * k2;  // X[k1 + N k2]
+                const size_t freq = pos + p->N * k2;  // X[k1 + N k2]: kernel A stores Z in natural frequency order
                 const size_t j = freq % p->R, k = freq / p->R;   // = X[R k + j] of the residue-major layout
                 perm[(size_t)k2 * p->N + pos] = (int)(j * p->N + inv[k]);
             }
@@ -1236,16 +1359,14 @@ size_t split_smem_b(const SelfPlan *p) {
            2 * (SF_THREADS / 32) * sizeof(double2);
 }
 
-template <int LOG2N>
 void launch_split_fft(size_t G, cudaStream_t st, const float *xyz, const double *b, const double *qs, int NF, int NM, size_t atom0,
                       size_t tl_first, size_t ntl, const SelfPlan *p, int dec, double2 *Zt) {
-    // FFT buffer + twiddle tables (256 + L/256 and 64 + N/64 entries) + the coordinates of one sub-sequence
-    constexpr size_t N_ = (size_t)1 << LOG2N;
-    const size_t smem = (N_ + N_ / 16 + 256 + (p->L >> 8) + 64 + (N_ >= 64 ? N_ / 64 : 1)) * sizeof(double2) +
-                        (((p->NF / p->R + 1) * 3 * sizeof(float) + 16 + 15) & ~(size_t)15);  // + the alignment offset
+    constexpr size_t N_ = 4096;
+    const size_t coords = ((p->NF / p->R + 1) * 3 * sizeof(float) + 16 + 15) & ~(size_t)15;  // + the alignment offset
     // tables grow with R, the coordinate buffer with NF/R <= N/2; 113 KB lets two CTAs share an SM (per-device attribute)
-    cudaFuncSetAttribute(self_split_fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-    self_split_fft_kernel<LOG2N><<<(unsigned)G, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, tl_first, ntl, p->R, dec, Zt);
+    const size_t smem = (N_ + 256 + (p->L >> 8)) * sizeof(double2) + 8 * sizeof(double) + coords;
+    cudaFuncSetAttribute(self_split_fft12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    self_split_fft12_kernel<<<(unsigned)G, SF_THREADS, smem, st>>>(xyz, b, qs, NF, NM, atom0, tl_first, ntl, p->R, dec, Zt);
 }
 }  // namespace
 
@@ -1283,14 +1404,9 @@ static int self_power_accumulate_split(const SelfPlan *p, const float *d_xyz_by_
     int launches = 0;
     for (size_t t0 = 0; t0 < ntl; t0 += tb) {
         const size_t nt = std::min(tb, ntl - t0);
-        const size_t GA = std::min<size_t>(nt, 2 * 148);  // two sub-transform CTAs per SM (128 registers each)
-        switch (p->log2N) {
-            case 8: launch_split_fft<8>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
-            case 9: launch_split_fft<9>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
-            case 10: launch_split_fft<10>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
-            case 11: launch_split_fft<11>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
-            default: launch_split_fft<12>(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt); break;
-        }
+        // two sub-transform CTAs per SM (128 registers each); the (timeline, r) pairs are dealt out evenly
+        const size_t GA = std::min<size_t>(nt * (size_t)p->R, 2 * 148);
+        launch_split_fft(GA, st, d_xyz_by_atom, d_b, d_qs, (int)p->NF, (int)NM, atom0, t0, nt, p, dec, Zt);
         size_t G = split_groups_b(p, nt);  // upper bound (Ppart2 is sized for it); the launchers pick whole waves
         if (p->reg_combine) {
 #define SF_RCASE(RR)                                                                                        \
