@@ -871,6 +871,18 @@ def bench_self(env, args):
     return line
 
 
+def host_mem_available():
+    """MemAvailable of /proc/meminfo in bytes (None if unreadable)"""
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
 def bench_streamed_self(env, args):
     """--workload C5s / C5: BASELINE configs[4], stager-streamed self scattering (50k frames).  The rank's atoms (ModAssignment)
     sit atom-major in PINNED HOST memory and pass through the GPU in waves: sgpu_stage_atoms_prefetch queues wave w+1 on the
@@ -895,9 +907,19 @@ def bench_streamed_self(env, args):
     NQ = min(len(qls_all), max(1, args.nq)) if full else 1
     u = synth.unit_vectors(NM, cfg["vseed"])
     b_all = synth.factors(cfg["NA"])
+    atom_bytes = NF * 12
+    # the ranks' atoms sit in pinned host memory: never ask for more than 70 % of what the box has free (a box driven out of
+    # memory dies); if the configuration does not fit, run as many atoms as do and say so (NA < NA_config in the line)
+    avail = host_mem_available()
+    if avail:
+        t_av = torch.tensor([float(avail)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_av, op=dist.ReduceOp.MIN)
+        fit = int(0.7 * float(t_av[0]) // atom_bytes)
+        if NA > fit:
+            NA = max(world, fit // world * world)
     na_loc = mod_assignment_count(world, rank, NA)
     b_loc = np.ascontiguousarray(b_all[rank:NA:world])
-    atom_bytes = NF * 12
     W = args.wave_atoms or max(64, int(2.0e9 // atom_bytes) // 64 * 64)  # ~2 GB per wave buffer
     W = max(1, min(W, na_loc))
     nwaves = (na_loc + W - 1) // W
@@ -928,6 +950,18 @@ def bench_streamed_self(env, args):
             dist.barrier()
         torch.cuda.synchronize()
         ctx.synchronize()
+
+    # what the copy engine delivers for one wave with nothing else running (all ranks at once: they share the host's memory)
+    w0 = min(W, na_loc)
+    ctx.stage_atoms_prefetch(host.array[0:w0])
+    ctx.stage_atoms_swap()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.stage_atoms_prefetch(host.array[0:w0])
+    ctx.stage_atoms_swap()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    h2d_idle_gbps = w0 * atom_bytes / (time.perf_counter() - t0) / 1e9
 
     kern_ms = [0.0]
 
@@ -1057,6 +1091,9 @@ def bench_streamed_self(env, args):
             "timelines_per_s": float(NA) * NM * NQ * args.steps / (wall_max * 1e-3),
             "fqt_wall_time_s_all_q": wall_max / args.steps * 1e-3 * (len(qls_all) / NQ) * (cfg["NA"] / NA),
             "staging": {"h2d_bytes_per_step_per_rank": int(na_loc * atom_bytes),
+                        "h2d_gbps_needed_per_rank": na_loc * atom_bytes / (wall_max / args.steps * 1e-3) / 1e9,
+                        "h2d_gbps_one_wave_idle_rank0": h2d_idle_gbps,
+                        "host_mem_available_bytes": avail,
                         "kernel_share_of_step": kern_max / wall_max,
                         "overlap": "wave w+1 is copied on the copy stream while wave w is evaluated; a step's wall time minus its "
                                    "kernel time is what staging, launches and the final reduce add",

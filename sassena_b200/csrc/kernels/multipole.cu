@@ -212,8 +212,13 @@ __global__ void multipole_assemble_kernel(const double2 *__restrict__ part, int 
 // more: the sum over atoms is sequential inside the owning thread, across tiles, in a fixed order.
 // Per tile: geometry (sincos) -> table tasks (Legendre column pairs (m, lmax-m): equal length; Bessel ladders with an
 // x-dependent Miller start) spread over all 512 threads -> product phase on 2 x NP threads.
-constexpr int MG_THREADS = 512;
-constexpr int MG_GROUPS = 2;    // thread groups of the product phase, A / MG_GROUPS atoms of a tile each
+// Two CTAs of 256 threads per SM (128 registers each, half the shared memory each) rather than one of 512: the table phase
+// of a tile is a bundle of serial chains (latency bound), the product phase streams shared memory into DFMAs (throughput
+// bound) -- two independent CTAs let one phase run under the other instead of alternating behind the same barriers.
+constexpr int MG_CTAS_PER_SM = 2;
+constexpr int MG_THREADS = 512 / MG_CTAS_PER_SM;
+constexpr int MG_GROUPS = MG_THREADS / 256;  // thread groups of the product phase, A / MG_GROUPS atoms of a tile each
+constexpr size_t MG_SMEM_CAP = (MG_CTAS_PER_SM == 1 ? 200 : 110) * 1024;
 constexpr int MG_ROUNDS = 4;    // rounds of table tasks per tile at most (limits the tile size)
 constexpr int MG_A_MAX = 64;    // atoms per tile: chosen per launch (mg_pick_tile) so that the (lmax+1+Q)*A table tasks fill
                                 // whole rounds of the 512 threads (24 atoms at L = 20, Q = 8 left the second round 36 % full)
@@ -257,7 +262,7 @@ __device__ __forceinline__ void mg_column(int m, int lmax, double ct, double st,
 }
 
 template <int Q>
-__global__ void __launch_bounds__(MG_THREADS, 1) multipole_gemm_kernel(
+__global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_kernel(
     const float *__restrict__ sph, const double *__restrict__ b, size_t b_stride, const double *__restrict__ qlens,
     int lmax, int lstart_max, size_t NA, size_t f0, size_t a_first, size_t a_last, size_t atoms_per_split,
     const double *__restrict__ tab, double2 *__restrict__ part, size_t nf, int q0, int NQ, int MG_A) {
@@ -528,8 +533,7 @@ const double *mp_tables(int lmax, cudaStream_t st) {
 
 // Atom splits per frame: grid = nf x nsplit CTAs, one CTA per SM (512 threads, ~170 KB shared memory).  At least four waves
 // of the 148 SMs when the atoms allow it, and the count whose last wave is fullest (600 CTAs = 4.05 waves ran as 5).
-int mp_nsplit(size_t nf, size_t NA) {
-    const size_t SMS = 148;
+int mp_nsplit(size_t nf, size_t NA, size_t SMS = 148) {  // SMS: resident CTAs of the device (148 SMs x CTAs per SM)
     size_t cap = (NA + 4 * MP_THREADS - 1) / (4 * MP_THREADS);
     if (cap < 1) cap = 1;
     if (cap > 4096) cap = 4096;
@@ -586,7 +590,7 @@ int launch_multipole_sphere(const float *d_sph, const double *d_b, double ql, co
 int multipole_batch_max() { return 8; }
 
 size_t multipole_batch_work_doubles(size_t nf, int lmax, size_t natoms, int NQ) {
-    return (size_t)mp_nsplit(nf, natoms) * MG_GROUPS * NQ * nf * mp_npairs(lmax) * 2;
+    return (size_t)mp_nsplit(nf, natoms, 148 * MG_CTAS_PER_SM) * MG_GROUPS * NQ * nf * mp_npairs(lmax) * 2;
 }
 
 // amplitudes of NQ |q| values at once: d_A[q] has NM timelines of ldA entries, q-th block at d_A + q*NM*ldA.
@@ -599,7 +603,7 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
     const double *tab = mp_tables(lmax, st);
     if (!tab) return -1;
     const size_t natoms = a_last > a_first ? a_last - a_first : 0;
-    const int nsplit = mp_nsplit(nf, std::max<size_t>(natoms, 1));
+    const int nsplit = mp_nsplit(nf, std::max<size_t>(natoms, 1), 148 * MG_CTAS_PER_SM);
     const size_t per = (natoms + nsplit - 1) / nsplit;
     const int L1 = lmax + 1, NP = mp_npairs(lmax);
     double2 *part = reinterpret_cast<double2 *>(d_work);
@@ -613,8 +617,8 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
         // (even, shared memory <= 200 KB) that fills its rounds best, the larger one on ties (fewer barriers per atom)
         int A = 2;
         double best = 0.0;
-        for (int c = 2; c <= MG_A_MAX; c += MG_GROUPS) {
-            if (smem_of(c) > (size_t)200 * 1024) break;
+        for (int c = 2; c <= MG_A_MAX; c += (MG_GROUPS > 1 ? MG_GROUPS : 1)) {
+            if (smem_of(c) > MG_SMEM_CAP) break;
             const int tasks = (L1 + Q) * c, rounds = (tasks + MG_THREADS - 1) / MG_THREADS;
             if (rounds > MG_ROUNDS) break;
             const double eff = (double)tasks / ((double)rounds * MG_THREADS);
@@ -624,7 +628,7 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
             }
         }
         const size_t per_tiles = ((per + A - 1) / A) * A;  // splits start on tile boundaries
-        cudaFuncSetAttribute(multipole_gemm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(multipole_gemm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MG_SMEM_CAP);
         multipole_gemm_kernel<Q><<<dim3((unsigned)nf, (unsigned)nsplit), MG_THREADS, smem_of(A), st>>>(
             d_sph, d_b, b_stride, d_qlens, lmax, mp_lstart(lmax), NA, f0, a_first, a_last, per_tiles, tab, part, nf, q0, NQ, A);
         launches++;

@@ -1617,7 +1617,12 @@ int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, cons
     double2 *A = reinterpret_cast<double2 *>(d_amp);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (lmax <= 21) {
-        rc = ensure_work(ctx, multipole_batch_work_doubles(ctx->NF, lmax, std::max<size_t>(atom_count, 1), (int)NQ) * sizeof(double));
+        // the atom splits (and with them the scratch) depend on the frames of a launch: size for the whole trajectory and
+        // for every staging chunk that may be launched on its own below
+        size_t work = multipole_batch_work_doubles(ctx->NF, lmax, std::max<size_t>(atom_count, 1), (int)NQ);
+        for (auto &c : ctx->chunks)
+            work = std::max(work, multipole_batch_work_doubles(c.nf, lmax, std::max<size_t>(atom_count, 1), (int)NQ));
+        rc = ensure_work(ctx, work * sizeof(double));
         if (rc) return rc;
         // one launch over all frames if every staging chunk has landed (and been converted), else one launch per chunk as
         // the chunks arrive: staging overlaps the kernel (as the coherent amplitude kernels do)
