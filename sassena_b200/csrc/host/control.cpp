@@ -95,13 +95,67 @@ struct Parser {
         if (p == s) fail("element name expected");
         return t.substr(s, p - s);
     }
-    XMLNode element() {
+    // XInclude (reference src/io/xml_interface.cpp:109-116 runs libxml2's xmlXIncludeProcess on every document): an
+    // <xi:include href="..." [parse="xml"|"text"]/> element is replaced by the root element of the referenced document
+    // (href relative to the including file) or by its text; a missing document takes the element's <xi:fallback> content.
+    // xpointer selections are not supported.
+    std::string base_dir;  // directory of the document being parsed ("" = current directory)
+    int depth = 0;         // inclusion nesting
+    typedef std::vector<std::pair<std::string, std::string>> Attrs;
+    static std::string local_name(const std::string &n) {
+        size_t c = n.find(':');
+        return c == std::string::npos ? n : n.substr(c + 1);
+    }
+    static const std::string *attr(const Attrs &a, const char *key) {
+        for (auto &kv : a)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+    // appends what the include element stands for to `parent`
+    void include_into(XMLNode &parent, const Attrs &a, const XMLNode &self) {
+        if (attr(a, "xpointer")) throw Error("XInclude: xpointer is not supported by the built-in XML reader");
+        const std::string *href = attr(a, "href");
+        if (!href || href->empty()) throw Error("XInclude: include element without href");
+        const std::string *mode = attr(a, "parse");
+        if (depth >= 16) throw Error("XInclude: inclusion nested deeper than 16 levels (a loop?): " + *href);
+        std::string fn = *href;
+        if (fn.compare(0, 7, "file://") == 0) fn = fn.substr(7);
+        if (!fn.empty() && fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+        std::string text;
+        {
+            std::ifstream f(fn.c_str(), std::ios::binary);
+            if (!f) {
+                for (auto &c : self.children)
+                    if (local_name(c.name) == "fallback") {
+                        parent.text += c.text;
+                        for (auto &g : c.children) parent.children.push_back(g);
+                        return;
+                    }
+                throw Error("XInclude: cannot open file: " + fn);
+            }
+            std::stringstream ss;
+            ss << f.rdbuf();
+            text = ss.str();
+        }
+        if (mode && *mode == "text") {
+            parent.text += text;
+            return;
+        }
+        if (mode && *mode != "xml") throw Error("XInclude: unknown parse mode: " + *mode);
+        Parser sub(text);
+        size_t slash = fn.rfind('/');
+        sub.base_dir = slash == std::string::npos ? std::string() : fn.substr(0, slash);
+        sub.depth = depth + 1;
+        sub.skip_misc();
+        if (sub.p >= text.size()) throw Error("XInclude: no root element in " + fn);
+        parent.children.push_back(sub.element());
+    }
+    XMLNode element(Attrs *attrs_out = nullptr) {
         if (t[p] != '<') fail("'<' expected");
         p++;
         XMLNode n;
         n.name = name();
-        if (n.name == "xi:include" || n.name == "include") throw Error("XInclude is not supported by the built-in XML reader");
-        // attributes are skipped
+        // attributes are skipped (the reference's schema carries everything in elements) unless the caller asks for them
         for (;;) {
             skip_ws();
             if (p >= t.size()) fail("unterminated start tag");
@@ -113,7 +167,7 @@ struct Parser {
                 p++;
                 break;
             }
-            name();
+            const std::string key = name();
             skip_ws();
             if (p < t.size() && t[p] == '=') {
                 p++;
@@ -122,6 +176,7 @@ struct Parser {
                 char q = t[p++];
                 size_t e = t.find(q, p);
                 if (e == std::string::npos) fail("unterminated attribute value");
+                if (attrs_out) attrs_out->push_back(std::make_pair(key, decode_entities(t.substr(p, e - p))));
                 p = e + 1;
             }
         }
@@ -143,8 +198,12 @@ struct Parser {
                 n.text += t.substr(p + 9, e - p - 9);
                 p = e + 3;
             } else if (starts("<?")) skip_until("?>");
-            else if (t[p] == '<') n.children.push_back(element());
-            else {
+            else if (t[p] == '<') {
+                Attrs a;
+                XMLNode c = element(&a);
+                if (local_name(c.name) == "include" && c.name != "include") include_into(n, a, c);  // prefixed: xi:include
+                else n.children.push_back(c);
+            } else {
                 size_t e = t.find('<', p);
                 if (e == std::string::npos) fail("unterminated element <" + n.name + ">");
                 n.text += decode_entities(t.substr(p, e - p));
@@ -173,14 +232,16 @@ std::vector<std::string> split_path(const std::string &s) {
 }
 }  // namespace
 
-XMLNode XMLInterface::parse(const std::string &text) {
+XMLNode XMLInterface::parse(const std::string &text, const std::string &base_dir) {
     Parser ps(text);
+    ps.base_dir = base_dir;
     ps.skip_misc();
     if (ps.p >= text.size()) throw Error("XML parse error: no root element");
     return ps.element();
 }
 
-XMLInterface::XMLInterface(const std::string &filename) : root_(parse(read_file(filename))) {}
+XMLInterface::XMLInterface(const std::string &filename)
+    : root_(parse(read_file(filename), filename.rfind('/') == std::string::npos ? std::string() : filename.substr(0, filename.rfind('/')))) {}
 
 std::vector<const XMLNode *> XMLInterface::get(const std::string &xpath) const {
     std::vector<const XMLNode *> cur;

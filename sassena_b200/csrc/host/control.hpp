@@ -32,7 +32,8 @@ class XMLInterface {  // reference src/io/xml_interface.cpp
 
    public:
     explicit XMLInterface(const std::string &filename);
-    static XMLNode parse(const std::string &text);
+    // base_dir: where relative XInclude hrefs of this document are looked up
+    static XMLNode parse(const std::string &text, const std::string &base_dir = std::string());
     std::vector<const XMLNode *> get(const std::string &xpath) const;
     bool exists(const std::string &xpath) const { return !get(xpath).empty(); }
     void set_current(const XMLNode *n) { current_ = n; }

@@ -617,7 +617,7 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
         // (even, shared memory <= 200 KB) that fills its rounds best, the larger one on ties (fewer barriers per atom)
         int A = 2;
         double best = 0.0;
-        for (int c = 2; c <= MG_A_MAX; c += (MG_GROUPS > 1 ? MG_GROUPS : 1)) {
+        for (int c = 2; c <= MG_A_MAX; c += 2) {  // even: keeps the double2 tables behind sB 16-byte aligned, and MG_GROUPS | c
             if (smem_of(c) > MG_SMEM_CAP) break;
             const int tasks = (L1 + Q) * c, rounds = (tasks + MG_THREADS - 1) / MG_THREADS;
             if (rounds > MG_ROUNDS) break;

@@ -416,6 +416,47 @@ def test_config_errors(tmp_path):
         host.Job(cfg)
 
 
+def test_xinclude(tmp_path):
+    """the reference runs libxml2's XInclude processing on every configuration document (xml_interface.cpp:109-116): an
+    <xi:include href=...> stands for the root element of the referenced document (relative to the including file, nested
+    includes relative to theirs), parse="text" for its text, <xi:fallback> for a missing one"""
+    cfg, _, _ = make_case(tmp_path, scattering=SCAN)
+    text = open(cfg).read()
+    ref_q = host.Job(cfg).qvectors()
+    a, b = text.index("<scattering>"), text.index("</scattering>") + len("</scattering>")
+    os.makedirs(tmp_path / "parts" / "deep", exist_ok=True)
+    scat = text[a:b]
+    va, vb = scat.index("<vectors>"), scat.index("</vectors>") + len("</vectors>")
+    open(tmp_path / "parts" / "deep" / "vectors.xml", "w").write('<?xml version="1.0"?>\n' + scat[va:vb])
+    open(tmp_path / "parts" / "scattering.xml", "w").write(
+        '<?xml version="1.0"?>\n' + scat[:va] + '<xi:include xmlns:xi="http://www.w3.org/2001/XInclude" href="deep/vectors.xml"/>'
+        + scat[vb:])
+    inc = '<xi:include xmlns:xi="http://www.w3.org/2001/XInclude" href="parts/scattering.xml"/>'
+    p = str(tmp_path / "with_include.xml")
+    open(p, "w").write(text[:a] + inc + text[b:])
+    assert np.array_equal(host.Job(p).qvectors(), ref_q)
+    # fallback content of a missing document; text inclusion
+    fb = ('<xi:include xmlns:xi="http://www.w3.org/2001/XInclude" href="parts/none.xml"><xi:fallback>' + scat
+          + '</xi:fallback></xi:include>')
+    open(p, "w").write(text[:a] + fb + text[b:])
+    assert np.array_equal(host.Job(p).qvectors(), ref_q)
+    open(tmp_path / "parts" / "three.txt", "w").write("3")
+    assert "<points>3</points>" in text
+    open(p, "w").write(text.replace("<points>3</points>", '<points><xi:include xmlns:xi="http://www.w3.org/2001/XInclude" '
+                                    'href="parts/three.txt" parse="text"/></points>'))
+    assert np.array_equal(host.Job(p).qvectors(), ref_q)
+    with pytest.raises(host.HostError, match="XInclude: cannot open"):
+        open(p, "w").write(text[:a] + inc.replace("scattering.xml", "absent.xml") + text[b:])
+        host.Job(p)
+    with pytest.raises(host.HostError, match="xpointer"):
+        open(p, "w").write(text[:a] + inc.replace("href=", 'xpointer="x" href=') + text[b:])
+        host.Job(p)
+    open(tmp_path / "parts" / "loop.xml", "w").write('<a><xi:include xmlns:xi="http://www.w3.org/2001/XInclude" href="loop.xml"/></a>')
+    with pytest.raises(host.HostError, match="nested deeper"):
+        open(p, "w").write(text[:a] + inc.replace("scattering.xml", "loop.xml") + text[b:])
+        host.Job(p)
+
+
 ORIENT = """<average><orientation><type>vectors</type>
   <vectors><type>sphere</type><algorithm>boost_uniform_on_sphere</algorithm><resolution>7</resolution><seed>5</seed></vectors>
 </orientation></average>"""

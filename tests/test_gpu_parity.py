@@ -162,14 +162,18 @@ def test_self_vectors_frame_counts(gpu_ctx, oracle, NF):
         assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
 
 
-@pytest.mark.parametrize("NF,NA,NM", [(4097, 3, 2), (5000, 7, 5), (6200, 2, 3), (8193, 1, 1), (10000, 5, 40), (12289, 2, 3),
-                                      (33000, 2, 2), (35000, 3, 3), (50000, 2, 3)])
+@pytest.mark.parametrize("NF,NA,NM", [(2049, 2, 3), (3000, 3, 2), (4096, 1, 5), (4097, 3, 2), (5000, 7, 5), (6200, 2, 3),
+                                      (8193, 1, 1), (10000, 5, 40), (10000, 61, 7), (12289, 2, 3), (33000, 2, 2), (35000, 3, 3),
+                                      (50000, 2, 3)])
 def test_self_vectors_split_path(oracle, monkeypatch, NF, NA, NM):
     """2NF-1 > 2*4096 (R >= 3): the split path -- every frame evaluated once, R decimated sub-FFTs per timeline, an
     R-point DFT across them, power spectrum permuted back to the residue-major layout -- against the oracle, forced with
     SASSENA_SELF_PATH=split (the library picks it from R = 5 on and the fused kernel below; both are checked).
     NF = 10000 is BASELINE config 2's timeline length (R = 5), NF = 50000 config 5's (R = 25, two-stage 5 x 5 combine);
-    33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18."""
+    33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18; 2049 / 3000 / 4096 are R = 2 (sub-sequences of 1025 ... 2048
+    frames: the shortest and the longest a 4096-point sub-transform takes).  Kernel A deals the (timeline, r) pairs out over
+    296 CTAs: 1 x 1 x 5 = 5 pairs leave most CTAs idle, 61 x 7 x 5 = 2135 give every CTA 7 or 8 with shares that begin and end
+    in the middle of a timeline."""
     xyz = synth.trajectory(NF, NA, 30.0, 0.1, 17, layout=1)
     b = synth.factors(NA)
     q = 1.3 * synth.unit_vectors(NM, 18)
@@ -186,6 +190,43 @@ def test_self_vectors_split_path(oracle, monkeypatch, NF, NA, NM):
         assert rel_err(fqt, rfqt) < TOL
         assert abs(fq - rfq) < TOL * abs(rfqt[0])
         assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
+
+
+@pytest.mark.parametrize("NF,NA,NM,W", [(9000, 9, 6, 4), (4500, 5, 3, 5), (50000, 3, 2, 2)])
+def test_self_split_path_on_streamed_waves(oracle, NF, NA, NM, W):
+    """the split path on wave buffers (sgpu_stage_atoms_prefetch / _swap): the coordinates stay in natural frame order there,
+    so kernel A gathers its decimated sub-sequences with 4-byte cp.async instead of copying contiguous runs; partials
+    accumulate over the waves (BASELINE config 5's path at timeline lengths that take R = 5, 3 and 25)."""
+    xyz = synth.trajectory(NF, NA, 30.0, 0.1, 29, layout=1)
+    b = synth.factors(NA)
+    q = 1.1 * synth.unit_vectors(NM, 30)
+    rfqt, rfq, rfq2 = oracle.compute_self_vectors(xyz, b, q, nthreads=8)
+    with sassena_b200.ScatterContext(0) as ctx:
+        host = ctx.pinned((NA, NF, 3), np.float32)
+        host.array[:] = xyz
+        plen = None
+        ctx.stage_atoms_prefetch(host.array[0:min(W, NA)])
+        for first in range(0, NA, W):
+            cnt = min(W, NA - first)
+            ctx.stage_atoms_swap()
+            if first + cnt < NA:
+                ctx.stage_atoms_prefetch(host.array[first + cnt:min(first + cnt + W, NA)])
+            ctx.set_factors(b[first:first + cnt])
+            if plen is None:
+                plen = ctx.partial_len("autocorrelate")
+                acc, part = ctx.device_alloc(plen * 8), ctx.device_alloc(plen * 8)
+                ctx.compute_self_vectors_partial(q, acc)
+            else:
+                ctx.compute_self_vectors_partial(q, part)
+                ctx.accumulate(acc, part, plen)
+        fqt, fq, fq2 = ctx.finalize(acc, 1.0 / NM)
+        ctx.synchronize()
+        ctx.device_free(acc)
+        ctx.device_free(part)
+        host.free()
+    assert rel_err(fqt, rfqt) < TOL
+    assert abs(fq - rfq) < TOL * abs(rfqt[0])
+    assert abs(fq2 - rfq2) <= TOL * abs(rfq2)
 
 
 def test_self_split_layout_roundtrip_and_generic_combine(oracle):
