@@ -62,6 +62,7 @@ SCAN_SETUP_INSTR, SCAN_SETUP_INSTR_CORR = 38.0, 40.0   # executed FP64-pipe inst
 SCAN_PAIR_INSTR, SCAN_PAIR_INSTR_CORR = 6.0, 10.0
 SCAN_SETUP_FLOP = 65.0                                 # algorithmic FP64 flop of the set-up (as round 1)
 SCAN_MAX_PASS, SCAN_MAX_PASS_CORR = 29, 17             # scan_sym.cu amplitude_scan_sym_max_pass
+SCAN_MAX_PASS_CORR32 = 25                              # ... with the first-order correction sums in FP32 (CORR = 2)
 
 
 def scan_passes(nq, max_b=SCAN_MAX_PASS):
@@ -76,11 +77,12 @@ def scan_passes(nq, max_b=SCAN_MAX_PASS):
     return out
 
 
-def scan_work_per_eval(nq, corrected):
+def scan_work_per_eval(nq, corrected, fp32d=False):
     """(algorithmic flop, executed FP64-pipe instructions) per evaluation of a scan of nq |q| values: a pass of L values runs
-    K = L // 2 pairs (an even L leaves one slot of the 2K+1 masked) plus the centre term"""
-    passes = scan_passes(nq, SCAN_MAX_PASS_CORR if corrected else SCAN_MAX_PASS)
-    pair = SCAN_PAIR_INSTR_CORR if corrected else SCAN_PAIR_INSTR
+    K = L // 2 pairs (an even L leaves one slot of the 2K+1 masked) plus the centre term.  fp32d: the corrected kernel whose
+    first-order sums run as packed FP32 instructions (the FP64 pipe sees the plain kernel's pair work)"""
+    passes = scan_passes(nq, (SCAN_MAX_PASS_CORR32 if fp32d else SCAN_MAX_PASS_CORR) if corrected else SCAN_MAX_PASS)
+    pair = (SCAN_PAIR_INSTR if fp32d else SCAN_PAIR_INSTR_CORR) if corrected else SCAN_PAIR_INSTR
     setup = SCAN_SETUP_INSTR_CORR if corrected else SCAN_SETUP_INSTR
     instr = sum(setup + pair * max(1, L // 2) for L in passes)
     # flop: a DFMA is two flop, the set-up as counted in round 1 (65) plus the correction products
@@ -582,14 +584,19 @@ def bench_coherent(env, args):
         nm0 = NM if (by_frames or world == 1) else div_assignment(world, 0, NM)[1]
         evals_rank = float(NA) * nf0 * nm0 * NQ * args.steps
         scan_plan = ctx.last_scan_plan() if scan else None
+        corrected = fp32d = False
         if scan:
             corrected = bool(scan_plan) and scan_plan[1] > 0  # what the library planned for this |q| list
-            flop_eval, instr_eval = scan_work_per_eval(NQ, corrected)
-            kernel = "amplitude_scan_sym_kernel" + (" (corrected: float-rounded scan)" if corrected else "")
+            # fewer corrected passes than the FP64-D kernel needs: the FP32-D kernel (25-|q| passes) was within its error bound
+            fp32d = corrected and scan_plan[1] < len(scan_passes(NQ, SCAN_MAX_PASS_CORR))
+            flop_eval, instr_eval = scan_work_per_eval(NQ, corrected, fp32d)
+            kernel = "amplitude_scan_sym_kernel" + ((" (corrected: float-rounded scan, first-order sums in " +
+                                                    ("packed FP32)" if fp32d else "FP64)")) if corrected else "")
         else:
             flop_eval, instr_eval, kernel = FLOP_PER_EVAL, FP64_INSTR_PER_EVAL, "amplitude_all_tiled_kernel"
         achieved = evals_rank * flop_eval / amp_s / 1e12
-        ncu = ncu_figures("scan_corrected" if (scan and corrected) else "scan_plain" if scan else "k1_tiled")
+        ncu = ncu_figures(("scan_corrected_fp32d" if fp32d else "scan_corrected") if (scan and corrected) else
+                          "scan_plain" if scan else "k1_tiled")
         traffic = ncu.get("dram_bytes_per_frame", None)
         traffic = traffic * nf0 if traffic is not None else None  # one launch covers all frames of the rank
         line = {
@@ -618,8 +625,9 @@ def bench_coherent(env, args):
                          "survey_8d_flop_per_eval": FLOP_PER_EVAL,
                          "frac_by_survey_8d_count": evals_rank * FLOP_PER_EVAL / amp_s / 1e12 / fp64_peak,
                          "note": ("symmetric scan kernel: 2 sincos per (atom, direction, pass) + two real Chebyshev recurrence "
-                                  "steps and four (corrected: eight) real accumulations per PAIR of |q|; `achieved` counts the "
-                                  "flop this formulation needs.  frac_by_survey_8d_count prices the same evaluations at SURVEY "
+                                  "steps and four (corrected with FP64 first-order sums: eight; with FP32 sums: four + packed "
+                                  "FP32) real accumulations per PAIR of |q|; `achieved` counts the FP64 flop this formulation "
+                                  "needs.  frac_by_survey_8d_count prices the same evaluations at SURVEY "
                                   "8(d)'s one-sincos-per-evaluation figure (45 flop) and therefore exceeds 1: the kernel does "
                                   "not execute that work.  fp64_pipe_util_ncu is sm__inst_executed_pipe_fp64 of the committed "
                                   "capture" if scan else "45 flop per evaluation (SURVEY 8d)"),
@@ -854,7 +862,7 @@ def bench_self(env, args):
             "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * len(qls),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": traffic,
-                         "kernel": "self_split_fft_kernel + self_split_combine_ring_kernel",
+                         "kernel": "self_split_fft12_kernel + self_split_combine_ring_kernel",
                          "kernel_share_of_step": amp_ms_max / ms_max,
                          "algorithmic_flop_per_timeline": self_flop_per_timeline(NF),
                          "note": "45 flop per amplitude + one forward 2NF-point FFT (5 L log2 L) per timeline (SURVEY 8d); "
@@ -1100,7 +1108,7 @@ def bench_streamed_self(env, args):
                         "hbm_high_water_bytes": int(hbm_max), "resident": resident},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "self_split_fft_kernel + self_split_combine_*",
+                         "kernel": "self_split_fft12_kernel + self_split_combine_*",
                          "kernel_share_of_step": kern_max / wall_max,
                          "algorithmic_flop_per_timeline": self_flop_per_timeline(NF),
                          "note": "45 flop per amplitude + one forward 2NF-point FFT (5 L log2 L) per timeline (SURVEY 8d)",

@@ -24,6 +24,10 @@
 // runs in FP32 as PACKED f32x2 instructions (sm_100 FFMA2): one for the (C_k, S_k) recurrence and two for the four
 // accumulations of a pair.  The FP32 recurrence is written on y_k = sg_k X_k with sg = + + - - + + ..., which turns the
 // subtraction into y_{k+1} = +-c2 y_k + y_{k-1} (FFMA2 has no negated operands); the signs are undone at the end.
+// CORR = 2 also takes D_n from the FP32 recurrence (two more FFMA2 per pair instead of four DFMAs): the inner loop is then
+// the plain kernel's 3 FP64 instructions per evaluation, and with D in packed floats the registers allow K = 12 (25 |q| per
+// pass, two passes for a 50-point scan instead of three).  Its error is bounded by theta_max (K^2 ulp32 + accumulation),
+// theta_max = max |kappa_n sigma|; plan_scan (sgpu_capi.cu) takes it only where that bound stays below 5e-10.
 //
 // Mapping (as the general kernel K1, amplitude.cu): one CTA = one frame x WARPS directions, one direction per warp, lanes
 // stride over the atoms of a TILE-atom tile; tiles stream through a STAGES-deep shared-memory ring filled by 1-D TMA bulk
@@ -95,14 +99,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) amplitude_scan_sym_kernel(
 
     // lane sums: centre term and the K pairs, for A (and D in FP64, E in FP32 as (P, Q) pairs per component)
     double a0r = 0.0, a0i = 0.0, pr[K], pi[K], qr[K], qi[K];
-    double d0r = 0.0, d0i = 0.0, dpr[CORR ? K : 1], dpi[CORR ? K : 1], dqr[CORR ? K : 1], dqi[CORR ? K : 1];
+    double d0r = 0.0, d0i = 0.0, dpr[CORR == 1 ? K : 1], dpi[CORR == 1 ? K : 1], dqr[CORR == 1 ? K : 1], dqi[CORR == 1 ? K : 1];
     float2 e0 = make_float2(0.f, 0.f), epq_r[CORR ? K : 1], epq_i[CORR ? K : 1];
+    float2 fd0 = make_float2(0.f, 0.f), dpqf_r[CORR == 2 ? K : 1], dpqf_i[CORR == 2 ? K : 1];  // D in FP32, as (P, Q) pairs
 #pragma unroll
     for (int k = 0; k < K; k++) pr[k] = pi[k] = qr[k] = qi[k] = 0.0;
     if (CORR) {
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            dpr[k] = dpi[k] = dqr[k] = dqi[k] = 0.0;
+            if (CORR == 1) dpr[k] = dpi[k] = dqr[k] = dqi[k] = 0.0;
+            if (CORR == 2) dpqf_r[k] = dpqf_i[k] = make_float2(0.f, 0.f);
             epq_r[k] = epq_i[k] = make_float2(0.f, 0.f);
         }
     }
@@ -130,13 +136,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) amplitude_scan_sym_kernel(
                 double Cp = 1.0, C = c1, Sp = 0.0, S = s1;
                 double wr = 0.0, wi = 0.0;
                 float2 yk = make_float2(0.f, 0.f), ykp = make_float2(0.f, 0.f), er_b = yk, ei_b = yk, c2p = yk, c2m = yk;
+                float2 dr_b = yk, di_b = yk;
                 if (CORR) {
-                    wr = sigma * zr;  // w0 = sigma z0
-                    wi = sigma * zi;
-                    d0r += wr;
-                    d0i += wi;
-                    const float fs = (float)sigma, fs2 = fs * fs;
-                    const float fer = fs2 * (float)zr, fei = fs2 * (float)zi;  // sigma^2 z0
+                    const float fs = (float)sigma, fs2 = fs * fs, fzr = (float)zr, fzi = (float)zi;
+                    if (CORR == 1) {
+                        wr = sigma * zr;  // w0 = sigma z0
+                        wi = sigma * zi;
+                        d0r += wr;
+                        d0i += wi;
+                    } else {
+                        const float fwr = fs * fzr, fwi = fs * fzi;
+                        fd0.x += fwr;
+                        fd0.y += fwi;
+                        dr_b = make_float2(fwr, fwr);
+                        di_b = make_float2(fwi, fwi);
+                    }
+                    const float fer = fs2 * fzr, fei = fs2 * fzi;  // sigma^2 z0
                     e0.x += fer;
                     e0.y += fei;
                     er_b = make_float2(fer, fer);
@@ -169,11 +184,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) amplitude_scan_sym_kernel(
                     pi[k - 1] = fma(C, zi, pi[k - 1]);
                     qi[k - 1] = fma(S, zi, qi[k - 1]);
                     qr[k - 1] = fma(S, zr, qr[k - 1]);
-                    if (CORR) {
+                    if (CORR == 1) {
                         dqr[k - 1] = fma(S, wr, dqr[k - 1]);
                         dqi[k - 1] = fma(S, wi, dqi[k - 1]);
                         dpi[k - 1] = fma(C, wi, dpi[k - 1]);
                         dpr[k - 1] = fma(C, wr, dpr[k - 1]);
+                    }
+                    if (CORR == 2) {
+                        dpqf_r[k - 1] = __ffma2_rn(yk, dr_b, dpqf_r[k - 1]);
+                        dpqf_i[k - 1] = __ffma2_rn(yk, di_b, dpqf_i[k - 1]);
+                    }
+                    if (CORR) {
                         epq_r[k - 1] = __ffma2_rn(yk, er_b, epq_r[k - 1]);  // (P, Q) of the real part, sign sg_k
                         epq_i[k - 1] = __ffma2_rn(yk, ei_b, epq_i[k - 1]);
                     }
@@ -199,17 +220,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) amplitude_scan_sym_kernel(
     if (CORR) {
         // fold the corrections in: A_n + i kappa_n D_n - (kappa_n^2 / 2) E_n
         double dre[B], dim[B], ere[B], eim[B];
-        dre[K] = d0r;
-        dim[K] = d0i;
+        dre[K] = CORR == 1 ? d0r : (double)fd0.x;
+        dim[K] = CORR == 1 ? d0i : (double)fd0.y;
         ere[K] = (double)e0.x;
         eim[K] = (double)e0.y;
 #pragma unroll
         for (int k = 1; k <= K; k++) {
-            dre[K + k] = dpr[k - 1] - dqi[k - 1];
-            dim[K + k] = dpi[k - 1] + dqr[k - 1];
-            dre[K - k] = dpr[k - 1] + dqi[k - 1];
-            dim[K - k] = dpi[k - 1] - dqr[k - 1];
             const double sg = ((k & 3) >= 2) ? -1.0 : 1.0;  // sign carried by the FP32 recurrence
+            double Dpr, Dpi, Dqr, Dqi;
+            if (CORR == 1) {
+                Dpr = dpr[k - 1], Dpi = dpi[k - 1], Dqr = dqr[k - 1], Dqi = dqi[k - 1];
+            } else {
+                Dpr = sg * (double)dpqf_r[k - 1].x, Dqr = sg * (double)dpqf_r[k - 1].y;
+                Dpi = sg * (double)dpqf_i[k - 1].x, Dqi = sg * (double)dpqf_i[k - 1].y;
+            }
+            dre[K + k] = Dpr - Dqi;
+            dim[K + k] = Dpi + Dqr;
+            dre[K - k] = Dpr + Dqi;
+            dim[K - k] = Dpi - Dqr;
             const double epr = sg * (double)epq_r[k - 1].x, eqr = sg * (double)epq_r[k - 1].y;
             const double epi = sg * (double)epq_i[k - 1].x, eqi = sg * (double)epq_i[k - 1].y;
             ere[K + k] = epr - eqi;
@@ -277,16 +305,27 @@ int launch_sym(const SymArgs &a) {
 
 template <int CORR, int WARPS>
 int dispatch_sym(int K, const SymArgs &a) {
-    switch (K) {
-        case 1: return launch_sym<1, WARPS, CORR>(a);
-        case 2: return launch_sym<2, WARPS, CORR>(a);
-        case 3: return launch_sym<3, WARPS, CORR>(a);
-        case 4: return launch_sym<4, WARPS, CORR>(a);
-        case 5: return launch_sym<5, WARPS, CORR>(a);
-        case 6: return launch_sym<6, WARPS, CORR>(a);
-        case 7: return launch_sym<7, WARPS, CORR>(a);
-        case 8: return launch_sym<8, WARPS, CORR>(a);
-        default: break;
+    if constexpr (CORR != 2) {
+        switch (K) {
+            case 1: return launch_sym<1, WARPS, CORR>(a);
+            case 2: return launch_sym<2, WARPS, CORR>(a);
+            case 3: return launch_sym<3, WARPS, CORR>(a);
+            case 4: return launch_sym<4, WARPS, CORR>(a);
+            case 5: return launch_sym<5, WARPS, CORR>(a);
+            case 6: return launch_sym<6, WARPS, CORR>(a);
+            case 7: return launch_sym<7, WARPS, CORR>(a);
+            case 8: return launch_sym<8, WARPS, CORR>(a);
+            default: break;
+        }
+    }
+    if constexpr (CORR == 2) {
+        switch (K) {
+            case 9: return launch_sym<9, WARPS, 2>(a);
+            case 10: return launch_sym<10, WARPS, 2>(a);
+            case 11: return launch_sym<11, WARPS, 2>(a);
+            case 12: return launch_sym<12, WARPS, 2>(a);
+            default: break;
+        }
     }
     if constexpr (!CORR) {
         switch (K) {
@@ -304,7 +343,8 @@ int dispatch_sym(int K, const SymArgs &a) {
 
 }  // namespace
 
-int amplitude_scan_sym_max_pass(int corrected) { return corrected ? 17 : 29; }
+// corrected: 1 = first-order sums in FP64 (K <= 8), 2 = in FP32 (K <= 12; plan_scan checks the error bound)
+int amplitude_scan_sym_max_pass(int corrected) { return corrected == 2 ? 25 : corrected ? 17 : 29; }
 int amplitude_scan_sym_qpad() { return 24; }  // a multiple of the directions per CTA (8 or 12 warps)
 
 int launch_amplitude_scan_sym_pass(const float *d_xyz, const double *d_b, const double *d_vs, double s0, double ds, int nq,
@@ -315,7 +355,8 @@ int launch_amplitude_scan_sym_pass(const float *d_xyz, const double *d_b, const 
     SymArgs a{d_xyz, d_b, d_vs, s0 + (double)K * ds, ds, nq, d_A, ldA, strideQ, NA, NM, f0, nf, st, ScanKappa()};
     if (kappa) {
         for (int n = 0; n < 32; n++) a.kap.k[n] = n < nq ? kappa[n] : 0.0;
-        return dispatch_sym<1, SYM_WARPS_CORR>(K, a);
+        // passes longer than the FP64-D kernel takes are the FP32-D kernel's (plan_scan makes them only within its error bound)
+        return K <= 8 ? dispatch_sym<1, SYM_WARPS_CORR>(K, a) : dispatch_sym<2, SYM_WARPS_CORR>(K, a);
     }
     return dispatch_sym<0, SYM_WARPS_PLAIN>(K, a);
 }

@@ -27,6 +27,7 @@ const double kTwoOverPi = 0.63661977236758134308;
 struct sgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t conv_stream = nullptr;  // per-chunk coordinate conversions of frames still being staged (created on demand)
     std::string err;
     uint64_t launches = 0;
 
@@ -110,6 +111,7 @@ struct sgpu_ctx {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (conv_stream) cudaStreamSynchronize(conv_stream);
         for (auto &c : chunks) cudaEventDestroy(c.ready);
         if (own_xyz && d_xyz) cudaFree(d_xyz);
         if (comm && comm_owned) {
@@ -149,6 +151,7 @@ struct sgpu_ctx {
         if (evd1) cudaEventDestroy(evd1);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (conv_stream) cudaStreamDestroy(conv_stream);
     }
 };
 
@@ -223,6 +226,7 @@ void drop_chunks(sgpu_ctx *ctx) {
 int release_xyz(sgpu_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));
     drop_chunks(ctx);
     if (!ctx->own_xyz) {
         ctx->d_xyz = nullptr;
@@ -416,6 +420,7 @@ int sgpu_synchronize(sgpu_ctx *ctx) {
     if (!ctx) return SGPU_EINVAL;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SGPU_OK;
 }
@@ -529,13 +534,15 @@ int sgpu_frames_to_spherical(sgpu_ctx *ctx) {
     if (ctx->chunks.empty()) {
         ctx->launches += launch_cart_to_spherical(ctx->d_xyz, ctx->NF * ctx->NA, ctx->stream);
     } else {
-        // staging chunks still in flight: convert every chunk as it lands (the compute stream waits per chunk, the host does
-        // not), and let the chunk's event from now on mean "converted", so that the multipole kernel can start on the first
-        // chunks while the last ones are still crossing PCIe
+        // staging chunks still in flight: convert every chunk as it lands, on a stream of its own (on the compute stream the
+        // conversions would queue IN FRONT of the multipole launches and hold all of them back until the last chunk has
+        // crossed PCIe), and let the chunk's event from now on mean "converted": the multipole kernel starts on the first
+        // chunks while the last ones are still being copied
+        if (!ctx->conv_stream) CK(cudaStreamCreateWithFlags(&ctx->conv_stream, cudaStreamNonBlocking));
         for (auto &c : ctx->chunks) {
-            CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
-            ctx->launches += launch_cart_to_spherical(ctx->d_xyz + c.f0 * ctx->NA * 3, c.nf * ctx->NA, ctx->stream);
-            CK(cudaEventRecord(c.ready, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->conv_stream, c.ready, 0));
+            ctx->launches += launch_cart_to_spherical(ctx->d_xyz + c.f0 * ctx->NA * 3, c.nf * ctx->NA, ctx->conv_stream);
+            CK(cudaEventRecord(c.ready, ctx->conv_stream));
         }
     }
     CK(cudaGetLastError());
@@ -582,6 +589,7 @@ int sgpu_frames_to_cylindrical(sgpu_ctx *ctx, const double axis[3]) {
     if (!vector_base(axis, base)) return fail(ctx, SGPU_EINVAL, "sgpu_frames_to_cylindrical: axis has zero length");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));
     drop_chunks(ctx);
     ctx->launches += launch_cart_to_cylindrical(ctx->d_xyz, ctx->NF * ctx->NA, base, ctx->stream);
     CK(cudaGetLastError());
@@ -704,6 +712,7 @@ int sgpu_stage_atoms_prefetch(sgpu_ctx *ctx, const float *xyz, size_t count, siz
         // grow both buffers: nothing may be in flight on either
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));
         if (ctx->wave_staged) {
             ctx->wave_staged = false;
             ctx->d_xyz = nullptr;
@@ -967,7 +976,8 @@ namespace {
 // bound of |r| over the staged coordinates (sqrt(3) * max |component|), computed once per staging
 int ensure_rmax(sgpu_ctx *ctx) {
     if (ctx->rmax_valid) return SGPU_OK;
-    CK(cudaStreamSynchronize(ctx->copy_stream));  // every staging chunk has to be resident
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));  // every staging chunk has to be resident
     drop_chunks(ctx);
     float *d_m = nullptr;
     CK(cudaMalloc(reinterpret_cast<void **>(&d_m), sizeof(float)));
@@ -1022,29 +1032,47 @@ int plan_scan(sgpu_ctx *ctx, const double *s, size_t NQ, double vmax, bool unifo
         int rc = ensure_rmax(ctx);
         if (rc) return rc;
     }
-    const size_t npass = (NQ + maxB - 1) / maxB;
-    size_t n0 = 0;
-    for (size_t p = 0; p < npass; p++) {
-        const size_t want = (NQ - n0 + (npass - p) - 1) / (npass - p);  // even share of what is left
-        // the symmetric scan kernel takes any pass length (2K+1 slots; an even length masks one); the kernel for
-        // |q|-dependent factors is instantiated for multiples of 4
-        size_t L = std::min<size_t>(std::min<size_t>(uniform_b ? want : ((want + 3) / 4) * 4, maxB), NQ - n0);
-        if (exact && !force_corr) {
-            plan.push_back(ScanPass{n0, (int)L, s[0] + (double)n0 * ds, ds, uniform_b ? 0 : 3, {}});
-        } else {
-            double ps0, pds, peps;
-            fit(n0, L, ps0, pds, peps);
-            const double theta = peps * vmax * ctx->rmax;  // largest phase deviation in radians
-            if (L >= 3 && theta <= 3e-4) {
-                ScanPass sp{n0, (int)L, ps0, pds, 1, {}};
-                for (size_t n = 0; n < L; n++) sp.kappa.push_back(1.5707963267948966 * (s[n0 + n] - (ps0 + (double)n * pds)));
-                plan.push_back(sp);
+    // lays the |q| values out in even passes of at most maxB; fp32d: only if every pass is a near-progression whose
+    // first-order correction may be summed in FP32 (scan_sym.cu, CORR = 2): the error of that path is bounded by
+    // theta_max * (K^2 ulp32 of the recurrence + FP32 accumulation over NA / 32 terms per lane), accepted below 5e-10
+    auto lay_out = [&](size_t maxB_, bool fp32d, std::vector<ScanPass> &out) -> bool {
+        out.clear();
+        const size_t npass = (NQ + maxB_ - 1) / maxB_;
+        size_t n0 = 0;
+        for (size_t p = 0; p < npass; p++) {
+            const size_t want = (NQ - n0 + (npass - p) - 1) / (npass - p);  // even share of what is left
+            // the symmetric scan kernel takes any pass length (2K+1 slots; an even length masks one); the kernel for
+            // |q|-dependent factors is instantiated for multiples of 4
+            size_t L = std::min<size_t>(std::min<size_t>(uniform_b ? want : ((want + 3) / 4) * 4, maxB_), NQ - n0);
+            if (exact && !force_corr) {
+                out.push_back(ScanPass{n0, (int)L, s[0] + (double)n0 * ds, ds, uniform_b ? 0 : 3, {}});
             } else {
-                for (size_t n = 0; n < L; n++) plan.push_back(ScanPass{n0 + n, 1, s[n0 + n], 0.0, 2, {}});
+                double ps0, pds, peps;
+                fit(n0, L, ps0, pds, peps);
+                const double theta = peps * vmax * ctx->rmax;  // largest phase deviation in radians
+                if (fp32d) {
+                    const double K = (double)(L / 2);
+                    const double bound = theta * (K * K * 7e-8 + 4e-8 * std::sqrt((double)ctx->NA / 32.0));
+                    if (L < 3 || theta > 3e-4 || bound > 5e-10) return false;
+                }
+                if (L >= 3 && theta <= 3e-4) {
+                    ScanPass sp{n0, (int)L, ps0, pds, 1, {}};
+                    for (size_t n = 0; n < L; n++) sp.kappa.push_back(1.5707963267948966 * (s[n0 + n] - (ps0 + (double)n * pds)));
+                    out.push_back(sp);
+                } else {
+                    for (size_t n = 0; n < L; n++) out.push_back(ScanPass{n0 + n, 1, s[n0 + n], 0.0, 2, {}});
+                }
             }
+            n0 += L;
         }
-        n0 += L;
-    }
+        return true;
+    };
+    // float-rounded scans longer than one FP64-D pass: try the longer FP32-D passes first (fewer passes, 3 instead of 5 FP64
+    // instructions per evaluation); SASSENA_SCAN_FP64_CORR keeps the first-order sums in FP64
+    if ((!exact || force_corr) && uniform_b && NQ > maxB && !getenv("SASSENA_SCAN_FP64_CORR") &&
+        lay_out((size_t)amplitude_scan_sym_max_pass(2), true, plan))
+        return SGPU_OK;
+    lay_out(maxB, false, plan);
     return SGPU_OK;
 }
 
@@ -1645,6 +1673,7 @@ int sgpu_mpsphere_amplitudes(sgpu_ctx *ctx, const double *qlens, size_t NQ, cons
         }
     } else {
         CK(cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));
         drop_chunks(ctx);
         // more (l,m) pairs than threads of the batched kernel: one pass per |q| with the shuffle-reduction kernel
         if (atom_first != 0 || atom_count != ctx->NA)
@@ -1890,6 +1919,7 @@ int sgpu_mpcylinder_amplitudes(sgpu_ctx *ctx, const double q[3], const double ax
     }
     if (qphi < 0) qphi = 2 * 3.14159265358979323846 + qphi;
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->conv_stream) CK(cudaStreamSynchronize(ctx->conv_stream));
     drop_chunks(ctx);
     rc = ensure_work(ctx, mpcylinder_work_doubles(ctx->NF, nmax, std::max<size_t>(atom_count, 1)) * sizeof(double));
     if (rc) return rc;

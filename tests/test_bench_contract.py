@@ -93,8 +93,8 @@ def test_bench_ours_small_sizes_json_line(extra):
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert d["parity"]["fqt_rel_err"] < 1e-9 and d["parity"]["fq_rel_err"] < 1e-9
     assert "workload" in d["config"]
-    if "C5s" in extra:  # streamed: three waves, same result as the resident run
-        assert d["config"]["waves_per_rank"] == 3 and d["staging"]["resident"]["streamed_vs_resident_rel_err"] < 1e-12
+    if "C5s" in extra:  # streamed: three waves, same result as the resident run (up to the order of the sums over atoms)
+        assert d["config"]["waves_per_rank"] == 3 and d["staging"]["resident"]["streamed_vs_resident_rel_err"] < 1e-11
 
 
 @pytest.mark.gpu

@@ -444,6 +444,35 @@ def test_all_vectors_scan_float_rounded_scan(gpu_ctx, oracle):
     assert rel_err(fqt[24], r[0]) > 1e-8
 
 
+def test_all_vectors_scan_float_rounded_scan_fp32_first_order(oracle, monkeypatch):
+    """A float-rounded 50-point scan whose phase deviations are small (box 60: theta_max ~ 1.6e-5) qualifies for the corrected
+    kernel that sums the first-order term in packed FP32 as well (scan_sym.cu, CORR = 2: 25-|q| passes, 3 FP64 instructions
+    per evaluation).  plan_scan admits it only while its error bound theta_max (K^2 ulp32 + accumulation) is below 5e-10;
+    measured here against the oracle at the exact q-vectors: ~1e-11, tolerance 1e-9.  SASSENA_SCAN_FP64_CORR keeps the
+    first-order sums in FP64 (three passes)."""
+    from sassena_b200 import host
+    xyz, b, u = small_case(NA=516, NF=12, NM=19, box=60.0)
+    qv = host.create_from_scans([{"base": (1, 0, 0), "from": 0.1, "to": 5.0, "points": 50}])
+    s = np.linalg.norm(qv, axis=1)
+    res = {}
+    for fp64 in (False, True):
+        if fp64:
+            monkeypatch.setenv("SASSENA_SCAN_FP64_CORR", "1")
+        with sassena_b200.ScatterContext(0) as ctx:
+            ctx.stage_frames(xyz)
+            ctx.set_factors(b)
+            res[fp64] = ctx.compute_all_vectors_scan(u, s)
+            plain, corr, single = ctx.last_scan_plan()
+        assert plain == 0 and single == 0 and corr == (3 if fp64 else 2)
+    worst = 0.0
+    for n in range(50):
+        r = oracle.compute_all_vectors(xyz, b, s[n] * u)
+        worst = max(worst, rel_err(res[False][0][n], r[0]))
+        assert rel_err(res[False][0][n], r[0]) < TOL and rel_err(res[True][0][n], r[0]) < 1e-11
+        assert abs(res[False][1][n] - r[1]) < TOL * abs(r[0][0])
+    assert worst < 2e-10, worst  # the bound plan_scan works with is 5e-10; typical 1e-11
+
+
 def test_all_vectors_scan_arbitrary_spacing_falls_back(gpu_ctx, oracle):
     """|q| values with no progression at all: the call is still valid, each |q| runs through the general kernel"""
     xyz, b, u = small_case(NA=120, NF=16, NM=12)
