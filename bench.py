@@ -812,8 +812,9 @@ def bench_self(env, args):
         e2e = {"value": evals_step * e2e_steps / e2e_s, "unit": "evals/s", "steps": e2e_steps,
                "h2d_bytes_per_step": int(na_loc * NF * 12 + na_loc * 8 + NM * 24), "d2h_bytes_per_step": int(NF * 16 + 32),
                "ms_per_step": 1e3 * e2e_s / e2e_steps,
-               "note": "every rank re-stages its atoms from pinned host memory every step (H2D, then the decimated frame "
-                       "order of the split path is rebuilt on the device); fqt/fq/fq2 of the step's |q| read back"}
+               "note": "every rank re-stages its atoms from pinned host memory every step (chunks of atoms on the copy stream; "
+                       "each chunk is brought into the decimated frame order of the split path and evaluated as it lands, the "
+                       "next copies run underneath); fqt/fq/fq2 of the step's |q| read back"}
 
     cpu_baseline = None
     parity = None

@@ -79,7 +79,9 @@ int sgpu_stage_frames_device(sgpu_ctx *ctx, const float *d_xyz, size_t NF, size_
 int sgpu_frames_to_spherical(sgpu_ctx *ctx);
 
 /* DataStagerByAtom::stage (data_stager.cpp:214-349): xyz is host float [NA_local][NF][3]
- * (atom-major, self_vectors_scatter_device.cpp:303). */
+ * (atom-major, self_vectors_scatter_device.cpp:303).  Asynchronous and chunked by atoms like sgpu_stage_frames: the
+ * autocorrelation path of sgpu_compute_self_vectors* evaluates every chunk as it lands (every other consumer waits for the
+ * last one on the device).  xyz must stay valid until sgpu_synchronize() or a compute that returns results has returned. */
 int sgpu_stage_atoms(sgpu_ctx *ctx, const float *xyz, size_t NA_local, size_t NF);
 int sgpu_stage_atoms_device(sgpu_ctx *ctx, const float *d_xyz, size_t NA_local, size_t NF);
 /* Frame-major host input [NF][NA][3] -> atom-major device layout for the atoms this rank owns under

@@ -134,13 +134,14 @@ class ScatterContext:
         self._ck(self.lib.sgpu_frames_to_spherical(self.h))
 
     def stage_atoms(self, xyz_by_atom):
-        """xyz_by_atom: float32 [NA_local][NF][3]."""
+        """xyz_by_atom: float32 [NA_local][NF][3].  Asynchronous like stage_frames (chunks of atoms on the copy stream; the
+        autocorrelation path evaluates them as they land): the array is kept alive here, do not overwrite or free its memory
+        before synchronize() or a compute that returns results."""
         a = np.ascontiguousarray(xyz_by_atom, dtype=np.float32)
         if a.ndim != 3 or a.shape[2] != 3:
             raise SgpuError(1, "stage_atoms expects [NA][NF][3]")
         self._keep = a
         self._ck(self.lib.sgpu_stage_atoms(self.h, a.ctypes.data, a.shape[0], a.shape[1]))
-        self.synchronize()
         self.NA, self.NF = a.shape[0], a.shape[1]
         self._NFt = 0
 

@@ -241,12 +241,42 @@ int release_xyz(sgpu_ctx *ctx) {
 
 // Atoms mode, owned buffer: bring the frames of every atom into decimated order for R (R > 0) or back to natural order
 // (R == 0).  Out of place through a bounce buffer, a batch of atoms at a time.  Adopted (caller-owned) buffers stay natural.
+// atoms mode: sgpu_stage_atoms copies in chunks of atoms on the copy stream (ctx->chunks holds (first atom, count, event)).
+// Consumers that need every atom make the compute stream wait for the last chunk (the copy stream is in order); only the
+// autocorrelation path of sgpu_compute_self_vectors_partial walks the chunks one by one.
+int atoms_landed(sgpu_ctx *ctx) {
+    if (ctx->mode != 2 || ctx->chunks.empty()) return SGPU_OK;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->chunks.back().ready, 0));
+    drop_chunks(ctx);
+    return SGPU_OK;
+}
+
+// rows [a0, a0 + na) of an owned atom-major buffer from natural frame order into the decimated order for R (out of place
+// through the bounce buffer, on the compute stream)
+int decimate_rows(sgpu_ctx *ctx, size_t a0, size_t na, int R) {
+    const size_t row = ctx->NF * 3 * sizeof(float);
+    const size_t batch = std::max<size_t>(1, std::min(na, ((size_t)256 << 20) / row));
+    int rc = ensure<float>(ctx, &ctx->d_stage_tmp, &ctx->stage_tmp_cap, batch * ctx->NF * 3);
+    if (rc) return rc;
+    for (size_t b0 = 0; b0 < na; b0 += batch) {
+        const size_t nb = std::min(batch, na - b0);
+        float *rows = ctx->d_xyz + (a0 + b0) * ctx->NF * 3;
+        CK(cudaMemcpyAsync(ctx->d_stage_tmp, rows, nb * row, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->launches += self_decimate_layout(ctx->d_stage_tmp, rows, nb, ctx->NF, R, 1, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    return SGPU_OK;
+}
+
 int set_atoms_layout(sgpu_ctx *ctx, int R) {
-    if (ctx->mode != 2 || ctx->atoms_dec_R == R) return SGPU_OK;
+    if (ctx->mode != 2) return SGPU_OK;
+    int rc = atoms_landed(ctx);
+    if (rc) return rc;
+    if (ctx->atoms_dec_R == R) return SGPU_OK;
     if (!ctx->own_xyz && !ctx->wave_staged) return SGPU_OK;
     const size_t row = ctx->NF * 3 * sizeof(float);
     const size_t batch = std::max<size_t>(1, std::min(ctx->NA, ((size_t)256 << 20) / row));
-    int rc = ensure<float>(ctx, &ctx->d_stage_tmp, &ctx->stage_tmp_cap, batch * ctx->NF * 3);
+    rc = ensure<float>(ctx, &ctx->d_stage_tmp, &ctx->stage_tmp_cap, batch * ctx->NF * 3);
     if (rc) return rc;
     for (int pass = 0; pass < 2; pass++) {
         const int cur = (pass == 0) ? ctx->atoms_dec_R : 0;
@@ -607,7 +637,24 @@ int sgpu_stage_atoms(sgpu_ctx *ctx, const float *xyz, size_t NA_local, size_t NF
     const size_t bytes = NA_local * NF * 3 * sizeof(float);
     rc = own_xyz_buffer(ctx, bytes);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->d_xyz, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // chunks of atoms on the copy stream, growing 64 MB ... 1 GB: the autocorrelation path starts on the first chunk while
+    // the rest is still crossing PCIe (release_xyz above has synchronised both streams, so nothing reads the buffer any more)
+    const size_t row = NF * 3 * sizeof(float);
+    size_t nac = std::max<size_t>(1, ((size_t)64 << 20) / row);
+    const size_t nac_max = std::max<size_t>(1, ((size_t)1024 << 20) / row);
+    for (size_t a0 = 0, na = 0; a0 < NA_local; a0 += na, nac = std::min(2 * nac, nac_max)) {
+        na = std::min(nac, NA_local - a0);
+        sgpu_ctx::Chunk c{a0, na, nullptr};
+        CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+        cudaError_t e = cudaMemcpyAsync(ctx->d_xyz + a0 * NF * 3, xyz + a0 * NF * 3, na * row, cudaMemcpyHostToDevice,
+                                        ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c.ready, ctx->copy_stream);
+        ctx->chunks.push_back(c);
+        if (e != cudaSuccess) {
+            drop_chunks(ctx);
+            return fail(ctx, SGPU_ECUDA, std::string("sgpu_stage_atoms: ") + cudaGetErrorString(e));
+        }
+    }
     ctx->mode = 2;
     ctx->NF = NF;
     ctx->NFt = NF;
@@ -1525,19 +1572,41 @@ int sgpu_compute_self_vectors_partial(sgpu_ctx *ctx, const double *qvecs, size_t
     if (dsp_type == SGPU_DSP_AUTOCORRELATE) {
         // fused path: timelines are generated, transformed and reduced inside the SM (selffused.cu)
         const SelfPlan &sp = ctx->splan;
-        rc = set_atoms_layout(ctx, sp.split ? sp.R : 0);  // the split path reads sub-sequences of frames: keep them contiguous
-        if (rc) return rc;
+        // freshly staged atoms still arriving in chunks (sgpu_stage_atoms): every chunk is brought into the layout the path
+        // wants and evaluated as soon as it has landed, the copy of the next ones runs underneath
+        const bool chunked = !ctx->chunks.empty() && ctx->own_xyz && ctx->atoms_dec_R == 0;
+        if (!chunked) {
+            rc = set_atoms_layout(ctx, sp.split ? sp.R : 0);  // the split path reads sub-sequences of frames: keep them contiguous
+            if (rc) return rc;
+        }
         size_t atoms_per_batch = std::max<size_t>(1, ((size_t)256 << 20) / (NM * (size_t)sp.R * sizeof(double2)));
         atoms_per_batch = std::min(atoms_per_batch, ctx->NA);
         rc = ensure_work(ctx, std::max(self_work_bytes(&sp, atoms_per_batch * NM), corr_work_bytes(&ctx->plan, 1)));
         if (rc) return rc;
         CK(cudaMemsetAsync(d_partial, 0, partial_len(ctx, dsp_type) * sizeof(double), ctx->stream));
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        for (size_t n0 = 0; n0 < ctx->NA; n0 += atoms_per_batch) {
-            const size_t nn = std::min(atoms_per_batch, ctx->NA - n0);
-            ctx->launches += self_power_accumulate(&sp, ctx->d_xyz, ctx->d_b, ctx->d_qs, NM, n0, nn, ctx->d_work, d_partial,
-                                                   d_partial + sp.L, ctx->atoms_dec_R == sp.R && sp.split ? 1 : 0, ctx->stream);
-            CK(cudaGetLastError());
+        std::vector<sgpu_ctx::Chunk> spans;
+        if (chunked) spans = ctx->chunks;
+        else spans.push_back(sgpu_ctx::Chunk{0, ctx->NA, nullptr});
+        const int dec = chunked ? (sp.split ? 1 : 0) : (ctx->atoms_dec_R == sp.R && sp.split ? 1 : 0);
+        for (auto &c : spans) {
+            if (c.ready) {
+                CK(cudaStreamWaitEvent(ctx->stream, c.ready, 0));
+                if (sp.split) {
+                    rc = decimate_rows(ctx, c.f0, c.nf, sp.R);
+                    if (rc) return rc;
+                }
+            }
+            for (size_t n0 = c.f0; n0 < c.f0 + c.nf; n0 += atoms_per_batch) {
+                const size_t nn = std::min(atoms_per_batch, c.f0 + c.nf - n0);
+                ctx->launches += self_power_accumulate(&sp, ctx->d_xyz, ctx->d_b, ctx->d_qs, NM, n0, nn, ctx->d_work, d_partial,
+                                                       d_partial + sp.L, dec, ctx->stream);
+                CK(cudaGetLastError());
+            }
+        }
+        if (chunked) {
+            drop_chunks(ctx);
+            ctx->atoms_dec_R = sp.split ? sp.R : 0;
         }
     } else {
     rc = set_atoms_layout(ctx, 0);
