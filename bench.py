@@ -1129,7 +1129,7 @@ def bench_streamed_self(env, args):
     return line
 
 
-MP_BATCH = 8  # |q| values per pass of the batched multipole kernel (MPSphereScatterDevice::runner batches them)
+MP_BATCH = 8  # |q| values per pass of the batched multipole kernel (MPSphereScatterDevice::runner batches as many)
 
 
 def mp_flop_per_atom_frame_q(L, nmom, Q=MP_BATCH):
@@ -1292,7 +1292,7 @@ def bench_mpsphere(env, args):
                "h2d_bytes_per_step": int(NF * a_cnt * 12 + MP_BATCH * a_cnt * 8 + NM * 16),
                "d2h_bytes_per_step": int(MP_BATCH * (NF * 16 + 32)), "ms_per_step": 1e3 * e2e_s / e2e_steps,
                "note": "every rank re-stages its atoms of all frames from pinned host memory every step (chunked async H2D), "
-                       "converts them to (r, phi, theta) on the device, uploads the factors of the 8 |q| and reads fqt/fq/fq2 back"}
+                       "converts them to (r, phi, theta) on the device, uploads the factors of the pass's |q| and reads fqt/fq/fq2 back"}
 
     cpu_baseline = None
     parity = None
@@ -1333,7 +1333,7 @@ def bench_mpsphere(env, args):
                        "cache": f"inputs ({NF * NA * 12 / 1e9:.1f} GB coordinates) larger than L2"},
             "fqt_wall_time_s_all_q": ms_max / args.steps * 1e-3 * (len(qls) / MP_BATCH),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None, "kernel": "multipole_gemm_kernel<8>",
+                         "frac": achieved / fp64_peak, "traffic": None, "kernel": f"multipole_gemm_kernel<{MP_BATCH}>",
                          "kernel_share_of_step": amp_ms_max / ms_max, "algorithmic_flop_per_eval": flop_eval,
                          "executed_fp64_flop_per_eval": (3.0 * 231 + 36.0 * 21 + MP_BATCH * (4.0 * 21 + 4.0 * 231)) / (MP_BATCH * NM)
                          if L == 20 else None,

@@ -1182,7 +1182,8 @@ void MPSphereScatterDevice::compute() {
 }
 
 void MPSphereScatterDevice::runner() {
-    const size_t BATCH = 8;
+    const size_t BATCH = 8;  // |q| values per pass of the batched multipole kernel (multipole_batch_max, multipole.cu; 16 per
+                             // pass measured 3 % faster on config 4: not worth a second instantiation)
     while (status() == 0) {
         const size_t nq = std::min(BATCH, vectors_.size() - current_vector_);
         timer_.start("sd:compute");
