@@ -13,6 +13,7 @@
 // Reduction over atoms: warp shuffle tree per (l,m), accumulated in per-warp shared memory, combined in
 // a fixed order (no atomics).
 #include "kernels.hpp"
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -215,6 +216,9 @@ __global__ void multipole_assemble_kernel(const double2 *__restrict__ part, int 
 // Two CTAs of 256 threads per SM (128 registers each, half the shared memory each) rather than one of 512: the table phase
 // of a tile is a bundle of serial chains (latency bound), the product phase streams shared memory into DFMAs (throughput
 // bound) -- two independent CTAs let one phase run under the other instead of alternating behind the same barriers.
+// Measured on config 4 (pass of 8 |q|, 16 frames, largest tile that fits): 19.6 ms against 19.9 ms for one 512-thread CTA.
+// 16 |q| per pass does not pay: 39.8 ms (the Legendre tables are ~1/20 of a pass; the Bessel ladders and the product scale
+// with the |q| count, and the larger B table shrinks the tile).
 constexpr int MG_CTAS_PER_SM = 2;
 constexpr int MG_THREADS = 512 / MG_CTAS_PER_SM;
 constexpr int MG_GROUPS = MG_THREADS / 256;  // thread groups of the product phase, A / MG_GROUPS atoms of a tile each
@@ -613,19 +617,15 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
         auto smem_of = [&](int A) {
             return ((size_t)2 * A * NP + (size_t)A * (Q * L1 + 2) + 2 * A * 5 + 2 * L1 + 2 * NP) * sizeof(double) + NP * sizeof(int);
         };
-        // tile size: the table phase runs (L1 + Q) * A serial-chain tasks on MG_THREADS threads in whole rounds; take the A
-        // (even, shared memory <= 200 KB) that fills its rounds best, the larger one on ties (fewer barriers per atom)
+        // tile size: the largest even A (even keeps the double2 tables behind sB 16-byte aligned) whose tables fit the shared
+        // memory of a CTA and whose (L1 + Q) * A table tasks take at most MG_ROUNDS rounds of the MG_THREADS threads.  Measured
+        // on config 4 (Q = 8, two CTAs per SM): A = 8 / 12 / 16 / 20 -> 29.4 / 22.0 / 20.2 / 19.6 ms per pass of 16 frames: the
+        // two barriers per tile weigh more than a partly filled last round of table tasks
         int A = 2;
-        double best = 0.0;
-        for (int c = 2; c <= MG_A_MAX; c += 2) {  // even: keeps the double2 tables behind sB 16-byte aligned, and MG_GROUPS | c
+        for (int c = 2; c <= MG_A_MAX; c += 2) {
             if (smem_of(c) > MG_SMEM_CAP) break;
-            const int tasks = (L1 + Q) * c, rounds = (tasks + MG_THREADS - 1) / MG_THREADS;
-            if (rounds > MG_ROUNDS) break;
-            const double eff = (double)tasks / ((double)rounds * MG_THREADS);
-            if (eff >= best - 1e-12) {
-                best = eff;
-                A = c;
-            }
+            if (((L1 + Q) * c + MG_THREADS - 1) / MG_THREADS > MG_ROUNDS) break;
+            A = c;
         }
         const size_t per_tiles = ((per + A - 1) / A) * A;  // splits start on tile boundaries
         cudaFuncSetAttribute(multipole_gemm_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MG_SMEM_CAP);

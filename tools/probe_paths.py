@@ -42,12 +42,13 @@ if which in ("all", "mp", "mpbatch"):
         print(f"mpsphere |q|={ql}: {NA} atoms x {NF} frames x {len(mom)} moments: {dt*1e3:.1f} ms (amp {ctx.last_amplitude_ms():.1f} ms) -> "
               f"{NA*NF*len(mom)/dt:.3e} moment-evals/s; cfg4 (1000 frames x 200 |q|) would take {dt/NF*1000*200:.0f} s")
 
-    ql8 = np.linspace(0.01, 0.5, 8)
+    nq8 = int(os.environ.get("MP_NQ", 8))
+    ql8 = np.linspace(0.01, 0.5, nq8)
     for it in range(2):
         ctx.synchronize(); t0 = time.time()
         ctx.compute_mpsphere_batch(ql8, mom, dsp="square")
         dt = time.time() - t0
-    print(f"mpsphere batch of 8 |q|: {dt*1e3:.1f} ms -> {8*NA*NF*len(mom)/dt:.3e} moment-evals/s; cfg4 would take {dt/NF*1000*200/8:.0f} s")
+    print(f"mpsphere batch of {nq8} |q|: {dt*1e3:.1f} ms -> {nq8*NA*NF*len(mom)/dt:.3e} moment-evals/s; cfg4 would take {dt/NF*1000*200/nq8:.0f} s")
 
 if which in ("all", "mpcyl"):
     # multipole cylinder (K6) on a config-4 shaped slice: 1M atoms, moments (0,0) + (l, 0..3) for l <= L
