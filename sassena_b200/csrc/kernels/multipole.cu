@@ -217,8 +217,8 @@ __global__ void multipole_assemble_kernel(const double2 *__restrict__ part, int 
 // of a tile is a bundle of serial chains (latency bound), the product phase streams shared memory into DFMAs (throughput
 // bound) -- two independent CTAs let one phase run under the other instead of alternating behind the same barriers.
 // Measured on config 4 (pass of 8 |q|, 16 frames, largest tile that fits): 19.6 ms against 19.9 ms for one 512-thread CTA.
-// 16 |q| per pass does not pay: 39.8 ms (the Legendre tables are ~1/20 of a pass; the Bessel ladders and the product scale
-// with the |q| count, and the larger B table shrinks the tile).
+// 16 |q| per pass does not pay: 39.8 ms against 2 x 19.9 ms (the larger B table shrinks the tile and the accumulators of 16
+// |q| leave no registers for loads in flight).
 constexpr int MG_CTAS_PER_SM = 2;
 constexpr int MG_THREADS = 512 / MG_CTAS_PER_SM;
 constexpr int MG_GROUPS = MG_THREADS / 256;  // thread groups of the product phase, A / MG_GROUPS atoms of a tile each
