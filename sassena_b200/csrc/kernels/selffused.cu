@@ -421,7 +421,8 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft12_kernel(
     // source and destination are congruent and the body moves as 16-byte cp.async; returns mis (0 for the gather).
     // Every WARP fetches exactly the frames it evaluates in pass 1 (rows 256 n1 + 32 warp .. + 32, i.e. the 16-byte chunks
     // 192 n1 + 24 warp + lane, lane < 24, plus one more when the rows straddle chunk boundaries), so the arrival of the
-    // coordinates is a warp-local matter (cp.async.wait_group + __syncwarp) and needs no CTA barrier.
+    // coordinates is a warp-local matter (cp.async.wait_group + __syncwarp) and needs no CTA barrier.  (Reads of pass 1
+    // beyond the sub-sequence's last frame are redirected to a frame of the warp's own first row; their values are discarded.)
     const int lane = tid & 31;
     const int gl = 96 * (tid >> 5) + 4 * lane;
     auto prefetch = [&](const float *p, int r) -> int {
@@ -436,12 +437,16 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft12_kernel(
 #pragma unroll
                 for (int n1 = 0; n1 < 8; n1++) {
                     const int gi = gl + 768 * n1;
-                    if (gi >= mis && gi + 4 <= g_end) {
+                    // this warp's floats of the row: shifted indices [lo, hi); a chunk that straddles lo or hi (the first and
+                    // the last of the row when the sub-sequence is not 16-byte aligned) is copied float by float, its other
+                    // floats belong to the neighbouring warp, which copies them itself: no byte is written twice
+                    const int lo = gi - 4 * lane + mis, hi = min(lo + 96, g_end);
+                    if (gi >= lo && gi + 4 <= hi) {
                         cp_async16(&cbuf[gi], &pa[gi]);
-                    } else if (gi < g_end) {  // the first and the last chunk of the sub-sequence
+                    } else if (gi < hi) {
 #pragma unroll 1
                         for (int i = 0; i < 4; i++)
-                            if (gi + i >= mis && gi + i < g_end) cp_async4(&cbuf[gi + i], &pa[gi + i]);
+                            if (gi + i >= lo && gi + i < hi) cp_async4(&cbuf[gi + i], &pa[gi + i]);
                     }
                 }
             }
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft12_kernel(
         if (rows == 8) {
 #pragma unroll
             for (int n1 = 0; n1 < 8; n1++) {
-                const int mm = tid + 256 * n1, mc = min(mm, Mr - 1);
+                const int mm = tid + 256 * n1, mc = mm < Mr ? mm : tid;  // dummy: a frame of this warp's own (Mr >= 1024)
                 const double cx = (double)cb[3 * mc], cy = (double)cb[3 * mc + 1], cz = (double)cb[3 * mc + 2];
                 double2 v;
                 sincos_qt(fma(cz, qz, fma(cy, qy, cx * qx)), v.y, v.x);
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(SF_THREADS, 2) self_split_fft12_kernel(
                 const int mm = tid + 256 * n1;
                 double2 v = make_double2(0.0, 0.0);
                 if (n1 < rows) {
-                    const int mc = min(mm, Mr - 1);
+                    const int mc = mm < Mr ? mm : tid;
                     const double cx = (double)cb[3 * mc], cy = (double)cb[3 * mc + 1], cz = (double)cb[3 * mc + 2];
                     sincos_qt(fma(cz, qz, fma(cy, qy, cx * qx)), v.y, v.x);
                     if (mm >= Mr) v = make_double2(0.0, 0.0);
