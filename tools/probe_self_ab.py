@@ -18,10 +18,9 @@ d = c0.device_alloc(NA * NF * 12)
 c0.synth_trajectory(d, NF, 30000, 70.0, 0.05, 3, layout=1, NA_out=NA)
 xa = np.empty((NA, NF, 3), dtype=np.float32); c0.memcpy_d2h(xa, d); c0.device_free(d); c0.close()
 for v in variants:
-    os.environ.pop("SASSENA_SELF_SPLIT_V1", None)
     os.environ["SASSENA_SELF_PATH"] = "fused" if v == "fused" else "split"
     if v == "v1":
-        os.environ["SASSENA_SELF_SPLIT_V1"] = "1"
+        raise SystemExit("v1 (the first design of kernel A) was removed; see profiles/r02_self_split_v3_ncu_summary.txt")
     ctx = sassena_b200.ScatterContext(0)
     ctx.stage_atoms(xa)
     ctx.set_factors(synth.factors(NA))

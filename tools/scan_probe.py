@@ -1,5 +1,6 @@
-"""Throughput of the |q|-scan amplitude kernel vs the per-|q| kernel on a C3-shaped sample (run on the GPU box).
-SASSENA_SCAN_VARIANT selects the pass size: 0 -> 16, 1 -> 32, 2 -> 24, 3 -> 8 with two directions per warp."""
+"""Throughput of the |q|-scan amplitude kernels vs the per-|q| kernel K1 on a C3-shaped sample, and the deviation of every |q|
+of the scan from K1 (run on the GPU box).  ROUNDED=1: the reference's float-rounded scan (corrected kernels;
+SASSENA_SCAN_FP64_CORR=1 keeps the first-order sums in FP64), VARB=1: |q|-dependent factors; NA / NF / NM / NQ override the shape."""
 import os
 import sys
 import time
