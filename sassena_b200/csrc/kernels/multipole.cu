@@ -230,38 +230,56 @@ constexpr int MG_A_MAX = 64;    // atoms per tile: chosen per launch (mg_pick_ti
 // one Legendre/azimuth column: col[pair_l(l,m)] = Pbar_lm(theta) (cos m phi, sin m phi), l = m..lmax, col = sY + a*NP.
 // cAB[pair(lmax,m,m) + l - m] = (A_lm, B_lm) of the three-term recurrence; the pair index advances by l per step
 // (pair_l(l,m) = l(l+1)/2 + m), the first two terms are peeled so that the loop body is branch-free.
-__device__ __forceinline__ void mg_column(int m, int lmax, double ct, double st, double c1, double s1,
-                                          const double *__restrict__ cK, const double *__restrict__ cM1,
-                                          const double2 *__restrict__ cAB, double2 *__restrict__ col) {
+// TWO atoms per call (geo = r, ct, st, c1, s1 per atom; columns col0, col1): the recurrence is a serial chain of ~25 cycles per
+// step, two independent chains share the coefficient loads and the loop and fill each other's latency.
+__device__ __forceinline__ void mg_column2(int m, int lmax, const double *__restrict__ g0, const double *__restrict__ g1,
+                                           const double *__restrict__ cK, const double *__restrict__ cM1,
+                                           const double2 *__restrict__ cAB, double2 *__restrict__ col0,
+                                           double2 *__restrict__ col1) {
+    const double ct0 = g0[1], st0 = g0[2], ct1 = g1[1], st1 = g1[2];
     // st^m and (c1 + i s1)^m by binary powering (short dependency chain)
-    double pw = 1.0, base = st, cm = 1.0, sm = 0.0, rc = c1, rs = s1;
+    double pw0 = 1.0, b0 = st0, cm0 = 1.0, sm0 = 0.0, rc0 = g0[3], rs0 = g0[4];
+    double pw1 = 1.0, b1 = st1, cm1 = 1.0, sm1 = 0.0, rc1 = g1[3], rs1 = g1[4];
     for (int e = m; e; e >>= 1) {
         if (e & 1) {
-            pw *= base;
-            const double t = cm * rc - sm * rs;
-            sm = fma(sm, rc, cm * rs);
-            cm = t;
+            pw0 *= b0;
+            pw1 *= b1;
+            const double t0 = cm0 * rc0 - sm0 * rs0, t1 = cm1 * rc1 - sm1 * rs1;
+            sm0 = fma(sm0, rc0, cm0 * rs0);
+            sm1 = fma(sm1, rc1, cm1 * rs1);
+            cm0 = t0;
+            cm1 = t1;
         }
-        base *= base;
-        const double t = rc * rc - rs * rs;
-        rs = 2.0 * rc * rs;
-        rc = t;
+        b0 *= b0;
+        b1 *= b1;
+        const double t0 = rc0 * rc0 - rs0 * rs0, t1 = rc1 * rc1 - rs1 * rs1;
+        rs0 = 2.0 * rc0 * rs0;
+        rs1 = 2.0 * rc1 * rs1;
+        rc0 = t0;
+        rc1 = t1;
     }
-    const double pmm = cK[m] * pw;
+    const double k = cK[m];
+    const double pmm0 = k * pw0, pmm1 = k * pw1;
     int idx = mp_pair_l(m, m);
-    col[idx] = make_double2(pmm * cm, pmm * sm);
+    col0[idx] = make_double2(pmm0 * cm0, pmm0 * sm0);
+    col1[idx] = make_double2(pmm1 * cm1, pmm1 * sm1);
     if (m == lmax) return;
-    double p2 = pmm, p1 = cM1[m] * ct * pmm;
+    const double k1 = cM1[m];
+    double p20 = pmm0, p10 = k1 * ct0 * pmm0, p21 = pmm1, p11 = k1 * ct1 * pmm1;
     idx += m + 1;
-    col[idx] = make_double2(p1 * cm, p1 * sm);
+    col0[idx] = make_double2(p10 * cm0, p10 * sm0);
+    col1[idx] = make_double2(p11 * cm1, p11 * sm1);
     const double2 *ab = cAB + (mp_pair(lmax, m, m) - m);  // ab[l]
     for (int l = m + 2; l <= lmax; l++) {
         const double2 c = ab[l];
-        const double pl = c.x * fma(ct, p1, -c.y * p2);
-        p2 = p1;
-        p1 = pl;
+        const double pl0 = c.x * fma(ct0, p10, -c.y * p20), pl1 = c.x * fma(ct1, p11, -c.y * p21);
+        p20 = p10;
+        p10 = pl0;
+        p21 = p11;
+        p11 = pl1;
         idx += l;
-        col[idx] = make_double2(pl * cm, pl * sm);
+        col0[idx] = make_double2(pl0 * cm0, pl0 * sm0);
+        col1[idx] = make_double2(pl1 * cm1, pl1 * sm1);
     }
 }
 
@@ -275,7 +293,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
     const int L1 = lmax + 1;
     const int NP = mp_npairs(lmax);
     double2 *sY = reinterpret_cast<double2 *>(smem);              // [MG_A][NP]
-    double *sB = smem + (size_t)2 * MG_A * NP;                    // [MG_A][L1][Q]  (q fastest: one LDS.128 = two |q|)
+    double *sB = smem + (size_t)2 * MG_A * NP;                    // [MG_A][Q/2][L1][2]: pairs of |q|, l fastest (see below)
     const int BS = L1 * Q + 2;                                    // per-atom stride of sB, padded against bank conflicts
     double *sGeo = sB + (size_t)MG_A * BS;                        // [2][MG_A][5]: r, ct, st, c1, s1 (double-buffered)
     double *sTab = sGeo + 2 * MG_A * 5;                               // recurrence tables: cM1[L1] cK[L1] (cA, cB)[NP]
@@ -305,13 +323,25 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
                         // around to a second round land on threads that finished early
     const int grp = tid >> 8, tp = tid & 255;
 
-    // this thread's table tasks (the same for every tile): id = tid + k*512 -> (atom a, row)
+    // this thread's table tasks (the same for every tile).  Bessel ladders (one per (|q|, atom), the longest chains) come first,
+    // then the Legendre columns, long ones first, TWO atoms per task; odd rounds run over the threads backwards so that the
+    // threads that drew the short tasks of one round take the next round's.  row < NK: column m = row of atoms a, a + 1;
+    // row >= NK: ladder of |q| row - NK for atom a.
+    const int AH = MG_A >> 1, nBes = Q * MG_A, nTask = nBes + NK * AH;
     int task_a[MG_ROUNDS], task_row[MG_ROUNDS];
 #pragma unroll
     for (int k = 0; k < MG_ROUNDS; k++) {
-        const int id = tid + k * MG_THREADS;
-        task_row[k] = (id < (NK + Q) * MG_A) ? id / MG_A : -1;
-        task_a[k] = id % MG_A;
+        const int id = ((k & 1) ? (MG_THREADS - 1 - tid) : tid) + k * MG_THREADS;
+        if (id < nBes) {
+            task_row[k] = NK + id / MG_A;
+            task_a[k] = id % MG_A;
+        } else if (id < nTask) {
+            task_row[k] = (id - nBes) / AH;
+            task_a[k] = 2 * ((id - nBes) % AH);
+        } else {
+            task_row[k] = -1;
+            task_a[k] = 0;
+        }
     }
 
     double2 acc[Q];
@@ -359,12 +389,15 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
             if (task_row[k] < 0) break;
             const int a = task_a[k], row = task_row[k];
             if (row < NK) {
-                const double ct = geo[a * 5 + 1], st = geo[a * 5 + 2], c1 = geo[a * 5 + 3], s1 = geo[a * 5 + 4];
-                mg_column(lmax - row, lmax, ct, st, c1, s1, cK, cM1, cAB, sY + (size_t)a * NP);
+                mg_column2(row, lmax, geo + a * 5, geo + (a + 1) * 5, cK, cM1, cAB, sY + (size_t)a * NP, sY + (size_t)(a + 1) * NP);
             } else {
                 const int q = row - NK;
                 const size_t atom = base + a;
-                double *J = sB + (size_t)a * BS + q;  // element l at J[l * Q]
+                // B table of an atom: [Q/2][L1] pairs (q, q+1), l fastest -- the product phase's warp reads the pair of ONE or
+                // two neighbouring l, i.e. one 128-byte line per LDS.128 (with q fastest the two l were 8 Q bytes apart: two
+                // wavefronts per load, 14 per warp and atom against 8 SM-cycles of DFMA issue).  Element l of this |q| at J[l * JS].
+                constexpr int JS = (Q >= 2) ? 2 : 1;
+                double *J = sB + (size_t)a * BS + ((Q >= 2) ? (size_t)(q >> 1) * (2 * L1) + (q & 1) : 0);
                 double bq = 0.0;
                 if (atom < a_end && q0 + q < NQ) bq = __ldg(&b[(size_t)(q0 + q) * b_stride + atom]);
                 const double ql = (q0 + q < NQ) ? __ldg(&qlens[q0 + q]) : 0.0;
@@ -381,7 +414,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
                             term *= x2 * __ldg(&cS[l * MP_SERIES_TERMS + k]);
                             sum += term;
                         }
-                        J[l * Q] = pref * sum;
+                        J[l * JS] = pref * sum;
                     }
                 } else {
                     double sn, cs;
@@ -394,14 +427,14 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
                     if (x >= (double)lmax) {
                         double jm = j0, jc = j1;
                         J[0] = bq * j0;
-                        if (lmax >= 1) J[Q] = bq * j1;
+                        if (lmax >= 1) J[JS] = bq * j1;
                         double t = 3.0 * invx;
                         for (int l = 1; l < lmax; l++) {
                             const double jn = fma(t, jc, -jm);
                             t += step;
                             jm = jc;
                             jc = jn;
-                            J[(l + 1) * Q] = bq * jn;
+                            J[(l + 1) * JS] = bq * jn;
                         }
                     } else {
                         // Miller downward recurrence; the start index needed for 1e-14 grows only slowly with x
@@ -422,10 +455,10 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
                             t -= step;
                             jp = jc;
                             jc = jm;
-                            J[(k - 1) * Q] = jc;
+                            J[(k - 1) * JS] = jc;
                         }
                         const double scale = bq * ((fabs(j0) >= fabs(j1)) ? j0 / jc : j1 / jp);
-                        for (int l = 0; l <= lmax; l++) J[l * Q] *= scale;
+                        for (int l = 0; l <= lmax; l++) J[l * JS] *= scale;
                     }
                 }
             }
@@ -438,11 +471,11 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
             for (int aa = 0; aa < MG_APG; aa++) {
                 const int a = grp * MG_APG + aa;
                 const double2 y = sY[(size_t)a * NP + tp];
-                const double *Bp = sB + (size_t)a * BS + (size_t)l * Q;
+                const double *Bp = sB + (size_t)a * BS + (size_t)l * ((Q >= 2) ? 2 : 1);  // pair (q, q+1) at Bp + q L1
                 if (Q >= 2) {
 #pragma unroll
                     for (int q = 0; q < Q; q += 2) {
-                        const double2 b2 = *reinterpret_cast<const double2 *>(Bp + q);
+                        const double2 b2 = *reinterpret_cast<const double2 *>(Bp + q * L1);
                         acc[q].x = fma(b2.x, y.x, acc[q].x);
                         acc[q].y = fma(b2.x, y.y, acc[q].y);
                         acc[q + (Q >= 2 ? 1 : 0)].x = fma(b2.y, y.x, acc[q + (Q >= 2 ? 1 : 0)].x);
