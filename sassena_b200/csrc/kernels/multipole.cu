@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
 
     // this thread's table tasks (the same for every tile).  Bessel ladders (one per (|q|, atom), the longest chains) come first,
     // then the Legendre columns, long ones first, TWO atoms per task; odd rounds run over the threads backwards so that the
-    // threads that drew the short tasks of one round take the next round's.  row < NK: column m = row of atoms a, a + 1;
+    // threads that drew the short tasks of one round take the next round's.  row < NK: column m = row of atoms a and a + A/2
+    // (consecutive lanes -> consecutive atoms: the column stores stay bank-conflict free);
     // row >= NK: ladder of |q| row - NK for atom a.
     const int AH = MG_A >> 1, nBes = Q * MG_A, nTask = nBes + NK * AH;
     int task_a[MG_ROUNDS], task_row[MG_ROUNDS];
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
             task_a[k] = id % MG_A;
         } else if (id < nTask) {
             task_row[k] = (id - nBes) / AH;
-            task_a[k] = 2 * ((id - nBes) % AH);
+            task_a[k] = (id - nBes) % AH;
         } else {
             task_row[k] = -1;
             task_a[k] = 0;
@@ -389,7 +390,8 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
             if (task_row[k] < 0) break;
             const int a = task_a[k], row = task_row[k];
             if (row < NK) {
-                mg_column2(row, lmax, geo + a * 5, geo + (a + 1) * 5, cK, cM1, cAB, sY + (size_t)a * NP, sY + (size_t)(a + 1) * NP);
+                mg_column2(row, lmax, geo + a * 5, geo + (a + AH) * 5, cK, cM1, cAB, sY + (size_t)a * NP,
+                           sY + (size_t)(a + AH) * NP);
             } else {
                 const int q = row - NK;
                 const size_t atom = base + a;
@@ -467,6 +469,8 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
         if (idle_index >= 0 && base + MG_A < a_end) geometry(base + MG_A, cur ^ 1, idle_index, n_idle);
         if (tp < NP) {
             const int l = sL[tp];
+            // (a hand-pipelined version -- operands of atom aa + 1 loaded before the DFMAs of atom aa -- measured 6 % slower
+            // than what ptxas makes of the four-fold unrolled loop)
 #pragma unroll 4
             for (int aa = 0; aa < MG_APG; aa++) {
                 const int a = grp * MG_APG + aa;
