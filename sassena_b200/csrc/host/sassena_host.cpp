@@ -89,7 +89,8 @@ size_t ModAssignment::index(size_t i) const {
 }
 
 // decomposition_plan.cpp:29-66
-DecompositionParameters::DecompositionParameters(size_t NN, size_t NQ, size_t NAF, size_t NNpP, size_t elbytesize) {
+DecompositionParameters::DecompositionParameters(size_t NN, size_t NQ, size_t NAF, size_t NNpP, size_t elbytesize,
+                                                 bool replicated) {
     size_t NP = NN / NNpP;
     size_t NPused = NP;
     if (NQ < NP) NPused = NQ;
@@ -108,19 +109,21 @@ DecompositionParameters::DecompositionParameters(size_t NN, size_t NQ, size_t NA
     m_NAF = NAF;
     m_NP = NP;
     m_elbytesize = elbytesize;
-    m_nbytesize = NAFcycles * m_elbytesize;
+    // replicated: the device stages ALL frames on every rank of a partition (multipole devices, the vector-sharded coherent
+    // path), so a larger partition does not shrink a rank's share of the coordinates
+    m_nbytesize = (replicated ? NAF : NAFcycles) * m_elbytesize;
 }
 
 // decomposition_plan.cpp:69-156
 DecompositionPlan::DecompositionPlan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize,
-                                     const DecompositionLimits &lim) {
+                                     const DecompositionLimits &lim, bool replicated) {
     if (naf < 1) throw Error("No data to decompose.");
     if (nn < 1) throw Error("No nodes to decompose onto.");
     if (lim.partitions_automatic) {
         size_t npmax = naf;
         if (naf > nn) npmax = nn;
         for (size_t nnpp = npmax; nnpp >= 1; nnpp--) {
-            std::unique_ptr<DecompositionParameters> p_dp(new DecompositionParameters(nn, nq, naf, nnpp, elbytesize));
+            std::unique_ptr<DecompositionParameters> p_dp(new DecompositionParameters(nn, nq, naf, nnpp, elbytesize, replicated));
             if (p_dp->nbytesize() > nmaxbytesize) continue;
             if (!p_dp_best || p_dp->penalty() < p_dp_best->penalty()) p_dp_best = std::move(p_dp);
         }
@@ -133,7 +136,11 @@ DecompositionPlan::DecompositionPlan(size_t nn, size_t nq, size_t naf, size_t el
         if (nnpp > nn) nnpp = nn;
         if (lim.partitions_size > naf) nnpp = naf;
         if (nnpp < 1) nnpp = 1;
-        p_dp_best.reset(new DecompositionParameters(nn, nq, naf, nnpp, elbytesize));
+        p_dp_best.reset(new DecompositionParameters(nn, nq, naf, nnpp, elbytesize, replicated));
+        // a manual partition size is not searched: say up front what the stager would say after reading the trajectory
+        if (replicated && p_dp_best->nbytesize() > nmaxbytesize)
+            throw Error("Insufficient Buffer size for coordinates (limits.memory.data): this device stages all frames on every "
+                        "rank. Requested (bytes): " + std::to_string(p_dp_best->nbytesize()));
     }
     if (utilization() < lim.utilization) {
         p_dp_best.reset();
@@ -1296,7 +1303,11 @@ IScatterDevice *ScatterDeviceFactory::create(std::shared_ptr<ICommunicator> scat
     // every rank evaluates the (deterministic) plan; the reference computes it on rank 0 and broadcasts (:95-102)
     // a self run whose atoms stream through the GPU in waves is not constrained by the coordinate budget
     const size_t plan_limit = (stype == "self" && params.limits.stage_stream) ? (size_t)-1 : params.limits.stage_memory_data;
-    DecompositionPlan dplan(NN, NQ, NAF, ELBYTESIZE, plan_limit, params.limits.decomposition);
+    // multipole devices and the vector-sharded coherent path keep every frame on every rank of a partition: the plan must
+    // not count on a larger partition to fit the coordinate budget (it would pass here and fail at stage time)
+    const bool replicated = stype == "all" && (params.scattering.orientation_type == "multipole" ||
+                                               params.limits.coherent_sharding == "vectors");
+    DecompositionPlan dplan(NN, NQ, NAF, ELBYTESIZE, plan_limit, params.limits.decomposition, replicated);
     size_t partitions = dplan.partitions();
     size_t partitionsize = dplan.partitionsize();
 

@@ -142,7 +142,7 @@ class DecompositionParameters {
     size_t m_penalty, m_NAFcycles, m_NQcycles, m_NNpP, m_NN, m_NQ, m_NAF, m_NP, m_elbytesize, m_nbytesize;
 
    public:
-    DecompositionParameters(size_t NN, size_t NQ, size_t NAF, size_t NNpP, size_t elbytesize);
+    DecompositionParameters(size_t NN, size_t NQ, size_t NAF, size_t NNpP, size_t elbytesize, bool replicated = false);
     size_t penalty() const { return m_penalty; }
     size_t nbytesize() const { return m_nbytesize; }
     size_t get_NN() const { return m_NN; }
@@ -164,8 +164,9 @@ class DecompositionPlan {
     std::unique_ptr<DecompositionParameters> p_dp_best;
 
    public:
+    // replicated: every rank of a partition stages all frames (multipole devices, vector-sharded coherent path)
     DecompositionPlan(size_t nn, size_t nq, size_t naf, size_t elbytesize, size_t nmaxbytesize,
-                      const DecompositionLimits &lim = DecompositionLimits());
+                      const DecompositionLimits &lim = DecompositionLimits(), bool replicated = false);
     size_t partitions() const { return p_dp_best->get_NP(); }
     size_t partitionsize() const { return p_dp_best->get_NNpP(); }
     size_t penalty() const { return p_dp_best->penalty(); }

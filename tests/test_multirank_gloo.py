@@ -93,6 +93,17 @@ def test_multirank_matches_single_rank(oracle, tmp_path, world, case):
         assert abs(r["fq2"] - rfq2) < 1e-11 * abs(rfq2)
 
 
+def test_replicated_staging_is_budgeted_up_front(oracle, tmp_path):
+    """multipole devices keep every frame on every rank of a partition, so a partition of two does not halve a rank's share of
+    the coordinates: with limits.stage.memory.data at 3/4 of the trajectory the plan must refuse up front (it used to accept
+    NNPP = 2 on the frame-split byte count and fail in the stager after the trajectory had been read); the coherent device,
+    which does split the frames, runs under the same budget"""
+    for rank, has, recs, _ in _run(2, "mp_tight", tmp_path):
+        assert not has and "Automatic decomposition failed" in recs
+    gathered = _run(2, "all_frames_tight", tmp_path)
+    assert all(has for _, has, _, _ in gathered) and sum(len(recs) for _, _, recs, _ in gathered) == 5
+
+
 @pytest.mark.parametrize("case", ["all_manual2", "self_manual2"])
 def test_spare_rank_does_not_hang_the_partition_split(oracle, tmp_path, case):
     """three ranks, manual partitions of two: the plan uses ranks 0-1 and leaves rank 2 spare (the reference allows this,
