@@ -356,6 +356,11 @@ def run_ours(args):
             subs = {}
             plan = [("C3_equally_spaced", sub_args(args, "C3", mode="scan", no_cpu=True)),
                     ("C2", sub_args(args, "C2")), ("C4", sub_args(args, "C4")), ("C5s", sub_args(args, "C5s"))]
+            if env.world > 1 and args.shard == "frames":
+                # the north star's partition of the coherent path -- q-vectors (here: the directions of the scan) over the
+                # GPUs, every rank holding all frames, one all-reduce of the packed partials -- next to the headline's frame
+                # partition (scatter_device_factory.cpp:104-138 splits q-vectors between partitions, frames inside one)
+                plan.insert(1, ("C3_vector_sharded", sub_args(args, "C3", shard="vectors", no_cpu=True)))
             for name, a in plan:
                 if name in args.skip:
                     continue
