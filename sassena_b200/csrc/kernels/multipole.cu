@@ -283,6 +283,69 @@ __device__ __forceinline__ void mg_column2(int m, int lmax, const double *__rest
     }
 }
 
+// b * j_l(x), l = 0..lmax, into J[l * JS] (one Bessel ladder): 4-term series below x = 0.05, upward recurrence from (j0, j1) for
+// x >= lmax, Miller's downward recurrence started at lmax + 8 + 1.5 x otherwise (measured sufficient for 1e-14)
+__device__ __forceinline__ void mg_bessel1(double x, double bq, double *__restrict__ J, int JS, int lmax, int lstart_max,
+                                           const double *__restrict__ cS) {
+    if (x < 0.05) {
+        // power series, 4 terms are exact to 1e-16 below x = 0.05
+        const double x2 = x * x;
+        double pref = bq;
+        for (int l = 0; l <= lmax; l++) {
+            if (l > 0) pref *= x / (double)(2 * l + 1);
+            double term = 1.0, sum = 1.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                term *= x2 * __ldg(&cS[l * MP_SERIES_TERMS + k]);
+                sum += term;
+            }
+            J[l * JS] = pref * sum;
+        }
+        return;
+    }
+    double sn, cs;
+    sincos(x, &sn, &cs);
+    const double invx = 1.0 / x;
+    const double j0 = sn * invx;
+    const double j1 = (sn * invx - cs) * invx;
+    // (2l+1)/x advances by 2/x per step: one DADD instead of an int->double conversion and a DMUL
+    const double step = 2.0 * invx;
+    if (x >= (double)lmax) {
+        double jm = j0, jc = j1;
+        J[0] = bq * j0;
+        if (lmax >= 1) J[JS] = bq * j1;
+        double t = 3.0 * invx;
+        for (int l = 1; l < lmax; l++) {
+            const double jn = fma(t, jc, -jm);
+            t += step;
+            jm = jc;
+            jc = jn;
+            J[(l + 1) * JS] = bq * jn;
+        }
+    } else {
+        // two loops: above lmax + 1 nothing is kept, below every value is
+        const int lstart = min(lstart_max, lmax + 8 + (int)(1.5 * x));
+        double jp = 0.0, jc = 1e-300;
+        double t = (double)(2 * lstart + 1) * invx;
+        int k = lstart;
+        for (; k > lmax + 1; k--) {
+            const double jm = fma(t, jc, -jp);
+            t -= step;
+            jp = jc;
+            jc = jm;
+        }
+        for (; k >= 1; k--) {
+            const double jm = fma(t, jc, -jp);
+            t -= step;
+            jp = jc;
+            jc = jm;
+            J[(k - 1) * JS] = jc;
+        }
+        const double scale = bq * ((fabs(j0) >= fabs(j1)) ? j0 / jc : j1 / jp);
+        for (int l = 0; l <= lmax; l++) J[l * JS] *= scale;
+    }
+}
+
 template <int Q>
 __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_kernel(
     const float *__restrict__ sph, const double *__restrict__ b, size_t b_stride, const double *__restrict__ qlens,
@@ -393,76 +456,19 @@ __global__ void __launch_bounds__(MG_THREADS, MG_CTAS_PER_SM) multipole_gemm_ker
                 mg_column2(row, lmax, geo + a * 5, geo + (a + AH) * 5, cK, cM1, cAB, sY + (size_t)a * NP,
                            sY + (size_t)(a + AH) * NP);
             } else {
-                const int q = row - NK;
-                const size_t atom = base + a;
                 // B table of an atom: [Q/2][L1] pairs (q, q+1), l fastest -- the product phase's warp reads the pair of ONE or
                 // two neighbouring l, i.e. one 128-byte line per LDS.128 (with q fastest the two l were 8 Q bytes apart: two
                 // wavefronts per load, 14 per warp and atom against 8 SM-cycles of DFMA issue).  Element l of this |q| at J[l * JS].
+                // (Two ladders of neighbouring |q| side by side in one task -- two chains per loop -- measured 5 % slower on
+                // config 4: half as many, longer tasks lengthen the critical path of the table phase.)
+                const int q = row - NK;
+                const size_t atom = base + a;
                 constexpr int JS = (Q >= 2) ? 2 : 1;
                 double *J = sB + (size_t)a * BS + ((Q >= 2) ? (size_t)(q >> 1) * (2 * L1) + (q & 1) : 0);
                 double bq = 0.0;
                 if (atom < a_end && q0 + q < NQ) bq = __ldg(&b[(size_t)(q0 + q) * b_stride + atom]);
                 const double ql = (q0 + q < NQ) ? __ldg(&qlens[q0 + q]) : 0.0;
-                const double x = ql * geo[a * 5];
-                if (x < 0.05) {
-                    // power series, 4 terms are exact to 1e-16 below x = 0.05
-                    const double x2 = x * x;
-                    double pref = bq;
-                    for (int l = 0; l <= lmax; l++) {
-                        if (l > 0) pref *= x / (double)(2 * l + 1);
-                        double term = 1.0, sum = 1.0;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            term *= x2 * __ldg(&cS[l * MP_SERIES_TERMS + k]);
-                            sum += term;
-                        }
-                        J[l * JS] = pref * sum;
-                    }
-                } else {
-                    double sn, cs;
-                    sincos(x, &sn, &cs);
-                    const double invx = 1.0 / x;
-                    const double j0 = sn * invx;
-                    const double j1 = (sn * invx - cs) * invx;
-                    // (2l+1)/x advances by 2/x per step: one DADD instead of an int->double conversion and a DMUL
-                    const double step = 2.0 * invx;
-                    if (x >= (double)lmax) {
-                        double jm = j0, jc = j1;
-                        J[0] = bq * j0;
-                        if (lmax >= 1) J[JS] = bq * j1;
-                        double t = 3.0 * invx;
-                        for (int l = 1; l < lmax; l++) {
-                            const double jn = fma(t, jc, -jm);
-                            t += step;
-                            jm = jc;
-                            jc = jn;
-                            J[(l + 1) * JS] = bq * jn;
-                        }
-                    } else {
-                        // Miller downward recurrence; the start index needed for 1e-14 grows only slowly with x
-                        // (measured: lmax + 2 .. lmax + 19 for x < lmax), use lmax + 8 + 1.5 x.  Two loops: above lmax + 1
-                        // nothing is kept, below every value is.
-                        const int lstart = min(lstart_max, lmax + 8 + (int)(1.5 * x));
-                        double jp = 0.0, jc = 1e-300;
-                        double t = (double)(2 * lstart + 1) * invx;
-                        int k = lstart;
-                        for (; k > lmax + 1; k--) {
-                            const double jm = fma(t, jc, -jp);
-                            t -= step;
-                            jp = jc;
-                            jc = jm;
-                        }
-                        for (; k >= 1; k--) {
-                            const double jm = fma(t, jc, -jp);
-                            t -= step;
-                            jp = jc;
-                            jc = jm;
-                            J[(k - 1) * JS] = jc;
-                        }
-                        const double scale = bq * ((fabs(j0) >= fabs(j1)) ? j0 / jc : j1 / jp);
-                        for (int l = 0; l <= lmax; l++) J[l * JS] *= scale;
-                    }
-                }
+                mg_bessel1(ql * geo[a * 5], bq, J, JS, lmax, lstart_max, cS);
             }
         }
         __syncthreads();
@@ -655,13 +661,13 @@ int launch_multipole_sphere_batch(const float *d_sph, const double *d_b, size_t 
             return ((size_t)2 * A * NP + (size_t)A * (Q * L1 + 2) + 2 * A * 5 + 2 * L1 + 2 * NP) * sizeof(double) + NP * sizeof(int);
         };
         // tile size: the largest even A (even keeps the double2 tables behind sB 16-byte aligned) whose tables fit the shared
-        // memory of a CTA and whose (L1 + Q) * A table tasks take at most MG_ROUNDS rounds of the MG_THREADS threads.  Measured
+        // memory of a CTA and whose (Q + L1/2) * A table tasks (ladders, column pairs) take at most MG_ROUNDS rounds of the MG_THREADS threads.  Measured
         // on config 4 (Q = 8, two CTAs per SM): A = 8 / 12 / 16 / 20 -> 29.4 / 22.0 / 20.2 / 19.6 ms per pass of 16 frames: the
         // two barriers per tile weigh more than a partly filled last round of table tasks
         int A = 2;
         for (int c = 2; c <= MG_A_MAX; c += 2) {
             if (smem_of(c) > MG_SMEM_CAP) break;
-            if (((L1 + Q) * c + MG_THREADS - 1) / MG_THREADS > MG_ROUNDS) break;
+            if (((Q + (L1 + 1) / 2) * c + MG_THREADS - 1) / MG_THREADS > MG_ROUNDS) break;  // table tasks of a tile
             A = c;
         }
         const size_t per_tiles = ((per + A - 1) / A) * A;  // splits start on tile boundaries
