@@ -680,6 +680,41 @@ def ref_select_range(first, last):
     return _ref_sel(ref_params_lib().ref_select_range, C.c_size_t(first), C.c_size_t(last))
 
 
+
+# the reference's own rotational fit (src/sample/center_of_mass.cpp:53-157; oracle/ref_cofm_wrap.cpp).  Its SVD is LAPACK's dgesvd,
+# reached through the Boost.Bindings call: the shim binds the dgesvd of the OpenBLAS that scipy bundles (a real LAPACK).
+def _lapack_lib():
+    import glob
+    import scipy
+    c = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+    return c[0] if c else None
+
+
+def have_ref_fit():
+    return have_ref_params() and _lapack_lib() is not None and hasattr(ref_params_lib(), "ref_fit")
+
+
+def ref_mass_reg(label, mass):
+    ref_params_lib().ref_mass_reg(label.encode(), C.c_double(mass))
+
+
+def ref_fit(pdbfile, xyz, xyz_ref, sel_ref, sel_manip):
+    """Fit(atoms, cs, all, manip, cs_ref, ref): the frame xyz [natoms][3] fitted onto the sel_ref atoms of the frame xyz_ref
+    (mass-weighted least-squares rotation + translation onto the reference's centre of mass), the sel_manip atoms moved.
+    Returns (fitted coordinates [natoms][3], centre of mass of the sel_ref atoms of xyz before the fit)."""
+    os.environ["ORACLE_LAPACK_LIB"] = _lapack_lib()
+    a = _f64(np.asarray(xyz, dtype=np.float64).reshape(-1, 3))
+    r = _f64(np.asarray(xyz_ref, dtype=np.float64).reshape(-1, 3))
+    sr = np.ascontiguousarray(sel_ref, dtype=np.uint64)
+    sm = np.ascontiguousarray(sel_manip, dtype=np.uint64)
+    out = np.zeros_like(a)
+    com = np.zeros(3)
+    ref_params_lib().ref_fit(str(pdbfile).encode(), _p(a, C.c_double), _p(r, C.c_double), C.c_size_t(len(a)),
+                             sr.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(len(sr)),
+                             sm.ctypes.data_as(C.POINTER(C.c_size_t)), C.c_size_t(len(sm)), _p(out, C.c_double), _p(com, C.c_double))
+    return out, com
+
+
 def ref_frames_read(format, file, first=0, last=0, last_set=False, stride=1):
     """the reference's own DCD / PDB / XTC / TRR frameset (frames.cpp; generate_index + trim_index + read_frame) -> float64
     [nframes][natoms][3]"""

@@ -1,1 +1,2 @@
-/* boost/numeric/ublas/vector.hpp — empty SHIM (included, unused by the code built here) */
+/* boost/numeric/ublas/vector.hpp — SHIM: the dense vector lives in the matrix shim */
+#include <boost/numeric/ublas/matrix.hpp>

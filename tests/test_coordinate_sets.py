@@ -340,3 +340,38 @@ def test_walkers_pinned_to_reference_build(oracle):
         host.motion_transforms("wobble", 3)
     with pytest.raises(host.HostError, match="radius size for local brownian"):
         host.motion_transforms("localbrownian", 3, displace=2.0, radius=1.0)
+
+
+def _rotfit_case(tmp_path, kind, ref_sel, NA=16, NF=6):
+    extra = f"""<alignments><alignment><type>{kind}</type><selection>{ref_sel}</selection><order>post</order>
+         <reference><type>frame</type><frame>0</frame><selection>{ref_sel}</selection></reference></alignment></alignments>"""
+    return job_frames(tmp_path, extra, NA=NA, NF=NF)
+
+
+def test_rotational_fit_pinned_to_reference_build(tmp_path, oracle):
+    """fitrottrans / fitrot against the REFERENCE's own Fit (src/sample/center_of_mass.cpp:53-157 compiled where it lies into
+    oracle/_ref/libparams_ref.so: mass-weighted correlation kernel, LAPACK dgesvd through its Boost.Bindings call -- here the
+    OpenBLAS that scipy bundles --, determinant correction, write-back).  The product computes the same rotation with Horn's
+    quaternion form; both are narrowed to float by the stager, so they agree to a float ulp.  tests/golden/ref_rotfit.npz holds
+    the reference build's output for the case below (tests/golden/make_ref_golden.py); live where the reference is present."""
+    import os
+    from test_control_plane import REF_DB_NAMES
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_rotfit.npz"))
+    for kind in ("fitrottrans", "fitrot"):
+        for sel_name, sel in (("system", np.arange(16)), ("front", np.arange(10))):
+            d = tmp_path / f"{kind}_{sel_name}"
+            d.mkdir()
+            job, fr, xyz, names = _rotfit_case(d, kind, sel_name)
+            assert np.array_equal(xyz, g["xyz"])
+            want = g[f"{kind}_{sel_name}"]
+            # prefix selections only: the reference writes cs_redcopy[atom index] back (in bounds and right only then, DESIGN 7)
+            assert np.max(np.abs(fr - want)) < 2e-6, (kind, sel_name, np.max(np.abs(fr - want)))
+            if oracle.have_ref_fit():
+                for el, rx in REF_DB_NAMES.items():
+                    oracle.ref_sample_name_reg(el, rx)
+                    oracle.ref_mass_reg(el, MASS[el])
+                for f in range(xyz.shape[0]):
+                    fit, pc = oracle.ref_fit(str(d / "sample.pdb"), xyz[f], xyz[0], sel, sel)
+                    if kind == "fitrot":  # the reference adds the old centre back after the fit (coordinate_sets.cpp:282-286)
+                        fit[sel] = fit[sel] + pc
+                    assert np.array_equal(fit.astype(np.float32), want[f]), (kind, sel_name, f)
