@@ -6,7 +6,11 @@ libhdf5 / h5py do not exist in this image, so the container code (csrc/host/h5mi
   2. the WRITER is then checked through that reader (values, extents, max extents, chunk shapes, meta strings), on the
      structural points a libhdf5 reader relies on (signatures, end-of-file address, B-tree node fan-out, sorted links),
      and byte-for-byte against the superblock / heap / symbol-node conventions seen in the real file.
-The chunk B-tree and extendible dataspaces cannot be cross-read by libhdf5 here; DESIGN.md says so."""
+  3. a SECOND, independent reader (tests/h5_independent.py: pure Python, written from the format specification, no code shared
+     with h5mini) is checked against the same libhdf5-written file and then reads what h5mini writes -- chunked, extendible
+     datasets with one-, two- and three-level chunk B-trees, fresh and resumed files: two implementations of the specification
+     have to agree on every byte they dereference.
+The chunk B-tree and extendible dataspaces cannot be cross-read by libhdf5 itself here; DESIGN.md says so."""
 import os
 import struct
 
@@ -211,3 +215,46 @@ def test_interrupted_run_is_recovered_from_the_row_journal(tmp_path, oracle):
     for row, i in enumerate(order):
         assert np.allclose(got["fqt"][row], full["fqt"][i], rtol=1e-13, atol=0) and np.isclose(got["fq2"][row], full["fq2"][i])
     assert not os.path.exists(str(sig) + ".d/rows.journal")
+
+
+def test_independent_reader_decodes_the_libhdf5_file():
+    import h5_independent as hi
+    d, lay = hi.read(_matlab_file(), with_layout=True)
+    assert list(d) == ["testdouble"] and d["testdouble"].shape == (9, 1)
+    assert np.array_equal(d["testdouble"][:, 0], np.pi / 4 * np.arange(9))
+    assert lay["testdouble"] == {"maxdims": None, "chunk": None}
+
+
+@pytest.mark.parametrize("n,NF,chunksize", [(0, 5, 10000), (1, 1, 10000), (7, 100, 10000), (50, 37, 16), (200, 3, 2), (3, 25, 10),
+                                            (5000, 4, 2)])
+def test_independent_reader_reads_what_h5mini_writes(tmp_path, n, NF, chunksize):
+    """the writer's files through the independent reader: same names, values, extents, unlimited dimensions and chunk shapes as
+    through h5mini's own reader.  (5000, 4, 2): 10 000 chunks of fqt under a three-level chunk B-tree (fan-out 64)."""
+    import h5_independent as hi
+    q, fqt, fq, fq2 = _signal(n, NF, seed=3)
+    p = tmp_path / "signal.h5"
+    host.write_signal_h5(p, q, fqt, fq, fq2, chunksize=chunksize, rawconfig="<root/>\n", config="<root/>", database="<database/>")
+    d, lay = hi.read(p, with_layout=True)
+    own, own_lay = host.read_h5(p, with_layout=True)
+    assert sorted(d) == sorted(own)
+    for k in ("qvectors", "fqt", "fq0", "fq", "fq2"):
+        assert np.array_equal(d[k], own[k]) and d[k].shape == own[k].shape
+        assert lay[k]["maxdims"] == own_lay[k]["maxdims"] and lay[k]["chunk"] == own_lay[k]["chunk"]
+    assert np.array_equal(d["qvectors"], q.reshape(n, 3)) and np.array_equal(d["fqt"][..., 0] + 1j * d["fqt"][..., 1], fqt)
+    assert np.array_equal(d["fq"][:, 0] + 1j * d["fq"][:, 1], fq) and np.array_equal(d["fq0"][:, 0] + 1j * d["fq0"][:, 1], fqt[:, 0])
+    assert d["meta/rawconfig"].tobytes() == b"<root/>\n"
+    assert d["meta/config"].tobytes().rstrip(b"\0") == b"<root/>" and d["meta/database"].tobytes().rstrip(b"\0") == b"<database/>"
+    f = hi.File(p)
+    assert f.eof == os.path.getsize(p) and (f.leaf_k, f.internal_k) == (4, 16)  # group K as libhdf5's defaults
+
+
+def test_independent_reader_reads_a_resumed_file(tmp_path):
+    """rows appended to an existing file (H5Dset_extent + hyperslab writes in the reference, file_writer_service.cpp:314-484)"""
+    import h5_independent as hi
+    q, fqt, fq, fq2 = _signal(90, 6, seed=5)
+    p = tmp_path / "signal.h5"
+    assert host.write_signal_h5(p, q[:40], fqt[:40], fq[:40], fq2[:40], chunksize=4) == 40
+    assert host.write_signal_h5(p, q[40:], fqt[40:], fq[40:], fq2[40:], chunksize=4, resume=True) == 90
+    d = hi.read(p)
+    assert d["qvectors"].shape == (90, 3) and np.array_equal(d["qvectors"], q)
+    assert np.array_equal(d["fqt"][..., 0] + 1j * d["fqt"][..., 1], fqt)
