@@ -581,6 +581,24 @@ def bench_coherent(env, args):
                   "fq_rel_err": float(abs(fq - rfq) / abs(rfqt[0])), "tolerance": 1e-9,
                   "vs": ("the reference's own AllVectorsScatterDevice (oracle/_ref build)" if cpu_reference_kind() == "reference"
                          else "oracle") + f" on the CPU sample, |q| index {nmid} of the scan"}
+        if scan:
+            # every |q| of the scan, not only the sampled one: the scan kernel's amplitudes (recurrences, and for float-rounded
+            # scans the first / second order corrections, part of them in FP32) against the general kernel K1, which evaluates
+            # one FP64 sincos per (atom, frame, q-vector) as the reference does
+            a_scan = torch.empty(NQ * NM_s * NF_s * 2, dtype=torch.float64, device=dev)
+            a_one = torch.empty(NM_s * NF_s * 2, dtype=torch.float64, device=dev)
+            ctx.all_vectors_scan_amplitudes(u[:NM_s], qls, a_scan.data_ptr())
+            worst, where = 0.0, 0
+            for n in range(NQ):
+                ctx.all_vectors_amplitudes(float(qls[n]) * u[:NM_s], a_one.data_ptr())
+                ctx.synchronize()
+                torch.cuda.synchronize()
+                d = float((a_scan.view(NQ, -1)[n] - a_one).abs().max() / a_one.abs().max())
+                if d > worst:
+                    worst, where = d, n
+            parity["scan_vs_per_q_kernel_max_rel_diff"] = worst
+            parity["scan_vs_per_q_kernel_worst_q_index"] = where
+            del a_scan, a_one
         stage_resident()
 
     if rank == 0:
