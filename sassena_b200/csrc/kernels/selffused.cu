@@ -32,6 +32,7 @@ namespace {
 
 constexpr int SF_THREADS = 256;
 constexpr int SF_MAX_LOG2N = 12;  // N <= 4096 (64 KB of shared memory per CTA)
+constexpr int SF_2S_THREADS = 64;  // positions per CTA of the two-stage combine kernel (see there)
 
 __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -885,33 +886,50 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_ring_kernel(con
 //     X[c + R1 d] = sum_b w_R2^{b d} ( w_R^{b c} sum_a z[R2 a + b] w_R1^{a c} )
 // in place in the thread's R registers (R1^2 R2 + R1 R2^2 complex multiply-adds instead of R^2).  The power accumulators and
 // the weights live in shared memory as thread-private columns [k2][tid].
-template <int R1, int R2>
-__global__ void __launch_bounds__(SF_THREADS) self_split_combine_2s_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
+// THREADS positions per CTA.  The kernel keeps R weights and R power accumulators per position in shared memory (24 R bytes per
+// thread) and holds a timeline's R inputs in registers, so a CTA alternates between a burst of loads and arithmetic; with 256
+// threads only ONE such CTA fits an SM and nothing covers its load latency (captured at R = 25: 483 us for 1.6 GB = 3.3 TB/s,
+// long-scoreboard stalls 45 % of the samples).  CTAs of 64 threads put several independent ones on an SM, and the next
+// timeline's inputs are prefetched with cp.async under the arithmetic.
+template <int R1, int R2, int THREADS>
+__global__ void __launch_bounds__(THREADS) self_split_combine_2s_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
                                                                            size_t tl_first,
                                                                            const double2 *__restrict__ What2,
                                                                            double *__restrict__ Ppart2,
                                                                            double2 *__restrict__ a_part) {
     constexpr int R = R1 * R2;
     extern __shared__ double2 sm3[];
-    double2 *wh = sm3;                                                   // [R][256]
-    double *acc = reinterpret_cast<double *>(wh + R * SF_THREADS);       // [R][256]
-    __shared__ double2 red[2][SF_THREADS / 32];
+    double2 *wh = sm3;               // [R][THREADS] weights
+    double2 *ring = wh + R * THREADS;  // [R][THREADS] inputs of the next timeline (thread-private columns)
+    double acc[R];                   // power accumulators of this position, registers
+    __shared__ double2 red[2][THREADS / 32];
     const int c_ = blockIdx.x, C = gridDim.x;
     const size_t g = blockIdx.y, G = gridDim.y;
     const int tid = threadIdx.x;
-    const int pos = c_ * SF_THREADS + tid;
-#pragma unroll 1
+    const int pos = c_ * THREADS + tid;
+#pragma unroll
     for (int k2 = 0; k2 < R; k2++) {
-        acc[k2 * SF_THREADS + tid] = 0.0;
-        wh[k2 * SF_THREADS + tid] = __ldg(&What2[(size_t)k2 * N + pos]);
+        acc[k2] = 0.0;
+        wh[k2 * THREADS + tid] = __ldg(&What2[(size_t)k2 * N + pos]);
     }
     const size_t per = (ntl + G - 1) / G;
     const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
+    // the inputs of the NEXT timeline are in flight as 16-byte cp.async into thread-private columns of shared memory (no
+    // barrier: a thread reads only what it copied itself) while this timeline's R values are transformed
+    auto prefetch = [&](size_t t) {
+        if (t < t_end) {
+#pragma unroll
+            for (int r = 0; r < R; r++) cp_async16(&ring[r * THREADS + tid], &Zt[(t * R + r) * (size_t)N + pos]);
+        }
+        cp_async_commit();
+    };
+    prefetch(t_begin);
     int buf = 0;
     for (size_t t = t_begin; t < t_end; t++, buf ^= 1) {
+        cp_async_wait<0>();
         double2 z[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) z[r] = Zt[(t * R + r) * (size_t)N + pos];
+        for (int r = 0; r < R; r++) z[r] = ring[r * THREADS + tid];
         // stage 1: R1-point DFT over a for every b, then the twiddle w_R^{b c}
 #pragma unroll
         for (int bb = 0; bb < R2; bb++) {
@@ -941,6 +959,7 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_2s_kernel(const
 #pragma unroll
             for (int c = 0; c < R1; c++) z[R2 * c + bb] = y[c];  // Y_b[c] stored at slot R2 c + b
         }
+        prefetch(t + 1);  // stage 1 has consumed every input: the ring column is free (its loads have completed)
         // stage 2: R2-point DFT over b for every c; output k2 = c + R1 d
         double2 ap = make_double2(0.0, 0.0);
 #pragma unroll
@@ -962,8 +981,8 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_2s_kernel(const
                 }
                 const int k2 = c + R1 * d;
                 const double pw = fma(xr, xr, xi * xi);
-                acc[k2 * SF_THREADS + tid] += pw;
-                const double2 w = wh[k2 * SF_THREADS + tid];
+                acc[k2] += pw;
+                const double2 w = wh[k2 * THREADS + tid];
                 ap.x = fma(pw, w.x, ap.x);
                 ap.y = fma(pw, w.y, ap.y);
             }
@@ -978,26 +997,26 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_2s_kernel(const
         if (tid == 0) {
             double2 sum = red[buf][0];
 #pragma unroll
-            for (int w = 1; w < SF_THREADS / 32; w++) {
+            for (int w = 1; w < THREADS / 32; w++) {
                 sum.x += red[buf][w].x;
                 sum.y += red[buf][w].y;
             }
             a_part[(tl_first + t) * C + c_] = sum;
         }
     }
-#pragma unroll 1
-    for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2 * SF_THREADS + tid];
+#pragma unroll
+    for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2];
 }
 
 // Timeline groups (grid.y) of a combine kernel with C position slices: as many CTAs as are resident at once, rounded DOWN
 // to whole groups -- a few CTAs more than one wave would double (or, at one CTA per SM, add half to) the kernel's duration.
 // (The process drives one device; residency is cached per kernel instantiation.)
 template <typename Kernel>
-size_t resident_ctas(Kernel kernel, size_t smem) {
+size_t resident_ctas(Kernel kernel, size_t smem, int threads = SF_THREADS) {
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SF_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     return (size_t)per_sm * (size_t)sms;
 }
 inline size_t combine_groups(size_t resident, size_t C, size_t cap) { return std::max<size_t>(1, std::min(resident / C, cap)); }
@@ -1005,14 +1024,15 @@ inline size_t combine_groups(size_t resident, size_t C, size_t cap) { return std
 template <int R1, int R2>
 size_t launch_combine_2s(size_t C, size_t gcap, cudaStream_t st, const double2 *Zt, int N, size_t nt, size_t t0, const double2 *w2,
                          double *Ppart2, double2 *a_part) {
-    constexpr size_t smem = (size_t)R1 * R2 * SF_THREADS * (sizeof(double2) + sizeof(double));
+    constexpr int T = SF_2S_THREADS;
+    constexpr size_t smem = (size_t)R1 * R2 * T * 2 * sizeof(double2);  // weights + the prefetched inputs of the next timeline
     static size_t resident = 0;
     if (!resident) {
-        cudaFuncSetAttribute(self_split_combine_2s_kernel<R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        resident = resident_ctas(self_split_combine_2s_kernel<R1, R2>, smem);
+        cudaFuncSetAttribute(self_split_combine_2s_kernel<R1, R2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        resident = resident_ctas(self_split_combine_2s_kernel<R1, R2, T>, smem, T);
     }
     const size_t G = combine_groups(resident, C, gcap);
-    self_split_combine_2s_kernel<R1, R2><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+    self_split_combine_2s_kernel<R1, R2, T><<<dim3((unsigned)C, (unsigned)G), T, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
     return G;
 }
 
@@ -1293,7 +1313,7 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
         p->reg_combine = p->R <= 16 && !generic;
         p->two_stage = false;
         for (const SplitFactor &sf : kSplitFactors) p->two_stage = p->two_stage || (sf.R == p->R && !generic);
-        int S = 256;
+        int S = p->two_stage ? SF_2S_THREADS : 256;
         while (!p->reg_combine && !p->two_stage && S > 8 && (size_t)S * p->R > 2048) S >>= 1;
         if ((size_t)S > p->N) S = (int)p->N;
         p->S = S;
@@ -1354,7 +1374,9 @@ size_t split_batch(const SelfPlan *p, size_t ntl) {
     return std::max<size_t>(1, std::min(ntl, kSplitZBytes / per_tl));
 }
 size_t split_groups_b(const SelfPlan *p, size_t tb) {
-    size_t G = (2 * 148 + p->C - 1) / p->C;  // two combine CTAs per SM
+    // upper bound of the timeline groups (sizes the partial spectra): two combine CTAs per SM, the two-stage kernel's small
+    // CTAs up to seven
+    size_t G = ((p->two_stage ? 7 : 2) * 148 + p->C - 1) / p->C;
     if (G > tb) G = tb;
     return std::max<size_t>(G, 1);
 }
