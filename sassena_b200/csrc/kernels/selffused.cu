@@ -701,97 +701,16 @@ __global__ void __launch_bounds__(SF_THREADS) self_split_combine_kernel(const do
     }
 }
 
-// Register version for compile-time R: a thread owns one position, keeps its R inputs in registers and evaluates the R
+// Compile-time R (combine kernels below): a thread owns one position, keeps its R inputs in registers and evaluates the R
 // outputs with the twiddles exp(-2 pi i k / R) read as constant-bank operands (c_Wr, set at plan creation) -- no index
-// arithmetic and no shared-memory traffic for the matrix.  grid = (C, G) with S = 256 positions per CTA... S == blockDim.
+// arithmetic and no shared-memory traffic for the matrix.
 __constant__ double2 c_Wr[64];
 
-template <int R>
-__global__ void __launch_bounds__(SF_THREADS) self_split_combine_reg_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
-                                                                            size_t tl_first,
-                                                                            const double2 *__restrict__ What2,
-                                                                            double *__restrict__ Ppart2,
-                                                                            double2 *__restrict__ a_part) {
-    constexpr int SLOTS = 8;  // per-warp partial sums of 8 timelines are combined with one barrier
-    __shared__ double2 red[SLOTS][SF_THREADS / 32];
-    const int c = blockIdx.x, C = gridDim.x;
-    const size_t g = blockIdx.y, G = gridDim.y;
-    const int tid = threadIdx.x;
-    const int pos = c * SF_THREADS + tid;
-    double acc[R];
-    double2 wh[R];
-#pragma unroll
-    for (int k2 = 0; k2 < R; k2++) {
-        acc[k2] = 0.0;
-        wh[k2] = __ldg(&What2[(size_t)k2 * N + pos]);
-    }
-    const size_t per = (ntl + G - 1) / G;
-    const size_t t_begin = g * per, t_end = min(ntl, t_begin + per);
-    double2 z[R], zn[R];
-    if (t_begin < t_end) {
-#pragma unroll
-        for (int r = 0; r < R; r++) zn[r] = Zt[(t_begin * R + r) * (size_t)N + pos];
-    }
-    auto flush = [&](size_t t_first, int count) {  // block sums of `count` timelines starting at t_first
-        __syncthreads();
-        if (tid < count) {
-            double2 sum = red[tid][0];
-#pragma unroll
-            for (int w = 1; w < SF_THREADS / 32; w++) {
-                sum.x += red[tid][w].x;
-                sum.y += red[tid][w].y;
-            }
-            a_part[(tl_first + t_first + tid) * C + c] = sum;
-        }
-        __syncthreads();
-    };
-    int slot = 0;
-    for (size_t t = t_begin; t < t_end; t++) {
-#pragma unroll
-        for (int r = 0; r < R; r++) z[r] = zn[r];
-        if (t + 1 < t_end) {  // software prefetch of the next timeline's inputs
-#pragma unroll
-            for (int r = 0; r < R; r++) zn[r] = Zt[((t + 1) * R + r) * (size_t)N + pos];
-        }
-        double2 ap = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int k2 = 0; k2 < R; k2++) {
-            double xr = z[0].x, xi = z[0].y;
-#pragma unroll
-            for (int r = 1; r < R; r++) {
-                const int idx = (r * k2) % R;
-                if (idx == 0) {
-                    xr += z[r].x;
-                    xi += z[r].y;
-                } else {
-                    xr = fma(z[r].x, c_Wr[idx].x, fma(-z[r].y, c_Wr[idx].y, xr));
-                    xi = fma(z[r].x, c_Wr[idx].y, fma(z[r].y, c_Wr[idx].x, xi));
-                }
-            }
-            const double pw = fma(xr, xr, xi * xi);
-            acc[k2] += pw;
-            ap.x = fma(pw, wh[k2].x, ap.x);
-            ap.y = fma(pw, wh[k2].y, ap.y);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ap.x += __shfl_xor_sync(0xffffffffu, ap.x, o);
-            ap.y += __shfl_xor_sync(0xffffffffu, ap.y, o);
-        }
-        if ((tid & 31) == 0) red[slot][tid >> 5] = ap;
-        if (++slot == SLOTS) {
-            flush(t + 1 - SLOTS, SLOTS);
-            slot = 0;
-        }
-    }
-    if (slot) flush(t_end - slot, slot);
-#pragma unroll
-    for (int k2 = 0; k2 < R; k2++) Ppart2[(g * R + k2) * (size_t)N + pos] = acc[k2];
-}
-
-// Ring version of the register kernel for R <= 8: the inputs of the next D-1 timelines are in flight as 16-byte cp.async
-// into a shared-memory ring of thread-private columns [stage][r][tid] (a thread reads only what it copied itself, so the
-// ring needs no barrier); 3x the bytes in flight of the register prefetch above -- the kernel is HBM-latency bound.
+// R <= 8: one R-point DFT per position and timeline, grid = (C, G) with 256 positions per CTA.  The inputs of the next D-1
+// timelines are in flight as 16-byte cp.async into a shared-memory ring of thread-private columns [stage][r][tid] (a thread
+// reads only what it copied itself, so the ring needs no barrier) -- the kernel is HBM-latency bound and, with the ring, runs
+// at the HBM floor (R = 5: 248 us for 1.61 GB).  (A register-prefetch version served R = 9...16 until the two-stage kernel below
+// took them over: 465 / 516 us at R = 13 / 15, one 256-thread CTA per SM.)
 template <int R>
 __global__ void __launch_bounds__(SF_THREADS) self_split_combine_ring_kernel(const double2 *__restrict__ Zt, int N, size_t ntl,
                                                                              size_t tl_first,
@@ -1036,33 +955,27 @@ size_t launch_combine_2s(size_t C, size_t gcap, cudaStream_t st, const double2 *
     return G;
 }
 
-// compile-time R <= 16: ring kernel for R <= 8, register-prefetch kernel above that
+// compile-time R <= 8: ring kernel
 template <int R>
 size_t launch_combine_reg(size_t C, size_t gcap, cudaStream_t st, const double2 *Zt, int N, size_t nt, size_t t0, const double2 *w2,
                           double *Ppart2, double2 *a_part) {
+    static_assert(R <= 8, "R > 8 goes through the two-stage kernel");
     static size_t resident = 0;
-    if constexpr (R <= 8) {
-        constexpr size_t smem = (size_t)((R <= 6) ? 4 : 3) * R * SF_THREADS * sizeof(double2);
-        if (!resident) {
-            cudaFuncSetAttribute(self_split_combine_ring_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            resident = resident_ctas(self_split_combine_ring_kernel<R>, smem);
-        }
-        const size_t G = combine_groups(resident, C, gcap);
-        self_split_combine_ring_kernel<R><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
-        return G;
-    } else {
-        if (!resident) resident = resident_ctas(self_split_combine_reg_kernel<R>, 0);
-        const size_t G = combine_groups(resident, C, gcap);
-        self_split_combine_reg_kernel<R><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, 0, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
-        return G;
+    constexpr size_t smem = (size_t)((R <= 6) ? 4 : 3) * R * SF_THREADS * sizeof(double2);
+    if (!resident) {
+        cudaFuncSetAttribute(self_split_combine_ring_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        resident = resident_ctas(self_split_combine_ring_kernel<R>, smem);
     }
+    const size_t G = combine_groups(resident, C, gcap);
+    self_split_combine_ring_kernel<R><<<dim3((unsigned)C, (unsigned)G), SF_THREADS, smem, st>>>(Zt, N, nt, t0, w2, Ppart2, a_part);
+    return G;
 }
 
-// composite R the two-stage kernel is instantiated for: (R1, R2) with R1 <= R2, both <= 8, R <= 32
+// composite R the two-stage kernel is instantiated for: (R1, R2) with R1 <= R2, both <= 8, 9 <= R <= 32
 struct SplitFactor {
     int R, R1, R2;
 };
-constexpr SplitFactor kSplitFactors[] = {{18, 3, 6}, {20, 4, 5}, {21, 3, 7}, {24, 4, 6}, {25, 5, 5}, {28, 4, 7}, {30, 5, 6}, {32, 4, 8}};
+constexpr SplitFactor kSplitFactors[] = {{9, 3, 3}, {10, 2, 5}, {12, 3, 4}, {14, 2, 7}, {15, 3, 5}, {16, 4, 4}, {18, 3, 6}, {20, 4, 5}, {21, 3, 7}, {24, 4, 6}, {25, 5, 5}, {28, 4, 7}, {30, 5, 6}, {32, 4, 8}};
 
 // P[perm[i]] += sum_g Ppart2[g][i]   (split layout -> residue-major layout; perm is a bijection)
 __global__ void sf_reduce_ppart_perm_kernel(const double *__restrict__ Ppart, size_t G, size_t len, const int *__restrict__ perm,
@@ -1276,9 +1189,9 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
     p->N = (size_t)1 << log2N;
     p->R = (int)((need + p->N - 1) / p->N);
     if (p->R > 4096) return 1;  // NF > ~8e6 frames
-    // any L >= 2NF-1 yields the same correlation: between 17 and 32 round R up to a value the two-stage combine kernel
+    // any L >= 2NF-1 yields the same correlation: between 9 and 32 round R up to a value the two-stage combine kernel
     // of the split path is instantiated for (at most 2 more sub-transforms)
-    if (p->R > 16 && p->R <= 32 && !getenv("SASSENA_SELF_EXACT_R")) {
+    if (p->R > 8 && p->R <= 32 && !getenv("SASSENA_SELF_EXACT_R")) {
         for (const SplitFactor &sf : kSplitFactors)
             if (sf.R >= p->R) {
                 p->R = sf.R;
@@ -1310,7 +1223,7 @@ int self_plan_create(SelfPlan *p, size_t NF, cudaStream_t st, uint64_t *launches
     }
     if (p->split) {
         const bool generic = getenv("SASSENA_SELF_GENERIC_COMBINE") != nullptr;
-        p->reg_combine = p->R <= 16 && !generic;
+        p->reg_combine = p->R <= 8 && !generic;
         p->two_stage = false;
         for (const SplitFactor &sf : kSplitFactors) p->two_stage = p->two_stage || (sf.R == p->R && !generic);
         int S = p->two_stage ? SF_2S_THREADS : 256;
@@ -1441,8 +1354,7 @@ static int self_power_accumulate_split(const SelfPlan *p, const float *d_xyz_by_
         G = launch_combine_reg<RR>(p->C, G, st, Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part);            \
         break;
             switch (p->R) {
-                SF_RCASE(2) SF_RCASE(3) SF_RCASE(4) SF_RCASE(5) SF_RCASE(6) SF_RCASE(7) SF_RCASE(8) SF_RCASE(9) SF_RCASE(10)
-                SF_RCASE(11) SF_RCASE(12) SF_RCASE(13) SF_RCASE(14) SF_RCASE(15) SF_RCASE(16)
+                SF_RCASE(2) SF_RCASE(3) SF_RCASE(4) SF_RCASE(5) SF_RCASE(6) SF_RCASE(7) SF_RCASE(8)
                 default: break;
             }
 #undef SF_RCASE
@@ -1452,6 +1364,7 @@ static int self_power_accumulate_split(const SelfPlan *p, const float *d_xyz_by_
         G = launch_combine_2s<A, B>(p->C, G, st, Zt, (int)p->N, nt, t0, p->d_w2, Ppart2, a_part);           \
         break;
             switch (p->R) {
+                SF_2CASE(9, 3, 3) SF_2CASE(10, 2, 5) SF_2CASE(12, 3, 4) SF_2CASE(14, 2, 7) SF_2CASE(15, 3, 5) SF_2CASE(16, 4, 4)
                 SF_2CASE(18, 3, 6) SF_2CASE(20, 4, 5) SF_2CASE(21, 3, 7) SF_2CASE(24, 4, 6) SF_2CASE(25, 5, 5) SF_2CASE(28, 4, 7)
                 SF_2CASE(30, 5, 6) SF_2CASE(32, 4, 8)
                 default: break;

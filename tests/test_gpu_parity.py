@@ -163,14 +163,16 @@ def test_self_vectors_frame_counts(gpu_ctx, oracle, NF):
 
 
 @pytest.mark.parametrize("NF,NA,NM", [(2049, 2, 3), (3000, 3, 2), (4096, 1, 5), (4097, 3, 2), (5000, 7, 5), (6200, 2, 3),
-                                      (8193, 1, 1), (10000, 5, 40), (10000, 61, 7), (12289, 2, 3), (33000, 2, 2), (35000, 3, 3),
+                                      (8193, 1, 1), (10000, 5, 40), (10000, 61, 7), (12289, 2, 3), (18000, 2, 2), (20000, 2, 3),
+                                      (22000, 1, 2), (26000, 3, 1), (30000, 2, 2), (32768, 1, 2), (33000, 2, 2), (35000, 3, 3),
                                       (50000, 2, 3)])
 def test_self_vectors_split_path(oracle, monkeypatch, NF, NA, NM):
     """2NF-1 > 2*4096 (R >= 3): the split path -- every frame evaluated once, R decimated sub-FFTs per timeline, an
     R-point DFT across them, power spectrum permuted back to the residue-major layout -- against the oracle, forced with
     SASSENA_SELF_PATH=split (the library picks it from R = 5 on and the fused kernel below; both are checked).
     NF = 10000 is BASELINE config 2's timeline length (R = 5), NF = 50000 config 5's (R = 25, two-stage 5 x 5 combine);
-    33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18; 2049 / 3000 / 4096 are R = 2 (sub-sequences of 1025 ... 2048
+    33000 needs R = 17 and runs with R = 18 (3 x 6), 35000 R = 18; 18000 / 20000 / 30000 / 32768 are R = 9 (3 x 3), 10 (2 x 5),
+    15 (3 x 5) and 16 (4 x 4), 22000 needs 11 and runs with 12 (3 x 4), 26000 needs 13 and runs with 14 (2 x 7); 2049 / 3000 / 4096 are R = 2 (sub-sequences of 1025 ... 2048
     frames: the shortest and the longest a 4096-point sub-transform takes).  Kernel A deals the (timeline, r) pairs out over
     296 CTAs: 1 x 1 x 5 = 5 pairs leave most CTAs idle, 61 x 7 x 5 = 2135 give every CTA 7 or 8 with shares that begin and end
     in the middle of a timeline."""
