@@ -32,6 +32,16 @@ DCDFrameset::DCDFrameset(const std::string &fn) : filename_(fn) {
     if (!detect(fn)) throw Error("file '" + fn + "' appears to not be a DCD file. INT Magic failed");
     f_ = fopen(fn.c_str(), "rb");
     if (!f_) throw Error("cannot open '" + fn + "'");
+    try {
+        parse_header(fn);
+    } catch (...) {  // the destructor does not run for a constructor that throws
+        fclose(f_);
+        f_ = nullptr;
+        throw;
+    }
+}
+
+void DCDFrameset::parse_header(const std::string &fn) {
     // DCDHeader (frames.hpp:152-164): headsize, fingerprint, number_of_frames, dummy1, timesteps_between_frames,
     // buf1[24], size_of_timestep, flag_ext_block1, flag_ext_block2
     unsigned char hdr[56];
@@ -77,6 +87,13 @@ DCDFrameset::DCDFrameset(const std::string &fn) : filename_(fn) {
         block2_byte_offset = rel();
     }
     block_size_byte = rel();
+    // The reference trusts the header's frame count (frames.cpp:261-268) and reads stale data for frames the file does not
+    // hold; a count that is negative or larger than the file can hold is refused here, before the index is sized by it.
+    seek(f_, 0, SEEK_END, fn);
+    const int64_t file_size = (int64_t)ftello(f_);
+    if (nof < 0 || block_size_byte <= 0 || (int64_t)nof > (file_size - init_byte_pos) / block_size_byte)
+        throw Error("DCD header of '" + fn + "' announces " + std::to_string(nof) + " frames, the file holds " +
+                    std::to_string(block_size_byte > 0 ? (file_size - init_byte_pos) / block_size_byte : 0));
     // generate_index (frames.cpp:261-268)
     for (size_t i = 0; i < number_of_frames; ++i) frameset_index_.push_back((int64_t)i * block_size_byte + init_byte_pos);
     buf_.resize(number_of_atoms);

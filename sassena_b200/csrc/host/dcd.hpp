@@ -19,6 +19,7 @@ class DCDFrameset {
     int64_t block1_byte_offset = 0, x_byte_offset = 0, y_byte_offset = 0, z_byte_offset = 0, block2_byte_offset = 0;
     int32_t flag_ext_block1 = 0, flag_ext_block2 = 0;
     std::vector<float> buf_;
+    void parse_header(const std::string &fn);
 
    public:
     size_t number_of_frames = 0, number_of_atoms = 0;

@@ -400,14 +400,28 @@ struct Reader {
     explicit Reader(const std::vector<uint8_t> &img) : b(img) {}
 
     uint64_t get(uint64_t off, int n) const {  // absolute file offset
-        if (off + n > b.size()) throw Error("h5: read beyond the end of the file");
+        if (off > b.size() || (uint64_t)n > b.size() - off) throw Error("h5: read beyond the end of the file");
         uint64_t v = 0;
         for (int i = 0; i < n; i++) v |= (uint64_t)b[off + i] << (8 * i);
         return v;
     }
     uint64_t at(uint64_t addr) const { return base + addr; }  // file address -> absolute offset
+    // [off, off + n) lies inside the file (written so that a corrupt address near 2^64 cannot wrap around the test)
+    bool inside(uint64_t off, uint64_t n) const { return off <= b.size() && n <= b.size() - off; }
     void expect(uint64_t off, const char *sig) const {
-        if (off + 4 > b.size() || memcmp(&b[off], sig, 4) != 0) throw Error(std::string("h5: missing signature ") + sig);
+        if (!inside(off, 4) || memcmp(&b[off], sig, 4) != 0) throw Error(std::string("h5: missing signature ") + sig);
+    }
+    // bytes of an extent; a corrupt dataspace must not turn into an allocation of petabytes: chunked datasets may be
+    // sparser than their extent, so the bound is generous (64 x the file + 64 MiB), overflow is refused outright
+    uint64_t extent_bytes(const std::vector<uint64_t> &dims, uint64_t elem, const std::string &name) const {
+        const uint64_t cap = 64 * (uint64_t)b.size() + ((uint64_t)64 << 20);
+        uint64_t p = elem;
+        for (uint64_t x : dims) {
+            if (x != 0 && p > cap / x) throw Error("h5: dataset " + name + ": extent not plausible for a file of this size");
+            p *= x;
+        }
+        if (p > cap) throw Error("h5: dataset " + name + ": extent not plausible for a file of this size");
+        return p;
     }
 
     struct Msg {
@@ -449,17 +463,21 @@ struct Reader {
     }
 
     // symbol table entries of a group B-tree, in order
-    void group_entries(uint64_t bt_addr, uint64_t heap, std::vector<std::pair<std::string, uint64_t>> &out, int depth = 0) const {
+    // (a child sits exactly one level below its parent: a corrupt tree that points back into itself is refused instead of
+    // being walked 2^depth times)
+    void group_entries(uint64_t bt_addr, uint64_t heap, std::vector<std::pair<std::string, uint64_t>> &out, int depth = 0,
+                       int want_level = -1) const {
         if (depth > 32) throw Error("h5: group B-tree too deep");
         const uint64_t n = at(bt_addr);
         expect(n, "TREE");
         if (get(n + 4, 1) != 0) throw Error("h5: group B-tree node of the wrong type");
         const int level = (int)get(n + 5, 1);
+        if (want_level >= 0 && level != want_level) throw Error("h5: group B-tree levels are inconsistent");
         const size_t used = get(n + 6, 2);
         for (size_t i = 0; i < used; i++) {
             const uint64_t child = get(n + 24 + 8 + 16 * i, 8);
             if (level > 0) {
-                group_entries(child, heap, out, depth + 1);
+                group_entries(child, heap, out, depth + 1, level - 1);
                 continue;
             }
             const uint64_t s = at(child);
@@ -476,19 +494,20 @@ struct Reader {
         std::vector<uint64_t> offset;
         uint64_t nbytes, addr;
     };
-    void chunk_entries(uint64_t bt_addr, size_t nd, std::vector<ChunkLoc> &out, int depth = 0) const {
+    void chunk_entries(uint64_t bt_addr, size_t nd, std::vector<ChunkLoc> &out, int depth = 0, int want_level = -1) const {
         if (depth > 32) throw Error("h5: chunk B-tree too deep");
         const uint64_t n = at(bt_addr);
         expect(n, "TREE");
         if (get(n + 4, 1) != 1) throw Error("h5: chunk B-tree node of the wrong type");
         const int level = (int)get(n + 5, 1);
+        if (want_level >= 0 && level != want_level) throw Error("h5: chunk B-tree levels are inconsistent");
         const size_t used = get(n + 6, 2);
         const size_t keysize = 8 + 8 * nd;
         for (size_t i = 0; i < used; i++) {
             const uint64_t k = n + 24 + i * (keysize + 8);
             const uint64_t child = get(k + keysize, 8);
             if (level > 0) {
-                chunk_entries(child, nd, out, depth + 1);
+                chunk_entries(child, nd, out, depth + 1, level - 1);
                 continue;
             }
             if (get(k + 4, 4) != 0) throw Error("h5: filtered chunks are not supported");
@@ -538,7 +557,7 @@ struct Reader {
         }
         if (!have_space || !have_type || !have_layout) throw Error("h5: dataset " + name + ": incomplete object header");
         const size_t rank = ds.dims.size();
-        const uint64_t total = product(ds.dims) * elem;
+        const uint64_t total = extent_bytes(ds.dims, elem, name);
         std::vector<uint8_t> raw(total, 0);
         const int ver = (int)get(layout.off, 1);
         int cls;
@@ -576,7 +595,7 @@ struct Reader {
         }
         if (cls == 1) {
             if (addr != UNDEF && total) {
-                if (at(addr) + total > b.size()) throw Error("h5: dataset " + name + " extends beyond the file");
+                if (!inside(at(addr), total)) throw Error("h5: dataset " + name + " extends beyond the file");
                 memcpy(raw.data(), &b[at(addr)], total);
             }
         } else if (cls == 2) {
@@ -589,10 +608,10 @@ struct Reader {
                 stride[d - 1] = stride[d] * ds.dims[d];
                 cstride[d - 1] = cstride[d] * ds.chunk[d];
             }
-            const uint64_t chunk_bytes = product(ds.chunk) * elem;
+            const uint64_t chunk_bytes = extent_bytes(ds.chunk, elem, name);
             for (auto &c : chunks) {
                 if (c.nbytes != chunk_bytes) throw Error("h5: chunk of unexpected size in " + name);
-                if (at(c.addr) + chunk_bytes > b.size()) throw Error("h5: chunk beyond the end of the file");
+                if (!inside(at(c.addr), chunk_bytes)) throw Error("h5: chunk beyond the end of the file");
                 bool inside = rank > 0;
                 for (size_t d = 0; d < rank; d++) inside = inside && c.offset[d] < ds.dims[d];
                 if (!inside) continue;  // a chunk left over from a larger extent
@@ -630,6 +649,7 @@ struct Reader {
 
     Group group(const std::string &name, uint64_t bt, uint64_t heap, int depth) const {
         if (depth > 16) throw Error("h5: groups nested too deeply");
+        if (++objects_ > 100000) throw Error("h5: too many objects (a group that contains itself?)");
         Group g;
         g.name = name;
         std::vector<std::pair<std::string, uint64_t>> entries;
@@ -641,11 +661,14 @@ struct Reader {
                 if (m.type == MSG_SYMBOL_TABLE) st = &m;
             if (st)
                 g.groups.push_back(group(e.first, get(st->off, 8), get(st->off + 8, 8), depth + 1));
+            else if (++objects_ > 100000)
+                throw Error("h5: too many objects (a group that contains itself?)");
             else
                 g.datasets.push_back(dataset(e.first, msgs));
         }
         return g;
     }
+    mutable size_t objects_ = 0;
 };
 
 }  // namespace

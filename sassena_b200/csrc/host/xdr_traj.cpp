@@ -246,7 +246,7 @@ bool XTCFrameset::read_frame_nm(float *xyz, float *box, bool decode) {
     if (!file_.read_bytes(packed_.data(), (size_t)nbytes)) return false;
 
     uint32_t range[3];
-    for (int c = 0; c < 3; c++) range[c] = (uint32_t)(hi[c] - lo[c] + 1);
+    for (int c = 0; c < 3; c++) range[c] = (uint32_t)hi[c] - (uint32_t)lo[c] + 1u;  // modulo 2^32: no UB on a corrupt header
     int wide_bits[3] = {0, 0, 0}, large_bits = 0;
     if ((range[0] | range[1] | range[2]) > 0xffffffu) {
         for (int c = 0; c < 3; c++) wide_bits[c] = bits_for(range[c]);
@@ -269,7 +269,7 @@ bool XTCFrameset::read_frame_nm(float *xyz, float *box, bool decode) {
         } else {
             bs.take_triple(large_bits, range, cur);
         }
-        for (int c = 0; c < 3; c++) cur[c] += lo[c];
+        for (int c = 0; c < 3; c++) cur[c] = (int)((uint32_t)cur[c] + (uint32_t)lo[c]);
         atom++;
         int step_idx = 0;  // change of the small radix after this group: -1, 0, +1
         if (bs.take(1)) {
@@ -286,7 +286,7 @@ bool XTCFrameset::read_frame_nm(float *xyz, float *box, bool decode) {
             for (int k = 0; k < run; k += 3) {
                 int s[3];
                 bs.take_triple(smallidx, small_r, s);
-                for (int c = 0; c < 3; c++) s[c] += prev[c] - half;
+                for (int c = 0; c < 3; c++) s[c] = (int)((uint32_t)s[c] + (uint32_t)prev[c] - (uint32_t)half);
                 atom++;
                 emit(dst, s);
                 if (k == 0) emit(dst, cur);  // the first small atom was stored after the large one: it comes out first
@@ -332,19 +332,20 @@ bool TRRFrameset::read_header(Header &h) {
     for (int32_t *p : fields)
         if (!file_.read_i32(*p)) return false;
     // width of a real: from the first block that is present
-    int width = 0;
+    int64_t width = 0;
+    const int64_t per_atom = 3 * (int64_t)h.natoms;  // 64-bit: a corrupt atom count must not overflow
     if (h.box_size)
         width = h.box_size / 9;
     else if (h.natoms > 0 && h.x_size)
-        width = h.x_size / (h.natoms * 3);
+        width = h.x_size / per_atom;
     else if (h.natoms > 0 && h.v_size)
-        width = h.v_size / (h.natoms * 3);
+        width = h.v_size / per_atom;
     else if (h.natoms > 0 && h.f_size)
-        width = h.f_size / (h.natoms * 3);
+        width = h.f_size / per_atom;
     if (width != 4 && width != 8) return false;
     h.is_double = width == 8;
     if (!file_.read_i32(h.step) || !file_.read_i32(h.nre)) return false;
-    return file_.skip(2 * width);  // time, lambda
+    return file_.skip(2 * (int64_t)width);  // time, lambda
 }
 
 bool TRRFrameset::read_frame_nm(float *xyz, double *box, bool decode) {

@@ -20,7 +20,7 @@ def _lib():
 
 def _ck(rc):
     if rc:
-        raise HostError(_lib().sass_last_error().decode())
+        raise HostError(_lib().sass_last_error().decode(errors="replace"))
 
 
 def _ctxp(ctx):
@@ -76,7 +76,7 @@ def create_from_scans(scans):
     n = _lib().sass_create_from_scans(_dp(rows), len(rows), None, 0)
     if n == 0 and _lib().sass_last_error():
         if len(scans) > 3:
-            raise HostError(_lib().sass_last_error().decode())
+            raise HostError(_lib().sass_last_error().decode(errors="replace"))
     out = np.zeros((max(n, 1), 3))
     _lib().sass_create_from_scans(_dp(rows), len(rows), _dp(out), n)
     return out[:n]
@@ -479,7 +479,7 @@ def read_h5(path, with_layout=False):
     def _cb(user, name, kind, rank, dims, maxdims, chunk, data, nbytes):
         shape = tuple(int(dims[i]) for i in range(rank))
         raw = C.string_at(data, nbytes) if nbytes else b""
-        key = name.decode()
+        key = name.decode(errors="replace")
         if kind == 0:
             out[key] = np.frombuffer(raw, dtype=np.float64).reshape(shape).copy()
         elif kind == 1:

@@ -258,3 +258,50 @@ def test_independent_reader_reads_a_resumed_file(tmp_path):
     d = hi.read(p)
     assert d["qvectors"].shape == (90, 3) and np.array_equal(d["qvectors"], q)
     assert np.array_equal(d["fqt"][..., 0] + 1j * d["fqt"][..., 1], fqt)
+
+
+def test_reader_refuses_implausible_extents_and_cyclic_trees(tmp_path):
+    """A corrupt signal file must be refused, not turned into a petabyte allocation or an endless walk: dataspace
+    dimensions far beyond the file's size, addresses near 2^64 (which would wrap a naive bounds test) and a chunk B-tree
+    whose child pointer leads back to the node itself."""
+    rng = np.random.default_rng(3)
+    q = rng.standard_normal((6, 3))
+    c = lambda *sh: rng.standard_normal(sh) + 1j * rng.standard_normal(sh)  # noqa: E731
+    path = tmp_path / "signal.h5"
+    host.write_signal_h5(path, q, c(6, 5), c(6), c(6), chunksize=2)
+    raw = open(path, "rb").read()
+    good = host.read_h5(path)
+    assert good["fqt"].shape == (6, 5, 2)
+    # (1) blow up the first dimension of fqt's dataspace: find the dims (6, 5, 2) as three little-endian 64-bit words
+    import struct
+    pat = struct.pack("<3Q", 6, 5, 2)
+    at = raw.index(pat)
+    for huge in (2**40, 2**62, 2**64 - 1):
+        bad = tmp_path / "huge.h5"
+        bad.write_bytes(raw[:at] + struct.pack("<Q", huge) + raw[at + 8:])
+        with pytest.raises(host.HostError, match="not plausible|beyond"):
+            host.read_h5(bad)
+    # (2) a chunk B-tree node of level 1 whose children point back at itself
+    trees = [i for i in range(0, len(raw) - 8) if raw[i:i + 4] == b"TREE" and raw[i + 4] == 1]
+    assert trees
+    t = trees[0]
+    cyc = bytearray(raw)
+    cyc[t + 5] = 1  # level 1: children are nodes
+    nd = 4 if struct.unpack_from("<I", raw, t + 24)[0] == 2 * 5 * 2 * 8 else 3  # rank + 1: fqt's tree or fq's / fq2's / fq0's
+    keysize = 8 + 8 * nd
+    used = struct.unpack_from("<H", raw, t + 6)[0]
+    for i in range(used):
+        struct.pack_into("<Q", cyc, t + 24 + i * (keysize + 8) + keysize, t)
+    bad = tmp_path / "cycle.h5"
+    bad.write_bytes(bytes(cyc))
+    with pytest.raises(host.HostError, match="levels are inconsistent"):
+        host.read_h5(bad)
+    # (3) addresses near 2^64
+    # (every 8-byte word after the dataspace in turn; the point is only that no mutation crashes or hangs)
+    for off in range(at + 24, min(at + 400, len(raw) - 8), 8):
+        bad = tmp_path / "addr.h5"
+        bad.write_bytes(raw[:off] + struct.pack("<Q", 2**64 - 9) + raw[off + 8:])
+        try:
+            host.read_h5(bad)
+        except host.HostError:
+            pass

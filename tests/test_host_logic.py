@@ -363,3 +363,27 @@ def test_dcd_reader_handles_title_and_optional_blocks(tmp_path):
     d = host.DCDFile(p)
     assert (d.number_of_frames, d.number_of_atoms, d.has_unitcell) == (NF, NA, False)
     assert np.array_equal(d.read(), xyz)
+
+
+def test_dcd_header_frame_count_is_checked_against_the_file(tmp_path):
+    """The reference sizes its frame index by the header's count alone (frames.cpp:261-268); a count that is negative or
+    larger than the file can hold (a truncated or corrupt trajectory) is refused when the file is opened."""
+    import struct
+    from sassena_b200 import synth
+    xyz = synth.trajectory(5, 4, 20.0, 0.3, 6)
+    path = tmp_path / "traj.dcd"
+    host.write_dcd(path, xyz)
+    raw = bytearray(open(path, "rb").read())
+    for count in (6, 2**31 - 1, -1, -2**31):
+        bad = tmp_path / "count.dcd"
+        bad.write_bytes(bytes(raw[:8]) + struct.pack("<i", count) + bytes(raw[12:]))
+        with pytest.raises(host.HostError, match="announces"):
+            host.DCDFile(bad)
+    cut = tmp_path / "cut.dcd"  # the last frame is incomplete
+    cut.write_bytes(bytes(raw[:-10]))
+    with pytest.raises(host.HostError, match="announces 5 frames, the file holds 4"):
+        host.DCDFile(cut)
+    fewer = tmp_path / "fewer.dcd"  # a header that announces fewer frames than the file holds is taken at its word
+    fewer.write_bytes(bytes(raw[:8]) + struct.pack("<i", 3) + bytes(raw[12:]))
+    d = host.DCDFile(fewer)
+    assert d.number_of_frames == 3 and np.array_equal(d.read(), xyz[:3])
