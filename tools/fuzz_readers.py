@@ -1,4 +1,5 @@
-"""Mutation fuzzing of the file readers of the host layer (trajectories: DCD, XTC, TRR; signal files: HDF5 subset), meant to
+"""Mutation fuzzing of the file readers of the host layer (trajectories: DCD, XTC, TRR; signal files: HDF5 subset; the text
+inputs of a job: scatter.xml, db.xml, PDB structure, ndx selections), meant to
 run against the ASan + UBSan build (tools/asan_host.sh builds it; see tools/fuzz_readers.sh).  A mutated file must either read
 or raise host.HostError -- anything else (another exception, a sanitizer report, a crash, a hang) is a finding.
 
@@ -50,6 +51,81 @@ def read_traj(path, fmt):
         f.close()
 
 
+TOKENS = [b"<", b">", b"</", b"/>", b"&", b"&amp;", b"<!--", b"-->", b"<![CDATA[", b"]]>", b"\"", b"'", b"\0", b"-1", b"1e999", b"nan",
+          b"99999999999999999999", b"<scan>", b"</sample>", b"<xi:include href=\"scatter.xml\"/>", b"\n", b" " * 100]
+
+
+def mutate_text(data: bytes, rng) -> bytes:
+    b = bytearray(data)
+    kind = rng.integers(0, 5)
+    if kind == 0:
+        return bytes(b[:rng.integers(0, len(b))])
+    if kind == 1:
+        for _ in range(rng.integers(1, 6)):
+            b[rng.integers(0, len(b))] = rng.integers(0, 256)
+        return bytes(b)
+    if kind == 2:  # insert a token that means something to an XML / number / column parser
+        o = rng.integers(0, len(b))
+        return bytes(b[:o] + TOKENS[rng.integers(0, len(TOKENS))] + b[o:])
+    if kind == 3:  # delete a span
+        o = rng.integers(0, len(b))
+        return bytes(b[:o] + b[o + rng.integers(1, 40):])
+    o = rng.integers(0, len(b))  # duplicate a span
+    n = rng.integers(1, 200)
+    return bytes(b[:o + n] + b[o:])
+
+
+def fuzz_job(tmp, iters, rng):
+    """scatter.xml, db.xml, the PDB structure and an ndx selection file of a small job, one mutated at a time"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from test_control_plane import make_case, SCAN, ORIENT  # noqa: E402
+    d = os.path.join(tmp, "job")
+    os.makedirs(d)
+    extra = """<selections>
+      <selection><type>index</type><name>picked</name><index>3</index><index>5</index></selection>
+      <selection><type>range</type><name>tail</name><from>20</from><to>23</to></selection>
+      <selection><type>lexical</type><name>carbons</name><expression>carbon</expression></selection>
+      <selection><type>file</type><name>flagged</name><file>sel.pdb</file><format>pdb</format></selection>
+      <selection><type>file</type><file>groups.ndx</file><format>ndx</format><expression>grp.*</expression></selection>
+    </selections>
+    <motions><motion><type>linear</type><displace>0.5</displace><selection>picked</selection></motion></motions>
+    <alignments><alignment><type>center</type><selection>carbons</selection></alignment></alignments>"""
+    cfg, _, _ = make_case(d, scattering=SCAN + ORIENT, sample_extra=extra,
+                          background="<background><factor>0.1</factor></background>")
+    open(os.path.join(d, "sel.pdb"), "w").write(open(os.path.join(d, "sample.pdb")).read())
+    open(os.path.join(d, "groups.ndx"), "w").write("[ grpA ]\n1 2 3\n4\n[ other ]\n7 8\n[ grpB ]\n10 11\n")
+    findings = 0
+    for target in ("scatter.xml", "db.xml", "sample.pdb", "groups.ndx"):
+        path = os.path.join(d, target)
+        data = open(path, "rb").read()
+        ok = err = 0
+        t0 = time.time()
+        for i in range(iters):
+            with open(path, "wb") as fh:
+                fh.write(mutate_text(data, rng))
+            try:
+                job = host.Job(cfg)
+                try:
+                    q = job.qvectors()
+                    if len(q):
+                        job.factors(float(np.linalg.norm(q[0])))
+                    job.frames()
+                finally:
+                    job.close()
+                ok += 1
+            except host.HostError:
+                err += 1
+            except Exception as e:  # noqa: BLE001
+                findings += 1
+                keep = os.path.join(tmp, f"finding_job_{findings}_{target}")
+                os.replace(path, keep)
+                print(f"FINDING {type(e).__name__}: {e} -> {keep}", flush=True)
+        with open(path, "wb") as fh:
+            fh.write(data)
+        print(f"{target:24s} {iters} mutations: {ok} read, {err} rejected, {time.time() - t0:.1f} s", flush=True)
+    return findings
+
+
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
@@ -89,6 +165,7 @@ def main():
                 os.replace(m, keep)
                 print(f"FINDING {type(e).__name__}: {e} -> {keep}", flush=True)
         print(f"{os.path.basename(path):24s} {iters} mutations: {ok} read, {err} rejected, {time.time() - t0:.1f} s", flush=True)
+    findings += fuzz_job(tmp, iters, rng)
     print("findings:", findings)
     return 1 if findings else 0
 
