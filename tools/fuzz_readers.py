@@ -166,6 +166,9 @@ def main():
                 print(f"FINDING {type(e).__name__}: {e} -> {keep}", flush=True)
         print(f"{os.path.basename(path):24s} {iters} mutations: {ok} read, {err} rejected, {time.time() - t0:.1f} s", flush=True)
     findings += fuzz_job(tmp, iters, rng)
+    if not findings:  # the mutated files of a finding stay for inspection
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
     print("findings:", findings)
     return 1 if findings else 0
 
