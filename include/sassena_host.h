@@ -189,6 +189,12 @@ int sass_h5_write_signal(const char *path, size_t NF, size_t chunksize, int flag
  * (src/services/file_writer_service.cpp:44-171); complex values are trailing [2] = (re, im). */
 typedef struct sass_job sass_job;
 int sass_job_load(const char *config_file, sass_job **out);
+/* the same with the reference's command-line overwrite options (Params::options / overwrite_options,
+ * src/control/parameters.cpp:795-875): n (key, value) pairs applied after the configuration file has been read.  Keys:
+ * sample.structure.file, sample.structure.format, stager.target, stager.dump, stager.file, stager.format,
+ * scattering.signal.file, limits.computation.threads; any other key is an error ("unrecognised option"). */
+int sass_job_load_overwrite(const char *config_file, const char *const *keys, const char *const *values, size_t n,
+                            sass_job **out);
 void sass_job_free(sass_job *j);
 /* counts: all atoms of the structure, atoms of stager.target, frames, q-vectors */
 int sass_job_info(const sass_job *j, size_t *natoms, size_t *ntarget, size_t *nframes, size_t *nqvectors);
@@ -203,6 +209,10 @@ int sass_job_selection(const sass_job *j, const char *name, size_t *ids, size_t 
 const sass_params *sass_job_params(const sass_job *j);
 /* scattering.signal.file resolved against the configuration file's directory (parameters.cpp:41-54; default signal.h5) */
 const char *sass_job_signal_file(const sass_job *j);
+/* the value in effect (after the configuration file and the overwrite options; file names resolved) of sample.structure.file,
+ * sample.structure.format, stager.target, stager.dump ("true" / "false"), stager.file, stager.format, scattering.signal.file;
+ * NULL for any other key.  Borrowed, valid until sass_job_free. */
+const char *sass_job_option(const sass_job *j, const char *key);
 /* runs every q-vector; comm/backend NULL = single process / the in-library CUDA backend */
 int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
                  sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap);

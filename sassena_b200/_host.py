@@ -115,8 +115,11 @@ SIGNATURES = {
                                        C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p, c_size_p]),
     "sass_init_subvectors": (C.c_size_t, [C.c_void_p, c_double_p, c_double_p, C.c_size_t]),
     "sass_job_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sass_job_load_overwrite": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t,
+                                          C.POINTER(C.c_void_p)]),
     "sass_job_free": (None, [C.c_void_p]),
     "sass_job_signal_file": (C.c_char_p, [C.c_void_p]),
+    "sass_job_option": (C.c_char_p, [C.c_void_p, C.c_char_p]),
     "sass_job_info": (C.c_int, [C.c_void_p, c_size_p, c_size_p, c_size_p, c_size_p]),
     "sass_job_qvectors": (C.c_int, [C.c_void_p, c_double_p]),
     "sass_job_factors": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),

@@ -1,5 +1,7 @@
 """`python -m sassena_b200.cli --config scatter.xml` — the reference executable's command line for the GPU path
-(reference src/main/sassena.cpp:200-260: --config, and the scattering.signal.file override).
+(reference src/main/sassena.cpp:200-260 and Params::options, src/control/parameters.cpp:795-836: --config and the overwrite
+options --sample.structure.file / .format, --stager.target / .dump / .file / .format, --scattering.signal.file,
+--limits.computation.threads).
 
 One process per GPU: run under `python -m torch.distributed.run --nproc-per-node N -m sassena_b200.cli ...` for N GPUs.
 The signal goes to scattering.signal.file (default signal.h5) as an HDF5 file in the reference's layout
@@ -10,12 +12,25 @@ import os
 import sys
 
 
+# Params::options (parameters.cpp:805-829)
+OVERWRITES = [("sample.structure.file", "Structure file name"), ("sample.structure.format", "Structure file format"),
+              ("stager.target", "Atom selection producing the signal (must be defined)"),
+              ("stager.dump", "Do/Don't dump the postprocessed coordinates to a file"),
+              ("stager.file", "Name of dump file"), ("stager.format", "Format of dump file"),
+              ("scattering.signal.file", "name of the signal file"),
+              ("limits.computation.threads", "Number of worker threads per process (no counterpart on the GPU path)")]
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="sassena_b200")
     ap.add_argument("--config", default="scatter.xml", help="xml configuration file (reference default: scatter.xml)")
     ap.add_argument("--signal", default=None, help="output file (.h5) or .npy directory (default: scattering.signal.file)")
     ap.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK or 0)")
+    ow = ap.add_argument_group("Overwrite options (applied after the configuration file has been read)")
+    for key, text in OVERWRITES:
+        ow.add_argument("--" + key, dest=key, default=None, metavar="ARG", help=text)
     args = ap.parse_args(argv)
+    overwrites = {key: getattr(args, key) for key, _ in OVERWRITES if getattr(args, key) is not None}
 
     from . import host
     from .api import ScatterContext
@@ -30,7 +45,7 @@ def main(argv=None):
         torch.cuda.set_device(dev)
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
         comm = host.TorchDistCommunicator()
-    job = host.Job(args.config)
+    job = host.Job(args.config, overwrites)
     signal = args.signal
     if signal is None:
         signal = job.signal_file

@@ -1158,8 +1158,54 @@ struct Collector : IResultSink {
 };
 }  // namespace
 
-void Job::load(const std::string &config_file) {
+// Params::overwrite_options (parameters.cpp:838-875).  The reference stores the three file names in `.file` only while every
+// consumer reads `.filepath` (sample.cpp:36-37, data_stager.cpp:92-93, sassena.cpp:256), so there --sample.structure.file,
+// --stager.file and --scattering.signal.file change nothing; here they take effect (the evident intent), resolved like the
+// same element of the configuration file (get_filepath: relative to the configuration's directory, absolute paths kept).
+static void overwrite_options(Config &cfg, const std::vector<std::pair<std::string, std::string>> &overwrites) {
+    auto to_bool = [](const std::string &key, const std::string &v) {
+        if (v == "1" || v == "true" || v == "on" || v == "yes") return true;
+        if (v == "0" || v == "false" || v == "off" || v == "no") return false;
+        throw Error("the argument ('" + v + "') for option '--" + key + "' is invalid");
+    };
+    for (const auto &kv : overwrites) {
+        const std::string &key = kv.first, &val = kv.second;
+        if (key == "sample.structure.file") {
+            cfg.structure_file = val;
+            cfg.structure_filepath = cfg.get_filepath(val);
+        } else if (key == "sample.structure.format") {
+            cfg.structure_format = val;
+        } else if (key == "stager.target") {
+            cfg.stager_target = val;
+        } else if (key == "stager.dump") {
+            cfg.stager.dump = to_bool(key, val);
+        } else if (key == "stager.file") {
+            cfg.stager.file = val;
+            cfg.stager.filepath = cfg.get_filepath(val);
+        } else if (key == "stager.format") {
+            cfg.stager.format = val;
+        } else if (key == "scattering.signal.file") {
+            cfg.signal_file = val;
+            cfg.signal_filepath = cfg.get_filepath(val);
+        } else if (key == "limits.computation.threads") {
+            size_t pos = 0;
+            int n = 0;
+            try {
+                n = std::stoi(val, &pos);
+            } catch (...) {
+                pos = 0;
+            }
+            if (pos != val.size() || val.empty()) throw Error("the argument ('" + val + "') for option '--" + key + "' is invalid");
+            (void)n;  // worker threads per process: no counterpart on the GPU path (accepted like the configuration's element)
+        } else {
+            throw Error("unrecognised option '--" + key + "'");
+        }
+    }
+}
+
+void Job::load(const std::string &config_file, const std::vector<std::pair<std::string, std::string>> &overwrites) {
     cfg.read_xml(config_file);
+    overwrite_options(cfg, overwrites);
     db.read_xml(cfg.database_filepath);
     if (cfg.structure_format != "pdb") throw Error("structure format not supported: " + cfg.structure_format);
     sample.atom_ids = read_pdb_atoms(cfg.structure_filepath, db);

@@ -224,7 +224,11 @@ struct Job {
     Database db;
     LoadedSample sample;
     std::unique_ptr<ScatterFactors> factors;
-    void load(const std::string &config_file);
+    // `overwrites`: the reference's command-line overwrite options (Params::options / overwrite_options,
+    // parameters.cpp:795-875), (key, value) pairs applied after the configuration file has been read and before the
+    // database and the sample are loaded.  Keys: sample.structure.file, sample.structure.format, stager.target,
+    // stager.dump, stager.file, stager.format, scattering.signal.file, limits.computation.threads.
+    void load(const std::string &config_file, const std::vector<std::pair<std::string, std::string>> &overwrites = {});
     // returns the number of q-vectors this rank wrote; with more than one rank every writing rank stores its rows
     // under <signal_dir>/rank_<r>/.  A `signal_dir` ending in ".h5" selects the reference's output: the rows go to
     // "<path>.d/" as above and rank 0 then writes <path> as an HDF5 file in the layout of

@@ -431,6 +431,22 @@ int sass_job_load(const char *config_file, sass_job **out) {
     });
 }
 
+int sass_job_load_overwrite(const char *config_file, const char *const *keys, const char *const *values, size_t n,
+                            sass_job **out) {
+    return guard([&] {
+        if (!config_file || !out || (n && (!keys || !values))) throw Error("sass_job_load_overwrite: NULL argument");
+        std::vector<std::pair<std::string, std::string>> kv;
+        for (size_t i = 0; i < n; i++) {
+            if (!keys[i] || !values[i]) throw Error("sass_job_load_overwrite: NULL key or value");
+            kv.emplace_back(keys[i], values[i]);
+        }
+        std::unique_ptr<sass_job> j(new sass_job);
+        j->job.load(config_file, kv);
+        j->params.params = static_cast<const Params &>(j->job.cfg);
+        *out = j.release();
+    });
+}
+
 void sass_job_free(sass_job *j) { delete j; }
 
 int sass_job_info(const sass_job *j, size_t *natoms, size_t *ntarget, size_t *nframes, size_t *nqvectors) {
@@ -481,6 +497,19 @@ int sass_job_selection(const sass_job *j, const char *name, size_t *ids, size_t 
 
 const sass_params *sass_job_params(const sass_job *j) { return j ? &j->params : nullptr; }
 const char *sass_job_signal_file(const sass_job *j) { return j ? j->job.cfg.signal_filepath.c_str() : nullptr; }
+const char *sass_job_option(const sass_job *j, const char *key) {
+    if (!j || !key) return nullptr;
+    const Config &c = j->job.cfg;
+    const std::string k(key);
+    if (k == "sample.structure.file") return c.structure_filepath.c_str();
+    if (k == "sample.structure.format") return c.structure_format.c_str();
+    if (k == "stager.target") return c.stager_target.c_str();
+    if (k == "stager.dump") return c.stager.dump ? "true" : "false";
+    if (k == "stager.file") return c.stager.filepath.c_str();
+    if (k == "stager.format") return c.stager.format.c_str();
+    if (k == "scattering.signal.file") return c.signal_filepath.c_str();
+    return nullptr;
+}
 
 int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
                  sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap) {

@@ -404,9 +404,15 @@ def run_scatter(params: Params, frames, qvectors, b=None, factors_fn=None, comm:
 class Job:
     """scatter.xml + db.xml + PDB + DCD loaded by the native control plane (csrc/host/control.cpp)."""
 
-    def __init__(self, config_file):
+    def __init__(self, config_file, overwrites=None):
+        """overwrites: {key: value} of the reference's command-line overwrite options (parameters.cpp:795-875), e.g.
+        {"stager.target": "carbons", "scattering.signal.file": "run2.h5"}; applied after the configuration is read."""
         h = C.c_void_p()
-        _ck(_lib().sass_job_load(str(config_file).encode(), C.byref(h)))
+        kv = [(str(k).encode(), (("true" if v else "false") if isinstance(v, bool) else str(v)).encode())
+              for k, v in (overwrites or {}).items()]
+        keys = (C.c_char_p * max(len(kv), 1))(*[k for k, _ in kv])
+        vals = (C.c_char_p * max(len(kv), 1))(*[v for _, v in kv])
+        _ck(_lib().sass_job_load_overwrite(str(config_file).encode(), keys, vals, len(kv), C.byref(h)))
         self.h = h
         n = [C.c_size_t() for _ in range(4)]
         _ck(_lib().sass_job_info(self.h, *[C.byref(x) for x in n]))
@@ -416,6 +422,11 @@ class Job:
     def signal_file(self):
         """scattering.signal.file resolved like the reference does (default: signal.h5 next to the configuration)"""
         return _lib().sass_job_signal_file(self.h).decode()
+
+    def option(self, key):
+        """value in effect of one of the overwritable options (file names resolved); None for any other key"""
+        v = _lib().sass_job_option(self.h, key.encode())
+        return None if v is None else v.decode()
 
     def close(self):
         if getattr(self, "h", None):

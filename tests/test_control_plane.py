@@ -560,3 +560,59 @@ def test_stager_dump_writes_the_staged_coordinates(tmp_path, oracle, kind):
     open(bad, "w").write(open(cfg).read().replace("<format>dcd</format></stager>", "<format>xyz</format></stager>"))
     with pytest.raises(host.HostError, match="Format for coordinate dumping not known"):
         host.Job(bad).run(str(tmp_path / "sig2"), backend=OracleBackend().vtbl)
+
+
+def test_command_line_overwrite_options(tmp_path):
+    """Params::options / overwrite_options (parameters.cpp:795-875): the eight overwrite options are applied after the
+    configuration file has been read.  (In the reference the three FILE options only change `.file`, which nothing reads
+    after the configuration has been parsed; here they take effect, resolved like the configuration's own elements.)"""
+    extra = """<selections>
+      <selection><type>lexical</type><name>carbons</name><expression>carbon</expression></selection>
+      <selection><type>range</type><name>head</name><from>0</from><to>4</to></selection>
+    </selections>"""
+    cfg, xyz, names = make_case(tmp_path, scattering=SCAN, sample_extra=extra, stager="<stager><target>carbons</target></stager>")
+    carbons = [i for i, n in enumerate(names) if NAME2EL[n] == "carbon"]
+    base = host.Job(cfg)
+    assert base.ntarget == len(carbons) and base.signal_file == str(tmp_path / "signal.h5")
+    assert base.option("stager.dump") == "false" and base.option("stager.target") == "carbons"
+    # stager.target, stager.dump / file / format, scattering.signal.file
+    job = host.Job(cfg, {"stager.target": "head", "stager.dump": True, "stager.file": "out/d.dcd", "stager.format": "dcd",
+                         "scattering.signal.file": "run2.h5", "limits.computation.threads": 4})
+    assert job.ntarget == 5 and np.array_equal(job.frames(), xyz[:, :5])
+    assert job.signal_file == str(tmp_path / "run2.h5")
+    assert job.option("stager.dump") == "true" and job.option("stager.file") == str(tmp_path / "out" / "d.dcd")
+    assert job.option("stager.target") == "head" and job.option("limits.computation.threads") is None
+    # sample.structure.file: a second structure with other atom names -> other elements behind the same selection name
+    other = tmp_path / "other.pdb"
+    lines = (tmp_path / "sample.pdb").read_text().splitlines()
+    other.write_text("\n".join(pdb_line(i, "CA") if ln.startswith("ATOM") else ln
+                               for i, ln in enumerate(l for l in lines)) + "\n")
+    job2 = host.Job(cfg, {"sample.structure.file": "other.pdb"})
+    assert job2.ntarget == len(names)  # every atom is a carbon now
+    with pytest.raises(host.HostError, match="structure format not supported"):
+        host.Job(cfg, {"sample.structure.format": "gro"})
+    with pytest.raises(host.HostError, match="unrecognised option '--stager.mode'"):
+        host.Job(cfg, {"stager.mode": "atoms"})
+    with pytest.raises(host.HostError, match="is invalid"):
+        host.Job(cfg, {"stager.dump": "maybe"})
+    with pytest.raises(host.HostError, match="is invalid"):
+        host.Job(cfg, {"limits.computation.threads": "many"})
+    # the command line of the executable carries them
+    from sassena_b200 import cli
+    got = {}
+
+    class _Stop(Exception):
+        pass
+
+    def fake_job(config, overwrites=None):
+        got.update(config=config, overwrites=overwrites)
+        raise _Stop
+
+    orig = host.Job
+    host.Job = fake_job
+    try:
+        with pytest.raises(_Stop):
+            cli.main(["--config", cfg, "--stager.target", "head", "--scattering.signal.file", "x.h5", "--stager.dump", "1"])
+    finally:
+        host.Job = orig
+    assert got == {"config": cfg, "overwrites": {"stager.target": "head", "scattering.signal.file": "x.h5", "stager.dump": "1"}}
