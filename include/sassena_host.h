@@ -213,6 +213,11 @@ const char *sass_job_signal_file(const sass_job *j);
  * sample.structure.format, stager.target, stager.dump ("true" / "false"), stager.file, stager.format, scattering.signal.file;
  * NULL for any other key.  Borrowed, valid until sass_job_free. */
 const char *sass_job_option(const sass_job *j, const char *key);
+/* the reference's `s_stage` executable (src/main/s_stage.cpp:205-232): stages the trajectory of stager.target the way
+ * stager.mode says ("frames" / "atoms") on the ranks of `comm` and, with stager.dump, writes the staged coordinates to
+ * stager.file (data_stager.cpp:131-165, 352-391).  *staged_bytes = what this rank staged. */
+int sass_job_stage(sass_job *j, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend, sgpu_ctx *ctx, size_t *staged_bytes,
+                   char *report, size_t report_cap);
 /* runs every q-vector; comm/backend NULL = single process / the in-library CUDA backend */
 int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
                  sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap);

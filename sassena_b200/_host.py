@@ -128,6 +128,8 @@ SIGNATURES = {
     "sass_job_params": (C.c_void_p, [C.c_void_p]),
     "sass_job_run": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(CommVtbl), C.POINTER(BackendVtbl), C.c_void_p, c_size_p,
                                C.c_char_p, C.c_size_t]),
+    "sass_job_stage": (C.c_int, [C.c_void_p, C.POINTER(CommVtbl), C.POINTER(BackendVtbl), C.c_void_p, c_size_p, C.c_char_p,
+                                 C.c_size_t]),
 }
 
 

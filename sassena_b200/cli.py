@@ -6,7 +6,9 @@ options --sample.structure.file / .format, --stager.target / .dump / .file / .fo
 One process per GPU: run under `python -m torch.distributed.run --nproc-per-node N -m sassena_b200.cli ...` for N GPUs.
 The signal goes to scattering.signal.file (default signal.h5) as an HDF5 file in the reference's layout
 (file_writer_service.cpp:44-171; an existing file is resumed like the reference does), with the per-rank rows kept as
-.npy datasets under <file>.d/.  `--signal DIR` (no .h5 suffix) writes the .npy directory only."""
+.npy datasets under <file>.d/.  `--signal DIR` (no .h5 suffix) writes the .npy directory only.
+`--stage-only` is the reference's second executable, s_stage (src/main/s_stage.cpp): stage and, with stager.dump, write the
+post-processed trajectory."""
 import argparse
 import os
 import sys
@@ -26,6 +28,9 @@ def main(argv=None):
     ap.add_argument("--config", default="scatter.xml", help="xml configuration file (reference default: scatter.xml)")
     ap.add_argument("--signal", default=None, help="output file (.h5) or .npy directory (default: scattering.signal.file)")
     ap.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK or 0)")
+    ap.add_argument("--stage-only", action="store_true",
+                    help="the reference's s_stage executable: stage the trajectory (stager.mode) and, with stager.dump, write "
+                         "the post-processed coordinates to stager.file; no scattering calculation")
     ow = ap.add_argument_group("Overwrite options (applied after the configuration file has been read)")
     for key, text in OVERWRITES:
         ow.add_argument("--" + key, dest=key, default=None, metavar="ARG", help=text)
@@ -51,7 +56,11 @@ def main(argv=None):
         signal = job.signal_file
     ctx = ScatterContext(dev)
     try:
-        written, report = job.run(signal, comm=comm, ctx=ctx)
+        if args.stage_only:
+            _, report = job.stage(comm=comm, ctx=ctx)
+            signal = job.option("stager.file") if job.option("stager.dump") == "true" else "(no dump)"
+        else:
+            written, report = job.run(signal, comm=comm, ctx=ctx)
     finally:
         ctx.close()
     if int(os.environ.get("RANK", "0")) == 0:

@@ -1348,4 +1348,47 @@ size_t Job::run(const std::string &signal_dir_in, std::shared_ptr<ICommunicator>
     return n;
 }
 
+size_t Job::stage(std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx, std::string *report) {
+    if (!factors) throw Error("Job::stage before Job::load");
+    LoadedSample &s = this->sample;
+    Sample smp;
+    smp.NA = s.target.size();
+    smp.NF = s.NF;
+    smp.frames = s.frames.data();
+    Timer timer;
+    timer.start("total");
+    size_t bytes = 0;
+    struct OwnedCtx {  // no context handed in: one on the device this process is bound to, for the duration of the call
+        const SgpuBackend &be;
+        sgpu_ctx *h = nullptr;
+        ~OwnedCtx() {
+            if (h) be.destroy(h);
+        }
+    } own{be};
+    if (!ctx) {
+        if (be.init(-1, &own.h)) throw Error(std::string("sgpu_init: ") + be.last_error(nullptr));
+        ctx = own.h;
+    }
+    if (cfg.stager.mode == "frames") {
+        DataStagerByFrame st(smp, *comm, *comm, timer, be, ctx, cfg);
+        st.stage_block();
+        bytes = DivAssignment(comm->size(), comm->rank(), smp.NF).size() * smp.NA * 3 * sizeof(float);
+    } else if (cfg.stager.mode == "atoms") {
+        DataStagerByAtom st(smp, *comm, *comm, timer, be, ctx, cfg);
+        st.stage();
+        bytes = ModAssignment(comm->size(), comm->rank(), smp.NA).size() * smp.NF * 3 * sizeof(float);
+    } else {  // s_stage.cpp:228-231
+        throw Error("Staging mode not understood stager.mode=" + cfg.stager.mode + "\nUse 'frames' or 'atoms'");
+    }
+    timer.stop("total");
+    if (report) {
+        std::ostringstream r;
+        r << "stager.mode=" << cfg.stager.mode << " target=" << smp.NA << " frames=" << smp.NF << " staged_bytes=" << bytes;
+        if (cfg.stager.dump) r << " dump=" << cfg.stager.filepath;
+        for (const std::string &k : timer.keys()) r << " " << k << "=" << timer.sum(k);
+        *report = r.str();
+    }
+    return bytes;
+}
+
 }  // namespace sassena

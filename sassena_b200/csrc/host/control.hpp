@@ -236,6 +236,11 @@ struct Job {
     // sassena.cpp:270-305).
     size_t run(const std::string &signal_dir, std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx,
                std::string *report);
+    // the `s_stage` executable's flow (src/main/s_stage.cpp:205-232): stage the trajectory of stager.target on the ranks of
+    // `comm` the way stager.mode says ("frames": DataStagerByFrame, every rank its DivAssignment block of frames; "atoms":
+    // DataStagerByAtom, every rank its ModAssignment atoms) and, with stager.dump, write the staged coordinates to
+    // stager.file.  Returns the bytes this rank staged.
+    size_t stage(std::shared_ptr<ICommunicator> comm, const SgpuBackend &be, sgpu_ctx *ctx, std::string *report);
 };
 
 }  // namespace sassena

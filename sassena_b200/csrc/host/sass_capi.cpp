@@ -511,6 +511,24 @@ const char *sass_job_option(const sass_job *j, const char *key) {
     return nullptr;
 }
 
+int sass_job_stage(sass_job *j, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend, sgpu_ctx *ctx, size_t *staged_bytes,
+                   char *report, size_t report_cap) {
+    return guard([&] {
+        if (!j) throw Error("sass_job_stage: NULL argument");
+        std::shared_ptr<ICommunicator> c;
+        if (comm) c = std::make_shared<CallbackCommunicator>(*comm, false);
+        else c = std::make_shared<SingleCommunicator>();
+        const SgpuBackend &be = backend ? *backend : default_backend();
+        std::string rep;
+        size_t n = j->job.stage(c, be, ctx, &rep);
+        if (staged_bytes) *staged_bytes = n;
+        if (report && report_cap) {
+            strncpy(report, rep.c_str(), report_cap - 1);
+            report[report_cap - 1] = 0;
+        }
+    });
+}
+
 int sass_job_run(sass_job *j, const char *signal_dir, const sass_comm_vtbl *comm, const sass_backend_vtbl *backend,
                  sgpu_ctx *ctx, size_t *written, char *report, size_t report_cap) {
     return guard([&] {

@@ -478,6 +478,16 @@ class Job:
         return n.value, rep.value.decode()
 
 
+    def stage(self, comm: TorchDistCommunicator | None = None, backend=None, ctx=None):
+        """The reference's `s_stage` executable (s_stage.cpp:205-232): stages stager.target the way stager.mode says and,
+        with stager.dump, writes the staged coordinates to stager.file.  Returns (bytes staged on this rank, report)."""
+        n = C.c_size_t()
+        rep = C.create_string_buffer(1024)
+        _ck(_lib().sass_job_stage(self.h, C.byref(comm.vtbl) if comm is not None else None,
+                                  C.byref(backend) if backend is not None else None, _ctxp(ctx), C.byref(n), rep, len(rep)))
+        return n.value, rep.value.decode()
+
+
 H5_DATASET_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_int, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                             C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t)
 

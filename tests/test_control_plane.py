@@ -616,3 +616,32 @@ def test_command_line_overwrite_options(tmp_path):
     finally:
         host.Job = orig
     assert got == {"config": cfg, "overwrites": {"stager.target": "head", "scattering.signal.file": "x.h5", "stager.dump": "1"}}
+
+
+@pytest.mark.parametrize("mode", ["frames", "atoms"])
+def test_stage_only_is_the_reference_s_stage_executable(tmp_path, oracle, mode):
+    """s_stage (src/main/s_stage.cpp:205-232): stage the trajectory of stager.target by stager.mode and, with stager.dump,
+    write the post-processed coordinates -- no scattering calculation, no signal file"""
+    from oracle_backend import OracleBackend
+    cfg, xyz, names = make_case(
+        tmp_path, NA=10, NF=6,
+        sample_extra="<selections><selection><type>range</type><name>part</name><from>1</from><to>7</to></selection></selections>",
+        stager=f"<stager><target>part</target><mode>{mode}</mode><file>staged.dcd</file></stager>", scattering=SCAN)
+    job = host.Job(cfg, {"stager.dump": True})
+    fr = job.frames()
+    nbytes, report = job.stage(backend=OracleBackend().vtbl)
+    assert nbytes == fr.size * 4 and f"stager.mode={mode}" in report and "staged.dcd" in report
+    got = host.DCDFile(str(tmp_path / "staged.dcd")).read()
+    if mode == "frames":
+        assert np.array_equal(got, fr)
+    else:
+        assert np.array_equal(got, fr.transpose(1, 0, 2))
+    assert not os.path.exists(tmp_path / "signal.h5")
+    # without the dump nothing is written; an unknown mode is the reference's error
+    os.remove(tmp_path / "staged.dcd")
+    host.Job(cfg).stage(backend=OracleBackend().vtbl)
+    assert not os.path.exists(tmp_path / "staged.dcd")
+    bad = str(tmp_path / "bad.xml")
+    open(bad, "w").write(open(cfg).read().replace(f"<mode>{mode}</mode>", "<mode>both</mode>"))
+    with pytest.raises(host.HostError, match="Staging mode not understood stager.mode=both"):
+        host.Job(bad).stage(backend=OracleBackend().vtbl)
