@@ -22,8 +22,11 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     be = OracleBackend()
     comm = host.TorchDistCommunicator(None, device_memory=False)
-    if case.startswith("job"):  # control plane: argv[3] = scatter.xml, argv[4] = signal directory
-        written, report = host.Job(sys.argv[3]).run(sys.argv[4], comm=comm, backend=be.vtbl)
+    if case.startswith("job") or case == "stage":  # control plane: argv[3] = scatter.xml, argv[4] = signal directory
+        if case == "stage":  # the s_stage flow: stage by stager.mode, dump, no scattering
+            written, report = host.Job(sys.argv[3]).stage(comm=comm, backend=be.vtbl)
+        else:
+            written, report = host.Job(sys.argv[3]).run(sys.argv[4], comm=comm, backend=be.vtbl)
         gathered = [None] * world
         dist.all_gather_object(gathered, (rank, written, report))
         if rank == 0:

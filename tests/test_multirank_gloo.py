@@ -168,3 +168,18 @@ def test_multirank_stager_dump(oracle, tmp_path, world, kind):
         assert np.array_equal(got, xyz)
     else:
         assert np.array_equal(got, xyz.transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("world,mode", [(2, "frames"), (3, "atoms")])
+def test_multirank_stage_only(oracle, tmp_path, world, mode):
+    """the s_stage flow (s_stage.cpp:205-232) on several ranks: every rank stages and dumps its DivAssignment block of frames
+    (stager.mode = frames) or its ModAssignment atoms (atoms); the bytes staged add up to the whole trajectory"""
+    from test_control_plane import SCAN, make_case
+    cfg, xyz, names = make_case(tmp_path, NA=11, NF=9, scattering=SCAN,
+                                stager=f"<stager><dump>true</dump><file>staged.dcd</file><mode>{mode}</mode></stager>")
+    gathered = _run(world, "stage", tmp_path, extra=(cfg, str(tmp_path / "unused")))
+    assert sum(n for _, n, _ in gathered) == xyz.size * 4
+    assert all(f"stager.mode={mode}" in rep for _, _, rep in gathered)
+    got = host.DCDFile(str(tmp_path / "staged.dcd")).read()
+    assert np.array_equal(got, xyz if mode == "frames" else xyz.transpose(1, 0, 2))
+    assert not os.path.exists(tmp_path / "unused")
